@@ -1,0 +1,272 @@
+"""The CoMatch unlabeled head (reference ``code/comatch.py:162-220``, inline in
+``CoMatch.train_one``) as a stateful device-side object.
+
+State mirrors ``code/comatch.py:90-96``: the memory bank ``queue_feats [K, D]`` /
+``queue_probs [K, C]``, the write pointer ``queue_ptr`` and the distribution-
+alignment history (``prob_list``; kept on the device as a ``[window, C]`` ring
+so a step has no host synchronisation).
+
+One step is five launches of ``libb200ssl.so`` (+ one in backward):
+
+====  ===============================  ==========================================
+K2    ``b200ssl_comatch_da``           softmax column-mean -> DA history -> prob_avg  (:167-173)
+K3    ``b200ssl_bank_smooth_partial``  rowsum / numer of exp(F_w Q_f^T / tau) Q_p     (:180-181)
+K4/7  ``b200ssl_comatch_finalize``     DA divide, alpha-mix, max/mask, focal soft-CE + grad (:174-176,182-185,216-220)
+K5    ``b200ssl_bank_enqueue``         ring write of [feats_u_w; feats_x], [probs_orig; onehot] (:187-196)
+K6    ``b200ssl_contrast_fwd`` / ``_bwd``   graph-contrastive loss (:199-213) and its gradient
+====  ===============================  ==========================================
+
+With a sharded bank (``process_group`` given) K3/K5 run against the local shard
+and NCCL collectives combine them (``bank.py``).
+"""
+from __future__ import annotations
+
+from typing import List
+
+import numpy as np
+import torch
+
+from . import _native as N
+from .bank import ShardGeometry, all_gather_rows, reduce_scatter_rows
+
+__all__ = ["CoMatchHead"]
+
+
+class _HeadFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, head, logits_u_w, logits_u_s0, feats_u_w, feats_u_s0, feats_u_s1, feats_x, targets_x):
+        f0, f1 = feats_u_s0.detach().contiguous(), feats_u_s1.detach().contiguous()
+        out = head._step(logits_u_w.detach(), logits_u_s0.detach(), feats_u_w.detach(), f0, f1,
+                         feats_x.detach(), targets_x)
+        ctx.head = head
+        ctx.save_for_backward(out["grad_s0"], f0, f1, out["probs"], out["stats"])
+        ctx.done = False
+        aux = (out["mask"], out["lbs"], out["scores"], out["probs"])
+        ctx.mark_non_differentiable(*aux)
+        sc = out["scalars"]
+        return (sc[0], sc[2], sc[1]) + aux
+
+    @staticmethod
+    def backward(ctx, g_u, g_c, g_mm, *unused):
+        if ctx.done:
+            raise RuntimeError("CoMatchHead: backward through the fused head twice (the stashed gradient is consumed)")
+        ctx.done = True
+        grad_s0, f0, f1, probs, stats = ctx.saved_tensors
+        head = ctx.head
+        gs0 = gf0 = gf1 = None
+        if ctx.needs_input_grad[2]:
+            gs0 = torch.zeros_like(grad_s0) if g_u is None else head._k_scale(grad_s0, g_u)
+        if ctx.needs_input_grad[4] or ctx.needs_input_grad[5]:
+            if g_c is None:
+                gf0, gf1 = torch.zeros_like(f0), torch.zeros_like(f1)
+            else:
+                gf0, gf1 = head._k_contrast_bwd(f0, f1, probs, stats, g_c)
+        return None, None, gs0, None, gf0, gf1, None, None
+
+
+class CoMatchHead:
+    """Device-resident CoMatch head state + fused step.
+
+    Parameters mirror the attributes of the reference trainer
+    (``comatch.py:29-39, 90-96``): ``alpha=0.9``, ``temperature=0.2``,
+    ``contrast_th=0.8``, ``gamma=2``; ``queue_size`` = K (global rows).
+
+    ``enqueue_mode``: ``'reference'`` keeps the guard ``n == queue_size`` of
+    ``comatch.py:192`` (quirk Q1: with ``queue_batch=5`` the bank is never
+    written); ``'always'`` is the ring write without the guard (upstream CoMatch).
+    """
+
+    def __init__(self, num_classes: int, low_dim: int, queue_size: int, thr: float, *, alpha: float = 0.9,
+                 temperature: float = 0.2, contrast_th: float = 0.8, gamma: float = 2.0, da_window: int = 32,
+                 enqueue_mode: str = "reference", smoothing: bool = True, device="cuda",
+                 dtype: torch.dtype = torch.float32, process_group=None):
+        if enqueue_mode not in ("reference", "always"):
+            raise ValueError(enqueue_mode)
+        self.num_classes, self.low_dim, self.queue_size = int(num_classes), int(low_dim), int(queue_size)
+        self.thr, self.alpha, self.temperature = float(thr), float(alpha), float(temperature)
+        self.contrast_th, self.gamma, self.da_window = float(contrast_th), float(gamma), int(da_window)
+        self.enqueue_mode, self.smoothing = enqueue_mode, bool(smoothing)
+        self.device = torch.device(device)
+        self._check_backend()
+        self.pg = process_group
+        world, rank = 1, 0
+        if process_group is not None:
+            import torch.distributed as dist
+            world, rank = dist.get_world_size(process_group), dist.get_rank(process_group)
+        self.geom = ShardGeometry(self.queue_size, world, rank)
+        self._alloc_bank(dtype)
+        self.queue_ptr = 0
+        self.da_ring = torch.zeros(self.da_window, self.num_classes, dtype=torch.float32, device=self.device)
+        self.da_state = torch.zeros(2, dtype=torch.int32, device=self.device)   # count, head
+        self.prob_avg = torch.empty(self.num_classes, dtype=torch.float32, device=self.device)
+        self._pristine = True
+        self.last = {}
+
+    def _check_backend(self) -> None:
+        if self.device.type != "cuda":
+            raise RuntimeError("CoMatchHead needs a CUDA device: the head is CUDA-only, there is no CPU path")
+        N.lib()
+
+    def _alloc_bank(self, dtype) -> None:
+        self.dtype = dtype
+        self.queue_feats = torch.zeros(self.geom.shard_rows, self.low_dim, dtype=dtype, device=self.device)
+        self.queue_probs = torch.zeros(self.geom.shard_rows, self.num_classes, dtype=dtype, device=self.device)
+
+    # ---- reference-visible state ------------------------------------------------
+    @property
+    def prob_list(self) -> List[torch.Tensor]:
+        """The DA history as the reference keeps it (``comatch.py:96``): oldest first."""
+        count, head = (int(v) for v in self.da_state.tolist())
+        return [self.da_ring[(head - count + a) % self.da_window].clone() for a in range(count)]
+
+    @prob_list.setter
+    def prob_list(self, entries) -> None:
+        entries = list(entries)[-self.da_window:]
+        self.da_ring.zero_()
+        for i, e in enumerate(entries):
+            self.da_ring[i].copy_(e.to(self.device, torch.float32))
+        self.da_state.copy_(torch.tensor([len(entries), len(entries) % self.da_window], dtype=torch.int32))
+
+    def state_dict(self) -> dict:
+        return {"queue_feats": self.queue_feats, "queue_probs": self.queue_probs, "queue_ptr": self.queue_ptr,
+                "da_ring": self.da_ring, "da_state": self.da_state}
+
+    def load_state_dict(self, sd: dict) -> None:
+        self._alloc_bank(sd["queue_feats"].dtype)
+        self.queue_feats.copy_(sd["queue_feats"])
+        self.queue_probs.copy_(sd["queue_probs"])
+        self.queue_ptr = int(sd["queue_ptr"])
+        self.da_ring.copy_(sd["da_ring"])
+        self.da_state.copy_(sd["da_state"])
+        self._pristine = False
+
+    # ---- the step -----------------------------------------------------------------
+    def __call__(self, logits_u_w, logits_u_s0, feats_u_w, feats_u_s0, feats_u_s1, feats_x, targets_x):
+        """Returns ``(loss_u, loss_contrast, mask_mean, mask, lbs_u_guess, scores, probs)``;
+        the two losses carry grad w.r.t. ``logits_u_s0`` / ``feats_u_s0`` / ``feats_u_s1``."""
+        return _HeadFn.apply(self, logits_u_w, logits_u_s0, feats_u_w, feats_u_s0, feats_u_s1, feats_x, targets_x)
+
+    def _step(self, lw, ls0, fw, fs0, fs1, fx, tx):
+        lw, ls0, fw, fx = (t.contiguous() for t in (lw, ls0, fw, fx))
+        tx = tx.to(torch.int64).contiguous()
+        rows, C = lw.shape
+        D, n_x = fw.shape[1], fx.shape[0]
+        if C != self.num_classes or D != self.low_dim:
+            raise ValueError(f"head built for C={self.num_classes}, D={self.low_dim}; got C={C}, D={D}")
+        if not (lw.dtype == ls0.dtype == fw.dtype == fs0.dtype == fs1.dtype == fx.dtype):
+            raise TypeError("all logits / embeddings of one step must share a dtype")
+        if lw.dtype != self.dtype:
+            if not self._pristine:
+                raise TypeError(f"bank holds {self.dtype} rows but the step is {lw.dtype}")
+            self._alloc_bank(lw.dtype)          # still all-zero: re-create in the step's dtype
+        R, geom = self.geom.world_size, self.geom
+
+        self._k_da(lw)                                                   # K2 (rank-local history)
+        # queries of every rank (the enqueue block contains them): [R*n, D], rank-major
+        block_f = torch.cat([fw, fx], dim=0) if R > 1 else None
+        gathered_f = all_gather_rows(block_f, self.pg) if R > 1 else None
+        rowsum = numer = None
+        if self.smoothing:                                               # K3, bank as of *before* this step's enqueue
+            if R == 1:
+                rowsum, numer = self._k_smooth(fw)
+            else:
+                n = rows + n_x
+                queries = gathered_f.view(R, n, D)[:, :rows, :].reshape(R * rows, D)
+                rs_all, nm_all = self._k_smooth(queries)
+                rowsum = reduce_scatter_rows(rs_all, self.pg)
+                numer = reduce_scatter_rows(nm_all, self.pg)
+        out = self._k_finalize(lw, ls0, rowsum, numer)                   # K2b + K4 + K7
+        n = rows + n_x
+        if geom.should_enqueue(n, self.enqueue_mode):                    # K5
+            if R == 1:
+                self._k_enqueue(fw, fx, out["probs_orig"], tx, 0)
+            else:
+                po_all = all_gather_rows(out["probs_orig"], self.pg).view(R, rows, C)
+                tx_all = all_gather_rows(tx, self.pg).view(R, n_x)
+                gf = gathered_f.view(R, n, D)
+                for r in range(R):                                       # block r sits at ptr + r*n
+                    self._k_enqueue(gf[r, :rows], gf[r, rows:], po_all[r], tx_all[r], r * n)
+            self.queue_ptr = geom.next_ptr(self.queue_ptr, n)
+            self._pristine = False
+        stats, loss_c = self._k_contrast_fwd(fs0, fs1, out["probs"], out["scalars"])  # K6
+        self.last = {"probs_orig": out["probs_orig"], "rowsum": rowsum, "numer": numer}
+        out["stats"] = stats
+        return out
+
+    # ---- kernel wrappers (one C-ABI call each) --------------------------------------
+    def _ws(self, rows):
+        return N.workspace(self.device, rows, self.num_classes, self.geom.shard_rows)
+
+    def _k_da(self, lw) -> None:
+        ws, wsb = self._ws(lw.shape[0])
+        N.check(N.lib().b200ssl_comatch_da(lw.data_ptr(), lw.shape[0], lw.shape[1], N.dtype_enum(lw),
+                                           self.da_ring.data_ptr(), self.da_state.data_ptr(), self.da_window,
+                                           self.prob_avg.data_ptr(), None, ws, wsb, N.stream_ptr(self.device)),
+                "comatch_da")
+
+    def _k_smooth(self, queries):
+        rows, D = queries.shape
+        C = self.num_classes
+        queries = queries.contiguous()
+        rowsum = torch.empty(rows, dtype=torch.float32, device=self.device)
+        numer = torch.empty(rows, C, dtype=torch.float32, device=self.device)
+        ws, wsb = self._ws(rows)
+        N.check(N.lib().b200ssl_bank_smooth_partial(queries.data_ptr(), self.queue_feats.data_ptr(),
+                                                    self.queue_probs.data_ptr(), rows, self.geom.shard_rows, D, C,
+                                                    N.dtype_enum(queries), self.temperature, rowsum.data_ptr(),
+                                                    numer.data_ptr(), ws, wsb, N.stream_ptr(self.device)),
+                "bank_smooth_partial")
+        return rowsum, numer
+
+    def _k_finalize(self, lw, ls0, rowsum, numer) -> dict:
+        rows, C = lw.shape
+        f32 = dict(dtype=torch.float32, device=self.device)
+        out = {"probs": torch.empty(rows, C, **f32), "probs_orig": torch.empty(rows, C, **f32),
+               "scores": torch.empty(rows, **f32), "mask": torch.empty(rows, **f32),
+               "lbs": torch.empty(rows, dtype=torch.int64, device=self.device),
+               "grad_s0": torch.empty_like(ls0),
+               "scalars": torch.empty(4, **f32)}      # loss_u, mask_mean, loss_contrast, -
+        ws, wsb = self._ws(rows)
+        N.check(N.lib().b200ssl_comatch_finalize(
+            lw.data_ptr(), ls0.data_ptr(), self.prob_avg.data_ptr(), N.ptr(rowsum), N.ptr(numer), rows, C,
+            N.dtype_enum(lw), float(np.float32(self.alpha)), float(np.float32(1.0 - self.alpha)), self.thr, self.gamma,
+            out["probs"].data_ptr(), out["probs_orig"].data_ptr(), out["scores"].data_ptr(), out["lbs"].data_ptr(),
+            out["mask"].data_ptr(), out["grad_s0"].data_ptr(), out["scalars"].data_ptr(), ws, wsb,
+            N.stream_ptr(self.device)), "comatch_finalize")
+        return out
+
+    def _k_enqueue(self, fw, fx, probs_orig, tx, block_offset: int) -> None:
+        g = self.geom
+        fw, fx, probs_orig, tx = (t.contiguous() for t in (fw, fx, probs_orig, tx))
+        N.check(N.lib().b200ssl_bank_enqueue(self.queue_feats.data_ptr(), self.queue_probs.data_ptr(), fw.data_ptr(),
+                                             fx.data_ptr(), probs_orig.data_ptr(), tx.data_ptr(), fw.shape[0],
+                                             fx.shape[0], self.low_dim, self.num_classes, N.dtype_enum(fw),
+                                             self.queue_ptr, block_offset, g.queue_size, g.shard_begin, g.shard_rows,
+                                             N.stream_ptr(self.device)), "bank_enqueue")
+
+    def _k_contrast_fwd(self, fs0, fs1, probs, scalars):
+        rows, D = fs0.shape
+        stats = torch.empty(3, rows, dtype=torch.float32, device=self.device)
+        ws, wsb = self._ws(rows)
+        N.check(N.lib().b200ssl_contrast_fwd(fs0.data_ptr(), fs1.data_ptr(), probs.data_ptr(), rows, D,
+                                             self.num_classes, N.dtype_enum(fs0), self.temperature, self.contrast_th,
+                                             stats.data_ptr(), scalars[2:].data_ptr(), ws, wsb,
+                                             N.stream_ptr(self.device)), "contrast_fwd")
+        return stats, scalars[2]
+
+    def _k_contrast_bwd(self, f0, f1, probs, stats, g_c):
+        g = g_c.detach().to(torch.float32).reshape(1).contiguous()
+        gf0, gf1 = torch.empty_like(f0), torch.empty_like(f1)
+        rows, D = f0.shape
+        ws, wsb = self._ws(rows)
+        N.check(N.lib().b200ssl_contrast_bwd(f0.data_ptr(), f1.data_ptr(), probs.data_ptr(), stats.data_ptr(), rows,
+                                             D, self.num_classes, N.dtype_enum(f0), self.temperature, self.contrast_th,
+                                             g.data_ptr(), gf0.data_ptr(), gf1.data_ptr(), ws, wsb,
+                                             N.stream_ptr(self.device)), "contrast_bwd")
+        return gf0, gf1
+
+    def _k_scale(self, grad, g):
+        g = g.detach().to(torch.float32).reshape(1).contiguous()
+        N.check(N.lib().b200ssl_scale_inplace(grad.data_ptr(), grad.numel(), N.dtype_enum(grad), g.data_ptr(),
+                                              N.stream_ptr(self.device)), "scale_inplace")
+        return grad

@@ -1,0 +1,204 @@
+// Shared device/host helpers for libb200ssl (sm_100a only).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "b200ssl.h"
+
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
+#error "libb200ssl is written for sm_100a (B200) only"
+#endif
+
+namespace b200ssl {
+
+// ---- host side error plumbing (api.cu) -------------------------------------
+int fail(int code, const char* fmt, ...);
+int check_launch(const char* what);
+inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+
+constexpr int kNumSMs = 148;  // B200
+
+// Workspace layout (caller zero-fills it once): [0,256) ticket counters of the
+// row kernels, [256, 256+64K) per-row-tile tickets of the similarity kernels,
+// then float partials.  Tickets reset themselves, partials are scratch.
+constexpr size_t kWsTicketBytes = 256;
+constexpr size_t kWsTicket2Bytes = 64 * 1024;
+constexpr size_t kWsHeaderBytes = kWsTicketBytes + kWsTicket2Bytes;
+constexpr int kMaxRowCtas = 4 * kNumSMs;
+int smooth_nsplit(long long rows, long long bank_rows, int* tiles_per_split);
+
+// ---- dtype helpers ---------------------------------------------------------
+template <typename T> __device__ __forceinline__ float to_f32(T v);
+template <> __device__ __forceinline__ float to_f32<float>(float v) { return v; }
+template <> __device__ __forceinline__ float to_f32<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
+template <typename T> __device__ __forceinline__ T from_f32(float v);
+template <> __device__ __forceinline__ float from_f32<float>(float v) { return v; }
+template <> __device__ __forceinline__ __nv_bfloat16 from_f32<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+
+template <typename T> struct Vec16;  // 16-byte vector of T
+template <> struct Vec16<float> { static constexpr int N = 4; };
+template <> struct Vec16<__nv_bfloat16> { static constexpr int N = 8; };
+template <> struct Vec16<__half> { static constexpr int N = 8; };
+
+__device__ __forceinline__ uint4 ldg128(const void* p) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void stg128(void* p, const uint4& v) {
+  asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};"
+               :: "l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+__device__ __forceinline__ void unpack16(const uint4& v, float (&out)[4], float) {
+  out[0] = __uint_as_float(v.x); out[1] = __uint_as_float(v.y);
+  out[2] = __uint_as_float(v.z); out[3] = __uint_as_float(v.w);
+}
+__device__ __forceinline__ void unpack16(const uint4& v, float (&out)[8], __nv_bfloat16) {
+  const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    out[2 * i] = __uint_as_float(w[i] << 16);
+    out[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+  }
+}
+__device__ __forceinline__ uint4 pack16(const float (&in)[4], float) {
+  return make_uint4(__float_as_uint(in[0]), __float_as_uint(in[1]), __float_as_uint(in[2]), __float_as_uint(in[3]));
+}
+__device__ __forceinline__ uint4 pack16(const float (&in)[8], __nv_bfloat16) {
+  uint32_t w[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(in[2 * i], in[2 * i + 1]);
+    w[i] = *reinterpret_cast<uint32_t*>(&h);
+  }
+  return make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+__device__ __forceinline__ void unpack16(const uint4& v, float (&out)[8], __half) {
+  const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const __half2 h = *reinterpret_cast<const __half2*>(&w[i]);
+    out[2 * i] = __low2float(h);
+    out[2 * i + 1] = __high2float(h);
+  }
+}
+__device__ __forceinline__ uint4 pack16(const float (&in)[8], __half) {
+  uint32_t w[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    __half2 h = __floats2half2_rn(in[2 * i], in[2 * i + 1]);
+    w[i] = *reinterpret_cast<uint32_t*>(&h);
+  }
+  return make_uint4(w[0], w[1], w[2], w[3]);
+}
+// Copy `count` contiguous elements global -> shared (as fp32) with 128-bit
+// loads when the global address is 16-byte aligned; all threads of the CTA.
+template <typename T>
+__device__ __forceinline__ void tile_g2s(const T* __restrict__ g, float* __restrict__ s, int count) {
+  constexpr int N = Vec16<T>::N;
+  const int tid = threadIdx.x, nt = blockDim.x;
+  if ((reinterpret_cast<uintptr_t>(g) & 15u) == 0) {
+    const int nvec = count / N;
+    for (int v = tid; v < nvec; v += nt) {
+      float f[N];
+      unpack16(ldg128(g + (size_t)v * N), f, T());
+#pragma unroll
+      for (int i = 0; i < N; ++i) s[v * N + i] = f[i];
+    }
+    for (int i = nvec * N + tid; i < count; i += nt) s[i] = to_f32<T>(g[i]);
+  } else {
+    for (int i = tid; i < count; i += nt) s[i] = to_f32<T>(g[i]);
+  }
+}
+// shared (fp32) -> global, same vectorisation rule.
+template <typename T>
+__device__ __forceinline__ void tile_s2g(const float* __restrict__ s, T* __restrict__ g, int count) {
+  constexpr int N = Vec16<T>::N;
+  const int tid = threadIdx.x, nt = blockDim.x;
+  if ((reinterpret_cast<uintptr_t>(g) & 15u) == 0) {
+    const int nvec = count / N;
+    for (int v = tid; v < nvec; v += nt) {
+      float f[N];
+#pragma unroll
+      for (int i = 0; i < N; ++i) f[i] = s[v * N + i];
+      stg128(g + (size_t)v * N, pack16(f, T()));
+    }
+    for (int i = nvec * N + tid; i < count; i += nt) g[i] = from_f32<T>(s[i]);
+  } else {
+    for (int i = tid; i < count; i += nt) g[i] = from_f32<T>(s[i]);
+  }
+}
+
+// ---- sub-warp (LPR lanes per row) butterfly reductions -----------------------
+template <int LPR> __device__ __forceinline__ float group_max(float v) {
+#pragma unroll
+  for (int o = LPR / 2; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+template <int LPR> __device__ __forceinline__ float group_sum(float v) {
+#pragma unroll
+  for (int o = LPR / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+// (value, index) arg-max with first-index tie-break (torch.max semantics).
+template <int LPR> __device__ __forceinline__ void group_argmax(float& v, int& i) {
+#pragma unroll
+  for (int o = LPR / 2; o > 0; o >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, v, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, i, o);
+    if (ov > v || (ov == v && oi < i)) { v = ov; i = oi; }
+  }
+}
+__device__ __forceinline__ float warp_sum(float v) { return group_sum<32>(v); }
+
+// Deterministic grid-wide sum of NV floats per CTA: every CTA stores its
+// partials, takes a ticket; the last CTA to arrive adds all partials in a
+// fixed order and returns true with the totals in `total` (valid in thread 0).
+// The ticket resets itself, so the workspace stays reusable.
+template <int NV>
+__device__ __forceinline__ bool grid_reduce_last(const float (&mine)[NV], float* partials, unsigned* ticket,
+                                                 float (&total)[NV]) {
+  __shared__ bool s_last;
+  __shared__ float s_red[NV][32];
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int v = 0; v < NV; ++v) partials[(size_t)blockIdx.x * NV + v] = mine[v];
+    __threadfence();
+    const unsigned t = atomicAdd(ticket, 1u);
+    s_last = (t == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!s_last) return false;
+  __threadfence();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+  float acc[NV];
+#pragma unroll
+  for (int v = 0; v < NV; ++v) acc[v] = 0.f;
+  for (unsigned b = threadIdx.x; b < gridDim.x; b += blockDim.x) {
+#pragma unroll
+    for (int v = 0; v < NV; ++v) acc[v] += __ldcg(&partials[(size_t)b * NV + v]);
+  }
+#pragma unroll
+  for (int v = 0; v < NV; ++v) {
+    acc[v] = warp_sum(acc[v]);
+    if (lane == 0) s_red[v][warp] = acc[v];
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+      float t = 0.f;
+      for (int w = 0; w < nwarp; ++w) t += s_red[v][w];
+      total[v] = t;
+    }
+    *ticket = 0u;
+  }
+  return true;
+}
+
+}  // namespace b200ssl

@@ -1,0 +1,665 @@
+// Row kernels of the SSL head: every one of them reads [rows, classes] logits
+// with 128-bit loads into shared memory, gives LPR lanes to a row, reduces with
+// warp shuffles and emits forward scalars AND the backward gradient in the same
+// launch.  HBM-bound by construction (each input read once, each output written
+// once); at the reference's sizes (rows <= 14336, 23 classes) they are launch-
+// latency floored -- see DESIGN.md.
+//
+//   K1  fixmatch_head_kernel   code/loss.py:126-164 (+ F.cross_entropy :119, bwd)
+//   f2  labeled_ce_kernel      code/loss.py:103-119, 308-364 (+ bwd)
+//   K2  comatch_da_kernel      code/comatch.py:167-173
+//   K4/K7 comatch_finalize_kernel  code/comatch.py:174-176,182,184-185,216-220 (+ bwd)
+#include <math.h>
+
+#include "common.cuh"
+
+namespace b200ssl {
+namespace {
+
+constexpr int kRowThreads = 128;
+constexpr int kRowWarps = kRowThreads / 32;
+
+template <int LPR, int EPL>
+struct RowCfg {
+  static constexpr int kRowsPerWarp = 32 / LPR;
+  static constexpr int kRowsPerTile = kRowWarps * kRowsPerWarp;
+};
+
+// ---- per-row primitives (LPR lanes cooperate, lane gl owns c = gl + k*LPR) ----
+template <int LPR, int EPL>
+__device__ __forceinline__ void row_load(const float* srow, int C, int gl, bool valid, float (&x)[EPL]) {
+#pragma unroll
+  for (int k = 0; k < EPL; ++k) {
+    const int c = gl + k * LPR;
+    x[k] = (valid && c < C) ? srow[c] : -INFINITY;
+  }
+}
+
+// e[k] = expf(x[k]-max) (0 for padding), returns max and sum over the row.
+template <int LPR, int EPL>
+__device__ __forceinline__ void row_softmax_stats(const float (&x)[EPL], float (&e)[EPL], float& mx, float& sum) {
+  float m = -INFINITY;
+#pragma unroll
+  for (int k = 0; k < EPL; ++k) m = fmaxf(m, x[k]);
+  m = group_max<LPR>(m);
+  if (m == -INFINITY) m = 0.f;  // fully padded (invalid) row
+  float s = 0.f;
+#pragma unroll
+  for (int k = 0; k < EPL; ++k) {
+    e[k] = (x[k] == -INFINITY) ? 0.f : expf(x[k] - m);
+    s += e[k];
+  }
+  sum = group_sum<LPR>(s);
+  mx = m;
+}
+
+template <int LPR, int EPL>
+__device__ __forceinline__ void row_argmax(const float (&p)[EPL], int C, int gl, float& best, int& besti) {
+  float bv = -INFINITY;
+  int bi = 0x7fffffff;
+#pragma unroll
+  for (int k = 0; k < EPL; ++k) {
+    const int c = gl + k * LPR;
+    if (c < C && p[k] > bv) { bv = p[k]; bi = c; }  // ascending c: strict > keeps the first
+  }
+  group_argmax<LPR>(bv, bi);
+  best = bv;
+  besti = bi;
+}
+
+// value of column `col` of a row held in registers (exact: one lane contributes).
+// Used instead of re-reading shared memory that sibling lanes may already be
+// overwriting with gradients.
+template <int LPR, int EPL>
+__device__ __forceinline__ float row_pick(const float (&x)[EPL], int gl, int col) {
+  float v = 0.f;
+#pragma unroll
+  for (int k = 0; k < EPL; ++k)
+    if (gl + k * LPR == col) v = x[k];
+  return group_sum<LPR>(v);
+}
+
+// block-level sum of NV per-thread values -> thread 0
+template <int NV>
+__device__ __forceinline__ void block_sum(float (&v)[NV]) {
+  __shared__ float s_part[NV][kRowWarps];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const float t = warp_sum(v[i]);
+    if (lane == 0) s_part[i][warp] = t;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      float t = 0.f;
+      for (int w = 0; w < kRowWarps; ++w) t += s_part[i][w];
+      v[i] = t;
+    }
+  }
+}
+
+// ============================================================ K1 ============
+struct HeadParams {
+  const void* w; const void* s; const void* s2;
+  void* gs; void* gs2;
+  long long rows; int C;
+  float thr, inv_T; int hard;
+  float* out; long long* idx; float* mask;
+  float* partials; unsigned* ticket;
+};
+
+template <typename T, int LPR, int EPL>
+__global__ void __launch_bounds__(kRowThreads) fixmatch_head_kernel(const HeadParams p) {
+  using Cfg = RowCfg<LPR, EPL>;
+  constexpr int ROWS = Cfg::kRowsPerTile;
+  extern __shared__ float smem[];
+  const int C = p.C;
+  float* sw = smem;
+  float* ss = sw + ROWS * C;
+  float* ss2 = ss + ROWS * C;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int gl = lane % LPR, rw = lane / LPR;
+  const bool dual = p.s2 != nullptr;
+  const float inv_rows = 1.0f / (float)p.rows;
+  const long long ntiles = (p.rows + ROWS - 1) / ROWS;
+  float acc[3] = {0.f, 0.f, 0.f};  // loss, mask count, loss2
+
+  for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const long long row0 = tile * ROWS;
+    const int nrows = (int)min((long long)ROWS, p.rows - row0);
+    const int cnt = nrows * C;
+    tile_g2s(static_cast<const T*>(p.w) + row0 * C, sw, cnt);
+    tile_g2s(static_cast<const T*>(p.s) + row0 * C, ss, cnt);
+    if (dual) tile_g2s(static_cast<const T*>(p.s2) + row0 * C, ss2, cnt);
+    __syncthreads();
+
+    const int r = warp * Cfg::kRowsPerWarp + rw;
+    const bool valid = r < nrows;
+    float x[EPL], e[EPL], pw[EPL];
+    float mx, sum;
+    // ---- weak view: pseudo label (loss.py:151-154) ----
+    row_load<LPR, EPL>(sw + r * C, C, gl, valid, x);
+    row_softmax_stats<LPR, EPL>(x, e, mx, sum);
+#pragma unroll
+    for (int k = 0; k < EPL; ++k) pw[k] = __fdiv_rn(e[k], sum);
+    float pmax; int idx;
+    row_argmax<LPR, EPL>(pw, C, gl, pmax, idx);
+    const float m = (valid && pmax >= p.thr) ? 1.f : 0.f;
+    float tsum = 1.f;
+    if (!p.hard) {  // soft targets softmax(w/T) (extension, quirk Q4)
+#pragma unroll
+      for (int k = 0; k < EPL; ++k) x[k] = x[k] * p.inv_T;
+      row_softmax_stats<LPR, EPL>(x, e, mx, sum);
+      float t = 0.f;
+#pragma unroll
+      for (int k = 0; k < EPL; ++k) { pw[k] = __fdiv_rn(e[k], sum); t += pw[k]; }
+      tsum = group_sum<LPR>(t);
+    }
+    if (valid && gl == 0) {
+      if (p.idx) p.idx[row0 + r] = idx;
+      if (p.mask) p.mask[row0 + r] = m;
+      acc[1] += m;
+    }
+    const float g = m * inv_rows;
+    // ---- strong view(s): masked CE + gradient (loss.py:157-164, :119) ----
+#pragma unroll 1
+    for (int head = 0; head < (dual ? 2 : 1); ++head) {
+      float* srow = (head ? ss2 : ss) + r * C;
+      row_load<LPR, EPL>(srow, C, gl, valid, x);
+      row_softmax_stats<LPR, EPL>(x, e, mx, sum);
+      const float logsum = logf(sum);
+      float lrow;
+      if (p.hard) {
+        const float sidx = row_pick<LPR, EPL>(x, gl, valid ? idx : -1);
+        lrow = -((sidx - mx) - logsum);
+      } else {
+        float d = 0.f;
+#pragma unroll
+        for (int k = 0; k < EPL; ++k)
+          if (gl + k * LPR < C && valid) d += -pw[k] * ((x[k] - mx) - logsum);
+        lrow = group_sum<LPR>(d);
+      }
+      if (valid && gl == 0) acc[head ? 2 : 0] += lrow * m;
+      if (valid) {
+#pragma unroll
+        for (int k = 0; k < EPL; ++k) {
+          const int c = gl + k * LPR;
+          if (c < C) {
+            const float sm = __fdiv_rn(e[k], sum);
+            float gr;
+            if (p.hard) gr = (c == idx) ? __fadd_rn(__fmul_rn(sm, g), -g) : __fmul_rn(sm, g);
+            else gr = g * (sm * tsum - pw[k]);
+            srow[c] = gr;
+          }
+        }
+      }
+    }
+    __syncthreads();
+    tile_s2g(ss, static_cast<T*>(p.gs) + row0 * C, cnt);
+    if (dual) tile_s2g(ss2, static_cast<T*>(p.gs2) + row0 * C, cnt);
+    __syncthreads();
+  }
+  block_sum<3>(acc);
+  float total[3];
+  if (grid_reduce_last<3>(acc, p.partials, p.ticket, total) && threadIdx.x == 0) {
+    const float n = (float)p.rows;
+    p.out[0] = total[0] / n;
+    p.out[1] = total[1] / n;
+    p.out[2] = total[2] / n;
+  }
+}
+
+// ============================================================ f2 ============
+struct LabeledParams {
+  const void* x; const long long* y; const float* cw; void* gx;
+  long long rows; int C; int poly; float eps;
+  float* out; float* partials; unsigned* ticket;
+};
+
+template <typename T, int LPR, int EPL>
+__global__ void __launch_bounds__(kRowThreads) labeled_ce_kernel(const LabeledParams p) {
+  using Cfg = RowCfg<LPR, EPL>;
+  constexpr int ROWS = Cfg::kRowsPerTile;
+  extern __shared__ float smem[];
+  const int C = p.C;
+  float* sx = smem;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int gl = lane % LPR, rw = lane / LPR;
+  const long long ntiles = (p.rows + ROWS - 1) / ROWS;
+  // normaliser: rows (poly / unweighted) or sum of w[y] (F.cross_entropy weighted mean)
+  __shared__ float s_norm;
+  if (!p.poly && p.cw) {
+    float v[1] = {0.f};
+    for (long long i = threadIdx.x; i < p.rows; i += blockDim.x) v[0] += p.cw[p.y[i]];
+    block_sum<1>(v);
+    if (threadIdx.x == 0) s_norm = v[0];
+  } else if (threadIdx.x == 0) {
+    s_norm = (float)p.rows;
+  }
+  __syncthreads();
+  const float inv_norm = 1.0f / s_norm;
+  float acc[1] = {0.f};
+  for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const long long row0 = tile * ROWS;
+    const int nrows = (int)min((long long)ROWS, p.rows - row0);
+    const int cnt = nrows * C;
+    tile_g2s(static_cast<const T*>(p.x) + row0 * C, sx, cnt);
+    __syncthreads();
+    const int r = warp * Cfg::kRowsPerWarp + rw;
+    const bool valid = r < nrows;
+    float* srow = sx + r * C;
+    float x[EPL], e[EPL];
+    float mx, sum;
+    row_load<LPR, EPL>(srow, C, gl, valid, x);
+    row_softmax_stats<LPR, EPL>(x, e, mx, sum);
+    const int y = valid ? (int)p.y[row0 + r] : 0;
+    const float wy = (valid && p.cw) ? p.cw[y] : 1.f;
+    const float xy = row_pick<LPR, EPL>(x, gl, valid ? y : -1);
+    const float ce = -((xy - mx) - logf(sum));
+    const float pt = __fdiv_rn(expf(xy - mx), sum);
+    const float rowl = p.poly ? (wy * ce + p.eps * (1.f - pt)) : wy * ce;
+    if (valid && gl == 0) acc[0] += rowl;
+    const float coef = (p.poly ? (wy + p.eps * pt) : wy) * inv_norm;
+    if (valid) {
+#pragma unroll
+      for (int k = 0; k < EPL; ++k) {
+        const int c = gl + k * LPR;
+        if (c < C) srow[c] = coef * (__fdiv_rn(e[k], sum) - (c == y ? 1.f : 0.f));
+      }
+    }
+    __syncthreads();
+    tile_s2g(sx, static_cast<T*>(p.gx) + row0 * C, cnt);
+    __syncthreads();
+  }
+  block_sum<1>(acc);
+  float total[1];
+  if (grid_reduce_last<1>(acc, p.partials, p.ticket, total) && threadIdx.x == 0) p.out[0] = total[0] / s_norm;
+}
+
+// ============================================================ K2 ============
+struct DaParams {
+  const void* w; long long rows; int C;
+  float* ring; int* state; int window; float* prob_avg; float* col_mean;
+  float* partials; unsigned* ticket;
+};
+
+template <typename T, int LPR, int EPL>
+__global__ void __launch_bounds__(kRowThreads) comatch_da_kernel(const DaParams p) {
+  using Cfg = RowCfg<LPR, EPL>;
+  constexpr int ROWS = Cfg::kRowsPerTile;
+  extern __shared__ float smem[];
+  const int C = p.C;
+  float* sw = smem;             // [ROWS*C]
+  float* scol = sw + ROWS * C;  // [C]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int gl = lane % LPR, rw = lane / LPR;
+  const long long ntiles = (p.rows + ROWS - 1) / ROWS;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) scol[c] = 0.f;
+  for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const long long row0 = tile * ROWS;
+    const int nrows = (int)min((long long)ROWS, p.rows - row0);
+    tile_g2s(static_cast<const T*>(p.w) + row0 * C, sw, nrows * C);
+    __syncthreads();
+    const int r = warp * Cfg::kRowsPerWarp + rw;
+    const bool valid = r < nrows;
+    float x[EPL], e[EPL];
+    float mx, sum;
+    row_load<LPR, EPL>(sw + r * C, C, gl, valid, x);
+    row_softmax_stats<LPR, EPL>(x, e, mx, sum);
+    if (valid) {
+#pragma unroll
+      for (int k = 0; k < EPL; ++k) {
+        const int c = gl + k * LPR;
+        if (c < C) sw[r * C + c] = __fdiv_rn(e[k], sum);
+      }
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+      float t = scol[c];
+      for (int rr = 0; rr < nrows; ++rr) t += sw[rr * C + c];
+      scol[c] = t;
+    }
+    __syncthreads();
+  }
+  // publish per-CTA column sums, last CTA folds them and updates the history
+  __shared__ bool s_last;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) p.partials[(size_t)blockIdx.x * C + c] = scol[c];
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = (atomicAdd(p.ticket, 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  const int count_old = p.state[0], head = p.state[1];
+  const int count = min(count_old + 1, p.window);
+  const int head_new = (head + 1) % p.window;
+  for (int c = warp; c < C; c += kRowWarps) {
+    float t = 0.f;
+    for (unsigned b = lane; b < gridDim.x; b += 32) t += __ldcg(&p.partials[(size_t)b * C + c]);
+    t = warp_sum(t);
+    const float mean = t / (float)p.rows;  // probs.mean(0), comatch.py:169
+    // history mean, oldest -> newest (comatch.py:172); the newest entry is `mean`
+    float h = 0.f;
+    for (int a = lane; a < count; a += 32) {
+      const int slot = (head_new - count + a + 2 * p.window) % p.window;
+      h += (a == count - 1) ? mean : p.ring[(size_t)slot * C + c];
+    }
+    h = warp_sum(h);
+    if (lane == 0) {
+      p.ring[(size_t)head * C + c] = mean;
+      p.prob_avg[c] = h / (float)count;
+      if (p.col_mean) p.col_mean[c] = mean;
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    p.state[0] = count;
+    p.state[1] = head_new;
+    *p.ticket = 0u;
+  }
+}
+
+// ====================================================== K2b + K4 + K7 =======
+struct FinalizeParams {
+  const void* w; const void* s0;
+  const float* prob_avg; const float* rowsum; const float* numer;
+  long long rows; int C;
+  float alpha, one_minus_alpha, thr, gamma;
+  float* probs; float* probs_orig; float* scores; long long* lbs; float* mask;
+  void* gs0; float* out; float* partials; unsigned* ticket;
+};
+
+__device__ __forceinline__ float pow_gamma(float b, float gamma) {
+  if (gamma == 2.f) return b * b;
+  if (gamma == 1.f) return b;
+  if (gamma == 0.f) return 1.f;
+  return powf(b, gamma);
+}
+
+template <typename T, int LPR, int EPL>
+__global__ void __launch_bounds__(kRowThreads) comatch_finalize_kernel(const FinalizeParams p) {
+  using Cfg = RowCfg<LPR, EPL>;
+  constexpr int ROWS = Cfg::kRowsPerTile;
+  extern __shared__ float smem[];
+  const int C = p.C;
+  float* sw = smem;            // weak logits  -> probs
+  float* ss = sw + ROWS * C;   // strong logits -> grad
+  float* so = ss + ROWS * C;   // probs_orig
+  float* sn = so + ROWS * C;   // numer
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int gl = lane % LPR, rw = lane / LPR;
+  const bool smooth = p.rowsum != nullptr && p.numer != nullptr;
+  const float inv_rows = 1.0f / (float)p.rows;
+  const long long ntiles = (p.rows + ROWS - 1) / ROWS;
+  float acc[2] = {0.f, 0.f};
+  for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const long long row0 = tile * ROWS;
+    const int nrows = (int)min((long long)ROWS, p.rows - row0);
+    const int cnt = nrows * C;
+    tile_g2s(static_cast<const T*>(p.w) + row0 * C, sw, cnt);
+    tile_g2s(static_cast<const T*>(p.s0) + row0 * C, ss, cnt);
+    if (smooth) tile_g2s(p.numer + row0 * C, sn, cnt);
+    __syncthreads();
+    const int r = warp * Cfg::kRowsPerWarp + rw;
+    const bool valid = r < nrows;
+    float x[EPL], e[EPL], pr[EPL];
+    float mx, sum;
+    // softmax + DA divide + renormalise (comatch.py:163,174-176)
+    row_load<LPR, EPL>(sw + r * C, C, gl, valid, x);
+    row_softmax_stats<LPR, EPL>(x, e, mx, sum);
+    float q = 0.f;
+#pragma unroll
+    for (int k = 0; k < EPL; ++k) {
+      const int c = gl + k * LPR;
+      pr[k] = (c < C) ? __fdiv_rn(__fdiv_rn(e[k], sum), p.prob_avg[c]) : 0.f;
+      q += pr[k];
+    }
+    q = group_sum<LPR>(q);
+    const float rs = (smooth && valid) ? p.rowsum[row0 + r] : 1.f;
+    float psum = 0.f;
+#pragma unroll
+    for (int k = 0; k < EPL; ++k) {
+      const int c = gl + k * LPR;
+      const float po = __fdiv_rn(pr[k], q);
+      if (valid && c < C) so[r * C + c] = po;
+      float v = po;
+      if (smooth && valid && c < C)  // comatch.py:181-182
+        v = __fadd_rn(__fmul_rn(p.alpha, po), __fmul_rn(p.one_minus_alpha, __fdiv_rn(sn[r * C + c], rs)));
+      pr[k] = (c < C) ? v : 0.f;
+      psum += pr[k];
+    }
+    psum = group_sum<LPR>(psum);
+    float score; int lb;
+    row_argmax<LPR, EPL>(pr, C, gl, score, lb);          // comatch.py:184
+    const float m = (valid && score >= p.thr) ? 1.f : 0.f;  // :185
+    if (valid) {
+#pragma unroll
+      for (int k = 0; k < EPL; ++k) {
+        const int c = gl + k * LPR;
+        if (c < C) sw[r * C + c] = pr[k];
+      }
+      if (gl == 0) {
+        if (p.scores) p.scores[row0 + r] = score;
+        if (p.lbs) p.lbs[row0 + r] = lb;
+        if (p.mask) p.mask[row0 + r] = m;
+        acc[1] += m;
+      }
+    }
+    // focal soft-CE on the strong view (comatch.py:216-220) + gradient
+    row_load<LPR, EPL>(ss + r * C, C, gl, valid, x);
+    row_softmax_stats<LPR, EPL>(x, e, mx, sum);
+    const float logsum = logf(sum);
+    float d = 0.f;
+#pragma unroll
+    for (int k = 0; k < EPL; ++k)
+      if (valid && gl + k * LPR < C) d += ((x[k] - mx) - logsum) * pr[k];
+    d = group_sum<LPR>(d);
+    const float logp = -d * m;
+    const float pp = expf(-logp);
+    const float om = 1.f - pp;
+    const float lrow = pow_gamma(om, p.gamma) * logp;
+    if (valid && gl == 0) acc[0] += lrow;
+    float dl = pow_gamma(om, p.gamma);
+    if (p.gamma != 0.f) dl += p.gamma * pow_gamma(om, p.gamma - 1.f) * pp * logp;
+    const float coef = dl * inv_rows * m;
+    if (valid) {
+#pragma unroll
+      for (int k = 0; k < EPL; ++k) {
+        const int c = gl + k * LPR;
+        if (c < C) ss[r * C + c] = coef * (__fdiv_rn(e[k], sum) * psum - pr[k]);
+      }
+    }
+    __syncthreads();
+    tile_s2g(sw, p.probs + row0 * C, cnt);
+    tile_s2g(so, p.probs_orig + row0 * C, cnt);
+    tile_s2g(ss, static_cast<T*>(p.gs0) + row0 * C, cnt);
+    __syncthreads();
+  }
+  block_sum<2>(acc);
+  float total[2];
+  if (grid_reduce_last<2>(acc, p.partials, p.ticket, total) && threadIdx.x == 0) {
+    p.out[0] = total[0] / (float)p.rows;
+    p.out[1] = total[1] / (float)p.rows;
+  }
+}
+
+// ---- grad *= *scale -----------------------------------------------------------
+template <typename T>
+__global__ void scale_kernel(T* g, long long n, const float* scale) {
+  const float sc = *scale;
+  constexpr int N = Vec16<T>::N;
+  const long long nvec = ((reinterpret_cast<uintptr_t>(g) & 15u) == 0) ? n / N : 0;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long v = blockIdx.x * (long long)blockDim.x + threadIdx.x; v < nvec; v += stride) {
+    float f[N];
+    unpack16(*reinterpret_cast<const uint4*>(g + v * N), f, T());
+#pragma unroll
+    for (int i = 0; i < N; ++i) f[i] *= sc;
+    *reinterpret_cast<uint4*>(g + v * N) = pack16(f, T());
+  }
+  for (long long i = nvec * N + blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += stride)
+    g[i] = from_f32<T>(to_f32<T>(g[i]) * sc);
+}
+
+// ---- launch helpers -------------------------------------------------------------
+struct RowLaunch { int grid; size_t smem; };
+
+template <int LPR, int EPL>
+RowLaunch row_launch(long long rows, int C, int ntile_arrays, int extra_floats = 0) {
+  constexpr int ROWS = RowCfg<LPR, EPL>::kRowsPerTile;
+  const long long ntiles = (rows + ROWS - 1) / ROWS;
+  RowLaunch l;
+  l.grid = (int)(ntiles < kMaxRowCtas ? ntiles : kMaxRowCtas);
+  if (l.grid < 1) l.grid = 1;
+  l.smem = ((size_t)ntile_arrays * ROWS * C + extra_floats) * sizeof(float);
+  return l;
+}
+
+int check_rows(const char* fn, long long rows, int C, int dtype) {
+  if (rows <= 0) return fail(B200SSL_E_SHAPE, "%s: rows must be > 0 (got %lld)", fn, rows);
+  if (C < 2 || C > B200SSL_MAX_CLASSES) return fail(B200SSL_E_SHAPE, "%s: classes %d outside [2, %d]", fn, C, B200SSL_MAX_CLASSES);
+  if (dtype != B200SSL_F32 && dtype != B200SSL_BF16) return fail(B200SSL_E_DTYPE, "%s: dtype %d (want f32=0 or bf16=1)", fn, dtype);
+  return 0;
+}
+int check_ws(const char* fn, void* ws, size_t have, size_t need) {
+  if (!ws) return fail(B200SSL_E_NULL, "%s: workspace is NULL", fn);
+  if (reinterpret_cast<uintptr_t>(ws) & 255u) return fail(B200SSL_E_ALIGN, "%s: workspace must be 256-byte aligned", fn);
+  if (have < need) return fail(B200SSL_E_WORKSPACE, "%s: workspace %zu < %zu bytes", fn, have, need);
+  return 0;
+}
+
+// dispatch on (dtype, classes) -> (T, LPR, EPL)
+#define B200SSL_ROW_DISPATCH(DTYPE, C, ...)                                  \
+  do {                                                                         \
+    if ((DTYPE) == B200SSL_F32) {                                              \
+      using T = float;                                                         \
+      if ((C) <= 32) { constexpr int LPR = 8, EPL = 4; __VA_ARGS__; }                 \
+      else if ((C) <= 128) { constexpr int LPR = 32, EPL = 4; __VA_ARGS__; }          \
+      else { constexpr int LPR = 32, EPL = 32; __VA_ARGS__; }                         \
+    } else {                                                                   \
+      using T = __nv_bfloat16;                                                 \
+      if ((C) <= 32) { constexpr int LPR = 8, EPL = 4; __VA_ARGS__; }                 \
+      else if ((C) <= 128) { constexpr int LPR = 32, EPL = 4; __VA_ARGS__; }          \
+      else { constexpr int LPR = 32, EPL = 32; __VA_ARGS__; }                         \
+    }                                                                          \
+  } while (0)
+
+template <typename K>
+int set_smem(K kernel, size_t smem) {
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return fail((int)e, "cudaFuncSetAttribute(smem=%zu): %s", smem, cudaGetErrorString(e));
+  }
+  return 0;
+}
+
+}  // namespace
+}  // namespace b200ssl
+
+using namespace b200ssl;
+
+extern "C" int b200ssl_fixmatch_head_fwd_bwd(const void* logits_w, const void* logits_s, const void* logits_s2,
+                                             void* grad_s, void* grad_s2, int64_t rows, int32_t classes,
+                                             int32_t dtype, float p_cutoff, float inv_T, int32_t use_hard_labels,
+                                             float* out_scalars, int64_t* idx, float* mask, void* workspace,
+                                             size_t workspace_bytes, void* stream) {
+  const char* fn = "b200ssl_fixmatch_head_fwd_bwd";
+  if (int e = check_rows(fn, rows, classes, dtype)) return e;
+  if (!logits_w || !logits_s || !grad_s || !out_scalars) return fail(B200SSL_E_NULL, "%s: NULL tensor", fn);
+  if ((logits_s2 == nullptr) != (grad_s2 == nullptr)) return fail(B200SSL_E_NULL, "%s: logits_s2 and grad_s2 go together", fn);
+  if (int e = check_ws(fn, workspace, workspace_bytes, kWsHeaderBytes + sizeof(float) * 3 * kMaxRowCtas)) return e;
+  HeadParams p{logits_w, logits_s, logits_s2, grad_s, grad_s2, rows, classes, p_cutoff, inv_T,
+               use_hard_labels ? 1 : 0, out_scalars, reinterpret_cast<long long*>(idx), mask,
+               reinterpret_cast<float*>(static_cast<char*>(workspace) + kWsHeaderBytes),
+               reinterpret_cast<unsigned*>(workspace)};
+  B200SSL_ROW_DISPATCH(dtype, classes, {
+    RowLaunch l = row_launch<LPR, EPL>(rows, classes, 3);
+    auto k = fixmatch_head_kernel<T, LPR, EPL>;
+    if (int e = set_smem(k, l.smem)) return e;
+    k<<<l.grid, kRowThreads, l.smem, as_stream(stream)>>>(p);
+  });
+  return check_launch(fn);
+}
+
+extern "C" int b200ssl_labeled_ce_fwd_bwd(const void* logits, const int64_t* targets, const float* class_weights,
+                                          void* grad, int64_t rows, int32_t classes, int32_t dtype, int32_t poly,
+                                          float epsilon, float* out_scalar, void* workspace, size_t workspace_bytes,
+                                          void* stream) {
+  const char* fn = "b200ssl_labeled_ce_fwd_bwd";
+  if (int e = check_rows(fn, rows, classes, dtype)) return e;
+  if (!logits || !targets || !grad || !out_scalar) return fail(B200SSL_E_NULL, "%s: NULL tensor", fn);
+  if (int e = check_ws(fn, workspace, workspace_bytes, kWsHeaderBytes + sizeof(float) * kMaxRowCtas)) return e;
+  LabeledParams p{logits, reinterpret_cast<const long long*>(targets), class_weights, grad, rows, classes,
+                  poly ? 1 : 0, poly ? epsilon : 0.f, out_scalar,
+                  reinterpret_cast<float*>(static_cast<char*>(workspace) + kWsHeaderBytes),
+                  reinterpret_cast<unsigned*>(workspace) + 1};
+  B200SSL_ROW_DISPATCH(dtype, classes, {
+    RowLaunch l = row_launch<LPR, EPL>(rows, classes, 1);
+    auto k = labeled_ce_kernel<T, LPR, EPL>;
+    if (int e = set_smem(k, l.smem)) return e;
+    k<<<l.grid, kRowThreads, l.smem, as_stream(stream)>>>(p);
+  });
+  return check_launch(fn);
+}
+
+extern "C" int b200ssl_comatch_da(const void* logits_u_w, int64_t rows, int32_t classes, int32_t dtype,
+                                  float* da_ring, int32_t* da_state, int32_t window, float* prob_avg,
+                                  float* col_mean_out, void* workspace, size_t workspace_bytes, void* stream) {
+  const char* fn = "b200ssl_comatch_da";
+  if (int e = check_rows(fn, rows, classes, dtype)) return e;
+  if (!logits_u_w || !da_ring || !da_state || !prob_avg) return fail(B200SSL_E_NULL, "%s: NULL tensor", fn);
+  if (window < 1 || window > B200SSL_DA_WINDOW_MAX) return fail(B200SSL_E_ARG, "%s: window %d outside [1,%d]", fn, window, B200SSL_DA_WINDOW_MAX);
+  if (int e = check_ws(fn, workspace, workspace_bytes, kWsHeaderBytes + sizeof(float) * (size_t)classes * kNumSMs)) return e;
+  DaParams p{logits_u_w, rows, classes, da_ring, da_state, window, prob_avg, col_mean_out,
+             reinterpret_cast<float*>(static_cast<char*>(workspace) + kWsHeaderBytes),
+             reinterpret_cast<unsigned*>(workspace) + 2};
+  B200SSL_ROW_DISPATCH(dtype, classes, {
+    RowLaunch l = row_launch<LPR, EPL>(rows, classes, 1, classes);
+    if (l.grid > kNumSMs) l.grid = kNumSMs;
+    auto k = comatch_da_kernel<T, LPR, EPL>;
+    if (int e = set_smem(k, l.smem)) return e;
+    k<<<l.grid, kRowThreads, l.smem, as_stream(stream)>>>(p);
+  });
+  return check_launch(fn);
+}
+
+extern "C" int b200ssl_comatch_finalize(const void* logits_u_w, const void* logits_u_s0, const float* prob_avg,
+                                        const float* rowsum, const float* numer, int64_t rows, int32_t classes,
+                                        int32_t dtype, float alpha, float one_minus_alpha, float thr, float gamma,
+                                        float* probs, float* probs_orig, float* scores, int64_t* lbs, float* mask,
+                                        void* grad_s0, float* out_scalars, void* workspace, size_t workspace_bytes,
+                                        void* stream) {
+  const char* fn = "b200ssl_comatch_finalize";
+  if (int e = check_rows(fn, rows, classes, dtype)) return e;
+  if (!logits_u_w || !logits_u_s0 || !prob_avg || !probs || !probs_orig || !grad_s0 || !out_scalars)
+    return fail(B200SSL_E_NULL, "%s: NULL tensor", fn);
+  if ((rowsum == nullptr) != (numer == nullptr)) return fail(B200SSL_E_NULL, "%s: rowsum and numer go together", fn);
+  if (int e = check_ws(fn, workspace, workspace_bytes, kWsHeaderBytes + sizeof(float) * 2 * kMaxRowCtas)) return e;
+  FinalizeParams p{logits_u_w, logits_u_s0, prob_avg, rowsum, numer, rows, classes, alpha, one_minus_alpha, thr, gamma,
+                   probs, probs_orig, scores, reinterpret_cast<long long*>(lbs), mask, grad_s0, out_scalars,
+                   reinterpret_cast<float*>(static_cast<char*>(workspace) + kWsHeaderBytes),
+                   reinterpret_cast<unsigned*>(workspace) + 3};
+  B200SSL_ROW_DISPATCH(dtype, classes, {
+    RowLaunch l = row_launch<LPR, EPL>(rows, classes, 4);
+    auto k = comatch_finalize_kernel<T, LPR, EPL>;
+    if (int e = set_smem(k, l.smem)) return e;
+    k<<<l.grid, kRowThreads, l.smem, as_stream(stream)>>>(p);
+  });
+  return check_launch(fn);
+}
+
+extern "C" int b200ssl_scale_inplace(void* grad, int64_t numel, int32_t dtype, const float* scale, void* stream) {
+  const char* fn = "b200ssl_scale_inplace";
+  if (!grad || !scale) return fail(B200SSL_E_NULL, "%s: NULL pointer", fn);
+  if (numel <= 0) return fail(B200SSL_E_SHAPE, "%s: numel must be > 0", fn);
+  const int threads = 256;
+  long long blocks = (numel / 4 + threads - 1) / threads;
+  if (blocks < 1) blocks = 1;
+  if (blocks > 8 * kNumSMs) blocks = 8 * kNumSMs;
+  if (dtype == B200SSL_F32) scale_kernel<float><<<(int)blocks, threads, 0, as_stream(stream)>>>(static_cast<float*>(grad), numel, scale);
+  else if (dtype == B200SSL_BF16) scale_kernel<__nv_bfloat16><<<(int)blocks, threads, 0, as_stream(stream)>>>(static_cast<__nv_bfloat16*>(grad), numel, scale);
+  else return fail(B200SSL_E_DTYPE, "%s: dtype %d", fn, dtype);
+  return check_launch(fn);
+}

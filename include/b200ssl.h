@@ -1,0 +1,213 @@
+/*
+ * b200ssl.h -- C ABI of libb200ssl.so: the FixMatch / CoMatch unlabeled-consistency
+ * head and the EMA weight update as hand-written sm_100a CUDA kernels.
+ *
+ * The reference (taindp98/Endoscopy-Image-Classification) has no FFI of its
+ * own: its boundary for this path is the Python call surface of code/loss.py,
+ * code/ema.py and the inline head in code/comatch.py.  Each entry point below
+ * replaces one eager-op sequence of that surface; the file:line it replaces is
+ * cited on the declaration (paths relative to the reference root).
+ *
+ * Conventions (all entry points):
+ *   - return 0 on success, <0 for a rejected argument (B200SSL_E_*), >0 is a
+ *     cudaError_t from the launch; b200ssl_last_error_string() describes it;
+ *   - never allocate, never synchronise, never throw; re-entrant across streams
+ *     as long as each stream uses its own workspace;
+ *   - every pointer is a BORROWED DEVICE pointer (tensor.data_ptr()); matrices
+ *     are dense row-major; `dtype` selects the storage type of the logits /
+ *     embeddings / bank (B200SSL_F32 or B200SSL_BF16); all arithmetic is fp32;
+ *   - scalars results (losses, means) are written to device memory;
+ *   - `workspace` must be zero-filled once when it is allocated (it holds
+ *     self-resetting ticket counters), >= b200ssl_workspace_bytes() long and
+ *     256-byte aligned;
+ *   - `stream` is a cudaStream_t passed as void*.
+ */
+#ifndef B200SSL_H_
+#define B200SSL_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200SSL_VERSION 100 /* 0.1.0 */
+
+#if defined(__GNUC__)
+#define B200SSL_API __attribute__((visibility("default")))
+#else
+#define B200SSL_API
+#endif
+
+enum b200ssl_dtype { B200SSL_F32 = 0, B200SSL_BF16 = 1, B200SSL_F16 = 2, B200SSL_I64 = 3, B200SSL_I32 = 4, B200SSL_U8 = 5 };
+
+enum b200ssl_error {
+  B200SSL_OK = 0,
+  B200SSL_E_NULL = -1,      /* required pointer is NULL */
+  B200SSL_E_SHAPE = -2,     /* rows/classes/dim outside the supported range */
+  B200SSL_E_DTYPE = -3,     /* unsupported dtype for this entry point */
+  B200SSL_E_ALIGN = -4,     /* pointer not aligned as required */
+  B200SSL_E_WORKSPACE = -5, /* workspace too small */
+  B200SSL_E_ARG = -6        /* other invalid argument */
+};
+
+/* limits */
+#define B200SSL_MAX_CLASSES 1024
+#define B200SSL_MAX_EMB_DIM 256
+#define B200SSL_DA_WINDOW_MAX 64
+
+B200SSL_API int b200ssl_version(void);
+B200SSL_API const char* b200ssl_last_error_string(void);
+/* bytes of scratch any single call below may need for the given problem */
+B200SSL_API size_t b200ssl_workspace_bytes(int64_t rows, int32_t classes, int64_t bank_rows);
+
+/* ---------------------------------------------------------------- K1 ----
+ * FixMatch unlabeled head, forward + backward in one launch.
+ * Replaces code/loss.py:126-164 (consistency_loss, name='ce') incl. the
+ * F.cross_entropy at :119 and its autograd backward; called from
+ * code/fixmatch.py:116 and twice per step from code/semiformer.py:129-130
+ * (pass logits_s2/grad_s2 to serve both strong heads with one read of w).
+ *   p = softmax(w); (pmax, idx) = max(p) [first maximal index];
+ *   mask = pmax >= p_cutoff;  loss = mean(CE(s, idx) * mask)
+ *   grad_s = mask/rows * (softmax(s) - onehot(idx))            (hard labels)
+ *   soft labels (use_hard_labels=0): targets softmax(w*inv_T).
+ * out_scalars[0]=loss, [1]=mask mean, [2]=loss of the second strong head.
+ * idx (int64[rows]) and mask (f32[rows]) are optional outputs.
+ */
+B200SSL_API int b200ssl_fixmatch_head_fwd_bwd(const void* logits_w, const void* logits_s, const void* logits_s2,
+                                  void* grad_s, void* grad_s2, int64_t rows, int32_t classes,
+                                  int32_t dtype, float p_cutoff, float inv_T, int32_t use_hard_labels,
+                                  float* out_scalars, int64_t* idx, float* mask, void* workspace,
+                                  size_t workspace_bytes, void* stream);
+
+/* grad[i] *= *scale  -- chains the stashed gradient with autograd's upstream
+ * gradient (a device scalar, e.g. LAMBDA_U at code/fixmatch.py:118). */
+B200SSL_API int b200ssl_scale_inplace(void* grad, int64_t numel, int32_t dtype, const float* scale, void* stream);
+
+/* ------------------------------------------------------------ f2 (next) --
+ * Labeled-branch criterion: class-weighted CE or Poly-1 CE, forward+backward.
+ * Replaces code/loss.py:103-119 + PolyLoss code/loss.py:308-364 (called at
+ * code/fixmatch.py:114, code/comatch.py:156-160, code/semiformer.py:126-128).
+ *   row_i = w[y_i]*CE_i + epsilon*(1 - softmax(x_i)[y_i])
+ *   poly=1: loss = mean_i(row_i)               (plain mean, loss.py:355-356)
+ *   poly=0: loss = sum_i w[y_i]*CE_i / sum_i w[y_i]   (F.cross_entropy 'mean')
+ * class_weights may be NULL.  out_scalar[0] = loss.
+ */
+B200SSL_API int b200ssl_labeled_ce_fwd_bwd(const void* logits, const int64_t* targets, const float* class_weights,
+                               void* grad, int64_t rows, int32_t classes, int32_t dtype, int32_t poly,
+                               float epsilon, float* out_scalar, void* workspace, size_t workspace_bytes,
+                               void* stream);
+
+/* ---------------------------------------------------------------- K2 ----
+ * CoMatch distribution alignment statistics.  Replaces code/comatch.py:167-173:
+ * softmax(logits_u_w).mean(0) is pushed on a device-resident history ring
+ * (da_ring f32[window*classes], da_state int32[2] = {count, head}) and
+ * prob_avg f32[classes] = mean over the history, summed oldest -> newest.
+ * col_mean_out (optional f32[classes]) receives this batch's column mean.
+ */
+B200SSL_API int b200ssl_comatch_da(const void* logits_u_w, int64_t rows, int32_t classes, int32_t dtype,
+                       float* da_ring, int32_t* da_state, int32_t window, float* prob_avg,
+                       float* col_mean_out, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------- K3 ----
+ * Memory-smoothing partial sums against (a shard of) the bank.  Replaces the
+ * two GEMMs + exp + row-sum of code/comatch.py:180-181 without materialising
+ * A[rows, bank_rows]:
+ *   rowsum[i]   = sum_k exp(<f_i, q_k> / temperature)
+ *   numer[i,c]  = sum_k exp(<f_i, q_k> / temperature) * queue_probs[k,c]
+ * feats / queue_* share `dtype`; rowsum/numer are fp32.  No running max (the
+ * reference has none; |<f,q>|/tau <= 5 for unit-norm embeddings).
+ */
+B200SSL_API int b200ssl_bank_smooth_partial(const void* feats_u_w, const void* queue_feats, const void* queue_probs,
+                                int64_t rows, int64_t bank_rows, int32_t dim, int32_t classes,
+                                int32_t dtype, float temperature, float* rowsum, float* numer,
+                                void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------- K2b+K4+K7 ------
+ * Per-row finalisation of the CoMatch pseudo-label and the focal soft-CE.
+ * Replaces code/comatch.py:163,174-176 (DA divide + renormalise), :182
+ * (alpha mix; rowsum/numer NULL => smoothing off), :184-185 (max / mask) and
+ * :216-220 (focal soft cross-entropy) incl. its autograd backward:
+ *   probs_orig = renorm(softmax(w) / prob_avg)
+ *   probs      = alpha*probs_orig + one_minus_alpha*numer/rowsum
+ *                (factors rounded to fp32 by the caller: (float)a, (float)(1.0-a))
+ *   (scores, lbs) = max(probs);  mask = scores >= thr
+ *   logp = -sum_c log_softmax(s0)_c*probs_c * mask;  p = exp(-logp)
+ *   loss_u = mean((1-p)^gamma * logp)
+ *   grad_s0 = dl * mask * (softmax(s0)*sum_c probs_c - probs),
+ *             dl = (gamma*(1-p)^(gamma-1)*p*logp + (1-p)^gamma)/rows
+ * probs / probs_orig are fp32 [rows, classes]; out_scalars[0]=loss_u,
+ * [1]=mask mean.  scores/lbs/mask optional.
+ */
+B200SSL_API int b200ssl_comatch_finalize(const void* logits_u_w, const void* logits_u_s0, const float* prob_avg,
+                             const float* rowsum, const float* numer, int64_t rows, int32_t classes,
+                             int32_t dtype, float alpha, float one_minus_alpha, float thr, float gamma,
+                             float* probs,
+                             float* probs_orig, float* scores, int64_t* lbs, float* mask, void* grad_s0,
+                             float* out_scalars, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------- K5 ----
+ * Ring-buffer enqueue.  Replaces code/comatch.py:187-196: rows are
+ * [unlabeled-weak (n_u) ; labeled (n_x)], probabilities [probs_orig ; onehot(targets_x)],
+ * written at global rows (ptr + r) mod bank_rows_global.  Only rows that fall
+ * into the local shard [shard_begin, shard_begin+shard_rows) are written (the
+ * whole bank for shard_begin=0, shard_rows=bank_rows_global).  `block_offset`
+ * is this block's row offset inside a multi-rank step (rank * n), 0 otherwise.
+ * The pointer arithmetic (ptr = (ptr+n) % K) stays on the host.
+ */
+B200SSL_API int b200ssl_bank_enqueue(void* queue_feats, void* queue_probs, const void* feats_u_w, const void* feats_x,
+                         const float* probs_orig, const int64_t* targets_x, int64_t n_u, int64_t n_x,
+                         int32_t dim, int32_t classes, int32_t dtype, int64_t ptr, int64_t block_offset,
+                         int64_t bank_rows_global, int64_t shard_begin, int64_t shard_rows, void* stream);
+
+/* ---------------------------------------------------------------- K6 ----
+ * Graph-contrastive loss.  Replaces code/comatch.py:199-213 and its autograd
+ * backward (closed form):
+ *   P = rowsoftmax-without-max(F0 F1^T / tau);  Q = probs probs^T, diag 1,
+ *   thresholded at contrast_th, row-normalised;  loss = mean_i(-sum_j log(P+1e-7) Q)
+ * fwd writes loss to out_scalar[0] and row statistics (rowsum, qsum, r) into
+ * stats f32[3*rows]; bwd consumes them and writes grad_f0 / grad_f1 scaled by
+ * *upstream (device scalar, NULL => 1).
+ */
+B200SSL_API int b200ssl_contrast_fwd(const void* feats_s0, const void* feats_s1, const float* probs, int64_t rows,
+                         int32_t dim, int32_t classes, int32_t dtype, float temperature, float contrast_th,
+                         float* stats, float* out_scalar, void* workspace, size_t workspace_bytes,
+                         void* stream);
+B200SSL_API int b200ssl_contrast_bwd(const void* feats_s0, const void* feats_s1, const float* probs, const float* stats,
+                         int64_t rows, int32_t dim, int32_t classes, int32_t dtype, float temperature,
+                         float contrast_th, const float* upstream, void* grad_f0, void* grad_f1,
+                         void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------- K8 ----
+ * Multi-tensor EMA.  Replaces the per-tensor loop of code/ema.py:51-59
+ * (update) and :61-62 (set) with one launch over a device-resident table.
+ *   update: e <- fl(fl(d*e) + fl((1-d)*m)), each op rounded in the tensor's
+ *   dtype like the eager mul, mul, add (no FMA contraction); applied `repeat`
+ *   times when the same storage appears several times in state_dict()
+ *   (custom_model.py:194-200); int64 buffers are computed in fp32 and truncated.
+ * The table is device resident: one 32-byte row per chunk (<= 4096 elements is
+ * the shipped host policy) of one tensor, carrying that chunk's two base
+ * pointers so a CTA needs one dependent load before it streams.  It must be
+ * 16-byte aligned.  decay / one_minus_decay are (float)d and (float)(1.0-d).
+ */
+typedef struct b200ssl_ema_block {
+  void* ema;          /* first element of the chunk in the EMA tensor */
+  const void* model;  /* first element of the chunk in the live model tensor */
+  int32_t count;      /* elements in this chunk */
+  int32_t dtype;      /* enum b200ssl_dtype (F32, BF16, F16, I64, I32, U8) */
+  int32_t repeat;     /* >= 1: multiplicity of this storage in state_dict() */
+  int32_t reserved;
+} b200ssl_ema_block;
+
+/* One launch handles the rows whose dtype == float_dtype (F32, BF16 or F16) and,
+ * when do_ints != 0, the integer rows; rows of another float type are skipped
+ * (a mixed-precision model takes one launch per float type present). */
+B200SSL_API int b200ssl_ema_multi_tensor(const b200ssl_ema_block* blocks, int32_t n_blocks, int32_t float_dtype,
+                             int32_t do_ints, float decay, float one_minus_decay,
+                             int32_t mode /*0 update, 1 set*/, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200SSL_H_ */

@@ -1,0 +1,174 @@
+"""CPU tests: the C-ABI library loads and exports every symbol include/b200ssl.h
+declares, rejects bad arguments before touching the GPU, and the host-side logic
+(EMA block table, shard geometry, config knobs, no-CPU-fallback guarantees)."""
+import ctypes as C
+import re
+import subprocess
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import REPO
+
+HEADER = REPO / "include" / "b200ssl.h"
+PKG = REPO / "endoscopy-image-classification_b200"
+
+
+@pytest.fixture(scope="module")
+def native():
+    lib_path = PKG / "libb200ssl.so"
+    if not lib_path.exists():
+        import __graft_entry__ as g
+        g.build()
+    from endoscopy_image_classification_b200 import _native
+    _native.lib()
+    return _native
+
+
+def declared_symbols():
+    text = HEADER.read_text()
+    return sorted(set(re.findall(r"B200SSL_API[^;(]*?\b(b200ssl_\w+)\s*\(", text)))
+
+
+def test_header_symbols_exported_and_bound(native):
+    syms = declared_symbols()
+    assert len(syms) >= 13
+    lib = C.CDLL(str(PKG / "libb200ssl.so"))
+    for s in syms:
+        assert hasattr(lib, s), f"{s} declared in include/b200ssl.h but not exported"
+    assert sorted(native.SIGNATURES) == syms, "ctypes SIGNATURES out of sync with the header"
+    exported = subprocess.run(["nm", "-D", "--defined-only", str(PKG / "libb200ssl.so")], capture_output=True, text=True).stdout
+    extra = [l.split()[-1] for l in exported.splitlines() if " T " in l and not l.split()[-1].startswith("b200ssl_")]
+    assert not extra, f"unexpected exported symbols: {extra[:5]}"
+
+
+def test_no_torch_types_in_header():
+    text = HEADER.read_text()
+    assert "torch" not in text.lower().replace("pytorch", "") and "at::" not in text and "#include <cuda" not in text
+
+
+def test_version_and_workspace(native):
+    lib = native.lib()
+    assert lib.b200ssl_version() == 100
+    small = lib.b200ssl_workspace_bytes(448, 23, 2560)
+    big = lib.b200ssl_workspace_bytes(14336, 23, 65536)
+    assert 256 + 65536 < small <= big and small % 256 == 0
+
+
+def test_argument_validation_without_gpu(native):
+    """Bad arguments are rejected with negative codes before any CUDA call."""
+    lib = native.lib()
+    buf = (C.c_char * 4096)()
+    p = C.addressof(buf)
+    p256 = (p + 255) & ~255
+    wsb = lib.b200ssl_workspace_bytes(16, 23, 0)
+    E_NULL, E_SHAPE, E_DTYPE, E_ALIGN, E_WS, E_ARG = -1, -2, -3, -4, -5, -6
+    f = lib.b200ssl_fixmatch_head_fwd_bwd
+    assert f(None, p, None, p, None, 16, 23, 0, 0.95, 1.0, 1, p, None, None, p256, wsb, None) == E_NULL
+    assert b"NULL" in lib.b200ssl_last_error_string()
+    assert f(p, p, None, p, None, 0, 23, 0, 0.95, 1.0, 1, p, None, None, p256, wsb, None) == E_SHAPE
+    assert f(p, p, None, p, None, 16, 5000, 0, 0.95, 1.0, 1, p, None, None, p256, wsb, None) == E_SHAPE
+    assert f(p, p, None, p, None, 16, 23, 9, 0.95, 1.0, 1, p, None, None, p256, wsb, None) == E_DTYPE
+    assert f(p, p, p, p, None, 16, 23, 0, 0.95, 1.0, 1, p, None, None, p256, wsb, None) == E_NULL   # s2 without grad_s2
+    assert f(p, p, None, p, None, 16, 23, 0, 0.95, 1.0, 1, p, None, None, p256 + 4, wsb, None) == E_ALIGN
+    assert f(p, p, None, p, None, 16, 23, 0, 0.95, 1.0, 1, p, None, None, p256, 64, None) == E_WS
+    assert lib.b200ssl_comatch_da(p, 16, 23, 0, p, p, 100, p, None, p256, wsb, None) == E_ARG      # window > 64
+    assert lib.b200ssl_bank_smooth_partial(p, p, p, 16, 64, 12, 23, 0, 0.2, p, p, p256, wsb, None) == E_SHAPE  # dim % 8
+    assert lib.b200ssl_bank_smooth_partial(p, p, p, 16, 64, 64, 23, 0, 0.0, p, p, p256, wsb, None) == E_ARG   # tau
+    assert lib.b200ssl_bank_enqueue(p, p, p, p, p, p, 4, 4, 64, 23, 0, 100, 0, 64, 0, 64, None) == E_ARG     # ptr >= K
+    assert lib.b200ssl_bank_enqueue(p, p, p, p, p, p, 4, 4, 64, 23, 0, 0, 0, 64, 32, 64, None) == E_ARG      # shard outside
+    assert lib.b200ssl_contrast_fwd(p, p, p, 16, 64, 500, 0, 0.2, 0.8, p, p, p256, wsb, None) == E_SHAPE
+    assert lib.b200ssl_ema_multi_tensor(None, 4, 0, 1, 0.999, 0.001, 0, None) == E_NULL
+    assert lib.b200ssl_ema_multi_tensor(p256, 4, 3, 1, 0.999, 0.001, 0, None) == E_DTYPE
+    assert lib.b200ssl_ema_multi_tensor(p256, 4, 0, 1, 0.999, 0.001, 7, None) == E_ARG
+    assert lib.b200ssl_scale_inplace(None, 4, 0, p, None) == E_NULL
+
+
+def test_product_has_no_cpu_fallback_and_no_oracle_import(native):
+    from endoscopy_image_classification_b200 import comatch_head, ema, loss
+    w, s = torch.randn(8, 23), torch.randn(8, 23)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        loss.consistency_loss(w, s)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        loss.ce_loss(w, torch.zeros(8, dtype=torch.long), reduction="mean")
+    with pytest.raises(RuntimeError, match="CUDA"):
+        comatch_head.CoMatchHead(23, 64, 512, 0.9, device="cpu")
+    m = torch.nn.Linear(4, 4)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        ema.ModelEMA(m, 0.9).update(m)
+    # nothing in the product imports the oracle or reads the reference tree
+    for f in PKG.rglob("*.py"):
+        src = f.read_text()
+        assert "oracle" not in src.replace("no reference oracle", "").replace("without reference oracle", ""), f
+        assert "/root/reference" not in src, f
+
+
+def test_missing_library_fails_loudly(tmp_path):
+    code = ("import os, sys; os.environ['B200SSL_LIB']=%r; sys.path.insert(0, %r);"
+            "from endoscopy_image_classification_b200 import _native as N\n"
+            "try:\n    N.lib()\nexcept N.NativeLibraryError as e:\n    print('LOUD', e); sys.exit(0)\nsys.exit(1)") % (
+        str(tmp_path / "nope.so"), str(REPO))
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True)
+    assert r.returncode == 0 and "LOUD" in r.stdout, r.stderr[-500:]
+
+
+def test_ema_block_table():
+    from endoscopy_image_classification_b200 import _native as N
+    from endoscopy_image_classification_b200.ema import BLOCK_DTYPE, build_block_table
+    entries = [(0x1000, 0x9000, 10000, 4, N.F32, 2), (0x20000, 0x30000, 1, 8, N.I64, 1), (0x40000, 0x50000, 4096, 2, N.BF16, 1),
+               (0x60000, 0x70000, 0, 4, N.F32, 1)]
+    t = build_block_table(entries)
+    assert t.dtype == BLOCK_DTYPE and t.dtype.itemsize == 32
+    assert t["count"].tolist() == [4096, 4096, 1808, 1, 4096]
+    assert t["ema"].tolist() == [0x1000, 0x1000 + 4096 * 4, 0x1000 + 8192 * 4, 0x20000, 0x40000]
+    assert t["model"][2] == 0x9000 + 8192 * 4
+    assert t["repeat"].tolist() == [2, 2, 2, 1, 1] and t["dtype"].tolist() == [0, 0, 0, 3, 1]
+    assert int(t["count"].sum()) == 10000 + 1 + 4096
+    assert C.sizeof(N.EmaBlock) == 32
+
+
+def test_shard_geometry_and_segments():
+    from endoscopy_image_classification_b200.bank import ShardGeometry, local_segments
+    with pytest.raises(ValueError):
+        ShardGeometry(100, 8, 0)
+    K, R, n = 96, 4, 16
+    covered = np.zeros(K, dtype=int)
+    ptr = 80
+    for rank in range(R):
+        g = ShardGeometry(K, R, rank)
+        assert g.shard_rows == 24 and g.shard_begin == 24 * rank
+        for src, dst, ln in local_segments(ptr, R * n, g):
+            rows = (ptr + src + np.arange(ln)) % K
+            assert (rows == g.shard_begin + dst + np.arange(ln)).all()
+            covered[rows] += 1
+    want = np.zeros(K, dtype=int)
+    want[(ptr + np.arange(R * n)) % K] = 1
+    assert (covered == want).all()
+    g = ShardGeometry(K, R, 1)
+    assert g.next_ptr(80, n) == (80 + 64) % 96
+    assert g.should_enqueue(n, "always") and not g.should_enqueue(n, "reference")
+    assert ShardGeometry(64, 4, 0).should_enqueue(16, "reference")
+    with pytest.raises(ValueError):
+        g.should_enqueue(100, "always")
+
+
+def test_config_roundtrip_and_reference_module_names(tmp_path):
+    import endoscopy_image_classification_b200 as eic
+    from endoscopy_image_classification_b200.utils import AverageMeter, get_config
+    cfg = get_config(PKG / "configs" / "comatch_r50_hyperkvasir.yaml")
+    assert cfg.TRAIN.THRES == 0.9 and cfg.DATA.MU == 7 and cfg.MODEL.LOW_DIM == 64 and cfg.MODEL.NUM_CLASSES == 23
+    assert cfg.TRAIN.EMA_DECAY == 0.999 and cfg.TRAIN.T == 1.0 and cfg.TRAIN.USE_EMA is True
+    m = AverageMeter()
+    m.update(2.0, 4)
+    m.update(4.0, 4)
+    assert m.avg == 3.0
+    eic.install_as_reference_modules(("loss", "ema", "utils"))
+    import ema as ref_named_ema
+    import loss as ref_named_loss
+    assert ref_named_loss.consistency_loss is eic.loss.consistency_loss
+    assert ref_named_ema.ModelEMA.__init__.__code__.co_varnames[:4] == ("self", "model", "decay", "device")
+    for n in ("loss", "ema", "utils"):
+        sys.modules.pop(n, None)
