@@ -95,7 +95,9 @@ class CoMatchHead:
             world, rank = dist.get_world_size(process_group), dist.get_rank(process_group)
         self.geom = ShardGeometry(self.queue_size, world, rank)
         self._alloc_bank(dtype)
-        self.queue_ptr = 0
+        # write pointer: device-resident {ptr, ticket} (graph-replay safe) + host mirror
+        self.ptr_state = torch.zeros(2, dtype=torch.int64, device=self.device)
+        self._queue_ptr = 0
         self.da_ring = torch.zeros(self.da_window, self.num_classes, dtype=torch.float32, device=self.device)
         self.da_state = torch.zeros(2, dtype=torch.int32, device=self.device)   # count, head
         self.prob_avg = torch.empty(self.num_classes, dtype=torch.float32, device=self.device)
@@ -113,6 +115,26 @@ class CoMatchHead:
         self.queue_probs = torch.zeros(self.geom.shard_rows, self.num_classes, dtype=dtype, device=self.device)
 
     # ---- reference-visible state ------------------------------------------------
+    @property
+    def queue_ptr(self) -> int:
+        """``self.queue_ptr`` of the reference (comatch.py:94).  Host mirror of the device pointer;
+        it advances deterministically, so reading it never synchronises."""
+        return self._queue_ptr
+
+    @queue_ptr.setter
+    def queue_ptr(self, value: int) -> None:
+        self._queue_ptr = int(value) % self.queue_size
+        self.ptr_state.copy_(torch.tensor([self._queue_ptr, 0], dtype=torch.int64))
+
+    def sync_ptr_from_device(self) -> int:
+        """Re-read the device pointer into the host mirror (synchronises; use after graph capture)."""
+        self._queue_ptr = int(self.ptr_state[0].item())
+        return self._queue_ptr
+
+    def note_graph_replay(self, n_per_rank: int) -> None:
+        """Advance the host mirror after a CUDA-graph replay of a step that enqueued."""
+        self._queue_ptr = self.geom.next_ptr(self._queue_ptr, n_per_rank)
+
     @property
     def prob_list(self) -> List[torch.Tensor]:
         """The DA history as the reference keeps it (``comatch.py:96``): oldest first."""
@@ -132,7 +154,8 @@ class CoMatchHead:
                 "da_ring": self.da_ring, "da_state": self.da_state}
 
     def load_state_dict(self, sd: dict) -> None:
-        self._alloc_bank(sd["queue_feats"].dtype)
+        if sd["queue_feats"].dtype != self.dtype:          # otherwise copy in place: captured graphs
+            self._alloc_bank(sd["queue_feats"].dtype)      # keep pointing at the same storage
         self.queue_feats.copy_(sd["queue_feats"])
         self.queue_probs.copy_(sd["queue_probs"])
         self.queue_ptr = int(sd["queue_ptr"])
@@ -179,14 +202,14 @@ class CoMatchHead:
         n = rows + n_x
         if geom.should_enqueue(n, self.enqueue_mode):                    # K5
             if R == 1:
-                self._k_enqueue(fw, fx, out["probs_orig"], tx, 0)
+                self._k_enqueue(fw, fx, out["probs_orig"], tx, 0, n)
             else:
                 po_all = all_gather_rows(out["probs_orig"], self.pg).view(R, rows, C)
                 tx_all = all_gather_rows(tx, self.pg).view(R, n_x)
                 gf = gathered_f.view(R, n, D)
                 for r in range(R):                                       # block r sits at ptr + r*n
-                    self._k_enqueue(gf[r, :rows], gf[r, rows:], po_all[r], tx_all[r], r * n)
-            self.queue_ptr = geom.next_ptr(self.queue_ptr, n)
+                    self._k_enqueue(gf[r, :rows], gf[r, rows:], po_all[r], tx_all[r], r * n, R * n if r == R - 1 else 0)
+            self._queue_ptr = geom.next_ptr(self._queue_ptr, n)
             self._pristine = False
         stats, loss_c = self._k_contrast_fwd(fs0, fs1, out["probs"], out["scalars"])  # K6
         self.last = {"probs_orig": out["probs_orig"], "rowsum": rowsum, "numer": numer}
@@ -235,13 +258,14 @@ class CoMatchHead:
             N.stream_ptr(self.device)), "comatch_finalize")
         return out
 
-    def _k_enqueue(self, fw, fx, probs_orig, tx, block_offset: int) -> None:
+    def _k_enqueue(self, fw, fx, probs_orig, tx, block_offset: int, advance: int) -> None:
         g = self.geom
         fw, fx, probs_orig, tx = (t.contiguous() for t in (fw, fx, probs_orig, tx))
         N.check(N.lib().b200ssl_bank_enqueue(self.queue_feats.data_ptr(), self.queue_probs.data_ptr(), fw.data_ptr(),
                                              fx.data_ptr(), probs_orig.data_ptr(), tx.data_ptr(), fw.shape[0],
                                              fx.shape[0], self.low_dim, self.num_classes, N.dtype_enum(fw),
-                                             self.queue_ptr, block_offset, g.queue_size, g.shard_begin, g.shard_rows,
+                                             0, self.ptr_state.data_ptr(), advance, block_offset, g.queue_size,
+                                             g.shard_begin, g.shard_rows,
                                              N.stream_ptr(self.device)), "bank_enqueue")
 
     def _k_contrast_fwd(self, fs0, fs1, probs, scalars):

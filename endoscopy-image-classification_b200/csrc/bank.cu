@@ -129,14 +129,31 @@ struct EnqueueParams {
   void* qf; void* qp; const void* fu; const void* fx; const float* po; const long long* tx;
   long long n_u, n_x; int D, C;
   long long ptr, block_offset, K, shard_begin, shard_rows;
+  long long* ptr_state; long long advance;  // device-resident {write pointer, ticket}; see b200ssl.h
 };
 
 template <typename T>
 __global__ void __launch_bounds__(256) bank_enqueue_kernel(const EnqueueParams p) {
   const int lane = threadIdx.x & 31;
   const long long r = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  // The write pointer lives on the device when ptr_state is given (CUDA-graph replays
+  // must not bake it in); every CTA reads it before taking a ticket, the last CTA to
+  // finish advances it: ptr = (ptr + n) % K  (comatch.py:196).
+  __shared__ long long s_ptr;
+  if (threadIdx.x == 0) s_ptr = p.ptr_state ? *reinterpret_cast<volatile long long*>(p.ptr_state) : p.ptr;
+  __syncthreads();
+  const long long ptr = s_ptr;
+  if (p.ptr_state && threadIdx.x == 0) {
+    __threadfence();
+    const unsigned long long t = atomicAdd(reinterpret_cast<unsigned long long*>(p.ptr_state + 1), 1ull);
+    if (t == gridDim.x - 1) {
+      p.ptr_state[1] = 0;
+      if (p.advance) p.ptr_state[0] = (ptr + p.advance) % p.K;
+      __threadfence();
+    }
+  }
   if (r >= p.n_u + p.n_x) return;
-  const long long g = (p.ptr + p.block_offset + r) % p.K;  // comatch.py:194-196 with wrap
+  const long long g = (ptr + p.block_offset + r) % p.K;  // comatch.py:194-196 with wrap
   const long long local = g - p.shard_begin;
   if (local < 0 || local >= p.shard_rows) return;
   const bool lab = r >= p.n_u;                              // rows: [unlabeled-weak ; labeled]  (:187)
@@ -218,19 +235,22 @@ extern "C" int b200ssl_bank_smooth_partial(const void* feats_u_w, const void* qu
 
 extern "C" int b200ssl_bank_enqueue(void* queue_feats, void* queue_probs, const void* feats_u_w, const void* feats_x,
                                     const float* probs_orig, const int64_t* targets_x, int64_t n_u, int64_t n_x,
-                                    int32_t dim, int32_t classes, int32_t dtype, int64_t ptr, int64_t block_offset,
-                                    int64_t bank_rows_global, int64_t shard_begin, int64_t shard_rows, void* stream) {
+                                    int32_t dim, int32_t classes, int32_t dtype, int64_t ptr, int64_t* ptr_state,
+                                    int64_t advance, int64_t block_offset, int64_t bank_rows_global,
+                                    int64_t shard_begin, int64_t shard_rows, void* stream) {
   const char* fn = "b200ssl_bank_enqueue";
   if (!queue_feats || !queue_probs) return fail(B200SSL_E_NULL, "%s: NULL bank", fn);
   if (n_u < 0 || n_x < 0 || n_u + n_x <= 0) return fail(B200SSL_E_SHAPE, "%s: n_u=%lld n_x=%lld", fn, (long long)n_u, (long long)n_x);
   if ((n_u > 0 && (!feats_u_w || !probs_orig)) || (n_x > 0 && (!feats_x || !targets_x))) return fail(B200SSL_E_NULL, "%s: NULL rows", fn);
   if (dim < 1 || classes < 2) return fail(B200SSL_E_SHAPE, "%s: dim=%d classes=%d", fn, dim, classes);
+  if (advance < 0 || (advance && !ptr_state)) return fail(B200SSL_E_ARG, "%s: advance needs ptr_state", fn);
   if (bank_rows_global <= 0 || ptr < 0 || ptr >= bank_rows_global || block_offset < 0 || shard_begin < 0 ||
       shard_rows <= 0 || shard_begin + shard_rows > bank_rows_global)
     return fail(B200SSL_E_ARG, "%s: bad ring geometry (K=%lld ptr=%lld off=%lld shard=[%lld,+%lld))", fn,
                 (long long)bank_rows_global, (long long)ptr, (long long)block_offset, (long long)shard_begin, (long long)shard_rows);
   EnqueueParams p{queue_feats, queue_probs, feats_u_w, feats_x, probs_orig, reinterpret_cast<const long long*>(targets_x),
-                  n_u, n_x, dim, classes, ptr, block_offset, bank_rows_global, shard_begin, shard_rows};
+                  n_u, n_x, dim, classes, ptr, block_offset, bank_rows_global, shard_begin, shard_rows,
+                  reinterpret_cast<long long*>(ptr_state), advance};
   const long long n = n_u + n_x;
   const int grid = (int)((n + 7) / 8);
   if (dtype == B200SSL_F32) bank_enqueue_kernel<float><<<grid, 256, 0, as_stream(stream)>>>(p);

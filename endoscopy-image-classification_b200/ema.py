@@ -147,6 +147,8 @@ class ModelEMA(object):
 
     def _get_plan(self, model) -> _EmaPlan:
         self._calls += 1
+        if self._plan is not None and torch.cuda.is_current_stream_capturing():
+            return self._plan                  # CUDA-graph capture: no table rebuild (it would synchronise)
         if (self._plan is None or not self._plan.matches(model)
                 or (self._revalidate_every > 0 and self._calls % self._revalidate_every == 0)):
             with torch.no_grad():

@@ -154,12 +154,17 @@ B200SSL_API int b200ssl_comatch_finalize(const void* logits_u_w, const void* log
  * into the local shard [shard_begin, shard_begin+shard_rows) are written (the
  * whole bank for shard_begin=0, shard_rows=bank_rows_global).  `block_offset`
  * is this block's row offset inside a multi-rank step (rank * n), 0 otherwise.
- * The pointer arithmetic (ptr = (ptr+n) % K) stays on the host.
+ * The write pointer is either the host value `ptr` (ptr_state == NULL) or, for
+ * CUDA-graph replay, device resident: ptr_state = int64[2] {write pointer, ticket
+ * (zero-initialised)}; the kernel then ignores `ptr`, and after all rows are
+ * written advances the device pointer by `advance` rows mod K (0 = leave it, for
+ * all but the last block of a multi-rank step).
  */
 B200SSL_API int b200ssl_bank_enqueue(void* queue_feats, void* queue_probs, const void* feats_u_w, const void* feats_x,
                          const float* probs_orig, const int64_t* targets_x, int64_t n_u, int64_t n_x,
-                         int32_t dim, int32_t classes, int32_t dtype, int64_t ptr, int64_t block_offset,
-                         int64_t bank_rows_global, int64_t shard_begin, int64_t shard_rows, void* stream);
+                         int32_t dim, int32_t classes, int32_t dtype, int64_t ptr, int64_t* ptr_state,
+                         int64_t advance, int64_t block_offset, int64_t bank_rows_global,
+                         int64_t shard_begin, int64_t shard_rows, void* stream);
 
 /* ---------------------------------------------------------------- K6 ----
  * Graph-contrastive loss.  Replaces code/comatch.py:199-213 and its autograd

@@ -383,7 +383,7 @@ def test_contrast_fwd_bwd_vs_oracle(pkg, rows, D):
     stats, _ = head._k_contrast_fwd(d0, d1, dp, scal)
     up = torch.tensor(1.5, device="cuda")
     g0, g1 = head._k_contrast_bwd(d0, d1, dp, stats, up)
-    assert rel_err(scal[2], ref.detach()) < FP32_TOL
+    assert abs(float(scal[2]) - float(ref)) < FP32_TOL * max(abs(float(ref)), 1e-2)   # rows=1: loss ~ -1e-7
     assert rel_err(g0, 1.5 * f0.grad) < FP32_TOL and rel_err(g1, 1.5 * f1.grad) < FP32_TOL
 
 
@@ -410,7 +410,7 @@ def test_enqueue_kernel_matches_segment_plan(pkg):
         for r, b in enumerate(blocks):
             fu, fx, po, tx = (b[k].cuda() for k in ("fu", "fx", "po", "tx"))
             N.check(lib.b200ssl_bank_enqueue(qf.data_ptr(), qp.data_ptr(), fu.data_ptr(), fx.data_ptr(), po.data_ptr(),
-                                             tx.data_ptr(), n_u, n_x, D, C, N.F32, ptr, r * n, K, geom.shard_begin,
+                                             tx.data_ptr(), n_u, n_x, D, C, N.F32, ptr, None, 0, r * n, K, geom.shard_begin,
                                              geom.shard_rows, N.stream_ptr(qf.device)))
         lo = geom.shard_begin
         assert torch.equal(qf.cpu(), st.queue_feats[lo:lo + geom.shard_rows])
@@ -419,3 +419,65 @@ def test_enqueue_kernel_matches_segment_plan(pkg):
         for src, dst, ln in local_segments(ptr, R * n, geom):
             touched[dst:dst + ln] = True
         assert torch.equal(touched, (qf.cpu() != 0).any(1))
+
+
+def test_graphed_step_matches_eager(pkg):
+    """CUDA-graph replay of head fwd+bwd (+EMA) == the eager calls: same losses, grads, bank,
+    device write pointer and DA history after several steps."""
+    from endoscopy_image_classification_b200.graphs import GraphedStep
+    g = torch.Generator().manual_seed(21)
+    B, MU, D, thr = 8, 7, 64, 0.9
+    Bu, n = B * MU, B * (MU + 1)
+    protos = torch.nn.functional.normalize(torch.randn(C, D, generator=g), dim=1)
+    batches = [_clustered(g, B, Bu, D, protos) for _ in range(5)]
+    keys = list(batches[0].keys())
+    net = torch.nn.Linear(32, 32).cuda()
+
+    def make():
+        head = pkg["head"].CoMatchHead(C, D, 3 * n, thr, enqueue_mode="always")
+        ema = pkg["ema"].ModelEMA(net, decay=0.9, device="cuda")
+        return head, ema
+
+    def run(head, ema, batch):
+        for k in ("logits_u_s0", "feats_u_s0", "feats_u_s1"):
+            batch[k].grad = None
+            batch[k].requires_grad_(True)
+        lu, lc = head(**batch)[:2]
+        total = 2.0 * lu + 2.0 * lc
+        total.backward()
+        ema.update(net)
+        return total
+
+    head_e, ema_e = make()
+    eager = []
+    for b in batches:
+        db = {k: v.cuda() for k, v in b.items()}
+        t = run(head_e, ema_e, db)
+        eager.append((float(t), db["feats_u_s0"].grad.clone(), db["logits_u_s0"].grad.clone()))
+
+    head_g, ema_g = make()
+    # capture runs 3 warm-up steps + captures on batch 0; rewind the state afterwards
+    gs = GraphedStep(lambda sb: run(head_g, ema_g, sb), {k: v.cuda() for k, v in batches[0].items()}, "cuda", warmup=3,
+                     on_replay=lambda: head_g.note_graph_replay(n), after_capture=lambda: head_g.sync_ptr_from_device())
+    fresh, ema_f = make()
+    head_g.load_state_dict(fresh.state_dict())
+    head_g.queue_ptr = 0
+    with torch.no_grad():
+        for a, b in zip(ema_g.ema.state_dict().values(), ema_f.ema.state_dict().values()):
+            a.copy_(b)
+    for i, b in enumerate(batches):
+        if i % 2 == 0:
+            for k in keys:
+                gs.static[k].detach().copy_(b[k].cuda())
+            val = float(gs.replay())
+        else:
+            val = gs.replay_host(b)
+        assert val == eager[i][0]
+        assert torch.equal(gs.static["feats_u_s0"].grad, eager[i][1])
+        assert torch.equal(gs.static["logits_u_s0"].grad, eager[i][2])
+    torch.cuda.synchronize()
+    assert head_g.queue_ptr == head_e.queue_ptr == int(head_g.ptr_state[0]) == int(head_e.ptr_state[0])
+    assert torch.equal(head_g.queue_feats, head_e.queue_feats) and torch.equal(head_g.queue_probs, head_e.queue_probs)
+    assert torch.equal(head_g.da_ring, head_e.da_ring) and torch.equal(head_g.da_state, head_e.da_state)
+    for a, b in zip(ema_g.ema.state_dict().values(), ema_e.ema.state_dict().values()):
+        assert torch.equal(a, b)
