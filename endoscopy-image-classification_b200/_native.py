@@ -42,7 +42,7 @@ SIGNATURES = {
     "b200ssl_workspace_bytes": (_sz, [_i64, _i32, _i64]),
     "b200ssl_fixmatch_head_fwd_bwd": (_i32, [_vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _f32, _f32, _i32,
                                              _vp, _vp, _vp, _vp, _sz, _vp]),
-    "b200ssl_scale_inplace": (_i32, [_vp, _i64, _i32, _vp, _vp]),
+    "b200ssl_scale_inplace": (_i32, [_vp, _i64, _i32, _vp, _f32, _vp]),
     "b200ssl_labeled_ce_fwd_bwd": (_i32, [_vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _f32, _vp, _vp, _sz, _vp]),
     "b200ssl_comatch_da": (_i32, [_vp, _i64, _i32, _i32, _vp, _vp, _i32, _vp, _vp, _vp, _sz, _vp]),
     "b200ssl_bank_smooth_partial": (_i32, [_vp, _vp, _vp, _i64, _i64, _i32, _i32, _i32, _f32, _vp, _vp,
@@ -51,8 +51,9 @@ SIGNATURES = {
                                         _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "b200ssl_bank_enqueue": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i32, _i32, _i32, _i64, _vp, _i64,
                                     _i64, _i64, _i64, _i64, _vp]),
-    "b200ssl_contrast_fwd": (_i32, [_vp, _vp, _vp, _i64, _i32, _i32, _i32, _f32, _f32, _vp, _vp, _vp, _sz, _vp]),
-    "b200ssl_contrast_bwd": (_i32, [_vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _f32, _f32, _vp, _vp, _vp,
+    "b200ssl_contrast_fwd": (_i32, [_vp, _vp, _vp, _i64, _i32, _i32, _i32, _f32, _f32, _vp, _vp, _vp, _f32, _f32, _vp,
+                                    _vp, _sz, _vp]),
+    "b200ssl_contrast_bwd": (_i32, [_vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _f32, _f32, _vp, _f32, _vp, _vp,
                                     _vp, _sz, _vp]),
     "b200ssl_ema_multi_tensor": (_i32, [_vp, _i32, _i32, _i32, _f32, _f32, _i32, _vp]),
 }
@@ -121,15 +122,19 @@ def stream_ptr(device: torch.device) -> int:
     return torch.cuda.current_stream(device).cuda_stream
 
 
-# one zero-initialised workspace per (device, stream); grows on demand
-_workspaces: Dict[Tuple[int, int], torch.Tensor] = {}
+# One zero-initialised workspace per device, grown on demand.  It serialises the head's
+# kernels on one stream per device (the trainer's); pass your own workspace through the C ABI
+# to run heads concurrently on several streams.
+_workspaces: Dict[int, torch.Tensor] = {}
 
 
 def workspace(device: torch.device, rows: int, classes: int, bank_rows: int = 0) -> Tuple[int, int]:
     need = int(lib().b200ssl_workspace_bytes(int(rows), int(classes), int(bank_rows)))
-    key = (device.index if device.index is not None else torch.cuda.current_device(), stream_ptr(device))
+    key = device.index if device.index is not None else torch.cuda.current_device()
     ws = _workspaces.get(key)
     if ws is None or ws.numel() < need:
+        if torch.cuda.is_current_stream_capturing():
+            raise RuntimeError("workspace must be allocated before CUDA-graph capture: run the step once eagerly first")
         ws = torch.zeros(max(need, 1 << 20), dtype=torch.uint8, device=device)
         _workspaces[key] = ws
     return ws.data_ptr(), ws.numel()

@@ -33,35 +33,51 @@ __all__ = ["CoMatchHead"]
 
 
 class _HeadFn(torch.autograd.Function):
+    """Outputs: loss_u, loss_contrast, mask_mean, total (= lambda_u*loss_u + lambda_c*loss_contrast,
+    comatch.py:222 without loss_x), then the non-differentiable mask, lbs, scores, probs."""
+
     @staticmethod
-    def forward(ctx, head, logits_u_w, logits_u_s0, feats_u_w, feats_u_s0, feats_u_s1, feats_x, targets_x):
+    def forward(ctx, head, lambda_u, lambda_c, logits_u_w, logits_u_s0, feats_u_w, feats_u_s0, feats_u_s1, feats_x,
+                targets_x):
         f0, f1 = feats_u_s0.detach().contiguous(), feats_u_s1.detach().contiguous()
         out = head._step(logits_u_w.detach(), logits_u_s0.detach(), feats_u_w.detach(), f0, f1,
-                         feats_x.detach(), targets_x)
-        ctx.head = head
+                         feats_x.detach(), targets_x, float(lambda_u), float(lambda_c))
+        ctx.head, ctx.lambda_u, ctx.lambda_c = head, float(lambda_u), float(lambda_c)
         ctx.save_for_backward(out["grad_s0"], f0, f1, out["probs"], out["stats"])
         ctx.done = False
+        ctx.set_materialize_grads(False)
         aux = (out["mask"], out["lbs"], out["scores"], out["probs"])
         ctx.mark_non_differentiable(*aux)
         sc = out["scalars"]
-        return (sc[0], sc[2], sc[1]) + aux
+        return (sc[0], sc[2], sc[1], sc[3]) + aux
 
     @staticmethod
-    def backward(ctx, g_u, g_c, g_mm, *unused):
+    def backward(ctx, g_u, g_c, g_mm, g_total, *unused):
         if ctx.done:
             raise RuntimeError("CoMatchHead: backward through the fused head twice (the stashed gradient is consumed)")
         ctx.done = True
         grad_s0, f0, f1, probs, stats = ctx.saved_tensors
         head = ctx.head
+
+        def upstream(g_own, lam):
+            """(device scalar, host factor) with d(loss)/d(own) = g_own + lam * g_total."""
+            if g_total is None:
+                return g_own, 1.0
+            if g_own is None:
+                return g_total, lam
+            return g_own + lam * g_total, 1.0
+
         gs0 = gf0 = gf1 = None
-        if ctx.needs_input_grad[2]:
-            gs0 = torch.zeros_like(grad_s0) if g_u is None else head._k_scale(grad_s0, g_u)
-        if ctx.needs_input_grad[4] or ctx.needs_input_grad[5]:
-            if g_c is None:
+        if ctx.needs_input_grad[4]:
+            g, fac = upstream(g_u, ctx.lambda_u)
+            gs0 = torch.zeros_like(grad_s0) if g is None else head._k_scale(grad_s0, g, fac)
+        if ctx.needs_input_grad[6] or ctx.needs_input_grad[7]:
+            g, fac = upstream(g_c, ctx.lambda_c)
+            if g is None:
                 gf0, gf1 = torch.zeros_like(f0), torch.zeros_like(f1)
             else:
-                gf0, gf1 = head._k_contrast_bwd(f0, f1, probs, stats, g_c)
-        return None, None, gs0, None, gf0, gf1, None, None
+                gf0, gf1 = head._k_contrast_bwd(f0, f1, probs, stats, g, fac)
+        return None, None, None, None, gs0, None, gf0, gf1, None, None
 
 
 class CoMatchHead:
@@ -167,9 +183,19 @@ class CoMatchHead:
     def __call__(self, logits_u_w, logits_u_s0, feats_u_w, feats_u_s0, feats_u_s1, feats_x, targets_x):
         """Returns ``(loss_u, loss_contrast, mask_mean, mask, lbs_u_guess, scores, probs)``;
         the two losses carry grad w.r.t. ``logits_u_s0`` / ``feats_u_s0`` / ``feats_u_s1``."""
-        return _HeadFn.apply(self, logits_u_w, logits_u_s0, feats_u_w, feats_u_s0, feats_u_s1, feats_x, targets_x)
+        o = _HeadFn.apply(self, 1.0, 1.0, logits_u_w, logits_u_s0, feats_u_w, feats_u_s0, feats_u_s1, feats_x, targets_x)
+        return o[:3] + o[4:]
 
-    def _step(self, lw, ls0, fw, fs0, fs1, fx, tx):
+    def total_loss(self, logits_u_w, logits_u_s0, feats_u_w, feats_u_s0, feats_u_s1, feats_x, targets_x,
+                   lambda_u: float = 1.0, lambda_c: float = 1.0):
+        """``LAMBDA_U*loss_u + LAMBDA_C*loss_contrast`` (the unlabeled part of comatch.py:222) formed on
+        the device by the last forward kernel, with both weights folded into the backward launches --
+        no eager elementwise kernels around the head.  Returns ``(total, loss_u, loss_contrast, mask_mean)``."""
+        o = _HeadFn.apply(self, lambda_u, lambda_c, logits_u_w, logits_u_s0, feats_u_w, feats_u_s0, feats_u_s1,
+                          feats_x, targets_x)
+        return o[3], o[0].detach(), o[1].detach(), o[2].detach()
+
+    def _step(self, lw, ls0, fw, fs0, fs1, fx, tx, lambda_u: float = 1.0, lambda_c: float = 1.0):
         lw, ls0, fw, fx = (t.contiguous() for t in (lw, ls0, fw, fx))
         tx = tx.to(torch.int64).contiguous()
         rows, C = lw.shape
@@ -211,8 +237,9 @@ class CoMatchHead:
                     self._k_enqueue(gf[r, :rows], gf[r, rows:], po_all[r], tx_all[r], r * n, R * n if r == R - 1 else 0)
             self._queue_ptr = geom.next_ptr(self._queue_ptr, n)
             self._pristine = False
-        stats, loss_c = self._k_contrast_fwd(fs0, fs1, out["probs"], out["scalars"])  # K6
-        self.last = {"probs_orig": out["probs_orig"], "rowsum": rowsum, "numer": numer}
+        stats, loss_c = self._k_contrast_fwd(fs0, fs1, out["probs"], out["scalars"], lambda_u, lambda_c)  # K6
+        self.last = {"probs_orig": out["probs_orig"], "rowsum": rowsum, "numer": numer, "probs": out["probs"],
+                     "mask": out["mask"], "lbs": out["lbs"], "scores": out["scores"]}
         out["stats"] = stats
         return out
 
@@ -268,29 +295,31 @@ class CoMatchHead:
                                              g.shard_begin, g.shard_rows,
                                              N.stream_ptr(self.device)), "bank_enqueue")
 
-    def _k_contrast_fwd(self, fs0, fs1, probs, scalars):
+    def _k_contrast_fwd(self, fs0, fs1, probs, scalars, lambda_u: float = 1.0, lambda_c: float = 1.0):
+        """scalars: [loss_u (in), mask_mean, loss_contrast (out), total (out)]."""
         rows, D = fs0.shape
         stats = torch.empty(3, rows, dtype=torch.float32, device=self.device)
         ws, wsb = self._ws(rows)
         N.check(N.lib().b200ssl_contrast_fwd(fs0.data_ptr(), fs1.data_ptr(), probs.data_ptr(), rows, D,
                                              self.num_classes, N.dtype_enum(fs0), self.temperature, self.contrast_th,
-                                             stats.data_ptr(), scalars[2:].data_ptr(), ws, wsb,
+                                             stats.data_ptr(), scalars[2:].data_ptr(), scalars.data_ptr(), lambda_u,
+                                             lambda_c, scalars[3:].data_ptr(), ws, wsb,
                                              N.stream_ptr(self.device)), "contrast_fwd")
         return stats, scalars[2]
 
-    def _k_contrast_bwd(self, f0, f1, probs, stats, g_c):
+    def _k_contrast_bwd(self, f0, f1, probs, stats, g_c, factor: float = 1.0):
         g = g_c.detach().to(torch.float32).reshape(1).contiguous()
         gf0, gf1 = torch.empty_like(f0), torch.empty_like(f1)
         rows, D = f0.shape
         ws, wsb = self._ws(rows)
         N.check(N.lib().b200ssl_contrast_bwd(f0.data_ptr(), f1.data_ptr(), probs.data_ptr(), stats.data_ptr(), rows,
                                              D, self.num_classes, N.dtype_enum(f0), self.temperature, self.contrast_th,
-                                             g.data_ptr(), gf0.data_ptr(), gf1.data_ptr(), ws, wsb,
+                                             g.data_ptr(), factor, gf0.data_ptr(), gf1.data_ptr(), ws, wsb,
                                              N.stream_ptr(self.device)), "contrast_bwd")
         return gf0, gf1
 
-    def _k_scale(self, grad, g):
+    def _k_scale(self, grad, g, factor: float = 1.0):
         g = g.detach().to(torch.float32).reshape(1).contiguous()
-        N.check(N.lib().b200ssl_scale_inplace(grad.data_ptr(), grad.numel(), N.dtype_enum(grad), g.data_ptr(),
+        N.check(N.lib().b200ssl_scale_inplace(grad.data_ptr(), grad.numel(), N.dtype_enum(grad), g.data_ptr(), factor,
                                               N.stream_ptr(self.device)), "scale_inplace")
         return grad

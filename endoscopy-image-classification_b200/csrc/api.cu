@@ -38,7 +38,7 @@ extern "C" size_t b200ssl_workspace_bytes(int64_t rows, int32_t classes, int64_t
   const size_t da = sizeof(float) * (size_t)classes * kNumSMs;              // DA column partials
   if (da > need) need = da;
   const long long row_tiles = (rows + kTM - 1) / kTM;
-  const size_t contrast = sizeof(float) * (size_t)row_tiles;
+  const size_t contrast = sizeof(float) * contrast_workspace_floats(rows, B200SSL_MAX_EMB_DIM);
   if (contrast > need) need = contrast;
   if (bank_rows > 0) {
     int tps = 0;

@@ -4,11 +4,14 @@
 // Nothing of size [rows, rows] is ever written: each 64x64 tile of
 //   S = F0 F1^T (embedding similarity) and Qraw = probs probs^T (pseudo-label graph)
 // is recomputed from shared memory where it is needed.
-//   fwd : pass 1 -> rowsum_i = sum_j exp(S_ij/tau), qsum_i = sum_j Qm_ij
-//         pass 2 -> loss_i = -sum_j log(P_ij+1e-7) Qn_ij,  r_i = sum_j G_ij P_ij
-//   bwd : dZ = P o (G - r);  dF0 = dZ F1 / tau (row CTAs);  dF1 = dZ^T F0 / tau (column CTAs)
+//   stats : rowsum_i = sum_j exp(S_ij/tau), qsum_i = sum_j Qm_ij
+//   loss  : loss_i = -sum_j log(P_ij+1e-7) Qn_ij,  r_i = sum_j G_ij P_ij
+//   bwd   : dZ = P o (G - r);  dF0 = dZ F1 / tau (row CTAs);  dF1 = dZ^T F0 / tau (column CTAs)
 // with P = exp(S/tau)/rowsum, Qm = threshold(diag1(Qraw)), Qn = Qm/qsum,
 // G = -Qn/(P+1e-7)/rows.
+// Every kernel splits the streamed dimension over gridDim.y CTAs so that the
+// reference's sizes (rows = 448 -> 7 tiles) still fill the 148 SMs; the split
+// partials are folded by the last CTA of a tile in split order (deterministic).
 #include <math.h>
 
 #include "common.cuh"
@@ -19,10 +22,15 @@ namespace {
 
 struct ContrastParams {
   const void* f0; const void* f1; const float* probs;
-  long long rows; int D, C; float tau, th;
+  long long rows, rows_pad; int D, C; float tau, th;
   float* stats;              // [3][rows]: rowsum, qsum, r
-  float* out; float* partials; unsigned* ticket;
-  const float* upstream; void* g0; void* g1;
+  float* out;
+  float* part;               // split partials
+  unsigned* tile_tickets;    // per (kernel, tile) tickets
+  unsigned* grid_ticket; float* grid_part;
+  int nsplit, tiles_per_split;
+  const float* upstream; float factor; void* g0; void* g1;
+  const float* loss_u; float lambda_u, lambda_c; float* total_out;
 };
 
 __device__ __forceinline__ void load_probs_padded(const float* __restrict__ g, int rows_valid, int C, float* __restrict__ s) {
@@ -39,7 +47,26 @@ __device__ __forceinline__ float graph_weight(float qraw, bool diag, float th) {
   return (q >= th) ? q : 0.f;
 }
 
-template <typename T>
+// fold the 16 column lanes (tx) of a row
+__device__ __forceinline__ float fold16(float v) {
+#pragma unroll
+  for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// Last-arriving split CTA of a tile returns true (all partials visible).
+__device__ __forceinline__ bool tile_last(unsigned* ticket, int nsplit) {
+  __shared__ bool s_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = (atomicAdd(ticket, 1u) == (unsigned)nsplit - 1);
+  __syncthreads();
+  if (s_last) __threadfence();
+  return s_last;
+}
+
+// PASS 0: row statistics.  PASS 1: per-row loss and r (needs the statistics).
+template <typename T, int PASS>
 __global__ void __launch_bounds__(kTileThreads) contrast_fwd_kernel(const ContrastParams p) {
   extern __shared__ float smem[];
   const int D = p.D, C = p.C, ldd = D + 1, ldc = C + 1;
@@ -51,84 +78,113 @@ __global__ void __launch_bounds__(kTileThreads) contrast_fwd_kernel(const Contra
   const long long i0 = (long long)blockIdx.x * kTM;
   const int mrows = (int)min((long long)kTM, p.rows - i0);
   const long long ntiles = (p.rows + kTN - 1) / kTN;
+  const int split = blockIdx.y;
+  const long long jt0 = (long long)split * p.tiles_per_split, jt1 = min(ntiles, jt0 + p.tiles_per_split);
   load_tile_padded(static_cast<const T*>(p.f0) + i0 * D, mrows, kTM, D, ldd, As);
   load_probs_padded(p.probs + i0 * C, mrows, C, Pi);
 
-  float rs[4] = {0.f, 0.f, 0.f, 0.f}, qs[4] = {0.f, 0.f, 0.f, 0.f};
-  float li[4] = {0.f, 0.f, 0.f, 0.f}, rr[4] = {0.f, 0.f, 0.f, 0.f};
-  const float inv_rows = 1.0f / (float)p.rows;
-#pragma unroll 1
-  for (int pass = 0; pass < 2; ++pass) {
-    for (long long jt = 0; jt < ntiles; ++jt) {
-      const long long j0 = jt * kTN;
-      const int ncols = (int)min((long long)kTN, p.rows - j0);
-      __syncthreads();
-      load_tile_padded(static_cast<const T*>(p.f1) + j0 * D, ncols, kTN, D, ldd, Bs);
-      load_probs_padded(p.probs + j0 * C, ncols, C, Pj);
-      __syncthreads();
-      float s[4][4], q[4][4];
-      tile_dot_4x4(As, Bs, ldd, D, ty, tx, s);
-      tile_dot_4x4(Pi, Pj, ldc, C, ty, tx, q);
+  float a0[4] = {0.f, 0.f, 0.f, 0.f}, a1[4] = {0.f, 0.f, 0.f, 0.f};   // (rs, qs) or (loss, rr)
+  float rs[4], qs[4];
+  if (PASS == 1) {
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int col = tx + 16 * j;
-          if (col >= ncols) continue;
-          const float e = expf(__fdiv_rn(s[i][j], p.tau));                       // :200
-          const float qm = graph_weight(q[i][j], (i0 + ty + 16 * i) == (j0 + col), p.th);
-          if (pass == 0) {
-            rs[i] += e;
-            qs[i] += qm;
-          } else if (qm != 0.f) {
-            const float P = __fdiv_rn(e, rs[i]);                                 // :201
-            const float qn = __fdiv_rn(qm, qs[i]);                               // :209
-            li[i] -= logf(P + 1e-7f) * qn;                                       // :212
-            rr[i] += qn * __fdiv_rn(P, P + 1e-7f);
-          }
-        }
-    }
-    if (pass == 0) {
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int o = 8; o > 0; o >>= 1) {
-          rs[i] += __shfl_xor_sync(0xffffffffu, rs[i], o);
-          qs[i] += __shfl_xor_sync(0xffffffffu, qs[i], o);
-        }
+    for (int i = 0; i < 4; ++i) {
+      const int r = ty + 16 * i;
+      rs[i] = (r < mrows) ? p.stats[i0 + r] : 1.f;
+      qs[i] = (r < mrows) ? p.stats[p.rows + i0 + r] : 1.f;
     }
   }
-  float acc[1] = {0.f};
+  for (long long jt = jt0; jt < jt1; ++jt) {
+    const long long j0 = jt * kTN;
+    const int ncols = (int)min((long long)kTN, p.rows - j0);
+    __syncthreads();
+    load_tile_padded(static_cast<const T*>(p.f1) + j0 * D, ncols, kTN, D, ldd, Bs);
+    load_probs_padded(p.probs + j0 * C, ncols, C, Pj);
+    __syncthreads();
+    float s[4][4], q[4][4];
+    tile_dot_4x4(As, Bs, ldd, D, ty, tx, s);
+    tile_dot_4x4(Pi, Pj, ldc, C, ty, tx, q);
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < 4; ++i)
 #pragma unroll
-    for (int o = 8; o > 0; o >>= 1) {
-      li[i] += __shfl_xor_sync(0xffffffffu, li[i], o);
-      rr[i] += __shfl_xor_sync(0xffffffffu, rr[i], o);
-    }
-    const int r = ty + 16 * i;
-    if (tx == 0 && r < mrows) {
-      p.stats[i0 + r] = rs[i];
-      p.stats[p.rows + i0 + r] = qs[i];
-      p.stats[2 * p.rows + i0 + r] = -rr[i] * inv_rows;
-      acc[0] += li[i];
+      for (int j = 0; j < 4; ++j) {
+        const int col = tx + 16 * j;
+        if (col >= ncols) continue;
+        const float e = expf(__fdiv_rn(s[i][j], p.tau));                       // :200
+        const float qm = graph_weight(q[i][j], (i0 + ty + 16 * i) == (j0 + col), p.th);
+        if (PASS == 0) {
+          a0[i] += e;
+          a1[i] += qm;
+        } else if (qm != 0.f) {
+          const float P = __fdiv_rn(e, rs[i]);                                 // :201
+          const float qn = __fdiv_rn(qm, qs[i]);                               // :209
+          a0[i] -= logf(P + 1e-7f) * qn;                                       // :212
+          a1[i] += qn * __fdiv_rn(P, P + 1e-7f);
+        }
+      }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { a0[i] = fold16(a0[i]); a1[i] = fold16(a1[i]); }
+  // publish this split's partials: part[(pass*2+w)][split][rows_pad]
+  float* base = p.part + (size_t)(PASS * 2) * p.nsplit * p.rows_pad;
+  if (tx == 0) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int r = ty + 16 * i;
+      base[(size_t)split * p.rows_pad + i0 + r] = a0[i];
+      base[(size_t)(p.nsplit + split) * p.rows_pad + i0 + r] = a1[i];
     }
   }
-  // CTA sum -> grid sum (deterministic)
+  if (!tile_last(p.tile_tickets + PASS * gridDim.x + blockIdx.x, p.nsplit)) return;
+  float lsum[1] = {0.f};
+  for (int r = tid; r < mrows; r += blockDim.x) {
+    float t0 = 0.f, t1 = 0.f;
+    for (int s2 = 0; s2 < p.nsplit; ++s2) {
+      t0 += __ldcg(base + (size_t)s2 * p.rows_pad + i0 + r);
+      t1 += __ldcg(base + (size_t)(p.nsplit + s2) * p.rows_pad + i0 + r);
+    }
+    if (PASS == 0) {
+      p.stats[i0 + r] = t0;
+      p.stats[p.rows + i0 + r] = t1;
+    } else {
+      p.stats[2 * p.rows + i0 + r] = -t1 / (float)p.rows;
+      lsum[0] += t0;
+    }
+  }
+  if (tid == 0) p.tile_tickets[PASS * gridDim.x + blockIdx.x] = 0u;
+  if (PASS == 0) return;
+  // loss: sum over the rows of this tile, then over tiles (last tile-finisher folds, fixed order)
   __shared__ float s_w[kTileThreads / 32];
-  const float t = warp_sum(acc[0]);
+  const float t = warp_sum(lsum[0]);
   if ((tid & 31) == 0) s_w[tid >> 5] = t;
+  __syncthreads();
+  __shared__ bool s_glast;
+  if (tid == 0) {
+    float c = 0.f;
+    for (int w = 0; w < kTileThreads / 32; ++w) c += s_w[w];
+    p.grid_part[blockIdx.x] = c;
+    __threadfence();
+    s_glast = (atomicAdd(p.grid_ticket, 1u) == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!s_glast) return;
+  __threadfence();
+  float v = 0.f;
+  for (unsigned b = tid; b < gridDim.x; b += blockDim.x) v += __ldcg(p.grid_part + b);
+  v = warp_sum(v);
+  __syncthreads();
+  if ((tid & 31) == 0) s_w[tid >> 5] = v;
   __syncthreads();
   if (tid == 0) {
     float c = 0.f;
     for (int w = 0; w < kTileThreads / 32; ++w) c += s_w[w];
-    acc[0] = c;
+    const float lc = c / (float)p.rows;                                          // :213
+    p.out[0] = lc;
+    if (p.total_out) p.total_out[0] = p.lambda_u * (p.loss_u ? *p.loss_u : 0.f) + p.lambda_c * lc;  // :222
+    *p.grid_ticket = 0u;
   }
-  float total[1];
-  if (grid_reduce_last<1>(acc, p.partials, p.ticket, total) && tid == 0) p.out[0] = total[0] / (float)p.rows;  // :213
 }
 
-// grid = (tiles, 2): y==0 -> dF0 of row tile x ; y==1 -> dF1 of column tile x.
+// grid = (tiles, nsplit, 2): z==0 -> dF0 of row tile x ; z==1 -> dF1 of column tile x.
 template <typename T, int ND>
 __global__ void __launch_bounds__(kTileThreads) contrast_bwd_kernel(const ContrastParams p) {
   extern __shared__ float smem[];
@@ -140,10 +196,12 @@ __global__ void __launch_bounds__(kTileThreads) contrast_bwd_kernel(const Contra
   float* Zs = Pj + kTN * ldc;          // dZ tile [64][65]
   float* St = Zs + kTM * (kTN + 1);    // stats of the i rows: [3][64]
   const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
-  const bool colmode = blockIdx.y == 1;
+  const bool colmode = blockIdx.z == 1;
+  const int split = blockIdx.y;
   const long long own0 = (long long)blockIdx.x * kTM;
   const int nown = (int)min((long long)kTM, p.rows - own0);
   const long long ntiles = (p.rows + kTN - 1) / kTN;
+  const long long t0 = (long long)split * p.tiles_per_split, t1 = min(ntiles, t0 + p.tiles_per_split);
   const float inv_rows = 1.0f / (float)p.rows;
   if (!colmode) {
     load_tile_padded(static_cast<const T*>(p.f0) + own0 * D, nown, kTM, D, ldd, As);
@@ -161,7 +219,7 @@ __global__ void __launch_bounds__(kTileThreads) contrast_bwd_kernel(const Contra
   for (int m = 0; m < ND; ++m) acc[m] = 0.f;
   const int orow = tid & 63, dg = tid >> 6;
 
-  for (long long t = 0; t < ntiles; ++t) {
+  for (long long t = t0; t < t1; ++t) {
     const long long o0 = t * kTN;
     const int nother = (int)min((long long)kTN, p.rows - o0);
     __syncthreads();
@@ -220,15 +278,33 @@ __global__ void __launch_bounds__(kTileThreads) contrast_bwd_kernel(const Contra
       }
     }
   }
-  const float up = p.upstream ? *p.upstream : 1.f;
+  const float up = (p.upstream ? *p.upstream : 1.f) * p.factor;
   T* out = static_cast<T*>(colmode ? p.g1 : p.g0);
-  if (orow < nown) {
+  if (p.nsplit == 1) {
+    if (orow < nown) {
 #pragma unroll
-    for (int m = 0; m < ND; ++m) {
-      const int d = dg + 4 * m;
-      if (d < D) out[(own0 + orow) * D + d] = from_f32<T>(__fdiv_rn(acc[m], p.tau) * up);
+      for (int m = 0; m < ND; ++m) {
+        const int d = dg + 4 * m;
+        if (d < D) out[(own0 + orow) * D + d] = from_f32<T>(__fdiv_rn(acc[m], p.tau) * up);
+      }
     }
+    return;
   }
+  // split partials [mode][split][rows_pad][D] -> last split CTA of (mode, tile) folds them in order
+  float* base = p.part + (size_t)(colmode ? 1 : 0) * p.nsplit * p.rows_pad * D;
+#pragma unroll
+  for (int m = 0; m < ND; ++m) {
+    const int d = dg + 4 * m;
+    if (d < D) base[((size_t)split * p.rows_pad + own0 + orow) * D + d] = acc[m];
+  }
+  unsigned* ticket = p.tile_tickets + (2 + (colmode ? 1 : 0)) * gridDim.x + blockIdx.x;
+  if (!tile_last(ticket, p.nsplit)) return;
+  for (int e = tid; e < nown * D; e += blockDim.x) {
+    float t = 0.f;
+    for (int s2 = 0; s2 < p.nsplit; ++s2) t += __ldcg(base + ((size_t)s2 * p.rows_pad + own0) * D + e);
+    out[own0 * D + e] = from_f32<T>(__fdiv_rn(t, p.tau) * up);
+  }
+  if (tid == 0) *ticket = 0u;
 }
 
 int check_contrast(const char* fn, long long rows, int D, int C, int dtype, float tau) {
@@ -241,56 +317,97 @@ int check_contrast(const char* fn, long long rows, int D, int C, int dtype, floa
 }
 
 }  // namespace
+
+// number of CTAs the streamed dimension is split over (shared with api.cu workspace sizing)
+int contrast_nsplit(long long rows, int modes, int* tiles_per_split) {
+  const long long tiles = (rows + kTM - 1) / kTM;
+  long long want = (2 * kNumSMs + tiles * modes - 1) / (tiles * modes);
+  if (want < 1) want = 1;
+  if (want > tiles) want = tiles;
+  const long long tps = (tiles + want - 1) / want;
+  if (tiles_per_split) *tiles_per_split = (int)tps;
+  return (int)((tiles + tps - 1) / tps);
+}
+
+size_t contrast_workspace_floats(long long rows, int dim) {
+  const long long tiles = (rows + kTM - 1) / kTM;
+  const long long rows_pad = tiles * kTM;
+  const size_t fwd = (size_t)4 * contrast_nsplit(rows, 1, nullptr) * rows_pad;
+  const int nb = contrast_nsplit(rows, 2, nullptr);
+  const size_t bwd = nb > 1 ? (size_t)2 * nb * rows_pad * dim : 0;
+  return (size_t)tiles + (fwd > bwd ? fwd : bwd);
+}
+
 }  // namespace b200ssl
 
 using namespace b200ssl;
 
+static int contrast_setup(const char* fn, ContrastParams& p, int modes, void* workspace, size_t workspace_bytes) {
+  const long long tiles = (p.rows + kTM - 1) / kTM;
+  p.rows_pad = tiles * kTM;
+  p.nsplit = contrast_nsplit(p.rows, modes, &p.tiles_per_split);
+  if (!workspace || (reinterpret_cast<uintptr_t>(workspace) & 255u)) return fail(B200SSL_E_ALIGN, "%s: workspace NULL or not 256-byte aligned", fn);
+  const size_t need = kWsHeaderBytes + sizeof(float) * contrast_workspace_floats(p.rows, p.D);
+  if (workspace_bytes < need) return fail(B200SSL_E_WORKSPACE, "%s: workspace %zu < %zu bytes", fn, workspace_bytes, need);
+  if ((size_t)tiles * 4 * sizeof(unsigned) > kWsTicket2Bytes) return fail(B200SSL_E_SHAPE, "%s: too many row tiles", fn);
+  p.tile_tickets = reinterpret_cast<unsigned*>(static_cast<char*>(workspace) + kWsTicketBytes);
+  p.grid_ticket = reinterpret_cast<unsigned*>(workspace) + 4;
+  p.grid_part = reinterpret_cast<float*>(static_cast<char*>(workspace) + kWsHeaderBytes);
+  p.part = p.grid_part + tiles;
+  return 0;
+}
+
 extern "C" int b200ssl_contrast_fwd(const void* feats_s0, const void* feats_s1, const float* probs, int64_t rows,
                                     int32_t dim, int32_t classes, int32_t dtype, float temperature, float contrast_th,
-                                    float* stats, float* out_scalar, void* workspace, size_t workspace_bytes,
+                                    float* stats, float* out_scalar, const float* loss_u, float lambda_u,
+                                    float lambda_c, float* total_out, void* workspace, size_t workspace_bytes,
                                     void* stream) {
   const char* fn = "b200ssl_contrast_fwd";
   if (int e = check_contrast(fn, rows, dim, classes, dtype, temperature)) return e;
   if (!feats_s0 || !feats_s1 || !probs || !stats || !out_scalar) return fail(B200SSL_E_NULL, "%s: NULL tensor", fn);
-  const long long tiles = (rows + kTM - 1) / kTM;
-  const size_t need = kWsHeaderBytes + sizeof(float) * (size_t)tiles;
-  if (!workspace || (reinterpret_cast<uintptr_t>(workspace) & 255u)) return fail(B200SSL_E_ALIGN, "%s: workspace NULL or not 256-byte aligned", fn);
-  if (workspace_bytes < need) return fail(B200SSL_E_WORKSPACE, "%s: workspace %zu < %zu bytes", fn, workspace_bytes, need);
   ContrastParams p{};
   p.f0 = feats_s0; p.f1 = feats_s1; p.probs = probs; p.rows = rows; p.D = dim; p.C = classes;
   p.tau = temperature; p.th = contrast_th; p.stats = stats; p.out = out_scalar;
-  p.partials = reinterpret_cast<float*>(static_cast<char*>(workspace) + kWsHeaderBytes);
-  p.ticket = reinterpret_cast<unsigned*>(workspace) + 4;
+  p.loss_u = loss_u; p.lambda_u = lambda_u; p.lambda_c = lambda_c; p.total_out = total_out;
+  if (int e = contrast_setup(fn, p, 1, workspace, workspace_bytes)) return e;
+  const long long tiles = (rows + kTM - 1) / kTM;
   const size_t smem = ((size_t)(kTM + kTN) * (dim + 1) + (size_t)(kTM + kTN) * (classes + 1)) * sizeof(float);
+  dim3 grid((unsigned)tiles, (unsigned)p.nsplit);
   cudaError_t e = cudaSuccess;
-  if (dtype == B200SSL_F32) {
-    auto k = contrast_fwd_kernel<float>;
-    if (smem > 48 * 1024) e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e == cudaSuccess) k<<<(unsigned)tiles, kTileThreads, smem, as_stream(stream)>>>(p);
-  } else {
-    auto k = contrast_fwd_kernel<__nv_bfloat16>;
-    if (smem > 48 * 1024) e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e == cudaSuccess) k<<<(unsigned)tiles, kTileThreads, smem, as_stream(stream)>>>(p);
-  }
+#define LAUNCH_FWD(T)                                                                                          \
+  do {                                                                                                         \
+    auto k0 = contrast_fwd_kernel<T, 0>;                                                                       \
+    auto k1 = contrast_fwd_kernel<T, 1>;                                                                       \
+    if (smem > 48 * 1024) {                                                                                    \
+      e = cudaFuncSetAttribute(k0, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                    \
+      if (e == cudaSuccess) e = cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+    }                                                                                                          \
+    if (e == cudaSuccess) {                                                                                    \
+      k0<<<grid, kTileThreads, smem, as_stream(stream)>>>(p);                                                  \
+      k1<<<grid, kTileThreads, smem, as_stream(stream)>>>(p);                                                  \
+    }                                                                                                          \
+  } while (0)
+  if (dtype == B200SSL_F32) LAUNCH_FWD(float); else LAUNCH_FWD(__nv_bfloat16);
+#undef LAUNCH_FWD
   if (e != cudaSuccess) return fail((int)e, "%s: cudaFuncSetAttribute: %s", fn, cudaGetErrorString(e));
   return check_launch(fn);
 }
 
 extern "C" int b200ssl_contrast_bwd(const void* feats_s0, const void* feats_s1, const float* probs, const float* stats,
                                     int64_t rows, int32_t dim, int32_t classes, int32_t dtype, float temperature,
-                                    float contrast_th, const float* upstream, void* grad_f0, void* grad_f1,
+                                    float contrast_th, const float* upstream, float factor, void* grad_f0, void* grad_f1,
                                     void* workspace, size_t workspace_bytes, void* stream) {
   const char* fn = "b200ssl_contrast_bwd";
-  (void)workspace; (void)workspace_bytes;
   if (int e = check_contrast(fn, rows, dim, classes, dtype, temperature)) return e;
   if (!feats_s0 || !feats_s1 || !probs || !stats || !grad_f0 || !grad_f1) return fail(B200SSL_E_NULL, "%s: NULL tensor", fn);
   ContrastParams p{};
   p.f0 = feats_s0; p.f1 = feats_s1; p.probs = probs; p.rows = rows; p.D = dim; p.C = classes;
   p.tau = temperature; p.th = contrast_th; p.stats = const_cast<float*>(stats);
-  p.upstream = upstream; p.g0 = grad_f0; p.g1 = grad_f1;
+  p.upstream = upstream; p.factor = factor; p.g0 = grad_f0; p.g1 = grad_f1;
+  if (int e = contrast_setup(fn, p, 2, workspace, workspace_bytes)) return e;
   const long long tiles = (rows + kTM - 1) / kTM;
   const size_t smem = ((size_t)(kTM + kTN) * (dim + 1) + (size_t)(kTM + kTN) * (classes + 1) + kTM * (kTN + 1) + 3 * kTM) * sizeof(float);
-  dim3 grid((unsigned)tiles, 2);
+  dim3 grid((unsigned)tiles, (unsigned)p.nsplit, 2);
   cudaError_t e = cudaSuccess;
 #define LAUNCH_BWD(T, ND)                                                                                    \
   do {                                                                                                       \

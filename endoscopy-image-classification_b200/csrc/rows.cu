@@ -487,8 +487,8 @@ __global__ void __launch_bounds__(kRowThreads) comatch_finalize_kernel(const Fin
 
 // ---- grad *= *scale -----------------------------------------------------------
 template <typename T>
-__global__ void scale_kernel(T* g, long long n, const float* scale) {
-  const float sc = *scale;
+__global__ void scale_kernel(T* g, long long n, const float* scale, float factor) {
+  const float sc = *scale * factor;
   constexpr int N = Vec16<T>::N;
   const long long nvec = ((reinterpret_cast<uintptr_t>(g) & 15u) == 0) ? n / N : 0;
   const long long stride = (long long)gridDim.x * blockDim.x;
@@ -650,7 +650,8 @@ extern "C" int b200ssl_comatch_finalize(const void* logits_u_w, const void* logi
   return check_launch(fn);
 }
 
-extern "C" int b200ssl_scale_inplace(void* grad, int64_t numel, int32_t dtype, const float* scale, void* stream) {
+extern "C" int b200ssl_scale_inplace(void* grad, int64_t numel, int32_t dtype, const float* scale, float factor,
+                                     void* stream) {
   const char* fn = "b200ssl_scale_inplace";
   if (!grad || !scale) return fail(B200SSL_E_NULL, "%s: NULL pointer", fn);
   if (numel <= 0) return fail(B200SSL_E_SHAPE, "%s: numel must be > 0", fn);
@@ -658,8 +659,8 @@ extern "C" int b200ssl_scale_inplace(void* grad, int64_t numel, int32_t dtype, c
   long long blocks = (numel / 4 + threads - 1) / threads;
   if (blocks < 1) blocks = 1;
   if (blocks > 8 * kNumSMs) blocks = 8 * kNumSMs;
-  if (dtype == B200SSL_F32) scale_kernel<float><<<(int)blocks, threads, 0, as_stream(stream)>>>(static_cast<float*>(grad), numel, scale);
-  else if (dtype == B200SSL_BF16) scale_kernel<__nv_bfloat16><<<(int)blocks, threads, 0, as_stream(stream)>>>(static_cast<__nv_bfloat16*>(grad), numel, scale);
+  if (dtype == B200SSL_F32) scale_kernel<float><<<(int)blocks, threads, 0, as_stream(stream)>>>(static_cast<float*>(grad), numel, scale, factor);
+  else if (dtype == B200SSL_BF16) scale_kernel<__nv_bfloat16><<<(int)blocks, threads, 0, as_stream(stream)>>>(static_cast<__nv_bfloat16*>(grad), numel, scale, factor);
   else return fail(B200SSL_E_DTYPE, "%s: dtype %d", fn, dtype);
   return check_launch(fn);
 }

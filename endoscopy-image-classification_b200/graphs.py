@@ -51,15 +51,18 @@ class GraphedStep:
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
             self.result = step_fn(self.static).detach().reshape(1).float()
+        # gradients the captured backward writes (static buffers of THIS graph)
+        self.grads = {k: v.grad for k, v in self.static.items() if v.grad is not None}
         self._note()
         self.graph_host = None
         if capture_host_io:
             self.graph_host = torch.cuda.CUDAGraph()
             with torch.cuda.graph(self.graph_host, pool=self.graph.pool()):
                 for k, v in self.static.items():
-                    v.copy_(self.staging[k], non_blocking=True)
+                    v.detach().copy_(self.staging[k], non_blocking=True)   # leaves may require grad
                 res = step_fn(self.static).detach().reshape(1).float()
                 self.result_host.copy_(res, non_blocking=True)
+            self.grads_host = {k: v.grad for k, v in self.static.items() if v.grad is not None}
             self._note()
         torch.cuda.synchronize(self.device)
         if after_capture is not None:

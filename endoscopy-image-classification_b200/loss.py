@@ -57,6 +57,7 @@ class _FixMatchHead(torch.autograd.Function):
             out.data_ptr(), N.ptr(idx), N.ptr(mask), ws, ws_bytes, N.stream_ptr(dev)), "fixmatch_head_fwd_bwd")
         ctx.save_for_backward(grad_s, grad_s2)
         ctx.has_s2 = s2 is not None
+        ctx.set_materialize_grads(False)
         ctx.mark_non_differentiable(*(t for t in (idx, mask) if t is not None))
         return out[0], out[1], out[2], idx, mask
 
@@ -74,7 +75,7 @@ class _FixMatchHead(torch.autograd.Function):
             g = g.detach().to(torch.float32).reshape(1).contiguous()
             # in place: the stash is consumed exactly once by the first backward
             N.check(lib.b200ssl_scale_inplace(stash.data_ptr(), stash.numel(), N.dtype_enum(stash),
-                                              g.data_ptr(), N.stream_ptr(dev)), "scale_inplace")
+                                              g.data_ptr(), 1.0, N.stream_ptr(dev)), "scale_inplace")
             return stash
 
         gs = chain(grad_s, g_loss) if ctx.needs_input_grad[1] else None
@@ -152,7 +153,7 @@ class _LabeledCE(torch.autograd.Function):
     def backward(ctx, g):
         (grad,) = ctx.saved_tensors
         g = g.detach().to(torch.float32).reshape(1).contiguous()
-        N.check(N.lib().b200ssl_scale_inplace(grad.data_ptr(), grad.numel(), N.dtype_enum(grad), g.data_ptr(),
+        N.check(N.lib().b200ssl_scale_inplace(grad.data_ptr(), grad.numel(), N.dtype_enum(grad), g.data_ptr(), 1.0,
                                               N.stream_ptr(grad.device)), "scale_inplace")
         return grad, None, None, None, None
 

@@ -81,9 +81,11 @@ B200SSL_API int b200ssl_fixmatch_head_fwd_bwd(const void* logits_w, const void* 
                                   float* out_scalars, int64_t* idx, float* mask, void* workspace,
                                   size_t workspace_bytes, void* stream);
 
-/* grad[i] *= *scale  -- chains the stashed gradient with autograd's upstream
- * gradient (a device scalar, e.g. LAMBDA_U at code/fixmatch.py:118). */
-B200SSL_API int b200ssl_scale_inplace(void* grad, int64_t numel, int32_t dtype, const float* scale, void* stream);
+/* grad[i] *= (*scale) * factor  -- chains the stashed gradient with autograd's
+ * upstream gradient (device scalar) and a host constant (e.g. LAMBDA_U at
+ * code/fixmatch.py:118). */
+B200SSL_API int b200ssl_scale_inplace(void* grad, int64_t numel, int32_t dtype, const float* scale, float factor,
+                                      void* stream);
 
 /* ------------------------------------------------------------ f2 (next) --
  * Labeled-branch criterion: class-weighted CE or Poly-1 CE, forward+backward.
@@ -171,17 +173,21 @@ B200SSL_API int b200ssl_bank_enqueue(void* queue_feats, void* queue_probs, const
  * backward (closed form):
  *   P = rowsoftmax-without-max(F0 F1^T / tau);  Q = probs probs^T, diag 1,
  *   thresholded at contrast_th, row-normalised;  loss = mean_i(-sum_j log(P+1e-7) Q)
- * fwd writes loss to out_scalar[0] and row statistics (rowsum, qsum, r) into
+ * fwd writes loss to out_scalar[0]; when total_out != NULL it also writes
+ * total_out[0] = lambda_u * loss_u[0] + lambda_c * loss (comatch.py:222 without
+ * loss_x; loss_u is the device scalar produced by b200ssl_comatch_finalize).
+ * fwd also stores the row statistics (rowsum, qsum, r) into
  * stats f32[3*rows]; bwd consumes them and writes grad_f0 / grad_f1 scaled by
- * *upstream (device scalar, NULL => 1).
+ * (*upstream) * factor (upstream: device scalar from autograd, NULL => 1; factor:
+ * host constant such as LAMBDA_C of comatch.py:222).
  */
 B200SSL_API int b200ssl_contrast_fwd(const void* feats_s0, const void* feats_s1, const float* probs, int64_t rows,
                          int32_t dim, int32_t classes, int32_t dtype, float temperature, float contrast_th,
-                         float* stats, float* out_scalar, void* workspace, size_t workspace_bytes,
-                         void* stream);
+                         float* stats, float* out_scalar, const float* loss_u, float lambda_u, float lambda_c,
+                         float* total_out, void* workspace, size_t workspace_bytes, void* stream);
 B200SSL_API int b200ssl_contrast_bwd(const void* feats_s0, const void* feats_s1, const float* probs, const float* stats,
                          int64_t rows, int32_t dim, int32_t classes, int32_t dtype, float temperature,
-                         float contrast_th, const float* upstream, void* grad_f0, void* grad_f1,
+                         float contrast_th, const float* upstream, float factor, void* grad_f0, void* grad_f1,
                          void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---------------------------------------------------------------- K8 ----

@@ -55,7 +55,7 @@ def test_version_and_workspace(native):
     assert lib.b200ssl_version() == 100
     small = lib.b200ssl_workspace_bytes(448, 23, 2560)
     big = lib.b200ssl_workspace_bytes(14336, 23, 65536)
-    assert 256 + 65536 < small <= big and small % 256 == 0
+    assert 256 + 65536 < small and 256 + 65536 < big and small % 256 == 0 and big % 256 == 0
 
 
 def test_argument_validation_without_gpu(native):
@@ -81,11 +81,11 @@ def test_argument_validation_without_gpu(native):
     assert lib.b200ssl_bank_enqueue(p, p, p, p, p, p, 4, 4, 64, 23, 0, 100, None, 0, 0, 64, 0, 64, None) == E_ARG  # ptr >= K
     assert lib.b200ssl_bank_enqueue(p, p, p, p, p, p, 4, 4, 64, 23, 0, 0, None, 0, 0, 64, 32, 64, None) == E_ARG   # shard outside
     assert lib.b200ssl_bank_enqueue(p, p, p, p, p, p, 4, 4, 64, 23, 0, 0, None, 8, 0, 64, 0, 64, None) == E_ARG    # advance w/o state
-    assert lib.b200ssl_contrast_fwd(p, p, p, 16, 64, 500, 0, 0.2, 0.8, p, p, p256, wsb, None) == E_SHAPE
+    assert lib.b200ssl_contrast_fwd(p, p, p, 16, 64, 500, 0, 0.2, 0.8, p, p, None, 1.0, 1.0, None, p256, wsb, None) == E_SHAPE
     assert lib.b200ssl_ema_multi_tensor(None, 4, 0, 1, 0.999, 0.001, 0, None) == E_NULL
     assert lib.b200ssl_ema_multi_tensor(p256, 4, 3, 1, 0.999, 0.001, 0, None) == E_DTYPE
     assert lib.b200ssl_ema_multi_tensor(p256, 4, 0, 1, 0.999, 0.001, 7, None) == E_ARG
-    assert lib.b200ssl_scale_inplace(None, 4, 0, p, None) == E_NULL
+    assert lib.b200ssl_scale_inplace(None, 4, 0, p, 1.0, None) == E_NULL
 
 
 def test_product_has_no_cpu_fallback_and_no_oracle_import(native):

@@ -321,8 +321,17 @@ def test_comatch_head_always_mode_vs_oracle(pkg, B, MU, D, qbatches, dtype):
         din = {k: v.cuda() for k, v in inp.items()}
         for k in ("logits_u_s0", "feats_u_s0", "feats_u_s1"):
             din[k].requires_grad_(True)
-        loss_u, loss_c, mask_mean, mask, lbs, scores, probs = head(**din)
-        (loss_u + loss_c).backward()
+        if step % 2 == 0:
+            loss_u, loss_c, mask_mean, mask, lbs, scores, probs = head(**din)
+            (loss_u + loss_c).backward()
+        else:                                   # fused weighting (comatch.py:222), undone below
+            total, loss_u, loss_c, mask_mean = head.total_loss(**din, lambda_u=2.0, lambda_c=0.5)
+            total.backward()
+            assert rel_err(total, 2.0 * loss_u + 0.5 * loss_c) < 1e-6
+            din["logits_u_s0"].grad.mul_(0.5)
+            din["feats_u_s0"].grad.mul_(2.0)
+            din["feats_u_s1"].grad.mul_(2.0)
+            probs, mask, lbs = head.last["probs"], head.last["mask"], head.last["lbs"]
         assert head.queue_ptr == state.queue_ptr
         assert torch.equal(head.queue_feats.float().cpu(), state.queue_feats)
         assert rel_err(head.queue_probs.float(), state.queue_probs) < tol
@@ -442,8 +451,7 @@ def test_graphed_step_matches_eager(pkg):
         for k in ("logits_u_s0", "feats_u_s0", "feats_u_s1"):
             batch[k].grad = None
             batch[k].requires_grad_(True)
-        lu, lc = head(**batch)[:2]
-        total = 2.0 * lu + 2.0 * lc
+        total, lu, lc, mm = head.total_loss(**batch, lambda_u=2.0, lambda_c=2.0)
         total.backward()
         ema.update(net)
         return total
@@ -469,12 +477,12 @@ def test_graphed_step_matches_eager(pkg):
         if i % 2 == 0:
             for k in keys:
                 gs.static[k].detach().copy_(b[k].cuda())
-            val = float(gs.replay())
+            val, grads = float(gs.replay()), gs.grads
         else:
-            val = gs.replay_host(b)
+            val, grads = gs.replay_host(b), gs.grads_host
         assert val == eager[i][0]
-        assert torch.equal(gs.static["feats_u_s0"].grad, eager[i][1])
-        assert torch.equal(gs.static["logits_u_s0"].grad, eager[i][2])
+        assert torch.equal(grads["feats_u_s0"], eager[i][1])
+        assert torch.equal(grads["logits_u_s0"], eager[i][2])
     torch.cuda.synchronize()
     assert head_g.queue_ptr == head_e.queue_ptr == int(head_g.ptr_state[0]) == int(head_e.ptr_state[0])
     assert torch.equal(head_g.queue_feats, head_e.queue_feats) and torch.equal(head_g.queue_probs, head_e.queue_probs)
