@@ -129,6 +129,10 @@ class CoMatchHead:
         self.dtype = dtype
         self.queue_feats = torch.zeros(self.geom.shard_rows, self.low_dim, dtype=dtype, device=self.device)
         self.queue_probs = torch.zeros(self.geom.shard_rows, self.num_classes, dtype=dtype, device=self.device)
+        # transposed, class-padded copy [32, K_local] for the tensor-core smoothing kernel (bf16 banks)
+        self.queue_probs_t = None
+        if dtype == torch.bfloat16 and self.num_classes <= 32 and self.low_dim == 64 and self.geom.shard_rows % 8 == 0:
+            self.queue_probs_t = torch.zeros(32, self.geom.shard_rows, dtype=dtype, device=self.device)
 
     # ---- reference-visible state ------------------------------------------------
     @property
@@ -174,6 +178,8 @@ class CoMatchHead:
             self._alloc_bank(sd["queue_feats"].dtype)      # keep pointing at the same storage
         self.queue_feats.copy_(sd["queue_feats"])
         self.queue_probs.copy_(sd["queue_probs"])
+        if self.queue_probs_t is not None:
+            self.queue_probs_t[: self.num_classes].copy_(self.queue_probs.t())
         self.queue_ptr = int(sd["queue_ptr"])
         self.da_ring.copy_(sd["da_ring"])
         self.da_state.copy_(sd["da_state"])
@@ -262,7 +268,7 @@ class CoMatchHead:
         numer = torch.empty(rows, C, dtype=torch.float32, device=self.device)
         ws, wsb = self._ws(rows)
         N.check(N.lib().b200ssl_bank_smooth_partial(queries.data_ptr(), self.queue_feats.data_ptr(),
-                                                    self.queue_probs.data_ptr(), rows, self.geom.shard_rows, D, C,
+                                                    self.queue_probs.data_ptr(), N.ptr(self.queue_probs_t), rows, self.geom.shard_rows, D, C,
                                                     N.dtype_enum(queries), self.temperature, rowsum.data_ptr(),
                                                     numer.data_ptr(), ws, wsb, N.stream_ptr(self.device)),
                 "bank_smooth_partial")
@@ -288,7 +294,8 @@ class CoMatchHead:
     def _k_enqueue(self, fw, fx, probs_orig, tx, block_offset: int, advance: int) -> None:
         g = self.geom
         fw, fx, probs_orig, tx = (t.contiguous() for t in (fw, fx, probs_orig, tx))
-        N.check(N.lib().b200ssl_bank_enqueue(self.queue_feats.data_ptr(), self.queue_probs.data_ptr(), fw.data_ptr(),
+        N.check(N.lib().b200ssl_bank_enqueue(self.queue_feats.data_ptr(), self.queue_probs.data_ptr(),
+                                             N.ptr(self.queue_probs_t), fw.data_ptr(),
                                              fx.data_ptr(), probs_orig.data_ptr(), tx.data_ptr(), fw.shape[0],
                                              fx.shape[0], self.low_dim, self.num_classes, N.dtype_enum(fw),
                                              0, self.ptr_state.data_ptr(), advance, block_offset, g.queue_size,

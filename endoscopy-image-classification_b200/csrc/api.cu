@@ -45,6 +45,8 @@ extern "C" size_t b200ssl_workspace_bytes(int64_t rows, int32_t classes, int64_t
     const int nsplit = smooth_nsplit(rows, bank_rows, &tps);
     const size_t sm = nsplit > 1 ? (size_t)nsplit * row_tiles * kTM * (1 + classes) * sizeof(float) : 0;
     if (sm > need) need = sm;
+    const size_t tc = sizeof(float) * smooth_tc_workspace_floats(rows, bank_rows, classes);
+    if (tc > need) need = tc;
   }
   return kWsHeaderBytes + ((need + 255) & ~(size_t)255);
 }

@@ -126,6 +126,7 @@ __global__ void __launch_bounds__(kTileThreads) bank_smooth_simt_kernel(const Sm
 
 // ---- K5 --------------------------------------------------------------------------
 struct EnqueueParams {
+  void* qpt;  // optional transposed, class-padded copy [32][shard_rows] (tensor-core path)
   void* qf; void* qp; const void* fu; const void* fx; const float* po; const long long* tx;
   long long n_u, n_x; int D, C;
   long long ptr, block_offset, K, shard_begin, shard_rows;
@@ -161,12 +162,13 @@ __global__ void __launch_bounds__(256) bank_enqueue_kernel(const EnqueueParams p
   T* df = static_cast<T*>(p.qf) + local * p.D;
   for (int d = lane; d < p.D; d += 32) df[d] = src[d];
   T* dp = static_cast<T*>(p.qp) + local * p.C;
-  if (lab) {
-    const int y = (int)p.tx[r - p.n_u];                     // one-hot (:188)
-    for (int c = lane; c < p.C; c += 32) dp[c] = from_f32<T>(c == y ? 1.f : 0.f);
-  } else {
-    const float* sp = p.po + r * p.C;                       // probs_orig (:189)
-    for (int c = lane; c < p.C; c += 32) dp[c] = from_f32<T>(sp[c]);
+  T* dt = p.qpt ? static_cast<T*>(p.qpt) + local : nullptr;
+  const int y = lab ? (int)p.tx[r - p.n_u] : -1;            // one-hot (:188)
+  const float* sp = lab ? nullptr : p.po + r * p.C;         // probs_orig (:189)
+  for (int c = lane; c < p.C; c += 32) {
+    const T v = from_f32<T>(lab ? (c == y ? 1.f : 0.f) : sp[c]);
+    dp[c] = v;
+    if (dt) dt[(size_t)c * p.shard_rows] = v;
   }
 }
 
@@ -190,8 +192,14 @@ int smooth_nsplit(long long rows, long long bank_rows, int* tiles_per_split) {
 
 using namespace b200ssl;
 
+namespace b200ssl {
+int bank_smooth_tc(const void* feats, const void* queue_feats, const void* queue_probs_t, long long rows,
+                   long long bank_rows, int classes, float temperature, float* rowsum, float* numer, void* workspace,
+                   size_t workspace_bytes, cudaStream_t stream);
+}
+
 extern "C" int b200ssl_bank_smooth_partial(const void* feats_u_w, const void* queue_feats, const void* queue_probs,
-                                           int64_t rows, int64_t bank_rows, int32_t dim, int32_t classes,
+                                           const void* queue_probs_t, int64_t rows, int64_t bank_rows, int32_t dim, int32_t classes,
                                            int32_t dtype, float temperature, float* rowsum, float* numer,
                                            void* workspace, size_t workspace_bytes, void* stream) {
   const char* fn = "b200ssl_bank_smooth_partial";
@@ -202,6 +210,12 @@ extern "C" int b200ssl_bank_smooth_partial(const void* feats_u_w, const void* qu
   if (!(temperature > 0.f)) return fail(B200SSL_E_ARG, "%s: temperature must be > 0", fn);
   if (dtype != B200SSL_F32 && dtype != B200SSL_BF16) return fail(B200SSL_E_DTYPE, "%s: dtype %d", fn, dtype);
   if (!workspace || (reinterpret_cast<uintptr_t>(workspace) & 255u)) return fail(B200SSL_E_ALIGN, "%s: workspace NULL or not 256-byte aligned", fn);
+  // bf16 bank with 128-byte rows: tcgen05 / TMEM / TMA kernel (bank_tc.cu); everything else: exact-fp32 FFMA tiles
+  if (dtype == B200SSL_BF16 && dim == 64 && classes <= 32 && queue_probs_t && bank_rows % 8 == 0 &&
+      !(reinterpret_cast<uintptr_t>(feats_u_w) & 15u) && !(reinterpret_cast<uintptr_t>(queue_feats) & 15u) &&
+      !(reinterpret_cast<uintptr_t>(queue_probs_t) & 15u))
+    return bank_smooth_tc(feats_u_w, queue_feats, queue_probs_t, rows, bank_rows, classes, temperature, rowsum, numer,
+                          workspace, workspace_bytes, as_stream(stream));
   SmoothParams p{};
   p.f = feats_u_w; p.qf = queue_feats; p.qp = queue_probs;
   p.rows = rows; p.bank_rows = bank_rows; p.D = dim; p.C = classes; p.tau = temperature;
@@ -233,7 +247,8 @@ extern "C" int b200ssl_bank_smooth_partial(const void* feats_u_w, const void* qu
   return check_launch(fn);
 }
 
-extern "C" int b200ssl_bank_enqueue(void* queue_feats, void* queue_probs, const void* feats_u_w, const void* feats_x,
+extern "C" int b200ssl_bank_enqueue(void* queue_feats, void* queue_probs, void* queue_probs_t, const void* feats_u_w,
+                                    const void* feats_x,
                                     const float* probs_orig, const int64_t* targets_x, int64_t n_u, int64_t n_x,
                                     int32_t dim, int32_t classes, int32_t dtype, int64_t ptr, int64_t* ptr_state,
                                     int64_t advance, int64_t block_offset, int64_t bank_rows_global,
@@ -248,7 +263,8 @@ extern "C" int b200ssl_bank_enqueue(void* queue_feats, void* queue_probs, const 
       shard_rows <= 0 || shard_begin + shard_rows > bank_rows_global)
     return fail(B200SSL_E_ARG, "%s: bad ring geometry (K=%lld ptr=%lld off=%lld shard=[%lld,+%lld))", fn,
                 (long long)bank_rows_global, (long long)ptr, (long long)block_offset, (long long)shard_begin, (long long)shard_rows);
-  EnqueueParams p{queue_feats, queue_probs, feats_u_w, feats_x, probs_orig, reinterpret_cast<const long long*>(targets_x),
+  if (queue_probs_t && classes > 32) return fail(B200SSL_E_SHAPE, "%s: transposed bank needs classes <= 32", fn);
+  EnqueueParams p{queue_probs_t, queue_feats, queue_probs, feats_u_w, feats_x, probs_orig, reinterpret_cast<const long long*>(targets_x),
                   n_u, n_x, dim, classes, ptr, block_offset, bank_rows_global, shard_begin, shard_rows,
                   reinterpret_cast<long long*>(ptr_state), advance};
   const long long n = n_u + n_x;

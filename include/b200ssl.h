@@ -120,9 +120,15 @@ B200SSL_API int b200ssl_comatch_da(const void* logits_u_w, int64_t rows, int32_t
  *   numer[i,c]  = sum_k exp(<f_i, q_k> / temperature) * queue_probs[k,c]
  * feats / queue_* share `dtype`; rowsum/numer are fp32.  No running max (the
  * reference has none; |<f,q>|/tau <= 5 for unit-norm embeddings).
+ * Two code paths, chosen by storage type (not a backend switch):
+ *   - bf16 bank, dim == 64, classes <= 32, bank_rows % 8 == 0 and queue_probs_t
+ *     given (bf16 [32, bank_rows]: transposed, class-padded copy of queue_probs
+ *     maintained by b200ssl_bank_enqueue): tcgen05.mma with TMEM accumulators,
+ *     operands staged by TMA (csrc/bank_tc.cu);
+ *   - otherwise exact-fp32 FFMA tiles (the reference's torch.mm is true fp32).
  */
 B200SSL_API int b200ssl_bank_smooth_partial(const void* feats_u_w, const void* queue_feats, const void* queue_probs,
-                                int64_t rows, int64_t bank_rows, int32_t dim, int32_t classes,
+                                const void* queue_probs_t, int64_t rows, int64_t bank_rows, int32_t dim, int32_t classes,
                                 int32_t dtype, float temperature, float* rowsum, float* numer,
                                 void* workspace, size_t workspace_bytes, void* stream);
 
@@ -156,13 +162,16 @@ B200SSL_API int b200ssl_comatch_finalize(const void* logits_u_w, const void* log
  * into the local shard [shard_begin, shard_begin+shard_rows) are written (the
  * whole bank for shard_begin=0, shard_rows=bank_rows_global).  `block_offset`
  * is this block's row offset inside a multi-rank step (rank * n), 0 otherwise.
+ * queue_probs_t (optional, may be NULL) is the transposed class-padded copy
+ * [32, shard_rows] read by the tensor-core smoothing kernel.
  * The write pointer is either the host value `ptr` (ptr_state == NULL) or, for
  * CUDA-graph replay, device resident: ptr_state = int64[2] {write pointer, ticket
  * (zero-initialised)}; the kernel then ignores `ptr`, and after all rows are
  * written advances the device pointer by `advance` rows mod K (0 = leave it, for
  * all but the last block of a multi-rank step).
  */
-B200SSL_API int b200ssl_bank_enqueue(void* queue_feats, void* queue_probs, const void* feats_u_w, const void* feats_x,
+B200SSL_API int b200ssl_bank_enqueue(void* queue_feats, void* queue_probs, void* queue_probs_t, const void* feats_u_w,
+                         const void* feats_x,
                          const float* probs_orig, const int64_t* targets_x, int64_t n_u, int64_t n_x,
                          int32_t dim, int32_t classes, int32_t dtype, int64_t ptr, int64_t* ptr_state,
                          int64_t advance, int64_t block_offset, int64_t bank_rows_global,

@@ -418,7 +418,7 @@ def test_enqueue_kernel_matches_segment_plan(pkg):
         qp = torch.zeros(geom.shard_rows, C, device="cuda")
         for r, b in enumerate(blocks):
             fu, fx, po, tx = (b[k].cuda() for k in ("fu", "fx", "po", "tx"))
-            N.check(lib.b200ssl_bank_enqueue(qf.data_ptr(), qp.data_ptr(), fu.data_ptr(), fx.data_ptr(), po.data_ptr(),
+            N.check(lib.b200ssl_bank_enqueue(qf.data_ptr(), qp.data_ptr(), None, fu.data_ptr(), fx.data_ptr(), po.data_ptr(),
                                              tx.data_ptr(), n_u, n_x, D, C, N.F32, ptr, None, 0, r * n, K, geom.shard_begin,
                                              geom.shard_rows, N.stream_ptr(qf.device)))
         lo = geom.shard_begin
@@ -489,3 +489,28 @@ def test_graphed_step_matches_eager(pkg):
     assert torch.equal(head_g.da_ring, head_e.da_ring) and torch.equal(head_g.da_state, head_e.da_state)
     for a, b in zip(ema_g.ema.state_dict().values(), ema_e.ema.state_dict().values()):
         assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize("rows,K", [(448, 2560), (100, 80), (1, 8), (130, 4104), (14336, 2560), (448, 65536), (3000, 16384)])
+def test_bank_smooth_tcgen05_bf16(pkg, rows, K):
+    """bf16 bank, D=64: the tcgen05/TMEM/TMA kernel (csrc/bank_tc.cu) against fp64 math on the same
+    bf16-rounded operands; includes ragged rows/keys, one-tile CTAs and multi-tile pipelines."""
+    D = 64
+    g = torch.Generator().manual_seed(rows * 3 + K)
+    nf = lambda n: torch.nn.functional.normalize(torch.randn(n, D, generator=g), dim=1).to(torch.bfloat16)
+    f, qf = nf(rows), nf(K)
+    qp = torch.softmax(2.0 * torch.randn(K, C, generator=g), 1).to(torch.bfloat16)
+    head = pkg["head"].CoMatchHead(C, D, K, 0.9, enqueue_mode="always", dtype=torch.bfloat16)
+    assert head.queue_probs_t is not None, "tensor-core bank layout not allocated"
+    head.queue_feats.copy_(qf)
+    head.queue_probs.copy_(qp)
+    head.queue_probs_t[:C].copy_(qp.t())
+    rowsum, numer = head._k_smooth(f.cuda())
+    torch.cuda.synchronize()
+    A = torch.exp(f.double() @ qf.double().t() / 0.2)
+    assert rel_err(rowsum, A.sum(1)) < 3e-3
+    assert rel_err(numer, A @ qp.double()) < 3e-3
+    # and the smoothed probabilities that the head would form from them
+    sm = (numer.double().cpu() / rowsum.double().cpu()[:, None])
+    ref = (A @ qp.double()) / A.sum(1, keepdim=True)
+    assert float((sm - ref).abs().max()) < 2e-3
