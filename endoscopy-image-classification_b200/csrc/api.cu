@@ -43,7 +43,7 @@ extern "C" size_t b200ssl_workspace_bytes(int64_t rows, int32_t classes, int64_t
   if (bank_rows > 0) {
     int tps = 0;
     const int nsplit = smooth_nsplit(rows, bank_rows, &tps);
-    const size_t sm = nsplit > 1 ? (size_t)nsplit * row_tiles * kTM * (1 + classes) * sizeof(float) : 0;
+    const size_t sm = nsplit > 1 ? (size_t)nsplit * row_tiles * kTM * ((1 + classes + 3) & ~3) * sizeof(float) : 0;
     if (sm > need) need = sm;
     const size_t tc = sizeof(float) * smooth_tc_workspace_floats(rows, bank_rows, classes);
     if (tc > need) need = tc;

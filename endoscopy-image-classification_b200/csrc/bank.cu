@@ -20,7 +20,7 @@ struct SmoothParams {
   long long rows, bank_rows; int D, C; float tau;
   float* rowsum; float* numer;
   float* part; unsigned* tickets;  // split-K partials [nsplit][rows_pad][1+C], per row-tile tickets
-  int nsplit, tiles_per_split; long long rows_pad;
+  int nsplit, tiles_per_split, W; long long rows_pad;
 };
 
 // grid = (row tiles, nsplit); 256 threads; NACC = ceil(maxC/4) numerator
@@ -85,20 +85,22 @@ __global__ void __launch_bounds__(kTileThreads) bank_smooth_simt_kernel(const Sm
     for (int o = 8; o > 0; o >>= 1) rs[i] += __shfl_xor_sync(0xffffffffu, rs[i], o);
   }
   const bool direct = p.nsplit == 1;
-  float* orow = direct ? p.rowsum : p.part + (size_t)split * p.rows_pad * (1 + C);
-  float* onum = direct ? p.numer : orow + p.rows_pad;
+  const int W = p.W;   // floats per row of a split partial: [rowsum, numer[0..C), pad]
+  float* pbase = p.part + (size_t)split * p.rows_pad * W;
   if (tx == 0) {
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const int r = ty + 16 * i;
-      if (r < mrows) orow[i0 + r] = rs[i];
+      if (direct) { if (r < mrows) p.rowsum[i0 + r] = rs[i]; }
+      else pbase[(i0 + r) * W] = rs[i];
     }
   }
-  if (prow < mrows) {
 #pragma unroll
-    for (int m = 0; m < NACC; ++m) {
-      const int c = cg + 4 * m;
-      if (c < C) onum[(i0 + prow) * C + c] = nacc[m];
+  for (int m = 0; m < NACC; ++m) {
+    const int c = cg + 4 * m;
+    if (c < C) {
+      if (direct) { if (prow < mrows) p.numer[(i0 + prow) * C + c] = nacc[m]; }
+      else pbase[(i0 + prow) * W + 1 + c] = nacc[m];
     }
   }
   if (direct) return;
@@ -110,17 +112,16 @@ __global__ void __launch_bounds__(kTileThreads) bank_smooth_simt_kernel(const Sm
   __syncthreads();
   if (!s_last) return;
   __threadfence();
-  const size_t sstride = (size_t)p.rows_pad * (1 + C);
-  for (int r = tid; r < mrows; r += blockDim.x) {
-    float t = 0.f;
-    for (int s = 0; s < p.nsplit; ++s) t += __ldcg(p.part + s * sstride + i0 + r);
-    p.rowsum[i0 + r] = t;
-  }
-  for (int e = tid; e < mrows * C; e += blockDim.x) {
-    float t = 0.f;
-    for (int s = 0; s < p.nsplit; ++s) t += __ldcg(p.part + s * sstride + p.rows_pad + i0 * C + e);
-    p.numer[i0 * C + e] = t;
-  }
+  fold_splits_vec4(reinterpret_cast<const float4*>(p.part + (size_t)i0 * W), (size_t)p.rows_pad * W / 4, p.nsplit,
+                   mrows * W / 4, [&](int i, float4 v) {
+                     const float vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                     for (int j = 0; j < 4; ++j) {
+                       const int e = 4 * i + j, row = e / W, col = e - row * W;
+                       if (col == 0) p.rowsum[i0 + row] = vv[j];
+                       else if (col <= C) p.numer[(i0 + row) * C + col - 1] = vv[j];
+                     }
+                   });
   if (tid == 0) p.tickets[blockIdx.x] = 0u;
 }
 
@@ -223,7 +224,8 @@ extern "C" int b200ssl_bank_smooth_partial(const void* feats_u_w, const void* qu
   p.nsplit = smooth_nsplit(rows, bank_rows, &p.tiles_per_split);
   const long long row_tiles = (rows + kTM - 1) / kTM;
   p.rows_pad = row_tiles * kTM;
-  const size_t need = kWsHeaderBytes + (p.nsplit > 1 ? (size_t)p.nsplit * p.rows_pad * (1 + classes) * sizeof(float) : 0);
+  p.W = (1 + classes + 3) & ~3;
+  const size_t need = kWsHeaderBytes + (p.nsplit > 1 ? (size_t)p.nsplit * p.rows_pad * p.W * sizeof(float) : 0);
   if (workspace_bytes < need) return fail(B200SSL_E_WORKSPACE, "%s: workspace %zu < %zu bytes", fn, workspace_bytes, need);
   if ((size_t)row_tiles * 4 > kWsTicket2Bytes) return fail(B200SSL_E_SHAPE, "%s: too many row tiles", fn);
   p.tickets = reinterpret_cast<unsigned*>(static_cast<char*>(workspace) + kWsTicketBytes);

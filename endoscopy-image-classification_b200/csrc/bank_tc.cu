@@ -81,7 +81,7 @@ constexpr size_t kSmemRequest = 120 * 1024;             // > half an SM: one CTA
 
 struct SmoothTcParams {
   long long rows, bank_rows, rows_pad;
-  int C, nsplit, tiles_per_split;
+  int C, W, nsplit, tiles_per_split;   // W = round_up(1 + C, 4): floats per row of a split partial
   float scale;                    // log2(e) / temperature
   float* rowsum; float* numer;
   float* part; unsigned* tickets;
@@ -228,16 +228,23 @@ bank_smooth_tc_kernel(const __grid_constant__ CUtensorMap tm_f, const __grid_con
     tc::tmem_ld_32x32(lane_addr + 2 * kBN, r);
     tc::tmem_ld_wait();
     const long long grow = (long long)row_tile * kBM + r_in;
-    const bool direct = p.nsplit == 1;
-    float* orow = direct ? p.rowsum : p.part + (size_t)split * p.rows_pad * (1 + p.C);
-    float* onum = direct ? p.numer : orow + p.rows_pad;
-    if (grow < p.rows || !direct) {
-      if (grow < p.rows_pad) {
-        orow[grow] = rowsum;
+    if (p.nsplit == 1) {
+      if (grow < p.rows) {
+        p.rowsum[grow] = rowsum;
 #pragma unroll
         for (int c = 0; c < kCP; ++c)
-          if (c < p.C) onum[grow * p.C + c] = __uint_as_float(r[c]);
+          if (c < p.C) p.numer[grow * p.C + c] = __uint_as_float(r[c]);
       }
+    } else {
+      // split partial, row-interleaved [split][rows_pad][W]: element 0 = rowsum, 1..C = numer
+      float4* o = reinterpret_cast<float4*>(p.part + ((size_t)split * p.rows_pad + grow) * p.W);
+      float vals[kCP + 4];
+      vals[0] = rowsum;
+#pragma unroll
+      for (int c = 0; c < kCP; ++c) vals[1 + c] = __uint_as_float(r[c]);
+#pragma unroll
+      for (int q = 0; q < (kCP + 4) / 4; ++q)
+        if (4 * q < p.W) o[q] = make_float4(vals[4 * q], vals[4 * q + 1], vals[4 * q + 2], vals[4 * q + 3]);
     }
     tc::tcgen05_fence_before();
   }
@@ -257,17 +264,17 @@ bank_smooth_tc_kernel(const __grid_constant__ CUtensorMap tm_f, const __grid_con
   __threadfence();
   const long long i0 = (long long)row_tile * kBM;
   const int mrows = (int)min((long long)kBM, p.rows - i0);
-  const size_t sstride = (size_t)p.rows_pad * (1 + p.C);
-  for (int r = threadIdx.x; r < mrows; r += blockDim.x) {
-    float t = 0.f;
-    for (int s = 0; s < p.nsplit; ++s) t += __ldcg(p.part + s * sstride + i0 + r);
-    p.rowsum[i0 + r] = t;
-  }
-  for (int e = threadIdx.x; e < mrows * p.C; e += blockDim.x) {
-    float t = 0.f;
-    for (int s = 0; s < p.nsplit; ++s) t += __ldcg(p.part + s * sstride + p.rows_pad + i0 * p.C + e);
-    p.numer[i0 * p.C + e] = t;
-  }
+  const int W = p.W, C = p.C;
+  fold_splits_vec4(reinterpret_cast<const float4*>(p.part + (size_t)i0 * W), (size_t)p.rows_pad * W / 4, p.nsplit,
+                   mrows * W / 4, [&](int i, float4 v) {
+                     const float vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                     for (int j = 0; j < 4; ++j) {
+                       const int e = 4 * i + j, row = e / W, col = e - row * W;
+                       if (col == 0) p.rowsum[i0 + row] = vv[j];
+                       else if (col <= C) p.numer[(i0 + row) * C + col - 1] = vv[j];
+                     }
+                   });
   if (threadIdx.x == 0) p.tickets[row_tile] = 0u;
 }
 
@@ -287,7 +294,7 @@ int smooth_tc_nsplit(long long rows, long long bank_rows, int* tiles_per_split) 
 size_t smooth_tc_workspace_floats(long long rows, long long bank_rows, int classes) {
   const long long row_tiles = (rows + kBM - 1) / kBM;
   const int ns = smooth_tc_nsplit(rows, bank_rows, nullptr);
-  return ns > 1 ? (size_t)ns * row_tiles * kBM * (1 + classes) : 0;
+  return ns > 1 ? (size_t)ns * row_tiles * kBM * ((1 + classes + 3) & ~3) : 0;
 }
 
 // bf16, dim 64, classes <= 32, bank rows a multiple of 8: the tensor-core path.
@@ -296,7 +303,7 @@ int bank_smooth_tc(const void* feats, const void* queue_feats, const void* queue
                    size_t workspace_bytes, cudaStream_t stream) {
   const char* fn = "b200ssl_bank_smooth_partial[tcgen05]";
   SmoothTcParams p{};
-  p.rows = rows; p.bank_rows = bank_rows; p.C = classes;
+  p.rows = rows; p.bank_rows = bank_rows; p.C = classes; p.W = (1 + classes + 3) & ~3;
   p.scale = (float)(1.4426950408889634 / (double)temperature);
   p.rowsum = rowsum; p.numer = numer;
   p.nsplit = smooth_tc_nsplit(rows, bank_rows, &p.tiles_per_split);

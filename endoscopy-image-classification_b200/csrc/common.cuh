@@ -159,6 +159,27 @@ template <int LPR> __device__ __forceinline__ void group_argmax(float& v, int& i
 }
 __device__ __forceinline__ float warp_sum(float v) { return group_sum<32>(v); }
 
+// Fold `nsplit` partial vectors (each `count4` float4 long, `stride4` float4 apart) in
+// split order and hand float4 #i of the total to f(i, sum).  The loads of 8 splits are
+// issued back to back (independent, L2-only) so the fold costs a few round trips instead
+// of nsplit * count4 / blockDim serialised ones.
+template <typename F>
+__device__ __forceinline__ void fold_splits_vec4(const float4* __restrict__ part, size_t stride4, int nsplit, int count4, F f) {
+  for (int i = threadIdx.x; i < count4; i += blockDim.x) {
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int s0 = 0; s0 < nsplit; s0 += 8) {
+      float4 v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+        if (s0 + u < nsplit) v[u] = __ldcg(part + (size_t)(s0 + u) * stride4 + i);
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+        if (s0 + u < nsplit) { acc.x += v[u].x; acc.y += v[u].y; acc.z += v[u].z; acc.w += v[u].w; }
+    }
+    f(i, acc);
+  }
+}
+
 // Deterministic grid-wide sum of NV floats per CTA: every CTA stores its
 // partials, takes a ticket; the last CTA to arrive adds all partials in a
 // fixed order and returns true with the totals in `total` (valid in thread 0).

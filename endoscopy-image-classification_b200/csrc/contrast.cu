@@ -136,12 +136,17 @@ __global__ void __launch_bounds__(kTileThreads) contrast_fwd_kernel(const Contra
   }
   if (!tile_last(p.tile_tickets + PASS * gridDim.x + blockIdx.x, p.nsplit)) return;
   float lsum[1] = {0.f};
+  // the two per-row quantities of this pass, folded over the splits (vectorised, split order)
+  __shared__ float s_fold[2][kTM];
+#pragma unroll
+  for (int w = 0; w < 2; ++w)
+    fold_splits_vec4(reinterpret_cast<const float4*>(base + (size_t)w * p.nsplit * p.rows_pad + i0), (size_t)p.rows_pad / 4,
+                     p.nsplit, kTM / 4, [&](int i, float4 v) {
+                       s_fold[w][4 * i] = v.x; s_fold[w][4 * i + 1] = v.y; s_fold[w][4 * i + 2] = v.z; s_fold[w][4 * i + 3] = v.w;
+                     });
+  __syncthreads();
   for (int r = tid; r < mrows; r += blockDim.x) {
-    float t0 = 0.f, t1 = 0.f;
-    for (int s2 = 0; s2 < p.nsplit; ++s2) {
-      t0 += __ldcg(base + (size_t)s2 * p.rows_pad + i0 + r);
-      t1 += __ldcg(base + (size_t)(p.nsplit + s2) * p.rows_pad + i0 + r);
-    }
+    const float t0 = s_fold[0][r], t1 = s_fold[1][r];
     if (PASS == 0) {
       p.stats[i0 + r] = t0;
       p.stats[p.rows + i0 + r] = t1;
@@ -299,11 +304,12 @@ __global__ void __launch_bounds__(kTileThreads) contrast_bwd_kernel(const Contra
   }
   unsigned* ticket = p.tile_tickets + (2 + (colmode ? 1 : 0)) * gridDim.x + blockIdx.x;
   if (!tile_last(ticket, p.nsplit)) return;
-  for (int e = tid; e < nown * D; e += blockDim.x) {
-    float t = 0.f;
-    for (int s2 = 0; s2 < p.nsplit; ++s2) t += __ldcg(base + ((size_t)s2 * p.rows_pad + own0) * D + e);
-    out[own0 * D + e] = from_f32<T>(__fdiv_rn(t, p.tau) * up);
-  }
+  fold_splits_vec4(reinterpret_cast<const float4*>(base + (size_t)own0 * D), (size_t)p.rows_pad * D / 4, p.nsplit,
+                   nown * D / 4, [&](int i, float4 v) {
+                     const float vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                     for (int j = 0; j < 4; ++j) out[own0 * D + 4 * i + j] = from_f32<T>(__fdiv_rn(vv[j], p.tau) * up);
+                   });
   if (tid == 0) *ticket = 0u;
 }
 

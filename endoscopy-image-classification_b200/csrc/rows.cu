@@ -335,23 +335,35 @@ __global__ void __launch_bounds__(kRowThreads) comatch_da_kernel(const DaParams 
   const int count_old = p.state[0], head = p.state[1];
   const int count = min(count_old + 1, p.window);
   const int head_new = (head + 1) % p.window;
-  for (int c = warp; c < C; c += kRowWarps) {
+  // All loads of the fold are issued up front (one thread per (class, lane) pair would
+  // serialise dependent round trips per class): thread c owns class c.
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
     float t = 0.f;
-    for (unsigned b = lane; b < gridDim.x; b += 32) t += __ldcg(&p.partials[(size_t)b * C + c]);
-    t = warp_sum(t);
+    for (unsigned b0 = 0; b0 < gridDim.x; b0 += 8) {
+      float v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v[u] = (b0 + u < gridDim.x) ? __ldcg(&p.partials[(size_t)(b0 + u) * C + c]) : 0.f;
+#pragma unroll
+      for (int u = 0; u < 8; ++u) t += v[u];
+    }
     const float mean = t / (float)p.rows;  // probs.mean(0), comatch.py:169
     // history mean, oldest -> newest (comatch.py:172); the newest entry is `mean`
     float h = 0.f;
-    for (int a = lane; a < count; a += 32) {
-      const int slot = (head_new - count + a + 2 * p.window) % p.window;
-      h += (a == count - 1) ? mean : p.ring[(size_t)slot * C + c];
+    for (int a0 = 0; a0 < count - 1; a0 += 8) {
+      float v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int a = a0 + u;
+        const int slot = (head_new - count + a + 2 * p.window) % p.window;
+        v[u] = (a < count - 1) ? p.ring[(size_t)slot * C + c] : 0.f;
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) h += v[u];
     }
-    h = warp_sum(h);
-    if (lane == 0) {
-      p.ring[(size_t)head * C + c] = mean;
-      p.prob_avg[c] = h / (float)count;
-      if (p.col_mean) p.col_mean[c] = mean;
-    }
+    h += mean;
+    p.ring[(size_t)head * C + c] = mean;
+    p.prob_avg[c] = h / (float)count;
+    if (p.col_mean) p.col_mean[c] = mean;
   }
   __syncthreads();
   if (threadIdx.x == 0) {

@@ -125,7 +125,7 @@ B200SSL_API int b200ssl_comatch_da(const void* logits_u_w, int64_t rows, int32_t
  *     given (bf16 [32, bank_rows]: transposed, class-padded copy of queue_probs
  *     maintained by b200ssl_bank_enqueue): tcgen05.mma with TMEM accumulators,
  *     operands staged by TMA (csrc/bank_tc.cu);
- *   - otherwise exact-fp32 FFMA tiles (the reference's torch.mm is true fp32).
+ *   - otherwise exact-fp32 FFMA tiles (the reference's matrix product is true fp32).
  */
 B200SSL_API int b200ssl_bank_smooth_partial(const void* feats_u_w, const void* queue_feats, const void* queue_probs,
                                 const void* queue_probs_t, int64_t rows, int64_t bank_rows, int32_t dim, int32_t classes,
