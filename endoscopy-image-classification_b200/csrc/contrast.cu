@@ -341,7 +341,7 @@ size_t contrast_workspace_floats(long long rows, int dim) {
   const size_t fwd = (size_t)4 * contrast_nsplit(rows, 1, nullptr) * rows_pad;
   const int nb = contrast_nsplit(rows, 2, nullptr);
   const size_t bwd = nb > 1 ? (size_t)2 * nb * rows_pad * dim : 0;
-  return (size_t)tiles + (fwd > bwd ? fwd : bwd);
+  return (size_t)((tiles + 3) & ~3LL) + (fwd > bwd ? fwd : bwd);
 }
 
 }  // namespace b200ssl
@@ -359,7 +359,7 @@ static int contrast_setup(const char* fn, ContrastParams& p, int modes, void* wo
   p.tile_tickets = reinterpret_cast<unsigned*>(static_cast<char*>(workspace) + kWsTicketBytes);
   p.grid_ticket = reinterpret_cast<unsigned*>(workspace) + 4;
   p.grid_part = reinterpret_cast<float*>(static_cast<char*>(workspace) + kWsHeaderBytes);
-  p.part = p.grid_part + tiles;
+  p.part = p.grid_part + ((tiles + 3) & ~3LL);   // keep the split partials 16-byte aligned (float4 folds)
   return 0;
 }
 
