@@ -43,7 +43,7 @@ class _HeadFn(torch.autograd.Function):
         out = head._step(logits_u_w.detach(), logits_u_s0.detach(), feats_u_w.detach(), f0, f1,
                          feats_x.detach(), targets_x, float(lambda_u), float(lambda_c))
         ctx.head, ctx.lambda_u, ctx.lambda_c = head, float(lambda_u), float(lambda_c)
-        ctx.save_for_backward(out["grad_s0"], f0, f1, out["probs"], out["stats"])
+        ctx.save_for_backward(out["grad_s0"], f0, f1, out["probs"], out["stats"], out["probs_hl"])
         ctx.done = False
         ctx.set_materialize_grads(False)
         aux = (out["mask"], out["lbs"], out["scores"], out["probs"])
@@ -56,7 +56,7 @@ class _HeadFn(torch.autograd.Function):
         if ctx.done:
             raise RuntimeError("CoMatchHead: backward through the fused head twice (the stashed gradient is consumed)")
         ctx.done = True
-        grad_s0, f0, f1, probs, stats = ctx.saved_tensors
+        grad_s0, f0, f1, probs, stats, probs_hl = ctx.saved_tensors
         head = ctx.head
 
         def upstream(g_own, lam):
@@ -76,7 +76,7 @@ class _HeadFn(torch.autograd.Function):
             if g is None:
                 gf0, gf1 = torch.zeros_like(f0), torch.zeros_like(f1)
             else:
-                gf0, gf1 = head._k_contrast_bwd(f0, f1, probs, stats, g, fac)
+                gf0, gf1 = head._k_contrast_bwd(f0, f1, probs, stats, g, fac, probs_hl)
         return None, None, None, None, gs0, None, gf0, gf1, None, None
 
 
@@ -243,7 +243,8 @@ class CoMatchHead:
                     self._k_enqueue(gf[r, :rows], gf[r, rows:], po_all[r], tx_all[r], r * n, R * n if r == R - 1 else 0)
             self._queue_ptr = geom.next_ptr(self._queue_ptr, n)
             self._pristine = False
-        stats, loss_c = self._k_contrast_fwd(fs0, fs1, out["probs"], out["scalars"], lambda_u, lambda_c)  # K6
+        stats, loss_c = self._k_contrast_fwd(fs0, fs1, out["probs"], out["scalars"], lambda_u, lambda_c,
+                                             probs_hl=out["probs_hl"])  # K6
         self.last = {"probs_orig": out["probs_orig"], "rowsum": rowsum, "numer": numer, "probs": out["probs"],
                      "mask": out["mask"], "lbs": out["lbs"], "scores": out["scores"]}
         out["stats"] = stats
@@ -281,12 +282,16 @@ class CoMatchHead:
                "scores": torch.empty(rows, **f32), "mask": torch.empty(rows, **f32),
                "lbs": torch.empty(rows, dtype=torch.int64, device=self.device),
                "grad_s0": torch.empty_like(ls0),
-               "scalars": torch.empty(4, **f32)}      # loss_u, mask_mean, loss_contrast, -
+               "scalars": torch.empty(4, **f32),      # loss_u, mask_mean, loss_contrast, total
+               # bf16 hi/lo split of probs: operand of the tensor-core graph kernel (contrast_tc.cu)
+               "probs_hl": (torch.empty(rows, 64, dtype=torch.bfloat16, device=self.device)
+                            if (lw.dtype == torch.bfloat16 and C <= 32 and self.low_dim == 64) else None)}
         ws, wsb = self._ws(rows)
         N.check(N.lib().b200ssl_comatch_finalize(
             lw.data_ptr(), ls0.data_ptr(), self.prob_avg.data_ptr(), N.ptr(rowsum), N.ptr(numer), rows, C,
             N.dtype_enum(lw), float(np.float32(self.alpha)), float(np.float32(1.0 - self.alpha)), self.thr, self.gamma,
-            out["probs"].data_ptr(), out["probs_orig"].data_ptr(), out["scores"].data_ptr(), out["lbs"].data_ptr(),
+            out["probs"].data_ptr(), out["probs_orig"].data_ptr(), N.ptr(out["probs_hl"]), out["scores"].data_ptr(),
+            out["lbs"].data_ptr(),
             out["mask"].data_ptr(), out["grad_s0"].data_ptr(), out["scalars"].data_ptr(), ws, wsb,
             N.stream_ptr(self.device)), "comatch_finalize")
         return out
@@ -302,24 +307,25 @@ class CoMatchHead:
                                              g.shard_begin, g.shard_rows,
                                              N.stream_ptr(self.device)), "bank_enqueue")
 
-    def _k_contrast_fwd(self, fs0, fs1, probs, scalars, lambda_u: float = 1.0, lambda_c: float = 1.0):
+    def _k_contrast_fwd(self, fs0, fs1, probs, scalars, lambda_u: float = 1.0, lambda_c: float = 1.0, probs_hl=None):
         """scalars: [loss_u (in), mask_mean, loss_contrast (out), total (out)]."""
         rows, D = fs0.shape
         stats = torch.empty(3, rows, dtype=torch.float32, device=self.device)
         ws, wsb = self._ws(rows)
-        N.check(N.lib().b200ssl_contrast_fwd(fs0.data_ptr(), fs1.data_ptr(), probs.data_ptr(), rows, D,
+        N.check(N.lib().b200ssl_contrast_fwd(fs0.data_ptr(), fs1.data_ptr(), probs.data_ptr(), N.ptr(probs_hl), rows, D,
                                              self.num_classes, N.dtype_enum(fs0), self.temperature, self.contrast_th,
                                              stats.data_ptr(), scalars[2:].data_ptr(), scalars.data_ptr(), lambda_u,
                                              lambda_c, scalars[3:].data_ptr(), ws, wsb,
                                              N.stream_ptr(self.device)), "contrast_fwd")
         return stats, scalars[2]
 
-    def _k_contrast_bwd(self, f0, f1, probs, stats, g_c, factor: float = 1.0):
+    def _k_contrast_bwd(self, f0, f1, probs, stats, g_c, factor: float = 1.0, probs_hl=None):
         g = g_c.detach().to(torch.float32).reshape(1).contiguous()
         gf0, gf1 = torch.empty_like(f0), torch.empty_like(f1)
         rows, D = f0.shape
         ws, wsb = self._ws(rows)
-        N.check(N.lib().b200ssl_contrast_bwd(f0.data_ptr(), f1.data_ptr(), probs.data_ptr(), stats.data_ptr(), rows,
+        N.check(N.lib().b200ssl_contrast_bwd(f0.data_ptr(), f1.data_ptr(), probs.data_ptr(), N.ptr(probs_hl),
+                                             stats.data_ptr(), rows,
                                              D, self.num_classes, N.dtype_enum(f0), self.temperature, self.contrast_th,
                                              g.data_ptr(), factor, gf0.data_ptr(), gf1.data_ptr(), ws, wsb,
                                              N.stream_ptr(self.device)), "contrast_bwd")

@@ -40,6 +40,8 @@ extern "C" size_t b200ssl_workspace_bytes(int64_t rows, int32_t classes, int64_t
   const long long row_tiles = (rows + kTM - 1) / kTM;
   const size_t contrast = sizeof(float) * contrast_workspace_floats(rows, B200SSL_MAX_EMB_DIM);
   if (contrast > need) need = contrast;
+  const size_t contrast_tc = sizeof(float) * contrast_tc_workspace_floats(rows);
+  if (contrast_tc > need) need = contrast_tc;
   if (bank_rows > 0) {
     int tps = 0;
     const int nsplit = smooth_nsplit(rows, bank_rows, &tps);

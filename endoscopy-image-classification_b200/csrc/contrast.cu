@@ -348,6 +348,21 @@ size_t contrast_workspace_floats(long long rows, int dim) {
 
 using namespace b200ssl;
 
+namespace b200ssl {
+int contrast_fwd_tc(const void* f0, const void* f1, const void* probs_hl, long long rows, int classes, float temperature,
+                    float contrast_th, float* stats, float* out_scalar, const float* loss_u, float lambda_u, float lambda_c,
+                    float* total_out, void* workspace, size_t workspace_bytes, cudaStream_t stream);
+int contrast_bwd_tc(const void* f0, const void* f1, const void* probs_hl, const float* stats, long long rows, int classes,
+                    float temperature, float contrast_th, const float* upstream, float factor, void* g0, void* g1,
+                    void* workspace, size_t workspace_bytes, cudaStream_t stream);
+}
+// bf16 embeddings with 128-byte rows + the hi/lo probability split: tcgen05 path (contrast_tc.cu)
+static bool use_tc(const void* f0, const void* f1, const void* probs_hl, int dim, int classes, int dtype, const void* g0 = nullptr,
+                   const void* g1 = nullptr) {
+  auto al = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15u) == 0; };
+  return dtype == B200SSL_BF16 && dim == 64 && classes <= 32 && probs_hl && al(f0) && al(f1) && al(probs_hl) && al(g0) && al(g1);
+}
+
 static int contrast_setup(const char* fn, ContrastParams& p, int modes, void* workspace, size_t workspace_bytes) {
   const long long tiles = (p.rows + kTM - 1) / kTM;
   p.rows_pad = tiles * kTM;
@@ -363,7 +378,8 @@ static int contrast_setup(const char* fn, ContrastParams& p, int modes, void* wo
   return 0;
 }
 
-extern "C" int b200ssl_contrast_fwd(const void* feats_s0, const void* feats_s1, const float* probs, int64_t rows,
+extern "C" int b200ssl_contrast_fwd(const void* feats_s0, const void* feats_s1, const float* probs, const void* probs_hl,
+                                    int64_t rows,
                                     int32_t dim, int32_t classes, int32_t dtype, float temperature, float contrast_th,
                                     float* stats, float* out_scalar, const float* loss_u, float lambda_u,
                                     float lambda_c, float* total_out, void* workspace, size_t workspace_bytes,
@@ -371,6 +387,10 @@ extern "C" int b200ssl_contrast_fwd(const void* feats_s0, const void* feats_s1, 
   const char* fn = "b200ssl_contrast_fwd";
   if (int e = check_contrast(fn, rows, dim, classes, dtype, temperature)) return e;
   if (!feats_s0 || !feats_s1 || !probs || !stats || !out_scalar) return fail(B200SSL_E_NULL, "%s: NULL tensor", fn);
+  if (!workspace || (reinterpret_cast<uintptr_t>(workspace) & 255u)) return fail(B200SSL_E_ALIGN, "%s: workspace NULL or not 256-byte aligned", fn);
+  if (use_tc(feats_s0, feats_s1, probs_hl, dim, classes, dtype))
+    return contrast_fwd_tc(feats_s0, feats_s1, probs_hl, rows, classes, temperature, contrast_th, stats, out_scalar, loss_u,
+                           lambda_u, lambda_c, total_out, workspace, workspace_bytes, as_stream(stream));
   ContrastParams p{};
   p.f0 = feats_s0; p.f1 = feats_s1; p.probs = probs; p.rows = rows; p.D = dim; p.C = classes;
   p.tau = temperature; p.th = contrast_th; p.stats = stats; p.out = out_scalar;
@@ -399,13 +419,17 @@ extern "C" int b200ssl_contrast_fwd(const void* feats_s0, const void* feats_s1, 
   return check_launch(fn);
 }
 
-extern "C" int b200ssl_contrast_bwd(const void* feats_s0, const void* feats_s1, const float* probs, const float* stats,
-                                    int64_t rows, int32_t dim, int32_t classes, int32_t dtype, float temperature,
+extern "C" int b200ssl_contrast_bwd(const void* feats_s0, const void* feats_s1, const float* probs, const void* probs_hl,
+                                    const float* stats, int64_t rows, int32_t dim, int32_t classes, int32_t dtype, float temperature,
                                     float contrast_th, const float* upstream, float factor, void* grad_f0, void* grad_f1,
                                     void* workspace, size_t workspace_bytes, void* stream) {
   const char* fn = "b200ssl_contrast_bwd";
   if (int e = check_contrast(fn, rows, dim, classes, dtype, temperature)) return e;
   if (!feats_s0 || !feats_s1 || !probs || !stats || !grad_f0 || !grad_f1) return fail(B200SSL_E_NULL, "%s: NULL tensor", fn);
+  if (!workspace || (reinterpret_cast<uintptr_t>(workspace) & 255u)) return fail(B200SSL_E_ALIGN, "%s: workspace NULL or not 256-byte aligned", fn);
+  if (use_tc(feats_s0, feats_s1, probs_hl, dim, classes, dtype, grad_f0, grad_f1))
+    return contrast_bwd_tc(feats_s0, feats_s1, probs_hl, stats, rows, classes, temperature, contrast_th, upstream, factor,
+                           grad_f0, grad_f1, workspace, workspace_bytes, as_stream(stream));
   ContrastParams p{};
   p.f0 = feats_s0; p.f1 = feats_s1; p.probs = probs; p.rows = rows; p.D = dim; p.C = classes;
   p.tau = temperature; p.th = contrast_th; p.stats = const_cast<float*>(stats);

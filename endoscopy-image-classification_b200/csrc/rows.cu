@@ -381,6 +381,7 @@ struct FinalizeParams {
   float alpha, one_minus_alpha, thr, gamma;
   float* probs; float* probs_orig; float* scores; long long* lbs; float* mask;
   void* gs0; float* out; float* partials; unsigned* ticket;
+  __nv_bfloat16* hl;   // optional [rows, 64] bf16: hi(32) | lo(32) split of probs for the tensor-core graph kernel
 };
 
 __device__ __forceinline__ float pow_gamma(float b, float gamma) {
@@ -451,6 +452,18 @@ __global__ void __launch_bounds__(kRowThreads) comatch_finalize_kernel(const Fin
       for (int k = 0; k < EPL; ++k) {
         const int c = gl + k * LPR;
         if (c < C) sw[r * C + c] = pr[k];
+      }
+      if (p.hl) {
+#pragma unroll
+        for (int k = 0; k < EPL; ++k) {
+          const int c = gl + k * LPR;
+          if (c < 32) {
+            const __nv_bfloat16 hi = __float2bfloat16_rn(pr[k]);
+            __nv_bfloat16* dst = p.hl + (row0 + r) * 64 + c;
+            dst[0] = hi;
+            dst[32] = __float2bfloat16_rn(pr[k] - __bfloat162float(hi));
+          }
+        }
       }
       if (gl == 0) {
         if (p.scores) p.scores[row0 + r] = score;
@@ -640,19 +653,20 @@ extern "C" int b200ssl_comatch_da(const void* logits_u_w, int64_t rows, int32_t 
 extern "C" int b200ssl_comatch_finalize(const void* logits_u_w, const void* logits_u_s0, const float* prob_avg,
                                         const float* rowsum, const float* numer, int64_t rows, int32_t classes,
                                         int32_t dtype, float alpha, float one_minus_alpha, float thr, float gamma,
-                                        float* probs, float* probs_orig, float* scores, int64_t* lbs, float* mask,
-                                        void* grad_s0, float* out_scalars, void* workspace, size_t workspace_bytes,
-                                        void* stream) {
+                                        float* probs, float* probs_orig, void* probs_hl, float* scores, int64_t* lbs,
+                                        float* mask, void* grad_s0, float* out_scalars, void* workspace,
+                                        size_t workspace_bytes, void* stream) {
   const char* fn = "b200ssl_comatch_finalize";
   if (int e = check_rows(fn, rows, classes, dtype)) return e;
   if (!logits_u_w || !logits_u_s0 || !prob_avg || !probs || !probs_orig || !grad_s0 || !out_scalars)
     return fail(B200SSL_E_NULL, "%s: NULL tensor", fn);
   if ((rowsum == nullptr) != (numer == nullptr)) return fail(B200SSL_E_NULL, "%s: rowsum and numer go together", fn);
+  if (probs_hl && classes > 32) return fail(B200SSL_E_SHAPE, "%s: probs_hl needs classes <= 32", fn);
   if (int e = check_ws(fn, workspace, workspace_bytes, kWsHeaderBytes + sizeof(float) * 2 * kMaxRowCtas)) return e;
   FinalizeParams p{logits_u_w, logits_u_s0, prob_avg, rowsum, numer, rows, classes, alpha, one_minus_alpha, thr, gamma,
                    probs, probs_orig, scores, reinterpret_cast<long long*>(lbs), mask, grad_s0, out_scalars,
                    reinterpret_cast<float*>(static_cast<char*>(workspace) + kWsHeaderBytes),
-                   reinterpret_cast<unsigned*>(workspace) + 3};
+                   reinterpret_cast<unsigned*>(workspace) + 3, static_cast<__nv_bfloat16*>(probs_hl)};
   B200SSL_ROW_DISPATCH(dtype, classes, {
     RowLaunch l = row_launch<LPR, EPL>(rows, classes, 4);
     auto k = comatch_finalize_kernel<T, LPR, EPL>;

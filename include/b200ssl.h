@@ -146,14 +146,16 @@ B200SSL_API int b200ssl_bank_smooth_partial(const void* feats_u_w, const void* q
  *   grad_s0 = dl * mask * (softmax(s0)*sum_c probs_c - probs),
  *             dl = (gamma*(1-p)^(gamma-1)*p*logp + (1-p)^gamma)/rows
  * probs / probs_orig are fp32 [rows, classes]; out_scalars[0]=loss_u,
- * [1]=mask mean.  scores/lbs/mask optional.
+ * [1]=mask mean.  scores/lbs/mask optional.  probs_hl (optional, classes <= 32)
+ * receives bf16 [rows, 64] = [hi(probs) padded to 32 | lo = probs - hi padded to 32],
+ * the operand of the tensor-core graph kernel (b200ssl_contrast_*).
  */
 B200SSL_API int b200ssl_comatch_finalize(const void* logits_u_w, const void* logits_u_s0, const float* prob_avg,
                              const float* rowsum, const float* numer, int64_t rows, int32_t classes,
                              int32_t dtype, float alpha, float one_minus_alpha, float thr, float gamma,
-                             float* probs,
-                             float* probs_orig, float* scores, int64_t* lbs, float* mask, void* grad_s0,
-                             float* out_scalars, void* workspace, size_t workspace_bytes, void* stream);
+                             float* probs, float* probs_orig, void* probs_hl, float* scores, int64_t* lbs,
+                             float* mask, void* grad_s0, float* out_scalars, void* workspace,
+                             size_t workspace_bytes, void* stream);
 
 /* ---------------------------------------------------------------- K5 ----
  * Ring-buffer enqueue.  Replaces code/comatch.py:187-196: rows are
@@ -185,17 +187,22 @@ B200SSL_API int b200ssl_bank_enqueue(void* queue_feats, void* queue_probs, void*
  * fwd writes loss to out_scalar[0]; when total_out != NULL it also writes
  * total_out[0] = lambda_u * loss_u[0] + lambda_c * loss (comatch.py:222 without
  * loss_x; loss_u is the device scalar produced by b200ssl_comatch_finalize).
+ * Two code paths by storage type: bf16 embeddings with dim == 64, classes <= 32 and
+ * probs_hl given run on tcgen05/TMEM/TMA (csrc/contrast_tc.cu, S = F0 F1^T and the
+ * hi/lo-split Q = probs probs^T as MMAs, dZ staged through swizzled shared memory for the
+ * two gradient GEMMs); everything else uses exact-fp32 FFMA tiles (csrc/contrast.cu).
  * fwd also stores the row statistics (rowsum, qsum, r) into
  * stats f32[3*rows]; bwd consumes them and writes grad_f0 / grad_f1 scaled by
  * (*upstream) * factor (upstream: device scalar from autograd, NULL => 1; factor:
  * host constant such as LAMBDA_C of comatch.py:222).
  */
-B200SSL_API int b200ssl_contrast_fwd(const void* feats_s0, const void* feats_s1, const float* probs, int64_t rows,
+B200SSL_API int b200ssl_contrast_fwd(const void* feats_s0, const void* feats_s1, const float* probs, const void* probs_hl,
+                         int64_t rows,
                          int32_t dim, int32_t classes, int32_t dtype, float temperature, float contrast_th,
                          float* stats, float* out_scalar, const float* loss_u, float lambda_u, float lambda_c,
                          float* total_out, void* workspace, size_t workspace_bytes, void* stream);
-B200SSL_API int b200ssl_contrast_bwd(const void* feats_s0, const void* feats_s1, const float* probs, const float* stats,
-                         int64_t rows, int32_t dim, int32_t classes, int32_t dtype, float temperature,
+B200SSL_API int b200ssl_contrast_bwd(const void* feats_s0, const void* feats_s1, const float* probs, const void* probs_hl,
+                         const float* stats, int64_t rows, int32_t dim, int32_t classes, int32_t dtype, float temperature,
                          float contrast_th, const float* upstream, float factor, void* grad_f0, void* grad_f1,
                          void* workspace, size_t workspace_bytes, void* stream);
 

@@ -81,7 +81,7 @@ def test_argument_validation_without_gpu(native):
     assert lib.b200ssl_bank_enqueue(p, p, None, p, p, p, p, 4, 4, 64, 23, 0, 100, None, 0, 0, 64, 0, 64, None) == E_ARG  # ptr >= K
     assert lib.b200ssl_bank_enqueue(p, p, None, p, p, p, p, 4, 4, 64, 23, 0, 0, None, 0, 0, 64, 32, 64, None) == E_ARG   # shard outside
     assert lib.b200ssl_bank_enqueue(p, p, None, p, p, p, p, 4, 4, 64, 23, 0, 0, None, 8, 0, 64, 0, 64, None) == E_ARG    # advance w/o state
-    assert lib.b200ssl_contrast_fwd(p, p, p, 16, 64, 500, 0, 0.2, 0.8, p, p, None, 1.0, 1.0, None, p256, wsb, None) == E_SHAPE
+    assert lib.b200ssl_contrast_fwd(p, p, p, None, 16, 64, 500, 0, 0.2, 0.8, p, p, None, 1.0, 1.0, None, p256, wsb, None) == E_SHAPE
     assert lib.b200ssl_ema_multi_tensor(None, 4, 0, 1, 0.999, 0.001, 0, None) == E_NULL
     assert lib.b200ssl_ema_multi_tensor(p256, 4, 3, 1, 0.999, 0.001, 0, None) == E_DTYPE
     assert lib.b200ssl_ema_multi_tensor(p256, 4, 0, 1, 0.999, 0.001, 7, None) == E_ARG

@@ -514,3 +514,38 @@ def test_bank_smooth_tcgen05_bf16(pkg, rows, K):
     sm = (numer.double().cpu() / rowsum.double().cpu()[:, None])
     ref = (A @ qp.double()) / A.sum(1, keepdim=True)
     assert float((sm - ref).abs().max()) < 2e-3
+
+
+@pytest.mark.parametrize("rows", [448, 1, 100, 130, 1000, 3584])
+def test_contrast_tcgen05_bf16(pkg, rows):
+    """bf16 embeddings, D=64: graph-contrastive fwd + bwd on tcgen05 (csrc/contrast_tc.cu) against
+    fp64 autograd on the same bf16-rounded embeddings and fp32 probabilities."""
+    D = 64
+    g = torch.Generator().manual_seed(rows * 11 + 5)
+    nf = lambda: torch.nn.functional.normalize(torch.randn(rows, D, generator=g), dim=1).to(torch.bfloat16)
+    y = torch.randint(0, C, (rows,), generator=g)
+    probs = torch.softmax(6.0 * torch.nn.functional.one_hot(y, C).float() + torch.randn(rows, C, generator=g), 1)
+    if rows > 2000:
+        # 12.8 M pairs: keep every Q = <p_i, p_j> at least 1e-2 away from the 0.8 graph threshold, otherwise a few
+        # dozen pairs graze it within the ~6e-6 accuracy of the bf16 hi/lo split and flip (not a numerics bug)
+        conf = 0.95 + 0.01 * (torch.rand(rows, 1, generator=g) - 0.5)
+        probs = (1 - conf) / (C - 1) * torch.ones(rows, C) + (conf - (1 - conf) / (C - 1)) * torch.nn.functional.one_hot(y, C).float()
+    f0b, f1b = nf(), nf()
+    f0, f1 = f0b.double().requires_grad_(True), f1b.double().requires_grad_(True)
+    ref = O.comatch_contrast(f0, f1, probs.double(), 0.2, 0.8)
+    ref.backward()
+    hi = probs.to(torch.bfloat16)
+    lo = (probs - hi.float()).to(torch.bfloat16)
+    hl = torch.zeros(rows, 64, dtype=torch.bfloat16)
+    hl[:, :C], hl[:, 32:32 + C] = hi, lo
+    head = pkg["head"].CoMatchHead(C, D, 64, 0.9, dtype=torch.bfloat16)
+    scal = torch.zeros(4, device="cuda")
+    d0, d1, dp, dhl = f0b.cuda(), f1b.cuda(), probs.cuda(), hl.cuda()
+    stats, _ = head._k_contrast_fwd(d0, d1, dp, scal, probs_hl=dhl)
+    up = torch.tensor(1.5, device="cuda")
+    g0, g1 = head._k_contrast_bwd(d0, d1, dp, stats, up, 2.0, probs_hl=dhl)
+    torch.cuda.synchronize()
+    assert abs(float(scal[2]) - float(ref)) < 2e-3 * max(abs(float(ref)), 1e-2)
+    A = torch.exp(f0b.double() @ f1b.double().t() / 0.2)
+    assert rel_err(stats[0], A.sum(1)) < 1e-3
+    assert rel_err(g0.float(), 3.0 * f0.grad) < BF16_TOL and rel_err(g1.float(), 3.0 * f1.grad) < BF16_TOL
