@@ -1,0 +1,246 @@
+"""Shared host-side shell of the three semi-supervised trainers.
+
+The reference repeats the same ~250 lines in ``code/fixmatch.py``, ``code/comatch.py`` and
+``code/semiformer.py`` (constructor, ``get_dataloader``, ``get_config``, ``train_one``,
+``evaluate_one``, ``save_checkpoint`` / ``load_checkpoint``, ``fit``).  Here the common
+orchestration lives once; each trainer only supplies its step.  Public names, attributes,
+config keys and checkpoint keys are the reference's, so driver code written against it
+(``learn.py``-style) keeps working.  Everything in this file is stock PyTorch host code --
+the accelerated path is what the steps call: ``loss.ce_loss`` / ``loss.consistency_loss``
+/ ``CoMatchHead`` / ``ModelEMA``.
+"""
+from __future__ import annotations
+
+import os
+from contextlib import nullcontext
+from datetime import date, datetime
+
+import numpy as np
+import torch
+
+from .ema import ModelEMA
+from .loss import ce_loss
+from .lr_scheduler import build_scheduler
+from .optimizer import build_optimizer
+from .utils import AverageMeter
+
+try:  # progress bars are cosmetic
+    from tqdm import tqdm
+except Exception:  # pragma: no cover
+    def tqdm(it, **kw):
+        return it
+
+
+def _cfg(section, key, default=None):
+    return section[key] if key in section else default
+
+
+class BatchSource:
+    """Endless ``next()`` over a DataLoader / iterable (the reference re-creates the iterator
+    inside a bare ``except`` when it is exhausted, ``fixmatch.py:91-100``; quirk Q5: it calls the
+    Python-2 style ``.next()`` -- here plain ``next(it)`` so modern loaders work)."""
+
+    def __init__(self, loader):
+        self.loader, self.it = loader, None
+
+    def next(self):
+        if self.it is None:
+            self.it = iter(self.loader)
+        try:
+            return next(self.it)
+        except StopIteration:
+            self.it = iter(self.loader)
+            return next(self.it)
+
+    __next__ = next
+
+
+class SemiSupervisedTrainer:
+    TRAINING_MODE = "semi-supervised"
+    EMA_BEFORE_FREEZE = False          # CoMatch / SemiFormer build the EMA copy before freezing (quirk Q9)
+
+    def __init__(self, model, opt_func="Adam", lr=1e-3, device="cpu"):
+        self.model = model
+        self.opt_func = opt_func
+        self.device = device
+        self.model.to(self.device)
+        self.epoch_start = 1
+        self.best_valid_perf = None
+
+    # ---- reference API ---------------------------------------------------------------
+    def get_dataloader(self, train_dl, valid_dl, test_dl=None):
+        self.train_labeled_dl, self.train_unlabeled_dl = train_dl
+        self.valid_dl = valid_dl
+        self.test_dl = test_dl
+
+    def _freeze_backbone(self):
+        for p in self.model.parameters():
+            p.requires_grad = False
+        head = self.model.classifier if self.config.MODEL.NAME == "densenet161" else self.model.fc
+        head.requires_grad_(True)
+
+    def _apply_freeze(self):
+        if _cfg(self.config.TRAIN, "IS_FREEZE", False):
+            print("Freeze backbone")
+            self._freeze_backbone()
+        elif not self.EMA_BEFORE_FREEZE:
+            print("Unfreeze backbone")
+            for p in self.model.parameters():
+                p.requires_grad = True
+
+    def _build_ema(self):
+        if self.config.TRAIN.USE_EMA:
+            self.ema_model = ModelEMA(model=self.model, decay=self.config.TRAIN.EMA_DECAY, device=self.device)
+
+    def _class_weights(self):
+        if not _cfg(self.config.TRAIN, "CLS_WEIGHT", False):
+            return None
+        from sklearn.utils import class_weight
+        df = self.train_labeled_dl.dataset.df
+        y = list(df[self.config.DATA.TARGET_NAME])
+        w = class_weight.compute_class_weight(class_weight="balanced", classes=np.unique(y).tolist(), y=y)
+        return torch.tensor(w, dtype=torch.float).to(self.device)
+
+    def get_config(self, config, optimizer=None, lr_scheduler=None):
+        """``fixmatch.py:36-70`` / ``comatch.py:48-96`` / ``semiformer.py:37-62``.  ``optimizer`` /
+        ``lr_scheduler`` may be injected; by default they are built like the reference does."""
+        self.config = config
+        print(f"Training mode: {self.TRAINING_MODE}")
+        if self.EMA_BEFORE_FREEZE:
+            self._build_ema()
+            self._apply_freeze()
+        else:
+            self._apply_freeze()
+            self._build_ema()
+        self.optimizer = optimizer or build_optimizer(self.model, opt_func=self.opt_func, lr=self.config.TRAIN.BASE_LR)
+        self.lr_scheduler = lr_scheduler or build_scheduler(config=self.config, optimizer=self.optimizer,
+                                                            n_iter_per_epoch=config.TRAIN.EVAL_STEP)
+        self.class_weights = self._class_weights()
+        amp = _cfg(self.config.TRAIN, "AMP", False)
+        self._autocast = (lambda: torch.autocast("cuda", dtype=torch.bfloat16)) if amp else nullcontext
+        self._labeled = BatchSource(self.train_labeled_dl) if hasattr(self, "train_labeled_dl") else None
+        self._unlabeled = BatchSource(self.train_unlabeled_dl) if hasattr(self, "train_unlabeled_dl") else None
+
+    def _after_backward(self, epoch, step_index, losses, summary_loss):
+        """optimizer step, per-iteration LR schedule, EMA, bookkeeping (``fixmatch.py:120-131``)."""
+        self.optimizer.step()
+        if self.lr_scheduler is not None:
+            self.lr_scheduler.step_update(step_index)
+        if self.config.TRAIN.USE_EMA:
+            self.ema_model.update(self.model)          # one multi-tensor launch
+        self.model.zero_grad()
+        summary_loss.update(losses.item(), self.config.DATA.BATCH_SIZE)
+
+    def train_one(self, epoch):
+        self.model.train()
+        summary_loss = AverageMeter()
+        steps = self._steps_in_epoch(epoch)
+        bar = tqdm(range(steps), total=steps)
+        for batch_idx in bar:
+            losses = self._train_step(epoch, batch_idx)
+            self.optimizer.zero_grad()
+            losses.backward()
+            self._after_backward(epoch, epoch * steps + batch_idx, losses, summary_loss)
+            if hasattr(bar, "set_postfix"):
+                bar.set_postfix(loss=summary_loss.avg)
+        return summary_loss
+
+    def _steps_in_epoch(self, epoch):
+        return self.config.TRAIN.EVAL_STEP
+
+    def _train_step(self, epoch, batch_idx):  # pragma: no cover - abstract
+        raise NotImplementedError
+
+    def _eval_forward(self, model, images):
+        return model(images)
+
+    def evaluate_one(self, show_metric=False, show_report=False, show_cf_matrix=False):
+        """Validation on the EMA weights when ``USE_EMA`` (``fixmatch.py:135-178``).  Returns
+        ``(AverageMeter, metrics dict)``; metrics are micro/macro precision, recall, F1 like
+        ``utils.calculate_metrics`` (plots are out of scope)."""
+        eval_model = self.ema_model.ema if self.config.TRAIN.USE_EMA else self.model
+        eval_model.eval()
+        summary_loss = AverageMeter()
+        preds, targs = [], []
+        with torch.no_grad():
+            for images, targets in tqdm(self.valid_dl, total=len(self.valid_dl)):
+                images = images.to(self.device, non_blocking=True)
+                targets = targets.to(self.device, non_blocking=True)
+                outputs = self._eval_forward(eval_model, images)
+                losses = ce_loss(outputs.float(), targets, reduction="mean")
+                summary_loss.update(losses.item(), self.config.DATA.BATCH_SIZE)
+                preds.append(outputs.argmax(dim=1).cpu())
+                targs.append(targets.cpu())
+        preds, targs = torch.cat(preds).numpy(), torch.cat(targs).numpy()
+        metric = self._metrics(preds, targs)
+        if show_metric:
+            print("Metric:\n", metric)
+        if show_report:
+            from sklearn.metrics import classification_report
+            print("Classification Report:\n", classification_report(targs, preds))
+        return summary_loss, metric
+
+    @staticmethod
+    def _metrics(pred, target):
+        from sklearn.metrics import f1_score, precision_score, recall_score
+        kw = dict(y_true=target, y_pred=pred, zero_division=0)
+        out = {}
+        for avg in ("micro", "macro"):
+            out[f"{avg}/precision"] = precision_score(average=avg, **kw)
+            out[f"{avg}/recall"] = recall_score(average=avg, **kw)
+            out[f"{avg}/f1"] = f1_score(average=avg, **kw)
+        return out
+
+    # ---- checkpoints (same dict keys as fixmatch.py:181-236) -------------------------------
+    def _extra_state(self):
+        return {}
+
+    def _load_extra_state(self, checkpoint):
+        pass
+
+    def save_checkpoint(self, foldname):
+        checkpoint = {}
+        if self.config.TRAIN.USE_EMA:
+            checkpoint["ema_state_dict"] = self.ema_model.ema.state_dict()
+        stamp = date.today().strftime("%m_%d_%Y") + "_" + datetime.now().strftime("%H_%M_%S")
+        checkpoint["epoch"] = self.epoch
+        checkpoint["best_valid_perf"] = self.best_valid_perf
+        checkpoint["model_state_dict"] = self.model.state_dict()
+        checkpoint["optimizer"] = self.optimizer.state_dict()
+        checkpoint["scheduler"] = self.lr_scheduler.state_dict() if self.lr_scheduler is not None else None
+        checkpoint.update(self._extra_state())
+        os.makedirs(foldname, exist_ok=True)
+        path = os.path.join(foldname, f"{stamp}_epoch_{self.epoch}.pth")
+        torch.save(checkpoint, path)
+        print("Saved checkpoint")
+        return path
+
+    def load_checkpoint(self, checkpoint_dir, is_train=False):
+        checkpoint = torch.load(checkpoint_dir, map_location="cpu", weights_only=False)
+        self.model.load_state_dict(checkpoint["model_state_dict"])
+        for p in self.model.parameters():
+            p.requires_grad = bool(is_train)
+        if self.config.TRAIN.USE_EMA:
+            self.ema_model.ema.load_state_dict(checkpoint["ema_state_dict"])     # in place: pointers stay valid
+            for p in self.ema_model.ema.parameters():
+                p.requires_grad = bool(is_train)
+        self.epoch_start = checkpoint["epoch"]
+        self.best_valid_perf = checkpoint["best_valid_perf"]
+        self.optimizer.load_state_dict(checkpoint["optimizer"])
+        if self.lr_scheduler is not None and checkpoint.get("scheduler") is not None:
+            self.lr_scheduler.load_state_dict(checkpoint["scheduler"])
+        self._load_extra_state(checkpoint)
+
+    def fit(self):
+        for epoch in range(self.epoch_start, self.config.TRAIN.EPOCHS + 1):
+            self.epoch = epoch
+            best = f"{float(self.best_valid_perf):.3f}" if self.best_valid_perf else "inf"
+            print(f'Training epoch: {self.epoch} | Current LR: {self.optimizer.param_groups[0]["lr"]:.6f} | The best loss: {best}')
+            train_loss = self.train_one(self.epoch)
+            print(f"\tTrain Loss: {train_loss.avg:.3f}")
+            if epoch % self.config.TRAIN.FREQ_EVAL == 0:
+                valid_loss, _ = self.evaluate_one()
+                if not self.best_valid_perf or self.best_valid_perf > valid_loss.avg:
+                    self.best_valid_perf = valid_loss.avg
+                self.save_checkpoint(self.config.TRAIN.SAVE_CP)
+                print(f"\tValid Loss: {valid_loss.avg:.3f}")

@@ -173,3 +173,37 @@ def test_config_roundtrip_and_reference_module_names(tmp_path):
     assert ref_named_ema.ModelEMA.__init__.__code__.co_varnames[:4] == ("self", "model", "decay", "device")
     for n in ("loss", "ema", "utils"):
         sys.modules.pop(n, None)
+
+
+def test_trainer_shells_and_schedules_on_cpu():
+    """Host logic that needs no GPU: optimizer groups, schedules, FixMatch get_config wiring."""
+    import torch.nn as nn
+    from endoscopy_image_classification_b200 import utils
+    from endoscopy_image_classification_b200.fixmatch import FixMatch
+    from endoscopy_image_classification_b200.lr_scheduler import build_scheduler
+    from endoscopy_image_classification_b200.optimizer import build_optimizer
+    net = nn.Sequential(nn.Linear(4, 8), nn.BatchNorm1d(8), nn.Linear(8, 3))
+    opt = build_optimizer(net, "sgd", lr=0.1)
+    assert len(opt.param_groups) == 2 and opt.param_groups[1]["weight_decay"] == 0.0
+    assert len(opt.param_groups[0]["params"]) == 2 and len(opt.param_groups[1]["params"]) == 4   # weights | biases + BN
+    assert build_optimizer(net, "nope") is None
+    A = utils.AttrDict
+    cfg = A(DATA=A(BATCH_SIZE=4, MU=2), MODEL=A(NUM_CLASSES=3, NAME="x"),
+            TRAIN=A(EPOCHS=10, WARMUP_EPOCHS=2, DECAY_EPOCHS=3, WARMUP_LR=0.01, SCH_NAME="cosine", LR_DECAY=0.5, BASE_LR=0.1,
+                    EVAL_STEP=5, USE_EMA=True, EMA_DECAY=0.99, IS_FREEZE=False, CLS_WEIGHT=False, THRES=0.95, T=1.0, LAMBDA_U=1))
+    sch = build_scheduler(cfg, opt, 5)
+    sch.step_update(0)
+    assert abs(opt.param_groups[0]["lr"] - 0.01) < 1e-12
+    sch.step_update(10)
+    assert abs(opt.param_groups[0]["lr"] - (5e-6 + 0.5 * (0.1 - 5e-6) * (1 + np.cos(np.pi * 10 / 50)))) < 1e-9
+    sch.step_update(50)
+    assert opt.param_groups[0]["lr"] == 5e-6
+    cfg.TRAIN.SCH_NAME = "step"
+    s2 = build_scheduler(cfg, build_optimizer(net, "adam", lr=0.1), 5)
+    s2.step_update(31)
+    assert abs(s2.optimizer.param_groups[0]["lr"] - 0.1 * 0.5 ** 2) < 1e-12
+    tr = FixMatch(net, opt_func="Adam", device="cpu")
+    tr.get_dataloader(([], []), [])
+    tr.get_config(cfg)
+    assert tr.ema_model.decay == 0.99 and not tr.ema_model.ema.training and tr.class_weights is None
+    assert tr.epoch_start == 1 and tr.best_valid_perf is None

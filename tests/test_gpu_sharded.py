@@ -1,0 +1,90 @@
+"""2-GPU (NCCL) parity of the rank-sharded CoMatch bank: real kernels on every rank against the
+single-process oracle for the concatenated batch with the full bank.  Skipped with
+fewer than two GPUs (run with `gpurun --gpus 2 -- python -m pytest tests/test_gpu_sharded.py -m gpu`)."""
+import os
+import socket
+import sys
+from pathlib import Path
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+pytestmark = pytest.mark.gpu
+REPO = Path(__file__).resolve().parents[1]
+C, D, B, MU, THR, STEPS = 23, 64, 16, 7, 0.9, 4
+K = 3 * 2 * (B + B * MU)          # 3 steps of 2 ranks: the ring wraps at step 4
+
+
+def _inputs(seed, dtype=torch.float32):
+    sys.path.insert(0, str(REPO))
+    from endoscopy_image_classification_b200.synthetic import comatch_step_inputs, rownorm
+    g = torch.Generator().manual_seed(seed)
+    protos = rownorm(torch.randn(C, D, generator=torch.Generator().manual_seed(7)))
+    b = comatch_step_inputs(g, B, MU, D, C, protos, dtype)
+    b.pop("logits_x")
+    return b
+
+
+def _worker(rank, world, port, out_dir, dtype_name):
+    sys.path.insert(0, str(REPO))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    from endoscopy_image_classification_b200.comatch_head import CoMatchHead
+    dtype = getattr(torch, dtype_name)
+    head = CoMatchHead(C, D, K, THR, enqueue_mode="always", device=f"cuda:{rank}", dtype=dtype, process_group=dist.group.WORLD)
+    outs = []
+    for step in range(STEPS):
+        inp = {k: v.cuda() for k, v in _inputs(100 * step + rank, dtype).items()}
+        for k in ("logits_u_s0", "feats_u_s0", "feats_u_s1"):
+            inp[k].requires_grad_(True)
+        total, lu, lc, mm = head.total_loss(**inp, lambda_u=2.0, lambda_c=0.5)
+        total.backward()
+        outs.append(dict(total=total.detach().cpu(), probs=head.last["probs"].cpu(), mask=head.last["mask"].cpu(),
+                         g_f0=inp["feats_u_s0"].grad.float().cpu(), ptr=head.queue_ptr, dev_ptr=int(head.ptr_state[0])))
+    torch.save(dict(outs=outs, qf=head.queue_feats.float().cpu(), qp=head.queue_probs.float().cpu()),
+               os.path.join(out_dir, f"rank{rank}.pt"))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+@pytest.mark.parametrize("dtype_name,tol", [("float32", 1e-5), ("bfloat16", 1e-2)])
+def test_two_gpu_sharded_bank(tmp_path, dtype_name, tol):
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    sys.path.insert(0, str(REPO))
+    from oracle import ssl_oracle as O
+    world = 2
+    mp.spawn(_worker, args=(world, _free_port(), str(tmp_path), dtype_name), nprocs=world, join=True)
+    res = [torch.load(tmp_path / f"rank{r}.pt", weights_only=False) for r in range(world)]
+    dtype = getattr(torch, dtype_name)
+    state = O.CoMatchState.zeros(K, D, C)
+    hist = [[] for _ in range(world)]
+    n = B + B * MU
+    for step in range(STEPS):
+        inputs = [{k: (v.float() if v.is_floating_point() else v) for k, v in _inputs(100 * step + r, dtype).items()} for r in range(world)]
+        if dtype != torch.float32:
+            state.queue_probs = state.queue_probs.to(dtype).float()
+        ref = O.comatch_head_sharded(state, hist, inputs, thr=THR, num_classes=C)
+        for r in range(world):
+            got = res[r]["outs"][step]
+            err = float((got["probs"].double() - ref[r]["probs"].double()).abs().max() / ref[r]["probs"].abs().max())
+            assert err < tol, (step, r, err)
+            if bool((got["mask"] == ref[r]["mask"]).all()):
+                want = float(2.0 * ref[r]["loss_u"] + 0.5 * ref[r]["loss_contrast"])
+                assert abs(float(got["total"]) - want) < tol * abs(want)
+            gref = 0.5 * ref[r]["grad_feats_s0"]
+            assert float((got["g_f0"] - gref).abs().max() / gref.abs().max()) < tol
+            assert got["ptr"] == got["dev_ptr"] == state.queue_ptr == ((step + 1) * world * n) % K
+    bank_f = torch.cat([res[r]["qf"] for r in range(world)])
+    assert torch.equal(bank_f, state.queue_feats)
+    bank_p = torch.cat([res[r]["qp"] for r in range(world)])
+    assert float((bank_p - state.queue_probs).abs().max()) < tol

@@ -1,0 +1,116 @@
+"""Drop-in trainers on the GPU against the golden fixtures produced by the REAL reference
+FixMatch.train_one / CoMatch.train_one (same scripted model outputs, same targets)."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import T, golden_meta, load_golden, rel_err
+from helpers import Loader, NoSched, ScriptedModel
+from oracle import ssl_oracle as O
+
+pytestmark = pytest.mark.gpu
+C = 23
+
+
+def _config(pkg_utils, **kw):
+    A = pkg_utils.AttrDict
+    base = dict(DATA=A(BATCH_SIZE=kw["B"], MU=kw["MU"], TARGET_NAME="target"),
+                MODEL=A(NUM_CLASSES=C, LOW_DIM=kw.get("D", 64), NAME="scripted"),
+                TRAIN=A(THRES=kw["thr"], T=1.0, USE_EMA=kw.get("ema", False), EMA_DECAY=0.999, LAMBDA_U=1.0, LAMBDA_C=1.0,
+                        EVAL_STEP=kw.get("steps", 1), EVAL_STEP_SUP=kw.get("sup", 0), IS_FREEZE=False, CLS_WEIGHT=False,
+                        BASE_LR=0.0, EPOCHS=1, FREQ_EVAL=1, SAVE_CP=kw.get("save", "/tmp/b200ssl_ckpt")))
+    for k, v in kw.get("train_extra", {}).items():
+        base["TRAIN"][k] = v
+    return A(base)
+
+
+def test_fixmatch_train_one_matches_reference_golden():
+    from endoscopy_image_classification_b200 import utils
+    from endoscopy_image_classification_b200.fixmatch import FixMatch
+    z = load_golden("fixmatch_train_one.npz")
+    m = golden_meta(z)
+    B, Bu = m["B"], m["B"] * m["MU"]
+    steps = [{"logits": T(z[f"s{i}/logits"])} for i in range(2)]
+    model = ScriptedModel(steps, with_feats=False)
+    tr = FixMatch(model, device="cuda")
+    tr.get_dataloader((Loader([(torch.zeros(B, 1), T(z[f"s{i}/targets_x"])) for i in range(2)]),
+                       Loader([((torch.zeros(Bu, 1), torch.zeros(Bu, 1)), None) for _ in range(2)])), None)
+    cfg = _config(utils, B=B, MU=m["MU"], thr=m["thr"], steps=1)
+    tr.get_config(cfg, optimizer=torch.optim.SGD(model.parameters(), lr=0.0), lr_scheduler=NoSched())
+    for i in range(2):
+        meter = tr.train_one(epoch=0)
+        assert abs(meter.avg - float(z[f"s{i}/total_loss"])) < 1e-5 * abs(float(z[f"s{i}/total_loss"]))
+        (leaf,) = model.seen[-1]
+        assert rel_err(leaf.grad, T(z[f"s{i}/grad_logits"])) < 1e-5
+
+
+@pytest.mark.parametrize("qb", [1, 5])
+def test_comatch_train_one_matches_reference_golden(qb):
+    from endoscopy_image_classification_b200 import utils
+    from endoscopy_image_classification_b200.comatch import CoMatch
+    z = load_golden(f"comatch_train_one_qb{qb}.npz")
+    m = golden_meta(z)
+    B, MU, D, n = m["B"], m["MU"], m["D"], m["nsteps"]
+    Bu = B * MU
+    steps = [{"logits": T(z[f"s{i}/logits"]), "feats": T(z[f"s{i}/feats"])} for i in range(n)]
+    model = ScriptedModel(steps, with_feats=True)
+    tr = CoMatch(model, device="cuda")
+    tr.queue_batch = qb
+    tr.get_dataloader((Loader([(torch.zeros(B, 1), T(z[f"s{i}/targets_x"])) for i in range(n)]),
+                       Loader([((torch.zeros(Bu, 1),) * 3, None) for _ in range(1)])), None)
+    tr.get_config(_config(utils, B=B, MU=MU, D=D, thr=m["thr"]), optimizer=torch.optim.SGD(model.parameters(), lr=0.0),
+                  lr_scheduler=NoSched())
+    assert tr.queue_size == qb * (MU + 1) * B and tr.queue_feats.shape == (tr.queue_size, D)
+    for i in range(n):
+        meter = tr.train_one(epoch=1)          # the unlabeled loader holds one batch -> one step
+        assert abs(meter.avg - float(z[f"s{i}/total_loss"])) < 2e-5 * abs(float(z[f"s{i}/total_loss"]))
+        lg, ft = model.seen[-1]
+        assert rel_err(lg.grad, T(z[f"s{i}/grad_logits"])) < 1e-5
+        assert rel_err(ft.grad, T(z[f"s{i}/grad_feats"])) < 1e-5
+        assert tr.queue_ptr == int(z[f"s{i}/queue_ptr"])
+        assert torch.equal(tr.queue_feats.cpu(), T(z[f"s{i}/queue_feats"]))
+    assert len(tr.prob_list) == n
+
+
+def test_semiformer_step_ema_and_checkpoint(tmp_path):
+    """Two-head step == two reference-style consistency losses; EMA runs; checkpoint round-trips
+    (incl. the CoMatch bank extension on the CoMatch trainer)."""
+    from endoscopy_image_classification_b200 import utils
+    from endoscopy_image_classification_b200.comatch import CoMatch
+    from endoscopy_image_classification_b200.semiformer import SemiFormer
+    g = torch.Generator().manual_seed(3)
+    B, MU, thr = 8, 3, 0.7
+    Bu = B * MU
+    steps = [{"logits": 4 * torch.randn(B + 2 * Bu, C, generator=g), "logits2": 4 * torch.randn(B + 2 * Bu, C, generator=g)}]
+    ty = torch.randint(0, C, (B,), generator=g)
+    model = ScriptedModel(steps, with_feats=False, two_heads=True)
+    tr = SemiFormer(model, device="cuda")
+    tr.get_dataloader((Loader([(torch.zeros(B, 1), ty)]), Loader([((torch.zeros(Bu, 1), torch.zeros(Bu, 1)), None)])), None)
+    tr.get_config(_config(utils, B=B, MU=MU, thr=thr, ema=True, sup=0, save=str(tmp_path)),
+                  optimizer=torch.optim.SGD(model.parameters(), lr=0.0), lr_scheduler=NoSched())
+    meter = tr.train_one(epoch=1)
+    lc, lt = steps[0]["logits"], steps[0]["logits2"]
+    w = lc[B:].chunk(2)[0]
+    ref = (O.ce_loss(lc[:B], ty, reduction="mean") + O.ce_loss(lt[:B], ty, reduction="mean")
+           + O.fixmatch_head_details(w, lc[B:].chunk(2)[1], thr)["loss"] + O.fixmatch_head_details(w, lt[B:].chunk(2)[1], thr)["loss"])
+    assert abs(meter.avg - float(ref)) < 1e-5 * abs(float(ref))
+    tr.epoch = 1
+    path = tr.save_checkpoint(str(tmp_path))
+    ck = torch.load(path, weights_only=False)
+    assert {"ema_state_dict", "epoch", "best_valid_perf", "model_state_dict", "optimizer", "scheduler"} <= set(ck)
+    tr.load_checkpoint(path, is_train=True)
+    # CoMatch: bank + DA history are added to the checkpoint (absent in the reference, comatch.py:285-306)
+    cm = CoMatch(ScriptedModel([], True), device="cuda")
+    cm.get_dataloader((Loader([]), Loader([])), None)
+    cm.get_config(_config(utils, B=4, MU=3, D=64, thr=0.9, save=str(tmp_path), train_extra={"ENQUEUE_MODE": "always", "QUEUE_SIZE": 64}),
+                  optimizer=torch.optim.SGD(cm.model.parameters(), lr=0.0), lr_scheduler=NoSched())
+    assert cm.queue_size == 64 and cm.head.enqueue_mode == "always"
+    cm.head.queue_feats.normal_()
+    cm.queue_ptr = 16
+    cm.epoch = 2
+    p2 = cm.save_checkpoint(str(tmp_path))
+    kept = cm.head.queue_feats.clone()
+    cm.head.queue_feats.zero_()
+    cm.queue_ptr = 0
+    cm.load_checkpoint(p2, is_train=True)
+    assert torch.equal(cm.head.queue_feats, kept) and cm.queue_ptr == 16 and int(cm.head.ptr_state[0]) == 16
