@@ -371,6 +371,14 @@ def run_b200(args, wl, rank, world, local_rank):
             line["cpu_baseline"] = cpu
         print(json.dumps(line), flush=True)
     if world > 1:
+        # captured graphs hold NCCL work: they must be released before the communicator is torn down
+        # (destroy_process_group() blocks forever otherwise, seen on 2xB200 with NCCL 2.28.9)
+        import gc
+        graphed.graph = graphed.graph_host = None
+        del graphed
+        gc.collect()
+        torch.cuda.synchronize(dev)
+        dist.barrier()
         dist.destroy_process_group()
 
 
