@@ -282,6 +282,7 @@ def run_b200(args, wl, rank, world, local_rank):
     sampler = ClockSampler(local_rank) if rank == 0 else None
     if sampler:
         time.sleep(1.0)                        # let nvidia-smi start before the timed regions
+    barrier()
     t_start, t_stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.profiler.start()                # ncu --profile-from-start off: only the timed graph replays
     t_start.record()
