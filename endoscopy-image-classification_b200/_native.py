@@ -39,6 +39,7 @@ _vp, _i64, _i32, _f32, _sz = C.c_void_p, C.c_int64, C.c_int32, C.c_float, C.c_si
 SIGNATURES = {
     "b200ssl_version": (_i32, []),
     "b200ssl_last_error_string": (C.c_char_p, []),
+    "b200ssl_debug_set_timing_buffer": (None, [_vp]),
     "b200ssl_workspace_bytes": (_sz, [_i64, _i32, _i64]),
     "b200ssl_fixmatch_head_fwd_bwd": (_i32, [_vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _f32, _f32, _i32,
                                              _vp, _vp, _vp, _vp, _sz, _vp]),

@@ -131,8 +131,9 @@ class CoMatchHead:
         self.queue_probs = torch.zeros(self.geom.shard_rows, self.num_classes, dtype=dtype, device=self.device)
         # transposed, class-padded copy [32, K_local] for the tensor-core smoothing kernel (bf16 banks)
         self.queue_probs_t = None
-        if dtype == torch.bfloat16 and self.num_classes <= 32 and self.low_dim == 64 and self.geom.shard_rows % 8 == 0:
+        if dtype == torch.bfloat16 and self.num_classes <= 31 and self.low_dim == 64 and self.geom.shard_rows % 8 == 0:
             self.queue_probs_t = torch.zeros(32, self.geom.shard_rows, dtype=dtype, device=self.device)
+            self.queue_probs_t[self.num_classes].fill_(1.0)      # "ones" row: the second MMA also yields the row sums
 
     # ---- reference-visible state ------------------------------------------------
     @property

@@ -8,7 +8,9 @@
 namespace b200ssl {
 namespace {
 thread_local char g_err[512] = "";
+unsigned long long* g_timing = nullptr;
 }
+unsigned long long* debug_timing_buffer() { return g_timing; }
 
 int fail(int code, const char* fmt, ...) {
   va_list ap;
@@ -28,6 +30,8 @@ int check_launch(const char* what) {
 using namespace b200ssl;
 
 extern "C" int b200ssl_version(void) { return B200SSL_VERSION; }
+
+extern "C" void b200ssl_debug_set_timing_buffer(void* device_u64) { g_timing = static_cast<unsigned long long*>(device_u64); }
 
 extern "C" const char* b200ssl_last_error_string(void) { return g_err; }
 

@@ -212,7 +212,7 @@ extern "C" int b200ssl_bank_smooth_partial(const void* feats_u_w, const void* qu
   if (dtype != B200SSL_F32 && dtype != B200SSL_BF16) return fail(B200SSL_E_DTYPE, "%s: dtype %d", fn, dtype);
   if (!workspace || (reinterpret_cast<uintptr_t>(workspace) & 255u)) return fail(B200SSL_E_ALIGN, "%s: workspace NULL or not 256-byte aligned", fn);
   // bf16 bank with 128-byte rows: tcgen05 / TMEM / TMA kernel (bank_tc.cu); everything else: exact-fp32 FFMA tiles
-  if (dtype == B200SSL_BF16 && dim == 64 && classes <= 32 && queue_probs_t && bank_rows % 8 == 0 &&
+  if (dtype == B200SSL_BF16 && dim == 64 && classes <= 31 && queue_probs_t && bank_rows % 8 == 0 &&
       !(reinterpret_cast<uintptr_t>(feats_u_w) & 15u) && !(reinterpret_cast<uintptr_t>(queue_feats) & 15u) &&
       !(reinterpret_cast<uintptr_t>(queue_probs_t) & 15u))
     return bank_smooth_tc(feats_u_w, queue_feats, queue_probs_t, rows, bank_rows, classes, temperature, rowsum, numer,

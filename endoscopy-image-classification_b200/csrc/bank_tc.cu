@@ -19,6 +19,8 @@
 // b200ssl_bank_enqueue.
 #include <math.h>
 
+#include <cooperative_groups.h>
+
 #include "common.cuh"
 #include "tc.cuh"
 
@@ -64,31 +66,43 @@ int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_
 
 namespace {
 
+namespace cg = cooperative_groups;
+
 constexpr int kBM = 128;          // queries per CTA  (UMMA M)
 constexpr int kBN = 128;          // keys per tile    (UMMA N of GEMM1 / K of GEMM2)
-constexpr int kCP = 32;           // classes, padded  (UMMA N of GEMM2)
+constexpr int kCP = 32;           // classes + the "ones" column, padded (UMMA N of GEMM2)
 constexpr int kStages = 2;
-constexpr int kTcThreads = 192;
+constexpr int kTcThreads = 320;   // warp 0 TMA + TMEM alloc, warp 1 MMA, warps 2..9 epilogue (2 per TMEM lane quarter)
+constexpr int kMaxCluster = 8;
 constexpr uint32_t kTileA = kBM * 128;                  // 16 KB: [128][64] bf16
 constexpr uint32_t kTileQf = kBN * 128;                 // 16 KB
 constexpr uint32_t kSubQp = kCP * 128;                  //  4 KB: [32][64] bf16
 constexpr uint32_t kTileQp = 2 * kSubQp;                //  8 KB
 constexpr uint32_t kSubP = kBM * 128;                   // 16 KB: [128][64] bf16
-constexpr uint32_t kTileP = 2 * kSubP;                  // 32 KB
+constexpr uint32_t kTileP = 2 * kSubP;                  // 32 KB (re-used as the fp32 reduction tile at the end)
 constexpr uint32_t kSmemData = kTileA + kStages * (kTileQf + kTileQp) + kTileP;   // 96 KB
 constexpr uint32_t kTmemCols = 512;                     // S[0] 0..127, S[1] 128..255, numer 256..287
 constexpr size_t kSmemRequest = 120 * 1024;             // > half an SM: one CTA per SM (it owns all TMEM columns)
+constexpr int kRedLd = 36;                              // floats per row of the reduction tile (16-byte rows, 4-way bank spread)
 
 struct SmoothTcParams {
   long long rows, bank_rows, rows_pad;
-  int C, W, nsplit, tiles_per_split;   // W = round_up(1 + C, 4): floats per row of a split partial
+  int C, W;                       // W = round_up(C + 1, 4): [numer 0..C-1, rowsum] per row of a partial
+  int nsplit, cluster, nouter;    // nsplit = cluster * nouter CTAs share one row tile
   float scale;                    // log2(e) / temperature
   float* rowsum; float* numer;
   float* part; unsigned* tickets;
+  unsigned long long* dbg;
 };
 
 enum { BAR_A = 0, BAR_KV_FULL = 1, BAR_KV_EMPTY = 3, BAR_S_FULL = 5, BAR_S_EMPTY = 7, BAR_P_FULL = 9, BAR_P_EMPTY = 10,
        BAR_ACC = 11, BAR_COUNT = 12 };
+
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 
 __global__ void __launch_bounds__(kTcThreads, 1)
 bank_smooth_tc_kernel(const __grid_constant__ CUtensorMap tm_f, const __grid_constant__ CUtensorMap tm_qf,
@@ -99,15 +113,18 @@ bank_smooth_tc_kernel(const __grid_constant__ CUtensorMap tm_f, const __grid_con
   uint8_t* sQf = sA + kTileA;
   uint8_t* sQp = sQf + kStages * kTileQf;
   uint8_t* sP = sQp + kStages * kTileQp;
+  float* sRed = reinterpret_cast<float*>(sP);             // [128][kRedLd] after the pipeline has drained
   uint64_t* bars = reinterpret_cast<uint64_t*>(sP + kTileP);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + BAR_COUNT);
   volatile int* abort_flag = reinterpret_cast<volatile int*>(tmem_slot + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int row_tile = blockIdx.x, split = blockIdx.y;
+  const int cta = blockIdx.y * gridDim.x + blockIdx.x;
+  if (threadIdx.x == 0) B200SSL_STAMP(p.dbg, cta, 0);
   const long long nktiles = (p.bank_rows + kBN - 1) / kBN;
-  const long long kt0 = (long long)split * p.tiles_per_split;
-  const int T = (int)(min(nktiles, kt0 + p.tiles_per_split) - kt0);
+  const long long kt0 = nktiles * split / p.nsplit;                // balanced: every split owns >= 1 key tile
+  const int T = (int)(nktiles * (split + 1) / p.nsplit - kt0);
 
   if (threadIdx.x == 0) {
     tc::mbar_init(&bars[BAR_A], 1);
@@ -115,9 +132,9 @@ bank_smooth_tc_kernel(const __grid_constant__ CUtensorMap tm_f, const __grid_con
       tc::mbar_init(&bars[BAR_KV_FULL + s], 1);
       tc::mbar_init(&bars[BAR_KV_EMPTY + s], 1);
       tc::mbar_init(&bars[BAR_S_FULL + s], 1);
-      tc::mbar_init(&bars[BAR_S_EMPTY + s], 128);
+      tc::mbar_init(&bars[BAR_S_EMPTY + s], 256);
     }
-    tc::mbar_init(&bars[BAR_P_FULL], 128);
+    tc::mbar_init(&bars[BAR_P_FULL], 256);
     tc::mbar_init(&bars[BAR_P_EMPTY], 1);
     tc::mbar_init(&bars[BAR_ACC], 1);
     *abort_flag = 0;
@@ -133,6 +150,7 @@ bank_smooth_tc_kernel(const __grid_constant__ CUtensorMap tm_f, const __grid_con
   __syncthreads();
   tc::tcgen05_fence_after();
   const uint32_t tmem = *tmem_slot;
+  if (threadIdx.x == 0) B200SSL_STAMP(p.dbg, cta, 1);     // setup (barrier init, TMEM alloc) done
 
   if (warp == 0) {
     // ================= TMA producer =================
@@ -156,6 +174,7 @@ bank_smooth_tc_kernel(const __grid_constant__ CUtensorMap tm_f, const __grid_con
       constexpr uint32_t idesc2 = tc::idesc_bf16_f32(kBM, kCP);
       const uint64_t a_desc = tc::smem_desc_sw128(tc::smem_u32(sA));
       tc::mbar_wait(&bars[BAR_A], 0, abort_flag);
+      B200SSL_STAMP(p.dbg, cta, 2);                         // query tile landed (TMA)
       auto gemm1 = [&](int t) {       // S[b] = F Qf^T   (K = 64 -> 4 x UMMA_K 16)
         const int s = t % kStages, b = t & 1;
         tc::mbar_wait(&bars[BAR_KV_FULL + s], (t / kStages) & 1, abort_flag);
@@ -173,7 +192,7 @@ bank_smooth_tc_kernel(const __grid_constant__ CUtensorMap tm_f, const __grid_con
         tc::mbar_wait(&bars[BAR_P_FULL], t & 1, abort_flag);
         tc::tcgen05_fence_after();
 #pragma unroll
-        for (int kb = 0; kb < 2; ++kb) {   // numer += P QpT^T   (K = 128 keys -> 2 sub-tiles x 4 x UMMA_K 16)
+        for (int kb = 0; kb < 2; ++kb) {   // [numer | rowsum] += P [QpT | 1]^T   (K = 128 keys -> 2 sub-tiles x 4 x UMMA_K 16)
           const uint64_t pa = tc::smem_desc_sw128(tc::smem_u32(sP + kb * kSubP));
           const uint64_t qb = tc::smem_desc_sw128(tc::smem_u32(sQp + s * kTileQp + kb * kSubQp));
 #pragma unroll
@@ -185,66 +204,53 @@ bank_smooth_tc_kernel(const __grid_constant__ CUtensorMap tm_f, const __grid_con
       tc::mma_commit(&bars[BAR_ACC]);
     }
   } else {
-    // ================= epilogue: thread <-> TMEM lane <-> query row =================
-    const int quarter = warp & 3;                 // TMEM lanes [32*quarter, +32) are visible to this warp
+    // ===== epilogue: two threads per TMEM lane (query row), 64 of the 128 key columns each =====
+    const int quarter = warp & 3, half = (warp - 2) >> 2;   // TMEM lanes [32*quarter, +32) are visible to this warp
     const int r_in = quarter * 32 + lane;
     const uint32_t lane_addr = tmem + ((uint32_t)(quarter * 32) << 16);
-    float rowsum = 0.f;
     for (int t = 0; t < T; ++t) {
       const int b = t & 1;
       tc::mbar_wait(&bars[BAR_S_FULL + b], (t >> 1) & 1, abort_flag);
+      if (t == 0 && threadIdx.x == 64) B200SSL_STAMP(p.dbg, cta, 3);   // first S tile ready (TMA + GEMM1)
       if (t >= 1) tc::mbar_wait(&bars[BAR_P_EMPTY], (t - 1) & 1, abort_flag);
       tc::tcgen05_fence_after();
-      const long long key0 = (kt0 + t) * kBN;
-#pragma unroll 1
-      for (int c4 = 0; c4 < 4; ++c4) {
-        uint32_t r[32];
-        tc::tmem_ld_32x32(lane_addr + b * kBN + c4 * 32, r);
-        tc::tmem_ld_wait();
-        uint32_t packed[16];
 #pragma unroll
-        for (int j = 0; j < 32; j += 2) {
-          const float e0 = (key0 + c4 * 32 + j < p.bank_rows) ? exp2f(__uint_as_float(r[j]) * p.scale) : 0.f;
-          const float e1 = (key0 + c4 * 32 + j + 1 < p.bank_rows) ? exp2f(__uint_as_float(r[j + 1]) * p.scale) : 0.f;
-          const __nv_bfloat162 h = __floats2bfloat162_rn(e0, e1);
-          rowsum += __low2float(h) + __high2float(h);     // the weights GEMM2 actually uses
-          packed[j >> 1] = *reinterpret_cast<const uint32_t*>(&h);
-        }
+      for (int c2 = 0; c2 < 2; ++c2) {
+        uint32_t r[32];
+        tc::tmem_ld_32x32(lane_addr + b * kBN + half * 64 + c2 * 32, r);
+        tc::tmem_ld_wait();
+        // keys beyond the bank need no mask: their QpT columns (incl. the ones column) are TMA zero fill
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-          const int sub = c4 >> 1, chunk = (c4 & 1) * 4 + q;
-          uint4 v = make_uint4(packed[4 * q], packed[4 * q + 1], packed[4 * q + 2], packed[4 * q + 3]);
-          *reinterpret_cast<uint4*>(sP + sub * kSubP + tc::sw128_offset(r_in, chunk)) = v;
+          uint32_t w[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float e0 = ex2_approx(__uint_as_float(r[8 * q + 2 * e]) * p.scale);        // comatch.py:180
+            const float e1 = ex2_approx(__uint_as_float(r[8 * q + 2 * e + 1]) * p.scale);
+            const __nv_bfloat162 h = __floats2bfloat162_rn(e0, e1);
+            w[e] = *reinterpret_cast<const uint32_t*>(&h);
+          }
+          *reinterpret_cast<uint4*>(sP + half * kSubP + tc::sw128_offset(r_in, c2 * 4 + q)) = make_uint4(w[0], w[1], w[2], w[3]);
         }
       }
       tc::tcgen05_fence_before();
       tc::mbar_arrive(&bars[BAR_S_EMPTY + b]);
       tc::fence_proxy_async_smem();               // generic-proxy writes of P -> visible to the tensor core
       tc::mbar_arrive(&bars[BAR_P_FULL]);
+      if (t == T - 1 && threadIdx.x == 64) B200SSL_STAMP(p.dbg, cta, 4);   // last exp tile done
     }
-    tc::mbar_wait(&bars[BAR_ACC], 0, abort_flag);
+    tc::mbar_wait(&bars[BAR_ACC], 0, abort_flag);           // all MMAs retired: P smem is free, accumulator final
+    if (threadIdx.x == 64) B200SSL_STAMP(p.dbg, cta, 5);
     tc::tcgen05_fence_after();
-    uint32_t r[32];
-    tc::tmem_ld_32x32(lane_addr + 2 * kBN, r);
-    tc::tmem_ld_wait();
-    const long long grow = (long long)row_tile * kBM + r_in;
-    if (p.nsplit == 1) {
-      if (grow < p.rows) {
-        p.rowsum[grow] = rowsum;
+    if (half == 0) {                                        // accumulator [numer | rowsum] -> fp32 reduction tile in smem
+      uint32_t r[32];
+      tc::tmem_ld_32x32(lane_addr + 2 * kBN, r);
+      tc::tmem_ld_wait();
+      float4* dst = reinterpret_cast<float4*>(sRed + r_in * kRedLd);
 #pragma unroll
-        for (int c = 0; c < kCP; ++c)
-          if (c < p.C) p.numer[grow * p.C + c] = __uint_as_float(r[c]);
-      }
-    } else {
-      // split partial, row-interleaved [split][rows_pad][W]: element 0 = rowsum, 1..C = numer
-      float4* o = reinterpret_cast<float4*>(p.part + ((size_t)split * p.rows_pad + grow) * p.W);
-      float vals[kCP + 4];
-      vals[0] = rowsum;
-#pragma unroll
-      for (int c = 0; c < kCP; ++c) vals[1 + c] = __uint_as_float(r[c]);
-#pragma unroll
-      for (int q = 0; q < (kCP + 4) / 4; ++q)
-        if (4 * q < p.W) o[q] = make_float4(vals[4 * q], vals[4 * q + 1], vals[4 * q + 2], vals[4 * q + 3]);
+      for (int q = 0; q < 8; ++q)
+        dst[q] = make_float4(__uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1]), __uint_as_float(r[4 * q + 2]),
+                             __uint_as_float(r[4 * q + 3]));
     }
     tc::tcgen05_fence_before();
   }
@@ -253,51 +259,104 @@ bank_smooth_tc_kernel(const __grid_constant__ CUtensorMap tm_f, const __grid_con
     tc::tcgen05_fence_after();
     tc::tmem_dealloc(tmem, kTmemCols);
   }
-  if (p.nsplit == 1) return;
-  // last split CTA of this row tile folds the partials in split order (deterministic)
+  if (threadIdx.x == 0) B200SSL_STAMP(p.dbg, cta, 6);      // accumulator staged, TMEM released
+
+  // ---- fold the splits of this row tile: first inside the cluster through distributed shared memory ----
+  cg::cluster_group cluster = cg::this_cluster();
+  const int CL = p.cluster;
+  const int crank = CL > 1 ? (int)cluster.block_rank() : 0;
+  if (CL > 1) cluster.sync();                              // every CTA's reduction tile is complete and visible
+  const int RB = kBM / CL;                                 // rows this CTA reduces
+  const int W = p.W, C = p.C;
+  const int outer = split / CL;
+  const long long i0 = (long long)row_tile * kBM;
+  const float* peer[kMaxCluster];
+#pragma unroll
+  for (int r = 0; r < kMaxCluster; ++r) peer[r] = (CL > 1 && r < CL) ? cluster.map_shared_rank(sRed, r) : sRed;
+  const int W4 = W / 4;
+  for (int idx = threadIdx.x; idx < RB * W4; idx += blockDim.x) {
+    const int rr = idx / W4, q4 = idx - rr * W4;
+    const int row = crank * RB + rr;
+    float4 v[kMaxCluster];
+#pragma unroll
+    for (int r = 0; r < kMaxCluster; ++r)                  // all remote loads in flight at once
+      if (r < CL) v[r] = *reinterpret_cast<const float4*>(peer[r] + row * kRedLd + 4 * q4);
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int r = 0; r < kMaxCluster; ++r)                  // rank order: deterministic
+      if (r < CL) { acc.x += v[r].x; acc.y += v[r].y; acc.z += v[r].z; acc.w += v[r].w; }
+    const long long grow = i0 + row;
+    const float vv[4] = {acc.x, acc.y, acc.z, acc.w};
+    if (p.nouter == 1) {
+      if (grow < p.rows) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int col = 4 * q4 + j;
+          if (col < C) p.numer[grow * C + col] = vv[j];
+          else if (col == C) p.rowsum[grow] = vv[j];       // the ones column: sum_k P_ik
+        }
+      }
+    } else {
+      *reinterpret_cast<float4*>(p.part + ((size_t)outer * p.rows_pad + grow) * W + 4 * q4) = acc;
+    }
+  }
+  if (CL > 1) cluster.sync();                              // nobody leaves while its smem is still being read
+  if (threadIdx.x == 0) B200SSL_STAMP(p.dbg, cta, 7);      // cluster fold done
+  if (p.nouter == 1) return;
+
+  // ---- then across clusters: last CTA of the row tile folds the `nouter` partials in order ----
   __shared__ bool s_last;
   __threadfence();
   __syncthreads();
   if (threadIdx.x == 0) s_last = (atomicAdd(&p.tickets[row_tile], 1u) == (unsigned)p.nsplit - 1);
   __syncthreads();
+  if (threadIdx.x == 0) B200SSL_STAMP(p.dbg, cta, 8);      // ticket taken
   if (!s_last) return;
   __threadfence();
-  const long long i0 = (long long)row_tile * kBM;
   const int mrows = (int)min((long long)kBM, p.rows - i0);
-  const int W = p.W, C = p.C;
-  fold_splits_vec4(reinterpret_cast<const float4*>(p.part + (size_t)i0 * W), (size_t)p.rows_pad * W / 4, p.nsplit,
+  fold_splits_vec4(reinterpret_cast<const float4*>(p.part + (size_t)i0 * W), (size_t)p.rows_pad * W / 4, p.nouter,
                    mrows * W / 4, [&](int i, float4 v) {
                      const float vv[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
                      for (int j = 0; j < 4; ++j) {
                        const int e = 4 * i + j, row = e / W, col = e - row * W;
-                       if (col == 0) p.rowsum[i0 + row] = vv[j];
-                       else if (col <= C) p.numer[(i0 + row) * C + col - 1] = vv[j];
+                       if (col < C) p.numer[(i0 + row) * C + col] = vv[j];
+                       else if (col == C) p.rowsum[i0 + row] = vv[j];
                      }
                    });
-  if (threadIdx.x == 0) p.tickets[row_tile] = 0u;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    p.tickets[row_tile] = 0u;
+    B200SSL_STAMP(p.dbg, cta, 9);                           // fold done (last CTA of the row tile only)
+  }
+}
+
+// cluster size (power of two <= 8) and number of clusters per row tile
+void smooth_tc_plan(long long rows, long long bank_rows, int* cluster, int* nouter) {
+  const long long row_tiles = (rows + kBM - 1) / kBM;
+  const long long ktiles = (bank_rows + kBN - 1) / kBN;
+  int cl = 1;
+  while (cl * 2 <= kMaxCluster && cl * 2 <= ktiles) cl *= 2;
+  long long no = 1;
+  if (ktiles / cl > 8) {                                    // long serial key loops: add clusters while SMs are free
+    no = kNumSMs / (row_tiles * cl);
+    if (no < 1) no = 1;
+    if (no > ktiles / cl) no = ktiles / cl;
+  }
+  *cluster = cl;
+  *nouter = (int)no;
 }
 
 }  // namespace
 
-int smooth_tc_nsplit(long long rows, long long bank_rows, int* tiles_per_split) {
-  const long long row_tiles = (rows + kBM - 1) / kBM;
-  const long long ktiles = (bank_rows + kBN - 1) / kBN;
-  long long want = (kNumSMs + row_tiles - 1) / row_tiles;     // one CTA per SM
-  if (want < 1) want = 1;
-  if (want > ktiles) want = ktiles;
-  const long long tps = (ktiles + want - 1) / want;
-  if (tiles_per_split) *tiles_per_split = (int)tps;
-  return (int)((ktiles + tps - 1) / tps);
-}
-
 size_t smooth_tc_workspace_floats(long long rows, long long bank_rows, int classes) {
   const long long row_tiles = (rows + kBM - 1) / kBM;
-  const int ns = smooth_tc_nsplit(rows, bank_rows, nullptr);
-  return ns > 1 ? (size_t)ns * row_tiles * kBM * ((1 + classes + 3) & ~3) : 0;
+  int cl, no;
+  smooth_tc_plan(rows, bank_rows, &cl, &no);
+  return no > 1 ? (size_t)no * row_tiles * kBM * ((1 + classes + 3) & ~3) : 0;
 }
 
-// bf16, dim 64, classes <= 32, bank rows a multiple of 8: the tensor-core path.
+// bf16, dim 64, classes <= 31, bank rows a multiple of 8: the tensor-core path.
 int bank_smooth_tc(const void* feats, const void* queue_feats, const void* queue_probs_t, long long rows,
                    long long bank_rows, int classes, float temperature, float* rowsum, float* numer, void* workspace,
                    size_t workspace_bytes, cudaStream_t stream) {
@@ -305,8 +364,9 @@ int bank_smooth_tc(const void* feats, const void* queue_feats, const void* queue
   SmoothTcParams p{};
   p.rows = rows; p.bank_rows = bank_rows; p.C = classes; p.W = (1 + classes + 3) & ~3;
   p.scale = (float)(1.4426950408889634 / (double)temperature);
-  p.rowsum = rowsum; p.numer = numer;
-  p.nsplit = smooth_tc_nsplit(rows, bank_rows, &p.tiles_per_split);
+  p.rowsum = rowsum; p.numer = numer; p.dbg = debug_timing_buffer();
+  smooth_tc_plan(rows, bank_rows, &p.cluster, &p.nouter);
+  p.nsplit = p.cluster * p.nouter;
   const long long row_tiles = (rows + kBM - 1) / kBM;
   p.rows_pad = row_tiles * kBM;
   const size_t need = kWsHeaderBytes + sizeof(float) * smooth_tc_workspace_floats(rows, bank_rows, classes);
@@ -325,8 +385,21 @@ int bank_smooth_tc(const void* feats, const void* queue_feats, const void* queue
     attr_set = true;
   }
   static_assert(kSmemData + 1024 + 256 <= kSmemRequest, "shared memory budget");
-  dim3 grid((unsigned)row_tiles, (unsigned)p.nsplit);
-  bank_smooth_tc_kernel<<<grid, kTcThreads, kSmemRequest, stream>>>(tm_f, tm_qf, tm_qpt, p);
+  static_assert(kBM * kRedLd * sizeof(float) <= kTileP, "reduction tile must fit in the P buffer");
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)row_tiles, (unsigned)p.nsplit, 1);
+  cfg.blockDim = dim3(kTcThreads, 1, 1);
+  cfg.dynamicSmemBytes = kSmemRequest;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 1;
+  attr[0].val.clusterDim.y = (unsigned)p.cluster;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, bank_smooth_tc_kernel, tm_f, tm_qf, tm_qpt, p);
+  if (e != cudaSuccess) return fail((int)e, "%s: cudaLaunchKernelEx: %s", fn, cudaGetErrorString(e));
   return check_launch(fn);
 }
 

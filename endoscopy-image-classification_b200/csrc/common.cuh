@@ -20,6 +20,15 @@ inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s
 
 constexpr int kNumSMs = 148;  // B200
 
+// Optional device-side timing probe (tools/kernel_timeline.py): when a buffer is registered with
+// b200ssl_debug_set_timing_buffer(), instrumented kernels store clock64() stamps per CTA:
+// dbg[cta * 16 + slot].  NULL (the default) costs one predictable branch per stamp.
+unsigned long long* debug_timing_buffer();
+#define B200SSL_STAMP(dbg, cta, slot)                                            \
+  do {                                                                          \
+    if ((dbg) != nullptr) (dbg)[(size_t)(cta) * 16 + (slot)] = clock64();       \
+  } while (0)
+
 // Workspace layout (caller zero-fills it once): [0,256) ticket counters of the
 // row kernels, [256, 256+64K) per-row-tile tickets of the similarity kernels,
 // then float partials.  Tickets reset themselves, partials are scratch.

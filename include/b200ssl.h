@@ -59,6 +59,9 @@ enum b200ssl_error {
 
 B200SSL_API int b200ssl_version(void);
 B200SSL_API const char* b200ssl_last_error_string(void);
+/* Debug aid (tools/kernel_timeline.py): device buffer of uint64 [ctas * 16] that instrumented
+ * kernels fill with clock64() stamps; NULL (default) disables it. */
+B200SSL_API void b200ssl_debug_set_timing_buffer(void* device_u64);
 /* bytes of scratch any single call below may need for the given problem */
 B200SSL_API size_t b200ssl_workspace_bytes(int64_t rows, int32_t classes, int64_t bank_rows);
 
@@ -121,10 +124,12 @@ B200SSL_API int b200ssl_comatch_da(const void* logits_u_w, int64_t rows, int32_t
  * feats / queue_* share `dtype`; rowsum/numer are fp32.  No running max (the
  * reference has none; |<f,q>|/tau <= 5 for unit-norm embeddings).
  * Two code paths, chosen by storage type (not a backend switch):
- *   - bf16 bank, dim == 64, classes <= 32, bank_rows % 8 == 0 and queue_probs_t
- *     given (bf16 [32, bank_rows]: transposed, class-padded copy of queue_probs
- *     maintained by b200ssl_bank_enqueue): tcgen05.mma with TMEM accumulators,
- *     operands staged by TMA (csrc/bank_tc.cu);
+ *   - bf16 bank, dim == 64, classes <= 31, bank_rows % 8 == 0 and queue_probs_t
+ *     given (bf16 [32, bank_rows]: rows 0..classes-1 = transposed copy of queue_probs
+ *     maintained by b200ssl_bank_enqueue, row `classes` = all ones so that the second
+ *     MMA also produces the row sums, remaining rows zero): tcgen05.mma with TMEM
+ *     accumulators, operands staged by TMA, split partials folded through thread-block
+ *     cluster distributed shared memory (csrc/bank_tc.cu);
  *   - otherwise exact-fp32 FFMA tiles (the reference's matrix product is true fp32).
  */
 B200SSL_API int b200ssl_bank_smooth_partial(const void* feats_u_w, const void* queue_feats, const void* queue_probs,
