@@ -68,14 +68,15 @@ def main():
     head._k_da(lw)
     rowsum, numer = head._k_smooth(fw)
     fin = head._k_finalize(lw, ls0, rowsum, numer)
-    stats, _ = head._k_contrast_fwd(fs0, fs1, fin["probs"], fin["scalars"])
+    stats, _ = head._k_contrast_fwd(fs0, fs1, fin["probs"], fin["scalars"], probs_hl=fin["probs_hl"])
     one = torch.ones(1, device=dev)
     out["comatch_da"] = graph_time(lambda: head._k_da(lw), a.reps)
     out["bank_smooth"] = graph_time(lambda: head._k_smooth(fw), a.reps)
     out["comatch_finalize"] = graph_time(lambda: head._k_finalize(lw, ls0, rowsum, numer), a.reps)
     out["bank_enqueue"] = graph_time(lambda: head._k_enqueue(fw, fx, fin["probs_orig"], tx, 0, a.rows + a.batch), a.reps)
-    out["contrast_fwd(2 kernels)"] = graph_time(lambda: head._k_contrast_fwd(fs0, fs1, fin["probs"], fin["scalars"]), a.reps)
-    out["contrast_bwd"] = graph_time(lambda: head._k_contrast_bwd(fs0, fs1, fin["probs"], stats, one), a.reps)
+    hl = fin["probs_hl"]
+    out["contrast_fwd"] = graph_time(lambda: head._k_contrast_fwd(fs0, fs1, fin["probs"], fin["scalars"], probs_hl=hl), a.reps)
+    out["contrast_bwd"] = graph_time(lambda: head._k_contrast_bwd(fs0, fs1, fin["probs"], stats, one, probs_hl=hl), a.reps)
     out["scale_inplace"] = graph_time(lambda: head._k_scale(fin["grad_s0"], one), a.reps)
     w = b["logits_u_w"]
     out["fixmatch_head_fwd_bwd"] = graph_time(lambda: fixmatch_head(w, ls0, None, 0.95), a.reps)
