@@ -90,7 +90,12 @@ class CoMatchHead:
     ``enqueue_mode``: ``'reference'`` keeps the guard ``n == queue_size`` of
     ``comatch.py:192`` (quirk Q1: with ``queue_batch=5`` the bank is never
     written); ``'always'`` is the ring write without the guard (upstream CoMatch).
+
+    Up to ``FUSED_ROWS_MAX`` unlabeled rows (unsharded bank, classes <= 32) the row phase
+    (DA + finalize + enqueue) is ONE thread-block-cluster launch; set ``fuse_rows = False`` to
+    force the three separate kernels (larger batches and sharded banks always use them).
     """
+    FUSED_ROWS_MAX = 2048
 
     def __init__(self, num_classes: int, low_dim: int, queue_size: int, thr: float, *, alpha: float = 0.9,
                  temperature: float = 0.2, contrast_th: float = 0.8, gamma: float = 2.0, da_window: int = 32,
@@ -118,6 +123,7 @@ class CoMatchHead:
         self.da_state = torch.zeros(2, dtype=torch.int32, device=self.device)   # count, head
         self.prob_avg = torch.empty(self.num_classes, dtype=torch.float32, device=self.device)
         self._pristine = True
+        self.fuse_rows = True
         self.last = {}
 
     def _check_backend(self) -> None:
@@ -217,31 +223,37 @@ class CoMatchHead:
             self._alloc_bank(lw.dtype)          # still all-zero: re-create in the step's dtype
         R, geom = self.geom.world_size, self.geom
 
-        self._k_da(lw)                                                   # K2 (rank-local history)
-        # queries of every rank (the enqueue block contains them): [R*n, D], rank-major
-        block_f = torch.cat([fw, fx], dim=0) if R > 1 else None
-        gathered_f = all_gather_rows(block_f, self.pg) if R > 1 else None
-        rowsum = numer = None
-        if self.smoothing:                                               # K3, bank as of *before* this step's enqueue
-            if R == 1:
-                rowsum, numer = self._k_smooth(fw)
-            else:
-                n = rows + n_x
-                queries = gathered_f.view(R, n, D)[:, :rows, :].reshape(R * rows, D)
-                rs_all, nm_all = self._k_smooth(queries)
-                rowsum = reduce_scatter_rows(rs_all, self.pg)
-                numer = reduce_scatter_rows(nm_all, self.pg)
-        out = self._k_finalize(lw, ls0, rowsum, numer)                   # K2b + K4 + K7
         n = rows + n_x
-        if geom.should_enqueue(n, self.enqueue_mode):                    # K5
-            if R == 1:
-                self._k_enqueue(fw, fx, out["probs_orig"], tx, 0, n)
-            else:
-                po_all = all_gather_rows(out["probs_orig"], self.pg).view(R, rows, C)
-                tx_all = all_gather_rows(tx, self.pg).view(R, n_x)
-                gf = gathered_f.view(R, n, D)
-                for r in range(R):                                       # block r sits at ptr + r*n
-                    self._k_enqueue(gf[r, :rows], gf[r, rows:], po_all[r], tx_all[r], r * n, R * n if r == R - 1 else 0)
+        do_enqueue = geom.should_enqueue(n, self.enqueue_mode)
+        if self.fuse_rows and R == 1 and C <= 32 and rows <= self.FUSED_ROWS_MAX:
+            # small batch, unsharded bank: K3, then ONE cluster launch for DA + finalize + enqueue
+            rowsum, numer = self._k_smooth(fw) if self.smoothing else (None, None)
+            out = self._k_rows_fused(lw, ls0, rowsum, numer, fw, fx, tx, do_enqueue)
+        else:
+            self._k_da(lw)                                                   # K2 (rank-local history)
+            # queries of every rank (the enqueue block contains them): [R*n, D], rank-major
+            block_f = torch.cat([fw, fx], dim=0) if R > 1 else None
+            gathered_f = all_gather_rows(block_f, self.pg) if R > 1 else None
+            rowsum = numer = None
+            if self.smoothing:                                               # K3, bank as of *before* this step's enqueue
+                if R == 1:
+                    rowsum, numer = self._k_smooth(fw)
+                else:
+                    queries = gathered_f.view(R, n, D)[:, :rows, :].reshape(R * rows, D)
+                    rs_all, nm_all = self._k_smooth(queries)
+                    rowsum = reduce_scatter_rows(rs_all, self.pg)
+                    numer = reduce_scatter_rows(nm_all, self.pg)
+            out = self._k_finalize(lw, ls0, rowsum, numer)                   # K2b + K4 + K7
+            if do_enqueue:                                                   # K5
+                if R == 1:
+                    self._k_enqueue(fw, fx, out["probs_orig"], tx, 0, n)
+                else:
+                    po_all = all_gather_rows(out["probs_orig"], self.pg).view(R, rows, C)
+                    tx_all = all_gather_rows(tx, self.pg).view(R, n_x)
+                    gf = gathered_f.view(R, n, D)
+                    for r in range(R):                                       # block r sits at ptr + r*n
+                        self._k_enqueue(gf[r, :rows], gf[r, rows:], po_all[r], tx_all[r], r * n, R * n if r == R - 1 else 0)
+        if do_enqueue:
             self._queue_ptr = geom.next_ptr(self._queue_ptr, n)
             self._pristine = False
         stats, loss_c = self._k_contrast_fwd(fs0, fs1, out["probs"], out["scalars"], lambda_u, lambda_c,
@@ -295,6 +307,28 @@ class CoMatchHead:
             out["lbs"].data_ptr(),
             out["mask"].data_ptr(), out["grad_s0"].data_ptr(), out["scalars"].data_ptr(), ws, wsb,
             N.stream_ptr(self.device)), "comatch_finalize")
+        return out
+
+    def _k_rows_fused(self, lw, ls0, rowsum, numer, fw, fx, tx, do_enqueue: bool) -> dict:
+        """DA statistics + finalisation (+ enqueue) in one cluster launch (``b200ssl_comatch_rows_fused``)."""
+        rows, C = lw.shape
+        f32 = dict(dtype=torch.float32, device=self.device)
+        out = {"probs": torch.empty(rows, C, **f32), "probs_orig": torch.empty(rows, C, **f32),
+               "scores": torch.empty(rows, **f32), "mask": torch.empty(rows, **f32),
+               "lbs": torch.empty(rows, dtype=torch.int64, device=self.device),
+               "grad_s0": torch.empty_like(ls0), "scalars": torch.empty(4, **f32),
+               "probs_hl": (torch.empty(rows, 64, dtype=torch.bfloat16, device=self.device)
+                            if (lw.dtype == torch.bfloat16 and C <= 32 and self.low_dim == 64) else None)}
+        enq = do_enqueue
+        N.check(N.lib().b200ssl_comatch_rows_fused(
+            lw.data_ptr(), ls0.data_ptr(), N.ptr(rowsum), N.ptr(numer), rows, C, N.dtype_enum(lw),
+            float(np.float32(self.alpha)), float(np.float32(1.0 - self.alpha)), self.thr, self.gamma,
+            self.da_ring.data_ptr(), self.da_state.data_ptr(), self.da_window, self.prob_avg.data_ptr(),
+            out["probs"].data_ptr(), out["probs_orig"].data_ptr(), N.ptr(out["probs_hl"]), out["scores"].data_ptr(),
+            out["lbs"].data_ptr(), out["mask"].data_ptr(), out["grad_s0"].data_ptr(), out["scalars"].data_ptr(),
+            self.queue_feats.data_ptr() if enq else None, self.queue_probs.data_ptr() if enq else None,
+            N.ptr(self.queue_probs_t) if enq else None, fw.data_ptr(), fx.data_ptr(), tx.data_ptr(), fx.shape[0],
+            self.low_dim, self.ptr_state.data_ptr(), self.queue_size, N.stream_ptr(self.device)), "comatch_rows_fused")
         return out
 
     def _k_enqueue(self, fw, fx, probs_orig, tx, block_offset: int, advance: int) -> None:

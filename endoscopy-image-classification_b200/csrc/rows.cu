@@ -9,6 +9,7 @@
 //   f2  labeled_ce_kernel      code/loss.py:103-119, 308-364 (+ bwd)
 //   K2  comatch_da_kernel      code/comatch.py:167-173
 //   K4/K7 comatch_finalize_kernel  code/comatch.py:174-176,182,184-185,216-220 (+ bwd)
+#include <cooperative_groups.h>
 #include <math.h>
 
 #include "common.cuh"
@@ -391,32 +392,14 @@ __device__ __forceinline__ float pow_gamma(float b, float gamma) {
   return powf(b, gamma);
 }
 
-template <typename T, int LPR, int EPL>
-__global__ void __launch_bounds__(kRowThreads) comatch_finalize_kernel(const FinalizeParams p) {
-  using Cfg = RowCfg<LPR, EPL>;
-  constexpr int ROWS = Cfg::kRowsPerTile;
-  extern __shared__ float smem[];
+// One row of the CoMatch finalisation (LPR lanes): pseudo-label from the weak logits in `sw`, alpha-mix
+// with the smoothing sums (`sn`, rowsum), confidence mask, focal soft-CE + gradient against the strong
+// logits in `ss`.  Leaves probs in sw, probs_orig in so, the gradient in ss; adds (loss, mask) to acc.
+template <int LPR, int EPL>
+__device__ __forceinline__ void finalize_row(const FinalizeParams& p, const float* __restrict__ prob_avg, float* sw, float* ss,
+                                             float* so, const float* sn, long long row0, int r, bool valid, int gl, bool smooth,
+                                             float inv_rows, float (&acc)[2]) {
   const int C = p.C;
-  float* sw = smem;            // weak logits  -> probs
-  float* ss = sw + ROWS * C;   // strong logits -> grad
-  float* so = ss + ROWS * C;   // probs_orig
-  float* sn = so + ROWS * C;   // numer
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int gl = lane % LPR, rw = lane / LPR;
-  const bool smooth = p.rowsum != nullptr && p.numer != nullptr;
-  const float inv_rows = 1.0f / (float)p.rows;
-  const long long ntiles = (p.rows + ROWS - 1) / ROWS;
-  float acc[2] = {0.f, 0.f};
-  for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    const long long row0 = tile * ROWS;
-    const int nrows = (int)min((long long)ROWS, p.rows - row0);
-    const int cnt = nrows * C;
-    tile_g2s(static_cast<const T*>(p.w) + row0 * C, sw, cnt);
-    tile_g2s(static_cast<const T*>(p.s0) + row0 * C, ss, cnt);
-    if (smooth) tile_g2s(p.numer + row0 * C, sn, cnt);
-    __syncthreads();
-    const int r = warp * Cfg::kRowsPerWarp + rw;
-    const bool valid = r < nrows;
     float x[EPL], e[EPL], pr[EPL];
     float mx, sum;
     // softmax + DA divide + renormalise (comatch.py:163,174-176)
@@ -426,7 +409,7 @@ __global__ void __launch_bounds__(kRowThreads) comatch_finalize_kernel(const Fin
 #pragma unroll
     for (int k = 0; k < EPL; ++k) {
       const int c = gl + k * LPR;
-      pr[k] = (c < C) ? __fdiv_rn(__fdiv_rn(e[k], sum), p.prob_avg[c]) : 0.f;
+      pr[k] = (c < C) ? __fdiv_rn(__fdiv_rn(e[k], sum), prob_avg[c]) : 0.f;
       q += pr[k];
     }
     q = group_sum<LPR>(q);
@@ -496,6 +479,35 @@ __global__ void __launch_bounds__(kRowThreads) comatch_finalize_kernel(const Fin
         if (c < C) ss[r * C + c] = coef * (__fdiv_rn(e[k], sum) * psum - pr[k]);
       }
     }
+}
+
+template <typename T, int LPR, int EPL>
+__global__ void __launch_bounds__(kRowThreads) comatch_finalize_kernel(const FinalizeParams p) {
+  using Cfg = RowCfg<LPR, EPL>;
+  constexpr int ROWS = Cfg::kRowsPerTile;
+  extern __shared__ float smem[];
+  const int C = p.C;
+  float* sw = smem;            // weak logits  -> probs
+  float* ss = sw + ROWS * C;   // strong logits -> grad
+  float* so = ss + ROWS * C;   // probs_orig
+  float* sn = so + ROWS * C;   // numer
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int gl = lane % LPR, rw = lane / LPR;
+  const bool smooth = p.rowsum != nullptr && p.numer != nullptr;
+  const float inv_rows = 1.0f / (float)p.rows;
+  const long long ntiles = (p.rows + ROWS - 1) / ROWS;
+  float acc[2] = {0.f, 0.f};
+  for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const long long row0 = tile * ROWS;
+    const int nrows = (int)min((long long)ROWS, p.rows - row0);
+    const int cnt = nrows * C;
+    tile_g2s(static_cast<const T*>(p.w) + row0 * C, sw, cnt);
+    tile_g2s(static_cast<const T*>(p.s0) + row0 * C, ss, cnt);
+    if (smooth) tile_g2s(p.numer + row0 * C, sn, cnt);
+    __syncthreads();
+    const int r = warp * Cfg::kRowsPerWarp + rw;
+    const bool valid = r < nrows;
+    finalize_row<LPR, EPL>(p, p.prob_avg, sw, ss, so, sn, row0, r, valid, gl, smooth, inv_rows, acc);
     __syncthreads();
     tile_s2g(sw, p.probs + row0 * C, cnt);
     tile_s2g(so, p.probs_orig + row0 * C, cnt);
@@ -508,6 +520,185 @@ __global__ void __launch_bounds__(kRowThreads) comatch_finalize_kernel(const Fin
     p.out[0] = total[0] / (float)p.rows;
     p.out[1] = total[1] / (float)p.rows;
   }
+}
+
+// ================================================= fused K2 + K2b/K4/K7 (+ K5) ==================
+// One thread-block cluster does the whole row phase of a CoMatch step for small batches: softmax
+// column means -> (cluster exchange through distributed shared memory) -> DA history + prob_avg
+// -> finalisation of every row -> optional ring-buffer enqueue -> loss / mask-mean (second
+// exchange).  No global tickets, no second and third launch: at the reference's sizes the
+// separate kernels cost 12 + 10 + 5 us of pure latency chains (profiles/README.md).
+constexpr int kFusedThreads = 512;
+constexpr int kFusedWarps = kFusedThreads / 32;
+constexpr int kFusedRows = kFusedWarps * 4;      // LPR = 8 -> 4 rows per warp, 64 rows per pass
+constexpr int kFusedMaxCluster = 8;
+
+struct FusedParams {
+  FinalizeParams f;
+  float* ring; int* state; int window;
+  // optional enqueue of [unlabeled-weak ; labeled] rows (qf == nullptr: skip)
+  void* qf; void* qp; void* qpt; const void* fu; const void* fx; const long long* tx;
+  long long n_x; int D; long long* ptr_state; long long K;
+  int CL; long long rows_per_cta;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(kFusedThreads) comatch_rows_fused_kernel(const FusedParams p) {
+  namespace cg = cooperative_groups;
+  constexpr int LPR = 8, EPL = 4, ROWS = kFusedRows;
+  extern __shared__ float smem[];
+  const FinalizeParams& f = p.f;
+  const int C = f.C;
+  float* sw = smem;
+  float* ss = sw + ROWS * C;
+  float* so = ss + ROWS * C;
+  float* sn = so + ROWS * C;
+  float* scol = sn + ROWS * C;      // [32] column sums of this CTA
+  float* savg = scol + 32;          // [32] prob_avg
+  float* sred = savg + 32;          // [2]  (loss, mask) of this CTA
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int gl = lane % LPR, rw = lane / LPR;
+  cg::cluster_group cluster = cg::this_cluster();
+  const int CL = p.CL;
+  const int crank = CL > 1 ? (int)cluster.block_rank() : 0;
+  const long long r_lo = min(f.rows, (long long)crank * p.rows_per_cta), r_hi = min(f.rows, r_lo + p.rows_per_cta);
+  const bool smooth = f.rowsum != nullptr && f.numer != nullptr;
+  const float inv_rows = 1.0f / (float)f.rows;
+  const long long ptr = p.qf ? *reinterpret_cast<volatile long long*>(p.ptr_state) : 0;
+
+  // ---- phase 1: softmax column sums of the rows this CTA owns (comatch.py:163,169) ----
+  if (tid < 32) scol[tid] = 0.f;
+  for (long long row0 = r_lo; row0 < r_hi; row0 += ROWS) {
+    const int nrows = (int)min((long long)ROWS, r_hi - row0);
+    __syncthreads();
+    tile_g2s(static_cast<const T*>(f.w) + row0 * C, sw, nrows * C);
+    __syncthreads();
+    const int r = warp * 4 + rw;
+    const bool valid = r < nrows;
+    float x[EPL], e[EPL];
+    float mx, sum;
+    row_load<LPR, EPL>(sw + r * C, C, gl, valid, x);
+    row_softmax_stats<LPR, EPL>(x, e, mx, sum);
+    if (valid) {
+#pragma unroll
+      for (int k = 0; k < EPL; ++k) {
+        const int c = gl + k * LPR;
+        if (c < C) sw[r * C + c] = __fdiv_rn(e[k], sum);
+      }
+    }
+    __syncthreads();
+    if (tid < C) {
+      float t = scol[tid];
+      for (int rr = 0; rr < nrows; ++rr) t += sw[rr * C + tid];
+      scol[tid] = t;
+    }
+  }
+  __syncthreads();
+  if (CL > 1) cluster.sync();
+  // ---- DA history -> prob_avg, computed identically by every CTA (comatch.py:169-173) ----
+  if (tid < C) {
+    float tot = 0.f;
+    for (int r = 0; r < CL; ++r) tot += (CL > 1 ? cluster.map_shared_rank(scol, r) : scol)[tid];   // rank order
+    const float mean = tot / (float)f.rows;
+    const int count_old = p.state[0], head = p.state[1];
+    const int count = min(count_old + 1, p.window), head_new = (head + 1) % p.window;
+    float h = 0.f;
+    for (int a0 = 0; a0 < count - 1; a0 += 8) {
+      float v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int a = a0 + u;
+        const int slot = (head_new - count + a + 2 * p.window) % p.window;
+        v[u] = (a < count - 1) ? p.ring[(size_t)slot * C + tid] : 0.f;
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) h += v[u];
+    }
+    h += mean;
+    savg[tid] = h / (float)count;
+    if (crank == 0) {
+      p.ring[(size_t)head * C + tid] = mean;      // slot `head` leaves the window: nobody reads it this step
+      const_cast<float*>(f.prob_avg)[tid] = savg[tid];
+    }
+  }
+  __syncthreads();
+
+  // ---- phase 2: finalise every row, store, enqueue ----
+  float acc[2] = {0.f, 0.f};
+  for (long long row0 = r_lo; row0 < r_hi; row0 += ROWS) {
+    const int nrows = (int)min((long long)ROWS, r_hi - row0);
+    const int cnt = nrows * C;
+    __syncthreads();
+    tile_g2s(static_cast<const T*>(f.w) + row0 * C, sw, cnt);
+    tile_g2s(static_cast<const T*>(f.s0) + row0 * C, ss, cnt);
+    if (smooth) tile_g2s(f.numer + row0 * C, sn, cnt);
+    __syncthreads();
+    const int r = warp * 4 + rw;
+    finalize_row<LPR, EPL>(f, savg, sw, ss, so, sn, row0, r, r < nrows, gl, smooth, inv_rows, acc);
+    __syncthreads();
+    tile_s2g(sw, f.probs + row0 * C, cnt);
+    tile_s2g(so, f.probs_orig + row0 * C, cnt);
+    tile_s2g(ss, static_cast<T*>(f.gs0) + row0 * C, cnt);
+    if (p.qf) {     // unlabeled-weak rows of this pass -> bank rows (ptr + row) % K     (comatch.py:187-196)
+      const int vec_per_row = p.D * (int)sizeof(T) / 16;
+      for (int i = tid; i < nrows * vec_per_row; i += kFusedThreads) {
+        const int rr = i / vec_per_row, v = i - rr * vec_per_row;
+        const long long g = (ptr + row0 + rr) % p.K;
+        const uint4 val = ldg128(static_cast<const T*>(p.fu) + (row0 + rr) * p.D + v * (16 / sizeof(T)));
+        *reinterpret_cast<uint4*>(static_cast<T*>(p.qf) + g * p.D + v * (16 / sizeof(T))) = val;
+      }
+      for (int i = tid; i < cnt; i += kFusedThreads) {
+        const int rr = i / C, c = i - rr * C;
+        const long long g = (ptr + row0 + rr) % p.K;
+        const T val = from_f32<T>(so[i]);
+        static_cast<T*>(p.qp)[g * C + c] = val;
+        if (p.qpt) static_cast<T*>(p.qpt)[(size_t)c * p.K + g] = val;
+      }
+    }
+  }
+  if (p.qf) {       // labeled rows: [feats_x ; onehot(targets_x)], spread over the CTAs
+    const int vec_per_row = p.D * (int)sizeof(T) / 16;
+    for (long long i = (long long)crank * kFusedThreads + tid; i < p.n_x * vec_per_row; i += (long long)CL * kFusedThreads) {
+      const long long rr = i / vec_per_row; const int v = (int)(i - rr * vec_per_row);
+      const long long g = (ptr + f.rows + rr) % p.K;
+      const uint4 val = ldg128(static_cast<const T*>(p.fx) + rr * p.D + v * (16 / sizeof(T)));
+      *reinterpret_cast<uint4*>(static_cast<T*>(p.qf) + g * p.D + v * (16 / sizeof(T))) = val;
+    }
+    for (long long i = (long long)crank * kFusedThreads + tid; i < p.n_x * C; i += (long long)CL * kFusedThreads) {
+      const long long rr = i / C; const int c = (int)(i - rr * C);
+      const long long g = (ptr + f.rows + rr) % p.K;
+      const T val = from_f32<T>(c == (int)p.tx[rr] ? 1.f : 0.f);
+      static_cast<T*>(p.qp)[g * C + c] = val;
+      if (p.qpt) static_cast<T*>(p.qpt)[(size_t)c * p.K + g] = val;
+    }
+  }
+  // ---- loss / mask mean: CTA sum, then rank 0 folds the CTAs in rank order ----
+  __shared__ float s_part[2][kFusedWarps];
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const float t = warp_sum(acc[i]);
+    if (lane == 0) s_part[i][warp] = t;
+  }
+  __syncthreads();
+  if (tid < 2) {
+    float t = 0.f;
+    for (int w = 0; w < kFusedWarps; ++w) t += s_part[tid][w];
+    sred[tid] = t;
+  }
+  __syncthreads();
+  if (CL > 1) cluster.sync();
+  if (crank == 0 && tid < 2) {
+    float t = 0.f;
+    for (int r = 0; r < CL; ++r) t += (CL > 1 ? cluster.map_shared_rank(sred, r) : sred)[tid];
+    f.out[tid] = t / (float)f.rows;
+  }
+  if (crank == 0 && tid == 0) {
+    const int count_old = p.state[0], head = p.state[1];
+    p.state[0] = min(count_old + 1, p.window);
+    p.state[1] = (head + 1) % p.window;
+    if (p.qf) p.ptr_state[0] = (ptr + f.rows + p.n_x) % p.K;       // comatch.py:196
+  }
+  if (CL > 1) cluster.sync();           // nobody leaves while its smem is still being read
 }
 
 // ---- grad *= *scale -----------------------------------------------------------
@@ -688,5 +879,64 @@ extern "C" int b200ssl_scale_inplace(void* grad, int64_t numel, int32_t dtype, c
   if (dtype == B200SSL_F32) scale_kernel<float><<<(int)blocks, threads, 0, as_stream(stream)>>>(static_cast<float*>(grad), numel, scale, factor);
   else if (dtype == B200SSL_BF16) scale_kernel<__nv_bfloat16><<<(int)blocks, threads, 0, as_stream(stream)>>>(static_cast<__nv_bfloat16*>(grad), numel, scale, factor);
   else return fail(B200SSL_E_DTYPE, "%s: dtype %d", fn, dtype);
+  return check_launch(fn);
+}
+
+extern "C" int b200ssl_comatch_rows_fused(const void* logits_u_w, const void* logits_u_s0, const float* rowsum,
+                                          const float* numer, int64_t rows, int32_t classes, int32_t dtype, float alpha,
+                                          float one_minus_alpha, float thr, float gamma, float* da_ring, int32_t* da_state,
+                                          int32_t window, float* prob_avg, float* probs, float* probs_orig, void* probs_hl,
+                                          float* scores, int64_t* lbs, float* mask, void* grad_s0, float* out_scalars,
+                                          void* queue_feats, void* queue_probs, void* queue_probs_t, const void* feats_u_w,
+                                          const void* feats_x, const int64_t* targets_x, int64_t n_x, int32_t dim,
+                                          int64_t* ptr_state, int64_t bank_rows, void* stream) {
+  const char* fn = "b200ssl_comatch_rows_fused";
+  if (int e = check_rows(fn, rows, classes, dtype)) return e;
+  if (classes > 32) return fail(B200SSL_E_SHAPE, "%s: classes %d > 32 (use the separate kernels)", fn, classes);
+  if (!logits_u_w || !logits_u_s0 || !da_ring || !da_state || !prob_avg || !probs || !probs_orig || !grad_s0 || !out_scalars)
+    return fail(B200SSL_E_NULL, "%s: NULL tensor", fn);
+  if ((rowsum == nullptr) != (numer == nullptr)) return fail(B200SSL_E_NULL, "%s: rowsum and numer go together", fn);
+  if (window < 1 || window > B200SSL_DA_WINDOW_MAX) return fail(B200SSL_E_ARG, "%s: window %d outside [1,%d]", fn, window, B200SSL_DA_WINDOW_MAX);
+  if (queue_feats) {
+    const size_t es = dtype == B200SSL_F32 ? 4 : 2;
+    if (!queue_probs || !feats_u_w || !ptr_state || (n_x > 0 && (!feats_x || !targets_x)))
+      return fail(B200SSL_E_NULL, "%s: NULL enqueue tensor", fn);
+    if (dim < 1 || (dim * es) % 16 || bank_rows <= 0 || rows + n_x > bank_rows || n_x < 0)
+      return fail(B200SSL_E_SHAPE, "%s: enqueue needs 16-byte rows and rows + n_x <= bank_rows", fn);
+    if ((reinterpret_cast<uintptr_t>(queue_feats) | reinterpret_cast<uintptr_t>(feats_u_w) | reinterpret_cast<uintptr_t>(feats_x)) & 15u)
+      return fail(B200SSL_E_ALIGN, "%s: embeddings must be 16-byte aligned", fn);
+  }
+  FusedParams p{};
+  p.f = FinalizeParams{logits_u_w, logits_u_s0, prob_avg, rowsum, numer, rows, classes, alpha, one_minus_alpha, thr, gamma,
+                       probs, probs_orig, scores, reinterpret_cast<long long*>(lbs), mask, grad_s0, out_scalars, nullptr, nullptr,
+                       static_cast<__nv_bfloat16*>(probs_hl)};
+  p.ring = da_ring; p.state = da_state; p.window = window;
+  p.qf = queue_feats; p.qp = queue_probs; p.qpt = queue_probs_t; p.fu = feats_u_w; p.fx = feats_x;
+  p.tx = reinterpret_cast<const long long*>(targets_x); p.n_x = n_x; p.D = dim;
+  p.ptr_state = reinterpret_cast<long long*>(ptr_state); p.K = bank_rows;
+  long long cl = (rows + kFusedRows - 1) / kFusedRows;
+  if (cl > kFusedMaxCluster) cl = kFusedMaxCluster;
+  int clp = 1;
+  while (clp * 2 <= cl) clp *= 2;
+  if (clp < cl) clp *= 2;                      // round up to a power of two (cluster sizes 1, 2, 4, 8)
+  p.CL = clp;
+  p.rows_per_cta = (((rows + clp - 1) / clp) + 7) & ~7LL;          // multiples of 8 rows keep the tiles 16-byte aligned
+  const size_t smem = ((size_t)4 * kFusedRows * classes + 32 + 32 + 4) * sizeof(float);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)clp, 1, 1);
+  cfg.blockDim = dim3(kFusedThreads, 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = as_stream(stream);
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)clp;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e;
+  if (dtype == B200SSL_F32) e = cudaLaunchKernelEx(&cfg, comatch_rows_fused_kernel<float>, p);
+  else e = cudaLaunchKernelEx(&cfg, comatch_rows_fused_kernel<__nv_bfloat16>, p);
+  if (e != cudaSuccess) return fail((int)e, "%s: cudaLaunchKernelEx: %s", fn, cudaGetErrorString(e));
   return check_launch(fn);
 }

@@ -162,6 +162,25 @@ B200SSL_API int b200ssl_comatch_finalize(const void* logits_u_w, const void* log
                              float* mask, void* grad_s0, float* out_scalars, void* workspace,
                              size_t workspace_bytes, void* stream);
 
+/* ------------------------------------------- K2 + K2b/K4/K7 (+ K5) fused ----
+ * The whole row phase of a CoMatch step in ONE thread-block-cluster launch, for small
+ * batches (classes <= 32; intended for rows <= ~2048, larger batches use the separate
+ * kernels above): b200ssl_comatch_da, then b200ssl_comatch_finalize, then -- when
+ * queue_feats != NULL -- b200ssl_bank_enqueue of the unsharded bank (device write pointer
+ * ptr_state, advanced by rows + n_x).  Same arithmetic, same outputs; the cross-row
+ * reductions (DA column means, loss, mask mean) are exchanged through distributed shared
+ * memory in rank order instead of global tickets.  Replaces code/comatch.py:163-176,
+ * 182-196, 216-220.
+ */
+B200SSL_API int b200ssl_comatch_rows_fused(const void* logits_u_w, const void* logits_u_s0, const float* rowsum,
+                               const float* numer, int64_t rows, int32_t classes, int32_t dtype, float alpha,
+                               float one_minus_alpha, float thr, float gamma, float* da_ring, int32_t* da_state,
+                               int32_t window, float* prob_avg, float* probs, float* probs_orig, void* probs_hl,
+                               float* scores, int64_t* lbs, float* mask, void* grad_s0, float* out_scalars,
+                               void* queue_feats, void* queue_probs, void* queue_probs_t, const void* feats_u_w,
+                               const void* feats_x, const int64_t* targets_x, int64_t n_x, int32_t dim,
+                               int64_t* ptr_state, int64_t bank_rows, void* stream);
+
 /* ---------------------------------------------------------------- K5 ----
  * Ring-buffer enqueue.  Replaces code/comatch.py:187-196: rows are
  * [unlabeled-weak (n_u) ; labeled (n_x)], probabilities [probs_orig ; onehot(targets_x)],

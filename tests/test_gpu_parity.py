@@ -295,10 +295,11 @@ def _clustered(g, B, Bu, D, protos, noise=0.075):
                 feats_u_s1=feats(y_u), feats_x=feats(y_x), targets_x=y_x)
 
 
+@pytest.mark.parametrize("fuse_rows", [True, False])
 @pytest.mark.parametrize("B,MU,D,qbatches,dtype", [(8, 7, 64, 5, torch.float32), (5, 3, 32, 3, torch.float32),
                                                    (64, 7, 64, 5, torch.float32), (64, 7, 64, 5, torch.bfloat16),
-                                                   (3, 5, 128, 4, torch.float32)])
-def test_comatch_head_always_mode_vs_oracle(pkg, B, MU, D, qbatches, dtype):
+                                                   (3, 5, 128, 4, torch.float32), (160, 7, 64, 2, torch.bfloat16)])
+def test_comatch_head_always_mode_vs_oracle(pkg, B, MU, D, qbatches, dtype, fuse_rows):
     """'always' enqueue (upstream semantics) over enough steps for the ring to wrap;
     ragged sizes (rows not a multiple of 64, K not a multiple of the tile)."""
     g = torch.Generator().manual_seed(B * 1000 + D)
@@ -308,6 +309,7 @@ def test_comatch_head_always_mode_vs_oracle(pkg, B, MU, D, qbatches, dtype):
     protos = torch.randn(C, D, generator=g)
     protos = protos / protos.norm(dim=1, keepdim=True)
     head = pkg["head"].CoMatchHead(C, D, K, thr, enqueue_mode="always", dtype=dtype)
+    head.fuse_rows = fuse_rows          # one cluster launch for DA + finalize + enqueue, or the three kernels
     state = O.CoMatchState.zeros(K, D, C)
     tol = FP32_TOL if dtype == torch.float32 else BF16_TOL
     fired = 0
