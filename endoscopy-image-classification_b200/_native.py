@@ -46,13 +46,13 @@ SIGNATURES = {
     "b200ssl_scale_inplace": (_i32, [_vp, _i64, _i32, _vp, _f32, _vp]),
     "b200ssl_labeled_ce_fwd_bwd": (_i32, [_vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _f32, _vp, _vp, _sz, _vp]),
     "b200ssl_comatch_da": (_i32, [_vp, _i64, _i32, _i32, _vp, _vp, _i32, _vp, _vp, _vp, _sz, _vp]),
-    "b200ssl_bank_smooth_partial": (_i32, [_vp, _vp, _vp, _vp, _i64, _i64, _i32, _i32, _i32, _f32, _vp, _vp,
+    "b200ssl_bank_smooth_partial": (_i32, [_vp, _vp, _vp, _vp, _i64, _i64, _i32, _i32, _i32, _f32, _vp, _vp, _i32, _i32,
                                            _vp, _sz, _vp]),
-    "b200ssl_comatch_finalize": (_i32, [_vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _f32, _f32, _f32, _f32,
+    "b200ssl_comatch_finalize": (_i32, [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _i64, _i32, _i32, _f32, _f32, _f32, _f32,
                                         _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
-    "b200ssl_comatch_rows_fused": (_i32, [_vp, _vp, _vp, _vp, _i64, _i32, _i32, _f32, _f32, _f32, _f32, _vp, _vp, _i32, _vp,
-                                          _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32,
-                                          _vp, _i64, _vp]),
+    "b200ssl_comatch_rows_fused": (_i32, [_vp, _vp, _vp, _vp, _i32, _i32, _i64, _i32, _i32, _f32, _f32, _f32, _f32, _vp, _vp,
+                                          _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
+                                          _i64, _i32, _vp, _i64, _i32, _vp]),
     "b200ssl_bank_enqueue": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i32, _i32, _i32, _i64, _vp, _i64,
                                     _i64, _i64, _i64, _i64, _vp]),
     "b200ssl_contrast_fwd": (_i32, [_vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _f32, _f32, _vp, _vp, _vp, _f32, _f32, _vp,

@@ -225,34 +225,44 @@ class CoMatchHead:
 
         n = rows + n_x
         do_enqueue = geom.should_enqueue(n, self.enqueue_mode)
-        if self.fuse_rows and R == 1 and C <= 32 and rows <= self.FUSED_ROWS_MAX:
-            # small batch, unsharded bank: K3, then ONE cluster launch for DA + finalize + enqueue
-            rowsum, numer = self._k_smooth(fw) if self.smoothing else (None, None)
-            out = self._k_rows_fused(lw, ls0, rowsum, numer, fw, fx, tx, do_enqueue)
-        else:
-            self._k_da(lw)                                                   # K2 (rank-local history)
-            # queries of every rank (the enqueue block contains them): [R*n, D], rank-major
-            block_f = torch.cat([fw, fx], dim=0) if R > 1 else None
-            gathered_f = all_gather_rows(block_f, self.pg) if R > 1 else None
-            rowsum = numer = None
+        fused = self.fuse_rows and C <= 32 and rows <= self.FUSED_ROWS_MAX
+        rowsum = numer = None
+        lds = (0, 0)                                                         # (rowsum_ld, numer_ld): 0 = dense
+        if R == 1:
+            if not fused:
+                self._k_da(lw)                                               # K2
             if self.smoothing:                                               # K3, bank as of *before* this step's enqueue
-                if R == 1:
-                    rowsum, numer = self._k_smooth(fw)
-                else:
-                    queries = gathered_f.view(R, n, D)[:, :rows, :].reshape(R * rows, D)
-                    rs_all, nm_all = self._k_smooth(queries)
-                    rowsum = reduce_scatter_rows(rs_all, self.pg)
-                    numer = reduce_scatter_rows(nm_all, self.pg)
-            out = self._k_finalize(lw, ls0, rowsum, numer)                   # K2b + K4 + K7
-            if do_enqueue:                                                   # K5
-                if R == 1:
-                    self._k_enqueue(fw, fx, out["probs_orig"], tx, 0, n)
-                else:
-                    po_all = all_gather_rows(out["probs_orig"], self.pg).view(R, rows, C)
-                    tx_all = all_gather_rows(tx, self.pg).view(R, n_x)
-                    gf = gathered_f.view(R, n, D)
-                    for r in range(R):                                       # block r sits at ptr + r*n
-                        self._k_enqueue(gf[r, :rows], gf[r, rows:], po_all[r], tx_all[r], r * n, R * n if r == R - 1 else 0)
+                rowsum, numer = self._k_smooth(fw)
+            if fused:                                                        # ONE cluster launch: DA + finalize + enqueue
+                out = self._k_rows_fused(lw, ls0, rowsum, numer, lds, fw, fx, tx, do_enqueue, False)
+            else:
+                out = self._k_finalize(lw, ls0, rowsum, numer, lds)          # K2b + K4 + K7
+                if do_enqueue:
+                    self._k_enqueue(fw, fx, out["probs_orig"], tx, 0, n)     # K5
+        else:
+            # sharded bank (bank.py): 3 collectives per step.  (1) all-gather of the enqueue blocks -- they contain
+            # every rank's queries; (2) reduce-scatter of the packed [R*n, W] partial sums computed against the
+            # local shard (all block rows, labeled ones included: their 1/MU of extra work avoids a strided copy);
+            # (3) all-gather of the probability blocks [probs_orig ; onehot], then ONE sharded ring write: the
+            # gathered buffers are already in global (rank-major) row order.
+            W = (C + 1 + 3) & ~3
+            block_f = torch.cat([fw, fx], dim=0)
+            gathered_f = all_gather_rows(block_f, self.pg)                   # [R*n, D]
+            if self.smoothing:
+                packed = self._k_smooth(gathered_f, packed_ld=W)             # [R*n, W]: numer | rowsum
+                mine = reduce_scatter_rows(packed, self.pg)                  # [n, W]; rows [0, rows) are this rank's queries
+                numer, rowsum, lds = mine, mine[:, C:], (W, W)
+            if fused:
+                out = self._k_rows_fused(lw, ls0, rowsum, numer, lds, fw, fx, tx, False, True)
+                probs_block = out["probs_block"]
+            else:
+                self._k_da(lw)
+                out = self._k_finalize(lw, ls0, rowsum, numer, lds)
+                onehot = torch.zeros(n_x, C, dtype=torch.float32, device=lw.device).scatter_(1, tx.view(-1, 1), 1.0)
+                probs_block = torch.cat([out["probs_orig"], onehot], dim=0)
+            if do_enqueue:
+                pb_all = all_gather_rows(probs_block, self.pg)               # [R*n, C]
+                self._k_enqueue(gathered_f, gathered_f[:0], pb_all, tx[:0], 0, R * n)
         if do_enqueue:
             self._queue_ptr = geom.next_ptr(self._queue_ptr, n)
             self._pristine = False
@@ -274,21 +284,28 @@ class CoMatchHead:
                                            self.prob_avg.data_ptr(), None, ws, wsb, N.stream_ptr(self.device)),
                 "comatch_da")
 
-    def _k_smooth(self, queries):
+    def _k_smooth(self, queries, packed_ld: int = 0):
+        """Returns ``(rowsum [rows], numer [rows, C])`` or, with ``packed_ld = W``, one ``[rows, W]`` tensor holding
+        numer in columns [0, C) and rowsum in column C (what the sharded bank reduce-scatters)."""
         rows, D = queries.shape
         C = self.num_classes
         queries = queries.contiguous()
-        rowsum = torch.empty(rows, dtype=torch.float32, device=self.device)
-        numer = torch.empty(rows, C, dtype=torch.float32, device=self.device)
+        if packed_ld:
+            packed = torch.empty(rows, packed_ld, dtype=torch.float32, device=self.device)
+            rowsum, numer, lds = packed[:, C:], packed, (packed_ld, packed_ld)
+        else:
+            rowsum = torch.empty(rows, dtype=torch.float32, device=self.device)
+            numer = torch.empty(rows, C, dtype=torch.float32, device=self.device)
+            lds = (0, 0)
         ws, wsb = self._ws(rows)
         N.check(N.lib().b200ssl_bank_smooth_partial(queries.data_ptr(), self.queue_feats.data_ptr(),
-                                                    self.queue_probs.data_ptr(), N.ptr(self.queue_probs_t), rows, self.geom.shard_rows, D, C,
-                                                    N.dtype_enum(queries), self.temperature, rowsum.data_ptr(),
-                                                    numer.data_ptr(), ws, wsb, N.stream_ptr(self.device)),
-                "bank_smooth_partial")
-        return rowsum, numer
+                                                    self.queue_probs.data_ptr(), N.ptr(self.queue_probs_t), rows,
+                                                    self.geom.shard_rows, D, C, N.dtype_enum(queries), self.temperature,
+                                                    rowsum.data_ptr(), numer.data_ptr(), lds[0], lds[1], ws, wsb,
+                                                    N.stream_ptr(self.device)), "bank_smooth_partial")
+        return packed if packed_ld else (rowsum, numer)
 
-    def _k_finalize(self, lw, ls0, rowsum, numer) -> dict:
+    def _k_finalize(self, lw, ls0, rowsum, numer, lds=(0, 0)) -> dict:
         rows, C = lw.shape
         f32 = dict(dtype=torch.float32, device=self.device)
         out = {"probs": torch.empty(rows, C, **f32), "probs_orig": torch.empty(rows, C, **f32),
@@ -301,7 +318,7 @@ class CoMatchHead:
                             if (lw.dtype == torch.bfloat16 and C <= 32 and self.low_dim == 64) else None)}
         ws, wsb = self._ws(rows)
         N.check(N.lib().b200ssl_comatch_finalize(
-            lw.data_ptr(), ls0.data_ptr(), self.prob_avg.data_ptr(), N.ptr(rowsum), N.ptr(numer), rows, C,
+            lw.data_ptr(), ls0.data_ptr(), self.prob_avg.data_ptr(), N.ptr(rowsum), N.ptr(numer), lds[0], lds[1], rows, C,
             N.dtype_enum(lw), float(np.float32(self.alpha)), float(np.float32(1.0 - self.alpha)), self.thr, self.gamma,
             out["probs"].data_ptr(), out["probs_orig"].data_ptr(), N.ptr(out["probs_hl"]), out["scores"].data_ptr(),
             out["lbs"].data_ptr(),
@@ -309,11 +326,13 @@ class CoMatchHead:
             N.stream_ptr(self.device)), "comatch_finalize")
         return out
 
-    def _k_rows_fused(self, lw, ls0, rowsum, numer, fw, fx, tx, do_enqueue: bool) -> dict:
-        """DA statistics + finalisation (+ enqueue) in one cluster launch (``b200ssl_comatch_rows_fused``)."""
+    def _k_rows_fused(self, lw, ls0, rowsum, numer, lds, fw, fx, tx, do_enqueue: bool, onehot_tail: bool) -> dict:
+        """DA statistics + finalisation (+ enqueue) in one cluster launch (``b200ssl_comatch_rows_fused``).
+        ``onehot_tail``: also emit ``probs_block = [probs_orig ; onehot(targets_x)]`` (sharded enqueue)."""
         rows, C = lw.shape
         f32 = dict(dtype=torch.float32, device=self.device)
-        out = {"probs": torch.empty(rows, C, **f32), "probs_orig": torch.empty(rows, C, **f32),
+        block = torch.empty(rows + (fx.shape[0] if onehot_tail else 0), C, **f32)
+        out = {"probs": torch.empty(rows, C, **f32), "probs_orig": block[:rows], "probs_block": block,
                "scores": torch.empty(rows, **f32), "mask": torch.empty(rows, **f32),
                "lbs": torch.empty(rows, dtype=torch.int64, device=self.device),
                "grad_s0": torch.empty_like(ls0), "scalars": torch.empty(4, **f32),
@@ -321,14 +340,15 @@ class CoMatchHead:
                             if (lw.dtype == torch.bfloat16 and C <= 32 and self.low_dim == 64) else None)}
         enq = do_enqueue
         N.check(N.lib().b200ssl_comatch_rows_fused(
-            lw.data_ptr(), ls0.data_ptr(), N.ptr(rowsum), N.ptr(numer), rows, C, N.dtype_enum(lw),
+            lw.data_ptr(), ls0.data_ptr(), N.ptr(rowsum), N.ptr(numer), lds[0], lds[1], rows, C, N.dtype_enum(lw),
             float(np.float32(self.alpha)), float(np.float32(1.0 - self.alpha)), self.thr, self.gamma,
             self.da_ring.data_ptr(), self.da_state.data_ptr(), self.da_window, self.prob_avg.data_ptr(),
             out["probs"].data_ptr(), out["probs_orig"].data_ptr(), N.ptr(out["probs_hl"]), out["scores"].data_ptr(),
             out["lbs"].data_ptr(), out["mask"].data_ptr(), out["grad_s0"].data_ptr(), out["scalars"].data_ptr(),
             self.queue_feats.data_ptr() if enq else None, self.queue_probs.data_ptr() if enq else None,
             N.ptr(self.queue_probs_t) if enq else None, fw.data_ptr(), fx.data_ptr(), tx.data_ptr(), fx.shape[0],
-            self.low_dim, self.ptr_state.data_ptr(), self.queue_size, N.stream_ptr(self.device)), "comatch_rows_fused")
+            self.low_dim, self.ptr_state.data_ptr(), self.queue_size, 1 if onehot_tail else 0,
+            N.stream_ptr(self.device)), "comatch_rows_fused")
         return out
 
     def _k_enqueue(self, fw, fx, probs_orig, tx, block_offset: int, advance: int) -> None:

@@ -21,6 +21,7 @@ struct SmoothParams {
   float* rowsum; float* numer;
   float* part; unsigned* tickets;  // split-K partials [nsplit][rows_pad][1+C], per row-tile tickets
   int nsplit, tiles_per_split, W; long long rows_pad;
+  int numer_ld, rowsum_ld;
 };
 
 // grid = (row tiles, nsplit); 256 threads; NACC = ceil(maxC/4) numerator
@@ -91,7 +92,7 @@ __global__ void __launch_bounds__(kTileThreads) bank_smooth_simt_kernel(const Sm
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const int r = ty + 16 * i;
-      if (direct) { if (r < mrows) p.rowsum[i0 + r] = rs[i]; }
+      if (direct) { if (r < mrows) p.rowsum[(i0 + r) * p.rowsum_ld] = rs[i]; }
       else pbase[(i0 + r) * W] = rs[i];
     }
   }
@@ -99,7 +100,7 @@ __global__ void __launch_bounds__(kTileThreads) bank_smooth_simt_kernel(const Sm
   for (int m = 0; m < NACC; ++m) {
     const int c = cg + 4 * m;
     if (c < C) {
-      if (direct) { if (prow < mrows) p.numer[(i0 + prow) * C + c] = nacc[m]; }
+      if (direct) { if (prow < mrows) p.numer[(i0 + prow) * p.numer_ld + c] = nacc[m]; }
       else pbase[(i0 + prow) * W + 1 + c] = nacc[m];
     }
   }
@@ -118,8 +119,8 @@ __global__ void __launch_bounds__(kTileThreads) bank_smooth_simt_kernel(const Sm
 #pragma unroll
                      for (int j = 0; j < 4; ++j) {
                        const int e = 4 * i + j, row = e / W, col = e - row * W;
-                       if (col == 0) p.rowsum[i0 + row] = vv[j];
-                       else if (col <= C) p.numer[(i0 + row) * C + col - 1] = vv[j];
+                       if (col == 0) p.rowsum[(i0 + row) * p.rowsum_ld] = vv[j];
+                       else if (col <= C) p.numer[(i0 + row) * p.numer_ld + col - 1] = vv[j];
                      }
                    });
   if (tid == 0) p.tickets[blockIdx.x] = 0u;
@@ -195,14 +196,15 @@ using namespace b200ssl;
 
 namespace b200ssl {
 int bank_smooth_tc(const void* feats, const void* queue_feats, const void* queue_probs_t, long long rows,
-                   long long bank_rows, int classes, float temperature, float* rowsum, float* numer, void* workspace,
-                   size_t workspace_bytes, cudaStream_t stream);
+                   long long bank_rows, int classes, float temperature, float* rowsum, float* numer, int rowsum_ld,
+                   int numer_ld, void* workspace, size_t workspace_bytes, cudaStream_t stream);
 }
 
 extern "C" int b200ssl_bank_smooth_partial(const void* feats_u_w, const void* queue_feats, const void* queue_probs,
                                            const void* queue_probs_t, int64_t rows, int64_t bank_rows, int32_t dim, int32_t classes,
                                            int32_t dtype, float temperature, float* rowsum, float* numer,
-                                           void* workspace, size_t workspace_bytes, void* stream) {
+                                           int32_t rowsum_ld, int32_t numer_ld, void* workspace, size_t workspace_bytes,
+                                           void* stream) {
   const char* fn = "b200ssl_bank_smooth_partial";
   if (!feats_u_w || !queue_feats || !queue_probs || !rowsum || !numer) return fail(B200SSL_E_NULL, "%s: NULL tensor", fn);
   if (rows <= 0 || bank_rows <= 0) return fail(B200SSL_E_SHAPE, "%s: rows=%lld bank_rows=%lld", fn, (long long)rows, (long long)bank_rows);
@@ -216,11 +218,13 @@ extern "C" int b200ssl_bank_smooth_partial(const void* feats_u_w, const void* qu
       !(reinterpret_cast<uintptr_t>(feats_u_w) & 15u) && !(reinterpret_cast<uintptr_t>(queue_feats) & 15u) &&
       !(reinterpret_cast<uintptr_t>(queue_probs_t) & 15u))
     return bank_smooth_tc(feats_u_w, queue_feats, queue_probs_t, rows, bank_rows, classes, temperature, rowsum, numer,
-                          workspace, workspace_bytes, as_stream(stream));
+                          rowsum_ld > 0 ? rowsum_ld : 1, numer_ld > 0 ? numer_ld : classes, workspace, workspace_bytes,
+                          as_stream(stream));
   SmoothParams p{};
   p.f = feats_u_w; p.qf = queue_feats; p.qp = queue_probs;
   p.rows = rows; p.bank_rows = bank_rows; p.D = dim; p.C = classes; p.tau = temperature;
   p.rowsum = rowsum; p.numer = numer;
+  p.rowsum_ld = rowsum_ld > 0 ? rowsum_ld : 1; p.numer_ld = numer_ld > 0 ? numer_ld : classes;
   p.nsplit = smooth_nsplit(rows, bank_rows, &p.tiles_per_split);
   const long long row_tiles = (rows + kTM - 1) / kTM;
   p.rows_pad = row_tiles * kTM;

@@ -90,7 +90,7 @@ struct SmoothTcParams {
   int C, W;                       // W = round_up(C + 1, 4): [numer 0..C-1, rowsum] per row of a partial
   int nsplit, cluster, nouter;    // nsplit = cluster * nouter CTAs share one row tile
   float scale;                    // log2(e) / temperature
-  float* rowsum; float* numer;
+  float* rowsum; float* numer; int rowsum_ld, numer_ld;
   float* part; unsigned* tickets;
   unsigned long long* dbg;
 };
@@ -292,8 +292,8 @@ bank_smooth_tc_kernel(const __grid_constant__ CUtensorMap tm_f, const __grid_con
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const int col = 4 * q4 + j;
-          if (col < C) p.numer[grow * C + col] = vv[j];
-          else if (col == C) p.rowsum[grow] = vv[j];       // the ones column: sum_k P_ik
+          if (col < C) p.numer[grow * p.numer_ld + col] = vv[j];
+          else if (col == C) p.rowsum[grow * p.rowsum_ld] = vv[j];       // the ones column: sum_k P_ik
         }
       }
     } else {
@@ -320,8 +320,8 @@ bank_smooth_tc_kernel(const __grid_constant__ CUtensorMap tm_f, const __grid_con
 #pragma unroll
                      for (int j = 0; j < 4; ++j) {
                        const int e = 4 * i + j, row = e / W, col = e - row * W;
-                       if (col < C) p.numer[(i0 + row) * C + col] = vv[j];
-                       else if (col == C) p.rowsum[i0 + row] = vv[j];
+                       if (col < C) p.numer[(i0 + row) * p.numer_ld + col] = vv[j];
+                       else if (col == C) p.rowsum[(i0 + row) * p.rowsum_ld] = vv[j];
                      }
                    });
   __syncthreads();
@@ -358,13 +358,13 @@ size_t smooth_tc_workspace_floats(long long rows, long long bank_rows, int class
 
 // bf16, dim 64, classes <= 31, bank rows a multiple of 8: the tensor-core path.
 int bank_smooth_tc(const void* feats, const void* queue_feats, const void* queue_probs_t, long long rows,
-                   long long bank_rows, int classes, float temperature, float* rowsum, float* numer, void* workspace,
-                   size_t workspace_bytes, cudaStream_t stream) {
+                   long long bank_rows, int classes, float temperature, float* rowsum, float* numer, int rowsum_ld,
+                   int numer_ld, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
   const char* fn = "b200ssl_bank_smooth_partial[tcgen05]";
   SmoothTcParams p{};
   p.rows = rows; p.bank_rows = bank_rows; p.C = classes; p.W = (1 + classes + 3) & ~3;
   p.scale = (float)(1.4426950408889634 / (double)temperature);
-  p.rowsum = rowsum; p.numer = numer; p.dbg = debug_timing_buffer();
+  p.rowsum = rowsum; p.numer = numer; p.rowsum_ld = rowsum_ld; p.numer_ld = numer_ld; p.dbg = debug_timing_buffer();
   smooth_tc_plan(rows, bank_rows, &p.cluster, &p.nouter);
   p.nsplit = p.cluster * p.nouter;
   const long long row_tiles = (rows + kBM - 1) / kBM;

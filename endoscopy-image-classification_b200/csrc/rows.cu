@@ -382,6 +382,7 @@ struct FinalizeParams {
   float alpha, one_minus_alpha, thr, gamma;
   float* probs; float* probs_orig; float* scores; long long* lbs; float* mask;
   void* gs0; float* out; float* partials; unsigned* ticket;
+  int numer_ld, rowsum_ld;   // row strides of numer / rowsum (C and 1, or W and W for the packed [rows, W] layout)
   __nv_bfloat16* hl;   // optional [rows, 64] bf16: hi(32) | lo(32) split of probs for the tensor-core graph kernel
 };
 
@@ -390,6 +391,15 @@ __device__ __forceinline__ float pow_gamma(float b, float gamma) {
   if (gamma == 1.f) return b;
   if (gamma == 0.f) return 1.f;
   return powf(b, gamma);
+}
+
+// numer rows [row0, row0+nrows) -> dense smem tile; vectorised when the rows are contiguous (ld == C)
+__device__ __forceinline__ void load_numer_tile(const float* __restrict__ numer, int ld, long long row0, int nrows, int C, float* s) {
+  if (ld == C) { tile_g2s(numer + row0 * C, s, nrows * C); return; }
+  for (int i = threadIdx.x; i < nrows * C; i += blockDim.x) {
+    const int r = i / C, c = i - r * C;
+    s[i] = numer[(row0 + r) * ld + c];
+  }
 }
 
 // One row of the CoMatch finalisation (LPR lanes): pseudo-label from the weak logits in `sw`, alpha-mix
@@ -413,7 +423,7 @@ __device__ __forceinline__ void finalize_row(const FinalizeParams& p, const floa
       q += pr[k];
     }
     q = group_sum<LPR>(q);
-    const float rs = (smooth && valid) ? p.rowsum[row0 + r] : 1.f;
+    const float rs = (smooth && valid) ? p.rowsum[(row0 + r) * p.rowsum_ld] : 1.f;
     float psum = 0.f;
 #pragma unroll
     for (int k = 0; k < EPL; ++k) {
@@ -503,7 +513,7 @@ __global__ void __launch_bounds__(kRowThreads) comatch_finalize_kernel(const Fin
     const int cnt = nrows * C;
     tile_g2s(static_cast<const T*>(p.w) + row0 * C, sw, cnt);
     tile_g2s(static_cast<const T*>(p.s0) + row0 * C, ss, cnt);
-    if (smooth) tile_g2s(p.numer + row0 * C, sn, cnt);
+    if (smooth) load_numer_tile(p.numer, p.numer_ld, row0, nrows, C, sn);
     __syncthreads();
     const int r = warp * Cfg::kRowsPerWarp + rw;
     const bool valid = r < nrows;
@@ -540,6 +550,7 @@ struct FusedParams {
   void* qf; void* qp; void* qpt; const void* fu; const void* fx; const long long* tx;
   long long n_x; int D; long long* ptr_state; long long K;
   int CL; long long rows_per_cta;
+  int onehot_tail;   // probs_orig has rows + n_x rows: fill the tail with onehot(targets_x) (block for the sharded enqueue)
 };
 
 template <typename T>
@@ -631,7 +642,7 @@ __global__ void __launch_bounds__(kFusedThreads) comatch_rows_fused_kernel(const
     __syncthreads();
     tile_g2s(static_cast<const T*>(f.w) + row0 * C, sw, cnt);
     tile_g2s(static_cast<const T*>(f.s0) + row0 * C, ss, cnt);
-    if (smooth) tile_g2s(f.numer + row0 * C, sn, cnt);
+    if (smooth) load_numer_tile(f.numer, f.numer_ld, row0, nrows, C, sn);
     __syncthreads();
     const int r = warp * 4 + rw;
     finalize_row<LPR, EPL>(f, savg, sw, ss, so, sn, row0, r, r < nrows, gl, smooth, inv_rows, acc);
@@ -670,6 +681,12 @@ __global__ void __launch_bounds__(kFusedThreads) comatch_rows_fused_kernel(const
       const T val = from_f32<T>(c == (int)p.tx[rr] ? 1.f : 0.f);
       static_cast<T*>(p.qp)[g * C + c] = val;
       if (p.qpt) static_cast<T*>(p.qpt)[(size_t)c * p.K + g] = val;
+    }
+  }
+  if (p.onehot_tail) {      // [probs_orig ; onehot(targets_x)] = the probability block of the enqueue (comatch.py:188-189)
+    for (long long i = (long long)crank * kFusedThreads + tid; i < p.n_x * C; i += (long long)CL * kFusedThreads) {
+      const long long rr = i / C; const int c = (int)(i - rr * C);
+      f.probs_orig[(f.rows + rr) * C + c] = (c == (int)p.tx[rr]) ? 1.f : 0.f;
     }
   }
   // ---- loss / mask mean: CTA sum, then rank 0 folds the CTAs in rank order ----
@@ -842,7 +859,8 @@ extern "C" int b200ssl_comatch_da(const void* logits_u_w, int64_t rows, int32_t 
 }
 
 extern "C" int b200ssl_comatch_finalize(const void* logits_u_w, const void* logits_u_s0, const float* prob_avg,
-                                        const float* rowsum, const float* numer, int64_t rows, int32_t classes,
+                                        const float* rowsum, const float* numer, int32_t rowsum_ld, int32_t numer_ld,
+                                        int64_t rows, int32_t classes,
                                         int32_t dtype, float alpha, float one_minus_alpha, float thr, float gamma,
                                         float* probs, float* probs_orig, void* probs_hl, float* scores, int64_t* lbs,
                                         float* mask, void* grad_s0, float* out_scalars, void* workspace,
@@ -857,7 +875,8 @@ extern "C" int b200ssl_comatch_finalize(const void* logits_u_w, const void* logi
   FinalizeParams p{logits_u_w, logits_u_s0, prob_avg, rowsum, numer, rows, classes, alpha, one_minus_alpha, thr, gamma,
                    probs, probs_orig, scores, reinterpret_cast<long long*>(lbs), mask, grad_s0, out_scalars,
                    reinterpret_cast<float*>(static_cast<char*>(workspace) + kWsHeaderBytes),
-                   reinterpret_cast<unsigned*>(workspace) + 3, static_cast<__nv_bfloat16*>(probs_hl)};
+                   reinterpret_cast<unsigned*>(workspace) + 3, numer_ld > 0 ? numer_ld : classes, rowsum_ld > 0 ? rowsum_ld : 1,
+                   static_cast<__nv_bfloat16*>(probs_hl)};
   B200SSL_ROW_DISPATCH(dtype, classes, {
     RowLaunch l = row_launch<LPR, EPL>(rows, classes, 4);
     auto k = comatch_finalize_kernel<T, LPR, EPL>;
@@ -883,13 +902,14 @@ extern "C" int b200ssl_scale_inplace(void* grad, int64_t numel, int32_t dtype, c
 }
 
 extern "C" int b200ssl_comatch_rows_fused(const void* logits_u_w, const void* logits_u_s0, const float* rowsum,
-                                          const float* numer, int64_t rows, int32_t classes, int32_t dtype, float alpha,
+                                          const float* numer, int32_t rowsum_ld, int32_t numer_ld, int64_t rows,
+                                          int32_t classes, int32_t dtype, float alpha,
                                           float one_minus_alpha, float thr, float gamma, float* da_ring, int32_t* da_state,
                                           int32_t window, float* prob_avg, float* probs, float* probs_orig, void* probs_hl,
                                           float* scores, int64_t* lbs, float* mask, void* grad_s0, float* out_scalars,
                                           void* queue_feats, void* queue_probs, void* queue_probs_t, const void* feats_u_w,
                                           const void* feats_x, const int64_t* targets_x, int64_t n_x, int32_t dim,
-                                          int64_t* ptr_state, int64_t bank_rows, void* stream) {
+                                          int64_t* ptr_state, int64_t bank_rows, int32_t onehot_tail, void* stream) {
   const char* fn = "b200ssl_comatch_rows_fused";
   if (int e = check_rows(fn, rows, classes, dtype)) return e;
   if (classes > 32) return fail(B200SSL_E_SHAPE, "%s: classes %d > 32 (use the separate kernels)", fn, classes);
@@ -909,11 +929,13 @@ extern "C" int b200ssl_comatch_rows_fused(const void* logits_u_w, const void* lo
   FusedParams p{};
   p.f = FinalizeParams{logits_u_w, logits_u_s0, prob_avg, rowsum, numer, rows, classes, alpha, one_minus_alpha, thr, gamma,
                        probs, probs_orig, scores, reinterpret_cast<long long*>(lbs), mask, grad_s0, out_scalars, nullptr, nullptr,
-                       static_cast<__nv_bfloat16*>(probs_hl)};
+                       numer_ld > 0 ? numer_ld : classes, rowsum_ld > 0 ? rowsum_ld : 1, static_cast<__nv_bfloat16*>(probs_hl)};
   p.ring = da_ring; p.state = da_state; p.window = window;
   p.qf = queue_feats; p.qp = queue_probs; p.qpt = queue_probs_t; p.fu = feats_u_w; p.fx = feats_x;
   p.tx = reinterpret_cast<const long long*>(targets_x); p.n_x = n_x; p.D = dim;
   p.ptr_state = reinterpret_cast<long long*>(ptr_state); p.K = bank_rows;
+  p.onehot_tail = onehot_tail ? 1 : 0;
+  if (onehot_tail && (n_x > 0 && !targets_x)) return fail(B200SSL_E_NULL, "%s: onehot_tail needs targets_x", fn);
   long long cl = (rows + kFusedRows - 1) / kFusedRows;
   if (cl > kFusedMaxCluster) cl = kFusedMaxCluster;
   int clp = 1;

@@ -131,11 +131,15 @@ B200SSL_API int b200ssl_comatch_da(const void* logits_u_w, int64_t rows, int32_t
  *     accumulators, operands staged by TMA, split partials folded through thread-block
  *     cluster distributed shared memory (csrc/bank_tc.cu);
  *   - otherwise exact-fp32 FFMA tiles (the reference's matrix product is true fp32).
+ * rowsum_ld / numer_ld are the row strides of the two outputs in floats (0 = dense: 1 and
+ * `classes`); a packed [rows, W] buffer (numer at column 0, rowsum at column `classes`,
+ * both strides W) lets the sharded bank reduce-scatter both with one collective.
  */
 B200SSL_API int b200ssl_bank_smooth_partial(const void* feats_u_w, const void* queue_feats, const void* queue_probs,
                                 const void* queue_probs_t, int64_t rows, int64_t bank_rows, int32_t dim, int32_t classes,
                                 int32_t dtype, float temperature, float* rowsum, float* numer,
-                                void* workspace, size_t workspace_bytes, void* stream);
+                                int32_t rowsum_ld, int32_t numer_ld, void* workspace, size_t workspace_bytes,
+                                void* stream);
 
 /* ------------------------------------------------------- K2b+K4+K7 ------
  * Per-row finalisation of the CoMatch pseudo-label and the focal soft-CE.
@@ -156,7 +160,8 @@ B200SSL_API int b200ssl_bank_smooth_partial(const void* feats_u_w, const void* q
  * the operand of the tensor-core graph kernel (b200ssl_contrast_*).
  */
 B200SSL_API int b200ssl_comatch_finalize(const void* logits_u_w, const void* logits_u_s0, const float* prob_avg,
-                             const float* rowsum, const float* numer, int64_t rows, int32_t classes,
+                             const float* rowsum, const float* numer, int32_t rowsum_ld, int32_t numer_ld,
+                             int64_t rows, int32_t classes,
                              int32_t dtype, float alpha, float one_minus_alpha, float thr, float gamma,
                              float* probs, float* probs_orig, void* probs_hl, float* scores, int64_t* lbs,
                              float* mask, void* grad_s0, float* out_scalars, void* workspace,
@@ -170,16 +175,19 @@ B200SSL_API int b200ssl_comatch_finalize(const void* logits_u_w, const void* log
  * ptr_state, advanced by rows + n_x).  Same arithmetic, same outputs; the cross-row
  * reductions (DA column means, loss, mask mean) are exchanged through distributed shared
  * memory in rank order instead of global tickets.  Replaces code/comatch.py:163-176,
- * 182-196, 216-220.
+ * 182-196, 216-220.  onehot_tail != 0: probs_orig has rows + n_x rows and the tail receives
+ * onehot(targets_x), i.e. the buffer becomes the probability block of the enqueue
+ * (comatch.py:188-189) that a sharded bank all-gathers.
  */
 B200SSL_API int b200ssl_comatch_rows_fused(const void* logits_u_w, const void* logits_u_s0, const float* rowsum,
-                               const float* numer, int64_t rows, int32_t classes, int32_t dtype, float alpha,
+                               const float* numer, int32_t rowsum_ld, int32_t numer_ld, int64_t rows,
+                               int32_t classes, int32_t dtype, float alpha,
                                float one_minus_alpha, float thr, float gamma, float* da_ring, int32_t* da_state,
                                int32_t window, float* prob_avg, float* probs, float* probs_orig, void* probs_hl,
                                float* scores, int64_t* lbs, float* mask, void* grad_s0, float* out_scalars,
                                void* queue_feats, void* queue_probs, void* queue_probs_t, const void* feats_u_w,
                                const void* feats_x, const int64_t* targets_x, int64_t n_x, int32_t dim,
-                               int64_t* ptr_state, int64_t bank_rows, void* stream);
+                               int64_t* ptr_state, int64_t bank_rows, int32_t onehot_tail, void* stream);
 
 /* ---------------------------------------------------------------- K5 ----
  * Ring-buffer enqueue.  Replaces code/comatch.py:187-196: rows are

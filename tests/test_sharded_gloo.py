@@ -45,13 +45,21 @@ def _make_head_class():
             self.prob_list = hist
             self.prob_avg.copy_(torch.stack(hist).mean(0))
 
-        def _k_smooth(self, queries):
+        def _k_smooth(self, queries, packed_ld=0):
             A = torch.exp(queries @ self.queue_feats.t() / self.temperature)
-            return A.sum(1), A @ self.queue_probs
+            if not packed_ld:
+                return A.sum(1), A @ self.queue_probs
+            packed = torch.zeros(queries.shape[0], packed_ld)
+            packed[:, :self.num_classes] = A @ self.queue_probs
+            packed[:, self.num_classes] = A.sum(1)
+            return packed
 
-        def _k_finalize(self, lw, ls0, rowsum, numer):
+        def _k_finalize(self, lw, ls0, rowsum, numer, lds=(0, 0)):
             p = torch.softmax(lw, 1) / self.prob_avg
             po = p / p.sum(1, keepdim=True)
+            rows, C = lw.shape
+            if rowsum is not None:
+                numer, rowsum = numer[:rows, :C], rowsum[:rows, 0] if rowsum.dim() == 2 else rowsum[:rows]
             probs = self.alpha * po + (1 - self.alpha) * numer / rowsum[:, None] if rowsum is not None else po
             scores, lbs = probs.max(1)
             mask = scores.ge(self.thr).float()
@@ -64,7 +72,7 @@ def _make_head_class():
 
         def _k_enqueue(self, fw, fx, probs_orig, tx, block_offset, advance):
             rows_f = torch.cat([fw, fx])
-            rows_p = torch.cat([probs_orig, F.one_hot(tx, self.num_classes).float()])
+            rows_p = torch.cat([probs_orig, F.one_hot(tx, self.num_classes).float().reshape(-1, self.num_classes)])
             ptr = int(self.ptr_state[0])
             for src, dst, ln in local_segments((ptr + block_offset) % self.queue_size, rows_f.shape[0], self.geom):
                 self.queue_feats[dst:dst + ln] = rows_f[src:src + ln]
@@ -97,6 +105,7 @@ def _worker(rank, world, port, out_dir):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     Head = _make_head_class()
     head = Head(C, D, K, THR, enqueue_mode="always", device="cpu", process_group=dist.group.WORLD)
+    head.fuse_rows = False             # the test double replaces the three separate row kernels
     assert head.geom.shard_rows == K // world and head.queue_feats.shape == (K // world, D)
     outs = []
     for step in range(STEPS):
