@@ -55,6 +55,7 @@ struct ContrastTcParams {
   float* out; unsigned* grid_ticket; float* grid_part;
   const float* loss_u; float lambda_u, lambda_c; float* total_out;
   const float* upstream; float factor; void* g0; void* g1;
+  unsigned long long* dbg;
 };
 
 __device__ __forceinline__ float ex2a(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
@@ -159,7 +160,10 @@ contrast_tc_fwd_kernel(const __grid_constant__ CUtensorMap tm_f0, const __grid_c
   const long long t0 = ntiles * crank / CL;
   const int T = (int)(ntiles * (crank + 1) / CL - t0);      // >= 1 (CL <= ntiles)
   const int U = (T == 1) ? 1 : 2 * T;                       // tile visits: pass A, then pass B recomputes unless T == 1
+  const int ctaid = blockIdx.y * gridDim.x + blockIdx.x;
+  if (threadIdx.x == 0) B200SSL_STAMP(p.dbg, ctaid, 0);
   const uint32_t tmem = setup(sm, warp, lane, &tm_f0, &tm_f1, &tm_ph);
+  if (threadIdx.x == 0) B200SSL_STAMP(p.dbg, ctaid, 1);
   float* statA = sm.stat;
   float* statB = sm.stat + 4 * kT;
 
@@ -251,6 +255,7 @@ contrast_tc_fwd_kernel(const __grid_constant__ CUtensorMap tm_f0, const __grid_c
       }
       for (int u = u_begin; u < u_end; ++u) {
         tc::mbar_wait(&sm.bars[CB_SQ_FULL], u & 1, sm.abort_flag);
+        if (u == 0 && threadIdx.x == 64) B200SSL_STAMP(p.dbg, ctaid, 2);     // first S/Q tile ready (TMA + 10 MMAs)
         tc::tcgen05_fence_after();
         epilogue_tile(phase, (t0 + (u % T)) * kT, a0, a1);
         tc::tcgen05_fence_before();
@@ -259,8 +264,10 @@ contrast_tc_fwd_kernel(const __grid_constant__ CUtensorMap tm_f0, const __grid_c
       float* st = phase == 0 ? statA : statB;
       st[(0 + half) * kT + r_in] = a0;
       st[(2 + half) * kT + r_in] = a1;
+      if (threadIdx.x == 64) B200SSL_STAMP(p.dbg, ctaid, 3 + 2 * phase);     // pass A (3) / pass B (5) done
     }
     if (CL > 1) cluster.sync(); else __syncthreads();       // partials of this pass visible cluster-wide
+    if (threadIdx.x == 0) B200SSL_STAMP(p.dbg, ctaid, 4 + 2 * phase);       // after exchange A (4) / B (6)
   }
   // ---- loss_i and r_i: cluster rank c folds rows [c*RB, (c+1)*RB) in rank order ----
   const int RB = kT / CL;
@@ -285,6 +292,7 @@ contrast_tc_fwd_kernel(const __grid_constant__ CUtensorMap tm_f0, const __grid_c
     tc::tcgen05_fence_after();
     tc::tmem_dealloc(tmem, kTmemColsCt);
   }
+  if (threadIdx.x == 0) B200SSL_STAMP(p.dbg, ctaid, 7);     // rows folded, final cluster sync passed, TMEM freed
   // ---- loss: CTA sum, then last CTA of the grid folds all CTA partials in order ----
   __shared__ float s_w[kCtThreads / 32];
   __shared__ bool s_glast;
@@ -301,6 +309,7 @@ contrast_tc_fwd_kernel(const __grid_constant__ CUtensorMap tm_f0, const __grid_c
     s_glast = (atomicAdd(p.grid_ticket, 1u) == ncta - 1);
   }
   __syncthreads();
+  if (threadIdx.x == 0) B200SSL_STAMP(p.dbg, ctaid, 8);     // grid ticket taken
   if (!s_glast) return;
   __threadfence();
   float v = 0.f;
@@ -334,7 +343,10 @@ contrast_tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_f0, const __grid_c
   const long long ntiles = (p.rows + kT - 1) / kT;
   const long long t0 = ntiles * crank / CL;
   const int T = (int)(ntiles * (crank + 1) / CL - t0);
+  const int ctaid = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+  if (threadIdx.x == 0) B200SSL_STAMP(p.dbg, ctaid, 0);
   const uint32_t tmem = setup(sm, warp, lane, &tm_f0, &tm_f1, &tm_ph);
+  if (threadIdx.x == 0) B200SSL_STAMP(p.dbg, ctaid, 1);
   float* sAcc = reinterpret_cast<float*>(sm.z);             // [128][kAccLd] fp32, after the pipeline has drained
 
   if (warp == 0) {
@@ -411,6 +423,7 @@ contrast_tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_f0, const __grid_c
       const long long j0 = colmode ? (long long)own_tile * kT : o0;
       if (colmode) { gi = o0 + r_in; load_stats(); }
       tc::mbar_wait(&sm.bars[CB_SQ_FULL], t & 1, sm.abort_flag);
+      if (t == 0 && threadIdx.x == 64) B200SSL_STAMP(p.dbg, ctaid, 2);       // first S/Q tile ready
       if (t >= 1) tc::mbar_wait(&sm.bars[CB_Z_EMPTY], (t - 1) & 1, sm.abort_flag);
       tc::tcgen05_fence_after();
 #pragma unroll 1
@@ -457,8 +470,10 @@ contrast_tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_f0, const __grid_c
       tc::mbar_arrive(&sm.bars[CB_SQ_EMPTY]);
       tc::fence_proxy_async_smem();
       tc::mbar_arrive(&sm.bars[CB_Z_FULL]);
+      if (t == T - 1 && threadIdx.x == 64) B200SSL_STAMP(p.dbg, ctaid, 3);   // last dZ tile written
     }
     tc::mbar_wait(&sm.bars[CB_ACC], 0, sm.abort_flag);       // all MMAs retired: dZ smem is free, accumulator final
+    if (threadIdx.x == 64) B200SSL_STAMP(p.dbg, ctaid, 4);   // gradient accumulator complete
     tc::tcgen05_fence_after();
     {                                                        // accumulator -> fp32 tile in smem: thread (row, half) takes 32 columns
       uint32_t av[32];
@@ -473,6 +488,7 @@ contrast_tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_f0, const __grid_c
     tc::tcgen05_fence_before();
   }
   if (CL > 1) cluster.sync(); else __syncthreads();
+  if (threadIdx.x == 0) B200SSL_STAMP(p.dbg, ctaid, 5);     // accumulators staged, cluster sync passed
   if (warp == 0) {
     tc::tcgen05_fence_after();
     tc::tmem_dealloc(tmem, kTmemColsCt);
@@ -509,6 +525,7 @@ contrast_tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_f0, const __grid_c
     }
   }
   if (CL > 1) cluster.sync();                                // nobody leaves while its smem is still being read
+  if (threadIdx.x == 0) B200SSL_STAMP(p.dbg, ctaid, 6);     // fold done
 }
 
 int ct_cluster(long long rows) {
@@ -566,7 +583,7 @@ int contrast_fwd_tc(const void* f0, const void* f1, const void* probs_hl, long l
   p.rows = rows; p.C = classes; p.scale = (float)(1.4426950408889634 / (double)temperature);
   p.inv_tau = 1.0f / temperature; p.th = contrast_th; p.stats = stats; p.out = out_scalar;
   p.loss_u = loss_u; p.lambda_u = lambda_u; p.lambda_c = lambda_c; p.total_out = total_out;
-  p.cluster = ct_cluster(rows);
+  p.cluster = ct_cluster(rows); p.dbg = debug_timing_buffer();
   const size_t need = kWsHeaderBytes + sizeof(float) * contrast_tc_workspace_floats(rows);
   if (workspace_bytes < need) return fail(B200SSL_E_WORKSPACE, "%s: workspace %zu < %zu bytes", fn, workspace_bytes, need);
   p.grid_ticket = reinterpret_cast<unsigned*>(workspace) + 4;
@@ -590,7 +607,7 @@ int contrast_bwd_tc(const void* f0, const void* f1, const void* probs_hl, const 
   p.rows = rows; p.C = classes; p.scale = (float)(1.4426950408889634 / (double)temperature);
   p.inv_tau = 1.0f / temperature; p.th = contrast_th; p.stats = const_cast<float*>(stats);
   p.upstream = upstream; p.factor = factor; p.g0 = g0; p.g1 = g1;
-  p.cluster = ct_cluster(rows);
+  p.cluster = ct_cluster(rows); p.dbg = debug_timing_buffer();
   CUtensorMap m[3];
   if (int e = ct_maps(m, f0, f1, probs_hl, rows)) return e;
   static bool attr = false;

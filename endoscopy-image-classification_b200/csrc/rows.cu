@@ -12,6 +12,8 @@
 #include <cooperative_groups.h>
 #include <math.h>
 
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace b200ssl {
@@ -36,8 +38,14 @@ __device__ __forceinline__ void row_load(const float* srow, int C, int gl, bool 
   }
 }
 
+// FAST = false: IEEE division / accurate expf, logf (fp32 storage: bit-level parity with the eager reference).
+// FAST = true : MUFU approximations (bf16 storage: the inputs carry 8 mantissa bits, tolerance 1e-2).
+template <bool FAST> __device__ __forceinline__ float fdiv(float a, float b) { return FAST ? __fdividef(a, b) : __fdiv_rn(a, b); }
+template <bool FAST> __device__ __forceinline__ float fexp(float a) { return FAST ? __expf(a) : expf(a); }
+template <bool FAST> __device__ __forceinline__ float flog(float a) { return FAST ? __logf(a) : logf(a); }
+
 // e[k] = expf(x[k]-max) (0 for padding), returns max and sum over the row.
-template <int LPR, int EPL>
+template <int LPR, int EPL, bool FAST = false>
 __device__ __forceinline__ void row_softmax_stats(const float (&x)[EPL], float (&e)[EPL], float& mx, float& sum) {
   float m = -INFINITY;
 #pragma unroll
@@ -47,7 +55,7 @@ __device__ __forceinline__ void row_softmax_stats(const float (&x)[EPL], float (
   float s = 0.f;
 #pragma unroll
   for (int k = 0; k < EPL; ++k) {
-    e[k] = (x[k] == -INFINITY) ? 0.f : expf(x[k] - m);
+    e[k] = (x[k] == -INFINITY) ? 0.f : fexp<FAST>(x[k] - m);
     s += e[k];
   }
   sum = group_sum<LPR>(s);
@@ -405,21 +413,21 @@ __device__ __forceinline__ void load_numer_tile(const float* __restrict__ numer,
 // One row of the CoMatch finalisation (LPR lanes): pseudo-label from the weak logits in `sw`, alpha-mix
 // with the smoothing sums (`sn`, rowsum), confidence mask, focal soft-CE + gradient against the strong
 // logits in `ss`.  Leaves probs in sw, probs_orig in so, the gradient in ss; adds (loss, mask) to acc.
-template <int LPR, int EPL>
+template <int LPR, int EPL, bool FAST = false>
 __device__ __forceinline__ void finalize_row(const FinalizeParams& p, const float* __restrict__ prob_avg, float* sw, float* ss,
                                              float* so, const float* sn, long long row0, int r, bool valid, int gl, bool smooth,
-                                             float inv_rows, float (&acc)[2]) {
+                                             float inv_rows, float (&acc)[2], __nv_bfloat16* shl = nullptr) {
   const int C = p.C;
     float x[EPL], e[EPL], pr[EPL];
     float mx, sum;
     // softmax + DA divide + renormalise (comatch.py:163,174-176)
     row_load<LPR, EPL>(sw + r * C, C, gl, valid, x);
-    row_softmax_stats<LPR, EPL>(x, e, mx, sum);
+    row_softmax_stats<LPR, EPL, FAST>(x, e, mx, sum);
     float q = 0.f;
 #pragma unroll
     for (int k = 0; k < EPL; ++k) {
       const int c = gl + k * LPR;
-      pr[k] = (c < C) ? __fdiv_rn(__fdiv_rn(e[k], sum), prob_avg[c]) : 0.f;
+      pr[k] = (c < C) ? fdiv<FAST>(fdiv<FAST>(e[k], sum), prob_avg[c]) : 0.f;
       q += pr[k];
     }
     q = group_sum<LPR>(q);
@@ -428,11 +436,11 @@ __device__ __forceinline__ void finalize_row(const FinalizeParams& p, const floa
 #pragma unroll
     for (int k = 0; k < EPL; ++k) {
       const int c = gl + k * LPR;
-      const float po = __fdiv_rn(pr[k], q);
+      const float po = fdiv<FAST>(pr[k], q);
       if (valid && c < C) so[r * C + c] = po;
       float v = po;
       if (smooth && valid && c < C)  // comatch.py:181-182
-        v = __fadd_rn(__fmul_rn(p.alpha, po), __fmul_rn(p.one_minus_alpha, __fdiv_rn(sn[r * C + c], rs)));
+        v = __fadd_rn(__fmul_rn(p.alpha, po), __fmul_rn(p.one_minus_alpha, fdiv<FAST>(sn[r * C + c], rs)));
       pr[k] = (c < C) ? v : 0.f;
       psum += pr[k];
     }
@@ -452,7 +460,7 @@ __device__ __forceinline__ void finalize_row(const FinalizeParams& p, const floa
           const int c = gl + k * LPR;
           if (c < 32) {
             const __nv_bfloat16 hi = __float2bfloat16_rn(pr[k]);
-            __nv_bfloat16* dst = p.hl + (row0 + r) * 64 + c;
+            __nv_bfloat16* dst = shl ? shl + r * 64 + c : p.hl + (row0 + r) * 64 + c;
             dst[0] = hi;
             dst[32] = __float2bfloat16_rn(pr[k] - __bfloat162float(hi));
           }
@@ -467,15 +475,15 @@ __device__ __forceinline__ void finalize_row(const FinalizeParams& p, const floa
     }
     // focal soft-CE on the strong view (comatch.py:216-220) + gradient
     row_load<LPR, EPL>(ss + r * C, C, gl, valid, x);
-    row_softmax_stats<LPR, EPL>(x, e, mx, sum);
-    const float logsum = logf(sum);
+    row_softmax_stats<LPR, EPL, FAST>(x, e, mx, sum);
+    const float logsum = flog<FAST>(sum);
     float d = 0.f;
 #pragma unroll
     for (int k = 0; k < EPL; ++k)
       if (valid && gl + k * LPR < C) d += ((x[k] - mx) - logsum) * pr[k];
     d = group_sum<LPR>(d);
     const float logp = -d * m;
-    const float pp = expf(-logp);
+    const float pp = fexp<FAST>(-logp);
     const float om = 1.f - pp;
     const float lrow = pow_gamma(om, p.gamma) * logp;
     if (valid && gl == 0) acc[0] += lrow;
@@ -486,7 +494,7 @@ __device__ __forceinline__ void finalize_row(const FinalizeParams& p, const floa
 #pragma unroll
       for (int k = 0; k < EPL; ++k) {
         const int c = gl + k * LPR;
-        if (c < C) ss[r * C + c] = coef * (__fdiv_rn(e[k], sum) * psum - pr[k]);
+        if (c < C) ss[r * C + c] = coef * (fdiv<FAST>(e[k], sum) * psum - pr[k]);
       }
     }
 }
@@ -550,6 +558,7 @@ struct FusedParams {
   void* qf; void* qp; void* qpt; const void* fu; const void* fx; const long long* tx;
   long long n_x; int D; long long* ptr_state; long long K;
   int CL; long long rows_per_cta;
+  unsigned long long* dbg;
   int onehot_tail;   // probs_orig has rows + n_x rows: fill the tail with onehot(targets_x) (block for the sharded enqueue)
 };
 
@@ -557,6 +566,7 @@ template <typename T>
 __global__ void __launch_bounds__(kFusedThreads) comatch_rows_fused_kernel(const FusedParams p) {
   namespace cg = cooperative_groups;
   constexpr int LPR = 8, EPL = 4, ROWS = kFusedRows;
+  constexpr bool FAST = !std::is_same<T, float>::value;       // bf16 storage: MUFU approximations are inside the budget
   extern __shared__ float smem[];
   const FinalizeParams& f = p.f;
   const int C = f.C;
@@ -564,57 +574,31 @@ __global__ void __launch_bounds__(kFusedThreads) comatch_rows_fused_kernel(const
   float* ss = sw + ROWS * C;
   float* so = ss + ROWS * C;
   float* sn = so + ROWS * C;
-  float* scol = sn + ROWS * C;      // [32] column sums of this CTA
-  float* savg = scol + 32;          // [32] prob_avg
-  float* sred = savg + 32;          // [2]  (loss, mask) of this CTA
+  float* sall = sn + ROWS * C;      // [8][32] column sums pushed by every CTA of the cluster
+  float* savg = sall + kFusedMaxCluster * 32;   // [32] prob_avg
+  float* sfin = savg + 32;          // [8][2]  (loss, mask) pushed into rank 0
+  __nv_bfloat16* shl = reinterpret_cast<__nv_bfloat16*>(sfin + kFusedMaxCluster * 2);   // [64][64] bf16 hi/lo staging
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int gl = lane % LPR, rw = lane / LPR;
   cg::cluster_group cluster = cg::this_cluster();
   const int CL = p.CL;
   const int crank = CL > 1 ? (int)cluster.block_rank() : 0;
   const long long r_lo = min(f.rows, (long long)crank * p.rows_per_cta), r_hi = min(f.rows, r_lo + p.rows_per_cta);
+  const bool single = (r_hi - r_lo) <= ROWS;                 // all rows of this CTA fit one pass: tiles are loaded once
   const bool smooth = f.rowsum != nullptr && f.numer != nullptr;
   const float inv_rows = 1.0f / (float)f.rows;
   const long long ptr = p.qf ? *reinterpret_cast<volatile long long*>(p.ptr_state) : 0;
+  if (tid == 0) B200SSL_STAMP(p.dbg, crank, 0);
 
-  // ---- phase 1: softmax column sums of the rows this CTA owns (comatch.py:163,169) ----
-  if (tid < 32) scol[tid] = 0.f;
-  for (long long row0 = r_lo; row0 < r_hi; row0 += ROWS) {
-    const int nrows = (int)min((long long)ROWS, r_hi - row0);
-    __syncthreads();
-    tile_g2s(static_cast<const T*>(f.w) + row0 * C, sw, nrows * C);
-    __syncthreads();
-    const int r = warp * 4 + rw;
-    const bool valid = r < nrows;
-    float x[EPL], e[EPL];
-    float mx, sum;
-    row_load<LPR, EPL>(sw + r * C, C, gl, valid, x);
-    row_softmax_stats<LPR, EPL>(x, e, mx, sum);
-    if (valid) {
-#pragma unroll
-      for (int k = 0; k < EPL; ++k) {
-        const int c = gl + k * LPR;
-        if (c < C) sw[r * C + c] = __fdiv_rn(e[k], sum);
-      }
-    }
-    __syncthreads();
-    if (tid < C) {
-      float t = scol[tid];
-      for (int rr = 0; rr < nrows; ++rr) t += sw[rr * C + tid];
-      scol[tid] = t;
-    }
-  }
-  __syncthreads();
-  if (CL > 1) cluster.sync();
-  // ---- DA history -> prob_avg, computed identically by every CTA (comatch.py:169-173) ----
+  // DA history: everything that does not depend on this batch is fetched up front (comatch.py:169-173)
+  int count = 1, head = 0;
+  float h_old = 0.f;
   if (tid < C) {
-    float tot = 0.f;
-    for (int r = 0; r < CL; ++r) tot += (CL > 1 ? cluster.map_shared_rank(scol, r) : scol)[tid];   // rank order
-    const float mean = tot / (float)f.rows;
-    const int count_old = p.state[0], head = p.state[1];
-    const int count = min(count_old + 1, p.window), head_new = (head + 1) % p.window;
-    float h = 0.f;
-    for (int a0 = 0; a0 < count - 1; a0 += 8) {
+    const int count_old = p.state[0];
+    head = p.state[1];
+    count = min(count_old + 1, p.window);
+    const int head_new = (head + 1) % p.window;
+    for (int a0 = 0; a0 < count - 1; a0 += 8) {               // oldest -> newest, the newest entry is this batch's mean
       float v[8];
 #pragma unroll
       for (int u = 0; u < 8; ++u) {
@@ -623,73 +607,127 @@ __global__ void __launch_bounds__(kFusedThreads) comatch_rows_fused_kernel(const
         v[u] = (a < count - 1) ? p.ring[(size_t)slot * C + tid] : 0.f;
       }
 #pragma unroll
-      for (int u = 0; u < 8; ++u) h += v[u];
+      for (int u = 0; u < 8; ++u) h_old += v[u];
     }
-    h += mean;
-    savg[tid] = h / (float)count;
+  }
+  if (single) {
+    const int nrows = (int)(r_hi - r_lo), cnt = nrows * C;
+    tile_g2s(static_cast<const T*>(f.w) + r_lo * C, sw, cnt);
+    tile_g2s(static_cast<const T*>(f.s0) + r_lo * C, ss, cnt);
+    if (smooth) load_numer_tile(f.numer, f.numer_ld, r_lo, nrows, C, sn);
+  }
+  // ---- phase 1: softmax column sums of the rows this CTA owns (comatch.py:163,169) ----
+  float colsum = 0.f;                                        // thread c < C owns class c
+  for (long long row0 = r_lo; row0 < r_hi; row0 += ROWS) {
+    const int nrows = (int)min((long long)ROWS, r_hi - row0);
+    __syncthreads();
+    if (!single) tile_g2s(static_cast<const T*>(f.w) + row0 * C, sw, nrows * C);
+    __syncthreads();
+    const int r = warp * 4 + rw;
+    const bool valid = r < nrows;
+    float x[EPL], e[EPL];
+    float mx, sum;
+    row_load<LPR, EPL>(sw + r * C, C, gl, valid, x);
+    row_softmax_stats<LPR, EPL, FAST>(x, e, mx, sum);
+    if (valid) {
+#pragma unroll
+      for (int k = 0; k < EPL; ++k) {
+        const int c = gl + k * LPR;
+        if (c < C) so[r * C + c] = fdiv<FAST>(e[k], sum);
+      }
+    }
+    __syncthreads();
+    if (tid < C)
+      for (int rr = 0; rr < nrows; ++rr) colsum += so[rr * C + tid];
+  }
+  if (tid < C) {                                             // push this CTA's column sums to every CTA of the cluster
+    for (int r = 0; r < CL; ++r) (CL > 1 ? cluster.map_shared_rank(sall, r) : sall)[crank * 32 + tid] = colsum;
+  }
+  if (tid == 0) B200SSL_STAMP(p.dbg, crank, 1);
+  if (CL > 1) cluster.sync(); else __syncthreads();
+  if (tid == 0) B200SSL_STAMP(p.dbg, crank, 2);
+  // ---- DA history -> prob_avg, computed identically by every CTA ----
+  if (tid < C) {
+    float tot = 0.f;
+    for (int r = 0; r < CL; ++r) tot += sall[r * 32 + tid];  // rank order, local reads
+    const float mean = tot / (float)f.rows;
+    savg[tid] = (h_old + mean) / (float)count;
     if (crank == 0) {
-      p.ring[(size_t)head * C + tid] = mean;      // slot `head` leaves the window: nobody reads it this step
+      p.ring[(size_t)head * C + tid] = mean;                 // slot `head` leaves the window: nobody reads it this step
       const_cast<float*>(f.prob_avg)[tid] = savg[tid];
     }
   }
   __syncthreads();
+  if (tid == 0) B200SSL_STAMP(p.dbg, crank, 3);
 
   // ---- phase 2: finalise every row, store, enqueue ----
   float acc[2] = {0.f, 0.f};
+  const int vec_per_row = p.D * (int)sizeof(T) / 16, epv = 16 / (int)sizeof(T);
   for (long long row0 = r_lo; row0 < r_hi; row0 += ROWS) {
     const int nrows = (int)min((long long)ROWS, r_hi - row0);
     const int cnt = nrows * C;
-    __syncthreads();
-    tile_g2s(static_cast<const T*>(f.w) + row0 * C, sw, cnt);
-    tile_g2s(static_cast<const T*>(f.s0) + row0 * C, ss, cnt);
-    if (smooth) load_numer_tile(f.numer, f.numer_ld, row0, nrows, C, sn);
-    __syncthreads();
+    if (!single) {
+      __syncthreads();
+      tile_g2s(static_cast<const T*>(f.w) + row0 * C, sw, cnt);
+      tile_g2s(static_cast<const T*>(f.s0) + row0 * C, ss, cnt);
+      if (smooth) load_numer_tile(f.numer, f.numer_ld, row0, nrows, C, sn);
+      __syncthreads();
+    }
+    if (tid == 0) B200SSL_STAMP(p.dbg, crank, 4);
     const int r = warp * 4 + rw;
-    finalize_row<LPR, EPL>(f, savg, sw, ss, so, sn, row0, r, r < nrows, gl, smooth, inv_rows, acc);
+    finalize_row<LPR, EPL, FAST>(f, savg, sw, ss, so, sn, row0, r, r < nrows, gl, smooth, inv_rows, acc, f.hl ? shl : nullptr);
     __syncthreads();
+    if (tid == 0) B200SSL_STAMP(p.dbg, crank, 5);
+    if (f.hl)                                             // [rows, 64] bf16 rows are 128 B: one 16-byte store per thread
+      for (int i = tid; i < nrows * 8; i += kFusedThreads)
+        reinterpret_cast<uint4*>(f.hl + row0 * 64)[i] = reinterpret_cast<const uint4*>(shl)[i];
     tile_s2g(sw, f.probs + row0 * C, cnt);
     tile_s2g(so, f.probs_orig + row0 * C, cnt);
     tile_s2g(ss, static_cast<T*>(f.gs0) + row0 * C, cnt);
     if (p.qf) {     // unlabeled-weak rows of this pass -> bank rows (ptr + row) % K     (comatch.py:187-196)
-      const int vec_per_row = p.D * (int)sizeof(T) / 16;
       for (int i = tid; i < nrows * vec_per_row; i += kFusedThreads) {
         const int rr = i / vec_per_row, v = i - rr * vec_per_row;
         const long long g = (ptr + row0 + rr) % p.K;
-        const uint4 val = ldg128(static_cast<const T*>(p.fu) + (row0 + rr) * p.D + v * (16 / sizeof(T)));
-        *reinterpret_cast<uint4*>(static_cast<T*>(p.qf) + g * p.D + v * (16 / sizeof(T))) = val;
+        const uint4 val = ldg128(static_cast<const T*>(p.fu) + (row0 + rr) * p.D + v * epv);
+        *reinterpret_cast<uint4*>(static_cast<T*>(p.qf) + g * p.D + v * epv) = val;
       }
       for (int i = tid; i < cnt; i += kFusedThreads) {
         const int rr = i / C, c = i - rr * C;
         const long long g = (ptr + row0 + rr) % p.K;
-        const T val = from_f32<T>(so[i]);
-        static_cast<T*>(p.qp)[g * C + c] = val;
-        if (p.qpt) static_cast<T*>(p.qpt)[(size_t)c * p.K + g] = val;
+        static_cast<T*>(p.qp)[g * C + c] = from_f32<T>(so[i]);
       }
+      if (p.qpt)                                            // transposed copy: consecutive threads -> consecutive bank rows
+        for (int i = tid; i < cnt; i += kFusedThreads) {
+          const int c = i / nrows, rr = i - c * nrows;
+          const long long g = (ptr + row0 + rr) % p.K;
+          static_cast<T*>(p.qpt)[(size_t)c * p.K + g] = from_f32<T>(so[rr * C + c]);
+        }
     }
   }
+  const int n_x = (int)p.n_x;
   if (p.qf) {       // labeled rows: [feats_x ; onehot(targets_x)], spread over the CTAs
-    const int vec_per_row = p.D * (int)sizeof(T) / 16;
-    for (long long i = (long long)crank * kFusedThreads + tid; i < p.n_x * vec_per_row; i += (long long)CL * kFusedThreads) {
-      const long long rr = i / vec_per_row; const int v = (int)(i - rr * vec_per_row);
+    for (int i = crank * kFusedThreads + tid; i < n_x * vec_per_row; i += CL * kFusedThreads) {
+      const int rr = i / vec_per_row, v = i - rr * vec_per_row;
       const long long g = (ptr + f.rows + rr) % p.K;
-      const uint4 val = ldg128(static_cast<const T*>(p.fx) + rr * p.D + v * (16 / sizeof(T)));
-      *reinterpret_cast<uint4*>(static_cast<T*>(p.qf) + g * p.D + v * (16 / sizeof(T))) = val;
+      const uint4 val = ldg128(static_cast<const T*>(p.fx) + (size_t)rr * p.D + v * epv);
+      *reinterpret_cast<uint4*>(static_cast<T*>(p.qf) + g * p.D + v * epv) = val;
     }
-    for (long long i = (long long)crank * kFusedThreads + tid; i < p.n_x * C; i += (long long)CL * kFusedThreads) {
-      const long long rr = i / C; const int c = (int)(i - rr * C);
+    for (int i = crank * kFusedThreads + tid; i < n_x * C; i += CL * kFusedThreads) {
+      const int rr = i / C, c = i - rr * C;
       const long long g = (ptr + f.rows + rr) % p.K;
       const T val = from_f32<T>(c == (int)p.tx[rr] ? 1.f : 0.f);
       static_cast<T*>(p.qp)[g * C + c] = val;
       if (p.qpt) static_cast<T*>(p.qpt)[(size_t)c * p.K + g] = val;
     }
   }
+  if (tid == 0) B200SSL_STAMP(p.dbg, crank, 6);
   if (p.onehot_tail) {      // [probs_orig ; onehot(targets_x)] = the probability block of the enqueue (comatch.py:188-189)
-    for (long long i = (long long)crank * kFusedThreads + tid; i < p.n_x * C; i += (long long)CL * kFusedThreads) {
-      const long long rr = i / C; const int c = (int)(i - rr * C);
+    for (int i = crank * kFusedThreads + tid; i < n_x * C; i += CL * kFusedThreads) {
+      const int rr = i / C, c = i - rr * C;
       f.probs_orig[(f.rows + rr) * C + c] = (c == (int)p.tx[rr]) ? 1.f : 0.f;
     }
   }
-  // ---- loss / mask mean: CTA sum, then rank 0 folds the CTAs in rank order ----
+  // ---- loss / mask mean: CTA sum pushed into rank 0, which folds the CTAs in rank order ----
   __shared__ float s_part[2][kFusedWarps];
 #pragma unroll
   for (int i = 0; i < 2; ++i) {
@@ -700,22 +738,20 @@ __global__ void __launch_bounds__(kFusedThreads) comatch_rows_fused_kernel(const
   if (tid < 2) {
     float t = 0.f;
     for (int w = 0; w < kFusedWarps; ++w) t += s_part[tid][w];
-    sred[tid] = t;
+    (CL > 1 ? cluster.map_shared_rank(sfin, 0) : sfin)[crank * 2 + tid] = t;
   }
-  __syncthreads();
-  if (CL > 1) cluster.sync();
+  if (CL > 1) cluster.sync(); else __syncthreads();          // last exchange: afterwards only rank 0 reads, and only its own smem
   if (crank == 0 && tid < 2) {
     float t = 0.f;
-    for (int r = 0; r < CL; ++r) t += (CL > 1 ? cluster.map_shared_rank(sred, r) : sred)[tid];
+    for (int r = 0; r < CL; ++r) t += sfin[r * 2 + tid];
     f.out[tid] = t / (float)f.rows;
   }
   if (crank == 0 && tid == 0) {
-    const int count_old = p.state[0], head = p.state[1];
-    p.state[0] = min(count_old + 1, p.window);
+    p.state[0] = count;
     p.state[1] = (head + 1) % p.window;
     if (p.qf) p.ptr_state[0] = (ptr + f.rows + p.n_x) % p.K;       // comatch.py:196
   }
-  if (CL > 1) cluster.sync();           // nobody leaves while its smem is still being read
+  if (tid == 0) B200SSL_STAMP(p.dbg, crank, 7);
 }
 
 // ---- grad *= *scale -----------------------------------------------------------
@@ -935,6 +971,7 @@ extern "C" int b200ssl_comatch_rows_fused(const void* logits_u_w, const void* lo
   p.tx = reinterpret_cast<const long long*>(targets_x); p.n_x = n_x; p.D = dim;
   p.ptr_state = reinterpret_cast<long long*>(ptr_state); p.K = bank_rows;
   p.onehot_tail = onehot_tail ? 1 : 0;
+  p.dbg = debug_timing_buffer();
   if (onehot_tail && (n_x > 0 && !targets_x)) return fail(B200SSL_E_NULL, "%s: onehot_tail needs targets_x", fn);
   long long cl = (rows + kFusedRows - 1) / kFusedRows;
   if (cl > kFusedMaxCluster) cl = kFusedMaxCluster;
@@ -943,7 +980,8 @@ extern "C" int b200ssl_comatch_rows_fused(const void* logits_u_w, const void* lo
   if (clp < cl) clp *= 2;                      // round up to a power of two (cluster sizes 1, 2, 4, 8)
   p.CL = clp;
   p.rows_per_cta = (((rows + clp - 1) / clp) + 7) & ~7LL;          // multiples of 8 rows keep the tiles 16-byte aligned
-  const size_t smem = ((size_t)4 * kFusedRows * classes + 32 + 32 + 4) * sizeof(float);
+  const size_t smem = ((size_t)4 * kFusedRows * classes + kFusedMaxCluster * 32 + 32 + kFusedMaxCluster * 2) * sizeof(float) +
+                      (size_t)kFusedRows * 64 * sizeof(__nv_bfloat16) + 16;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)clp, 1, 1);
   cfg.blockDim = dim3(kFusedThreads, 1, 1);
