@@ -58,7 +58,7 @@ SIGNATURES = {
     "b200ssl_contrast_fwd": (_i32, [_vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _f32, _f32, _vp, _vp, _vp, _f32, _f32, _vp,
                                     _vp, _sz, _vp]),
     "b200ssl_contrast_bwd": (_i32, [_vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _f32, _f32, _vp, _f32, _vp, _vp,
-                                    _vp, _sz, _vp]),
+                                    _vp, _i64, _vp, _f32, _vp, _sz, _vp]),
     "b200ssl_ema_multi_tensor": (_i32, [_vp, _i32, _i32, _i32, _f32, _f32, _i32, _vp]),
 }
 

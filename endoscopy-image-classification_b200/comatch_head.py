@@ -68,15 +68,20 @@ class _HeadFn(torch.autograd.Function):
             return g_own + lam * g_total, 1.0
 
         gs0 = gf0 = gf1 = None
-        if ctx.needs_input_grad[4]:
-            g, fac = upstream(g_u, ctx.lambda_u)
-            gs0 = torch.zeros_like(grad_s0) if g is None else head._k_scale(grad_s0, g, fac)
-        if ctx.needs_input_grad[6] or ctx.needs_input_grad[7]:
-            g, fac = upstream(g_c, ctx.lambda_c)
-            if g is None:
-                gf0, gf1 = torch.zeros_like(f0), torch.zeros_like(f1)
-            else:
-                gf0, gf1 = head._k_contrast_bwd(f0, f1, probs, stats, g, fac, probs_hl)
+        gu, fac_u = upstream(g_u, ctx.lambda_u)
+        gc, fac_c = upstream(g_c, ctx.lambda_c)
+        want_s0 = ctx.needs_input_grad[4]
+        want_f = ctx.needs_input_grad[6] or ctx.needs_input_grad[7]
+        if want_f and gc is not None:
+            # one launch: contrastive gradients + (piggy-backed) scaling of the stashed focal-CE gradient
+            piggy = (grad_s0, gu, fac_u) if (want_s0 and gu is not None) else None
+            gf0, gf1 = head._k_contrast_bwd(f0, f1, probs, stats, gc, fac_c, probs_hl, scale=piggy)
+            if piggy is not None:
+                gs0, want_s0 = grad_s0, False
+        elif want_f:
+            gf0, gf1 = torch.zeros_like(f0), torch.zeros_like(f1)
+        if want_s0:
+            gs0 = torch.zeros_like(grad_s0) if gu is None else head._k_scale(grad_s0, gu, fac_u)
         return None, None, None, None, gs0, None, gf0, gf1, None, None
 
 
@@ -374,15 +379,20 @@ class CoMatchHead:
                                              N.stream_ptr(self.device)), "contrast_fwd")
         return stats, scalars[2]
 
-    def _k_contrast_bwd(self, f0, f1, probs, stats, g_c, factor: float = 1.0, probs_hl=None):
+    def _k_contrast_bwd(self, f0, f1, probs, stats, g_c, factor: float = 1.0, probs_hl=None, scale=None):
         g = g_c.detach().to(torch.float32).reshape(1).contiguous()
+        sg, sn, su, sf = None, 0, None, 1.0
+        if scale is not None:
+            sg, su, sf = scale[0], scale[1].detach().to(torch.float32).reshape(1).contiguous(), float(scale[2])
+            sn = sg.numel()
         gf0, gf1 = torch.empty_like(f0), torch.empty_like(f1)
         rows, D = f0.shape
         ws, wsb = self._ws(rows)
         N.check(N.lib().b200ssl_contrast_bwd(f0.data_ptr(), f1.data_ptr(), probs.data_ptr(), N.ptr(probs_hl),
                                              stats.data_ptr(), rows,
                                              D, self.num_classes, N.dtype_enum(f0), self.temperature, self.contrast_th,
-                                             g.data_ptr(), factor, gf0.data_ptr(), gf1.data_ptr(), ws, wsb,
+                                             g.data_ptr(), factor, gf0.data_ptr(), gf1.data_ptr(), N.ptr(sg), sn, N.ptr(su), sf,
+                                             ws, wsb,
                                              N.stream_ptr(self.device)), "contrast_bwd")
         return gf0, gf1
 

@@ -354,6 +354,7 @@ int contrast_fwd_tc(const void* f0, const void* f1, const void* probs_hl, long l
                     float* total_out, void* workspace, size_t workspace_bytes, cudaStream_t stream);
 int contrast_bwd_tc(const void* f0, const void* f1, const void* probs_hl, const float* stats, long long rows, int classes,
                     float temperature, float contrast_th, const float* upstream, float factor, void* g0, void* g1,
+                    void* scale_grad, long long scale_numel, const float* scale_up, float scale_factor,
                     void* workspace, size_t workspace_bytes, cudaStream_t stream);
 }
 // bf16 embeddings with 128-byte rows + the hi/lo probability split: tcgen05 path (contrast_tc.cu)
@@ -422,14 +423,22 @@ extern "C" int b200ssl_contrast_fwd(const void* feats_s0, const void* feats_s1, 
 extern "C" int b200ssl_contrast_bwd(const void* feats_s0, const void* feats_s1, const float* probs, const void* probs_hl,
                                     const float* stats, int64_t rows, int32_t dim, int32_t classes, int32_t dtype, float temperature,
                                     float contrast_th, const float* upstream, float factor, void* grad_f0, void* grad_f1,
+                                    void* scale_grad, int64_t scale_numel, const float* scale_upstream, float scale_factor,
                                     void* workspace, size_t workspace_bytes, void* stream) {
   const char* fn = "b200ssl_contrast_bwd";
   if (int e = check_contrast(fn, rows, dim, classes, dtype, temperature)) return e;
   if (!feats_s0 || !feats_s1 || !probs || !stats || !grad_f0 || !grad_f1) return fail(B200SSL_E_NULL, "%s: NULL tensor", fn);
   if (!workspace || (reinterpret_cast<uintptr_t>(workspace) & 255u)) return fail(B200SSL_E_ALIGN, "%s: workspace NULL or not 256-byte aligned", fn);
-  if (use_tc(feats_s0, feats_s1, probs_hl, dim, classes, dtype, grad_f0, grad_f1))
+  if (use_tc(feats_s0, feats_s1, probs_hl, dim, classes, dtype, grad_f0, grad_f1)) {
+    const bool piggy = scale_grad && (reinterpret_cast<uintptr_t>(scale_grad) & 15u) == 0;   // vector path needs 16-byte alignment
+    if (scale_grad && !piggy)
+      if (int e = b200ssl_scale_inplace(scale_grad, scale_numel, dtype, scale_upstream, scale_factor, stream)) return e;
     return contrast_bwd_tc(feats_s0, feats_s1, probs_hl, stats, rows, classes, temperature, contrast_th, upstream, factor,
-                           grad_f0, grad_f1, workspace, workspace_bytes, as_stream(stream));
+                           grad_f0, grad_f1, piggy ? scale_grad : nullptr, scale_numel, scale_upstream, scale_factor, workspace,
+                           workspace_bytes, as_stream(stream));
+  }
+  if (scale_grad)      // exact-fp32 path: the scaling is its own (tiny) launch
+    if (int e = b200ssl_scale_inplace(scale_grad, scale_numel, dtype, scale_upstream, scale_factor, stream)) return e;
   ContrastParams p{};
   p.f0 = feats_s0; p.f1 = feats_s1; p.probs = probs; p.rows = rows; p.D = dim; p.C = classes;
   p.tau = temperature; p.th = contrast_th; p.stats = const_cast<float*>(stats);

@@ -39,7 +39,7 @@ constexpr uint32_t kTileF = kT * 128;         // 16 KB: [128][64] bf16
 constexpr uint32_t kStageBytes = 2 * kTileF;  // F tile + probs hi/lo tile
 constexpr uint32_t kSubZ = kT * 128;          // 16 KB: dZ columns [64*kb, +64)
 constexpr uint32_t kSmemCt = 2 * kTileF + 2 * kStageBytes + 4 * kSubZ;   // 160 KB (dZ is kept as a bf16 hi + lo pair)
-constexpr size_t kSmemCtRequest = kSmemCt + 1024 + 512 + 2 * 4 * kT * sizeof(float);
+constexpr size_t kSmemCtRequest = kSmemCt + 1024 + 512 + 2 * kMaxCl * 4 * kT * sizeof(float);   // + two [8][4][128] exchange areas
 constexpr uint32_t kTmemColsCt = 512;         // S 0..127, Q 128..255, dF accumulator 256..319
 constexpr int kAccLd = 68;                    // floats per row of the staged accumulator (16-byte rows, bank spread)
 
@@ -56,6 +56,8 @@ struct ContrastTcParams {
   const float* loss_u; float lambda_u, lambda_c; float* total_out;
   const float* upstream; float factor; void* g0; void* g1;
   unsigned long long* dbg;
+  // optional piggy-backed task of the backward launch: sgrad[i] *= (*sup) * sfactor  (the stashed focal-CE gradient)
+  __nv_bfloat16* sgrad; long long snumel; const float* sup; float sfactor;
 };
 
 __device__ __forceinline__ float ex2a(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
@@ -83,7 +85,7 @@ struct Smem {
   uint64_t* bars;
   uint32_t* tmem_slot;
   volatile int* abort_flag;
-  float* stat;            // [2 passes][4][128]: per-row partials (value 0/1 x half 0/1)
+  float* stat;            // [2 passes][8 source ranks][4][128]: per-row partials (value 0/1 x half 0/1) pushed by the cluster
 };
 
 __device__ __forceinline__ Smem carve(uint8_t* smem_raw) {
@@ -164,8 +166,8 @@ contrast_tc_fwd_kernel(const __grid_constant__ CUtensorMap tm_f0, const __grid_c
   if (threadIdx.x == 0) B200SSL_STAMP(p.dbg, ctaid, 0);
   const uint32_t tmem = setup(sm, warp, lane, &tm_f0, &tm_f1, &tm_ph);
   if (threadIdx.x == 0) B200SSL_STAMP(p.dbg, ctaid, 1);
-  float* statA = sm.stat;
-  float* statB = sm.stat + 4 * kT;
+  float* statA = sm.stat;                                   // [src rank][4][128]
+  float* statB = sm.stat + kMaxCl * 4 * kT;
 
   // per-thread epilogue state (valid in warps 2..9)
   const int quarter = warp & 3, half = (warp - 2) >> 2;
@@ -174,7 +176,16 @@ contrast_tc_fwd_kernel(const __grid_constant__ CUtensorMap tm_f0, const __grid_c
   const long long gi = (long long)own_tile * kT + r_in;
   float inv_rs = 1.f, inv_qs = 1.f;
 
-  auto epilogue_tile = [&](int pass, long long j0, float& a0, float& a1) {
+  // Positives of the pseudo-label graph are ~1/classes dense: pass B first compacts (s, qm) of the positive
+  // columns into a shared-memory list (static register indices on the read side, conflict-free [slot][thread]
+  // layout), then runs the exp / log / rcp math only over that list.
+  float2* plist = reinterpret_cast<float2*>(sm.z);           // [32 (+1 scratch)][256] float2 <= 66 KB (the dZ buffers are idle in fwd)
+  const int et = threadIdx.x - 64;                          // epilogue thread index 0..255
+  const int rows_i = (int)p.rows, gi_i = (int)gi;
+  auto epilogue_tile = [&](int pass, long long j0ll, float& a0, float& a1) {
+    const int j0 = (int)j0ll;
+    // interior tile: every (row, column) is inside the matrix and off the diagonal -> no per-element checks
+    const bool interior = (own_tile * kT + kT <= rows_i) && (j0 + kT <= rows_i) && (j0 != own_tile * kT);
 #pragma unroll 1
     for (int c2 = 0; c2 < 2; ++c2) {
       const int col0 = half * 64 + c2 * 32;
@@ -182,19 +193,46 @@ contrast_tc_fwd_kernel(const __grid_constant__ CUtensorMap tm_f0, const __grid_c
       tc::tmem_ld_32x32(lane_addr + col0, sv);
       tc::tmem_ld_32x32(lane_addr + kT + col0, qv);
       tc::tmem_ld_wait();
+      if (pass == 0) {
+        if (interior) {
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        const long long gj = j0 + col0 + j;
-        const bool ok = (gi < p.rows) && (gj < p.rows);
-        float q = __uint_as_float(qv[j]);
-        q = (gi == gj) ? 1.f : q;                           // fill_diagonal_(1)   comatch.py:205
-        const float qm = (ok && q >= p.th) ? q : 0.f;       // pos_mask            :206-208
-        if (pass == 0) {
-          a0 += ok ? ex2a(__uint_as_float(sv[j]) * p.scale) : 0.f;               // :200
-          a1 += qm;
-        } else if (qm != 0.f) {
-          const float P = ex2a(__uint_as_float(sv[j]) * p.scale) * inv_rs;        // :201
-          const float qn = qm * inv_qs;                                           // :209
+          for (int j = 0; j < 32; ++j) {
+            const float q = __uint_as_float(qv[j]);
+            a0 += ex2a(__uint_as_float(sv[j]) * p.scale);                         // comatch.py:200
+            a1 += (q >= p.th) ? q : 0.f;                                          // :206-208
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int gj = j0 + col0 + j;
+            const bool ok = (gi_i < rows_i) && (gj < rows_i);
+            float q = __uint_as_float(qv[j]);
+            q = (gi_i == gj) ? 1.f : q;                                           // fill_diagonal_(1)  :205
+            a0 += ok ? ex2a(__uint_as_float(sv[j]) * p.scale) : 0.f;
+            a1 += (ok && q >= p.th) ? q : 0.f;
+          }
+        }
+      } else {
+        int cnt = 0;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const int gj = j0 + col0 + j;
+          float q = __uint_as_float(qv[j]);
+          bool pos;
+          if (interior) {
+            pos = q >= p.th;
+          } else {
+            q = (gi_i == gj) ? 1.f : q;
+            pos = (gi_i < rows_i) && (gj < rows_i) && (q >= p.th);
+          }
+          plist[cnt * 256 + et] = make_float2(__uint_as_float(sv[j]), q);   // branch-free: the slot is simply
+          cnt += pos ? 1 : 0;                                               // re-used when this column is no positive
+        }
+        if (threadIdx.x == 64) B200SSL_STAMP(p.dbg, ctaid, 10 + c2);           // positives of this chunk compacted
+        for (int k = 0; k < cnt; ++k) {
+          const float2 sq = plist[k * 256 + et];
+          const float P = ex2a(sq.x * p.scale) * inv_rs;                          // :201
+          const float qn = sq.y * inv_qs;                                         // :209
           a0 -= lg2a(P + 1e-7f) * 0.6931471805599453f * qn;                       // :212
           a1 += qn * P * rcpa(P + 1e-7f);
         }
@@ -239,8 +277,8 @@ contrast_tc_fwd_kernel(const __grid_constant__ CUtensorMap tm_f0, const __grid_c
     } else {
       if (phase == 1) {                                     // full row statistics from every CTA of the cluster
         float rs = 0.f, qs = 0.f;
-        for (int r = 0; r < CL; ++r) {
-          const float* st = CL > 1 ? cluster.map_shared_rank(statA, r) : statA;
+        for (int r = 0; r < CL; ++r) {                      // pushed by every rank before the cluster sync: local reads
+          const float* st = statA + r * 4 * kT;
           rs += st[0 * kT + r_in] + st[1 * kT + r_in];
           qs += st[2 * kT + r_in] + st[3 * kT + r_in];
         }
@@ -248,6 +286,7 @@ contrast_tc_fwd_kernel(const __grid_constant__ CUtensorMap tm_f0, const __grid_c
         inv_qs = 1.0f / qs;
         if (half == 0 && crank == 0 && gi < p.rows) { p.stats[gi] = rs; p.stats[p.rows + gi] = qs; }
         a0 = a1 = 0.f;
+        if (threadIdx.x == 64) B200SSL_STAMP(p.dbg, ctaid, 9);                // row statistics assembled
         if (T == 1) {                                       // the only S/Q tile of this CTA is still in TMEM
           tc::tcgen05_fence_after();
           epilogue_tile(1, t0 * kT, a0, a1);
@@ -261,9 +300,16 @@ contrast_tc_fwd_kernel(const __grid_constant__ CUtensorMap tm_f0, const __grid_c
         tc::tcgen05_fence_before();
         if (!(T == 1)) tc::mbar_arrive(&sm.bars[CB_SQ_EMPTY]);
       }
-      float* st = phase == 0 ? statA : statB;
-      st[(0 + half) * kT + r_in] = a0;
-      st[(2 + half) * kT + r_in] = a1;
+      // push the per-row partials: pass A to every CTA of the cluster (all need the full row statistics),
+      // pass B only to the CTA that folds this row
+      const int RBx = kT / CL;
+      for (int r = 0; r < CL; ++r) {
+        if (phase == 1 && r != r_in / RBx) continue;
+        float* st = (phase == 0 ? statA : statB) + crank * 4 * kT;
+        if (CL > 1) st = cluster.map_shared_rank(st, r);
+        st[(0 + half) * kT + r_in] = a0;
+        st[(2 + half) * kT + r_in] = a1;
+      }
       if (threadIdx.x == 64) B200SSL_STAMP(p.dbg, ctaid, 3 + 2 * phase);     // pass A (3) / pass B (5) done
     }
     if (CL > 1) cluster.sync(); else __syncthreads();       // partials of this pass visible cluster-wide
@@ -275,8 +321,8 @@ contrast_tc_fwd_kernel(const __grid_constant__ CUtensorMap tm_f0, const __grid_c
   if (threadIdx.x < RB) {
     const int row = crank * RB + threadIdx.x;
     float li = 0.f, rr = 0.f;
-    for (int r = 0; r < CL; ++r) {
-      const float* st = CL > 1 ? cluster.map_shared_rank(statB, r) : statB;
+    for (int r = 0; r < CL; ++r) {                          // rank order, local reads
+      const float* st = statB + r * 4 * kT;
       li += st[0 * kT + row] + st[1 * kT + row];
       rr += st[2 * kT + row] + st[3 * kT + row];
     }
@@ -287,12 +333,12 @@ contrast_tc_fwd_kernel(const __grid_constant__ CUtensorMap tm_f0, const __grid_c
     }
   }
   tc::tcgen05_fence_before();
-  if (CL > 1) cluster.sync(); else __syncthreads();         // nobody leaves while its smem is still being read
+  __syncthreads();                                          // all exchanges were pushes: nothing remote is read after exchange B
   if (warp == 0) {
     tc::tcgen05_fence_after();
     tc::tmem_dealloc(tmem, kTmemColsCt);
   }
-  if (threadIdx.x == 0) B200SSL_STAMP(p.dbg, ctaid, 7);     // rows folded, final cluster sync passed, TMEM freed
+  if (threadIdx.x == 0) B200SSL_STAMP(p.dbg, ctaid, 7);     // rows folded, TMEM freed
   // ---- loss: CTA sum, then last CTA of the grid folds all CTA partials in order ----
   __shared__ float s_w[kCtThreads / 32];
   __shared__ bool s_glast;
@@ -333,6 +379,20 @@ contrast_tc_fwd_kernel(const __grid_constant__ CUtensorMap tm_f0, const __grid_c
 __global__ void __launch_bounds__(kCtThreads, 1)
 contrast_tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_f0, const __grid_constant__ CUtensorMap tm_f1,
                        const __grid_constant__ CUtensorMap tm_ph, const ContrastTcParams p) {
+  if (blockIdx.z == 2) {                                    // whole clusters of this z-slice only scale the stashed gradient
+    const float sc = (p.sup ? *p.sup : 1.f) * p.sfactor;
+    const long long nvec = p.snumel / 8, stride = (long long)gridDim.x * gridDim.y * blockDim.x;
+    for (long long v = (long long)(blockIdx.y * gridDim.x + blockIdx.x) * blockDim.x + threadIdx.x; v < nvec; v += stride) {
+      float f[8];
+      unpack16(*reinterpret_cast<const uint4*>(p.sgrad + v * 8), f, __nv_bfloat16());
+#pragma unroll
+      for (int e = 0; e < 8; ++e) f[e] *= sc;
+      *reinterpret_cast<uint4*>(p.sgrad + v * 8) = pack16(f, __nv_bfloat16());
+    }
+    for (long long i = nvec * 8 + (long long)(blockIdx.y * gridDim.x + blockIdx.x) * blockDim.x + threadIdx.x; i < p.snumel; i += stride)
+      p.sgrad[i] = __float2bfloat16_rn(__bfloat162float(p.sgrad[i]) * sc);
+    return;
+  }
   extern __shared__ uint8_t smem_raw[];
   const Smem sm = carve(smem_raw);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -347,7 +407,8 @@ contrast_tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_f0, const __grid_c
   if (threadIdx.x == 0) B200SSL_STAMP(p.dbg, ctaid, 0);
   const uint32_t tmem = setup(sm, warp, lane, &tm_f0, &tm_f1, &tm_ph);
   if (threadIdx.x == 0) B200SSL_STAMP(p.dbg, ctaid, 1);
-  float* sAcc = reinterpret_cast<float*>(sm.z);             // [128][kAccLd] fp32, after the pipeline has drained
+  float* sGather = sm.stat;                                 // [source rank][RB rows][64] fp32 = 32 KB, written by the peers
+  const float up = (p.upstream ? *p.upstream : 1.f) * p.factor * p.inv_tau;   // fetched early: off the critical tail
 
   if (warp == 0) {
     if (lane == 0) {
@@ -411,17 +472,23 @@ contrast_tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_f0, const __grid_c
     const int r_in = quarter * 32 + lane;
     const uint32_t lane_addr = tmem + ((uint32_t)(quarter * 32) << 16);
     const float inv_rows = 1.0f / (float)p.rows;
-    long long gi = colmode ? 0 : (long long)own_tile * kT + r_in;
-    float inv_rs = 1.f, inv_qs = 1.f, r_i = 0.f;
+    const int rows_i = (int)p.rows;
+    int gi = colmode ? 0 : own_tile * kT + r_in;
+    float inv_rs = 1.f, qscale = 0.f, r_i = 0.f;            // qscale = -1 / (qsum_i * rows)
     auto load_stats = [&]() {
-      inv_rs = inv_qs = 1.f; r_i = 0.f;
-      if (gi < p.rows) { inv_rs = 1.0f / p.stats[gi]; inv_qs = 1.0f / p.stats[p.rows + gi]; r_i = p.stats[2 * p.rows + gi]; }
+      inv_rs = 1.f; qscale = 0.f; r_i = 0.f;
+      if (gi < rows_i) {
+        inv_rs = 1.0f / p.stats[gi];
+        qscale = -inv_rows / p.stats[p.rows + gi];
+        r_i = p.stats[2 * p.rows + gi];
+      }
     };
     if (!colmode) load_stats();
     for (int t = 0; t < T; ++t) {
-      const long long o0 = (t0 + t) * kT;
-      const long long j0 = colmode ? (long long)own_tile * kT : o0;
+      const int o0 = (int)((t0 + t) * kT);
+      const int i0 = colmode ? o0 : own_tile * kT, j0 = colmode ? own_tile * kT : o0;
       if (colmode) { gi = o0 + r_in; load_stats(); }
+      const bool interior = (i0 + kT <= rows_i) && (j0 + kT <= rows_i) && (i0 != j0);
       tc::mbar_wait(&sm.bars[CB_SQ_FULL], t & 1, sm.abort_flag);
       if (t == 0 && threadIdx.x == 64) B200SSL_STAMP(p.dbg, ctaid, 2);       // first S/Q tile ready
       if (t >= 1) tc::mbar_wait(&sm.bars[CB_Z_EMPTY], (t - 1) & 1, sm.abort_flag);
@@ -437,17 +504,18 @@ contrast_tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_f0, const __grid_c
         float dz_even = 0.f;
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
-          const long long gj = j0 + col0 + j;
-          const bool ok = (gi < p.rows) && (gj < p.rows);
           float q = __uint_as_float(qv[j]);
-          q = (gi == gj) ? 1.f : q;
-          const float qm = (ok && q >= p.th) ? q : 0.f;
-          float dz = 0.f;
-          if (ok) {
-            const float P = ex2a(__uint_as_float(sv[j]) * p.scale) * inv_rs;
-            const float G = (qm != 0.f) ? -(qm * inv_qs) * rcpa(P + 1e-7f) * inv_rows : 0.f;
-            dz = P * (G - r_i);
+          bool ok = true;
+          if (!interior) {
+            const int gj = j0 + col0 + j;
+            ok = (gi < rows_i) && (gj < rows_i);
+            q = (gi == gj) ? 1.f : q;
           }
+          // dZ = P (G - r),  G = -(qm / qsum) / (P + 1e-7) / rows   (branch-free: qm = 0 off the graph)
+          const float qm = (q >= p.th) ? q : 0.f;
+          const float P = ex2a(__uint_as_float(sv[j]) * p.scale) * inv_rs;
+          float dz = P * (qm * qscale * rcpa(P + 1e-7f) - r_i);
+          dz = ok ? dz : 0.f;
           if (j & 1) {
             const __nv_bfloat162 h = __floats2bfloat162_rn(dz_even, dz);
             const __nv_bfloat162 l = __floats2bfloat162_rn(dz_even - __low2float(h), dz - __high2float(h));
@@ -475,56 +543,50 @@ contrast_tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_f0, const __grid_c
     tc::mbar_wait(&sm.bars[CB_ACC], 0, sm.abort_flag);       // all MMAs retired: dZ smem is free, accumulator final
     if (threadIdx.x == 64) B200SSL_STAMP(p.dbg, ctaid, 4);   // gradient accumulator complete
     tc::tcgen05_fence_after();
-    {                                                        // accumulator -> fp32 tile in smem: thread (row, half) takes 32 columns
+    {   // accumulator -> the CTA that folds this row: thread (row, half) pushes 32 fp32 columns into the owner's
+        // gather buffer [source rank][local row][kAccLd] through distributed shared memory
       uint32_t av[32];
       tc::tmem_ld_32x32(lane_addr + 2 * kT + half * 32, av);
       tc::tmem_ld_wait();
-      float4* dst = reinterpret_cast<float4*>(sAcc + r_in * kAccLd + half * 32);
+      // (the gather buffer must not alias the pipeline buffers: a peer may push while this CTA still runs MMAs)
+      const int RBx = kT / CL, owner = r_in / RBx, lrow = r_in - owner * RBx;
+      float* base = sGather + ((size_t)crank * RBx + lrow) * 64;
+      float4* dst = reinterpret_cast<float4*>(CL > 1 ? cluster.map_shared_rank(base, owner) : base);
 #pragma unroll
-      for (int q4 = 0; q4 < 8; ++q4)
-        dst[q4] = make_float4(__uint_as_float(av[4 * q4]), __uint_as_float(av[4 * q4 + 1]), __uint_as_float(av[4 * q4 + 2]),
-                              __uint_as_float(av[4 * q4 + 3]));
+      for (int q4 = 0; q4 < 8; ++q4)                        // 16-byte chunk index XOR (row & 7): bank spread at the destination
+        dst[(half * 8 + q4) ^ (lrow & 7)] = make_float4(__uint_as_float(av[4 * q4]), __uint_as_float(av[4 * q4 + 1]),
+                                                        __uint_as_float(av[4 * q4 + 2]), __uint_as_float(av[4 * q4 + 3]));
     }
     tc::tcgen05_fence_before();
   }
-  if (CL > 1) cluster.sync(); else __syncthreads();
-  if (threadIdx.x == 0) B200SSL_STAMP(p.dbg, ctaid, 5);     // accumulators staged, cluster sync passed
+  if (CL > 1) cluster.sync(); else __syncthreads();          // every slice has landed; afterwards only local reads
+  if (threadIdx.x == 0) B200SSL_STAMP(p.dbg, ctaid, 5);
   if (warp == 0) {
     tc::tcgen05_fence_after();
     tc::tmem_dealloc(tmem, kTmemColsCt);
   }
-  // ---- cluster fold: rank c reduces rows [c*RB, (c+1)*RB) of the [128 x 64] accumulators in rank order ----
+  // ---- fold: this CTA owns rows [crank*RB, (crank+1)*RB) and adds the CL pushed slices in rank order ----
   const int RB = kT / CL;
-  const float up = (p.upstream ? *p.upstream : 1.f) * p.factor * p.inv_tau;
   __nv_bfloat16* out = static_cast<__nv_bfloat16*>(colmode ? p.g1 : p.g0);
-  const float* peer[kMaxCl];
-#pragma unroll
-  for (int r = 0; r < kMaxCl; ++r) peer[r] = (CL > 1 && r < CL) ? cluster.map_shared_rank(sAcc, r) : sAcc;
   for (int idx = threadIdx.x; idx < RB * 8; idx += blockDim.x) {     // 8 x (8 bf16 = 16 B) per row
     const int rr = idx >> 3, c8 = idx & 7;
-    const int row = crank * RB + rr;
     float f[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    float4 lo[kMaxCl], hi[kMaxCl];
 #pragma unroll
     for (int r = 0; r < kMaxCl; ++r)
       if (r < CL) {
-        lo[r] = *reinterpret_cast<const float4*>(peer[r] + row * kAccLd + 8 * c8);
-        hi[r] = *reinterpret_cast<const float4*>(peer[r] + row * kAccLd + 8 * c8 + 4);
+        const float4* row = reinterpret_cast<const float4*>(sGather + ((size_t)r * RB + rr) * 64);
+        const float4 lo = row[(2 * c8) ^ (rr & 7)];
+        const float4 hi = row[(2 * c8 + 1) ^ (rr & 7)];
+        f[0] += lo.x; f[1] += lo.y; f[2] += lo.z; f[3] += lo.w;
+        f[4] += hi.x; f[5] += hi.y; f[6] += hi.z; f[7] += hi.w;
       }
-#pragma unroll
-    for (int r = 0; r < kMaxCl; ++r)
-      if (r < CL) {
-        f[0] += lo[r].x; f[1] += lo[r].y; f[2] += lo[r].z; f[3] += lo[r].w;
-        f[4] += hi[r].x; f[5] += hi[r].y; f[6] += hi[r].z; f[7] += hi[r].w;
-      }
-    const long long grow = (long long)own_tile * kT + row;
+    const long long grow = (long long)own_tile * kT + crank * RB + rr;
     if (grow < p.rows) {
 #pragma unroll
       for (int e = 0; e < 8; ++e) f[e] *= up;
       *reinterpret_cast<uint4*>(out + grow * 64 + 8 * c8) = pack16(f, __nv_bfloat16());
     }
   }
-  if (CL > 1) cluster.sync();                                // nobody leaves while its smem is still being read
   if (threadIdx.x == 0) B200SSL_STAMP(p.dbg, ctaid, 6);     // fold done
 }
 
@@ -600,6 +662,7 @@ int contrast_fwd_tc(const void* f0, const void* f1, const void* probs_hl, long l
 
 int contrast_bwd_tc(const void* f0, const void* f1, const void* probs_hl, const float* stats, long long rows, int classes,
                     float temperature, float contrast_th, const float* upstream, float factor, void* g0, void* g1,
+                    void* scale_grad, long long scale_numel, const float* scale_up, float scale_factor,
                     void* workspace, size_t workspace_bytes, cudaStream_t stream) {
   const char* fn = "b200ssl_contrast_bwd[tcgen05]";
   (void)workspace; (void)workspace_bytes;
@@ -608,6 +671,7 @@ int contrast_bwd_tc(const void* f0, const void* f1, const void* probs_hl, const 
   p.inv_tau = 1.0f / temperature; p.th = contrast_th; p.stats = const_cast<float*>(stats);
   p.upstream = upstream; p.factor = factor; p.g0 = g0; p.g1 = g1;
   p.cluster = ct_cluster(rows); p.dbg = debug_timing_buffer();
+  p.sgrad = static_cast<__nv_bfloat16*>(scale_grad); p.snumel = scale_numel; p.sup = scale_up; p.sfactor = scale_factor;
   CUtensorMap m[3];
   if (int e = ct_maps(m, f0, f1, probs_hl, rows)) return e;
   static bool attr = false;
@@ -615,8 +679,9 @@ int contrast_bwd_tc(const void* f0, const void* f1, const void* probs_hl, const 
     if (int e = ct_attr(fn, contrast_tc_bwd_kernel)) return e;
     attr = true;
   }
-  static_assert(kT * kAccLd * sizeof(float) <= 4 * kSubZ, "staged accumulator must fit in the dZ buffers");
-  return ct_launch(fn, contrast_tc_bwd_kernel, dim3((unsigned)((rows + kT - 1) / kT), (unsigned)p.cluster, 2), p.cluster, stream, m, p);
+  static_assert(kT * 64 * sizeof(float) <= 2 * kMaxCl * 4 * kT * sizeof(float), "gather buffer must fit in the exchange area");
+  return ct_launch(fn, contrast_tc_bwd_kernel, dim3((unsigned)((rows + kT - 1) / kT), (unsigned)p.cluster, scale_grad ? 3 : 2), p.cluster,
+                   stream, m, p);
 }
 
 }  // namespace b200ssl

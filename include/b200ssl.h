@@ -226,7 +226,9 @@ B200SSL_API int b200ssl_bank_enqueue(void* queue_feats, void* queue_probs, void*
  * fwd also stores the row statistics (rowsum, qsum, r) into
  * stats f32[3*rows]; bwd consumes them and writes grad_f0 / grad_f1 scaled by
  * (*upstream) * factor (upstream: device scalar from autograd, NULL => 1; factor:
- * host constant such as LAMBDA_C of comatch.py:222).
+ * host constant such as LAMBDA_C of comatch.py:222).  Optional piggy-back (scale_grad != NULL):
+ * the same launch also performs scale_grad[i] *= (*scale_upstream) * scale_factor, i.e. the
+ * b200ssl_scale_inplace of the stashed focal-CE gradient (saves one launch per backward).
  */
 B200SSL_API int b200ssl_contrast_fwd(const void* feats_s0, const void* feats_s1, const float* probs, const void* probs_hl,
                          int64_t rows,
@@ -236,6 +238,7 @@ B200SSL_API int b200ssl_contrast_fwd(const void* feats_s0, const void* feats_s1,
 B200SSL_API int b200ssl_contrast_bwd(const void* feats_s0, const void* feats_s1, const float* probs, const void* probs_hl,
                          const float* stats, int64_t rows, int32_t dim, int32_t classes, int32_t dtype, float temperature,
                          float contrast_th, const float* upstream, float factor, void* grad_f0, void* grad_f1,
+                         void* scale_grad, int64_t scale_numel, const float* scale_upstream, float scale_factor,
                          void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---------------------------------------------------------------- K8 ----

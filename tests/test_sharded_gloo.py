@@ -86,10 +86,12 @@ def _make_head_class():
             scalars[3] = lambda_u * scalars[0] + lambda_c * lc
             return torch.zeros(3, fs0.shape[0]), lc
 
-        def _k_contrast_bwd(self, f0, f1, probs, stats, g_c, factor=1.0, probs_hl=None):
+        def _k_contrast_bwd(self, f0, f1, probs, stats, g_c, factor=1.0, probs_hl=None, scale=None):
             with torch.enable_grad():
                 a, b = f0.clone().requires_grad_(True), f1.clone().requires_grad_(True)
                 O.comatch_contrast(a, b, probs, self.temperature, self.contrast_th).backward()
+            if scale is not None:
+                scale[0].mul_(scale[1] * scale[2])
             return a.grad * g_c * factor, b.grad * g_c * factor
 
         def _k_scale(self, grad, g, factor=1.0):

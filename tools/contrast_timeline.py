@@ -36,7 +36,8 @@ def run(fn, names):
             print(f"    {nm:34s} {col.min():8d} {int(np.median(col)):8d} {col.max():8d}  (n={ok.sum()})")
 print(f"contrast fwd rows={rows}")
 run(lambda: head._k_contrast_fwd(f0, f1, dp, scal, probs_hl=dhl),
-    ["setup", "first S/Q ready", "pass A done", "after exchange A", "pass B done", "after exchange B", "rows folded+sync+dealloc", "grid ticket"])
+    ["setup", "first S/Q ready", "pass A done", "after exchange A", "pass B done", "after exchange B", "rows folded+sync+dealloc", "grid ticket",
+     "B: row stats assembled", "B: chunk 0 compacted", "B: chunk 1 compacted"])
 print(f"contrast bwd rows={rows}")
 run(lambda: head._k_contrast_bwd(f0, f1, dp, stats, one, probs_hl=dhl),
     ["setup", "first S/Q ready", "last dZ written", "acc complete", "staged + cluster sync", "fold done"])
