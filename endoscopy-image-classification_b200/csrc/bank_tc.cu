@@ -46,6 +46,13 @@ static EncodeTiledFn encode_fn() {
 
 int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t row_stride_bytes,
                       uint32_t box_rows, uint32_t box_cols) {
+  // The driver API needs a context that is current in the CALLING thread.  autograd runs backward on its
+  // own worker thread, where our launch can be the first CUDA call: bind the primary context once per thread.
+  static thread_local bool ctx_bound = false;
+  if (!ctx_bound) {
+    cudaFree(nullptr);
+    ctx_bound = true;
+  }
   EncodeTiledFn fn = encode_fn();
   if (!fn) return fail(B200SSL_E_ARG, "cuTensorMapEncodeTiled is not available from the driver");
   if ((reinterpret_cast<uintptr_t>(base) & 15u) || (row_stride_bytes & 15u))

@@ -551,3 +551,25 @@ def test_contrast_tcgen05_bf16(pkg, rows):
     A = torch.exp(f0b.double() @ f1b.double().t() / 0.2)
     assert rel_err(stats[0], A.sum(1)) < 1e-3
     assert rel_err(g0.float(), 3.0 * f0.grad) < BF16_TOL and rel_err(g1.float(), 3.0 * f1.grad) < BF16_TOL
+
+
+def test_tensor_core_path_from_a_fresh_thread(pkg):
+    """autograd runs backward on its own worker thread, where a launch of ours can be the first CUDA call: the
+    tensor-map encode (driver API) must bind the context itself (regression: CUresult 201 in bench.py)."""
+    import threading
+    head = pkg["head"].CoMatchHead(C, 64, 256, 0.9, enqueue_mode="always", dtype=torch.bfloat16)
+    f = torch.nn.functional.normalize(torch.randn(64, 64), dim=1).to(torch.bfloat16).cuda()
+    err = []
+
+    def work():
+        try:
+            with torch.cuda.device(0):
+                rowsum, _ = head._k_smooth(f)
+                torch.cuda.synchronize()
+                assert bool(torch.isfinite(rowsum).all())
+        except Exception as e:  # pragma: no cover
+            err.append(e)
+    t = threading.Thread(target=work)
+    t.start()
+    t.join()
+    assert not err, err
