@@ -128,7 +128,7 @@ bank_smooth_tc_kernel(const __grid_constant__ CUtensorMap tm_f, const __grid_con
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int row_tile = blockIdx.x, split = blockIdx.y;
   const int cta = blockIdx.y * gridDim.x + blockIdx.x;
-  if (threadIdx.x == 0) B200SSL_STAMP(p.dbg, cta, 0);
+  pdl_launch_dependents();                                 // the next kernel may start its prologue
   const long long nktiles = (p.bank_rows + kBN - 1) / kBN;
   const long long kt0 = nktiles * split / p.nsplit;                // balanced: every split owns >= 1 key tile
   const int T = (int)(nktiles * (split + 1) / p.nsplit - kt0);
@@ -157,6 +157,7 @@ bank_smooth_tc_kernel(const __grid_constant__ CUtensorMap tm_f, const __grid_con
   __syncthreads();
   tc::tcgen05_fence_after();
   const uint32_t tmem = *tmem_slot;
+  pdl_wait();                                              // previous kernel complete: global memory may be touched now
   if (threadIdx.x == 0) B200SSL_STAMP(p.dbg, cta, 1);     // setup (barrier init, TMEM alloc) done
 
   if (warp == 0) {
@@ -393,19 +394,8 @@ int bank_smooth_tc(const void* feats, const void* queue_feats, const void* queue
   }
   static_assert(kSmemData + 1024 + 256 <= kSmemRequest, "shared memory budget");
   static_assert(kBM * kRedLd * sizeof(float) <= kTileP, "reduction tile must fit in the P buffer");
-  cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3((unsigned)row_tiles, (unsigned)p.nsplit, 1);
-  cfg.blockDim = dim3(kTcThreads, 1, 1);
-  cfg.dynamicSmemBytes = kSmemRequest;
-  cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = 1;
-  attr[0].val.clusterDim.y = (unsigned)p.cluster;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, bank_smooth_tc_kernel, tm_f, tm_qf, tm_qpt, p);
+  cudaError_t e = launch_pdl(PDL_SMOOTH, bank_smooth_tc_kernel, dim3((unsigned)row_tiles, (unsigned)p.nsplit, 1), dim3(kTcThreads, 1, 1),
+                             kSmemRequest, stream, dim3(1, (unsigned)p.cluster, 1), tm_f, tm_qf, tm_qpt, p);
   if (e != cudaSuccess) return fail((int)e, "%s: cudaLaunchKernelEx: %s", fn, cudaGetErrorString(e));
   return check_launch(fn);
 }

@@ -4,6 +4,7 @@
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "b200ssl.h"
 
@@ -41,6 +42,45 @@ int contrast_nsplit(long long rows, int modes, int* tiles_per_split);
 size_t contrast_workspace_floats(long long rows, int dim);
 size_t smooth_tc_workspace_floats(long long rows, long long bank_rows, int classes);
 size_t contrast_tc_workspace_floats(long long rows);
+
+// ---- programmatic dependent launch (PDL) -------------------------------------
+// Every hot kernel (a) lets the next kernel of the stream be scheduled as soon as it has started itself and
+// (b) waits for the complete previous kernel (incl. its memory flush) before it touches global memory.  The
+// launch latency, barrier init, TMEM allocation and descriptor prefetch of kernel N+1 then overlap the tail
+// of kernel N -- at the reference's sizes the head is a chain of ~5 launch-latency-bound kernels per step.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+// cudaLaunchKernelEx with the PDL attribute and an optional thread-block cluster.
+enum { PDL_SMOOTH = 0, PDL_ROWS = 1, PDL_CONTRAST_FWD = 2, PDL_CONTRAST_BWD = 3, PDL_EMA = 4 };
+constexpr int kPdlDefaultMask = 15;   // the four head kernels; measured: the HBM-bound EMA launch loses 4 us when it is scheduled early
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(int tag, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, dim3 cluster,
+                              Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[2];
+  int n = 0;
+  static const int pdl_mask = getenv("B200SSL_PDL_MASK") ? atoi(getenv("B200SSL_PDL_MASK")) : kPdlDefaultMask;   // A/B aid
+  if ((pdl_mask >> tag) & 1) {
+    attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[n].val.programmaticStreamSerializationAllowed = 1;
+    ++n;
+  }
+  if (cluster.x * cluster.y * cluster.z > 1) {
+    attr[n].id = cudaLaunchAttributeClusterDimension;
+    attr[n].val.clusterDim.x = cluster.x;
+    attr[n].val.clusterDim.y = cluster.y;
+    attr[n].val.clusterDim.z = cluster.z;
+    ++n;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = n;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
 
 // ---- dtype helpers ---------------------------------------------------------
 template <typename T> __device__ __forceinline__ float to_f32(T v);

@@ -127,6 +127,7 @@ __device__ __forceinline__ uint32_t setup(const Smem& sm, int warp, int lane, co
   tc::tcgen05_fence_before();
   __syncthreads();
   tc::tcgen05_fence_after();
+  pdl_wait();                                               // previous kernel complete: global memory may be touched now
   return *sm.tmem_slot;
 }
 
@@ -163,8 +164,9 @@ contrast_tc_fwd_kernel(const __grid_constant__ CUtensorMap tm_f0, const __grid_c
   const int T = (int)(ntiles * (crank + 1) / CL - t0);      // >= 1 (CL <= ntiles)
   const int U = (T == 1) ? 1 : 2 * T;                       // tile visits: pass A, then pass B recomputes unless T == 1
   const int ctaid = blockIdx.y * gridDim.x + blockIdx.x;
-  if (threadIdx.x == 0) B200SSL_STAMP(p.dbg, ctaid, 0);
+  pdl_launch_dependents();
   const uint32_t tmem = setup(sm, warp, lane, &tm_f0, &tm_f1, &tm_ph);
+  if (threadIdx.x == 0) B200SSL_STAMP(p.dbg, ctaid, 0);
   if (threadIdx.x == 0) B200SSL_STAMP(p.dbg, ctaid, 1);
   float* statA = sm.stat;                                   // [src rank][4][128]
   float* statB = sm.stat + kMaxCl * 4 * kT;
@@ -379,7 +381,9 @@ contrast_tc_fwd_kernel(const __grid_constant__ CUtensorMap tm_f0, const __grid_c
 __global__ void __launch_bounds__(kCtThreads, 1)
 contrast_tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_f0, const __grid_constant__ CUtensorMap tm_f1,
                        const __grid_constant__ CUtensorMap tm_ph, const ContrastTcParams p) {
+  pdl_launch_dependents();
   if (blockIdx.z == 2) {                                    // whole clusters of this z-slice only scale the stashed gradient
+    pdl_wait();
     const float sc = (p.sup ? *p.sup : 1.f) * p.sfactor;
     const long long nvec = p.snumel / 8, stride = (long long)gridDim.x * gridDim.y * blockDim.x;
     for (long long v = (long long)(blockIdx.y * gridDim.x + blockIdx.x) * blockDim.x + threadIdx.x; v < nvec; v += stride) {
@@ -404,8 +408,8 @@ contrast_tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_f0, const __grid_c
   const long long t0 = ntiles * crank / CL;
   const int T = (int)(ntiles * (crank + 1) / CL - t0);
   const int ctaid = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
-  if (threadIdx.x == 0) B200SSL_STAMP(p.dbg, ctaid, 0);
   const uint32_t tmem = setup(sm, warp, lane, &tm_f0, &tm_f1, &tm_ph);
+  if (threadIdx.x == 0) B200SSL_STAMP(p.dbg, ctaid, 0);
   if (threadIdx.x == 0) B200SSL_STAMP(p.dbg, ctaid, 1);
   float* sGather = sm.stat;                                 // [source rank][RB rows][64] fp32 = 32 KB, written by the peers
   const float up = (p.upstream ? *p.upstream : 1.f) * p.factor * p.inv_tau;   // fetched early: off the critical tail
@@ -618,21 +622,9 @@ static int ct_maps(CUtensorMap* m, const void* f0, const void* f1, const void* p
 }
 
 template <typename K>
-static int ct_launch(const char* fn, K kernel, dim3 grid, int cluster, cudaStream_t stream, const CUtensorMap* m,
+static int ct_launch(const char* fn, int tag, K kernel, dim3 grid, int cluster, cudaStream_t stream, const CUtensorMap* m,
                      const ContrastTcParams& p) {
-  cudaLaunchConfig_t cfg{};
-  cfg.gridDim = grid;
-  cfg.blockDim = dim3(kCtThreads, 1, 1);
-  cfg.dynamicSmemBytes = kSmemCtRequest;
-  cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = 1;
-  attr[0].val.clusterDim.y = (unsigned)cluster;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, m[0], m[1], m[2], p);
+  cudaError_t e = launch_pdl(tag, kernel, grid, dim3(kCtThreads, 1, 1), kSmemCtRequest, stream, dim3(1, (unsigned)cluster, 1), m[0], m[1], m[2], p);
   if (e != cudaSuccess) return fail((int)e, "%s: cudaLaunchKernelEx: %s", fn, cudaGetErrorString(e));
   return check_launch(fn);
 }
@@ -657,7 +649,7 @@ int contrast_fwd_tc(const void* f0, const void* f1, const void* probs_hl, long l
     if (int e = ct_attr(fn, contrast_tc_fwd_kernel)) return e;
     attr = true;
   }
-  return ct_launch(fn, contrast_tc_fwd_kernel, dim3((unsigned)((rows + kT - 1) / kT), (unsigned)p.cluster, 1), p.cluster, stream, m, p);
+  return ct_launch(fn, PDL_CONTRAST_FWD, contrast_tc_fwd_kernel, dim3((unsigned)((rows + kT - 1) / kT), (unsigned)p.cluster, 1), p.cluster, stream, m, p);
 }
 
 int contrast_bwd_tc(const void* f0, const void* f1, const void* probs_hl, const float* stats, long long rows, int classes,
@@ -680,7 +672,7 @@ int contrast_bwd_tc(const void* f0, const void* f1, const void* probs_hl, const 
     attr = true;
   }
   static_assert(kT * 64 * sizeof(float) <= 2 * kMaxCl * 4 * kT * sizeof(float), "gather buffer must fit in the exchange area");
-  return ct_launch(fn, contrast_tc_bwd_kernel, dim3((unsigned)((rows + kT - 1) / kT), (unsigned)p.cluster, scale_grad ? 3 : 2), p.cluster,
+  return ct_launch(fn, PDL_CONTRAST_BWD, contrast_tc_bwd_kernel, dim3((unsigned)((rows + kT - 1) / kT), (unsigned)p.cluster, scale_grad ? 3 : 2), p.cluster,
                    stream, m, p);
 }
 

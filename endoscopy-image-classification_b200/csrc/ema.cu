@@ -112,6 +112,8 @@ template <typename T, int DT>
 __global__ void __launch_bounds__(kEmaThreads, 4) ema_multi_tensor_kernel(const b200ssl_ema_block* __restrict__ blocks,
                                                                           int n_blocks, float d, float o, int mode,
                                                                           int do_ints) {
+  pdl_launch_dependents();
+  pdl_wait();                                               // the weights may still be written by the previous kernel
   for (int b = blockIdx.x; b < n_blocks; b += gridDim.x) {
     const uint4 lo = ldg128(&blocks[b]);
     const uint4 hi = ldg128(reinterpret_cast<const char*>(&blocks[b]) + 16);
@@ -145,18 +147,23 @@ extern "C" int b200ssl_ema_multi_tensor(const b200ssl_ema_block* blocks, int32_t
   const int max_grid = kNumSMs * 4;  // 4 resident CTAs of 256 threads per SM
   const int grid = n_blocks < max_grid ? n_blocks : max_grid;
   cudaStream_t st = as_stream(stream);
+  cudaError_t e = cudaSuccess;
   switch (float_dtype) {
     case B200SSL_F32:
-      ema_multi_tensor_kernel<float, B200SSL_F32><<<grid, kEmaThreads, 0, st>>>(blocks, n_blocks, decay, one_minus_decay, mode, do_ints);
+      e = launch_pdl(PDL_EMA, ema_multi_tensor_kernel<float, B200SSL_F32>, dim3(grid), dim3(kEmaThreads), 0, st, dim3(1, 1, 1), blocks, n_blocks,
+                     decay, one_minus_decay, mode, do_ints);
       break;
     case B200SSL_BF16:
-      ema_multi_tensor_kernel<__nv_bfloat16, B200SSL_BF16><<<grid, kEmaThreads, 0, st>>>(blocks, n_blocks, decay, one_minus_decay, mode, do_ints);
+      e = launch_pdl(PDL_EMA, ema_multi_tensor_kernel<__nv_bfloat16, B200SSL_BF16>, dim3(grid), dim3(kEmaThreads), 0, st, dim3(1, 1, 1), blocks,
+                     n_blocks, decay, one_minus_decay, mode, do_ints);
       break;
     case B200SSL_F16:
-      ema_multi_tensor_kernel<__half, B200SSL_F16><<<grid, kEmaThreads, 0, st>>>(blocks, n_blocks, decay, one_minus_decay, mode, do_ints);
+      e = launch_pdl(PDL_EMA, ema_multi_tensor_kernel<__half, B200SSL_F16>, dim3(grid), dim3(kEmaThreads), 0, st, dim3(1, 1, 1), blocks, n_blocks,
+                     decay, one_minus_decay, mode, do_ints);
       break;
     default:
       return fail(B200SSL_E_DTYPE, "%s: float_dtype %d (want F32, BF16 or F16)", fn, float_dtype);
   }
+  if (e != cudaSuccess) return fail((int)e, "%s: cudaLaunchKernelEx: %s", fn, cudaGetErrorString(e));
   return check_launch(fn);
 }

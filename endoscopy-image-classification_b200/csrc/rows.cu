@@ -587,6 +587,8 @@ __global__ void __launch_bounds__(kFusedThreads) comatch_rows_fused_kernel(const
   const bool single = (r_hi - r_lo) <= ROWS;                 // all rows of this CTA fit one pass: tiles are loaded once
   const bool smooth = f.rowsum != nullptr && f.numer != nullptr;
   const float inv_rows = 1.0f / (float)f.rows;
+  pdl_launch_dependents();
+  pdl_wait();                                                // previous kernel complete: global memory may be touched now
   const long long ptr = p.qf ? *reinterpret_cast<volatile long long*>(p.ptr_state) : 0;
   if (tid == 0) B200SSL_STAMP(p.dbg, crank, 0);
 
@@ -982,21 +984,13 @@ extern "C" int b200ssl_comatch_rows_fused(const void* logits_u_w, const void* lo
   p.rows_per_cta = (((rows + clp - 1) / clp) + 7) & ~7LL;          // multiples of 8 rows keep the tiles 16-byte aligned
   const size_t smem = ((size_t)4 * kFusedRows * classes + kFusedMaxCluster * 32 + 32 + kFusedMaxCluster * 2) * sizeof(float) +
                       (size_t)kFusedRows * 64 * sizeof(__nv_bfloat16) + 16;
-  cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3((unsigned)clp, 1, 1);
-  cfg.blockDim = dim3(kFusedThreads, 1, 1);
-  cfg.dynamicSmemBytes = smem;
-  cfg.stream = as_stream(stream);
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = (unsigned)clp;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
   cudaError_t e;
-  if (dtype == B200SSL_F32) e = cudaLaunchKernelEx(&cfg, comatch_rows_fused_kernel<float>, p);
-  else e = cudaLaunchKernelEx(&cfg, comatch_rows_fused_kernel<__nv_bfloat16>, p);
+  if (dtype == B200SSL_F32)
+    e = launch_pdl(PDL_ROWS, comatch_rows_fused_kernel<float>, dim3((unsigned)clp, 1, 1), dim3(kFusedThreads, 1, 1), smem, as_stream(stream),
+                   dim3((unsigned)clp, 1, 1), p);
+  else
+    e = launch_pdl(PDL_ROWS, comatch_rows_fused_kernel<__nv_bfloat16>, dim3((unsigned)clp, 1, 1), dim3(kFusedThreads, 1, 1), smem,
+                   as_stream(stream), dim3((unsigned)clp, 1, 1), p);
   if (e != cudaSuccess) return fail((int)e, "%s: cudaLaunchKernelEx: %s", fn, cudaGetErrorString(e));
   return check_launch(fn);
 }
