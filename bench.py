@@ -216,7 +216,8 @@ def run_b200(args, wl, rank, world, local_rank):
 
     if wl["kind"] == "comatch":
         model = S.modelwemb_like(wl["arch"], C, D).to(dev)
-        head = CoMatchHead(C, D, wl["K"], wl["thr"], enqueue_mode="always", device=dev, dtype=dtype, process_group=pg)
+        head = CoMatchHead(C, D, wl["K"], wl["thr"], enqueue_mode="always", device=dev, dtype=dtype, process_group=pg,
+                           exchange=args.exchange)
         protos = S.rownorm(torch.randn(C, D, generator=torch.Generator().manual_seed(99)))
         host = [S.comatch_step_inputs(g, B, MU, D, C, protos, dtype) for _ in range(4)]
         keys = ["logits_u_w", "logits_u_s0", "feats_u_w", "feats_u_s0", "feats_u_s1", "feats_x", "targets_x"]
@@ -232,7 +233,11 @@ def run_b200(args, wl, rank, world, local_rank):
     gdev = torch.Generator(device=dev).manual_seed(5)
     S.perturb_(model, gdev)                    # m != e, like after an optimizer step
     grad_keys = ("logits_u_s0", "feats_u_s0", "feats_u_s1") if wl["kind"] == "comatch" else ("logits_u_s",)
-    launches_per_step = (5 if wl["kind"] == "comatch" else 3)   # smooth, rows (DA+finalize+enqueue), contrast fwd, contrast bwd (+scale), ema
+    # N=1: smooth, rows (DA+finalize+enqueue), contrast fwd, contrast bwd (+scale), ema.  Sharded bank: + enqueue and,
+    # with peer-memory exchanges, the three exchange launches (all ours); NCCL's kernels are not counted.
+    launches_per_step = (5 if wl["kind"] == "comatch" else 3)
+    if world > 1 and head is not None:
+        launches_per_step += 1 + (3 if head.exchange == "peer" else 0)
     one = torch.ones((), dtype=torch.float32, device=dev)
 
     def step(batch):
@@ -354,6 +359,9 @@ def run_b200(args, wl, rank, world, local_rank):
                 "scaling": "weak", "vs_baseline": None, "dtype": wl["dtype"], "data": "synthetic",
                 "config": {"workload": wl["desc"], "global_batch_unlabeled": world * Bu, "per_gpu_unlabeled": Bu,
                            "bank_rows_global": wl["K"], "bank_sharded_over": world, "parallelism": f"dp{world}",
+                           "bank_exchange": (None if world == 1 or head is None else
+                                             "own kernels over NVLink peer memory (csrc/peer.cu): all-gather, reduce-scatter, "
+                                             "all-gather per step" if head.exchange == "peer" else "NCCL collectives"),
                            "ema_state": {"entries": plan.n_entries, "unique_storages": plan.n_unique,
                                          "unique_elems": plan.unique_elems, "blocks": plan.n_blocks},
                            "execution": "whole step (head fwd+bwd + EMA) captured once in a CUDA graph and replayed; "
@@ -373,6 +381,10 @@ def run_b200(args, wl, rank, world, local_rank):
             line["cpu_baseline"] = cpu
         print(json.dumps(line), flush=True)
     if world > 1:
+        if head is not None:
+            n_to = head.peer_timeouts()
+            if n_to:
+                raise RuntimeError(f"rank {rank}: {n_to} peer-memory waits timed out; the numbers above are invalid")
         # captured graphs hold NCCL work: they must be released before the communicator is torn down
         # (destroy_process_group() blocks forever otherwise, seen on 2xB200 with NCCL 2.28.9)
         import gc
@@ -380,6 +392,8 @@ def run_b200(args, wl, rank, world, local_rank):
         del graphed
         gc.collect()
         torch.cuda.synchronize(dev)
+        if head is not None:
+            head.close()
         dist.barrier()
         dist.destroy_process_group()
 
@@ -392,6 +406,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--exchange", default="auto", choices=["auto", "peer", "collective"],
+                    help="row exchanges of the sharded bank at N>1: own NVLink peer-memory kernels (default) or NCCL")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     rank = int(os.environ.get("RANK", "0"))

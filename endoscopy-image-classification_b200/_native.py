@@ -60,6 +60,14 @@ SIGNATURES = {
     "b200ssl_contrast_bwd": (_i32, [_vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _f32, _f32, _vp, _f32, _vp, _vp,
                                     _vp, _i64, _vp, _f32, _vp, _sz, _vp]),
     "b200ssl_ema_multi_tensor": (_i32, [_vp, _i32, _i32, _i32, _f32, _f32, _i32, _vp]),
+    "b200ssl_peer_control_bytes": (_sz, []),
+    "b200ssl_peer_alloc": (_i32, [_sz, _vp, _vp]),
+    "b200ssl_peer_open": (_i32, [_vp, _vp]),
+    "b200ssl_peer_close": (_i32, [_vp]),
+    "b200ssl_peer_free": (_i32, [_vp]),
+    "b200ssl_peer_timeouts": (_i32, [_vp, _vp]),
+    "b200ssl_peer_all_gather": (_i32, [_vp, _sz, _vp, _sz, _vp, _vp, _sz, _sz, _i32, _i32, _i32, _vp]),
+    "b200ssl_peer_reduce_scatter_f32": (_i32, [_vp, _vp, _i64, _vp, _sz, _sz, _i32, _i32, _i32, _vp]),
 }
 
 _lib = None

@@ -105,9 +105,11 @@ class CoMatchHead:
     def __init__(self, num_classes: int, low_dim: int, queue_size: int, thr: float, *, alpha: float = 0.9,
                  temperature: float = 0.2, contrast_th: float = 0.8, gamma: float = 2.0, da_window: int = 32,
                  enqueue_mode: str = "reference", smoothing: bool = True, device="cuda",
-                 dtype: torch.dtype = torch.float32, process_group=None):
+                 dtype: torch.dtype = torch.float32, process_group=None, exchange: str = "auto"):
         if enqueue_mode not in ("reference", "always"):
             raise ValueError(enqueue_mode)
+        if exchange not in ("auto", "peer", "collective"):
+            raise ValueError(exchange)
         self.num_classes, self.low_dim, self.queue_size = int(num_classes), int(low_dim), int(queue_size)
         self.thr, self.alpha, self.temperature = float(thr), float(alpha), float(temperature)
         self.contrast_th, self.gamma, self.da_window = float(contrast_th), float(gamma), int(da_window)
@@ -120,6 +122,10 @@ class CoMatchHead:
             import torch.distributed as dist
             world, rank = dist.get_world_size(process_group), dist.get_rank(process_group)
         self.geom = ShardGeometry(self.queue_size, world, rank)
+        # row exchanges of the sharded bank: 'peer' = own kernels over NVLink peer memory (peer.py, one node),
+        # 'collective' = torch.distributed collectives (NCCL; gloo in the CPU tests); 'auto' = peer on CUDA
+        self.exchange = ("peer" if self.device.type == "cuda" else "collective") if exchange == "auto" else exchange
+        self._arena = None
         self._alloc_bank(dtype)
         # write pointer: device-resident {ptr, ticket} (graph-replay safe) + host mirror
         self.ptr_state = torch.zeros(2, dtype=torch.int64, device=self.device)
@@ -251,11 +257,11 @@ class CoMatchHead:
             # (3) all-gather of the probability blocks [probs_orig ; onehot], then ONE sharded ring write: the
             # gathered buffers are already in global (rank-major) row order.
             W = (C + 1 + 3) & ~3
-            block_f = torch.cat([fw, fx], dim=0)
-            gathered_f = all_gather_rows(block_f, self.pg)                   # [R*n, D]
+            arena = self._peer_arena(n, D * fw.element_size(), W * 4, C * 4)
+            gathered_f = self._x_all_gather(arena, 0, [fw, fx])              # [R*n, D]
             if self.smoothing:
                 packed = self._k_smooth(gathered_f, packed_ld=W)             # [R*n, W]: numer | rowsum
-                mine = reduce_scatter_rows(packed, self.pg)                  # [n, W]; rows [0, rows) are this rank's queries
+                mine = self._x_reduce_scatter(arena, 1, packed)              # [n, W]; rows [0, rows) are this rank's queries
                 numer, rowsum, lds = mine, mine[:, C:], (W, W)
             if fused:
                 out = self._k_rows_fused(lw, ls0, rowsum, numer, lds, fw, fx, tx, False, True)
@@ -266,7 +272,7 @@ class CoMatchHead:
                 onehot = torch.zeros(n_x, C, dtype=torch.float32, device=lw.device).scatter_(1, tx.view(-1, 1), 1.0)
                 probs_block = torch.cat([out["probs_orig"], onehot], dim=0)
             if do_enqueue:
-                pb_all = all_gather_rows(probs_block, self.pg)               # [R*n, C]
+                pb_all = self._x_all_gather(arena, 2, [probs_block])         # [R*n, C]
                 self._k_enqueue(gathered_f, gathered_f[:0], pb_all, tx[:0], 0, R * n)
         if do_enqueue:
             self._queue_ptr = geom.next_ptr(self._queue_ptr, n)
@@ -277,6 +283,42 @@ class CoMatchHead:
                      "mask": out["mask"], "lbs": out["lbs"], "scores": out["scores"]}
         out["stats"] = stats
         return out
+
+    # ---- row exchanges of the sharded bank ------------------------------------------
+    def _peer_arena(self, n: int, feat_row_bytes: int, packed_row_bytes: int, prob_row_bytes: int):
+        """The NVLink peer-memory arena for blocks of ``n`` rows, (re)built collectively when the block grows;
+        ``None`` when the exchanges go through torch.distributed."""
+        if self.exchange != "peer":
+            return None
+        need = {0: n * feat_row_bytes, 1: n * packed_row_bytes, 2: n * prob_row_bytes}
+        if self._arena is None or not all(self._arena.fits(x, b) for x, b in need.items()):
+            if torch.cuda.is_current_stream_capturing():
+                raise RuntimeError("the peer arena must exist before CUDA graph capture: run one eager step first")
+            from .peer import PeerArena
+            if self._arena is not None:
+                self._arena.close()
+            self._arena = PeerArena(self.pg, self.device, need)
+        return self._arena
+
+    def _x_all_gather(self, arena, x: int, parts):
+        if arena is not None and all((t.numel() * t.element_size()) % 16 == 0 for t in parts):
+            return arena.all_gather(x, parts)
+        return all_gather_rows(parts[0] if len(parts) == 1 else torch.cat(list(parts), dim=0), self.pg)
+
+    def _x_reduce_scatter(self, arena, x: int, packed):
+        if arena is not None and (packed.numel() // self.geom.world_size * 4) % 16 == 0:
+            return arena.reduce_scatter(x, packed)
+        return reduce_scatter_rows(packed, self.pg)
+
+    def peer_timeouts(self) -> int:
+        """Peer waits that gave up since the arena was built (0 in a healthy job; synchronises)."""
+        return self._arena.timeouts() if self._arena is not None else 0
+
+    def close(self) -> None:
+        """Collective: release the peer arena (before ``destroy_process_group``)."""
+        if self._arena is not None:
+            self._arena.close()
+            self._arena = None
 
     # ---- kernel wrappers (one C-ABI call each) --------------------------------------
     def _ws(self, rows):

@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdlib.h>
+#include <string.h>
 
 #include "b200ssl.h"
 
@@ -52,7 +53,7 @@ __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepc
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 // cudaLaunchKernelEx with the PDL attribute and an optional thread-block cluster.
-enum { PDL_SMOOTH = 0, PDL_ROWS = 1, PDL_CONTRAST_FWD = 2, PDL_CONTRAST_BWD = 3, PDL_EMA = 4 };
+enum { PDL_SMOOTH = 0, PDL_ROWS = 1, PDL_CONTRAST_FWD = 2, PDL_CONTRAST_BWD = 3, PDL_EMA = 4, PDL_PEER = 5 };
 constexpr int kPdlDefaultMask = 15;   // the four head kernels; measured: the HBM-bound EMA launch loses 4 us when it is scheduled early
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_pdl(int tag, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, dim3 cluster,

@@ -269,6 +269,43 @@ B200SSL_API int b200ssl_ema_multi_tensor(const b200ssl_ema_block* blocks, int32_
                              int32_t do_ints, float decay, float one_minus_decay,
                              int32_t mode /*0 update, 1 set*/, void* stream);
 
+/* ------------------------------------------------------------ SURVEY 8e ----
+ * Row exchanges of the rank-sharded memory bank over NVLink peer memory.  The
+ * reference has no distributed code (one bank per process, code/comatch.py:90-96);
+ * these entry points carry the three exchanges a sharded step needs (all-gather of
+ * the enqueue blocks, reduce-scatter of the smoothing partial sums, all-gather of
+ * the probability blocks) without a communication library on the data path.
+ *
+ * Arena: one device allocation per rank, exported through CUDA IPC and mapped by
+ * every rank of the node.  Layout: b200ssl_peer_control_bytes() of flags/epochs
+ * (zero-initialised by b200ssl_peer_alloc), then caller-defined staging regions;
+ * the region of one exchange holds [2 parities][world][slot_bytes].
+ *   arenas       device array [world] of arena base addresses AS MAPPED IN THIS
+ *                PROCESS (entry `rank` = the own arena)
+ *   exchange_id  0..7, one per call site; all ranks must issue the same sequence
+ *                of calls (SPMD).  Epoch counters live in the arena: launches can
+ *                be captured in a CUDA graph and replayed.
+ * One launch = push to all peers + publish + wait + copy-out, `out` is ordinary
+ * local memory.  A wait gives up after 20 s and counts a timeout instead of
+ * hanging the device (the results of that step are then undefined).
+ */
+B200SSL_API size_t b200ssl_peer_control_bytes(void);
+B200SSL_API int b200ssl_peer_alloc(size_t bytes, void** arena, void* ipc_handle_64 /* 64 bytes out */);
+B200SSL_API int b200ssl_peer_open(const void* ipc_handle_64, void** arena);
+B200SSL_API int b200ssl_peer_close(void* arena);
+B200SSL_API int b200ssl_peer_free(void* arena);
+B200SSL_API int b200ssl_peer_timeouts(const void* own_arena, uint32_t* count /* host out; synchronises */);
+
+/* out[r] = rank r's block [src0 ; src1] (bytes0 + bytes1 bytes, both multiples of 16), r = 0..world-1. */
+B200SSL_API int b200ssl_peer_all_gather(const void* src0, size_t bytes0, const void* src1, size_t bytes1, void* out,
+                            void* const* arenas, size_t region_offset, size_t slot_bytes, int32_t exchange_id,
+                            int32_t rank, int32_t world, void* stream);
+
+/* out[i] = sum over ranks r = 0..world-1 (in that order, fp32 round-to-nearest) of rank r's src[rank*count + i]. */
+B200SSL_API int b200ssl_peer_reduce_scatter_f32(const float* src, float* out, int64_t count_per_rank, void* const* arenas,
+                                    size_t region_offset, size_t slot_bytes, int32_t exchange_id, int32_t rank,
+                                    int32_t world, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -27,14 +27,66 @@ def _inputs(seed, dtype=torch.float32):
     return b
 
 
-def _worker(rank, world, port, out_dir, dtype_name):
+def _check_peer_primitives(rank, world, dev):
+    """PeerArena launches against the NCCL collectives on the same data: many epochs (slot parity, epoch
+    counters), two-part gathers, and a CUDA-graph replay of both exchanges."""
+    from endoscopy_image_classification_b200.peer import PeerArena
+    arena = PeerArena(dist.group.WORLD, dev, {0: 471 * 128, 1: 471 * 96, 3: 4096})
+    g = torch.Generator(device=dev).manual_seed(11 + rank)
+    for it in range(9):
+        a = torch.randn(448 - 8 * it, 64, generator=g, device=dev).to(torch.bfloat16)
+        b = torch.randn(23, 64, generator=g, device=dev).to(torch.bfloat16)
+        got = arena.all_gather(0, [a, b])
+        want = torch.empty(world * (a.shape[0] + 23), 64, dtype=torch.bfloat16, device=dev)
+        dist.all_gather_into_tensor(want, torch.cat([a, b]))
+        assert torch.equal(got, want), ("all_gather", it)
+        part = torch.randn(world * (471 - it), 24, generator=g, device=dev)
+        got = arena.reduce_scatter(1, part)
+        want = torch.empty(471 - it, 24, device=dev)
+        dist.reduce_scatter_tensor(want, part.clone())
+        if world == 2:
+            assert torch.equal(got, want), ("reduce_scatter", it)      # two addends: order cannot matter
+        torch.testing.assert_close(got, want, rtol=1e-6, atol=1e-6)
+    # graph replay: epochs live on the device
+    src = torch.zeros(64, 16, device=dev)
+    part = torch.zeros(world * 32, 8, device=dev)
+    torch.cuda.synchronize()
+    dist.barrier()
+    graph = torch.cuda.CUDAGraph()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        arena.all_gather(3, [src])
+        arena.reduce_scatter(1, part)
+        torch.cuda.synchronize()
+        with torch.cuda.graph(graph, stream=side):
+            out_g = arena.all_gather(3, [src])
+            out_r = arena.reduce_scatter(1, part)
+    torch.cuda.current_stream().wait_stream(side)
+    for it in range(5):
+        src.fill_(float(10 * it + rank))
+        part.fill_(float(it + 1 + rank))
+        graph.replay()
+        torch.cuda.synchronize()
+        want = torch.cat([torch.full((64, 16), float(10 * it + r)) for r in range(world)])
+        assert torch.equal(out_g.cpu(), want), ("graph all_gather", it)
+        assert torch.equal(out_r.cpu(), torch.full((32, 8), float(sum(it + 1 + r for r in range(world))))), ("graph reduce_scatter", it)
+    assert arena.timeouts() == 0
+    del graph
+    arena.close()
+
+
+def _worker(rank, world, port, out_dir, dtype_name, exchange):
     sys.path.insert(0, str(REPO))
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
     from endoscopy_image_classification_b200.comatch_head import CoMatchHead
     dtype = getattr(torch, dtype_name)
-    head = CoMatchHead(C, D, K, THR, enqueue_mode="always", device=f"cuda:{rank}", dtype=dtype, process_group=dist.group.WORLD)
+    if exchange == "peer" and dtype_name == "float32":
+        _check_peer_primitives(rank, world, torch.device("cuda", rank))
+    head = CoMatchHead(C, D, K, THR, enqueue_mode="always", device=f"cuda:{rank}", dtype=dtype, process_group=dist.group.WORLD,
+                       exchange=exchange)
     outs = []
     for step in range(STEPS):
         inp = {k: v.cuda() for k, v in _inputs(100 * step + rank, dtype).items()}
@@ -46,6 +98,9 @@ def _worker(rank, world, port, out_dir, dtype_name):
                          g_f0=inp["feats_u_s0"].grad.float().cpu(), ptr=head.queue_ptr, dev_ptr=int(head.ptr_state[0])))
     torch.save(dict(outs=outs, qf=head.queue_feats.float().cpu(), qp=head.queue_probs.float().cpu()),
                os.path.join(out_dir, f"rank{rank}.pt"))
+    assert head.peer_timeouts() == 0
+    assert (head._arena is not None) == (exchange == "peer")
+    head.close()
     dist.barrier()
     dist.destroy_process_group()
 
@@ -56,14 +111,16 @@ def _free_port():
         return s.getsockname()[1]
 
 
+@pytest.mark.timeout(300)
+@pytest.mark.parametrize("exchange", ["peer", "collective"])
 @pytest.mark.parametrize("dtype_name,tol", [("float32", 1e-5), ("bfloat16", 1e-2)])
-def test_two_gpu_sharded_bank(tmp_path, dtype_name, tol):
+def test_two_gpu_sharded_bank(tmp_path, dtype_name, tol, exchange):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     sys.path.insert(0, str(REPO))
     from oracle import ssl_oracle as O
     world = 2
-    mp.spawn(_worker, args=(world, _free_port(), str(tmp_path), dtype_name), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, _free_port(), str(tmp_path), dtype_name, exchange), nprocs=world, join=True)
     res = [torch.load(tmp_path / f"rank{r}.pt", weights_only=False) for r in range(world)]
     dtype = getattr(torch, dtype_name)
     state = O.CoMatchState.zeros(K, D, C)
