@@ -233,11 +233,12 @@ def run_b200(args, wl, rank, world, local_rank):
     gdev = torch.Generator(device=dev).manual_seed(5)
     S.perturb_(model, gdev)                    # m != e, like after an optimizer step
     grad_keys = ("logits_u_s0", "feats_u_s0", "feats_u_s1") if wl["kind"] == "comatch" else ("logits_u_s",)
-    # N=1: smooth, rows (DA+finalize+enqueue), contrast fwd, contrast bwd (+scale), ema.  Sharded bank: + enqueue and,
-    # with peer-memory exchanges, the three exchange launches (all ours); NCCL's kernels are not counted.
+    # N=1: smooth, rows (DA+finalize+enqueue), contrast fwd, contrast bwd (+scale), ema.  Sharded bank: the same five
+    # with the directly addressed bank; + enqueue and three exchange launches with the peer-memory exchanges; + enqueue
+    # with NCCL (its kernels are not counted).
     launches_per_step = (5 if wl["kind"] == "comatch" else 3)
     if world > 1 and head is not None:
-        launches_per_step += 1 + (3 if head.exchange == "peer" else 0)
+        launches_per_step += {"direct": 0, "peer": 4, "collective": 1}[head.exchange]
     one = torch.ones((), dtype=torch.float32, device=dev)
 
     def step(batch):
@@ -345,6 +346,8 @@ def run_b200(args, wl, rank, world, local_rank):
     e2e_eager_ms = g0.elapsed_time(g1) / n_eager
     clocks = sampler.stop() if sampler else None
 
+    if world > 1 and head is not None and head.peer_timeouts():
+        raise RuntimeError(f"rank {rank}: peer-memory waits timed out; no valid measurement")
     times = torch.tensor([ms, e2e_ms, ema_ms, eager_ms, e2e_eager_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
@@ -360,8 +363,12 @@ def run_b200(args, wl, rank, world, local_rank):
                 "config": {"workload": wl["desc"], "global_batch_unlabeled": world * Bu, "per_gpu_unlabeled": Bu,
                            "bank_rows_global": wl["K"], "bank_sharded_over": world, "parallelism": f"dp{world}",
                            "bank_exchange": (None if world == 1 or head is None else
-                                             "own kernels over NVLink peer memory (csrc/peer.cu): all-gather, reduce-scatter, "
-                                             "all-gather per step" if head.exchange == "peer" else "NCCL collectives"),
+                                             {"direct": "shards in NVLink peer memory: K3 reads every shard in place (TMA over NVLink), "
+                                                        "the enqueue stores into the owning shard; two epoch flags per step, no "
+                                                        "exchange launches",
+                                              "peer": "own kernels over NVLink peer memory (csrc/peer.cu): all-gather, reduce-scatter, "
+                                                      "all-gather per step",
+                                              "collective": "NCCL collectives"}[head.exchange]),
                            "ema_state": {"entries": plan.n_entries, "unique_storages": plan.n_unique,
                                          "unique_elems": plan.unique_elems, "blocks": plan.n_blocks},
                            "execution": "whole step (head fwd+bwd + EMA) captured once in a CUDA graph and replayed; "
@@ -381,10 +388,6 @@ def run_b200(args, wl, rank, world, local_rank):
             line["cpu_baseline"] = cpu
         print(json.dumps(line), flush=True)
     if world > 1:
-        if head is not None:
-            n_to = head.peer_timeouts()
-            if n_to:
-                raise RuntimeError(f"rank {rank}: {n_to} peer-memory waits timed out; the numbers above are invalid")
         # captured graphs hold NCCL work: they must be released before the communicator is torn down
         # (destroy_process_group() blocks forever otherwise, seen on 2xB200 with NCCL 2.28.9)
         import gc
@@ -406,8 +409,9 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--exchange", default="auto", choices=["auto", "peer", "collective"],
-                    help="row exchanges of the sharded bank at N>1: own NVLink peer-memory kernels (default) or NCCL")
+    ap.add_argument("--exchange", default="auto", choices=["auto", "direct", "peer", "collective"],
+                    help="sharded bank at N>1: directly addressed shards in NVLink peer memory (auto), own peer-memory "
+                         "exchange kernels, or NCCL collectives")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     rank = int(os.environ.get("RANK", "0"))

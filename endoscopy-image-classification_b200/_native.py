@@ -36,6 +36,13 @@ assert C.sizeof(EmaBlock) == 32
 _vp, _i64, _i32, _f32, _sz = C.c_void_p, C.c_int64, C.c_int32, C.c_float, C.c_size_t
 
 # name -> (restype, argtypes); must list every symbol include/b200ssl.h declares
+class BankShards(C.Structure):
+    """``b200ssl_bank_shards`` of include/b200ssl.h (directly addressed rank-sharded bank)."""
+    _fields_ = [("world", C.c_int32), ("rank", C.c_int32), ("shard_rows", C.c_int64), ("arenas_host", C.c_void_p),
+                ("arenas_dev", C.c_void_p), ("feats_offset", C.c_uint64), ("probs_offset", C.c_uint64),
+                ("probs_t_offset", C.c_uint64)]
+
+
 SIGNATURES = {
     "b200ssl_version": (_i32, []),
     "b200ssl_last_error_string": (C.c_char_p, []),
@@ -47,12 +54,12 @@ SIGNATURES = {
     "b200ssl_labeled_ce_fwd_bwd": (_i32, [_vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _f32, _vp, _vp, _sz, _vp]),
     "b200ssl_comatch_da": (_i32, [_vp, _i64, _i32, _i32, _vp, _vp, _i32, _vp, _vp, _vp, _sz, _vp]),
     "b200ssl_bank_smooth_partial": (_i32, [_vp, _vp, _vp, _vp, _i64, _i64, _i32, _i32, _i32, _f32, _vp, _vp, _i32, _i32,
-                                           _vp, _sz, _vp]),
+                                           _vp, _vp, _sz, _vp]),
     "b200ssl_comatch_finalize": (_i32, [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _i64, _i32, _i32, _f32, _f32, _f32, _f32,
                                         _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "b200ssl_comatch_rows_fused": (_i32, [_vp, _vp, _vp, _vp, _i32, _i32, _i64, _i32, _i32, _f32, _f32, _f32, _f32, _vp, _vp,
                                           _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
-                                          _i64, _i32, _vp, _i64, _i32, _vp]),
+                                          _i64, _i32, _vp, _i64, _i32, _vp, _vp]),
     "b200ssl_bank_enqueue": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i32, _i32, _i32, _i64, _vp, _i64,
                                     _i64, _i64, _i64, _i64, _vp]),
     "b200ssl_contrast_fwd": (_i32, [_vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _f32, _f32, _vp, _vp, _vp, _f32, _f32, _vp,

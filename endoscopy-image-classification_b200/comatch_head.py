@@ -29,6 +29,12 @@ import torch
 from . import _native as N
 from .bank import ShardGeometry, all_gather_rows, reduce_scatter_rows
 
+def C_byref(struct):
+    """ctypes pointer to an optional struct (None -> NULL)."""
+    import ctypes
+    return None if struct is None else ctypes.byref(struct)
+
+
 __all__ = ["CoMatchHead"]
 
 
@@ -108,7 +114,7 @@ class CoMatchHead:
                  dtype: torch.dtype = torch.float32, process_group=None, exchange: str = "auto"):
         if enqueue_mode not in ("reference", "always"):
             raise ValueError(enqueue_mode)
-        if exchange not in ("auto", "peer", "collective"):
+        if exchange not in ("auto", "direct", "peer", "collective"):
             raise ValueError(exchange)
         self.num_classes, self.low_dim, self.queue_size = int(num_classes), int(low_dim), int(queue_size)
         self.thr, self.alpha, self.temperature = float(thr), float(alpha), float(temperature)
@@ -122,10 +128,17 @@ class CoMatchHead:
             import torch.distributed as dist
             world, rank = dist.get_world_size(process_group), dist.get_rank(process_group)
         self.geom = ShardGeometry(self.queue_size, world, rank)
-        # row exchanges of the sharded bank: 'peer' = own kernels over NVLink peer memory (peer.py, one node),
-        # 'collective' = torch.distributed collectives (NCCL; gloo in the CPU tests); 'auto' = peer on CUDA
-        self.exchange = ("peer" if self.device.type == "cuda" else "collective") if exchange == "auto" else exchange
+        # How the sharded bank (world > 1) is reached:
+        #   'direct'     the shards live in NVLink peer memory; K3 reads every shard in place and the enqueue stores
+        #                into the owning shard -- same launches as one GPU, two epoch flags per step (bf16 banks with
+        #                the tensor-core layout, <= 8 ranks of one node)
+        #   'peer'       all-gather / reduce-scatter / all-gather by own kernels over peer memory (peer.py)
+        #   'collective' the same three exchanges through torch.distributed (NCCL; gloo in the CPU tests)
+        #   'auto'       direct when the bank qualifies, else peer; collective on CPU
+        self._exchange_req = exchange
+        self.exchange = "collective"
         self._arena = None
+        self._shards = None
         self._alloc_bank(dtype)
         # write pointer: device-resident {ptr, ticket} (graph-replay safe) + host mirror
         self.ptr_state = torch.zeros(2, dtype=torch.int64, device=self.device)
@@ -144,6 +157,31 @@ class CoMatchHead:
 
     def _alloc_bank(self, dtype) -> None:
         self.dtype = dtype
+        Ks, C, D, R = self.geom.shard_rows, self.num_classes, self.low_dim, self.geom.world_size
+        req, on_gpu = self._exchange_req, self.device.type == "cuda"
+        self.queue_feats = self.queue_probs = self.queue_probs_t = self._shards = None
+        if self._arena is not None:
+            self._arena.close()
+            self._arena = None
+        direct_ok = (R > 1 and R <= 8 and on_gpu and dtype == torch.bfloat16 and C <= 31 and D == 64 and Ks % 8 == 0
+                     and self.smoothing)
+        if req == "direct" and not direct_ok:
+            raise ValueError("exchange='direct' needs 2..8 CUDA ranks, a bf16 bank, low_dim 64, <= 31 classes, shard rows % 8 == 0")
+        self.exchange = ("direct" if direct_ok else "peer" if on_gpu else "collective") if req == "auto" else req
+        if R > 1 and self.exchange == "direct":
+            import ctypes
+            import torch.distributed as dist
+            from .peer import PeerArena
+            self._arena = a = PeerArena(self.pg, self.device, {}, named={"qf": Ks * D * 2, "qp": Ks * C * 2, "qpt": 32 * Ks * 2})
+            self.queue_feats = a.tensor("qf", (Ks, D), dtype)            # zero-filled by the allocation
+            self.queue_probs = a.tensor("qp", (Ks, C), dtype)
+            self.queue_probs_t = a.tensor("qpt", (32, Ks), dtype)
+            self.queue_probs_t[C].fill_(1.0)
+            self._shards = N.BankShards(R, self.geom.rank, Ks, ctypes.addressof(a.bases_host), a.bases.data_ptr(),
+                                        a.named_offset["qf"], a.named_offset["qp"], a.named_offset["qpt"])
+            torch.cuda.synchronize(self.device)
+            dist.barrier(group=self.pg)          # the ones row of every shard is in place before any peer reads it
+            return
         self.queue_feats = torch.zeros(self.geom.shard_rows, self.low_dim, dtype=dtype, device=self.device)
         self.queue_probs = torch.zeros(self.geom.shard_rows, self.num_classes, dtype=dtype, device=self.device)
         # transposed, class-padded copy [32, K_local] for the tensor-core smoothing kernel (bf16 banks)
@@ -239,7 +277,10 @@ class CoMatchHead:
         fused = self.fuse_rows and C <= 32 and rows <= self.FUSED_ROWS_MAX
         rowsum = numer = None
         lds = (0, 0)                                                         # (rowsum_ld, numer_ld): 0 = dense
-        if R == 1:
+        if R == 1 or self.exchange == "direct":
+            if R > 1 and not fused:
+                raise RuntimeError(f"exchange='direct' needs the fused row kernel (<= {self.FUSED_ROWS_MAX} unlabeled rows per "
+                                   "rank, fuse_rows=True); build the head with exchange='peer' for larger batches")
             if not fused:
                 self._k_da(lw)                                               # K2
             if self.smoothing:                                               # K3, bank as of *before* this step's enqueue
@@ -317,12 +358,15 @@ class CoMatchHead:
     def close(self) -> None:
         """Collective: release the peer arena (before ``destroy_process_group``)."""
         if self._arena is not None:
+            torch.cuda.synchronize(self.device)
+            self.queue_feats = self.queue_probs = self.queue_probs_t = self._shards = None    # they alias the arena
             self._arena.close()
             self._arena = None
 
     # ---- kernel wrappers (one C-ABI call each) --------------------------------------
     def _ws(self, rows):
-        return N.workspace(self.device, rows, self.num_classes, self.geom.shard_rows)
+        return N.workspace(self.device, rows, self.num_classes,
+                           self.queue_size if self._shards is not None else self.geom.shard_rows)
 
     def _k_da(self, lw) -> None:
         ws, wsb = self._ws(lw.shape[0])
@@ -345,10 +389,13 @@ class CoMatchHead:
             numer = torch.empty(rows, C, dtype=torch.float32, device=self.device)
             lds = (0, 0)
         ws, wsb = self._ws(rows)
+        sh = self._shards
         N.check(N.lib().b200ssl_bank_smooth_partial(queries.data_ptr(), self.queue_feats.data_ptr(),
                                                     self.queue_probs.data_ptr(), N.ptr(self.queue_probs_t), rows,
-                                                    self.geom.shard_rows, D, C, N.dtype_enum(queries), self.temperature,
-                                                    rowsum.data_ptr(), numer.data_ptr(), lds[0], lds[1], ws, wsb,
+                                                    self.queue_size if sh is not None else self.geom.shard_rows, D, C,
+                                                    N.dtype_enum(queries), self.temperature,
+                                                    rowsum.data_ptr(), numer.data_ptr(), lds[0], lds[1],
+                                                    C_byref(sh), ws, wsb,
                                                     N.stream_ptr(self.device)), "bank_smooth_partial")
         return packed if packed_ld else (rowsum, numer)
 
@@ -394,7 +441,7 @@ class CoMatchHead:
             out["lbs"].data_ptr(), out["mask"].data_ptr(), out["grad_s0"].data_ptr(), out["scalars"].data_ptr(),
             self.queue_feats.data_ptr() if enq else None, self.queue_probs.data_ptr() if enq else None,
             N.ptr(self.queue_probs_t) if enq else None, fw.data_ptr(), fx.data_ptr(), tx.data_ptr(), fx.shape[0],
-            self.low_dim, self.ptr_state.data_ptr(), self.queue_size, 1 if onehot_tail else 0,
+            self.low_dim, self.ptr_state.data_ptr(), self.queue_size, 1 if onehot_tail else 0, C_byref(self._shards),
             N.stream_ptr(self.device)), "comatch_rows_fused")
         return out
 

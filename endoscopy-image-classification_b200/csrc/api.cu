@@ -10,7 +10,7 @@ namespace {
 thread_local char g_err[512] = "";
 unsigned long long* g_timing = nullptr;
 }
-unsigned long long* debug_timing_buffer() { return g_timing; }
+unsigned long long* debug_timing_buffer(int kernel_tag) { return g_timing ? g_timing + (size_t)kernel_tag * kDebugRegion : nullptr; }
 
 int fail(int code, const char* fmt, ...) {
   va_list ap;

@@ -197,16 +197,30 @@ using namespace b200ssl;
 namespace b200ssl {
 int bank_smooth_tc(const void* feats, const void* queue_feats, const void* queue_probs_t, long long rows,
                    long long bank_rows, int classes, float temperature, float* rowsum, float* numer, int rowsum_ld,
-                   int numer_ld, void* workspace, size_t workspace_bytes, cudaStream_t stream);
+                   int numer_ld, const b200ssl_bank_shards* shards, void* workspace, size_t workspace_bytes, cudaStream_t stream);
 }
 
 extern "C" int b200ssl_bank_smooth_partial(const void* feats_u_w, const void* queue_feats, const void* queue_probs,
                                            const void* queue_probs_t, int64_t rows, int64_t bank_rows, int32_t dim, int32_t classes,
                                            int32_t dtype, float temperature, float* rowsum, float* numer,
-                                           int32_t rowsum_ld, int32_t numer_ld, void* workspace, size_t workspace_bytes,
-                                           void* stream) {
+                                           int32_t rowsum_ld, int32_t numer_ld, const b200ssl_bank_shards* shards,
+                                           void* workspace, size_t workspace_bytes, void* stream) {
   const char* fn = "b200ssl_bank_smooth_partial";
-  if (!feats_u_w || !queue_feats || !queue_probs || !rowsum || !numer) return fail(B200SSL_E_NULL, "%s: NULL tensor", fn);
+  if (!feats_u_w || !rowsum || !numer || (!shards && (!queue_feats || !queue_probs))) return fail(B200SSL_E_NULL, "%s: NULL tensor", fn);
+  if (shards) {
+    // directly addressed sharded bank: tensor-core path only
+    if (shards->world < 2 || shards->world > 8 || shards->rank < 0 || shards->rank >= shards->world || !shards->arenas_host ||
+        !shards->arenas_dev || shards->shard_rows <= 0 || shards->shard_rows % 8 || bank_rows != shards->shard_rows * shards->world)
+      return fail(B200SSL_E_ARG, "%s: bad shard table (2..8 ranks, shard_rows a multiple of 8, bank_rows = world*shard_rows)", fn);
+    if (dtype != B200SSL_BF16 || dim != 64 || classes > 31 || classes < 2 || (reinterpret_cast<uintptr_t>(feats_u_w) & 15u) ||
+        ((shards->feats_offset | shards->probs_t_offset) & 127u))
+      return fail(B200SSL_E_DTYPE, "%s: the directly addressed sharded bank needs bf16, dim 64, classes <= 31, aligned rows", fn);
+    if (!(temperature > 0.f) || rows <= 0 || !workspace || (reinterpret_cast<uintptr_t>(workspace) & 255u))
+      return fail(B200SSL_E_ARG, "%s: rows / temperature / workspace", fn);
+    return bank_smooth_tc(feats_u_w, nullptr, nullptr, rows, bank_rows, classes, temperature, rowsum, numer,
+                          rowsum_ld > 0 ? rowsum_ld : 1, numer_ld > 0 ? numer_ld : classes, shards, workspace, workspace_bytes,
+                          as_stream(stream));
+  }
   if (rows <= 0 || bank_rows <= 0) return fail(B200SSL_E_SHAPE, "%s: rows=%lld bank_rows=%lld", fn, (long long)rows, (long long)bank_rows);
   if (dim < 8 || dim > B200SSL_MAX_EMB_DIM || dim % 8) return fail(B200SSL_E_SHAPE, "%s: dim %d must be a multiple of 8 in [8,%d]", fn, dim, B200SSL_MAX_EMB_DIM);
   if (classes < 2 || classes > 128) return fail(B200SSL_E_SHAPE, "%s: classes %d outside [2,128]", fn, classes);
@@ -218,7 +232,7 @@ extern "C" int b200ssl_bank_smooth_partial(const void* feats_u_w, const void* qu
       !(reinterpret_cast<uintptr_t>(feats_u_w) & 15u) && !(reinterpret_cast<uintptr_t>(queue_feats) & 15u) &&
       !(reinterpret_cast<uintptr_t>(queue_probs_t) & 15u))
     return bank_smooth_tc(feats_u_w, queue_feats, queue_probs_t, rows, bank_rows, classes, temperature, rowsum, numer,
-                          rowsum_ld > 0 ? rowsum_ld : 1, numer_ld > 0 ? numer_ld : classes, workspace, workspace_bytes,
+                          rowsum_ld > 0 ? rowsum_ld : 1, numer_ld > 0 ? numer_ld : classes, nullptr, workspace, workspace_bytes,
                           as_stream(stream));
   SmoothParams p{};
   p.f = feats_u_w; p.qf = queue_feats; p.qp = queue_probs;

@@ -22,6 +22,7 @@
 #include <cooperative_groups.h>
 
 #include "common.cuh"
+#include "peer.cuh"
 #include "tc.cuh"
 
 namespace b200ssl {
@@ -81,6 +82,7 @@ constexpr int kCP = 32;           // classes + the "ones" column, padded (UMMA N
 constexpr int kStages = 2;
 constexpr int kTcThreads = 320;   // warp 0 TMA + TMEM alloc, warp 1 MMA, warps 2..9 epilogue (2 per TMEM lane quarter)
 constexpr int kMaxCluster = 8;
+constexpr int kMaxSeg = 8;        // bank segments = shards of a rank-sharded bank (1 = the whole bank is local)
 constexpr uint32_t kTileA = kBM * 128;                  // 16 KB: [128][64] bf16
 constexpr uint32_t kTileQf = kBN * 128;                 // 16 KB
 constexpr uint32_t kSubQp = kCP * 128;                  //  4 KB: [32][64] bf16
@@ -92,8 +94,16 @@ constexpr uint32_t kTmemCols = 512;                     // S[0] 0..127, S[1] 128
 constexpr size_t kSmemRequest = 120 * 1024;             // > half an SM: one CTA per SM (it owns all TMEM columns)
 constexpr int kRedLd = 36;                              // floats per row of the reduction tile (16-byte rows, 4-way bank spread)
 
+struct BankMaps {                 // one pair of tensor maps per shard; remote shards are peer-mapped NVLink addresses
+  CUtensorMap qf[kMaxSeg];
+  CUtensorMap qpt[kMaxSeg];
+};
+
 struct SmoothTcParams {
-  long long rows, bank_rows, rows_pad;
+  long long rows, rows_pad;
+  int nseg, tps;                  // key tiles are enumerated shard by shard: tile kt -> (kt / tps, kt % tps)
+  uint8_t* const* arenas;         // non-NULL: directly addressed sharded bank (peer.cuh flags / epochs)
+  int rank, world;
   int C, W;                       // W = round_up(C + 1, 4): [numer 0..C-1, rowsum] per row of a partial
   int nsplit, cluster, nouter;    // nsplit = cluster * nouter CTAs share one row tile
   float scale;                    // log2(e) / temperature
@@ -112,8 +122,7 @@ __device__ __forceinline__ float ex2_approx(float x) {
 }
 
 __global__ void __launch_bounds__(kTcThreads, 1)
-bank_smooth_tc_kernel(const __grid_constant__ CUtensorMap tm_f, const __grid_constant__ CUtensorMap tm_qf,
-                      const __grid_constant__ CUtensorMap tm_qpt, const SmoothTcParams p) {
+bank_smooth_tc_kernel(const __grid_constant__ CUtensorMap tm_f, const __grid_constant__ BankMaps maps, const SmoothTcParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* sA = smem;
@@ -129,7 +138,7 @@ bank_smooth_tc_kernel(const __grid_constant__ CUtensorMap tm_f, const __grid_con
   const int row_tile = blockIdx.x, split = blockIdx.y;
   const int cta = blockIdx.y * gridDim.x + blockIdx.x;
   pdl_launch_dependents();                                 // the next kernel may start its prologue
-  const long long nktiles = (p.bank_rows + kBN - 1) / kBN;
+  const long long nktiles = (long long)p.nseg * p.tps;
   const long long kt0 = nktiles * split / p.nsplit;                // balanced: every split owns >= 1 key tile
   const int T = (int)(nktiles * (split + 1) / p.nsplit - kt0);
 
@@ -150,8 +159,8 @@ bank_smooth_tc_kernel(const __grid_constant__ CUtensorMap tm_f, const __grid_con
   if (warp == 0) tc::tmem_alloc(tmem_slot, kTmemCols);
   if (warp == 1 && lane == 0) {
     tc::tma_prefetch_desc(&tm_f);
-    tc::tma_prefetch_desc(&tm_qf);
-    tc::tma_prefetch_desc(&tm_qpt);
+    tc::tma_prefetch_desc(&maps.qf[(int)(kt0 / p.tps)]);
+    tc::tma_prefetch_desc(&maps.qpt[(int)(kt0 / p.tps)]);
   }
   tc::tcgen05_fence_before();
   __syncthreads();
@@ -165,14 +174,24 @@ bank_smooth_tc_kernel(const __grid_constant__ CUtensorMap tm_f, const __grid_con
     if (lane == 0) {
       tc::mbar_arrive_expect_tx(&bars[BAR_A], kTileA);
       tc::tma_load_2d(sA, &tm_f, 0, row_tile * kBM, &bars[BAR_A]);
+      if (p.arenas) {
+        // sharded bank: every rank's enqueue of the previous step must have landed in the shards (its flag was
+        // published a contrastive forward + backward + EMA ago, so this normally falls through)
+        uint8_t* mine = p.arenas[p.rank];
+        peer::LocalCtl* ctl = peer::local_ctl(mine);
+        const unsigned long long need = *reinterpret_cast<volatile unsigned long long*>(&ctl->epoch[peer::kXSmoothDone]);
+        for (int s = 0; s < p.world; ++s)
+          if (s != p.rank) peer::wait_flag(peer::flag_of(mine, peer::kXEnqueueDone, s), need, ctl);
+      }
       for (int t = 0; t < T; ++t) {
         const int s = t % kStages;
         if (t >= kStages) tc::mbar_wait(&bars[BAR_KV_EMPTY + s], ((t / kStages) - 1) & 1, abort_flag);
-        const int key0 = (int)((kt0 + t) * kBN);
+        const int seg = (int)((kt0 + t) / p.tps);
+        const int key0 = (int)((kt0 + t) - (long long)seg * p.tps) * kBN;          // row inside the shard
         tc::mbar_arrive_expect_tx(&bars[BAR_KV_FULL + s], kTileQf + kTileQp);
-        tc::tma_load_2d(sQf + s * kTileQf, &tm_qf, 0, key0, &bars[BAR_KV_FULL + s]);
-        tc::tma_load_2d(sQp + s * kTileQp, &tm_qpt, key0, 0, &bars[BAR_KV_FULL + s]);
-        tc::tma_load_2d(sQp + s * kTileQp + kSubQp, &tm_qpt, key0 + 64, 0, &bars[BAR_KV_FULL + s]);
+        tc::tma_load_2d(sQf + s * kTileQf, &maps.qf[seg], 0, key0, &bars[BAR_KV_FULL + s]);
+        tc::tma_load_2d(sQp + s * kTileQp, &maps.qpt[seg], key0, 0, &bars[BAR_KV_FULL + s]);
+        tc::tma_load_2d(sQp + s * kTileQp + kSubQp, &maps.qpt[seg], key0 + 64, 0, &bars[BAR_KV_FULL + s]);
       }
     }
   } else if (warp == 1) {
@@ -268,6 +287,20 @@ bank_smooth_tc_kernel(const __grid_constant__ CUtensorMap tm_f, const __grid_con
     tc::tmem_dealloc(tmem, kTmemCols);
   }
   if (threadIdx.x == 0) B200SSL_STAMP(p.dbg, cta, 6);      // accumulator staged, TMEM released
+  if (p.arenas && threadIdx.x == 0) {
+    // every key tile of this CTA has been consumed.  The last CTA of the grid tells the peers that this rank no
+    // longer reads the shards of this step: their enqueue may overwrite rows.
+    uint8_t* mine = p.arenas[p.rank];
+    peer::LocalCtl* ctl = peer::local_ctl(mine);
+    const unsigned long long epoch = *reinterpret_cast<volatile unsigned long long*>(&ctl->epoch[peer::kXSmoothDone]) + 1;
+    __threadfence();
+    if (atomicAdd(&ctl->done[peer::kXSmoothDone], 1u) == gridDim.x * gridDim.y - 1) {
+      ctl->done[peer::kXSmoothDone] = 0;
+      for (int s = 0; s < p.world; ++s)
+        if (s != p.rank) peer::st_release_sys(peer::flag_of(p.arenas[s], peer::kXSmoothDone, p.rank), epoch);
+      *reinterpret_cast<volatile unsigned long long*>(&ctl->epoch[peer::kXSmoothDone]) = epoch;
+    }
+  }
 
   // ---- fold the splits of this row tile: first inside the cluster through distributed shared memory ----
   cg::cluster_group cluster = cg::this_cluster();
@@ -340,9 +373,8 @@ bank_smooth_tc_kernel(const __grid_constant__ CUtensorMap tm_f, const __grid_con
 }
 
 // cluster size (power of two <= 8) and number of clusters per row tile
-void smooth_tc_plan(long long rows, long long bank_rows, int* cluster, int* nouter) {
+void smooth_tc_plan(long long rows, long long ktiles, int* cluster, int* nouter) {
   const long long row_tiles = (rows + kBM - 1) / kBM;
-  const long long ktiles = (bank_rows + kBN - 1) / kBN;
   int cl = 1;
   while (cl * 2 <= kMaxCluster && cl * 2 <= ktiles) cl *= 2;
   long long no = 1;
@@ -360,32 +392,44 @@ void smooth_tc_plan(long long rows, long long bank_rows, int* cluster, int* nout
 size_t smooth_tc_workspace_floats(long long rows, long long bank_rows, int classes) {
   const long long row_tiles = (rows + kBM - 1) / kBM;
   int cl, no;
-  smooth_tc_plan(rows, bank_rows, &cl, &no);
+  smooth_tc_plan(rows, (bank_rows + kBN - 1) / kBN, &cl, &no);
   return no > 1 ? (size_t)no * row_tiles * kBM * ((1 + classes + 3) & ~3) : 0;
 }
 
 // bf16, dim 64, classes <= 31, bank rows a multiple of 8: the tensor-core path.
 int bank_smooth_tc(const void* feats, const void* queue_feats, const void* queue_probs_t, long long rows,
                    long long bank_rows, int classes, float temperature, float* rowsum, float* numer, int rowsum_ld,
-                   int numer_ld, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+                   int numer_ld, const b200ssl_bank_shards* sh, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
   const char* fn = "b200ssl_bank_smooth_partial[tcgen05]";
   SmoothTcParams p{};
-  p.rows = rows; p.bank_rows = bank_rows; p.C = classes; p.W = (1 + classes + 3) & ~3;
+  const long long seg_rows = sh ? sh->shard_rows : bank_rows;
+  p.nseg = sh ? sh->world : 1;
+  p.tps = (int)((seg_rows + kBN - 1) / kBN);
+  if (sh) {
+    p.arenas = reinterpret_cast<uint8_t* const*>(sh->arenas_dev); p.rank = sh->rank; p.world = sh->world;
+  }
+  p.rows = rows; p.C = classes; p.W = (1 + classes + 3) & ~3;
   p.scale = (float)(1.4426950408889634 / (double)temperature);
-  p.rowsum = rowsum; p.numer = numer; p.rowsum_ld = rowsum_ld; p.numer_ld = numer_ld; p.dbg = debug_timing_buffer();
-  smooth_tc_plan(rows, bank_rows, &p.cluster, &p.nouter);
+  p.rowsum = rowsum; p.numer = numer; p.rowsum_ld = rowsum_ld; p.numer_ld = numer_ld; p.dbg = debug_timing_buffer(PDL_SMOOTH);
+  smooth_tc_plan(rows, (long long)p.nseg * p.tps, &p.cluster, &p.nouter);
   p.nsplit = p.cluster * p.nouter;
   const long long row_tiles = (rows + kBM - 1) / kBM;
   p.rows_pad = row_tiles * kBM;
-  const size_t need = kWsHeaderBytes + sizeof(float) * smooth_tc_workspace_floats(rows, bank_rows, classes);
+  const size_t need = kWsHeaderBytes + sizeof(float) * (p.nouter > 1 ? (size_t)p.nouter * row_tiles * kBM * p.W : 0);
   if (workspace_bytes < need) return fail(B200SSL_E_WORKSPACE, "%s: workspace %zu < %zu bytes", fn, workspace_bytes, need);
   if ((size_t)row_tiles * 4 > kWsTicket2Bytes) return fail(B200SSL_E_SHAPE, "%s: too many row tiles", fn);
   p.tickets = reinterpret_cast<unsigned*>(static_cast<char*>(workspace) + kWsTicketBytes);
   p.part = reinterpret_cast<float*>(static_cast<char*>(workspace) + kWsHeaderBytes);
-  CUtensorMap tm_f, tm_qf, tm_qpt;
+  CUtensorMap tm_f;
+  BankMaps maps;
   if (int e = tc::make_tmap_bf16_2d(&tm_f, feats, (uint64_t)rows, 64, 128, kBM, 64)) return e;
-  if (int e = tc::make_tmap_bf16_2d(&tm_qf, queue_feats, (uint64_t)bank_rows, 64, 128, kBN, 64)) return e;
-  if (int e = tc::make_tmap_bf16_2d(&tm_qpt, queue_probs_t, kCP, (uint64_t)bank_rows, (uint64_t)bank_rows * 2, kCP, 64)) return e;
+  for (int s = 0; s < kMaxSeg; ++s) {
+    const int src = s < p.nseg ? s : 0;                    // unused entries repeat segment 0 (never dereferenced)
+    const void* qf = sh ? reinterpret_cast<const void*>(sh->arenas_host[src] + sh->feats_offset) : queue_feats;
+    const void* qpt = sh ? reinterpret_cast<const void*>(sh->arenas_host[src] + sh->probs_t_offset) : queue_probs_t;
+    if (int e = tc::make_tmap_bf16_2d(&maps.qf[s], qf, (uint64_t)seg_rows, 64, 128, kBN, 64)) return e;
+    if (int e = tc::make_tmap_bf16_2d(&maps.qpt[s], qpt, kCP, (uint64_t)seg_rows, (uint64_t)seg_rows * 2, kCP, 64)) return e;
+  }
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(bank_smooth_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemRequest);
@@ -395,7 +439,7 @@ int bank_smooth_tc(const void* feats, const void* queue_feats, const void* queue
   static_assert(kSmemData + 1024 + 256 <= kSmemRequest, "shared memory budget");
   static_assert(kBM * kRedLd * sizeof(float) <= kTileP, "reduction tile must fit in the P buffer");
   cudaError_t e = launch_pdl(PDL_SMOOTH, bank_smooth_tc_kernel, dim3((unsigned)row_tiles, (unsigned)p.nsplit, 1), dim3(kTcThreads, 1, 1),
-                             kSmemRequest, stream, dim3(1, (unsigned)p.cluster, 1), tm_f, tm_qf, tm_qpt, p);
+                             kSmemRequest, stream, dim3(1, (unsigned)p.cluster, 1), tm_f, maps, p);
   if (e != cudaSuccess) return fail((int)e, "%s: cudaLaunchKernelEx: %s", fn, cudaGetErrorString(e));
   return check_launch(fn);
 }

@@ -25,7 +25,8 @@ constexpr int kNumSMs = 148;  // B200
 // Optional device-side timing probe (tools/kernel_timeline.py): when a buffer is registered with
 // b200ssl_debug_set_timing_buffer(), instrumented kernels store clock64() stamps per CTA:
 // dbg[cta * 16 + slot].  NULL (the default) costs one predictable branch per stamp.
-unsigned long long* debug_timing_buffer();
+constexpr size_t kDebugRegion = 4096 * 16;   // u64 slots per instrumented kernel (region index = its PDL_* tag)
+unsigned long long* debug_timing_buffer(int kernel_tag);
 #define B200SSL_STAMP(dbg, cta, slot)                                            \
   do {                                                                          \
     if ((dbg) != nullptr) (dbg)[(size_t)(cta) * 16 + (slot)] = clock64();       \

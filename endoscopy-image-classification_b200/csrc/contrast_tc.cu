@@ -637,7 +637,7 @@ int contrast_fwd_tc(const void* f0, const void* f1, const void* probs_hl, long l
   p.rows = rows; p.C = classes; p.scale = (float)(1.4426950408889634 / (double)temperature);
   p.inv_tau = 1.0f / temperature; p.th = contrast_th; p.stats = stats; p.out = out_scalar;
   p.loss_u = loss_u; p.lambda_u = lambda_u; p.lambda_c = lambda_c; p.total_out = total_out;
-  p.cluster = ct_cluster(rows); p.dbg = debug_timing_buffer();
+  p.cluster = ct_cluster(rows); p.dbg = debug_timing_buffer(PDL_CONTRAST_FWD);
   const size_t need = kWsHeaderBytes + sizeof(float) * contrast_tc_workspace_floats(rows);
   if (workspace_bytes < need) return fail(B200SSL_E_WORKSPACE, "%s: workspace %zu < %zu bytes", fn, workspace_bytes, need);
   p.grid_ticket = reinterpret_cast<unsigned*>(workspace) + 4;
@@ -662,7 +662,7 @@ int contrast_bwd_tc(const void* f0, const void* f1, const void* probs_hl, const 
   p.rows = rows; p.C = classes; p.scale = (float)(1.4426950408889634 / (double)temperature);
   p.inv_tau = 1.0f / temperature; p.th = contrast_th; p.stats = const_cast<float*>(stats);
   p.upstream = upstream; p.factor = factor; p.g0 = g0; p.g1 = g1;
-  p.cluster = ct_cluster(rows); p.dbg = debug_timing_buffer();
+  p.cluster = ct_cluster(rows); p.dbg = debug_timing_buffer(PDL_CONTRAST_BWD);
   p.sgrad = static_cast<__nv_bfloat16*>(scale_grad); p.snumel = scale_numel; p.sup = scale_up; p.sfactor = scale_factor;
   CUtensorMap m[3];
   if (int e = ct_maps(m, f0, f1, probs_hl, rows)) return e;

@@ -16,40 +16,12 @@
 // exchange ahead of this rank (it needs this rank's flag of epoch e+1 to go further), so the slots of epoch e
 // are never overwritten before the local copy-out of epoch e has run.
 #include "common.cuh"
+#include "peer.cuh"
 
 namespace b200ssl {
 namespace {
 
-constexpr int kMaxWorld = 16;
-constexpr int kMaxExchange = 8;
-constexpr size_t kFlagBytes = 1024;                 // flags[kMaxExchange][kMaxWorld] u64
-constexpr size_t kCtlBytes = 4096;
-constexpr int kPeerThreads = 256;
-constexpr int kChunkBytes = 16384;                  // one CTA moves 16 KB: 4 x 16 B per thread
-constexpr unsigned long long kTimeoutNs = 20ull * 1000ull * 1000ull * 1000ull;
-
-struct LocalCtl {                                   // at arena + kFlagBytes
-  unsigned long long epoch[kMaxExchange];
-  unsigned int done[kMaxExchange];                  // CTAs of the running launch that have finished
-  unsigned int pushed[kMaxExchange][kMaxWorld];     // CTAs that have finished pushing to one destination
-  unsigned int timeouts;                            // sticky: a wait gave up (results of that step are garbage)
-};
-static_assert(sizeof(LocalCtl) <= kCtlBytes - kFlagBytes, "control block overflows its page");
-
-__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
-  unsigned long long v;
-  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
-  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-__device__ __forceinline__ unsigned long long globaltimer_ns() {
-  unsigned long long t;
-  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
-  return t;
-}
-__device__ __forceinline__ uint4 ld_cg(const void* p) { return __ldcg(reinterpret_cast<const uint4*>(p)); }
+using namespace peer;
 
 struct PeerParams {
   const uint8_t* src0; size_t bytes0;               // all-gather: my block = [src0 ; src1];  reduce-scatter: src0 = [R][bytes] fp32
@@ -63,19 +35,6 @@ struct PeerParams {
 
 __device__ __forceinline__ uint4 load_src(const PeerParams& p, size_t off) {     // 16-byte piece of [src0 ; src1]
   return off < p.bytes0 ? *reinterpret_cast<const uint4*>(p.src0 + off) : *reinterpret_cast<const uint4*>(p.src1 + (off - p.bytes0));
-}
-
-// Waits until flags[x][s] >= epoch for the sources s handled by the calling thread.
-__device__ __forceinline__ void wait_flag(const unsigned long long* flag, unsigned long long epoch, LocalCtl* ctl) {
-  if (ld_acquire_sys(flag) >= epoch) return;
-  const unsigned long long t0 = globaltimer_ns();
-  while (ld_acquire_sys(flag) < epoch) {
-    __nanosleep(64);
-    if (globaltimer_ns() - t0 > kTimeoutNs) {
-      atomicAdd(&ctl->timeouts, 1u);
-      return;
-    }
-  }
 }
 
 // grid (chunks, world): CTA (c, y) pushes chunk c to destination y, then serves chunk c of SOURCE y.

@@ -15,6 +15,7 @@
 #include <type_traits>
 
 #include "common.cuh"
+#include "peer.cuh"
 
 namespace b200ssl {
 namespace {
@@ -560,7 +561,22 @@ struct FusedParams {
   int CL; long long rows_per_cta;
   unsigned long long* dbg;
   int onehot_tail;   // probs_orig has rows + n_x rows: fill the tail with onehot(targets_x) (block for the sharded enqueue)
+  // directly addressed sharded bank (arenas != nullptr): global row g lives in arena g / shard_rows
+  uint8_t* const* arenas; int rank, world; long long shard_rows; size_t qf_off, qp_off, qpt_off;
+  long long block_offset, advance;   // this rank's block starts at ptr + block_offset; the pointer advances by `advance`
 };
+
+// Where global bank row g lives: the local bank, or the shard of the rank that owns it (peer-mapped NVLink memory).
+template <typename T>
+struct BankRow { T* qf; T* qp; T* qpt; long long row, ld; };
+template <typename T>
+__device__ __forceinline__ BankRow<T> bank_row(const FusedParams& p, long long g) {
+  if (!p.arenas) return {static_cast<T*>(p.qf), static_cast<T*>(p.qp), static_cast<T*>(p.qpt), g, p.K};
+  const int s = (int)(g / p.shard_rows);
+  uint8_t* base = p.arenas[s];
+  return {reinterpret_cast<T*>(base + p.qf_off), reinterpret_cast<T*>(base + p.qp_off), reinterpret_cast<T*>(base + p.qpt_off),
+          g - (long long)s * p.shard_rows, p.shard_rows};
+}
 
 template <typename T>
 __global__ void __launch_bounds__(kFusedThreads) comatch_rows_fused_kernel(const FusedParams p) {
@@ -589,7 +605,12 @@ __global__ void __launch_bounds__(kFusedThreads) comatch_rows_fused_kernel(const
   const float inv_rows = 1.0f / (float)f.rows;
   pdl_launch_dependents();
   pdl_wait();                                                // previous kernel complete: global memory may be touched now
-  const long long ptr = p.qf ? *reinterpret_cast<volatile long long*>(p.ptr_state) : 0;
+  const long long ptr0 = p.qf ? *reinterpret_cast<volatile long long*>(p.ptr_state) : 0;
+  const long long ptr = ptr0 + p.block_offset;
+  const bool sharded = p.arenas != nullptr;
+  uint8_t* my_arena = sharded ? p.arenas[p.rank] : nullptr;
+  const unsigned long long x_epoch =
+      sharded ? *reinterpret_cast<volatile unsigned long long*>(&peer::local_ctl(my_arena)->epoch[peer::kXEnqueueDone]) + 1 : 0;
   if (tid == 0) B200SSL_STAMP(p.dbg, crank, 0);
 
   // DA history: everything that does not depend on this batch is fetched up front (comatch.py:169-173)
@@ -659,6 +680,10 @@ __global__ void __launch_bounds__(kFusedThreads) comatch_rows_fused_kernel(const
       const_cast<float*>(f.prob_avg)[tid] = savg[tid];
     }
   }
+  // sharded bank: nobody may still be reading the rows this step overwrites -- every rank's smoothing pass of this
+  // step has published "reads done" (it finished about when ours did, a DA phase ago)
+  if (sharded && p.qf && tid < p.world && tid != p.rank)
+    peer::wait_flag(peer::flag_of(my_arena, peer::kXSmoothDone, tid), x_epoch, peer::local_ctl(my_arena));
   __syncthreads();
   if (tid == 0) B200SSL_STAMP(p.dbg, crank, 3);
 
@@ -689,20 +714,20 @@ __global__ void __launch_bounds__(kFusedThreads) comatch_rows_fused_kernel(const
     if (p.qf) {     // unlabeled-weak rows of this pass -> bank rows (ptr + row) % K     (comatch.py:187-196)
       for (int i = tid; i < nrows * vec_per_row; i += kFusedThreads) {
         const int rr = i / vec_per_row, v = i - rr * vec_per_row;
-        const long long g = (ptr + row0 + rr) % p.K;
+        const BankRow<T> b = bank_row<T>(p, (ptr + row0 + rr) % p.K);
         const uint4 val = ldg128(static_cast<const T*>(p.fu) + (row0 + rr) * p.D + v * epv);
-        *reinterpret_cast<uint4*>(static_cast<T*>(p.qf) + g * p.D + v * epv) = val;
+        *reinterpret_cast<uint4*>(b.qf + b.row * p.D + v * epv) = val;
       }
       for (int i = tid; i < cnt; i += kFusedThreads) {
         const int rr = i / C, c = i - rr * C;
-        const long long g = (ptr + row0 + rr) % p.K;
-        static_cast<T*>(p.qp)[g * C + c] = from_f32<T>(so[i]);
+        const BankRow<T> b = bank_row<T>(p, (ptr + row0 + rr) % p.K);
+        b.qp[b.row * C + c] = from_f32<T>(so[i]);
       }
       if (p.qpt)                                            // transposed copy: consecutive threads -> consecutive bank rows
         for (int i = tid; i < cnt; i += kFusedThreads) {
           const int c = i / nrows, rr = i - c * nrows;
-          const long long g = (ptr + row0 + rr) % p.K;
-          static_cast<T*>(p.qpt)[(size_t)c * p.K + g] = from_f32<T>(so[rr * C + c]);
+          const BankRow<T> b = bank_row<T>(p, (ptr + row0 + rr) % p.K);
+          b.qpt[(size_t)c * b.ld + b.row] = from_f32<T>(so[rr * C + c]);
         }
     }
   }
@@ -710,18 +735,19 @@ __global__ void __launch_bounds__(kFusedThreads) comatch_rows_fused_kernel(const
   if (p.qf) {       // labeled rows: [feats_x ; onehot(targets_x)], spread over the CTAs
     for (int i = crank * kFusedThreads + tid; i < n_x * vec_per_row; i += CL * kFusedThreads) {
       const int rr = i / vec_per_row, v = i - rr * vec_per_row;
-      const long long g = (ptr + f.rows + rr) % p.K;
+      const BankRow<T> b = bank_row<T>(p, (ptr + f.rows + rr) % p.K);
       const uint4 val = ldg128(static_cast<const T*>(p.fx) + (size_t)rr * p.D + v * epv);
-      *reinterpret_cast<uint4*>(static_cast<T*>(p.qf) + g * p.D + v * epv) = val;
+      *reinterpret_cast<uint4*>(b.qf + b.row * p.D + v * epv) = val;
     }
     for (int i = crank * kFusedThreads + tid; i < n_x * C; i += CL * kFusedThreads) {
       const int rr = i / C, c = i - rr * C;
-      const long long g = (ptr + f.rows + rr) % p.K;
+      const BankRow<T> b = bank_row<T>(p, (ptr + f.rows + rr) % p.K);
       const T val = from_f32<T>(c == (int)p.tx[rr] ? 1.f : 0.f);
-      static_cast<T*>(p.qp)[g * C + c] = val;
-      if (p.qpt) static_cast<T*>(p.qpt)[(size_t)c * p.K + g] = val;
+      b.qp[b.row * C + c] = val;
+      if (p.qpt) b.qpt[(size_t)c * b.ld + b.row] = val;
     }
   }
+  if (sharded) __threadfence_system();                      // remote rows are performed before the flag below is published
   if (tid == 0) B200SSL_STAMP(p.dbg, crank, 6);
   if (p.onehot_tail) {      // [probs_orig ; onehot(targets_x)] = the probability block of the enqueue (comatch.py:188-189)
     for (int i = crank * kFusedThreads + tid; i < n_x * C; i += CL * kFusedThreads) {
@@ -751,7 +777,11 @@ __global__ void __launch_bounds__(kFusedThreads) comatch_rows_fused_kernel(const
   if (crank == 0 && tid == 0) {
     p.state[0] = count;
     p.state[1] = (head + 1) % p.window;
-    if (p.qf) p.ptr_state[0] = (ptr + f.rows + p.n_x) % p.K;       // comatch.py:196
+    if (p.qf) p.ptr_state[0] = (ptr0 + p.advance) % p.K;           // comatch.py:196 (all ranks' blocks when sharded)
+  }
+  if (sharded && crank == 0) {                                // after the cluster barrier: every CTA's rows are out
+    if (tid < p.world && tid != p.rank) peer::st_release_sys(peer::flag_of(p.arenas[tid], peer::kXEnqueueDone, p.rank), x_epoch);
+    if (tid == 0) *reinterpret_cast<volatile unsigned long long*>(&peer::local_ctl(my_arena)->epoch[peer::kXEnqueueDone]) = x_epoch;
   }
   if (tid == 0) B200SSL_STAMP(p.dbg, crank, 7);
 }
@@ -947,7 +977,8 @@ extern "C" int b200ssl_comatch_rows_fused(const void* logits_u_w, const void* lo
                                           float* scores, int64_t* lbs, float* mask, void* grad_s0, float* out_scalars,
                                           void* queue_feats, void* queue_probs, void* queue_probs_t, const void* feats_u_w,
                                           const void* feats_x, const int64_t* targets_x, int64_t n_x, int32_t dim,
-                                          int64_t* ptr_state, int64_t bank_rows, int32_t onehot_tail, void* stream) {
+                                          int64_t* ptr_state, int64_t bank_rows, int32_t onehot_tail,
+                                          const b200ssl_bank_shards* shards, void* stream) {
   const char* fn = "b200ssl_comatch_rows_fused";
   if (int e = check_rows(fn, rows, classes, dtype)) return e;
   if (classes > 32) return fail(B200SSL_E_SHAPE, "%s: classes %d > 32 (use the separate kernels)", fn, classes);
@@ -973,7 +1004,18 @@ extern "C" int b200ssl_comatch_rows_fused(const void* logits_u_w, const void* lo
   p.tx = reinterpret_cast<const long long*>(targets_x); p.n_x = n_x; p.D = dim;
   p.ptr_state = reinterpret_cast<long long*>(ptr_state); p.K = bank_rows;
   p.onehot_tail = onehot_tail ? 1 : 0;
-  p.dbg = debug_timing_buffer();
+  p.advance = rows + n_x;
+  if (shards) {
+    if (shards->world < 2 || shards->world > 8 || shards->rank < 0 || shards->rank >= shards->world || !shards->arenas_dev ||
+        shards->shard_rows <= 0 || bank_rows != shards->shard_rows * shards->world || dtype != B200SSL_BF16)
+      return fail(B200SSL_E_ARG, "%s: bad shard table (2..8 ranks, bf16, bank_rows = world*shard_rows)", fn);
+    if ((rows + n_x) * shards->world > bank_rows) return fail(B200SSL_E_SHAPE, "%s: world*(rows + n_x) > bank_rows", fn);
+    p.arenas = reinterpret_cast<uint8_t* const*>(shards->arenas_dev); p.rank = shards->rank; p.world = shards->world;
+    p.shard_rows = shards->shard_rows; p.qf_off = shards->feats_offset; p.qp_off = shards->probs_offset; p.qpt_off = shards->probs_t_offset;
+    p.block_offset = (long long)shards->rank * (rows + n_x);
+    p.advance = (long long)shards->world * (rows + n_x);
+  }
+  p.dbg = debug_timing_buffer(PDL_ROWS);
   if (onehot_tail && (n_x > 0 && !targets_x)) return fail(B200SSL_E_NULL, "%s: onehot_tail needs targets_x", fn);
   long long cl = (rows + kFusedRows - 1) / kFusedRows;
   if (cl > kFusedMaxCluster) cl = kFusedMaxCluster;

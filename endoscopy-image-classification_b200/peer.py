@@ -11,7 +11,7 @@ The reference has no distributed code (``code/comatch.py:90-96`` keeps one bank 
 from __future__ import annotations
 
 import ctypes as C
-from typing import Dict, Sequence
+from typing import Dict, Optional, Sequence
 
 import torch
 
@@ -27,7 +27,7 @@ def _round_up(x: int, m: int) -> int:
 class PeerArena:
     """``regions``: ``{exchange_id: bytes_per_rank}`` -- the largest block one rank contributes to that exchange."""
 
-    def __init__(self, pg, device, regions: Dict[int, int]):
+    def __init__(self, pg, device, regions: Dict[int, int], named: Optional[Dict[str, int]] = None):
         import torch.distributed as dist
         self.pg, self.device = pg, torch.device(device)
         self.rank, self.world = dist.get_rank(pg), dist.get_world_size(pg)
@@ -39,6 +39,12 @@ class PeerArena:
             self.slot[x] = _round_up(int(regions[x]), 256)
             self.offset[x] = off
             off += 2 * self.world * self.slot[x]
+        # named areas (e.g. the bank shard itself): same offset in every arena, 256-byte aligned
+        self.named_offset: Dict[str, int] = {}
+        self.named_bytes: Dict[str, int] = dict(named or {})
+        for name, nbytes in self.named_bytes.items():
+            self.named_offset[name] = off
+            off += _round_up(int(nbytes), 256)
         self.bytes = off
         self._own = C.c_void_p()
         handle = (C.c_ubyte * 64)()
@@ -56,9 +62,27 @@ class PeerArena:
                 N.check(lib.b200ssl_peer_open((C.c_ubyte * 64).from_buffer_copy(h), C.byref(p)), f"peer_open(rank {r})")
                 self._mapped.append(p)
                 bases.append(p.value)
+        self.bases_host = (C.c_uint64 * self.world)(*bases)
         self.bases = torch.tensor(bases, dtype=torch.int64).to(self.device)
         dist.barrier(group=pg)                  # nobody pushes before every rank has mapped every arena
         torch.cuda.synchronize(self.device)
+
+    def tensor(self, name: str, shape: Sequence[int], dtype: torch.dtype) -> torch.Tensor:
+        """A torch tensor aliasing the named area of the OWN arena (zero-copy; valid until ``close``)."""
+        numel = 1
+        for d in shape:
+            numel *= int(d)
+        itemsize = torch.empty(0, dtype=dtype).element_size()
+        if numel * itemsize > self.named_bytes[name]:
+            raise ValueError(f"area {name!r} holds {self.named_bytes[name]} bytes, asked for {numel * itemsize}")
+        typestr = {torch.bfloat16: "<i2", torch.float32: "<f4", torch.float16: "<f2"}[dtype]
+
+        class _View:
+            __cuda_array_interface__ = {"shape": tuple(int(d) for d in shape), "typestr": typestr, "version": 2,
+                                        "data": (self._own.value + self.named_offset[name], False)}
+
+        t = torch.as_tensor(_View(), device=self.device)
+        return t.view(torch.bfloat16) if dtype == torch.bfloat16 else t
 
     def fits(self, exchange_id: int, nbytes: int) -> bool:
         return exchange_id in self.slot and nbytes <= self.slot[exchange_id]

@@ -60,7 +60,7 @@ enum b200ssl_error {
 B200SSL_API int b200ssl_version(void);
 B200SSL_API const char* b200ssl_last_error_string(void);
 /* Debug aid (tools/kernel_timeline.py): device buffer of uint64 [ctas * 16] that instrumented
- * kernels fill with clock64() stamps; NULL (default) disables it. */
+ * kernels fill with clock64() stamps (4 regions of 4096*16, one per kernel); NULL (default) disables it. */
 B200SSL_API void b200ssl_debug_set_timing_buffer(void* device_u64);
 /* bytes of scratch any single call below may need for the given problem */
 B200SSL_API size_t b200ssl_workspace_bytes(int64_t rows, int32_t classes, int64_t bank_rows);
@@ -115,6 +115,33 @@ B200SSL_API int b200ssl_comatch_da(const void* logits_u_w, int64_t rows, int32_t
                        float* da_ring, int32_t* da_state, int32_t window, float* prob_avg,
                        float* col_mean_out, void* workspace, size_t workspace_bytes, void* stream);
 
+/* ------------------------------------------------------------ SURVEY 8e ----
+ * Directly addressed, rank-sharded memory bank (one node, NVLink peer memory).
+ * Rank s keeps global bank rows [s*shard_rows, (s+1)*shard_rows) inside its peer
+ * arena (see the b200ssl_peer_* functions at the end of this file), every rank maps
+ * every arena.  K3 then reads ALL shards in place (TMA over NVLink for the remote
+ * ones) and the enqueue stores each row into the shard that owns it, so a sharded
+ * step has the launches of the single-GPU step and no separate exchange:
+ *   - b200ssl_bank_smooth_partial(shards != NULL) waits until every rank's enqueue
+ *     of the previous step is visible, then publishes "my reads are done";
+ *   - b200ssl_comatch_rows_fused(shards != NULL) waits for every rank's "reads
+ *     done" of this step before it writes rank `rank`'s block at global rows
+ *     [ptr + rank*n, ptr + (rank+1)*n) (n = rows + n_x, ptr advances by world*n),
+ *     then publishes "my rows are in".
+ * Both flags have a whole kernel (resp. the rest of the step) of slack, so the
+ * waits are normally free.  Requirements: bf16 bank, dim 64, classes <= 31,
+ * shard_rows a multiple of 8, world <= 8; all ranks run the same call sequence.
+ */
+typedef struct b200ssl_bank_shards {
+  int32_t world, rank;
+  int64_t shard_rows;             /* rows per shard; the global bank has world*shard_rows rows */
+  const uint64_t* arenas_host;    /* host array [world]: arena base addresses as mapped in this process */
+  void* const* arenas_dev;        /* the same table in device memory */
+  uint64_t feats_offset;          /* byte offsets, identical in every arena, of queue_feats [shard_rows, 64], */
+  uint64_t probs_offset;          /*   queue_probs [shard_rows, classes] and                                 */
+  uint64_t probs_t_offset;        /*   queue_probs_t [32, shard_rows] (row `classes` = ones)                 */
+} b200ssl_bank_shards;
+
 /* ---------------------------------------------------------------- K3 ----
  * Memory-smoothing partial sums against (a shard of) the bank.  Replaces the
  * two GEMMs + exp + row-sum of code/comatch.py:180-181 without materialising
@@ -138,8 +165,8 @@ B200SSL_API int b200ssl_comatch_da(const void* logits_u_w, int64_t rows, int32_t
 B200SSL_API int b200ssl_bank_smooth_partial(const void* feats_u_w, const void* queue_feats, const void* queue_probs,
                                 const void* queue_probs_t, int64_t rows, int64_t bank_rows, int32_t dim, int32_t classes,
                                 int32_t dtype, float temperature, float* rowsum, float* numer,
-                                int32_t rowsum_ld, int32_t numer_ld, void* workspace, size_t workspace_bytes,
-                                void* stream);
+                                int32_t rowsum_ld, int32_t numer_ld, const struct b200ssl_bank_shards* shards,
+                                void* workspace, size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------- K2b+K4+K7 ------
  * Per-row finalisation of the CoMatch pseudo-label and the focal soft-CE.
@@ -187,7 +214,8 @@ B200SSL_API int b200ssl_comatch_rows_fused(const void* logits_u_w, const void* l
                                float* scores, int64_t* lbs, float* mask, void* grad_s0, float* out_scalars,
                                void* queue_feats, void* queue_probs, void* queue_probs_t, const void* feats_u_w,
                                const void* feats_x, const int64_t* targets_x, int64_t n_x, int32_t dim,
-                               int64_t* ptr_state, int64_t bank_rows, int32_t onehot_tail, void* stream);
+                               int64_t* ptr_state, int64_t bank_rows, int32_t onehot_tail,
+                               const struct b200ssl_bank_shards* shards, void* stream);
 
 /* ---------------------------------------------------------------- K5 ----
  * Ring-buffer enqueue.  Replaces code/comatch.py:187-196: rows are

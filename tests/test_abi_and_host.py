@@ -76,8 +76,8 @@ def test_argument_validation_without_gpu(native):
     assert f(p, p, None, p, None, 16, 23, 0, 0.95, 1.0, 1, p, None, None, p256 + 4, wsb, None) == E_ALIGN
     assert f(p, p, None, p, None, 16, 23, 0, 0.95, 1.0, 1, p, None, None, p256, 64, None) == E_WS
     assert lib.b200ssl_comatch_da(p, 16, 23, 0, p, p, 100, p, None, p256, wsb, None) == E_ARG      # window > 64
-    assert lib.b200ssl_bank_smooth_partial(p, p, p, None, 16, 64, 12, 23, 0, 0.2, p, p, 0, 0, p256, wsb, None) == E_SHAPE  # dim % 8
-    assert lib.b200ssl_bank_smooth_partial(p, p, p, None, 16, 64, 64, 23, 0, 0.0, p, p, 0, 0, p256, wsb, None) == E_ARG   # tau
+    assert lib.b200ssl_bank_smooth_partial(p, p, p, None, 16, 64, 12, 23, 0, 0.2, p, p, 0, 0, None, p256, wsb, None) == E_SHAPE  # dim % 8
+    assert lib.b200ssl_bank_smooth_partial(p, p, p, None, 16, 64, 64, 23, 0, 0.0, p, p, 0, 0, None, p256, wsb, None) == E_ARG   # tau
     assert lib.b200ssl_bank_enqueue(p, p, None, p, p, p, p, 4, 4, 64, 23, 0, 100, None, 0, 0, 64, 0, 64, None) == E_ARG  # ptr >= K
     assert lib.b200ssl_bank_enqueue(p, p, None, p, p, p, p, 4, 4, 64, 23, 0, 0, None, 0, 0, 64, 32, 64, None) == E_ARG   # shard outside
     assert lib.b200ssl_bank_enqueue(p, p, None, p, p, p, p, 4, 4, 64, 23, 0, 0, None, 8, 0, 64, 0, 64, None) == E_ARG    # advance w/o state

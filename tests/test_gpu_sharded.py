@@ -99,7 +99,7 @@ def _worker(rank, world, port, out_dir, dtype_name, exchange):
     torch.save(dict(outs=outs, qf=head.queue_feats.float().cpu(), qp=head.queue_probs.float().cpu()),
                os.path.join(out_dir, f"rank{rank}.pt"))
     assert head.peer_timeouts() == 0
-    assert (head._arena is not None) == (exchange == "peer")
+    assert head.exchange == exchange and (head._arena is not None) == (exchange in ("peer", "direct"))
     head.close()
     dist.barrier()
     dist.destroy_process_group()
@@ -112,11 +112,13 @@ def _free_port():
 
 
 @pytest.mark.timeout(300)
-@pytest.mark.parametrize("exchange", ["peer", "collective"])
+@pytest.mark.parametrize("exchange", ["direct", "peer", "collective"])
 @pytest.mark.parametrize("dtype_name,tol", [("float32", 1e-5), ("bfloat16", 1e-2)])
 def test_two_gpu_sharded_bank(tmp_path, dtype_name, tol, exchange):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
+    if exchange == "direct" and dtype_name != "bfloat16":
+        pytest.skip("the directly addressed bank is the bf16 tensor-core layout")
     sys.path.insert(0, str(REPO))
     from oracle import ssl_oracle as O
     world = 2

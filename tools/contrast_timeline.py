@@ -23,7 +23,7 @@ for _ in range(3):
     head._k_contrast_bwd(f0, f1, dp, stats, one, probs_hl=dhl)
 torch.cuda.synchronize()
 def run(fn, names):
-    buf = torch.zeros(8192 * 16, dtype=torch.int64, device=dev)
+    buf = torch.zeros(4 * 4096 * 16, dtype=torch.int64, device=dev)   # one region per instrumented kernel
     N.lib().b200ssl_debug_set_timing_buffer(buf.data_ptr())
     fn(); torch.cuda.synchronize()
     N.lib().b200ssl_debug_set_timing_buffer(None)

@@ -21,7 +21,7 @@ fw = S.rownorm(torch.randn(rows, 64, generator=g)).to(torch.bfloat16).to(dev)
 for _ in range(3):
     head._k_smooth(fw)
 torch.cuda.synchronize()
-buf = torch.zeros(4096 * 16, dtype=torch.int64, device=dev)
+buf = torch.zeros(4 * 4096 * 16, dtype=torch.int64, device=dev)   # one region per instrumented kernel
 N.lib().b200ssl_debug_set_timing_buffer(buf.data_ptr())
 head._k_smooth(fw)
 torch.cuda.synchronize()

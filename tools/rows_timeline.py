@@ -16,7 +16,7 @@ rowsum, numer = head._k_smooth(fw)
 for _ in range(3):
     head._k_rows_fused(lw, ls0, rowsum, numer, (0, 0), fw, fx, tx, True, False)
 torch.cuda.synchronize()
-buf = torch.zeros(64 * 16, dtype=torch.int64, device=dev)
+buf = torch.zeros(4 * 4096 * 16, dtype=torch.int64, device=dev)   # one region per instrumented kernel
 N.lib().b200ssl_debug_set_timing_buffer(buf.data_ptr())
 head._k_rows_fused(lw, ls0, rowsum, numer, (0, 0), fw, fx, tx, True, False)
 torch.cuda.synchronize()
