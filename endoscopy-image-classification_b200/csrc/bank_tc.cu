@@ -79,7 +79,7 @@ namespace cg = cooperative_groups;
 constexpr int kBM = 128;          // queries per CTA  (UMMA M)
 constexpr int kBN = 128;          // keys per tile    (UMMA N of GEMM1 / K of GEMM2)
 constexpr int kCP = 32;           // classes + the "ones" column, padded (UMMA N of GEMM2)
-constexpr int kStages = 2;
+constexpr int kStages = 3;        // >= key tiles per CTA at the reference's sizes: every load is in flight at once (remote shards: NVLink latency)
 constexpr int kTcThreads = 320;   // warp 0 TMA + TMEM alloc, warp 1 MMA, warps 2..9 epilogue (2 per TMEM lane quarter)
 constexpr int kMaxCluster = 8;
 constexpr int kMaxSeg = 8;        // bank segments = shards of a rank-sharded bank (1 = the whole bank is local)
@@ -89,9 +89,9 @@ constexpr uint32_t kSubQp = kCP * 128;                  //  4 KB: [32][64] bf16
 constexpr uint32_t kTileQp = 2 * kSubQp;                //  8 KB
 constexpr uint32_t kSubP = kBM * 128;                   // 16 KB: [128][64] bf16
 constexpr uint32_t kTileP = 2 * kSubP;                  // 32 KB (re-used as the fp32 reduction tile at the end)
-constexpr uint32_t kSmemData = kTileA + kStages * (kTileQf + kTileQp) + kTileP;   // 96 KB
+constexpr uint32_t kSmemData = kTileA + kStages * (kTileQf + kTileQp) + kTileP;   // 120 KB
 constexpr uint32_t kTmemCols = 512;                     // S[0] 0..127, S[1] 128..255, numer 256..287
-constexpr size_t kSmemRequest = 120 * 1024;             // > half an SM: one CTA per SM (it owns all TMEM columns)
+constexpr size_t kSmemRequest = 124 * 1024;             // > half an SM: one CTA per SM (it owns all TMEM columns)
 constexpr int kRedLd = 36;                              // floats per row of the reduction tile (16-byte rows, 4-way bank spread)
 
 struct BankMaps {                 // one pair of tensor maps per shard; remote shards are peer-mapped NVLink addresses
@@ -112,8 +112,8 @@ struct SmoothTcParams {
   unsigned long long* dbg;
 };
 
-enum { BAR_A = 0, BAR_KV_FULL = 1, BAR_KV_EMPTY = 3, BAR_S_FULL = 5, BAR_S_EMPTY = 7, BAR_P_FULL = 9, BAR_P_EMPTY = 10,
-       BAR_ACC = 11, BAR_COUNT = 12 };
+enum { BAR_A = 0, BAR_KV_FULL = 1, BAR_KV_EMPTY = BAR_KV_FULL + kStages, BAR_S_FULL = BAR_KV_EMPTY + kStages,
+       BAR_S_EMPTY = BAR_S_FULL + 2, BAR_P_FULL = BAR_S_EMPTY + 2, BAR_P_EMPTY, BAR_ACC, BAR_COUNT };
 
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;
@@ -139,14 +139,23 @@ bank_smooth_tc_kernel(const __grid_constant__ CUtensorMap tm_f, const __grid_con
   const int cta = blockIdx.y * gridDim.x + blockIdx.x;
   pdl_launch_dependents();                                 // the next kernel may start its prologue
   const long long nktiles = (long long)p.nseg * p.tps;
-  const long long kt0 = nktiles * split / p.nsplit;                // balanced: every split owns >= 1 key tile
-  const int T = (int)(nktiles * (split + 1) / p.nsplit - kt0);
+  // Key tiles are dealt round-robin to the splits: tile u = split + t*nsplit of the enumeration that starts at the
+  // OWN shard, so every CTA begins with local tiles while its remote ones are already in flight.
+  const int T = (int)((nktiles - split + p.nsplit - 1) / p.nsplit);      // >= 1: nsplit <= nktiles
+  auto tile_of = [&](int t, int* seg) {                                  // -> first bank row of the tile inside its shard
+    const long long u = split + (long long)t * p.nsplit;
+    const int si = (int)(u / p.tps);
+    *seg = (p.rank + si) % p.nseg;
+    return (int)(u - (long long)si * p.tps) * kBN;
+  };
 
   if (threadIdx.x == 0) {
     tc::mbar_init(&bars[BAR_A], 1);
     for (int s = 0; s < kStages; ++s) {
       tc::mbar_init(&bars[BAR_KV_FULL + s], 1);
       tc::mbar_init(&bars[BAR_KV_EMPTY + s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
       tc::mbar_init(&bars[BAR_S_FULL + s], 1);
       tc::mbar_init(&bars[BAR_S_EMPTY + s], 256);
     }
@@ -159,8 +168,10 @@ bank_smooth_tc_kernel(const __grid_constant__ CUtensorMap tm_f, const __grid_con
   if (warp == 0) tc::tmem_alloc(tmem_slot, kTmemCols);
   if (warp == 1 && lane == 0) {
     tc::tma_prefetch_desc(&tm_f);
-    tc::tma_prefetch_desc(&maps.qf[(int)(kt0 / p.tps)]);
-    tc::tma_prefetch_desc(&maps.qpt[(int)(kt0 / p.tps)]);
+    int seg0;
+    tile_of(0, &seg0);
+    tc::tma_prefetch_desc(&maps.qf[seg0]);
+    tc::tma_prefetch_desc(&maps.qpt[seg0]);
   }
   tc::tcgen05_fence_before();
   __syncthreads();
@@ -186,8 +197,8 @@ bank_smooth_tc_kernel(const __grid_constant__ CUtensorMap tm_f, const __grid_con
       for (int t = 0; t < T; ++t) {
         const int s = t % kStages;
         if (t >= kStages) tc::mbar_wait(&bars[BAR_KV_EMPTY + s], ((t / kStages) - 1) & 1, abort_flag);
-        const int seg = (int)((kt0 + t) / p.tps);
-        const int key0 = (int)((kt0 + t) - (long long)seg * p.tps) * kBN;          // row inside the shard
+        int seg;
+        const int key0 = tile_of(t, &seg);
         tc::mbar_arrive_expect_tx(&bars[BAR_KV_FULL + s], kTileQf + kTileQp);
         tc::tma_load_2d(sQf + s * kTileQf, &maps.qf[seg], 0, key0, &bars[BAR_KV_FULL + s]);
         tc::tma_load_2d(sQp + s * kTileQp, &maps.qpt[seg], key0, 0, &bars[BAR_KV_FULL + s]);
@@ -289,15 +300,15 @@ bank_smooth_tc_kernel(const __grid_constant__ CUtensorMap tm_f, const __grid_con
   if (threadIdx.x == 0) B200SSL_STAMP(p.dbg, cta, 6);      // accumulator staged, TMEM released
   if (p.arenas && threadIdx.x == 0) {
     // every key tile of this CTA has been consumed.  The last CTA of the grid tells the peers that this rank no
-    // longer reads the shards of this step: their enqueue may overwrite rows.
+    // longer reads the shards of this step: their enqueue may overwrite rows.  Nothing this rank WROTE has to be
+    // visible with the flag, so plain (relaxed) system-scope stores do -- no fence on the way to the fold.
     uint8_t* mine = p.arenas[p.rank];
     peer::LocalCtl* ctl = peer::local_ctl(mine);
     const unsigned long long epoch = *reinterpret_cast<volatile unsigned long long*>(&ctl->epoch[peer::kXSmoothDone]) + 1;
-    __threadfence();
     if (atomicAdd(&ctl->done[peer::kXSmoothDone], 1u) == gridDim.x * gridDim.y - 1) {
       ctl->done[peer::kXSmoothDone] = 0;
       for (int s = 0; s < p.world; ++s)
-        if (s != p.rank) peer::st_release_sys(peer::flag_of(p.arenas[s], peer::kXSmoothDone, p.rank), epoch);
+        if (s != p.rank) peer::st_relaxed_sys(peer::flag_of(p.arenas[s], peer::kXSmoothDone, p.rank), epoch);
       *reinterpret_cast<volatile unsigned long long*>(&ctl->epoch[peer::kXSmoothDone]) = epoch;
     }
   }

@@ -689,7 +689,8 @@ __global__ void __launch_bounds__(kFusedThreads) comatch_rows_fused_kernel(const
 
   // ---- phase 2: finalise every row, store, enqueue ----
   float acc[2] = {0.f, 0.f};
-  const int vec_per_row = p.D * (int)sizeof(T) / 16, epv = 16 / (int)sizeof(T);
+  constexpr int epv = 16 / (int)sizeof(T);
+  const int vec_per_row = p.D * (int)sizeof(T) / 16;
   for (long long row0 = r_lo; row0 < r_hi; row0 += ROWS) {
     const int nrows = (int)min((long long)ROWS, r_hi - row0);
     const int cnt = nrows * C;
@@ -711,43 +712,92 @@ __global__ void __launch_bounds__(kFusedThreads) comatch_rows_fused_kernel(const
     tile_s2g(sw, f.probs + row0 * C, cnt);
     tile_s2g(so, f.probs_orig + row0 * C, cnt);
     tile_s2g(ss, static_cast<T*>(f.gs0) + row0 * C, cnt);
+    if (tid == 0) B200SSL_STAMP(p.dbg, crank, 8);
     if (p.qf) {     // unlabeled-weak rows of this pass -> bank rows (ptr + row) % K     (comatch.py:187-196)
-      for (int i = tid; i < nrows * vec_per_row; i += kFusedThreads) {
+      const long long g0 = (ptr + row0) % p.K;
+      const BankRow<T> b0 = bank_row<T>(p, g0);
+      // common case: the pass lands in one shard without wrapping, on a 16-byte boundary -> 128-bit stores only
+      // (they matter most when the shard is a peer's: NVLink writes are paid per transaction)
+      if (g0 + nrows <= p.K && b0.row + nrows <= b0.ld && b0.row % epv == 0 && nrows % epv == 0 && b0.ld % epv == 0) {
+        for (int i = tid; i < nrows * vec_per_row; i += kFusedThreads)
+          reinterpret_cast<uint4*>(b0.qf + b0.row * p.D)[i] = ldg128(static_cast<const T*>(p.fu) + row0 * p.D + (long long)i * epv);
+        for (int i = tid; i < cnt / epv; i += kFusedThreads)
+          reinterpret_cast<uint4*>(b0.qp + b0.row * C)[i] = pack16(*reinterpret_cast<const float(*)[epv]>(so + i * epv), T());
+        if (p.qpt) {
+          const int chunks = nrows / epv;
+          for (int i = tid; i < C * chunks; i += kFusedThreads) {
+            const int c = i / chunks, ch = i - c * chunks;
+            float v[epv];
+#pragma unroll
+            for (int k = 0; k < epv; ++k) v[k] = so[(ch * epv + k) * C + c];
+            *reinterpret_cast<uint4*>(b0.qpt + (size_t)c * b0.ld + b0.row + ch * epv) = pack16(v, T());
+          }
+        }
+      } else {
+        for (int i = tid; i < nrows * vec_per_row; i += kFusedThreads) {
+          const int rr = i / vec_per_row, v = i - rr * vec_per_row;
+          const BankRow<T> b = bank_row<T>(p, (ptr + row0 + rr) % p.K);
+          const uint4 val = ldg128(static_cast<const T*>(p.fu) + (row0 + rr) * p.D + v * epv);
+          *reinterpret_cast<uint4*>(b.qf + b.row * p.D + v * epv) = val;
+        }
+        for (int i = tid; i < cnt; i += kFusedThreads) {
+          const int rr = i / C, c = i - rr * C;
+          const BankRow<T> b = bank_row<T>(p, (ptr + row0 + rr) % p.K);
+          b.qp[b.row * C + c] = from_f32<T>(so[i]);
+        }
+        if (p.qpt)                                          // transposed copy: consecutive threads -> consecutive bank rows
+          for (int i = tid; i < cnt; i += kFusedThreads) {
+            const int c = i / nrows, rr = i - c * nrows;
+            const BankRow<T> b = bank_row<T>(p, (ptr + row0 + rr) % p.K);
+            b.qpt[(size_t)c * b.ld + b.row] = from_f32<T>(so[rr * C + c]);
+          }
+      }
+    }
+  }
+  if (tid == 0) B200SSL_STAMP(p.dbg, crank, 9);
+  const int n_x = (int)p.n_x;
+  if (p.qf && n_x > 0) {       // labeled rows: [feats_x ; onehot(targets_x)], spread over the CTAs
+    const long long g0 = (ptr + f.rows) % p.K;
+    const BankRow<T> b0 = bank_row<T>(p, g0);
+    const int i0 = crank * kFusedThreads + tid, istep = CL * kFusedThreads;
+    if (g0 + n_x <= p.K && b0.row + n_x <= b0.ld && b0.row % epv == 0 && n_x % epv == 0 && b0.ld % epv == 0) {   // 128-bit stores only
+      for (int i = i0; i < n_x * vec_per_row; i += istep)
+        reinterpret_cast<uint4*>(b0.qf + b0.row * p.D)[i] = ldg128(static_cast<const T*>(p.fx) + (size_t)i * epv);
+      for (int i = i0; i < n_x * C / epv; i += istep) {
+        float v[epv];
+#pragma unroll
+        for (int k = 0; k < epv; ++k) {
+          const int e = i * epv + k, rr = e / C;
+          v[k] = (e - rr * C == (int)p.tx[rr]) ? 1.f : 0.f;
+        }
+        reinterpret_cast<uint4*>(b0.qp + b0.row * C)[i] = pack16(v, T());
+      }
+      if (p.qpt) {
+        const int chunks = n_x / epv;
+        for (int i = i0; i < C * chunks; i += istep) {
+          const int c = i / chunks, ch = i - c * chunks;
+          float v[epv];
+#pragma unroll
+          for (int k = 0; k < epv; ++k) v[k] = (c == (int)p.tx[ch * epv + k]) ? 1.f : 0.f;
+          *reinterpret_cast<uint4*>(b0.qpt + (size_t)c * b0.ld + b0.row + ch * epv) = pack16(v, T());
+        }
+      }
+    } else {
+      for (int i = i0; i < n_x * vec_per_row; i += istep) {
         const int rr = i / vec_per_row, v = i - rr * vec_per_row;
-        const BankRow<T> b = bank_row<T>(p, (ptr + row0 + rr) % p.K);
-        const uint4 val = ldg128(static_cast<const T*>(p.fu) + (row0 + rr) * p.D + v * epv);
+        const BankRow<T> b = bank_row<T>(p, (ptr + f.rows + rr) % p.K);
+        const uint4 val = ldg128(static_cast<const T*>(p.fx) + (size_t)rr * p.D + v * epv);
         *reinterpret_cast<uint4*>(b.qf + b.row * p.D + v * epv) = val;
       }
-      for (int i = tid; i < cnt; i += kFusedThreads) {
+      for (int i = i0; i < n_x * C; i += istep) {
         const int rr = i / C, c = i - rr * C;
-        const BankRow<T> b = bank_row<T>(p, (ptr + row0 + rr) % p.K);
-        b.qp[b.row * C + c] = from_f32<T>(so[i]);
+        const BankRow<T> b = bank_row<T>(p, (ptr + f.rows + rr) % p.K);
+        const T val = from_f32<T>(c == (int)p.tx[rr] ? 1.f : 0.f);
+        b.qp[b.row * C + c] = val;
+        if (p.qpt) b.qpt[(size_t)c * b.ld + b.row] = val;
       }
-      if (p.qpt)                                            // transposed copy: consecutive threads -> consecutive bank rows
-        for (int i = tid; i < cnt; i += kFusedThreads) {
-          const int c = i / nrows, rr = i - c * nrows;
-          const BankRow<T> b = bank_row<T>(p, (ptr + row0 + rr) % p.K);
-          b.qpt[(size_t)c * b.ld + b.row] = from_f32<T>(so[rr * C + c]);
-        }
     }
   }
-  const int n_x = (int)p.n_x;
-  if (p.qf) {       // labeled rows: [feats_x ; onehot(targets_x)], spread over the CTAs
-    for (int i = crank * kFusedThreads + tid; i < n_x * vec_per_row; i += CL * kFusedThreads) {
-      const int rr = i / vec_per_row, v = i - rr * vec_per_row;
-      const BankRow<T> b = bank_row<T>(p, (ptr + f.rows + rr) % p.K);
-      const uint4 val = ldg128(static_cast<const T*>(p.fx) + (size_t)rr * p.D + v * epv);
-      *reinterpret_cast<uint4*>(b.qf + b.row * p.D + v * epv) = val;
-    }
-    for (int i = crank * kFusedThreads + tid; i < n_x * C; i += CL * kFusedThreads) {
-      const int rr = i / C, c = i - rr * C;
-      const BankRow<T> b = bank_row<T>(p, (ptr + f.rows + rr) % p.K);
-      const T val = from_f32<T>(c == (int)p.tx[rr] ? 1.f : 0.f);
-      b.qp[b.row * C + c] = val;
-      if (p.qpt) b.qpt[(size_t)c * b.ld + b.row] = val;
-    }
-  }
-  if (sharded) __threadfence_system();                      // remote rows are performed before the flag below is published
   if (tid == 0) B200SSL_STAMP(p.dbg, crank, 6);
   if (p.onehot_tail) {      // [probs_orig ; onehot(targets_x)] = the probability block of the enqueue (comatch.py:188-189)
     for (int i = crank * kFusedThreads + tid; i < n_x * C; i += CL * kFusedThreads) {
@@ -768,6 +818,9 @@ __global__ void __launch_bounds__(kFusedThreads) comatch_rows_fused_kernel(const
     for (int w = 0; w < kFusedWarps; ++w) t += s_part[tid][w];
     (CL > 1 ? cluster.map_shared_rank(sfin, 0) : sfin)[crank * 2 + tid] = t;
   }
+  // one system-scope fence per CTA (cumulative over the stores its threads ordered with the barrier above): the remote
+  // rows are performed before the flag below is published.  A fence in every thread costs ~5 us here.
+  if (sharded && tid == 32) __threadfence_system();
   if (CL > 1) cluster.sync(); else __syncthreads();          // last exchange: afterwards only rank 0 reads, and only its own smem
   if (crank == 0 && tid < 2) {
     float t = 0.f;
@@ -780,7 +833,8 @@ __global__ void __launch_bounds__(kFusedThreads) comatch_rows_fused_kernel(const
     if (p.qf) p.ptr_state[0] = (ptr0 + p.advance) % p.K;           // comatch.py:196 (all ranks' blocks when sharded)
   }
   if (sharded && crank == 0) {                                // after the cluster barrier: every CTA's rows are out
-    if (tid < p.world && tid != p.rank) peer::st_release_sys(peer::flag_of(p.arenas[tid], peer::kXEnqueueDone, p.rank), x_epoch);
+    // relaxed is enough: every CTA fenced at system scope before the cluster barrier that precedes this store
+    if (tid < p.world && tid != p.rank) peer::st_relaxed_sys(peer::flag_of(p.arenas[tid], peer::kXEnqueueDone, p.rank), x_epoch);
     if (tid == 0) *reinterpret_cast<volatile unsigned long long*>(&peer::local_ctl(my_arena)->epoch[peer::kXEnqueueDone]) = x_epoch;
   }
   if (tid == 0) B200SSL_STAMP(p.dbg, crank, 7);

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """In-kernel timeline of one sharded CoMatch step (directly addressed bank) on every rank:
 clock64() stamps of the smoothing, row, contrastive forward and backward kernels, printed by rank 0
-as microseconds relative to the first stamp of the step.
+as microseconds since each CTA's own first stamp (clock64 is per SM).
 
     python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 tools/sharded_timeline.py [exchange]
 """
@@ -55,19 +55,21 @@ step()
 torch.cuda.synchronize()
 N.lib().b200ssl_debug_set_timing_buffer(None)
 t = buf.cpu().numpy().reshape(4, -1, 16)
-t0 = min(int(r[r > 0].min()) for r in t if (r > 0).any())
 if rank == 0:
-    print(f"exchange={head.exchange} world={world}; us since the first stamp of the step (min / max over CTAs), 1.965 GHz")
+    # clock64() is per SM: only differences inside one CTA are meaningful
+    print(f"exchange={head.exchange} world={world}; us since the CTA's first stamp (min / median / max over CTAs), 1.965 GHz")
     for tag, name in enumerate(["smooth", "rows", "contrast fwd", "contrast bwd"]):
         r = t[tag]
-        r = r[r[:, 1] != 0] if tag != 1 else r[r[:, 0] != 0]
+        r = r[(r != 0).any(axis=1)]
         if not len(r):
             continue
+        first = np.where(r != 0, r, np.iinfo(np.int64).max).min(axis=1)
         print(f"  {name} ({len(r)} CTAs)")
         for slot in range(16):
-            col = r[:, slot][r[:, slot] != 0]
-            if len(col):
-                print(f"    stamp {slot:2d}: {(col.min() - t0) / 1965:8.2f} {(col.max() - t0) / 1965:8.2f}")
+            ok = r[:, slot] != 0
+            if ok.any():
+                d = (r[ok, slot] - first[ok]) / 1965.0
+                print(f"    stamp {slot:2d}: {d.min():7.2f} {np.median(d):7.2f} {d.max():7.2f}   (n={int(ok.sum())})")
 if world > 1:
     print(f"rank {rank}: peer timeouts {head.peer_timeouts()}")
     head.close()

@@ -16,13 +16,21 @@ from endoscopy_image_classification_b200.graphs import GraphedStep  # noqa: E402
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 500
 with_ema = os.environ.get("STEP_NO_EMA") is None
-dev = torch.device("cuda:0")
+rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", 0)))
+torch.cuda.set_device(dev)
+pg = None
+if world > 1:                      # under torchrun: the sharded bank (STEP_EXCHANGE = auto | direct | peer | collective)
+    import torch.distributed as dist
+    dist.init_process_group("nccl", device_id=dev)
+    pg = dist.group.WORLD
 B, MU, C, D, K = 64, 7, 23, 64, 2560
-g = torch.Generator().manual_seed(1)
+g = torch.Generator().manual_seed(1 + rank)
 keys = ["logits_u_w", "logits_u_s0", "feats_u_w", "feats_u_s0", "feats_u_s1", "feats_x", "targets_x"]
 protos = S.rownorm(torch.randn(C, D, generator=torch.Generator().manual_seed(99)))
 batch = {k: v.to(dev) for k, v in S.comatch_step_inputs(g, B, MU, D, C, protos, torch.bfloat16).items() if k in keys}
-head = CoMatchHead(C, D, K, 0.9, enqueue_mode="always", device=dev, dtype=torch.bfloat16)
+head = CoMatchHead(C, D, K, 0.9, enqueue_mode="always", device=dev, dtype=torch.bfloat16, process_group=pg,
+                   exchange=os.environ.get("STEP_EXCHANGE", "auto"))
 model = S.modelwemb_like("resnet50", C, D).to(dev)
 ema = ModelEMA(model, 0.999, device=dev)
 one = torch.ones((), device=dev)
@@ -45,6 +53,8 @@ gs = GraphedStep(step, batch, dev, warmup=3, on_replay=lambda: head.note_graph_r
 for _ in range(20):
     gs.replay()
 torch.cuda.synchronize()
+if world > 1:
+    dist.barrier()
 best = 1e9
 for rep in range(3):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -54,4 +64,20 @@ for rep in range(3):
     e1.record()
     torch.cuda.synchronize()
     best = min(best, 1e3 * e0.elapsed_time(e1) / n)
-print(f"mask={os.environ.get('B200SSL_PDL_MASK', 'default')} ema={with_ema}: {best:.2f} us/step")
+if world > 1:
+    tb = torch.tensor([best], device=dev, dtype=torch.float64)
+    dist.all_reduce(tb, op=dist.ReduceOp.MAX)
+    best = float(tb)
+if rank == 0:
+    print(f"world={world} exchange={head.exchange if world > 1 else '-'} mask={os.environ.get('B200SSL_PDL_MASK', 'default')} "
+          f"ema={with_ema}: {best:.2f} us/step")
+if world > 1:
+    assert head.peer_timeouts() == 0
+    gs.graph = gs.graph_host = None
+    del gs
+    import gc
+    gc.collect()
+    torch.cuda.synchronize()
+    head.close()
+    dist.barrier()
+    dist.destroy_process_group()
