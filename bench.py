@@ -216,7 +216,10 @@ def run_b200(args, wl, rank, world, local_rank):
 
     if wl["kind"] == "comatch":
         model = S.modelwemb_like(wl["arch"], C, D).to(dev)
-        head = CoMatchHead(C, D, wl["K"], wl["thr"], enqueue_mode="always", device=dev, dtype=dtype, process_group=pg,
+        # comatch.py:91: queue_size = queue_batch*(MU+1)*BATCH_SIZE.  Data parallel, BATCH_SIZE is the global batch, so the
+        # global bank grows with the rank count and every rank keeps a shard of the single-GPU size (weak scaling).
+        K_global = wl["K"] * world
+        head = CoMatchHead(C, D, K_global, wl["thr"], enqueue_mode="always", device=dev, dtype=dtype, process_group=pg,
                            exchange=args.exchange)
         protos = S.rownorm(torch.randn(C, D, generator=torch.Generator().manual_seed(99)))
         host = [S.comatch_step_inputs(g, B, MU, D, C, protos, dtype) for _ in range(4)]
@@ -238,7 +241,7 @@ def run_b200(args, wl, rank, world, local_rank):
     # with NCCL (its kernels are not counted).
     launches_per_step = (5 if wl["kind"] == "comatch" else 3)
     if world > 1 and head is not None:
-        launches_per_step += {"direct": 0, "peer": 4, "collective": 1}[head.exchange]
+        launches_per_step += {"replicated": 0, "direct": 0, "peer": 4, "collective": 1}[head.exchange]
     one = torch.ones((), dtype=torch.float32, device=dev)
 
     def step(batch):
@@ -361,9 +364,12 @@ def run_b200(args, wl, rank, world, local_rank):
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": wl["dtype"], "data": "synthetic",
                 "config": {"workload": wl["desc"], "global_batch_unlabeled": world * Bu, "per_gpu_unlabeled": Bu,
-                           "bank_rows_global": wl["K"], "bank_sharded_over": world, "parallelism": f"dp{world}",
+                           "bank_rows_global": wl["K"] * world, "bank_rows_per_rank": wl["K"], "bank_sharded_over": world, "parallelism": f"dp{world}",
                            "bank_exchange": (None if world == 1 or head is None else
-                                             {"direct": "shards in NVLink peer memory: K3 reads every shard in place (TMA over NVLink), "
+                                             {"replicated": "every rank keeps the whole ring in NVLink peer memory; the enqueue block is written "
+                                                            "through into every copy by the row kernel (the only exchange of a step); "
+                                                            "two epoch flags per step, no exchange launches",
+                                              "direct": "shards in NVLink peer memory: K3 reads every shard in place (TMA over NVLink), "
                                                         "the enqueue stores into the owning shard; two epoch flags per step, no "
                                                         "exchange launches",
                                               "peer": "own kernels over NVLink peer memory (csrc/peer.cu): all-gather, reduce-scatter, "
@@ -409,7 +415,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--exchange", default="auto", choices=["auto", "direct", "peer", "collective"],
+    ap.add_argument("--exchange", default="auto", choices=["auto", "replicated", "direct", "peer", "collective"],
                     help="sharded bank at N>1: directly addressed shards in NVLink peer memory (auto), own peer-memory "
                          "exchange kernels, or NCCL collectives")
     args = ap.parse_args()

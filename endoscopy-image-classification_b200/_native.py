@@ -40,7 +40,7 @@ class BankShards(C.Structure):
     """``b200ssl_bank_shards`` of include/b200ssl.h (directly addressed rank-sharded bank)."""
     _fields_ = [("world", C.c_int32), ("rank", C.c_int32), ("shard_rows", C.c_int64), ("arenas_host", C.c_void_p),
                 ("arenas_dev", C.c_void_p), ("feats_offset", C.c_uint64), ("probs_offset", C.c_uint64),
-                ("probs_t_offset", C.c_uint64)]
+                ("probs_t_offset", C.c_uint64), ("replicated", C.c_int32), ("reserved", C.c_int32)]
 
 
 SIGNATURES = {

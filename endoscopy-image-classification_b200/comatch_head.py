@@ -107,6 +107,7 @@ class CoMatchHead:
     force the three separate kernels (larger batches and sharded banks always use them).
     """
     FUSED_ROWS_MAX = 2048
+    REPLICATE_MAX_BYTES = 256 << 20      # 'auto' keeps a full copy of the ring per rank up to this size
 
     def __init__(self, num_classes: int, low_dim: int, queue_size: int, thr: float, *, alpha: float = 0.9,
                  temperature: float = 0.2, contrast_th: float = 0.8, gamma: float = 2.0, da_window: int = 32,
@@ -114,7 +115,7 @@ class CoMatchHead:
                  dtype: torch.dtype = torch.float32, process_group=None, exchange: str = "auto"):
         if enqueue_mode not in ("reference", "always"):
             raise ValueError(enqueue_mode)
-        if exchange not in ("auto", "direct", "peer", "collective"):
+        if exchange not in ("auto", "replicated", "direct", "peer", "collective"):
             raise ValueError(exchange)
         self.num_classes, self.low_dim, self.queue_size = int(num_classes), int(low_dim), int(queue_size)
         self.thr, self.alpha, self.temperature = float(thr), float(alpha), float(temperature)
@@ -128,13 +129,16 @@ class CoMatchHead:
             import torch.distributed as dist
             world, rank = dist.get_world_size(process_group), dist.get_rank(process_group)
         self.geom = ShardGeometry(self.queue_size, world, rank)
-        # How the sharded bank (world > 1) is reached:
+        # How the bank of a multi-rank job (world > 1) is kept:
+        #   'replicated' every rank keeps the whole ring in NVLink peer memory; the only exchange of a step is the
+        #                enqueue block, written through into every copy by the row kernel (two epoch flags per step).
+        #                K3 never leaves local memory -- the fastest layout while the ring fits (REPLICATE_MAX_BYTES)
         #   'direct'     the shards live in NVLink peer memory; K3 reads every shard in place and the enqueue stores
         #                into the owning shard -- same launches as one GPU, two epoch flags per step (bf16 banks with
         #                the tensor-core layout, <= 8 ranks of one node)
         #   'peer'       all-gather / reduce-scatter / all-gather by own kernels over peer memory (peer.py)
         #   'collective' the same three exchanges through torch.distributed (NCCL; gloo in the CPU tests)
-        #   'auto'       direct when the bank qualifies, else peer; collective on CPU
+        #   'auto'       replicated / direct when the bank qualifies (bf16 tensor-core layout), else peer; collective on CPU
         self._exchange_req = exchange
         self.exchange = "collective"
         self._arena = None
@@ -165,10 +169,14 @@ class CoMatchHead:
             self._arena = None
         direct_ok = (R > 1 and R <= 8 and on_gpu and dtype == torch.bfloat16 and C <= 31 and D == 64 and Ks % 8 == 0
                      and self.smoothing)
-        if req == "direct" and not direct_ok:
-            raise ValueError("exchange='direct' needs 2..8 CUDA ranks, a bf16 bank, low_dim 64, <= 31 classes, shard rows % 8 == 0")
-        self.exchange = ("direct" if direct_ok else "peer" if on_gpu else "collective") if req == "auto" else req
-        if R > 1 and self.exchange == "direct":
+        if req in ("direct", "replicated") and not direct_ok:
+            raise ValueError(f"exchange={req!r} needs 2..8 CUDA ranks, a bf16 bank, low_dim 64, <= 31 classes, shard rows % 8 == 0")
+        small = self.queue_size * (D + C + 32) * 2 <= self.REPLICATE_MAX_BYTES
+        self.exchange = ((("replicated" if small else "direct") if direct_ok else "peer" if on_gpu else "collective")
+                         if req == "auto" else req)
+        if R > 1 and self.exchange in ("direct", "replicated"):
+            rep = self.exchange == "replicated"
+            Ks = self.queue_size if rep else Ks                      # rows held by this rank
             import ctypes
             import torch.distributed as dist
             from .peer import PeerArena
@@ -178,7 +186,7 @@ class CoMatchHead:
             self.queue_probs_t = a.tensor("qpt", (32, Ks), dtype)
             self.queue_probs_t[C].fill_(1.0)
             self._shards = N.BankShards(R, self.geom.rank, Ks, ctypes.addressof(a.bases_host), a.bases.data_ptr(),
-                                        a.named_offset["qf"], a.named_offset["qp"], a.named_offset["qpt"])
+                                        a.named_offset["qf"], a.named_offset["qp"], a.named_offset["qpt"], 1 if rep else 0, 0)
             torch.cuda.synchronize(self.device)
             dist.barrier(group=self.pg)          # the ones row of every shard is in place before any peer reads it
             return
@@ -277,9 +285,9 @@ class CoMatchHead:
         fused = self.fuse_rows and C <= 32 and rows <= self.FUSED_ROWS_MAX
         rowsum = numer = None
         lds = (0, 0)                                                         # (rowsum_ld, numer_ld): 0 = dense
-        if R == 1 or self.exchange == "direct":
+        if R == 1 or self._shards is not None:
             if R > 1 and not fused:
-                raise RuntimeError(f"exchange='direct' needs the fused row kernel (<= {self.FUSED_ROWS_MAX} unlabeled rows per "
+                raise RuntimeError(f"exchange={self.exchange!r} needs the fused row kernel (<= {self.FUSED_ROWS_MAX} unlabeled rows per "
                                    "rank, fuse_rows=True); build the head with exchange='peer' for larger batches")
             if not fused:
                 self._k_da(lw)                                               # K2

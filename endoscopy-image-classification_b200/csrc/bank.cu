@@ -210,8 +210,10 @@ extern "C" int b200ssl_bank_smooth_partial(const void* feats_u_w, const void* qu
   if (shards) {
     // directly addressed sharded bank: tensor-core path only
     if (shards->world < 2 || shards->world > 8 || shards->rank < 0 || shards->rank >= shards->world || !shards->arenas_host ||
-        !shards->arenas_dev || shards->shard_rows <= 0 || shards->shard_rows % 8 || bank_rows != shards->shard_rows * shards->world)
-      return fail(B200SSL_E_ARG, "%s: bad shard table (2..8 ranks, shard_rows a multiple of 8, bank_rows = world*shard_rows)", fn);
+        !shards->arenas_dev || shards->shard_rows <= 0 || shards->shard_rows % 8 ||
+        bank_rows != shards->shard_rows * (shards->replicated ? 1 : shards->world))
+      return fail(B200SSL_E_ARG, "%s: bad shard table (2..8 ranks, shard_rows a multiple of 8, bank_rows = world*shard_rows or, "
+                                 "replicated, = shard_rows)", fn);
     if (dtype != B200SSL_BF16 || dim != 64 || classes > 31 || classes < 2 || (reinterpret_cast<uintptr_t>(feats_u_w) & 15u) ||
         ((shards->feats_offset | shards->probs_t_offset) & 127u))
       return fail(B200SSL_E_DTYPE, "%s: the directly addressed sharded bank needs bf16, dim 64, classes <= 31, aligned rows", fn);

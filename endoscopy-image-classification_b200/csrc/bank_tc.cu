@@ -103,7 +103,7 @@ struct SmoothTcParams {
   long long rows, rows_pad;
   int nseg, tps;                  // key tiles are enumerated shard by shard: tile kt -> (kt / tps, kt % tps)
   uint8_t* const* arenas;         // non-NULL: directly addressed sharded bank (peer.cuh flags / epochs)
-  int rank, world;
+  int rank, world, seg_first;     // seg_first: segment the tile enumeration starts at (the own shard)
   int C, W;                       // W = round_up(C + 1, 4): [numer 0..C-1, rowsum] per row of a partial
   int nsplit, cluster, nouter;    // nsplit = cluster * nouter CTAs share one row tile
   float scale;                    // log2(e) / temperature
@@ -145,7 +145,7 @@ bank_smooth_tc_kernel(const __grid_constant__ CUtensorMap tm_f, const __grid_con
   auto tile_of = [&](int t, int* seg) {                                  // -> first bank row of the tile inside its shard
     const long long u = split + (long long)t * p.nsplit;
     const int si = (int)(u / p.tps);
-    *seg = (p.rank + si) % p.nseg;
+    *seg = (p.seg_first + si) % p.nseg;
     return (int)(u - (long long)si * p.tps) * kBN;
   };
 
@@ -413,11 +413,13 @@ int bank_smooth_tc(const void* feats, const void* queue_feats, const void* queue
                    int numer_ld, const b200ssl_bank_shards* sh, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
   const char* fn = "b200ssl_bank_smooth_partial[tcgen05]";
   SmoothTcParams p{};
-  const long long seg_rows = sh ? sh->shard_rows : bank_rows;
-  p.nseg = sh ? sh->world : 1;
+  const bool direct = sh && !sh->replicated;               // shards read in place; a replicated ring is one local segment
+  const long long seg_rows = direct ? sh->shard_rows : bank_rows;
+  p.nseg = direct ? sh->world : 1;
   p.tps = (int)((seg_rows + kBN - 1) / kBN);
   if (sh) {
     p.arenas = reinterpret_cast<uint8_t* const*>(sh->arenas_dev); p.rank = sh->rank; p.world = sh->world;
+    p.seg_first = direct ? sh->rank : 0;
   }
   p.rows = rows; p.C = classes; p.W = (1 + classes + 3) & ~3;
   p.scale = (float)(1.4426950408889634 / (double)temperature);
@@ -435,7 +437,7 @@ int bank_smooth_tc(const void* feats, const void* queue_feats, const void* queue
   BankMaps maps;
   if (int e = tc::make_tmap_bf16_2d(&tm_f, feats, (uint64_t)rows, 64, 128, kBM, 64)) return e;
   for (int s = 0; s < kMaxSeg; ++s) {
-    const int src = s < p.nseg ? s : 0;                    // unused entries repeat segment 0 (never dereferenced)
+    const int src = direct ? (s < p.nseg ? s : 0) : (sh ? sh->rank : 0);   // unused entries repeat a valid one (never dereferenced)
     const void* qf = sh ? reinterpret_cast<const void*>(sh->arenas_host[src] + sh->feats_offset) : queue_feats;
     const void* qpt = sh ? reinterpret_cast<const void*>(sh->arenas_host[src] + sh->probs_t_offset) : queue_probs_t;
     if (int e = tc::make_tmap_bf16_2d(&maps.qf[s], qf, (uint64_t)seg_rows, 64, 128, kBN, 64)) return e;

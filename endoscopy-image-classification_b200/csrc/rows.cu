@@ -564,14 +564,19 @@ struct FusedParams {
   // directly addressed sharded bank (arenas != nullptr): global row g lives in arena g / shard_rows
   uint8_t* const* arenas; int rank, world; long long shard_rows; size_t qf_off, qp_off, qpt_off;
   long long block_offset, advance;   // this rank's block starts at ptr + block_offset; the pointer advances by `advance`
+  int ndst;                          // 1, or world when every rank keeps a full copy of the ring (write-through enqueue)
 };
 
 // Where global bank row g lives: the local bank, or the shard of the rank that owns it (peer-mapped NVLink memory).
 template <typename T>
 struct BankRow { T* qf; T* qp; T* qpt; long long row, ld; };
 template <typename T>
-__device__ __forceinline__ BankRow<T> bank_row(const FusedParams& p, long long g) {
+__device__ __forceinline__ BankRow<T> bank_row(const FusedParams& p, long long g, int d = 0) {
   if (!p.arenas) return {static_cast<T*>(p.qf), static_cast<T*>(p.qp), static_cast<T*>(p.qpt), g, p.K};
+  if (p.ndst > 1) {                                           // d-th copy of the whole ring, the own one first
+    uint8_t* base = p.arenas[(p.rank + d) % p.world];
+    return {reinterpret_cast<T*>(base + p.qf_off), reinterpret_cast<T*>(base + p.qp_off), reinterpret_cast<T*>(base + p.qpt_off), g, p.K};
+  }
   const int s = (int)(g / p.shard_rows);
   uint8_t* base = p.arenas[s];
   return {reinterpret_cast<T*>(base + p.qf_off), reinterpret_cast<T*>(base + p.qp_off), reinterpret_cast<T*>(base + p.qpt_off),
@@ -715,7 +720,8 @@ __global__ void __launch_bounds__(kFusedThreads) comatch_rows_fused_kernel(const
     if (tid == 0) B200SSL_STAMP(p.dbg, crank, 8);
     if (p.qf) {     // unlabeled-weak rows of this pass -> bank rows (ptr + row) % K     (comatch.py:187-196)
       const long long g0 = (ptr + row0) % p.K;
-      const BankRow<T> b0 = bank_row<T>(p, g0);
+      for (int d = 0; d < p.ndst; ++d) {
+      const BankRow<T> b0 = bank_row<T>(p, g0, d);
       // common case: the pass lands in one shard without wrapping, on a 16-byte boundary -> 128-bit stores only
       // (they matter most when the shard is a peer's: NVLink writes are paid per transaction)
       if (g0 + nrows <= p.K && b0.row + nrows <= b0.ld && b0.row % epv == 0 && nrows % epv == 0 && b0.ld % epv == 0) {
@@ -736,21 +742,22 @@ __global__ void __launch_bounds__(kFusedThreads) comatch_rows_fused_kernel(const
       } else {
         for (int i = tid; i < nrows * vec_per_row; i += kFusedThreads) {
           const int rr = i / vec_per_row, v = i - rr * vec_per_row;
-          const BankRow<T> b = bank_row<T>(p, (ptr + row0 + rr) % p.K);
+          const BankRow<T> b = bank_row<T>(p, (ptr + row0 + rr) % p.K, d);
           const uint4 val = ldg128(static_cast<const T*>(p.fu) + (row0 + rr) * p.D + v * epv);
           *reinterpret_cast<uint4*>(b.qf + b.row * p.D + v * epv) = val;
         }
         for (int i = tid; i < cnt; i += kFusedThreads) {
           const int rr = i / C, c = i - rr * C;
-          const BankRow<T> b = bank_row<T>(p, (ptr + row0 + rr) % p.K);
+          const BankRow<T> b = bank_row<T>(p, (ptr + row0 + rr) % p.K, d);
           b.qp[b.row * C + c] = from_f32<T>(so[i]);
         }
         if (p.qpt)                                          // transposed copy: consecutive threads -> consecutive bank rows
           for (int i = tid; i < cnt; i += kFusedThreads) {
             const int c = i / nrows, rr = i - c * nrows;
-            const BankRow<T> b = bank_row<T>(p, (ptr + row0 + rr) % p.K);
+            const BankRow<T> b = bank_row<T>(p, (ptr + row0 + rr) % p.K, d);
             b.qpt[(size_t)c * b.ld + b.row] = from_f32<T>(so[rr * C + c]);
           }
+      }
       }
     }
   }
@@ -758,8 +765,9 @@ __global__ void __launch_bounds__(kFusedThreads) comatch_rows_fused_kernel(const
   const int n_x = (int)p.n_x;
   if (p.qf && n_x > 0) {       // labeled rows: [feats_x ; onehot(targets_x)], spread over the CTAs
     const long long g0 = (ptr + f.rows) % p.K;
-    const BankRow<T> b0 = bank_row<T>(p, g0);
     const int i0 = crank * kFusedThreads + tid, istep = CL * kFusedThreads;
+    for (int d = 0; d < p.ndst; ++d) {
+    const BankRow<T> b0 = bank_row<T>(p, g0, d);
     if (g0 + n_x <= p.K && b0.row + n_x <= b0.ld && b0.row % epv == 0 && n_x % epv == 0 && b0.ld % epv == 0) {   // 128-bit stores only
       for (int i = i0; i < n_x * vec_per_row; i += istep)
         reinterpret_cast<uint4*>(b0.qf + b0.row * p.D)[i] = ldg128(static_cast<const T*>(p.fx) + (size_t)i * epv);
@@ -785,17 +793,18 @@ __global__ void __launch_bounds__(kFusedThreads) comatch_rows_fused_kernel(const
     } else {
       for (int i = i0; i < n_x * vec_per_row; i += istep) {
         const int rr = i / vec_per_row, v = i - rr * vec_per_row;
-        const BankRow<T> b = bank_row<T>(p, (ptr + f.rows + rr) % p.K);
+        const BankRow<T> b = bank_row<T>(p, (ptr + f.rows + rr) % p.K, d);
         const uint4 val = ldg128(static_cast<const T*>(p.fx) + (size_t)rr * p.D + v * epv);
         *reinterpret_cast<uint4*>(b.qf + b.row * p.D + v * epv) = val;
       }
       for (int i = i0; i < n_x * C; i += istep) {
         const int rr = i / C, c = i - rr * C;
-        const BankRow<T> b = bank_row<T>(p, (ptr + f.rows + rr) % p.K);
+        const BankRow<T> b = bank_row<T>(p, (ptr + f.rows + rr) % p.K, d);
         const T val = from_f32<T>(c == (int)p.tx[rr] ? 1.f : 0.f);
         b.qp[b.row * C + c] = val;
         if (p.qpt) b.qpt[(size_t)c * b.ld + b.row] = val;
       }
+    }
     }
   }
   if (tid == 0) B200SSL_STAMP(p.dbg, crank, 6);
@@ -1059,15 +1068,18 @@ extern "C" int b200ssl_comatch_rows_fused(const void* logits_u_w, const void* lo
   p.ptr_state = reinterpret_cast<long long*>(ptr_state); p.K = bank_rows;
   p.onehot_tail = onehot_tail ? 1 : 0;
   p.advance = rows + n_x;
+  p.ndst = 1;
   if (shards) {
     if (shards->world < 2 || shards->world > 8 || shards->rank < 0 || shards->rank >= shards->world || !shards->arenas_dev ||
-        shards->shard_rows <= 0 || bank_rows != shards->shard_rows * shards->world || dtype != B200SSL_BF16)
-      return fail(B200SSL_E_ARG, "%s: bad shard table (2..8 ranks, bf16, bank_rows = world*shard_rows)", fn);
+        shards->shard_rows <= 0 || bank_rows != shards->shard_rows * (shards->replicated ? 1 : shards->world) ||
+        dtype != B200SSL_BF16)
+      return fail(B200SSL_E_ARG, "%s: bad shard table (2..8 ranks, bf16, bank_rows = world*shard_rows or, replicated, = shard_rows)", fn);
     if ((rows + n_x) * shards->world > bank_rows) return fail(B200SSL_E_SHAPE, "%s: world*(rows + n_x) > bank_rows", fn);
     p.arenas = reinterpret_cast<uint8_t* const*>(shards->arenas_dev); p.rank = shards->rank; p.world = shards->world;
     p.shard_rows = shards->shard_rows; p.qf_off = shards->feats_offset; p.qp_off = shards->probs_offset; p.qpt_off = shards->probs_t_offset;
     p.block_offset = (long long)shards->rank * (rows + n_x);
     p.advance = (long long)shards->world * (rows + n_x);
+    p.ndst = shards->replicated ? shards->world : 1;
   }
   p.dbg = debug_timing_buffer(PDL_ROWS);
   if (onehot_tail && (n_x > 0 && !targets_x)) return fail(B200SSL_E_NULL, "%s: onehot_tail needs targets_x", fn);

@@ -129,7 +129,9 @@ B200SSL_API int b200ssl_comatch_da(const void* logits_u_w, int64_t rows, int32_t
  *     [ptr + rank*n, ptr + (rank+1)*n) (n = rows + n_x, ptr advances by world*n),
  *     then publishes "my rows are in".
  * Both flags have a whole kernel (resp. the rest of the step) of slack, so the
- * waits are normally free.  Requirements: bf16 bank, dim 64, classes <= 31,
+ * waits are normally free.  With `replicated` set the same protocol keeps one full
+ * copy of the ring per rank instead of shards: remote traffic is then only the
+ * enqueued rows (written through to every copy), K3 never leaves local memory.  Requirements: bf16 bank, dim 64, classes <= 31,
  * shard_rows a multiple of 8, world <= 8; all ranks run the same call sequence.
  */
 typedef struct b200ssl_bank_shards {
@@ -140,6 +142,8 @@ typedef struct b200ssl_bank_shards {
   uint64_t feats_offset;          /* byte offsets, identical in every arena, of queue_feats [shard_rows, 64], */
   uint64_t probs_offset;          /*   queue_probs [shard_rows, classes] and                                 */
   uint64_t probs_t_offset;        /*   queue_probs_t [32, shard_rows] (row `classes` = ones)                 */
+  int32_t replicated;             /* != 0: every arena holds the WHOLE ring (shard_rows = all bank rows): K3 reads only  */
+  int32_t reserved;               /*   the local copy and the enqueue writes this rank's rows into every rank's copy      */
 } b200ssl_bank_shards;
 
 /* ---------------------------------------------------------------- K3 ----

@@ -99,7 +99,7 @@ def _worker(rank, world, port, out_dir, dtype_name, exchange):
     torch.save(dict(outs=outs, qf=head.queue_feats.float().cpu(), qp=head.queue_probs.float().cpu()),
                os.path.join(out_dir, f"rank{rank}.pt"))
     assert head.peer_timeouts() == 0
-    assert head.exchange == exchange and (head._arena is not None) == (exchange in ("peer", "direct"))
+    assert head.exchange == exchange and (head._arena is not None) == (exchange != "collective")
     head.close()
     dist.barrier()
     dist.destroy_process_group()
@@ -112,13 +112,13 @@ def _free_port():
 
 
 @pytest.mark.timeout(300)
-@pytest.mark.parametrize("exchange", ["direct", "peer", "collective"])
+@pytest.mark.parametrize("exchange", ["replicated", "direct", "peer", "collective"])
 @pytest.mark.parametrize("dtype_name,tol", [("float32", 1e-5), ("bfloat16", 1e-2)])
 def test_two_gpu_sharded_bank(tmp_path, dtype_name, tol, exchange):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
-    if exchange == "direct" and dtype_name != "bfloat16":
-        pytest.skip("the directly addressed bank is the bf16 tensor-core layout")
+    if exchange in ("direct", "replicated") and dtype_name != "bfloat16":
+        pytest.skip("the peer-memory resident bank is the bf16 tensor-core layout")
     sys.path.insert(0, str(REPO))
     from oracle import ssl_oracle as O
     world = 2
@@ -143,7 +143,9 @@ def test_two_gpu_sharded_bank(tmp_path, dtype_name, tol, exchange):
             gref = 0.5 * ref[r]["grad_feats_s0"]
             assert float((got["g_f0"] - gref).abs().max() / gref.abs().max()) < tol
             assert got["ptr"] == got["dev_ptr"] == state.queue_ptr == ((step + 1) * world * n) % K
-    bank_f = torch.cat([res[r]["qf"] for r in range(world)])
-    assert torch.equal(bank_f, state.queue_feats)
-    bank_p = torch.cat([res[r]["qp"] for r in range(world)])
-    assert float((bank_p - state.queue_probs).abs().max()) < tol
+    # shards concatenate to the oracle's ring; with exchange='replicated' every rank holds the whole ring
+    banks = ([(res[r]["qf"], res[r]["qp"]) for r in range(world)] if exchange == "replicated" else
+             [(torch.cat([res[r]["qf"] for r in range(world)]), torch.cat([res[r]["qp"] for r in range(world)]))])
+    for bank_f, bank_p in banks:
+        assert torch.equal(bank_f, state.queue_feats)
+        assert float((bank_p - state.queue_probs).abs().max()) < tol

@@ -29,7 +29,7 @@ g = torch.Generator().manual_seed(1 + rank)
 keys = ["logits_u_w", "logits_u_s0", "feats_u_w", "feats_u_s0", "feats_u_s1", "feats_x", "targets_x"]
 protos = S.rownorm(torch.randn(C, D, generator=torch.Generator().manual_seed(99)))
 batch = {k: v.to(dev) for k, v in S.comatch_step_inputs(g, B, MU, D, C, protos, torch.bfloat16).items() if k in keys}
-head = CoMatchHead(C, D, K, 0.9, enqueue_mode="always", device=dev, dtype=torch.bfloat16, process_group=pg,
+head = CoMatchHead(C, D, K * world, 0.9, enqueue_mode="always", device=dev, dtype=torch.bfloat16, process_group=pg,
                    exchange=os.environ.get("STEP_EXCHANGE", "auto"))
 model = S.modelwemb_like("resnet50", C, D).to(dev)
 ema = ModelEMA(model, 0.999, device=dev)
