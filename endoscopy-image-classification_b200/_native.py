@@ -73,6 +73,7 @@ SIGNATURES = {
     "b200ssl_peer_close": (_i32, [_vp]),
     "b200ssl_peer_free": (_i32, [_vp]),
     "b200ssl_peer_timeouts": (_i32, [_vp, _vp]),
+    "b200ssl_bank_enqueue_peer": (_i32, [_vp, _vp, _vp, _vp, _i64, _i64, _i32, _i32, _i32, _vp, _vp, _vp]),
     "b200ssl_peer_all_gather": (_i32, [_vp, _sz, _vp, _sz, _vp, _vp, _sz, _sz, _i32, _i32, _i32, _vp]),
     "b200ssl_peer_reduce_scatter_f32": (_i32, [_vp, _vp, _i64, _vp, _sz, _sz, _i32, _i32, _i32, _vp]),
 }

@@ -168,9 +168,10 @@ class CoMatchHead:
             self._arena.close()
             self._arena = None
         direct_ok = (R > 1 and R <= 8 and on_gpu and dtype == torch.bfloat16 and C <= 31 and D == 64 and Ks % 8 == 0
-                     and self.smoothing)
+                     and self.smoothing and self.enqueue_mode == "always")    # the epoch flags need one enqueue per step
         if req in ("direct", "replicated") and not direct_ok:
-            raise ValueError(f"exchange={req!r} needs 2..8 CUDA ranks, a bf16 bank, low_dim 64, <= 31 classes, shard rows % 8 == 0")
+            raise ValueError(f"exchange={req!r} needs 2..8 CUDA ranks, a bf16 bank, low_dim 64, <= 31 classes, shard rows % 8 == 0, "
+                             "smoothing and enqueue_mode='always'")
         small = self.queue_size * (D + C + 32) * 2 <= self.REPLICATE_MAX_BYTES
         self.exchange = ((("replicated" if small else "direct") if direct_ok else "peer" if on_gpu else "collective")
                          if req == "auto" else req)
@@ -283,7 +284,7 @@ class CoMatchHead:
         n = rows + n_x
         do_enqueue = geom.should_enqueue(n, self.enqueue_mode)
         fused = self.fuse_rows and C <= 32 and rows <= self.FUSED_ROWS_MAX
-        rowsum = numer = None
+        rowsum = numer = join_side = None
         lds = (0, 0)                                                         # (rowsum_ld, numer_ld): 0 = dense
         if R == 1 or self._shards is not None:
             if R > 1 and not fused:
@@ -293,8 +294,17 @@ class CoMatchHead:
                 self._k_da(lw)                                               # K2
             if self.smoothing:                                               # K3, bank as of *before* this step's enqueue
                 rowsum, numer = self._k_smooth(fw)
+            multi = self._shards is not None
             if fused:                                                        # ONE cluster launch: DA + finalize + enqueue
-                out = self._k_rows_fused(lw, ls0, rowsum, numer, lds, fw, fx, tx, do_enqueue, False)
+                out = self._k_rows_fused(lw, ls0, rowsum, numer, lds, fw, fx, tx, do_enqueue and not multi, False)
+                if multi:
+                    # peer-memory bank: this rank's rows go out (over NVLink) in a wide launch on a side stream --
+                    # nothing of this step depends on them; the stream is joined after the contrastive forward
+                    side, cur = self._side_stream(), torch.cuda.current_stream(self.device)
+                    side.wait_stream(cur)
+                    with torch.cuda.stream(side):
+                        self._k_enqueue_peer(fw, fx, out["probs_orig"], tx)
+                    join_side = side
             else:
                 out = self._k_finalize(lw, ls0, rowsum, numer, lds)          # K2b + K4 + K7
                 if do_enqueue:
@@ -328,6 +338,8 @@ class CoMatchHead:
             self._pristine = False
         stats, loss_c = self._k_contrast_fwd(fs0, fs1, out["probs"], out["scalars"], lambda_u, lambda_c,
                                              probs_hl=out["probs_hl"])  # K6
+        if join_side is not None:
+            torch.cuda.current_stream(self.device).wait_stream(join_side)
         self.last = {"probs_orig": out["probs_orig"], "rowsum": rowsum, "numer": numer, "probs": out["probs"],
                      "mask": out["mask"], "lbs": out["lbs"], "scores": out["scores"]}
         out["stats"] = stats
@@ -449,9 +461,21 @@ class CoMatchHead:
             out["lbs"].data_ptr(), out["mask"].data_ptr(), out["grad_s0"].data_ptr(), out["scalars"].data_ptr(),
             self.queue_feats.data_ptr() if enq else None, self.queue_probs.data_ptr() if enq else None,
             N.ptr(self.queue_probs_t) if enq else None, fw.data_ptr(), fx.data_ptr(), tx.data_ptr(), fx.shape[0],
-            self.low_dim, self.ptr_state.data_ptr(), self.queue_size, 1 if onehot_tail else 0, C_byref(self._shards),
+            self.low_dim, self.ptr_state.data_ptr(), self.queue_size, 1 if onehot_tail else 0, None,
             N.stream_ptr(self.device)), "comatch_rows_fused")
         return out
+
+    def _side_stream(self):
+        if getattr(self, "_side", None) is None:
+            self._side = torch.cuda.Stream(self.device)
+        return self._side
+
+    def _k_enqueue_peer(self, fw, fx, probs_orig, tx) -> None:
+        """This rank's block -> the peer-memory bank (owning shard, or every copy of a replicated ring)."""
+        N.check(N.lib().b200ssl_bank_enqueue_peer(fw.data_ptr(), fx.data_ptr(), probs_orig.data_ptr(), tx.data_ptr(), fw.shape[0],
+                                                  fx.shape[0], self.low_dim, self.num_classes, N.dtype_enum(fw),
+                                                  self.ptr_state.data_ptr(), C_byref(self._shards),
+                                                  N.stream_ptr(self.device)), "bank_enqueue_peer")
 
     def _k_enqueue(self, fw, fx, probs_orig, tx, block_offset: int, advance: int) -> None:
         g = self.geom

@@ -185,15 +185,18 @@ bank_smooth_tc_kernel(const __grid_constant__ CUtensorMap tm_f, const __grid_con
     if (lane == 0) {
       tc::mbar_arrive_expect_tx(&bars[BAR_A], kTileA);
       tc::tma_load_2d(sA, &tm_f, 0, row_tile * kBM, &bars[BAR_A]);
-      if (p.arenas) {
-        // sharded bank: every rank's enqueue of the previous step must have landed in the shards (its flag was
-        // published a contrastive forward + backward + EMA ago, so this normally falls through)
-        uint8_t* mine = p.arenas[p.rank];
-        peer::LocalCtl* ctl = peer::local_ctl(mine);
-        const unsigned long long need = *reinterpret_cast<volatile unsigned long long*>(&ctl->epoch[peer::kXSmoothDone]);
-        for (int s = 0; s < p.world; ++s)
-          if (s != p.rank) peer::wait_flag(peer::flag_of(mine, peer::kXEnqueueDone, s), need, ctl);
-      }
+    }
+    if (p.arenas) {
+      // multi-rank bank: every rank's enqueue of the previous step must have landed (its flag was published a
+      // contrastive forward + backward + EMA ago, so this normally falls through).  One lane per peer: the
+      // acquire loads overlap instead of costing one L2 round trip each.
+      uint8_t* mine = p.arenas[p.rank];
+      peer::LocalCtl* ctl = peer::local_ctl(mine);
+      const unsigned long long need = *reinterpret_cast<volatile unsigned long long*>(&ctl->epoch[peer::kXSmoothDone]);
+      if (lane < p.world && lane != p.rank) peer::wait_flag(peer::flag_of(mine, peer::kXEnqueueDone, lane), need, ctl);
+      __syncwarp();
+    }
+    if (lane == 0) {
       for (int t = 0; t < T; ++t) {
         const int s = t % kStages;
         if (t >= kStages) tc::mbar_wait(&bars[BAR_KV_EMPTY + s], ((t / kStages) - 1) & 1, abort_flag);

@@ -110,6 +110,104 @@ __global__ void __launch_bounds__(kPeerThreads) peer_exchange_kernel(const PeerP
   }
 }
 
+// ---- enqueue of this rank's block into a peer-memory resident bank (b200ssl_bank_enqueue_peer) -----------------
+// grid (ceil(n / 32), ndst): CTA (c, d) stages rows [32c, 32c+32) of the block [feats_u_w ; feats_x] /
+// [probs_orig ; onehot(targets_x)] in shared memory and writes them into destination d -- copy (rank + d) % world of a
+// replicated ring, or the shard that owns the rows.  Wide (it leaves the row kernel's 8 CTAs: remote stores are
+// throughput-limited per SM) and meant for a side stream: the step's losses do not depend on it.
+constexpr int kEnqRows = 32;
+constexpr int kEnqThreads = 256;
+
+struct EnqueuePeerParams {
+  const __nv_bfloat16* fu; const __nv_bfloat16* fx; const float* po; const long long* tx;
+  long long n_u, n_x, K, shard_rows;
+  int C, rank, world, replicated;
+  uint8_t* const* arenas; size_t qf_off, qp_off, qpt_off;
+  long long* ptr_state;
+};
+
+__global__ void __launch_bounds__(kEnqThreads) bank_enqueue_peer_kernel(const EnqueuePeerParams p) {
+  __shared__ uint4 sF[kEnqRows * 8];                         // [32][64] bf16
+  __shared__ __align__(16) __nv_bfloat16 sP[kEnqRows * 32];  // [32][C] bf16, row-major like queue_probs
+  const int tid = threadIdx.x, C = p.C;
+  uint8_t* mine = p.arenas[p.rank];
+  LocalCtl* ctl = local_ctl(mine);
+  const unsigned long long epoch = *reinterpret_cast<volatile unsigned long long*>(&ctl->epoch[kXEnqueueDone]) + 1;
+  const long long ptr0 = *reinterpret_cast<volatile long long*>(p.ptr_state);
+  const long long n = p.n_u + p.n_x;
+  const long long r0 = (long long)blockIdx.x * kEnqRows;
+  const int nrows = (int)min((long long)kEnqRows, n - r0);
+  // nobody may still be reading the rows this step overwrites: every rank's smoothing pass has published "reads done"
+  if (tid < p.world && tid != p.rank) wait_flag(flag_of(mine, kXSmoothDone, tid), epoch, ctl);
+  // stage the tile (local reads)
+  for (int i = tid; i < nrows * 8; i += kEnqThreads) {
+    const long long r = r0 + (i >> 3);
+    const __nv_bfloat16* src = r < p.n_u ? p.fu + r * 64 : p.fx + (r - p.n_u) * 64;
+    sF[i] = *reinterpret_cast<const uint4*>(src + (i & 7) * 8);
+  }
+  for (int i = tid; i < nrows * C; i += kEnqThreads) {
+    const int rr = i / C, c = i - rr * C;
+    const long long r = r0 + rr;
+    sP[i] = __float2bfloat16_rn(r < p.n_u ? p.po[r * C + c] : (c == (int)p.tx[r - p.n_u] ? 1.f : 0.f));   // comatch.py:188-189
+  }
+  __syncthreads();
+  // destination of the tile's first row
+  const long long g0 = (ptr0 + (long long)p.rank * n + r0) % p.K;       // comatch.py:194-196, rank-major blocks
+  const long long ld = p.replicated ? p.K : p.shard_rows;
+  auto locate = [&](long long g, long long* row) -> uint8_t* {
+    if (p.replicated) { *row = g; return p.arenas[(p.rank + blockIdx.y) % p.world]; }
+    const int s = (int)(g / p.shard_rows);
+    *row = g - (long long)s * p.shard_rows;
+    return p.arenas[s];
+  };
+  long long row0;
+  uint8_t* base0 = locate(g0, &row0);
+  if (nrows == kEnqRows && (g0 & 7) == 0 && g0 + kEnqRows <= p.K && row0 + kEnqRows <= ld) {
+    // aligned tile inside one shard: 128-bit stores only
+    uint4* qf = reinterpret_cast<uint4*>(base0 + p.qf_off) + row0 * 8;
+    for (int i = tid; i < kEnqRows * 8; i += kEnqThreads) qf[i] = sF[i];
+    uint4* qp = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(base0 + p.qp_off) + row0 * C);
+    for (int i = tid; i < kEnqRows * C / 8; i += kEnqThreads) qp[i] = reinterpret_cast<const uint4*>(sP)[i];
+    __nv_bfloat16* qpt = reinterpret_cast<__nv_bfloat16*>(base0 + p.qpt_off);
+    for (int i = tid; i < C * (kEnqRows / 8); i += kEnqThreads) {
+      const int c = i / (kEnqRows / 8), j = i - c * (kEnqRows / 8);
+      __align__(16) __nv_bfloat16 v[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[k] = sP[(8 * j + k) * C + c];
+      *reinterpret_cast<uint4*>(qpt + (size_t)c * ld + row0 + 8 * j) = *reinterpret_cast<const uint4*>(v);
+    }
+  } else {
+    for (int i = tid; i < nrows * 8; i += kEnqThreads) {
+      long long row;
+      uint8_t* base = locate((g0 + (i >> 3)) % p.K, &row);
+      reinterpret_cast<uint4*>(base + p.qf_off)[row * 8 + (i & 7)] = sF[i];
+    }
+    for (int i = tid; i < nrows * C; i += kEnqThreads) {
+      const int rr = i / C, c = i - rr * C;
+      long long row;
+      uint8_t* base = locate((g0 + rr) % p.K, &row);
+      reinterpret_cast<__nv_bfloat16*>(base + p.qp_off)[row * C + c] = sP[i];
+      reinterpret_cast<__nv_bfloat16*>(base + p.qpt_off)[(size_t)c * ld + row] = sP[i];
+    }
+  }
+  // last CTA of the grid: all rows of this rank are out -> advance the ring pointer, publish "my rows are in"
+  __syncthreads();
+  __shared__ bool s_last;
+  if (tid == 0) {
+    __threadfence_system();                                  // cumulative over the CTA's (remote) stores
+    s_last = atomicAdd(&ctl->done[kXEnqueueDone], 1u) == gridDim.x * gridDim.y - 1;
+  }
+  __syncthreads();
+  if (!s_last) return;
+  if (tid == 0) {
+    __threadfence();
+    ctl->done[kXEnqueueDone] = 0;
+    p.ptr_state[0] = (ptr0 + (long long)p.world * n) % p.K;
+    *reinterpret_cast<volatile unsigned long long*>(&ctl->epoch[kXEnqueueDone]) = epoch;
+  }
+  if (tid < p.world && tid != p.rank) st_relaxed_sys(flag_of(p.arenas[tid], kXEnqueueDone, p.rank), epoch);
+}
+
 int check_common(const char* fn, const void* src, const void* out, size_t bytes, const void* arenas, size_t region, size_t slot,
                  int x, int rank, int world) {
   if (!src || !out || !arenas) return fail(B200SSL_E_NULL, "%s: NULL pointer", fn);
@@ -208,6 +306,33 @@ int b200ssl_peer_reduce_scatter_f32(const float* src, float* out, int64_t count_
   cudaError_t e = launch_pdl(PDL_PEER, peer_exchange_kernel<true>, dim3((unsigned)p.chunks, (unsigned)world, 1), dim3(kPeerThreads, 1, 1), 0,
                              as_stream(stream), dim3(1, 1, 1), p);
   if (e != cudaSuccess) return fail((int)e, "%s: cudaLaunchKernelEx: %s", fn, cudaGetErrorString(e));
+  return check_launch(fn);
+}
+
+int b200ssl_bank_enqueue_peer(const void* feats_u_w, const void* feats_x, const float* probs_orig, const int64_t* targets_x,
+                              int64_t n_u, int64_t n_x, int32_t dim, int32_t classes, int32_t dtype, int64_t* ptr_state,
+                              const b200ssl_bank_shards* shards, void* stream) {
+  const char* fn = "b200ssl_bank_enqueue_peer";
+  if (!shards || !ptr_state) return fail(B200SSL_E_NULL, "%s: NULL shard table / ptr_state", fn);
+  if (n_u < 0 || n_x < 0 || n_u + n_x <= 0) return fail(B200SSL_E_SHAPE, "%s: n_u=%lld n_x=%lld", fn, (long long)n_u, (long long)n_x);
+  if ((n_u > 0 && (!feats_u_w || !probs_orig)) || (n_x > 0 && (!feats_x || !targets_x))) return fail(B200SSL_E_NULL, "%s: NULL rows", fn);
+  if (dtype != B200SSL_BF16 || dim != 64 || classes < 2 || classes > 31)
+    return fail(B200SSL_E_DTYPE, "%s: the peer-memory bank is bf16, dim 64, classes <= 31", fn);
+  if (shards->world < 2 || shards->world > 8 || shards->rank < 0 || shards->rank >= shards->world || !shards->arenas_dev ||
+      shards->shard_rows <= 0 || shards->shard_rows % 8)
+    return fail(B200SSL_E_ARG, "%s: bad shard table", fn);
+  if ((reinterpret_cast<uintptr_t>(feats_u_w) | reinterpret_cast<uintptr_t>(feats_x)) & 15u) return fail(B200SSL_E_ALIGN, "%s: embeddings must be 16-byte aligned", fn);
+  EnqueuePeerParams p{};
+  p.fu = static_cast<const __nv_bfloat16*>(feats_u_w); p.fx = static_cast<const __nv_bfloat16*>(feats_x); p.po = probs_orig;
+  p.tx = reinterpret_cast<const long long*>(targets_x); p.n_u = n_u; p.n_x = n_x;
+  p.shard_rows = shards->shard_rows; p.K = shards->shard_rows * (shards->replicated ? 1 : shards->world);
+  p.C = classes; p.rank = shards->rank; p.world = shards->world; p.replicated = shards->replicated ? 1 : 0;
+  p.arenas = reinterpret_cast<uint8_t* const*>(shards->arenas_dev);
+  p.qf_off = shards->feats_offset; p.qp_off = shards->probs_offset; p.qpt_off = shards->probs_t_offset;
+  p.ptr_state = reinterpret_cast<long long*>(ptr_state);
+  if ((n_u + n_x) * shards->world > p.K) return fail(B200SSL_E_SHAPE, "%s: world*(n_u + n_x) > bank rows", fn);
+  const dim3 grid((unsigned)((n_u + n_x + kEnqRows - 1) / kEnqRows), (unsigned)(p.replicated ? p.world : 1), 1);
+  bank_enqueue_peer_kernel<<<grid, kEnqThreads, 0, as_stream(stream)>>>(p);
   return check_launch(fn);
 }
 

@@ -328,6 +328,15 @@ B200SSL_API int b200ssl_peer_close(void* arena);
 B200SSL_API int b200ssl_peer_free(void* arena);
 B200SSL_API int b200ssl_peer_timeouts(const void* own_arena, uint32_t* count /* host out; synchronises */);
 
+/* Enqueue (code/comatch.py:187-196) of this rank's block [feats_u_w ; feats_x] / [probs_orig ; onehot(targets_x)] into a
+ * peer-memory resident bank (b200ssl_bank_shards): global rows [ptr + rank*n, ptr + (rank+1)*n) mod K go to the shard that
+ * owns them or, replicated, into every rank's copy.  Waits for every rank's "reads done" flag of this step, advances the
+ * device ring pointer by world*n and publishes "my rows are in".  A wide launch for a side stream: nothing else in the
+ * step depends on it (b200ssl_comatch_rows_fused is then called with queue_feats = NULL and shards = NULL). */
+B200SSL_API int b200ssl_bank_enqueue_peer(const void* feats_u_w, const void* feats_x, const float* probs_orig,
+                              const int64_t* targets_x, int64_t n_u, int64_t n_x, int32_t dim, int32_t classes,
+                              int32_t dtype, int64_t* ptr_state, const struct b200ssl_bank_shards* shards, void* stream);
+
 /* out[r] = rank r's block [src0 ; src1] (bytes0 + bytes1 bytes, both multiples of 16), r = 0..world-1. */
 B200SSL_API int b200ssl_peer_all_gather(const void* src0, size_t bytes0, const void* src1, size_t bytes1, void* out,
                             void* const* arenas, size_t region_offset, size_t slot_bytes, int32_t exchange_id,
