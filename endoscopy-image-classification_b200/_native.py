@@ -59,7 +59,7 @@ SIGNATURES = {
                                         _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "b200ssl_comatch_rows_fused": (_i32, [_vp, _vp, _vp, _vp, _i32, _i32, _i64, _i32, _i32, _f32, _f32, _f32, _f32, _vp, _vp,
                                           _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
-                                          _i64, _i32, _vp, _i64, _i32, _vp, _vp]),
+                                          _i64, _i32, _vp, _i64, _i32, _vp]),
     "b200ssl_bank_enqueue": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i32, _i32, _i32, _i64, _vp, _i64,
                                     _i64, _i64, _i64, _i64, _vp]),
     "b200ssl_contrast_fwd": (_i32, [_vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _f32, _f32, _vp, _vp, _vp, _f32, _f32, _vp,

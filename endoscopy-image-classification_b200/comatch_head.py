@@ -461,7 +461,7 @@ class CoMatchHead:
             out["lbs"].data_ptr(), out["mask"].data_ptr(), out["grad_s0"].data_ptr(), out["scalars"].data_ptr(),
             self.queue_feats.data_ptr() if enq else None, self.queue_probs.data_ptr() if enq else None,
             N.ptr(self.queue_probs_t) if enq else None, fw.data_ptr(), fx.data_ptr(), tx.data_ptr(), fx.shape[0],
-            self.low_dim, self.ptr_state.data_ptr(), self.queue_size, 1 if onehot_tail else 0, None,
+            self.low_dim, self.ptr_state.data_ptr(), self.queue_size, 1 if onehot_tail else 0,
             N.stream_ptr(self.device)), "comatch_rows_fused")
         return out
 

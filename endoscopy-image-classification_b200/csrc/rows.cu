@@ -15,7 +15,6 @@
 #include <type_traits>
 
 #include "common.cuh"
-#include "peer.cuh"
 
 namespace b200ssl {
 namespace {
@@ -561,26 +560,14 @@ struct FusedParams {
   int CL; long long rows_per_cta;
   unsigned long long* dbg;
   int onehot_tail;   // probs_orig has rows + n_x rows: fill the tail with onehot(targets_x) (block for the sharded enqueue)
-  // directly addressed sharded bank (arenas != nullptr): global row g lives in arena g / shard_rows
-  uint8_t* const* arenas; int rank, world; long long shard_rows; size_t qf_off, qp_off, qpt_off;
-  long long block_offset, advance;   // this rank's block starts at ptr + block_offset; the pointer advances by `advance`
-  int ndst;                          // 1, or world when every rank keeps a full copy of the ring (write-through enqueue)
 };
 
-// Where global bank row g lives: the local bank, or the shard of the rank that owns it (peer-mapped NVLink memory).
+// Bank row g of the (local) ring.
 template <typename T>
 struct BankRow { T* qf; T* qp; T* qpt; long long row, ld; };
 template <typename T>
-__device__ __forceinline__ BankRow<T> bank_row(const FusedParams& p, long long g, int d = 0) {
-  if (!p.arenas) return {static_cast<T*>(p.qf), static_cast<T*>(p.qp), static_cast<T*>(p.qpt), g, p.K};
-  if (p.ndst > 1) {                                           // d-th copy of the whole ring, the own one first
-    uint8_t* base = p.arenas[(p.rank + d) % p.world];
-    return {reinterpret_cast<T*>(base + p.qf_off), reinterpret_cast<T*>(base + p.qp_off), reinterpret_cast<T*>(base + p.qpt_off), g, p.K};
-  }
-  const int s = (int)(g / p.shard_rows);
-  uint8_t* base = p.arenas[s];
-  return {reinterpret_cast<T*>(base + p.qf_off), reinterpret_cast<T*>(base + p.qp_off), reinterpret_cast<T*>(base + p.qpt_off),
-          g - (long long)s * p.shard_rows, p.shard_rows};
+__device__ __forceinline__ BankRow<T> bank_row(const FusedParams& p, long long g) {
+  return {static_cast<T*>(p.qf), static_cast<T*>(p.qp), static_cast<T*>(p.qpt), g, p.K};
 }
 
 template <typename T>
@@ -610,12 +597,7 @@ __global__ void __launch_bounds__(kFusedThreads) comatch_rows_fused_kernel(const
   const float inv_rows = 1.0f / (float)f.rows;
   pdl_launch_dependents();
   pdl_wait();                                                // previous kernel complete: global memory may be touched now
-  const long long ptr0 = p.qf ? *reinterpret_cast<volatile long long*>(p.ptr_state) : 0;
-  const long long ptr = ptr0 + p.block_offset;
-  const bool sharded = p.arenas != nullptr;
-  uint8_t* my_arena = sharded ? p.arenas[p.rank] : nullptr;
-  const unsigned long long x_epoch =
-      sharded ? *reinterpret_cast<volatile unsigned long long*>(&peer::local_ctl(my_arena)->epoch[peer::kXEnqueueDone]) + 1 : 0;
+  const long long ptr = p.qf ? *reinterpret_cast<volatile long long*>(p.ptr_state) : 0;
   if (tid == 0) B200SSL_STAMP(p.dbg, crank, 0);
 
   // DA history: everything that does not depend on this batch is fetched up front (comatch.py:169-173)
@@ -685,10 +667,6 @@ __global__ void __launch_bounds__(kFusedThreads) comatch_rows_fused_kernel(const
       const_cast<float*>(f.prob_avg)[tid] = savg[tid];
     }
   }
-  // sharded bank: nobody may still be reading the rows this step overwrites -- every rank's smoothing pass of this
-  // step has published "reads done" (it finished about when ours did, a DA phase ago)
-  if (sharded && p.qf && tid < p.world && tid != p.rank)
-    peer::wait_flag(peer::flag_of(my_arena, peer::kXSmoothDone, tid), x_epoch, peer::local_ctl(my_arena));
   __syncthreads();
   if (tid == 0) B200SSL_STAMP(p.dbg, crank, 3);
 
@@ -720,10 +698,8 @@ __global__ void __launch_bounds__(kFusedThreads) comatch_rows_fused_kernel(const
     if (tid == 0) B200SSL_STAMP(p.dbg, crank, 8);
     if (p.qf) {     // unlabeled-weak rows of this pass -> bank rows (ptr + row) % K     (comatch.py:187-196)
       const long long g0 = (ptr + row0) % p.K;
-      for (int d = 0; d < p.ndst; ++d) {
-      const BankRow<T> b0 = bank_row<T>(p, g0, d);
-      // common case: the pass lands in one shard without wrapping, on a 16-byte boundary -> 128-bit stores only
-      // (they matter most when the shard is a peer's: NVLink writes are paid per transaction)
+      const BankRow<T> b0 = bank_row<T>(p, g0);
+      // common case: the pass does not wrap and starts on a 16-byte boundary -> 128-bit stores only
       if (g0 + nrows <= p.K && b0.row + nrows <= b0.ld && b0.row % epv == 0 && nrows % epv == 0 && b0.ld % epv == 0) {
         for (int i = tid; i < nrows * vec_per_row; i += kFusedThreads)
           reinterpret_cast<uint4*>(b0.qf + b0.row * p.D)[i] = ldg128(static_cast<const T*>(p.fu) + row0 * p.D + (long long)i * epv);
@@ -742,22 +718,21 @@ __global__ void __launch_bounds__(kFusedThreads) comatch_rows_fused_kernel(const
       } else {
         for (int i = tid; i < nrows * vec_per_row; i += kFusedThreads) {
           const int rr = i / vec_per_row, v = i - rr * vec_per_row;
-          const BankRow<T> b = bank_row<T>(p, (ptr + row0 + rr) % p.K, d);
+          const BankRow<T> b = bank_row<T>(p, (ptr + row0 + rr) % p.K);
           const uint4 val = ldg128(static_cast<const T*>(p.fu) + (row0 + rr) * p.D + v * epv);
           *reinterpret_cast<uint4*>(b.qf + b.row * p.D + v * epv) = val;
         }
         for (int i = tid; i < cnt; i += kFusedThreads) {
           const int rr = i / C, c = i - rr * C;
-          const BankRow<T> b = bank_row<T>(p, (ptr + row0 + rr) % p.K, d);
+          const BankRow<T> b = bank_row<T>(p, (ptr + row0 + rr) % p.K);
           b.qp[b.row * C + c] = from_f32<T>(so[i]);
         }
         if (p.qpt)                                          // transposed copy: consecutive threads -> consecutive bank rows
           for (int i = tid; i < cnt; i += kFusedThreads) {
             const int c = i / nrows, rr = i - c * nrows;
-            const BankRow<T> b = bank_row<T>(p, (ptr + row0 + rr) % p.K, d);
+            const BankRow<T> b = bank_row<T>(p, (ptr + row0 + rr) % p.K);
             b.qpt[(size_t)c * b.ld + b.row] = from_f32<T>(so[rr * C + c]);
           }
-      }
       }
     }
   }
@@ -766,8 +741,7 @@ __global__ void __launch_bounds__(kFusedThreads) comatch_rows_fused_kernel(const
   if (p.qf && n_x > 0) {       // labeled rows: [feats_x ; onehot(targets_x)], spread over the CTAs
     const long long g0 = (ptr + f.rows) % p.K;
     const int i0 = crank * kFusedThreads + tid, istep = CL * kFusedThreads;
-    for (int d = 0; d < p.ndst; ++d) {
-    const BankRow<T> b0 = bank_row<T>(p, g0, d);
+    const BankRow<T> b0 = bank_row<T>(p, g0);
     if (g0 + n_x <= p.K && b0.row + n_x <= b0.ld && b0.row % epv == 0 && n_x % epv == 0 && b0.ld % epv == 0) {   // 128-bit stores only
       for (int i = i0; i < n_x * vec_per_row; i += istep)
         reinterpret_cast<uint4*>(b0.qf + b0.row * p.D)[i] = ldg128(static_cast<const T*>(p.fx) + (size_t)i * epv);
@@ -793,18 +767,17 @@ __global__ void __launch_bounds__(kFusedThreads) comatch_rows_fused_kernel(const
     } else {
       for (int i = i0; i < n_x * vec_per_row; i += istep) {
         const int rr = i / vec_per_row, v = i - rr * vec_per_row;
-        const BankRow<T> b = bank_row<T>(p, (ptr + f.rows + rr) % p.K, d);
+        const BankRow<T> b = bank_row<T>(p, (ptr + f.rows + rr) % p.K);
         const uint4 val = ldg128(static_cast<const T*>(p.fx) + (size_t)rr * p.D + v * epv);
         *reinterpret_cast<uint4*>(b.qf + b.row * p.D + v * epv) = val;
       }
       for (int i = i0; i < n_x * C; i += istep) {
         const int rr = i / C, c = i - rr * C;
-        const BankRow<T> b = bank_row<T>(p, (ptr + f.rows + rr) % p.K, d);
+        const BankRow<T> b = bank_row<T>(p, (ptr + f.rows + rr) % p.K);
         const T val = from_f32<T>(c == (int)p.tx[rr] ? 1.f : 0.f);
         b.qp[b.row * C + c] = val;
         if (p.qpt) b.qpt[(size_t)c * b.ld + b.row] = val;
       }
-    }
     }
   }
   if (tid == 0) B200SSL_STAMP(p.dbg, crank, 6);
@@ -827,9 +800,6 @@ __global__ void __launch_bounds__(kFusedThreads) comatch_rows_fused_kernel(const
     for (int w = 0; w < kFusedWarps; ++w) t += s_part[tid][w];
     (CL > 1 ? cluster.map_shared_rank(sfin, 0) : sfin)[crank * 2 + tid] = t;
   }
-  // one system-scope fence per CTA (cumulative over the stores its threads ordered with the barrier above): the remote
-  // rows are performed before the flag below is published.  A fence in every thread costs ~5 us here.
-  if (sharded && tid == 32) __threadfence_system();
   if (CL > 1) cluster.sync(); else __syncthreads();          // last exchange: afterwards only rank 0 reads, and only its own smem
   if (crank == 0 && tid < 2) {
     float t = 0.f;
@@ -839,12 +809,7 @@ __global__ void __launch_bounds__(kFusedThreads) comatch_rows_fused_kernel(const
   if (crank == 0 && tid == 0) {
     p.state[0] = count;
     p.state[1] = (head + 1) % p.window;
-    if (p.qf) p.ptr_state[0] = (ptr0 + p.advance) % p.K;           // comatch.py:196 (all ranks' blocks when sharded)
-  }
-  if (sharded && crank == 0) {                                // after the cluster barrier: every CTA's rows are out
-    // relaxed is enough: every CTA fenced at system scope before the cluster barrier that precedes this store
-    if (tid < p.world && tid != p.rank) peer::st_relaxed_sys(peer::flag_of(p.arenas[tid], peer::kXEnqueueDone, p.rank), x_epoch);
-    if (tid == 0) *reinterpret_cast<volatile unsigned long long*>(&peer::local_ctl(my_arena)->epoch[peer::kXEnqueueDone]) = x_epoch;
+    if (p.qf) p.ptr_state[0] = (ptr + f.rows + p.n_x) % p.K;       // comatch.py:196
   }
   if (tid == 0) B200SSL_STAMP(p.dbg, crank, 7);
 }
@@ -1040,8 +1005,7 @@ extern "C" int b200ssl_comatch_rows_fused(const void* logits_u_w, const void* lo
                                           float* scores, int64_t* lbs, float* mask, void* grad_s0, float* out_scalars,
                                           void* queue_feats, void* queue_probs, void* queue_probs_t, const void* feats_u_w,
                                           const void* feats_x, const int64_t* targets_x, int64_t n_x, int32_t dim,
-                                          int64_t* ptr_state, int64_t bank_rows, int32_t onehot_tail,
-                                          const b200ssl_bank_shards* shards, void* stream) {
+                                          int64_t* ptr_state, int64_t bank_rows, int32_t onehot_tail, void* stream) {
   const char* fn = "b200ssl_comatch_rows_fused";
   if (int e = check_rows(fn, rows, classes, dtype)) return e;
   if (classes > 32) return fail(B200SSL_E_SHAPE, "%s: classes %d > 32 (use the separate kernels)", fn, classes);
@@ -1067,20 +1031,6 @@ extern "C" int b200ssl_comatch_rows_fused(const void* logits_u_w, const void* lo
   p.tx = reinterpret_cast<const long long*>(targets_x); p.n_x = n_x; p.D = dim;
   p.ptr_state = reinterpret_cast<long long*>(ptr_state); p.K = bank_rows;
   p.onehot_tail = onehot_tail ? 1 : 0;
-  p.advance = rows + n_x;
-  p.ndst = 1;
-  if (shards) {
-    if (shards->world < 2 || shards->world > 8 || shards->rank < 0 || shards->rank >= shards->world || !shards->arenas_dev ||
-        shards->shard_rows <= 0 || bank_rows != shards->shard_rows * (shards->replicated ? 1 : shards->world) ||
-        dtype != B200SSL_BF16)
-      return fail(B200SSL_E_ARG, "%s: bad shard table (2..8 ranks, bf16, bank_rows = world*shard_rows or, replicated, = shard_rows)", fn);
-    if ((rows + n_x) * shards->world > bank_rows) return fail(B200SSL_E_SHAPE, "%s: world*(rows + n_x) > bank_rows", fn);
-    p.arenas = reinterpret_cast<uint8_t* const*>(shards->arenas_dev); p.rank = shards->rank; p.world = shards->world;
-    p.shard_rows = shards->shard_rows; p.qf_off = shards->feats_offset; p.qp_off = shards->probs_offset; p.qpt_off = shards->probs_t_offset;
-    p.block_offset = (long long)shards->rank * (rows + n_x);
-    p.advance = (long long)shards->world * (rows + n_x);
-    p.ndst = shards->replicated ? shards->world : 1;
-  }
   p.dbg = debug_timing_buffer(PDL_ROWS);
   if (onehot_tail && (n_x > 0 && !targets_x)) return fail(B200SSL_E_NULL, "%s: onehot_tail needs targets_x", fn);
   long long cl = (rows + kFusedRows - 1) / kFusedRows;

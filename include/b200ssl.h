@@ -116,23 +116,27 @@ B200SSL_API int b200ssl_comatch_da(const void* logits_u_w, int64_t rows, int32_t
                        float* col_mean_out, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------ SURVEY 8e ----
- * Directly addressed, rank-sharded memory bank (one node, NVLink peer memory).
- * Rank s keeps global bank rows [s*shard_rows, (s+1)*shard_rows) inside its peer
- * arena (see the b200ssl_peer_* functions at the end of this file), every rank maps
- * every arena.  K3 then reads ALL shards in place (TMA over NVLink for the remote
- * ones) and the enqueue stores each row into the shard that owns it, so a sharded
- * step has the launches of the single-GPU step and no separate exchange:
- *   - b200ssl_bank_smooth_partial(shards != NULL) waits until every rank's enqueue
- *     of the previous step is visible, then publishes "my reads are done";
- *   - b200ssl_comatch_rows_fused(shards != NULL) waits for every rank's "reads
- *     done" of this step before it writes rank `rank`'s block at global rows
- *     [ptr + rank*n, ptr + (rank+1)*n) (n = rows + n_x, ptr advances by world*n),
- *     then publishes "my rows are in".
- * Both flags have a whole kernel (resp. the rest of the step) of slack, so the
- * waits are normally free.  With `replicated` set the same protocol keeps one full
- * copy of the ring per rank instead of shards: remote traffic is then only the
- * enqueued rows (written through to every copy), K3 never leaves local memory.  Requirements: bf16 bank, dim 64, classes <= 31,
- * shard_rows a multiple of 8, world <= 8; all ranks run the same call sequence.
+ * Memory bank of a multi-rank job, resident in NVLink peer memory (one node).
+ * The reference keeps one bank per process and has no distributed code
+ * (code/comatch.py:90-96); here every rank maps every rank's peer arena (see the
+ * b200ssl_peer_* functions at the end of this file) and the bank lives inside the arenas:
+ *   sharded     rank s keeps global rows [s*shard_rows, (s+1)*shard_rows); K3 reads ALL
+ *               shards in place (TMA over NVLink for the remote ones) and the enqueue
+ *               stores each row into the shard that owns it;
+ *   replicated  every arena holds the whole ring (shard_rows = all rows); K3 reads only
+ *               the local copy and the enqueue writes this rank's rows through into
+ *               every copy -- the only NVLink traffic is the enqueued rows.
+ * Either way a step has the launches of the single-GPU step plus one enqueue launch on
+ * a side stream, and no collective.  Two epoch flags per step keep the ring consistent:
+ *   - b200ssl_bank_smooth_partial(shards != NULL) waits until every rank's enqueue of
+ *     the previous step is visible, and publishes "my reads are done" when it ends;
+ *   - b200ssl_bank_enqueue_peer waits for every rank's "reads done" of this step
+ *     before it writes rank `rank`'s block at global rows [ptr + rank*n, ptr +
+ *     (rank+1)*n) (n = rows + n_x; ptr advances by world*n), then publishes "my rows
+ *     are in".
+ * Both flags have most of a step of slack, so the waits are normally free.
+ * Requirements: bf16 bank, dim 64, classes <= 31, shard_rows a multiple of 8,
+ * world <= 8; all ranks run the same call sequence, one enqueue per smoothing pass.
  */
 typedef struct b200ssl_bank_shards {
   int32_t world, rank;
@@ -142,8 +146,8 @@ typedef struct b200ssl_bank_shards {
   uint64_t feats_offset;          /* byte offsets, identical in every arena, of queue_feats [shard_rows, 64], */
   uint64_t probs_offset;          /*   queue_probs [shard_rows, classes] and                                 */
   uint64_t probs_t_offset;        /*   queue_probs_t [32, shard_rows] (row `classes` = ones)                 */
-  int32_t replicated;             /* != 0: every arena holds the WHOLE ring (shard_rows = all bank rows): K3 reads only  */
-  int32_t reserved;               /*   the local copy and the enqueue writes this rank's rows into every rank's copy      */
+  int32_t replicated;             /* != 0: every arena holds the whole ring (shard_rows = all bank rows) */
+  int32_t reserved;
 } b200ssl_bank_shards;
 
 /* ---------------------------------------------------------------- K3 ----
@@ -218,8 +222,7 @@ B200SSL_API int b200ssl_comatch_rows_fused(const void* logits_u_w, const void* l
                                float* scores, int64_t* lbs, float* mask, void* grad_s0, float* out_scalars,
                                void* queue_feats, void* queue_probs, void* queue_probs_t, const void* feats_u_w,
                                const void* feats_x, const int64_t* targets_x, int64_t n_x, int32_t dim,
-                               int64_t* ptr_state, int64_t bank_rows, int32_t onehot_tail,
-                               const struct b200ssl_bank_shards* shards, void* stream);
+                               int64_t* ptr_state, int64_t bank_rows, int32_t onehot_tail, void* stream);
 
 /* ---------------------------------------------------------------- K5 ----
  * Ring-buffer enqueue.  Replaces code/comatch.py:187-196: rows are
