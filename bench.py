@@ -236,12 +236,12 @@ def run_b200(args, wl, rank, world, local_rank):
     gdev = torch.Generator(device=dev).manual_seed(5)
     S.perturb_(model, gdev)                    # m != e, like after an optimizer step
     grad_keys = ("logits_u_s0", "feats_u_s0", "feats_u_s1") if wl["kind"] == "comatch" else ("logits_u_s",)
-    # N=1: smooth, rows (DA+finalize+enqueue), contrast fwd, contrast bwd (+scale), ema.  Sharded bank: the same five
-    # with the directly addressed bank; + enqueue and three exchange launches with the peer-memory exchanges; + enqueue
+    # N=1: smooth, rows (DA+finalize+enqueue), contrast fwd, contrast bwd (+scale), ema.  N>1: + the side-stream enqueue
+    # with a peer-memory resident bank; + enqueue and three exchange launches with the peer-memory exchanges; + enqueue
     # with NCCL (its kernels are not counted).
     launches_per_step = (5 if wl["kind"] == "comatch" else 3)
     if world > 1 and head is not None:
-        launches_per_step += {"replicated": 0, "direct": 0, "peer": 4, "collective": 1}[head.exchange]
+        launches_per_step += {"replicated": 1, "direct": 1, "peer": 4, "collective": 1}[head.exchange]
     one = torch.ones((), dtype=torch.float32, device=dev)
 
     def step(batch):
@@ -368,10 +368,10 @@ def run_b200(args, wl, rank, world, local_rank):
                            "bank_exchange": (None if world == 1 or head is None else
                                              {"replicated": "every rank keeps the whole ring in NVLink peer memory; the enqueue block is written "
                                                             "through into every copy by the row kernel (the only exchange of a step); "
-                                                            "two epoch flags per step, no exchange launches",
+                                                            "two epoch flags per step, one extra (side-stream) enqueue launch, no collective",
                                               "direct": "shards in NVLink peer memory: K3 reads every shard in place (TMA over NVLink), "
-                                                        "the enqueue stores into the owning shard; two epoch flags per step, no "
-                                                        "exchange launches",
+                                                        "the enqueue stores into the owning shard; two epoch flags per step, one extra "
+                                                        "(side-stream) enqueue launch, no collective",
                                               "peer": "own kernels over NVLink peer memory (csrc/peer.cu): all-gather, reduce-scatter, "
                                                       "all-gather per step",
                                               "collective": "NCCL collectives"}[head.exchange]),
@@ -383,7 +383,10 @@ def run_b200(args, wl, rank, world, local_rank):
                            "l2": "no explicit flush: the EMA kernel streams 300 MB/step (> 126 MB L2); head inputs (~0.3 MB) "
                                  "come straight from the backbone in training, i.e. L2-resident there too"},
                 "roofline": {"kernel": "ema_multi_tensor_kernel", "bound": "hbm", "achieved": achieved, "peak": peak,
-                             "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                             "unit": "GB/s", "frac": achieved / peak,
+                             # dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full
+                             # (profiles/r01_ncu_ema_full_raw.csv; ModelwEmb-R50 state only)
+                             "traffic": 252.96e6 if plan.bytes_per_update == 300359460 else None, "peak_source": peak_src,
                              "algorithmic_bytes_per_launch": plan.bytes_per_update, "avg_launch_ms": ema_ms,
                              "timed": f"{n_ema} back-to-back launches between two CUDA events on the launching stream"},
                 "e2e": {"value": world * Bu * args.steps / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
