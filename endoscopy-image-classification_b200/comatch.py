@@ -49,13 +49,17 @@ class CoMatch(SemiSupervisedTrainer):
                 else:
                     setattr(self, attr, config.TRAIN[key])
         self.low_dim = config.MODEL.LOW_DIM
-        self.queue_size = queue_size or self.queue_batch * (config.DATA.MU + 1) * config.DATA.BATCH_SIZE   # comatch.py:91
-        pg = None
+        pg, world = None, 1
         if _cfg(config.TRAIN, "SHARD_BANK", False) and torch.distributed.is_available() and torch.distributed.is_initialized():
             pg = torch.distributed.group.WORLD
+            world = torch.distributed.get_world_size(pg)
+        # comatch.py:91 with the GLOBAL batch: one ring for the whole job, every rank contributes its block per step
+        # (TRAIN.QUEUE_SIZE, when given, is the global size)
+        self.queue_size = queue_size or self.queue_batch * (config.DATA.MU + 1) * config.DATA.BATCH_SIZE * world
         self.head = CoMatchHead(config.MODEL.NUM_CLASSES, self.low_dim, self.queue_size, config.TRAIN.THRES,
                                 alpha=self.alpha, temperature=self.temperature, contrast_th=self.contrast_th,
-                                gamma=self.gamma, enqueue_mode=self.enqueue_mode, device=self.device, process_group=pg)
+                                gamma=self.gamma, enqueue_mode=self.enqueue_mode, device=self.device, process_group=pg,
+                                exchange=_cfg(config.TRAIN, "BANK_EXCHANGE", "auto"))
 
     # ---- reference-visible bank state (comatch.py:92-96) lives in the head -------------------
     queue_feats = property(lambda self: self.head.queue_feats)

@@ -86,6 +86,32 @@ def test_argument_validation_without_gpu(native):
     assert lib.b200ssl_ema_multi_tensor(p256, 4, 3, 1, 0.999, 0.001, 0, None) == E_DTYPE
     assert lib.b200ssl_ema_multi_tensor(p256, 4, 0, 1, 0.999, 0.001, 7, None) == E_ARG
     assert lib.b200ssl_scale_inplace(None, 4, 0, p, 1.0, None) == E_NULL
+    # multi-rank bank / peer memory entry points
+    out = C.c_void_p()
+    assert lib.b200ssl_peer_alloc(16, C.byref(out), p) == E_ARG                      # smaller than the control page
+    assert lib.b200ssl_peer_alloc(1 << 20, None, p) == E_NULL
+    ctl = lib.b200ssl_peer_control_bytes()
+    assert ctl >= 1024 and ctl % 256 == 0
+    ag, rs = lib.b200ssl_peer_all_gather, lib.b200ssl_peer_reduce_scatter_f32
+    assert ag(None, 64, None, 0, p, p, ctl, 256, 0, 0, 2, None) == E_NULL
+    assert ag(p, 64, None, 0, p256, p, ctl, 256, 0, 0, 1, None) == E_ARG             # world < 2
+    assert ag(p256, 64, None, 0, p256, p, ctl, 256, 9, 0, 2, None) == E_ARG          # exchange id
+    assert ag(p256, 60, None, 0, p256, p, ctl, 256, 0, 0, 2, None) == E_ALIGN        # bytes % 16
+    assert ag(p256, 512, None, 0, p256, p, ctl, 256, 0, 0, 2, None) == E_ALIGN       # slot < bytes
+    assert rs(p256, p256, 0, p, ctl, 256, 1, 0, 2, None) == E_SHAPE
+    assert rs(p256, p256, 16, p, 64, 256, 1, 0, 2, None) == E_ALIGN                  # region inside the control page
+    sh = native.BankShards(2, 0, 64, p, p, 4096, 4096 + 8192, 4096 + 16384, 0, 0)
+    assert C.sizeof(native.BankShards) == 64
+    enq = lib.b200ssl_bank_enqueue_peer
+    assert enq(p, p, p, p, 4, 4, 64, 23, 1, p, None, None) == E_NULL                  # no shard table
+    assert enq(p, p, p, p, 4, 4, 64, 23, 0, p, C.byref(sh), None) == E_DTYPE         # fp32 bank
+    assert enq(p, p, p, p, 4, 4, 64, 23, 1, None, C.byref(sh), None) == E_NULL       # no ptr_state
+    assert enq(p256, p256, p, p, 40, 40, 64, 23, 1, p, C.byref(sh), None) == E_SHAPE  # world*n > bank rows
+    bad = native.BankShards(1, 0, 64, p, p, 4096, 8192, 16384, 0, 0)
+    sm = lib.b200ssl_bank_smooth_partial
+    assert sm(p256, None, None, None, 16, 64, 64, 23, 1, 0.2, p, p, 0, 0, C.byref(bad), p256, wsb, None) == E_ARG    # one rank
+    assert sm(p256, None, None, None, 16, 100, 64, 23, 1, 0.2, p, p, 0, 0, C.byref(sh), p256, wsb, None) == E_ARG    # K != world*shard
+    assert sm(p256, None, None, None, 16, 128, 64, 23, 0, 0.2, p, p, 0, 0, C.byref(sh), p256, wsb, None) == E_DTYPE  # fp32
 
 
 def test_product_has_no_cpu_fallback_and_no_oracle_import(native):
