@@ -11,7 +11,7 @@ ticket counters) lives in device memory.
 Two graphs are captured over the same static tensors:
 
 * ``replay()``       -- compute only; inputs already in the static device tensors;
-* ``replay_host()``  -- H2D copies of the inputs from pinned staging buffers, the
+* ``replay_host()``  -- one H2D copy of all inputs from a pinned staging buffer, the
   compute, and a D2H copy of the scalar result into pinned memory (the trainer's
   ``losses.item()``), i.e. the end-to-end step.
 """
@@ -35,10 +35,25 @@ class GraphedStep:
         host code ran without device work (e.g. ``CoMatchHead.sync_ptr_from_device``)."""
         self.device = torch.device(device)
         self.on_replay = None
-        self.static = {k: v.detach().to(self.device).clone() for k, v in example.items()}
-        self.staging = {k: torch.empty(v.shape, dtype=v.dtype).pin_memory() for k, v in self.static.items()}
+        # All inputs live in ONE device buffer (256-byte aligned slices) mirrored by ONE pinned host buffer, so the
+        # end-to-end graph needs a single H2D copy node instead of one per tensor (each costs ~2 us of stream time).
+        offsets, total = {}, 0
+        for k, v in example.items():
+            offsets[k] = total
+            total += (v.numel() * v.element_size() + 255) // 256 * 256
+        self._packed_dev = torch.zeros(max(total, 256), dtype=torch.uint8, device=self.device)
+        self._packed_host = torch.zeros(max(total, 256), dtype=torch.uint8).pin_memory()
+
+        def carve(buf, k, v):
+            nbytes = v.numel() * v.element_size()
+            return buf[offsets[k]:offsets[k] + nbytes].view(v.dtype).view(v.shape)
+
+        self.static = {k: carve(self._packed_dev, k, v) for k, v in example.items()}
+        self.staging = {k: carve(self._packed_host, k, v) for k, v in example.items()}
+        for k, v in example.items():
+            self.static[k].copy_(v.detach())
         self.result_host = torch.zeros(1, dtype=torch.float32).pin_memory()
-        self.h2d_bytes = sum(v.numel() * v.element_size() for v in self.static.values())
+        self.h2d_bytes = int(self._packed_dev.numel())       # what the H2D node moves per step (tensors + alignment padding)
         self._calls = 0
         side = torch.cuda.Stream(self.device)
         side.wait_stream(torch.cuda.current_stream(self.device))
@@ -58,8 +73,8 @@ class GraphedStep:
         if capture_host_io:
             self.graph_host = torch.cuda.CUDAGraph()
             with torch.cuda.graph(self.graph_host, pool=self.graph.pool()):
-                for k, v in self.static.items():
-                    v.detach().copy_(self.staging[k], non_blocking=True)   # leaves may require grad
+                with torch.no_grad():
+                    self._packed_dev.copy_(self._packed_host, non_blocking=True)      # one H2D node for all inputs
                 res = step_fn(self.static).detach().reshape(1).float()
                 self.result_host.copy_(res, non_blocking=True)
             self.grads_host = {k: v.grad for k, v in self.static.items() if v.grad is not None}
