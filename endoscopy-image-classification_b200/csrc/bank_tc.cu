@@ -7,11 +7,11 @@
 //   Qf tile [128 x 64]  -+                                     rowsum += E ; P = bf16(E) -> smem (swizzled)
 //   QpT tile [32 x 128] ---->  numer[128 x 32] += P QpT^T (TMEM accumulator, K = 128 keys)
 //
-// Warp roles (192 threads): warp 0 = TMEM allocator + TMA producer, warp 1 = MMA
-// issuer (one thread), warps 2..5 = epilogue (thread <-> TMEM lane <-> query row).
-// S is double-buffered in TMEM so GEMM1 of key tile t+1 overlaps the exp of tile t;
-// the bank is split over gridDim.y CTAs and the last CTA of a row tile folds the
-// split partials in order (deterministic).
+// Warp roles (576 threads): warp 0 = TMEM allocator + TMA producer, warp 1 = MMA
+// issuer (one thread), warps 2..17 = epilogue (4 threads per TMEM lane = query row,
+// 32 key columns each).  S (TMEM) and P (smem) are double-buffered so GEMM1 of key
+// tile t+1 and GEMM2 of tile t-1 overlap the exp of tile t; the bank is split over a
+// cluster of CTAs whose partials are folded through DSMEM in rank order (deterministic).
 //
 // Bank layout for this path: queue_feats [K, 64] bf16 row-major (a row is exactly one
 // 128-byte swizzle row) and a transposed, class-padded copy of the probabilities
@@ -80,7 +80,11 @@ constexpr int kBM = 128;          // queries per CTA  (UMMA M)
 constexpr int kBN = 128;          // keys per tile    (UMMA N of GEMM1 / K of GEMM2)
 constexpr int kCP = 32;           // classes + the "ones" column, padded (UMMA N of GEMM2)
 constexpr int kStages = 3;        // >= key tiles per CTA at the reference's sizes: every load is in flight at once (remote shards: NVLink latency)
-constexpr int kTcThreads = 320;   // warp 0 TMA + TMEM alloc, warp 1 MMA, warps 2..9 epilogue (2 per TMEM lane quarter)
+constexpr int kEpiWarps = 16;     // 4 per TMEM lane quarter: each thread owns 32 of the 128 key columns of its row.
+                                  // The epilogue is MUFU-bound; 4 warps per SM sub-partition keep ex2 issuing while others wait
+                                  // on tcgen05.ld / mbarriers (8 warps reached 43 % of the MUFU rate, see profiles/)
+constexpr int kEpiThreads = kEpiWarps * 32;
+constexpr int kTcThreads = 64 + kEpiThreads;   // warp 0 TMA + TMEM alloc, warp 1 MMA, warps 2.. epilogue
 constexpr int kMaxCluster = 8;
 constexpr int kMaxSeg = 8;        // bank segments = shards of a rank-sharded bank (1 = the whole bank is local)
 constexpr uint32_t kTileA = kBM * 128;                  // 16 KB: [128][64] bf16
@@ -89,9 +93,9 @@ constexpr uint32_t kSubQp = kCP * 128;                  //  4 KB: [32][64] bf16
 constexpr uint32_t kTileQp = 2 * kSubQp;                //  8 KB
 constexpr uint32_t kSubP = kBM * 128;                   // 16 KB: [128][64] bf16
 constexpr uint32_t kTileP = 2 * kSubP;                  // 32 KB (re-used as the fp32 reduction tile at the end)
-constexpr uint32_t kSmemData = kTileA + kStages * (kTileQf + kTileQp) + kTileP;   // 120 KB
+constexpr uint32_t kSmemData = kTileA + kStages * (kTileQf + kTileQp) + 2 * kTileP;   // 152 KB (P is double buffered)
 constexpr uint32_t kTmemCols = 512;                     // S[0] 0..127, S[1] 128..255, numer 256..287
-constexpr size_t kSmemRequest = 124 * 1024;             // > half an SM: one CTA per SM (it owns all TMEM columns)
+constexpr size_t kSmemRequest = 156 * 1024;             // > half an SM: one CTA per SM (it owns all TMEM columns)
 constexpr int kRedLd = 36;                              // floats per row of the reduction tile (16-byte rows, 4-way bank spread)
 
 struct BankMaps {                 // one pair of tensor maps per shard; remote shards are peer-mapped NVLink addresses
@@ -113,7 +117,8 @@ struct SmoothTcParams {
 };
 
 enum { BAR_A = 0, BAR_KV_FULL = 1, BAR_KV_EMPTY = BAR_KV_FULL + kStages, BAR_S_FULL = BAR_KV_EMPTY + kStages,
-       BAR_S_EMPTY = BAR_S_FULL + 2, BAR_P_FULL = BAR_S_EMPTY + 2, BAR_P_EMPTY, BAR_ACC, BAR_COUNT };
+       BAR_S_EMPTY = BAR_S_FULL + 2, BAR_P_FULL = BAR_S_EMPTY + 2, BAR_P_EMPTY = BAR_P_FULL + 2,
+       BAR_ACC = BAR_P_EMPTY + 2, BAR_COUNT };
 
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;
@@ -130,7 +135,7 @@ bank_smooth_tc_kernel(const __grid_constant__ CUtensorMap tm_f, const __grid_con
   uint8_t* sQp = sQf + kStages * kTileQf;
   uint8_t* sP = sQp + kStages * kTileQp;
   float* sRed = reinterpret_cast<float*>(sP);             // [128][kRedLd] after the pipeline has drained
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + kTileP);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * kTileP);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + BAR_COUNT);
   volatile int* abort_flag = reinterpret_cast<volatile int*>(tmem_slot + 1);
 
@@ -157,10 +162,12 @@ bank_smooth_tc_kernel(const __grid_constant__ CUtensorMap tm_f, const __grid_con
     }
     for (int s = 0; s < 2; ++s) {
       tc::mbar_init(&bars[BAR_S_FULL + s], 1);
-      tc::mbar_init(&bars[BAR_S_EMPTY + s], 256);
+      tc::mbar_init(&bars[BAR_S_EMPTY + s], kEpiThreads);
     }
-    tc::mbar_init(&bars[BAR_P_FULL], 256);
-    tc::mbar_init(&bars[BAR_P_EMPTY], 1);
+    for (int s = 0; s < 2; ++s) {
+      tc::mbar_init(&bars[BAR_P_FULL + s], kEpiThreads);
+      tc::mbar_init(&bars[BAR_P_EMPTY + s], 1);
+    }
     tc::mbar_init(&bars[BAR_ACC], 1);
     *abort_flag = 0;
     tc::fence_barrier_init();
@@ -230,60 +237,62 @@ bank_smooth_tc_kernel(const __grid_constant__ CUtensorMap tm_f, const __grid_con
       for (int t = 0; t < T; ++t) {
         if (t + 1 < T) gemm1(t + 1);
         const int s = t % kStages;
-        tc::mbar_wait(&bars[BAR_P_FULL], t & 1, abort_flag);
+        const int pb = t & 1;                                // P is double buffered like S: exp of tile t+1 overlaps GEMM2 of t
+        tc::mbar_wait(&bars[BAR_P_FULL + pb], (t >> 1) & 1, abort_flag);
         tc::tcgen05_fence_after();
 #pragma unroll
         for (int kb = 0; kb < 2; ++kb) {   // [numer | rowsum] += P [QpT | 1]^T   (K = 128 keys -> 2 sub-tiles x 4 x UMMA_K 16)
-          const uint64_t pa = tc::smem_desc_sw128(tc::smem_u32(sP + kb * kSubP));
+          const uint64_t pa = tc::smem_desc_sw128(tc::smem_u32(sP + pb * kTileP + kb * kSubP));
           const uint64_t qb = tc::smem_desc_sw128(tc::smem_u32(sQp + s * kTileQp + kb * kSubQp));
 #pragma unroll
           for (int k = 0; k < 4; ++k) tc::mma_bf16_ss(tmem + 2 * kBN, pa + 2 * k, qb + 2 * k, idesc2, (t | kb | k) != 0);
         }
         tc::mma_commit(&bars[BAR_KV_EMPTY + s]);
-        tc::mma_commit(&bars[BAR_P_EMPTY]);
+        tc::mma_commit(&bars[BAR_P_EMPTY + pb]);
       }
       tc::mma_commit(&bars[BAR_ACC]);
     }
   } else {
-    // ===== epilogue: two threads per TMEM lane (query row), 64 of the 128 key columns each =====
-    const int quarter = warp & 3, half = (warp - 2) >> 2;   // TMEM lanes [32*quarter, +32) are visible to this warp
+    // ===== epilogue: four threads per TMEM lane (query row), 32 of the 128 key columns each =====
+    const int quarter = warp & 3, colq = (warp - 2) >> 2;   // TMEM lanes [32*quarter, +32) are visible to this warp
+    const int half = colq >> 1, c2 = colq & 1;              // P sub-tile (64 keys) and 32-column group inside it
     const int r_in = quarter * 32 + lane;
     const uint32_t lane_addr = tmem + ((uint32_t)(quarter * 32) << 16);
     for (int t = 0; t < T; ++t) {
       const int b = t & 1;
       tc::mbar_wait(&bars[BAR_S_FULL + b], (t >> 1) & 1, abort_flag);
       if (t == 0 && threadIdx.x == 64) B200SSL_STAMP(p.dbg, cta, 3);   // first S tile ready (TMA + GEMM1)
-      if (t >= 1) tc::mbar_wait(&bars[BAR_P_EMPTY], (t - 1) & 1, abort_flag);
       tc::tcgen05_fence_after();
-#pragma unroll
-      for (int c2 = 0; c2 < 2; ++c2) {
+      {
         uint32_t r[32];
-        tc::tmem_ld_32x32(lane_addr + b * kBN + half * 64 + c2 * 32, r);
+        tc::tmem_ld_32x32(lane_addr + b * kBN + colq * 32, r);
         tc::tmem_ld_wait();
+        tc::tcgen05_fence_before();
+        tc::mbar_arrive(&bars[BAR_S_EMPTY + b]);            // S[b] is in registers: GEMM1 of tile t+2 may overwrite it
         // keys beyond the bank need no mask: their QpT columns (incl. the ones column) are TMA zero fill
+        uint32_t w[16];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          uint32_t w[4];
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const float e0 = ex2_approx(__uint_as_float(r[8 * q + 2 * e]) * p.scale);        // comatch.py:180
-            const float e1 = ex2_approx(__uint_as_float(r[8 * q + 2 * e + 1]) * p.scale);
-            const __nv_bfloat162 h = __floats2bfloat162_rn(e0, e1);
-            w[e] = *reinterpret_cast<const uint32_t*>(&h);
-          }
-          *reinterpret_cast<uint4*>(sP + half * kSubP + tc::sw128_offset(r_in, c2 * 4 + q)) = make_uint4(w[0], w[1], w[2], w[3]);
+        for (int e = 0; e < 16; ++e) {
+          const float e0 = ex2_approx(__uint_as_float(r[2 * e]) * p.scale);                  // comatch.py:180
+          const float e1 = ex2_approx(__uint_as_float(r[2 * e + 1]) * p.scale);
+          const __nv_bfloat162 h = __floats2bfloat162_rn(e0, e1);
+          w[e] = *reinterpret_cast<const uint32_t*>(&h);
         }
+        // the P buffer of tile t-2 must have been consumed -- only now, after the exponentials
+        if (t >= 2) tc::mbar_wait(&bars[BAR_P_EMPTY + b], ((t >> 1) - 1) & 1, abort_flag);
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          *reinterpret_cast<uint4*>(sP + b * kTileP + half * kSubP + tc::sw128_offset(r_in, c2 * 4 + q)) =
+              make_uint4(w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
       }
-      tc::tcgen05_fence_before();
-      tc::mbar_arrive(&bars[BAR_S_EMPTY + b]);
       tc::fence_proxy_async_smem();               // generic-proxy writes of P -> visible to the tensor core
-      tc::mbar_arrive(&bars[BAR_P_FULL]);
+      tc::mbar_arrive(&bars[BAR_P_FULL + b]);
       if (t == T - 1 && threadIdx.x == 64) B200SSL_STAMP(p.dbg, cta, 4);   // last exp tile done
     }
     tc::mbar_wait(&bars[BAR_ACC], 0, abort_flag);           // all MMAs retired: P smem is free, accumulator final
     if (threadIdx.x == 64) B200SSL_STAMP(p.dbg, cta, 5);
     tc::tcgen05_fence_after();
-    if (half == 0) {                                        // accumulator [numer | rowsum] -> fp32 reduction tile in smem
+    if (colq == 0) {                                        // accumulator [numer | rowsum] -> fp32 reduction tile in smem
       uint32_t r[32];
       tc::tmem_ld_32x32(lane_addr + 2 * kBN, r);
       tc::tmem_ld_wait();
