@@ -11,7 +11,9 @@ shards, rank ``r`` owning rows ``[r*K/R, (r+1)*K/R)``.  Per 
    into its shard; ``ptr`` advances identically everywhere.
 
 Everything in this file is device agnostic (NCCL on GPUs, gloo in the CPU
-tests); the kernels it feeds live in ``csrc/bank.cu``.
+tests); the kernels it feeds live in ``csrc/bank.cu``.  This is the ``exchange='collective'``
+path of ``CoMatchHead``; ``peer.py`` carries the same exchanges -- or removes them by keeping
+the ring in NVLink peer memory -- without a communication library on the data path.
 """
 from __future__ import annotations
 

@@ -6,18 +6,21 @@ State mirrors ``code/comatch.py:90-96``: the memory bank ``queue_feats [K, D]`` 
 alignment history (``prob_list``; kept on the device as a ``[window, C]`` ring
 so a step has no host synchronisation).
 
-One step is five launches of ``libb200ssl.so`` (+ one in backward):
+A bf16 step at the reference's size is four launches of ``libb200ssl.so`` (three in forward, one in backward):
 
-====  ===============================  ==========================================
-K2    ``b200ssl_comatch_da``           softmax column-mean -> DA history -> prob_avg  (:167-173)
-K3    ``b200ssl_bank_smooth_partial``  rowsum / numer of exp(F_w Q_f^T / tau) Q_p     (:180-181)
-K4/7  ``b200ssl_comatch_finalize``     DA divide, alpha-mix, max/mask, focal soft-CE + grad (:174-176,182-185,216-220)
-K5    ``b200ssl_bank_enqueue``         ring write of [feats_u_w; feats_x], [probs_orig; onehot] (:187-196)
-K6    ``b200ssl_contrast_fwd`` / ``_bwd``   graph-contrastive loss (:199-213) and its gradient
-====  ===============================  ==========================================
+====  ===================================  ==========================================
+K3    ``b200ssl_bank_smooth_partial``      rowsum / numer of exp(F_w Q_f^T / tau) Q_p                         (:180-181)
+rows  ``b200ssl_comatch_rows_fused``       DA history + prob_avg (:167-173), DA divide, alpha-mix, max/mask, focal
+                                           soft-CE + grad (:174-176,182-185,216-220), ring enqueue (:187-196)
+K6    ``b200ssl_contrast_fwd`` / ``_bwd``  graph-contrastive loss (:199-213), LAMBDA-weighted total; its gradient
+====  ===================================  ==========================================
 
-With a sharded bank (``process_group`` given) K3/K5 run against the local shard
-and NCCL collectives combine them (``bank.py``).
+Larger batches / more than 32 classes use the un-fused row kernels (``b200ssl_comatch_da``,
+``b200ssl_comatch_finalize``, ``b200ssl_bank_enqueue``).
+
+With ``process_group`` given the ring spans the ranks of one node; ``exchange`` selects whether it
+lives in NVLink peer memory (write-through copies or shards read in place, ``peer.py``) or is sharded behind
+own / NCCL row exchanges (``bank.py``).
 """
 from __future__ import annotations
 
@@ -102,9 +105,9 @@ class CoMatchHead:
     ``comatch.py:192`` (quirk Q1: with ``queue_batch=5`` the bank is never
     written); ``'always'`` is the ring write without the guard (upstream CoMatch).
 
-    Up to ``FUSED_ROWS_MAX`` unlabeled rows (unsharded bank, classes <= 32) the row phase
-    (DA + finalize + enqueue) is ONE thread-block-cluster launch; set ``fuse_rows = False`` to
-    force the three separate kernels (larger batches and sharded banks always use them).
+    Up to ``FUSED_ROWS_MAX`` unlabeled rows (classes <= 32) the row phase (DA + finalize + single-GPU
+    enqueue) is ONE thread-block-cluster launch; set ``fuse_rows = False`` to force the three separate
+    kernels (larger batches always use them).  ``exchange``: see ``__init__`` and DESIGN section 5.
     """
     FUSED_ROWS_MAX = 2048
     REPLICATE_MAX_BYTES = 256 << 20      # 'auto' keeps a full copy of the ring per rank up to this size
