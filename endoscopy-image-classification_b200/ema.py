@@ -54,7 +54,8 @@ def build_block_table(entries, block_elems: int = N.EMA_BLOCK_ELEMS) -> np.ndarr
 class _EmaPlan:
     """Device block table for one (ema module, model) pair."""
 
-    def __init__(self, ema_mod: torch.nn.Module, model: torch.nn.Module):
+    def __init__(self, ema_mod: torch.nn.Module, model: torch.nn.Module, exclude=()):
+        """``exclude``: model storages (``data_ptr``) that another launch updates (``fused_step.FusedOptimizerEMA``)."""
         e_vals = list(ema_mod.state_dict().values())
         m_vals = list(model.state_dict().values())
         if len(e_vals) != len(m_vals):
@@ -66,7 +67,7 @@ class _EmaPlan:
                 raise ValueError(f"EMA/model entry mismatch: {tuple(e.shape)}/{e.dtype} vs {tuple(m.shape)}/{m.dtype}")
             if not (e.is_contiguous() and m.is_contiguous()):
                 raise ValueError("ModelEMA needs contiguous state tensors")
-            if e.numel() == 0:
+            if e.numel() == 0 or m.data_ptr() in exclude:
                 continue
             key = e.data_ptr()
             if key in uniq:

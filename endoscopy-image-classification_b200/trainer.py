@@ -117,18 +117,29 @@ class SemiSupervisedTrainer:
                                                             n_iter_per_epoch=config.TRAIN.EVAL_STEP)
         self.class_weights = self._class_weights()
         amp = _cfg(self.config.TRAIN, "AMP", False)
+        # TRAIN.FUSED_OPT_EMA: optimizer.step() + ema.update() as one multi-tensor launch (fused_step.py)
+        self._fused = None
+        if _cfg(self.config.TRAIN, "FUSED_OPT_EMA", False):
+            from .fused_step import FusedOptimizerEMA
+            self._fused = FusedOptimizerEMA(self.optimizer, self.ema_model if self.config.TRAIN.USE_EMA else None, self.model)
         self._autocast = (lambda: torch.autocast("cuda", dtype=torch.bfloat16)) if amp else nullcontext
         self._labeled = BatchSource(self.train_labeled_dl) if hasattr(self, "train_labeled_dl") else None
         self._unlabeled = BatchSource(self.train_unlabeled_dl) if hasattr(self, "train_unlabeled_dl") else None
 
     def _after_backward(self, epoch, step_index, losses, summary_loss):
         """optimizer step, per-iteration LR schedule, EMA, bookkeeping (``fixmatch.py:120-131``)."""
-        self.optimizer.step()
-        if self.lr_scheduler is not None:
-            self.lr_scheduler.step_update(step_index)
-        if self.config.TRAIN.USE_EMA:
-            self.ema_model.update(self.model)          # one multi-tensor launch
-        self.model.zero_grad()
+        if self._fused is not None:
+            self._fused.step()                         # optimizer + EMA: one launch (the EMA sees the new weights)
+            if self.lr_scheduler is not None:
+                self.lr_scheduler.step_update(step_index)
+            self._fused.zero_grad()
+        else:
+            self.optimizer.step()
+            if self.lr_scheduler is not None:
+                self.lr_scheduler.step_update(step_index)
+            if self.config.TRAIN.USE_EMA:
+                self.ema_model.update(self.model)      # one multi-tensor launch
+            self.model.zero_grad()
         summary_loss.update(losses.item(), self.config.DATA.BATCH_SIZE)
 
     def train_one(self, epoch):
@@ -138,7 +149,10 @@ class SemiSupervisedTrainer:
         bar = tqdm(range(steps), total=steps)
         for batch_idx in bar:
             losses = self._train_step(epoch, batch_idx)
-            self.optimizer.zero_grad()
+            if self._fused is not None:
+                self._fused.zero_grad()                 # in place: gradient addresses are in the device table
+            else:
+                self.optimizer.zero_grad()
             losses.backward()
             self._after_backward(epoch, epoch * steps + batch_idx, losses, summary_loss)
             if hasattr(bar, "set_postfix"):

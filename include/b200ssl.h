@@ -304,6 +304,46 @@ B200SSL_API int b200ssl_ema_multi_tensor(const b200ssl_ema_block* blocks, int32_
                              int32_t do_ints, float decay, float one_minus_decay,
                              int32_t mode /*0 update, 1 set*/, void* stream);
 
+/* ------------------------------------------------------------ SURVEY 8(f1) ----
+ * Optimizer step + EMA in one multi-tensor pass over the trainable fp32 parameters.
+ * Replaces `self.optimizer.step()` (code/fixmatch.py:123; the SGD-nesterov / Adam /
+ * AdamW instances built by code/optimizer.py:43-51 with the no-decay group of
+ * :13-27) followed by `self.ema_model.update(self.model)` (fixmatch.py:127,
+ * ema.py:51-59) for those parameters; buffers and frozen parameters stay with
+ * b200ssl_ema_multi_tensor.  Per element, torch.optim's single-tensor formulas:
+ *   SGD    g += wd*p; buf = first_step ? g : momentum*buf + g; g = nesterov ? g + momentum*buf : buf; p -= lr*g
+ *   ADAM   g += wd*p; m += (1-beta1)*(g-m); v = beta2*v + (1-beta2)*g*g; p -= step_size * m / (sqrt(v)/bias2_sqrt + eps)
+ *   ADAMW  p *= decay_factor; then ADAM with wd = 0
+ * then, when `ema` != NULL, `ema_repeat` times  e = decay*e + one_minus_decay*p  (rounded op by op).
+ * The block table is DEVICE resident and 16-byte aligned; the group rows (1..8) are a HOST array read
+ * at call time and passed to the kernel by value.  The host fills them every step:
+ * step_size = lr/(1-beta1^t), bias2_sqrt = sqrt(1-beta2^t), decay_factor = 1-lr*wd,
+ * one_minus_beta* = 1-beta*, all computed in double and rounded once.
+ */
+enum b200ssl_opt_kind { B200SSL_OPT_SGD = 0, B200SSL_OPT_ADAM = 1, B200SSL_OPT_ADAMW = 2 };
+
+typedef struct b200ssl_opt_block {   /* one chunk (<= 4096 elements is the shipped host policy) of one parameter */
+  void* param;
+  const void* grad;
+  void* state1;        /* SGD: momentum_buffer (NULL when momentum == 0); Adam: exp_avg */
+  void* state2;        /* Adam: exp_avg_sq; SGD: NULL */
+  void* ema;           /* EMA copy of the parameter, or NULL */
+  int32_t count;       /* elements in this chunk */
+  int32_t group;       /* row of the group table */
+  int32_t ema_repeat;  /* multiplicity of the storage in state_dict() (code/ema.py loops over every entry) */
+  int32_t reserved;
+  int64_t reserved2;
+} b200ssl_opt_block;
+
+typedef struct b200ssl_opt_group {
+  float lr, beta1, beta2, eps, weight_decay, step_size, bias2_sqrt, momentum;
+  int32_t kind, nesterov, first_step, reserved;
+  float one_minus_beta1, one_minus_beta2, decay_factor, pad;
+} b200ssl_opt_group;
+
+B200SSL_API int b200ssl_opt_ema_multi_tensor(const b200ssl_opt_block* blocks, int32_t n_blocks, const b200ssl_opt_group* groups,
+                                 int32_t n_groups, float decay, float one_minus_decay, void* stream);
+
 /* ------------------------------------------------------------ SURVEY 8e ----
  * Row exchanges of the rank-sharded memory bank over NVLink peer memory.  The
  * reference has no distributed code (one bank per process, code/comatch.py:90-96);

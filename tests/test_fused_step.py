@@ -1,0 +1,179 @@
+"""optimizer step + EMA as one launch (`fused_step.FusedOptimizerEMA`).
+
+CPU: the per-element arithmetic the kernel implements (restated with numpy fp32 scalars, same operation order as
+csrc/opt_ema.cu) and the per-step group scalars (`group_row`) against `torch.optim` + the reference EMA update on CPU.
+GPU: the real launch against `optimizer.step(); ema.update(model)` on the same device, several steps, all three
+optimizers `code/optimizer.py:43-51` builds, weight-decay / no-decay groups, buffers, ragged sizes."""
+import copy
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+
+REPO = Path(__file__).resolve().parents[1]
+sys.path.insert(0, str(REPO))
+
+KINDS = {"sgd": 0, "adam": 1, "adamw": 2}
+
+
+def _make_opt(kind, groups, lr):
+    if kind == "sgd":
+        return torch.optim.SGD(groups, momentum=0.9, nesterov=True, lr=lr, weight_decay=0.05)
+    if kind == "adamw":
+        return torch.optim.AdamW(groups, eps=1e-8, betas=(0.9, 0.999), lr=lr, weight_decay=0.05)
+    return torch.optim.Adam(groups, lr=lr, betas=(0.9, 0.999), eps=1e-8, weight_decay=0)
+
+
+def _kernel_math(kind, row, p, g, s1, s2, e, d, o, rep):
+    """csrc/opt_ema.cu::update_elem on numpy fp32 arrays (fused multiply-adds evaluated in double then rounded)."""
+    f = np.float32
+    names = ["lr", "beta1", "beta2", "eps", "wd", "step_size", "bias2_sqrt", "momentum", "kind", "nesterov", "first", "rsv",
+             "omb1", "omb2", "decay_factor", "pad"]
+    h = dict(zip(names, row))
+    fma = lambda a, b, c: (np.float64(a) * np.float64(b) + np.float64(c)).astype(np.float32)
+    if kind == 0:
+        if h["wd"]:
+            g = fma(f(h["wd"]), p, g)
+        if h["momentum"]:
+            s1 = g.copy() if h["first"] else (s1 * f(h["momentum"])).astype(f) + g
+            g = fma(f(h["momentum"]), s1, g) if h["nesterov"] else s1
+        p = fma(-f(h["lr"]), g, p)
+    else:
+        if kind == 2:
+            p = (p * f(h["decay_factor"])).astype(f)
+        elif h["wd"]:
+            g = fma(f(h["wd"]), p, g)
+        s1 = fma(f(h["omb1"]), (g - s1).astype(f), s1)
+        s2 = fma((f(h["omb2"]) * g).astype(f), g, (s2 * f(h["beta2"])).astype(f))
+        denom = (np.sqrt(s2).astype(f) / f(h["bias2_sqrt"])).astype(f) + f(h["eps"])
+        p = fma(-f(h["step_size"]), (s1 / denom).astype(f), p)
+    for _ in range(rep):
+        e = (f(d) * e).astype(f) + (f(o) * p).astype(f)
+    return p, s1, s2, e
+
+
+@pytest.mark.parametrize("kind", ["sgd", "adam", "adamw"])
+def test_kernel_arithmetic_and_group_scalars_match_torch_optim_cpu(kind):
+    from endoscopy_image_classification_b200.fused_step import group_row
+    torch.manual_seed(0)
+    w = torch.nn.Parameter(torch.randn(257))
+    b = torch.nn.Parameter(torch.randn(31))
+    opt = _make_opt(kind, [{"params": [w]}, {"params": [b], "weight_decay": 0.0}], lr=3e-3)
+    ema = [w.detach().clone(), b.detach().clone()]
+    mine = [dict(p=t.detach().numpy().copy(), s1=np.zeros(t.numel(), np.float32), s2=np.zeros(t.numel(), np.float32),
+                 e=t.detach().numpy().copy()) for t in (w, b)]
+    d = 0.999
+    d32, o32 = np.float32(d), np.float32(1.0 - d)
+    for step in range(1, 6):
+        grads = [torch.randn_like(w), torch.randn_like(b)]
+        opt.param_groups[0]["lr"] = opt.param_groups[1]["lr"] = 3e-3 * (1.0 - 0.1 * step)     # a scheduler moves the lr
+        for t, g in zip((w, b), grads):
+            t.grad = g.clone()
+        opt.step()
+        for e, t in zip(ema, (w, b)):                       # code/ema.py:53-56, applied twice for an aliased storage
+            for _ in range(2):
+                e.mul_(d).add_((1.0 - d) * t.detach())
+        for gi, (m, g) in enumerate(zip(mine, grads)):
+            row = group_row(KINDS[kind], opt.param_groups[gi], step)
+            m["p"], m["s1"], m["s2"], m["e"] = _kernel_math(KINDS[kind], row, m["p"], g.numpy(), m["s1"], m["s2"], m["e"], d32, o32, 2)
+    for m, t, e in zip(mine, (w, b), ema):
+        np.testing.assert_allclose(m["p"], t.detach().numpy(), rtol=2e-6, atol=1e-7)
+        np.testing.assert_allclose(m["e"], e.numpy(), rtol=2e-6, atol=1e-7)
+    st = opt.state[w]
+    if kind == "sgd":
+        np.testing.assert_allclose(mine[0]["s1"], st["momentum_buffer"].numpy(), rtol=2e-6, atol=1e-7)
+    else:
+        np.testing.assert_allclose(mine[0]["s1"], st["exp_avg"].numpy(), rtol=2e-6, atol=1e-7)
+        np.testing.assert_allclose(mine[0]["s2"], st["exp_avg_sq"].numpy(), rtol=2e-6, atol=1e-9)
+
+
+def test_fused_step_rejects_what_it_does_not_implement():
+    from endoscopy_image_classification_b200.fused_step import FusedOptimizerEMA
+    w = torch.nn.Parameter(torch.randn(4))
+    with pytest.raises(NotImplementedError):
+        FusedOptimizerEMA(torch.optim.RMSprop([w]))
+    with pytest.raises(NotImplementedError):
+        FusedOptimizerEMA(torch.optim.Adam([w], amsgrad=True))
+    with pytest.raises(NotImplementedError):
+        FusedOptimizerEMA(torch.optim.SGD([w], lr=0.1, momentum=0.9, dampening=0.5))
+    f = FusedOptimizerEMA(torch.optim.Adam([w]))
+    w.grad = torch.zeros(4)
+    with pytest.raises(RuntimeError, match="CUDA"):          # no CPU path
+        f.step()
+
+
+class _Net(torch.nn.Module):
+    def __init__(self):
+        super().__init__()
+        self.conv = torch.nn.Conv2d(3, 24, 3, bias=False)      # 648 weights
+        self.bn = torch.nn.BatchNorm2d(24)                     # 1-D params (no decay) + float / int64 buffers
+        self.fc1 = torch.nn.Linear(24, 517)                    # 12408 weights: several 4096-chunks, ragged tail
+        self.fc2 = torch.nn.Linear(517, 23)
+        self.frozen = torch.nn.Linear(7, 5)
+        self.frozen.requires_grad_(False)
+
+    def forward(self, x):
+        h = torch.relu(self.bn(self.conv(x))).mean((2, 3))
+        return self.fc2(torch.relu(self.fc1(h)))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind", ["sgd", "adam", "adamw"])
+@pytest.mark.parametrize("use_ema", [True, False])
+def test_fused_optimizer_ema_matches_torch_optim_then_ema(kind, use_ema):
+    from endoscopy_image_classification_b200.ema import ModelEMA
+    from endoscopy_image_classification_b200.fused_step import FusedOptimizerEMA
+    from endoscopy_image_classification_b200.optimizer import set_weight_decay
+    dev = torch.device("cuda:0")
+    torch.manual_seed(1)
+    ref = _Net().to(dev)
+    new = copy.deepcopy(ref)
+    opt_r = _make_opt(kind, set_weight_decay(ref), lr=2e-3)
+    opt_n = _make_opt(kind, set_weight_decay(new), lr=2e-3)
+    ema_r = ModelEMA(ref, 0.99, device=dev) if use_ema else None
+    ema_n = ModelEMA(new, 0.99, device=dev) if use_ema else None
+    fused = FusedOptimizerEMA(opt_n, ema_n, new)
+    g = torch.Generator(device=dev).manual_seed(3)
+    for step in range(5):
+        x = torch.randn(8, 3, 9, 9, device=dev, generator=g)
+        y = torch.randint(0, 23, (8,), device=dev, generator=g)
+        torch.nn.functional.cross_entropy(ref(x), y).backward()
+        with torch.no_grad():
+            new(x)                                          # BatchNorm running statistics move in both models
+        for pr, pn in zip(ref.parameters(), new.parameters()):      # identical gradients for both optimizers
+            if pr.grad is not None:
+                if pn.grad is None:
+                    pn.grad = pr.grad.clone()
+                else:
+                    pn.grad.copy_(pr.grad)
+        for o in (opt_r, opt_n):
+            for grp in o.param_groups:
+                grp["lr"] = 2e-3 * (1.0 - 0.15 * step)
+        opt_r.step()
+        if use_ema:
+            ema_r.update(ref)
+        opt_r.zero_grad(set_to_none=False)
+        fused.step()
+        fused.zero_grad()
+        if step == 2:                                       # a gradient that moved is detected: tables are rebuilt
+            opt_n.zero_grad(set_to_none=True)
+    tol = dict(rtol=2e-6, atol=1e-7)
+    for (n, a), (_, b) in zip(ref.state_dict().items(), new.state_dict().items()):
+        torch.testing.assert_close(b, a, **tol, msg=lambda m, n=n: f"model {n}: {m}")
+    if use_ema:
+        for (n, a), (_, b) in zip(ema_r.ema.state_dict().items(), ema_n.ema.state_dict().items()):
+            torch.testing.assert_close(b, a, **tol, msg=lambda m, n=n: f"ema {n}: {m}")
+    sr, sn = opt_r.state_dict()["state"], opt_n.state_dict()["state"]
+    assert sr.keys() == sn.keys()
+    for k in sr:
+        assert sr[k].keys() == sn[k].keys(), (k, sr[k].keys(), sn[k].keys())
+        for name in sr[k]:
+            torch.testing.assert_close(sn[k][name].float().cpu(), sr[k][name].float().cpu(), rtol=2e-6, atol=1e-9,
+                                       msg=lambda m, k=k, name=name: f"state[{k}][{name}]: {m}")
+    # the wrapped optimizer can simply take over again
+    for pn in new.parameters():
+        if pn.requires_grad:
+            pn.grad = torch.ones_like(pn)
+    opt_n.step()
