@@ -310,7 +310,7 @@ B200SSL_API int b200ssl_ema_multi_tensor(const b200ssl_ema_block* blocks, int32_
  * AdamW instances built by code/optimizer.py:43-51 with the no-decay group of
  * :13-27) followed by `self.ema_model.update(self.model)` (fixmatch.py:127,
  * ema.py:51-59) for those parameters; buffers and frozen parameters stay with
- * b200ssl_ema_multi_tensor.  Per element, torch.optim's single-tensor formulas:
+ * b200ssl_ema_multi_tensor.  Per element, the stock optimizers' single-tensor formulas:
  *   SGD    g += wd*p; buf = first_step ? g : momentum*buf + g; g = nesterov ? g + momentum*buf : buf; p -= lr*g
  *   ADAM   g += wd*p; m += (1-beta1)*(g-m); v = beta2*v + (1-beta2)*g*g; p -= step_size * m / (sqrt(v)/bias2_sqrt + eps)
  *   ADAMW  p *= decay_factor; then ADAM with wd = 0
