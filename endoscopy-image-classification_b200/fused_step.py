@@ -148,14 +148,21 @@ class FusedOptimizerEMA:
         blocks = torch.from_numpy(tbl.view(np.uint8).copy()).to(device)
         if self.ema is not None:
             rest_plan = _EmaPlan(self.ema.ema, self.model, exclude=fused_ptrs)
-        grads = [(p, p.grad.data_ptr(), p.data_ptr()) for _, _, p in params]
-        self._tables = dict(blocks=blocks, n_blocks=len(tbl), device=device,
-                            grads=grads, rest=rest_plan, params=[p for _, _, p in params])
+        # host-side bookkeeping, prepared once: the gradient OBJECTS (kept alive: a gradient that was dropped and
+        # re-allocated is a different object), the per-group live parameters and the Adam step counters
+        plist = [p for _, _, p in params]
+        live = [[p for gi2, _, p in params if gi2 == gi] for gi in range(len(self.optimizer.param_groups))]
+        steps = [] if self.kind == OPT_SGD else [self.optimizer.state[p]["step"] for p in plist]
+        self._tables = dict(blocks=blocks, n_blocks=len(tbl), device=device, rest=rest_plan, params=plist, live=live, steps=steps,
+                            grads=[(p, p.grad) for p in plist], ptrs=[(p, p.data_ptr()) for p in (plist[0], plist[-1])])
 
     def _valid(self) -> bool:
         t = self._tables
-        return t is not None and all(p.grad is not None and p.grad.data_ptr() == gp and p.data_ptr() == pp
-                                     for p, gp, pp in t["grads"])
+        if t is None:
+            return False
+        if self.kind != OPT_SGD and any(self.optimizer.state[p].get("step") is not s for p, s in zip(t["params"][:1], t["steps"][:1])):
+            return False                             # optimizer state was replaced (load_state_dict)
+        return all(p.grad is g for p, g in t["grads"]) and all(p.data_ptr() == a for p, a in t["ptrs"])
 
     # ---- public API ---------------------------------------------------------------------------
     @torch.no_grad()
@@ -165,11 +172,16 @@ class FusedOptimizerEMA:
         t = self._tables
         # per-group scalars of this step (the step counters live in the optimizer's state like torch keeps them)
         rows = np.zeros(len(self.optimizer.param_groups), dtype=GROUP)
+        any_first = False
         for gi, g in enumerate(self.optimizer.param_groups):
             step = 1
-            live = [p for p in g["params"] if p.grad is not None]
+            live = t["live"][gi]
             if self.kind == OPT_SGD:
-                first = any(self.optimizer.state[p].get("_b200_first", False) for p in live)
+                flags = [self.optimizer.state[p].get("_b200_first", False) for p in live]
+                first = any(flags)
+                if first and not all(flags):
+                    raise NotImplementedError("SGD: parameters of one group must receive their first gradient in the same step")
+                any_first |= first
                 step = 1 if first else 2
             elif live:
                 step = int(self.optimizer.state[live[0]]["step"]) + 1
@@ -181,12 +193,12 @@ class FusedOptimizerEMA:
         if t["rest"] is not None and t["rest"].n_blocks > 0:
             t["rest"].launch(self.ema.decay, 0)
         # bookkeeping torch.optim would have done
-        for p in t["params"]:
-            st = self.optimizer.state[p]
-            if self.kind == OPT_SGD:
-                st.pop("_b200_first", None)
-            else:
-                st["step"] += 1
+        if self.kind == OPT_SGD:
+            if any_first:
+                for p in t["params"]:
+                    self.optimizer.state[p].pop("_b200_first", None)
+        else:
+            torch._foreach_add_(t["steps"], 1)       # the per-parameter step tensors torch.optim keeps (CPU scalars)
         self._steps += 1
 
     def zero_grad(self) -> None:
