@@ -80,6 +80,24 @@ class FusedOptimizerEMA:
             raise NotImplementedError("the fused step takes at most 8 parameter groups")
         self._tables = None          # block table, n_blocks, device, grad pointers, EMA plan of the remaining state
         self._steps = 0
+        # torch.optim keeps one CPU `step` tensor per parameter; bumping 161 of them costs more host time than the
+        # whole launch, so fused steps are counted here and written back just before anybody can look
+        # (state_dict(), a plain optimizer.step(), load_state_dict()).
+        self._pending = 0
+        optimizer.register_state_dict_pre_hook(lambda opt: self._flush_steps())
+        optimizer.register_step_pre_hook(lambda opt, args, kwargs: self._flush_steps())
+        optimizer.register_load_state_dict_post_hook(lambda opt: self._invalidate())
+
+    def _flush_steps(self) -> None:
+        t = self._tables
+        if self._pending and t is not None and t["steps"]:
+            torch._foreach_add_(t["steps"], float(self._pending))
+            t["base"] = [b + self._pending for b in t["base"]]
+        self._pending = 0
+
+    def _invalidate(self) -> None:
+        self._pending = 0
+        self._tables = None
 
     # ---- state, owned by the wrapped optimizer (same lazy init as torch.optim) -----------------
     def _state_for(self, p: torch.Tensor, group: dict):
@@ -98,6 +116,7 @@ class FusedOptimizerEMA:
         return st["exp_avg"], st["exp_avg_sq"]
 
     def _build(self):
+        self._flush_steps()
         params: List[tuple] = []
         for gi, g in enumerate(self.optimizer.param_groups):
             for p in g["params"]:
@@ -153,7 +172,8 @@ class FusedOptimizerEMA:
         plist = [p for _, _, p in params]
         live = [[p for gi2, _, p in params if gi2 == gi] for gi in range(len(self.optimizer.param_groups))]
         steps = [] if self.kind == OPT_SGD else [self.optimizer.state[p]["step"] for p in plist]
-        self._tables = dict(blocks=blocks, n_blocks=len(tbl), device=device, rest=rest_plan, params=plist, live=live, steps=steps,
+        base = [int(self.optimizer.state[ps[0]]["step"]) if (ps and self.kind != OPT_SGD) else 0 for ps in live]
+        self._tables = dict(base=base, blocks=blocks, n_blocks=len(tbl), device=device, rest=rest_plan, params=plist, live=live, steps=steps,
                             grads=[(p, p.grad) for p in plist], ptrs=[(p, p.data_ptr()) for p in (plist[0], plist[-1])])
 
     def _valid(self) -> bool:
@@ -184,7 +204,7 @@ class FusedOptimizerEMA:
                 any_first |= first
                 step = 1 if first else 2
             elif live:
-                step = int(self.optimizer.state[live[0]]["step"]) + 1
+                step = t["base"][gi] + self._pending + 1
             rows[gi] = group_row(self.kind, g, step)
         d = self.ema.decay if self.ema is not None else 0.0
         N.check(N.lib().b200ssl_opt_ema_multi_tensor(t["blocks"].data_ptr(), t["n_blocks"], rows.ctypes.data,
@@ -198,7 +218,7 @@ class FusedOptimizerEMA:
                 for p in t["params"]:
                     self.optimizer.state[p].pop("_b200_first", None)
         else:
-            torch._foreach_add_(t["steps"], 1)       # the per-parameter step tensors torch.optim keeps (CPU scalars)
+            self._pending += 1                       # written back to the per-parameter step tensors by _flush_steps()
         self._steps += 1
 
     def zero_grad(self) -> None:
@@ -211,5 +231,4 @@ class FusedOptimizerEMA:
         return self.optimizer.state_dict()
 
     def load_state_dict(self, sd) -> None:
-        self.optimizer.load_state_dict(sd)
-        self._tables = None               # state tensors were re-created
+        self.optimizer.load_state_dict(sd)      # the post hook drops the tables: state tensors were re-created
