@@ -66,6 +66,7 @@ class SemiSupervisedTrainer:
         self.model.to(self.device)
         self.epoch_start = 1
         self.best_valid_perf = None
+        self._fused = None                 # fused_step.FusedOptimizerEMA when TRAIN.FUSED_OPT_EMA is set
 
     # ---- reference API ---------------------------------------------------------------
     def get_dataloader(self, train_dl, valid_dl, test_dl=None):
