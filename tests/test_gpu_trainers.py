@@ -114,3 +114,41 @@ def test_semiformer_step_ema_and_checkpoint(tmp_path):
     cm.queue_ptr = 0
     cm.load_checkpoint(p2, is_train=True)
     assert torch.equal(cm.head.queue_feats, kept) and cm.queue_ptr == 16 and int(cm.head.ptr_state[0]) == 16
+
+
+@pytest.mark.parametrize("opt_name", ["adam", "sgd"])
+def test_trainer_with_fused_optimizer_ema_equals_the_eager_pair(opt_name):
+    """TRAIN.FUSED_OPT_EMA: FixMatch.train_one with the fused optimizer + EMA launch ends with the same
+    weights, EMA weights and optimizer state as with `optimizer.step(); ema_model.update(model)`."""
+    import copy
+
+    from endoscopy_image_classification_b200 import utils
+    from endoscopy_image_classification_b200.fixmatch import FixMatch
+    from endoscopy_image_classification_b200.optimizer import build_optimizer
+    g = torch.Generator().manual_seed(11)
+    B, MU, steps = 4, 2, 3
+    Bu = B * MU
+    lab = [(torch.randn(B, 3, 4, 4, generator=g), torch.randint(0, C, (B,), generator=g)) for _ in range(steps)]
+    unl = [((torch.randn(Bu, 3, 4, 4, generator=g), torch.randn(Bu, 3, 4, 4, generator=g)), None) for _ in range(steps)]
+    base = torch.nn.Sequential(torch.nn.Flatten(), torch.nn.Linear(48, 37), torch.nn.ReLU(), torch.nn.Linear(37, C))
+    result = {}
+    for fused in (False, True):
+        model = copy.deepcopy(base)
+        tr = FixMatch(model, device="cuda")
+        tr.get_dataloader((Loader(lab), Loader(unl)), None)
+        cfg = _config(utils, B=B, MU=MU, thr=0.0, ema=True, steps=steps, train_extra={"FUSED_OPT_EMA": fused})
+        tr.get_config(cfg, optimizer=build_optimizer(model.cuda(), opt_name, lr=1e-2), lr_scheduler=NoSched())
+        assert (tr._fused is not None) == fused
+        tr.train_one(epoch=0)
+        result[fused] = (copy.deepcopy(tr.model.state_dict()), copy.deepcopy(tr.ema_model.ema.state_dict()),
+                         copy.deepcopy(tr.optimizer.state_dict()["state"]))
+    for a, b in zip(result[False][:2], result[True][:2]):
+        for k in a:
+            torch.testing.assert_close(b[k], a[k], rtol=2e-6, atol=1e-7)
+        assert any(float((a[k] - base.state_dict()[k].cuda()).abs().max()) > 1e-4 for k in a)       # the steps did move the weights
+    sa, sb = result[False][2], result[True][2]
+    assert sa.keys() == sb.keys()
+    for k in sa:
+        assert sa[k].keys() == sb[k].keys()
+        for n in sa[k]:
+            torch.testing.assert_close(sb[k][n].float().cpu(), sa[k][n].float().cpu(), rtol=2e-6, atol=1e-9)
