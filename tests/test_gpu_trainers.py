@@ -145,7 +145,8 @@ def test_trainer_with_fused_optimizer_ema_equals_the_eager_pair(opt_name):
     for a, b in zip(result[False][:2], result[True][:2]):
         for k in a:
             torch.testing.assert_close(b[k], a[k], rtol=2e-6, atol=1e-7)
-        assert any(float((a[k] - base.state_dict()[k].cuda()).abs().max()) > 1e-4 for k in a)       # the steps did move the weights
+    moved = result[True][0]
+    assert any(float((moved[k] - base.state_dict()[k].cuda()).abs().max()) > 1e-3 for k in moved)   # the steps did move the weights
     sa, sb = result[False][2], result[True][2]
     assert sa.keys() == sb.keys()
     for k in sa:
