@@ -142,9 +142,11 @@ def test_trainer_with_fused_optimizer_ema_equals_the_eager_pair(opt_name):
         tr.train_one(epoch=0)
         result[fused] = (copy.deepcopy(tr.model.state_dict()), copy.deepcopy(tr.ema_model.ema.state_dict()),
                          copy.deepcopy(tr.optimizer.state_dict()["state"]))
+    # wiring test: the two runs back-propagate separately, so their gradients agree to rounding only (the op-by-op
+    # comparison on identical gradients is tests/test_fused_step.py)
     for a, b in zip(result[False][:2], result[True][:2]):
         for k in a:
-            torch.testing.assert_close(b[k], a[k], rtol=2e-6, atol=1e-7)
+            torch.testing.assert_close(b[k], a[k], rtol=1e-5, atol=1e-6)
     moved = result[True][0]
     assert any(float((moved[k] - base.state_dict()[k].cuda()).abs().max()) > 1e-3 for k in moved)   # the steps did move the weights
     sa, sb = result[False][2], result[True][2]
