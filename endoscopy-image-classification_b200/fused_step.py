@@ -20,7 +20,6 @@ tables are rebuilt.
 """
 from __future__ import annotations
 
-import ctypes as C
 import math
 from typing import Dict, List, Optional
 
@@ -143,7 +142,7 @@ class FusedOptimizerEMA:
                     ema_of[m.data_ptr()][1] += 1
                 else:
                     ema_of[m.data_ptr()] = [e, 1]
-        parts, fused_ptrs, first_flags = [], set(), []
+        parts, fused_ptrs = [], set()
         for gi, g, p in params:
             s1, s2 = self._state_for(p, g)
             e, rep = ema_of.get(p.data_ptr(), (None, 0))

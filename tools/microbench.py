@@ -13,7 +13,6 @@ from pathlib import Path
 sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
 import torch  # noqa: E402
 
-from endoscopy_image_classification_b200 import _native as N  # noqa: E402
 from endoscopy_image_classification_b200 import synthetic as S  # noqa: E402
 from endoscopy_image_classification_b200.comatch_head import CoMatchHead  # noqa: E402
 from endoscopy_image_classification_b200.ema import ModelEMA  # noqa: E402
