@@ -26,7 +26,7 @@ if world > 1:
     dist.init_process_group("nccl", device_id=dev)
     pg = dist.group.WORLD
 exchange = sys.argv[1] if len(sys.argv) > 1 else "auto"
-B, MU, C, D, K = 64, 7, 23, 64, 2560
+B, MU, C, D, K = 64, 7, 23, 64, 2560 * world
 keys = ["logits_u_w", "logits_u_s0", "feats_u_w", "feats_u_s0", "feats_u_s1", "feats_x", "targets_x"]
 g = torch.Generator().manual_seed(1 + rank)
 protos = S.rownorm(torch.randn(C, D, generator=torch.Generator().manual_seed(99)))
