@@ -233,3 +233,52 @@ def test_trainer_shells_and_schedules_on_cpu():
     tr.get_config(cfg)
     assert tr.ema_model.decay == 0.99 and not tr.ema_model.ema.training and tr.class_weights is None
     assert tr.epoch_start == 1 and tr.best_valid_perf is None
+
+
+def test_peer_arena_layout_with_stubbed_allocation(native, monkeypatch):
+    """Region / slot / named-area arithmetic of PeerArena (pure host logic); the allocation and the process group are
+    stand-ins, the kernels are not called."""
+    import torch.distributed as dist
+    from endoscopy_image_classification_b200 import peer
+
+    class Lib:
+        def b200ssl_peer_control_bytes(self):
+            return 4096
+
+        def b200ssl_peer_alloc(self, nbytes, out, handle):
+            C.cast(out, C.POINTER(C.c_void_p))[0] = 0x7F0000000000
+            self.nbytes = nbytes
+            return 0
+
+    lib = Lib()
+    monkeypatch.setattr(native, "lib", lambda: lib)
+    monkeypatch.setattr(torch.cuda, "device", lambda d: __import__("contextlib").nullcontext())
+    monkeypatch.setattr(torch.cuda, "synchronize", lambda d=None: None)
+    monkeypatch.setattr(dist, "get_rank", lambda pg=None: 1)
+    monkeypatch.setattr(dist, "get_world_size", lambda pg=None: 4)
+    monkeypatch.setattr(dist, "barrier", lambda group=None: None)
+
+    def fake_gather(out, obj, group=None):
+        out[:] = [obj] * len(out)
+    monkeypatch.setattr(dist, "all_gather_object", fake_gather)
+
+    class OpenLib(Lib):
+        opened = 0
+
+        def b200ssl_peer_open(self, handle, out):
+            OpenLib.opened += 1
+            C.cast(out, C.POINTER(C.c_void_p))[0] = 0x7E0000000000 + OpenLib.opened * (1 << 32)
+            return 0
+    lib = OpenLib()
+    a = peer.PeerArena(None, "cpu", {0: 60288, 2: 1000}, named={"qf": 320 * 128, "qpt": 32 * 320 * 2})
+    assert a.rank == 1 and a.world == 4 and OpenLib.opened == 3
+    assert a.slot == {0: 60416, 2: 1024}                                   # rounded up to 256 bytes
+    assert a.offset[0] == 4096 and a.offset[2] == 4096 + 2 * 4 * 60416     # [2 parities][world][slot] per exchange
+    end = a.offset[2] + 2 * 4 * 1024
+    assert a.named_offset == {"qf": end, "qpt": end + 320 * 128} and a.bytes == lib.nbytes == end + 320 * 128 + 32 * 320 * 2
+    assert a.fits(0, 60288) and not a.fits(0, 60417) and not a.fits(1, 16)
+    assert int(a.bases[1]) == 0x7F0000000000 and len(set(a.bases.tolist())) == 4      # own base at index `rank`
+    with pytest.raises(ValueError):
+        a.all_gather(0, [torch.zeros(3, 5)])                               # 60 bytes: not a multiple of 16
+    with pytest.raises(ValueError):
+        a.reduce_scatter(2, torch.zeros(8, 3, dtype=torch.float64))

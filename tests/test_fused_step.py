@@ -177,3 +177,85 @@ def test_fused_optimizer_ema_matches_torch_optim_then_ema(kind, use_ema):
         if pn.requires_grad:
             pn.grad = torch.ones_like(pn)
     opt_n.step()
+
+
+class _StubLib:
+    """Records the C-ABI calls of the fused step so its host logic can run on CPU tensors (no GPU here)."""
+
+    def __init__(self):
+        self.calls = []
+
+    def b200ssl_opt_ema_multi_tensor(self, blocks, n_blocks, groups, n_groups, decay, omd, stream):
+        import ctypes
+        from endoscopy_image_classification_b200.fused_step import GROUP
+        raw = ctypes.string_at(groups, n_groups * GROUP.itemsize)
+        self.calls.append(dict(n_blocks=n_blocks, groups=np.frombuffer(raw, dtype=GROUP).copy(), decay=decay, omd=omd))
+        return 0
+
+    def b200ssl_ema_multi_tensor(self, *a):
+        self.calls.append(dict(rest=a))
+        return 0
+
+
+def test_fused_step_host_logic_tables_counters_and_hooks(monkeypatch):
+    """Block / group tables, EMA pairing (aliased storages, entries left to the plain EMA launch), lazily written step
+    counters and the rebuild on a moved gradient -- with the native launch stubbed out."""
+    from endoscopy_image_classification_b200 import _native as N
+    from endoscopy_image_classification_b200 import ema as ema_mod
+    from endoscopy_image_classification_b200 import fused_step as F
+    stub = _StubLib()
+    monkeypatch.setattr(N, "lib", lambda: stub)
+    monkeypatch.setattr(N, "require_cuda", lambda *a, **k: torch.device("cpu"))
+    monkeypatch.setattr(N, "stream_ptr", lambda d: 0)
+
+    class Net(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.body = torch.nn.Linear(100, 90)            # 9000 weights -> 3 chunks of <= 4096
+            self.bn = torch.nn.BatchNorm1d(90)
+            self.alias = self.body                          # the same storages under a second name (custom_model.py:194-200)
+            self.frozen = torch.nn.Linear(3, 3).requires_grad_(False)
+
+    model = Net()
+    ema = ema_mod.ModelEMA.__new__(ema_mod.ModelEMA)        # the constructor insists on CUDA; the fields are all we need
+    ema.ema, ema.decay = copy.deepcopy(model), 0.99
+    opt = torch.optim.AdamW([{"params": [model.body.weight]}, {"params": [model.body.bias, model.bn.weight, model.bn.bias],
+                                                               "weight_decay": 0.0}], lr=1e-3, weight_decay=0.05)
+    fused = F.FusedOptimizerEMA(opt, ema, model)
+    for p in opt.param_groups[0]["params"] + opt.param_groups[1]["params"]:
+        p.grad = torch.ones_like(p)
+    fused.step()
+    t = fused._tables
+    tbl = np.frombuffer(t["blocks"].numpy().tobytes(), dtype=F.BLOCK)
+    assert t["n_blocks"] == len(tbl) == 3 + 1 + 1 + 1
+    w = model.body.weight
+    assert list(tbl["count"][:3]) == [4096, 4096, 9000 - 8192] and list(tbl["group"]) == [0, 0, 0, 1, 1, 1]
+    assert list(tbl["param"][:3]) == [w.data_ptr() + 4 * o for o in (0, 4096, 8192)]
+    assert list(tbl["grad"][:3]) == [w.grad.data_ptr() + 4 * o for o in (0, 4096, 8192)]
+    assert list(tbl["s1"][:3]) == [opt.state[w]["exp_avg"].data_ptr() + 4 * o for o in (0, 4096, 8192)]
+    assert list(tbl["ema"][:3]) == [ema.ema.body.weight.data_ptr() + 4 * o for o in (0, 4096, 8192)]
+    assert list(tbl["ema_repeat"]) == [2, 2, 2, 2, 1, 1]    # body.* appears twice in state_dict(), bn.* once
+    # everything the optimizer does not own stays with the plain EMA launch: bn buffers + the frozen layer
+    rest = t["rest"]
+    assert rest.n_unique == 3 + 2 and any("rest" in c for c in stub.calls)
+    g0, g1 = stub.calls[0]["groups"]
+    assert g0["kind"] == g1["kind"] == F.OPT_ADAMW and g0["first_step"] == 1
+    assert np.isclose(g0["decay_factor"], 1 - 1e-3 * 0.05) and g1["decay_factor"] == 1.0
+    assert np.isclose(g0["step_size"], 1e-3 / (1 - 0.9)) and np.isclose(g0["bias2_sqrt"], np.sqrt(1 - 0.999))
+    # step counters: written back lazily, visible through state_dict() and before a plain optimizer.step()
+    fused.step()
+    assert float(opt.state[w]["step"]) == 0.0 and fused._pending == 2
+    assert stub.calls[-2]["groups"][0]["first_step"] == 0
+    assert np.isclose(stub.calls[-2]["groups"][0]["step_size"], 1e-3 / (1 - 0.9 ** 2))
+    assert all(float(s["step"]) == 2.0 for s in opt.state_dict()["state"].values()) and fused._pending == 0
+    # a gradient that moved (zero_grad(set_to_none=True) + backward) rebuilds the table; in-place zeroing does not
+    fused.zero_grad()
+    assert fused._valid() and float(w.grad.abs().sum()) == 0.0
+    w.grad = torch.ones_like(w)
+    assert not fused._valid()
+    fused.step()
+    assert fused._tables is not t and fused._tables["base"] == [2, 2] and fused._pending == 1
+    opt.step()                                              # hands back: the hook flushes first
+    assert float(opt.state[w]["step"]) == 4.0
+    opt.load_state_dict(opt.state_dict())
+    assert fused._tables is None
