@@ -102,6 +102,18 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------ reference arm
+def cpu_model_name() -> str:
+    """Host CPU model for the CPU-baseline report (core count and CPU model beside the number)."""
+    try:
+        with open("/proc/cpuinfo") as f:
+            for line in f:
+                if line.lower().startswith("model name"):
+                    return line.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
+
+
 def run_reference(args, wl, rank, world):
     """The reference's own CPU path for the same step (oracle port of code/comatch.py:162-220
     or code/loss.py:126-164, + code/ema.py:51-59), all host threads, rank 0 only."""
@@ -147,7 +159,7 @@ def run_reference(args, wl, rank, world):
             "config": {"workload": wl["desc"], "global_batch_unlabeled": Bu,
                        "note": "reference CPU path (oracle port of the reference's PyTorch code; the reference is a Python "
                                "repo and /root/reference does not travel to the GPU box), fp32, rank 0 only"},
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "cpu_model": cpu_model_name(), "kind": "port",
                              "sample": f"{args.steps} full steps of the workload (head fwd+bwd + EMA) after {args.warmup} warm-up"},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
@@ -189,7 +201,7 @@ def cpu_baseline_sample(wl, budget_s=10.0):
         dt = time.perf_counter() - t0
         if dt > budget_s and n >= 5:
             break
-    return {"value": Bu * n / dt, "unit": UNIT, "cores": cores, "kind": "port",
+    return {"value": Bu * n / dt, "unit": UNIT, "cores": cores, "cpu_model": cpu_model_name(), "kind": "port",
             "sample": f"{n} full steps (oracle head fwd+bwd + EMA loop, fp32) in {dt:.1f} s on {cores} host threads"}
 
 
