@@ -94,7 +94,8 @@ class CoMatch(SemiSupervisedTrainer):
         T = self.config.TRAIN
         total_u, self.last_loss_u, self.last_loss_contrast, self.last_mask_mean = self.head.total_loss(
             logits_u_w, logits_u_s0, feats_u_w, feats_u_s0, feats_u_s1, feats_x, targets_x,
-            lambda_u=float(T.LAMBDA_U), lambda_c=float(T.LAMBDA_C))
+            lambda_u=float(T.LAMBDA_U), lambda_c=float(T.LAMBDA_C),
+            smooth=(epoch > 0 or batch_idx > self.queue_batch))                 # the gate of comatch.py:179
         return loss_x + total_u                                                 # comatch.py:222
 
     # the reference does not checkpoint the bank / DA history (comatch.py:285-306); we add them

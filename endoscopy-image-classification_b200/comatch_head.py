@@ -38,7 +38,7 @@ def C_byref(struct):
     return None if struct is None else ctypes.byref(struct)
 
 
-__all__ = ["CoMatchHead"]
+__all__ = ["CoMatchHead", "lockstep_total_loss"]
 
 
 class _HeadFn(torch.autograd.Function):
@@ -47,10 +47,10 @@ class _HeadFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, head, lambda_u, lambda_c, logits_u_w, logits_u_s0, feats_u_w, feats_u_s0, feats_u_s1, feats_x,
-                targets_x):
+                targets_x, smooth=None):
         f0, f1 = feats_u_s0.detach().contiguous(), feats_u_s1.detach().contiguous()
         out = head._step(logits_u_w.detach(), logits_u_s0.detach(), feats_u_w.detach(), f0, f1,
-                         feats_x.detach(), targets_x, float(lambda_u), float(lambda_c))
+                         feats_x.detach(), targets_x, float(lambda_u), float(lambda_c), smooth)
         ctx.head, ctx.lambda_u, ctx.lambda_c = head, float(lambda_u), float(lambda_c)
         ctx.save_for_backward(out["grad_s0"], f0, f1, out["probs"], out["stats"], out["probs_hl"])
         ctx.done = False
@@ -91,7 +91,7 @@ class _HeadFn(torch.autograd.Function):
             gf0, gf1 = torch.zeros_like(f0), torch.zeros_like(f1)
         if want_s0:
             gs0 = torch.zeros_like(grad_s0) if gu is None else head._k_scale(grad_s0, gu, fac_u)
-        return None, None, None, None, gs0, None, gf0, gf1, None, None
+        return None, None, None, None, gs0, None, gf0, gf1, None, None, None
 
 
 class CoMatchHead:
@@ -115,7 +115,7 @@ class CoMatchHead:
     def __init__(self, num_classes: int, low_dim: int, queue_size: int, thr: float, *, alpha: float = 0.9,
                  temperature: float = 0.2, contrast_th: float = 0.8, gamma: float = 2.0, da_window: int = 32,
                  enqueue_mode: str = "reference", smoothing: bool = True, device="cuda",
-                 dtype: torch.dtype = torch.float32, process_group=None, exchange: str = "auto"):
+                 dtype: torch.dtype = torch.float32, process_group=None, exchange: str = "auto", local_ranks=None):
         if enqueue_mode not in ("reference", "always"):
             raise ValueError(enqueue_mode)
         if exchange not in ("auto", "replicated", "direct", "peer", "collective"):
@@ -128,7 +128,14 @@ class CoMatchHead:
         self._check_backend()
         self.pg = process_group
         world, rank = 1, 0
-        if process_group is not None:
+        # local_ranks = (peer.LocalArenaSet, rank): this head is one of several emulated ranks of ONE process on ONE GPU
+        # (single-GPU validation of the peer-memory bank; drive the heads with lockstep_total_loss)
+        self._local = local_ranks
+        if local_ranks is not None:
+            if process_group is not None:
+                raise ValueError("process_group and local_ranks exclude each other")
+            world, rank = int(local_ranks[0].world), int(local_ranks[1])
+        elif process_group is not None:
             import torch.distributed as dist
             world, rank = dist.get_world_size(process_group), dist.get_rank(process_group)
         self.geom = ShardGeometry(self.queue_size, world, rank)
@@ -155,6 +162,7 @@ class CoMatchHead:
         self.prob_avg = torch.empty(self.num_classes, dtype=torch.float32, device=self.device)
         self._pristine = True
         self.fuse_rows = True
+        self._presmoothed = None
         self.last = {}
 
     def _check_backend(self) -> None:
@@ -178,13 +186,17 @@ class CoMatchHead:
         small = self.queue_size * (D + C + 32) * 2 <= self.REPLICATE_MAX_BYTES
         self.exchange = ((("replicated" if small else "direct") if direct_ok else "peer" if on_gpu else "collective")
                          if req == "auto" else req)
+        if self._local is not None and self.exchange not in ("direct", "replicated"):
+            raise ValueError("emulated ranks (local_ranks) run the peer-memory bank only: exchange 'direct' or 'replicated'")
         if R > 1 and self.exchange in ("direct", "replicated"):
             rep = self.exchange == "replicated"
             Ks = self.queue_size if rep else Ks                      # rows held by this rank
             import ctypes
             import torch.distributed as dist
             from .peer import PeerArena
-            self._arena = a = PeerArena(self.pg, self.device, {}, named={"qf": Ks * D * 2, "qp": Ks * C * 2, "qpt": 32 * Ks * 2})
+            named = {"qf": Ks * D * 2, "qp": Ks * C * 2, "qpt": 32 * Ks * 2}
+            self._arena = a = (PeerArena(self.pg, self.device, {}, named=named) if self._local is None else
+                               self._local[0].arena(self.geom.rank, {}, named))
             self.queue_feats = a.tensor("qf", (Ks, D), dtype)            # zero-filled by the allocation
             self.queue_probs = a.tensor("qp", (Ks, C), dtype)
             self.queue_probs_t = a.tensor("qpt", (32, Ks), dtype)
@@ -192,7 +204,8 @@ class CoMatchHead:
             self._shards = N.BankShards(R, self.geom.rank, Ks, ctypes.addressof(a.bases_host), a.bases.data_ptr(),
                                         a.named_offset["qf"], a.named_offset["qp"], a.named_offset["qpt"], 1 if rep else 0, 0)
             torch.cuda.synchronize(self.device)
-            dist.barrier(group=self.pg)          # the ones row of every shard is in place before any peer reads it
+            if self._local is None:
+                dist.barrier(group=self.pg)      # the ones row of every shard is in place before any peer reads it
             return
         self.queue_feats = torch.zeros(self.geom.shard_rows, self.low_dim, dtype=dtype, device=self.device)
         self.queue_probs = torch.zeros(self.geom.shard_rows, self.num_classes, dtype=dtype, device=self.device)
@@ -254,22 +267,31 @@ class CoMatchHead:
         self._pristine = False
 
     # ---- the step -----------------------------------------------------------------
-    def __call__(self, logits_u_w, logits_u_s0, feats_u_w, feats_u_s0, feats_u_s1, feats_x, targets_x):
+    def __call__(self, logits_u_w, logits_u_s0, feats_u_w, feats_u_s0, feats_u_s1, feats_x, targets_x, smooth=None):
         """Returns ``(loss_u, loss_contrast, mask_mean, mask, lbs_u_guess, scores, probs)``;
-        the two losses carry grad w.r.t. ``logits_u_s0`` / ``feats_u_s0`` / ``feats_u_s1``."""
-        o = _HeadFn.apply(self, 1.0, 1.0, logits_u_w, logits_u_s0, feats_u_w, feats_u_s0, feats_u_s1, feats_x, targets_x)
+        the two losses carry grad w.r.t. ``logits_u_s0`` / ``feats_u_s0`` / ``feats_u_s1``.
+        ``smooth``: the per-step gate of comatch.py:179 (``epoch > 0 or batch_idx > queue_batch``);
+        ``None`` = the head's ``smoothing`` attribute."""
+        o = _HeadFn.apply(self, 1.0, 1.0, logits_u_w, logits_u_s0, feats_u_w, feats_u_s0, feats_u_s1, feats_x, targets_x,
+                          smooth)
         return o[:3] + o[4:]
 
     def total_loss(self, logits_u_w, logits_u_s0, feats_u_w, feats_u_s0, feats_u_s1, feats_x, targets_x,
-                   lambda_u: float = 1.0, lambda_c: float = 1.0):
+                   lambda_u: float = 1.0, lambda_c: float = 1.0, smooth=None):
         """``LAMBDA_U*loss_u + LAMBDA_C*loss_contrast`` (the unlabeled part of comatch.py:222) formed on
         the device by the last forward kernel, with both weights folded into the backward launches --
         no eager elementwise kernels around the head.  Returns ``(total, loss_u, loss_contrast, mask_mean)``."""
         o = _HeadFn.apply(self, lambda_u, lambda_c, logits_u_w, logits_u_s0, feats_u_w, feats_u_s0, feats_u_s1,
-                          feats_x, targets_x)
+                          feats_x, targets_x, smooth)
         return o[3], o[0].detach(), o[1].detach(), o[2].detach()
 
-    def _step(self, lw, ls0, fw, fs0, fs1, fx, tx, lambda_u: float = 1.0, lambda_c: float = 1.0):
+    def presmooth(self, feats_u_w) -> None:
+        """Phase 1 of a lock-step step over emulated ranks: K3 of this rank now, consumed by its next step."""
+        if self._shards is None:
+            raise RuntimeError("presmooth is the lock-step protocol of a peer-memory bank")
+        self._presmoothed = self._k_smooth(feats_u_w.detach().contiguous())
+
+    def _step(self, lw, ls0, fw, fs0, fs1, fx, tx, lambda_u: float = 1.0, lambda_c: float = 1.0, smooth=None):
         lw, ls0, fw, fx = (t.contiguous() for t in (lw, ls0, fw, fx))
         tx = tx.to(torch.int64).contiguous()
         rows, C = lw.shape
@@ -295,9 +317,15 @@ class CoMatchHead:
                                    "rank, fuse_rows=True); build the head with exchange='peer' for larger batches")
             if not fused:
                 self._k_da(lw)                                               # K2
-            if self.smoothing:                                               # K3, bank as of *before* this step's enqueue
-                rowsum, numer = self._k_smooth(fw)
             multi = self._shards is not None
+            smooth = self.smoothing if smooth is None else bool(smooth)
+            if self._presmoothed is not None:                                # lock-step emulation: K3 ran in phase 1
+                rowsum, numer = self._presmoothed
+                self._presmoothed = None
+            elif smooth or multi:                                            # K3, bank as of *before* this step's enqueue
+                rowsum, numer = self._k_smooth(fw)                           # (peer-memory bank: K3 also carries the epoch flags)
+            if not smooth:
+                rowsum = numer = None                                        # comatch.py:179 gate closed: un-smoothed probs
             if fused:                                                        # ONE cluster launch: DA + finalize + enqueue
                 out = self._k_rows_fused(lw, ls0, rowsum, numer, lds, fw, fx, tx, do_enqueue and not multi, False)
                 if multi:
@@ -321,7 +349,7 @@ class CoMatchHead:
             W = (C + 1 + 3) & ~3
             arena = self._peer_arena(n, D * fw.element_size(), W * 4, C * 4)
             gathered_f = self._x_all_gather(arena, 0, [fw, fx])              # [R*n, D]
-            if self.smoothing:
+            if self.smoothing if smooth is None else bool(smooth):
                 packed = self._k_smooth(gathered_f, packed_ld=W)             # [R*n, W]: numer | rowsum
                 mine = self._x_reduce_scatter(arena, 1, packed)              # [n, W]; rows [0, rows) are this rank's queries
                 numer, rowsum, lds = mine, mine[:, C:], (W, W)
@@ -525,3 +553,13 @@ class CoMatchHead:
         N.check(N.lib().b200ssl_scale_inplace(grad.data_ptr(), grad.numel(), N.dtype_enum(grad), g.data_ptr(), factor,
                                               N.stream_ptr(self.device)), "scale_inplace")
         return grad
+
+
+def lockstep_total_loss(heads, batches, lambda_u: float = 1.0, lambda_c: float = 1.0):
+    """One step of several emulated ranks (``CoMatchHead(local_ranks=...)``) on ONE GPU and ONE stream, phase by phase:
+    every rank's K3 first (it needs all enqueues of the previous step, which are complete), then every rank's row
+    kernel, enqueue and contrastive forward (the enqueue needs every rank's K3 of this step).  No kernel is ever
+    launched before one whose flag it waits for, so nothing spins on the device.  Returns the per-rank ``total_loss`` tuples."""
+    for h, b in zip(heads, batches):
+        h.presmooth(b["feats_u_w"])
+    return [h.total_loss(**b, lambda_u=lambda_u, lambda_c=lambda_c) for h, b in zip(heads, batches)]

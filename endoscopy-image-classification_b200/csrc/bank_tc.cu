@@ -76,13 +76,13 @@ namespace {
 
 namespace cg = cooperative_groups;
 
-constexpr int kBM = 128;          // queries per CTA  (UMMA M)
+constexpr int kBM = 128;          // queries per row tile (UMMA M)
 constexpr int kBN = 128;          // keys per tile    (UMMA N of GEMM1 / K of GEMM2)
 constexpr int kCP = 32;           // classes + the "ones" column, padded (UMMA N of GEMM2)
 constexpr int kStages = 3;        // >= key tiles per CTA at the reference's sizes: every load is in flight at once (remote shards: NVLink latency)
+constexpr int kMaxMT = 4;         // row tiles one CTA can serve from ONE staged key tile ("row loop"): a remote key tile
+                                  // then crosses NVLink once per step instead of once per row tile
 constexpr int kEpiWarps = 16;     // 4 per TMEM lane quarter: each thread owns 32 of the 128 key columns of its row.
-                                  // The epilogue is MUFU-bound; 4 warps per SM sub-partition keep ex2 issuing while others wait
-                                  // on tcgen05.ld / mbarriers (8 warps reached 43 % of the MUFU rate, see profiles/)
 constexpr int kEpiThreads = kEpiWarps * 32;
 constexpr int kTcThreads = 64 + kEpiThreads;   // warp 0 TMA + TMEM alloc, warp 1 MMA, warps 2.. epilogue
 constexpr int kMaxCluster = 8;
@@ -92,11 +92,12 @@ constexpr uint32_t kTileQf = kBN * 128;                 // 16 KB
 constexpr uint32_t kSubQp = kCP * 128;                  //  4 KB: [32][64] bf16
 constexpr uint32_t kTileQp = 2 * kSubQp;                //  8 KB
 constexpr uint32_t kSubP = kBM * 128;                   // 16 KB: [128][64] bf16
-constexpr uint32_t kTileP = 2 * kSubP;                  // 32 KB (re-used as the fp32 reduction tile at the end)
-constexpr uint32_t kSmemData = kTileA + kStages * (kTileQf + kTileQp) + 2 * kTileP;   // 152 KB (P is double buffered)
-constexpr uint32_t kTmemCols = 512;                     // S[0] 0..127, S[1] 128..255, numer 256..287
-constexpr size_t kSmemRequest = 156 * 1024;             // > half an SM: one CTA per SM (it owns all TMEM columns)
-constexpr int kRedLd = 36;                              // floats per row of the reduction tile (16-byte rows, 4-way bank spread)
+constexpr uint32_t kTileP = 2 * kSubP;                  // 32 KB
+constexpr uint32_t kSmemStages = kStages * (kTileQf + kTileQp) + 2 * kTileP;   // 136 KB (P is double buffered)
+constexpr uint32_t kTmemCols = 512;                     // S[0] 0..127, S[1] 128..255, [numer | rowsum] of row tile m at 256 + 32 m
+constexpr int kRedLd = 36;                              // floats per row of a reduction tile (16-byte rows, 4-way bank spread)
+constexpr uint32_t kRedTile = kBM * kRedLd * 4;         // 18 KB per row tile, staged over the drained pipeline buffers
+constexpr size_t smem_request(int mt) { return 1024 + (size_t)mt * kTileA + kSmemStages + 512; }   // mt = 1: 153.5 KB > half an SM
 
 struct BankMaps {                 // one pair of tensor maps per shard; remote shards are peer-mapped NVLink addresses
   CUtensorMap qf[kMaxSeg];
@@ -105,12 +106,15 @@ struct BankMaps {                 // one pair of tensor maps per shard; remote s
 
 struct SmoothTcParams {
   long long rows, rows_pad;
+  int row_tiles;                  // ceil(rows / 128)
+  int mt;                         // row tiles per CTA
   int nseg, tps;                  // key tiles are enumerated shard by shard: tile kt -> (kt / tps, kt % tps)
   uint8_t* const* arenas;         // non-NULL: directly addressed sharded bank (peer.cuh flags / epochs)
   int rank, world, seg_first;     // seg_first: segment the tile enumeration starts at (the own shard)
   int C, W;                       // W = round_up(C + 1, 4): [numer 0..C-1, rowsum] per row of a partial
-  int nsplit, cluster, nouter;    // nsplit = cluster * nouter CTAs share one row tile
+  int nsplit, cluster, nouter;    // nsplit = cluster * nouter CTAs share one group of row tiles
   float scale;                    // log2(e) / temperature
+  float s_min;                    // lower clamp of S for the polynomial exponentials (-126 / scale)
   float* rowsum; float* numer; int rowsum_ld, numer_ld;
   float* part; unsigned* tickets;
   unsigned long long* dbg;
@@ -126,27 +130,51 @@ __device__ __forceinline__ float ex2_approx(float x) {
   return y;
 }
 
+// 2^(s * scale) on the FMA pipe (the MUFU unit makes 16 exponentials per clock and SM, a quarter of what the two GEMMs of a
+// key tile could consume): round-to-nearest split x = j + f through the 1.5 * 2^23 trick, degree-3 minimax polynomial of
+// 2^f on [-0.5, 0.5] (relative error 7.5e-5, far below the bf16 rounding of P that follows), exponent patched in with one
+// integer shift-add.  s is clamped from below so that j stays inside the exponent range (the reference's exp underflows
+// there); above the range the reference's own fp32 exp overflows too.
+__device__ __forceinline__ float ex2_poly(float s, float scale, float s_min) {
+  constexpr float kMagic = 12582912.f;                      // 1.5 * 2^23
+  s = fmaxf(s, s_min);
+  const float t = fmaf(s, scale, kMagic);                   // low mantissa bits = round(x)
+  const float f = fmaf(s, scale, -(t - kMagic));            // x - round(x)
+  float p = fmaf(0x1.c3f76p-5f, f, 0x1.f0de1ap-3f);
+  p = fmaf(p, f, 0x1.62f31ap-1f);
+  p = fmaf(p, f, 0x1.fff692p-1f);
+  return __uint_as_float(__float_as_uint(p) + (__float_as_uint(t) << 23));    // (magic << 23) == 0 (mod 2^32)
+}
+
+// NPOLY of the 32 exponentials a thread makes per S tile go through ex2_poly, spread evenly between the MUFU ones.
+template <int NPOLY>
+__device__ __forceinline__ constexpr bool poly_slot(int i) { return ((i + 1) * NPOLY) / 32 != (i * NPOLY) / 32; }
+
+template <int NPOLY>
 __global__ void __launch_bounds__(kTcThreads, 1)
 bank_smooth_tc_kernel(const __grid_constant__ CUtensorMap tm_f, const __grid_constant__ BankMaps maps, const SmoothTcParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint8_t* sA = smem;
-  uint8_t* sQf = sA + kTileA;
+  uint8_t* sA = smem;                                       // [mt][128][64] bf16 query tiles
+  uint8_t* sQf = sA + (size_t)p.mt * kTileA;
   uint8_t* sQp = sQf + kStages * kTileQf;
   uint8_t* sP = sQp + kStages * kTileQp;
-  float* sRed = reinterpret_cast<float*>(sP);             // [128][kRedLd] after the pipeline has drained
+  float* sRed = reinterpret_cast<float*>(sQf);             // [mt][128][kRedLd] after the pipeline has drained
   uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * kTileP);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + BAR_COUNT);
   volatile int* abort_flag = reinterpret_cast<volatile int*>(tmem_slot + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int row_tile = blockIdx.x, split = blockIdx.y;
+  const int row_group = blockIdx.x, split = blockIdx.y;
   const int cta = blockIdx.y * gridDim.x + blockIdx.x;
+  const int tile0 = row_group * p.mt;                      // first row tile of this CTA
+  const int M = min(p.mt, p.row_tiles - tile0);            // row tiles it serves (>= 1)
   pdl_launch_dependents();                                 // the next kernel may start its prologue
   const long long nktiles = (long long)p.nseg * p.tps;
   // Key tiles are dealt round-robin to the splits: tile u = split + t*nsplit of the enumeration that starts at the
   // OWN shard, so every CTA begins with local tiles while its remote ones are already in flight.
   const int T = (int)((nktiles - split + p.nsplit - 1) / p.nsplit);      // >= 1: nsplit <= nktiles
+  const int J = T * M;                                                   // (key tile, row tile) units, row tile fastest
   auto tile_of = [&](int t, int* seg) {                                  // -> first bank row of the tile inside its shard
     const long long u = split + (long long)t * p.nsplit;
     const int si = (int)(u / p.tps);
@@ -190,8 +218,8 @@ bank_smooth_tc_kernel(const __grid_constant__ CUtensorMap tm_f, const __grid_con
   if (warp == 0) {
     // ================= TMA producer =================
     if (lane == 0) {
-      tc::mbar_arrive_expect_tx(&bars[BAR_A], kTileA);
-      tc::tma_load_2d(sA, &tm_f, 0, row_tile * kBM, &bars[BAR_A]);
+      tc::mbar_arrive_expect_tx(&bars[BAR_A], (uint32_t)M * kTileA);
+      for (int m = 0; m < M; ++m) tc::tma_load_2d(sA + (size_t)m * kTileA, &tm_f, 0, (tile0 + m) * kBM, &bars[BAR_A]);
     }
     if (p.arenas) {
       // multi-rank bank: every rank's enqueue of the previous step must have landed (its flag was published a
@@ -220,35 +248,40 @@ bank_smooth_tc_kernel(const __grid_constant__ CUtensorMap tm_f, const __grid_con
     if (lane == 0) {
       constexpr uint32_t idesc1 = tc::idesc_bf16_f32(kBM, kBN);
       constexpr uint32_t idesc2 = tc::idesc_bf16_f32(kBM, kCP);
-      const uint64_t a_desc = tc::smem_desc_sw128(tc::smem_u32(sA));
       tc::mbar_wait(&bars[BAR_A], 0, abort_flag);
-      B200SSL_STAMP(p.dbg, cta, 2);                         // query tile landed (TMA)
-      auto gemm1 = [&](int t) {       // S[b] = F Qf^T   (K = 64 -> 4 x UMMA_K 16)
-        const int s = t % kStages, b = t & 1;
-        tc::mbar_wait(&bars[BAR_KV_FULL + s], (t / kStages) & 1, abort_flag);
-        if (t >= 2) tc::mbar_wait(&bars[BAR_S_EMPTY + b], ((t >> 1) - 1) & 1, abort_flag);
+      B200SSL_STAMP(p.dbg, cta, 2);                         // query tiles landed (TMA)
+      // unit j = (key tile t, row tile m), m fastest: S[j & 1] = F_m Qf_t^T   (K = 64 -> 4 x UMMA_K 16)
+      auto gemm1 = [&](int j, int t, int m) {
+        const int s = t % kStages, b = j & 1;
+        if (m == 0) tc::mbar_wait(&bars[BAR_KV_FULL + s], (t / kStages) & 1, abort_flag);
+        if (j >= 2) tc::mbar_wait(&bars[BAR_S_EMPTY + b], ((j >> 1) - 1) & 1, abort_flag);
         tc::tcgen05_fence_after();
+        const uint64_t a_desc = tc::smem_desc_sw128(tc::smem_u32(sA + (size_t)m * kTileA));
         const uint64_t b_desc = tc::smem_desc_sw128(tc::smem_u32(sQf + s * kTileQf));
 #pragma unroll
         for (int k = 0; k < 4; ++k) tc::mma_bf16_ss(tmem + b * kBN, a_desc + 2 * k, b_desc + 2 * k, idesc1, k > 0);
         tc::mma_commit(&bars[BAR_S_FULL + b]);
       };
-      gemm1(0);
-      for (int t = 0; t < T; ++t) {
-        if (t + 1 < T) gemm1(t + 1);
+      gemm1(0, 0, 0);
+      int t = 0, m = 0;                                      // (t, m) of unit j
+      for (int j = 0; j < J; ++j) {
+        int tn = t, mn = m + 1;                              // (t, m) of unit j + 1
+        if (mn == M) { mn = 0; ++tn; }
+        if (j + 1 < J) gemm1(j + 1, tn, mn);
         const int s = t % kStages;
-        const int pb = t & 1;                                // P is double buffered like S: exp of tile t+1 overlaps GEMM2 of t
-        tc::mbar_wait(&bars[BAR_P_FULL + pb], (t >> 1) & 1, abort_flag);
+        const int pb = j & 1;                                // P is double buffered like S: exp of unit j+1 overlaps GEMM2 of j
+        tc::mbar_wait(&bars[BAR_P_FULL + pb], (j >> 1) & 1, abort_flag);
         tc::tcgen05_fence_after();
 #pragma unroll
-        for (int kb = 0; kb < 2; ++kb) {   // [numer | rowsum] += P [QpT | 1]^T   (K = 128 keys -> 2 sub-tiles x 4 x UMMA_K 16)
+        for (int kb = 0; kb < 2; ++kb) {   // [numer | rowsum]_m += P [QpT | 1]^T   (K = 128 keys -> 2 sub-tiles x 4 x UMMA_K 16)
           const uint64_t pa = tc::smem_desc_sw128(tc::smem_u32(sP + pb * kTileP + kb * kSubP));
           const uint64_t qb = tc::smem_desc_sw128(tc::smem_u32(sQp + s * kTileQp + kb * kSubQp));
 #pragma unroll
-          for (int k = 0; k < 4; ++k) tc::mma_bf16_ss(tmem + 2 * kBN, pa + 2 * k, qb + 2 * k, idesc2, (t | kb | k) != 0);
+          for (int k = 0; k < 4; ++k) tc::mma_bf16_ss(tmem + 2 * kBN + m * kCP, pa + 2 * k, qb + 2 * k, idesc2, (t | kb | k) != 0);
         }
-        tc::mma_commit(&bars[BAR_KV_EMPTY + s]);
+        if (m == M - 1) tc::mma_commit(&bars[BAR_KV_EMPTY + s]);   // the key tile has served every row tile
         tc::mma_commit(&bars[BAR_P_EMPTY + pb]);
+        t = tn; m = mn;
       }
       tc::mma_commit(&bars[BAR_ACC]);
     }
@@ -258,28 +291,29 @@ bank_smooth_tc_kernel(const __grid_constant__ CUtensorMap tm_f, const __grid_con
     const int half = colq >> 1, c2 = colq & 1;              // P sub-tile (64 keys) and 32-column group inside it
     const int r_in = quarter * 32 + lane;
     const uint32_t lane_addr = tmem + ((uint32_t)(quarter * 32) << 16);
-    for (int t = 0; t < T; ++t) {
-      const int b = t & 1;
-      tc::mbar_wait(&bars[BAR_S_FULL + b], (t >> 1) & 1, abort_flag);
-      if (t == 0 && threadIdx.x == 64) B200SSL_STAMP(p.dbg, cta, 3);   // first S tile ready (TMA + GEMM1)
+    for (int j = 0; j < J; ++j) {
+      const int b = j & 1;
+      tc::mbar_wait(&bars[BAR_S_FULL + b], (j >> 1) & 1, abort_flag);
+      if (j == 0 && threadIdx.x == 64) B200SSL_STAMP(p.dbg, cta, 3);   // first S tile ready (TMA + GEMM1)
       tc::tcgen05_fence_after();
       {
         uint32_t r[32];
         tc::tmem_ld_32x32(lane_addr + b * kBN + colq * 32, r);
         tc::tmem_ld_wait();
         tc::tcgen05_fence_before();
-        tc::mbar_arrive(&bars[BAR_S_EMPTY + b]);            // S[b] is in registers: GEMM1 of tile t+2 may overwrite it
+        tc::mbar_arrive(&bars[BAR_S_EMPTY + b]);            // S[b] is in registers: GEMM1 of unit j+2 may overwrite it
         // keys beyond the bank need no mask: their QpT columns (incl. the ones column) are TMA zero fill
         uint32_t w[16];
 #pragma unroll
         for (int e = 0; e < 16; ++e) {
-          const float e0 = ex2_approx(__uint_as_float(r[2 * e]) * p.scale);                  // comatch.py:180
-          const float e1 = ex2_approx(__uint_as_float(r[2 * e + 1]) * p.scale);
+          const float s0 = __uint_as_float(r[2 * e]), s1 = __uint_as_float(r[2 * e + 1]);               // comatch.py:180
+          const float e0 = poly_slot<NPOLY>(2 * e) ? ex2_poly(s0, p.scale, p.s_min) : ex2_approx(s0 * p.scale);
+          const float e1 = poly_slot<NPOLY>(2 * e + 1) ? ex2_poly(s1, p.scale, p.s_min) : ex2_approx(s1 * p.scale);
           const __nv_bfloat162 h = __floats2bfloat162_rn(e0, e1);
           w[e] = *reinterpret_cast<const uint32_t*>(&h);
         }
-        // the P buffer of tile t-2 must have been consumed -- only now, after the exponentials
-        if (t >= 2) tc::mbar_wait(&bars[BAR_P_EMPTY + b], ((t >> 1) - 1) & 1, abort_flag);
+        // the P buffer of unit j-2 must have been consumed -- only now, after the exponentials
+        if (j >= 2) tc::mbar_wait(&bars[BAR_P_EMPTY + b], ((j >> 1) - 1) & 1, abort_flag);
 #pragma unroll
         for (int q = 0; q < 4; ++q)
           *reinterpret_cast<uint4*>(sP + b * kTileP + half * kSubP + tc::sw128_offset(r_in, c2 * 4 + q)) =
@@ -287,16 +321,16 @@ bank_smooth_tc_kernel(const __grid_constant__ CUtensorMap tm_f, const __grid_con
       }
       tc::fence_proxy_async_smem();               // generic-proxy writes of P -> visible to the tensor core
       tc::mbar_arrive(&bars[BAR_P_FULL + b]);
-      if (t == T - 1 && threadIdx.x == 64) B200SSL_STAMP(p.dbg, cta, 4);   // last exp tile done
+      if (j == J - 1 && threadIdx.x == 64) B200SSL_STAMP(p.dbg, cta, 4);   // last exp tile done
     }
-    tc::mbar_wait(&bars[BAR_ACC], 0, abort_flag);           // all MMAs retired: P smem is free, accumulator final
+    tc::mbar_wait(&bars[BAR_ACC], 0, abort_flag);           // all MMAs retired: pipeline smem is free, accumulators final
     if (threadIdx.x == 64) B200SSL_STAMP(p.dbg, cta, 5);
     tc::tcgen05_fence_after();
-    if (colq == 0) {                                        // accumulator [numer | rowsum] -> fp32 reduction tile in smem
+    if (colq < M) {                                         // warp group colq stages row tile colq: [numer | rowsum] -> fp32 tile
       uint32_t r[32];
-      tc::tmem_ld_32x32(lane_addr + 2 * kBN, r);
+      tc::tmem_ld_32x32(lane_addr + 2 * kBN + colq * kCP, r);
       tc::tmem_ld_wait();
-      float4* dst = reinterpret_cast<float4*>(sRed + r_in * kRedLd);
+      float4* dst = reinterpret_cast<float4*>(sRed + ((size_t)colq * kBM + r_in) * kRedLd);
 #pragma unroll
       for (int q = 0; q < 8; ++q)
         dst[q] = make_float4(__uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1]), __uint_as_float(r[4 * q + 2]),
@@ -309,7 +343,7 @@ bank_smooth_tc_kernel(const __grid_constant__ CUtensorMap tm_f, const __grid_con
     tc::tcgen05_fence_after();
     tc::tmem_dealloc(tmem, kTmemCols);
   }
-  if (threadIdx.x == 0) B200SSL_STAMP(p.dbg, cta, 6);      // accumulator staged, TMEM released
+  if (threadIdx.x == 0) B200SSL_STAMP(p.dbg, cta, 6);      // accumulators staged, TMEM released
   if (p.arenas && threadIdx.x == 0) {
     // every key tile of this CTA has been consumed.  The last CTA of the grid tells the peers that this rank no
     // longer reads the shards of this step: their enqueue may overwrite rows.  Nothing this rank WROTE has to be
@@ -325,31 +359,31 @@ bank_smooth_tc_kernel(const __grid_constant__ CUtensorMap tm_f, const __grid_con
     }
   }
 
-  // ---- fold the splits of this row tile: first inside the cluster through distributed shared memory ----
+  // ---- fold the splits of this row group: first inside the cluster through distributed shared memory ----
   cg::cluster_group cluster = cg::this_cluster();
   const int CL = p.cluster;
   const int crank = CL > 1 ? (int)cluster.block_rank() : 0;
-  if (CL > 1) cluster.sync();                              // every CTA's reduction tile is complete and visible
-  const int RB = kBM / CL;                                 // rows this CTA reduces
+  if (CL > 1) cluster.sync();                              // every CTA's reduction tiles are complete and visible
+  const int RB = kBM / CL;                                 // rows of every row tile this CTA reduces
   const int W = p.W, C = p.C;
   const int outer = split / CL;
-  const long long i0 = (long long)row_tile * kBM;
   const float* peer[kMaxCluster];
 #pragma unroll
   for (int r = 0; r < kMaxCluster; ++r) peer[r] = (CL > 1 && r < CL) ? cluster.map_shared_rank(sRed, r) : sRed;
   const int W4 = W / 4;
-  for (int idx = threadIdx.x; idx < RB * W4; idx += blockDim.x) {
-    const int rr = idx / W4, q4 = idx - rr * W4;
+  for (int idx = threadIdx.x; idx < M * RB * W4; idx += blockDim.x) {
+    const int m = idx / (RB * W4), rem = idx - m * (RB * W4);
+    const int rr = rem / W4, q4 = rem - rr * W4;
     const int row = crank * RB + rr;
     float4 v[kMaxCluster];
 #pragma unroll
     for (int r = 0; r < kMaxCluster; ++r)                  // all remote loads in flight at once
-      if (r < CL) v[r] = *reinterpret_cast<const float4*>(peer[r] + row * kRedLd + 4 * q4);
+      if (r < CL) v[r] = *reinterpret_cast<const float4*>(peer[r] + ((size_t)m * kBM + row) * kRedLd + 4 * q4);
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
     for (int r = 0; r < kMaxCluster; ++r)                  // rank order: deterministic
       if (r < CL) { acc.x += v[r].x; acc.y += v[r].y; acc.z += v[r].z; acc.w += v[r].w; }
-    const long long grow = i0 + row;
+    const long long grow = (long long)(tile0 + m) * kBM + row;
     const float vv[4] = {acc.x, acc.y, acc.z, acc.w};
     if (p.nouter == 1) {
       if (grow < p.rows) {
@@ -368,55 +402,119 @@ bank_smooth_tc_kernel(const __grid_constant__ CUtensorMap tm_f, const __grid_con
   if (threadIdx.x == 0) B200SSL_STAMP(p.dbg, cta, 7);      // cluster fold done
   if (p.nouter == 1) return;
 
-  // ---- then across clusters: last CTA of the row tile folds the `nouter` partials in order ----
-  __shared__ bool s_last;
+  // ---- then across clusters: the slice (row tile, cluster rank) = RB rows is folded, in cluster order, by whichever of
+  // the `nouter` CTAs that wrote it arrives last -- the outer folds of a launch run on M * CL CTAs in parallel ----
+  __shared__ int s_last[kMaxMT];
   __threadfence();
   __syncthreads();
-  if (threadIdx.x == 0) s_last = (atomicAdd(&p.tickets[row_tile], 1u) == (unsigned)p.nsplit - 1);
+  if (threadIdx.x < M)
+    s_last[threadIdx.x] = atomicAdd(&p.tickets[(tile0 + threadIdx.x) * kMaxCluster + crank], 1u) == (unsigned)p.nouter - 1;
   __syncthreads();
-  if (threadIdx.x == 0) B200SSL_STAMP(p.dbg, cta, 8);      // ticket taken
-  if (!s_last) return;
-  __threadfence();
-  const int mrows = (int)min((long long)kBM, p.rows - i0);
-  fold_splits_vec4(reinterpret_cast<const float4*>(p.part + (size_t)i0 * W), (size_t)p.rows_pad * W / 4, p.nouter,
-                   mrows * W / 4, [&](int i, float4 v) {
-                     const float vv[4] = {v.x, v.y, v.z, v.w};
+  if (threadIdx.x == 0) B200SSL_STAMP(p.dbg, cta, 8);      // tickets taken
+  for (int m = 0; m < M; ++m) {
+    if (!s_last[m]) continue;
+    __threadfence();
+    const long long r0 = (long long)(tile0 + m) * kBM + crank * RB;
+    const int mrows = (int)max(0LL, min((long long)RB, p.rows - r0));
+    fold_splits_vec4(reinterpret_cast<const float4*>(p.part + (size_t)r0 * W), (size_t)p.rows_pad * W / 4, p.nouter,
+                     mrows * W / 4, [&](int i, float4 v) {
+                       const float vv[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-                     for (int j = 0; j < 4; ++j) {
-                       const int e = 4 * i + j, row = e / W, col = e - row * W;
-                       if (col < C) p.numer[(i0 + row) * p.numer_ld + col] = vv[j];
-                       else if (col == C) p.rowsum[(i0 + row) * p.rowsum_ld] = vv[j];
-                     }
-                   });
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    p.tickets[row_tile] = 0u;
-    B200SSL_STAMP(p.dbg, cta, 9);                           // fold done (last CTA of the row tile only)
+                       for (int j = 0; j < 4; ++j) {
+                         const int e = 4 * i + j, row = e / W, col = e - row * W;
+                         if (col < C) p.numer[(r0 + row) * p.numer_ld + col] = vv[j];
+                         else if (col == C) p.rowsum[(r0 + row) * p.rowsum_ld] = vv[j];
+                       }
+                     });
   }
+  __syncthreads();
+  if (threadIdx.x < M && s_last[threadIdx.x]) p.tickets[(tile0 + threadIdx.x) * kMaxCluster + crank] = 0u;
+  if (threadIdx.x == 0) B200SSL_STAMP(p.dbg, cta, 9);      // outer folds done
 }
 
-// cluster size (power of two <= 8) and number of clusters per row tile
-void smooth_tc_plan(long long rows, long long ktiles, int* cluster, int* nouter) {
+struct SmoothPlan { int mt, cluster, nouter; };
+
+// A/B aids (tools/k3_tune.py): B200SSL_K3_MT / B200SSL_K3_POLY in the environment, or b200ssl_debug_set_k3 at run time.
+int g_force_mt = getenv("B200SSL_K3_MT") ? atoi(getenv("B200SSL_K3_MT")) : 0;       // 1: no row loop, 2..4: row loop where it fits
+int g_force_poly = getenv("B200SSL_K3_POLY") ? atoi(getenv("B200SSL_K3_POLY")) : -1;   // exponentials (of 32) on the FMA pipe
+
+// How a launch is cut: `mt` row tiles per CTA, and per group of row tiles a cluster of `cluster` CTAs (power of two <= 8,
+// folded through DSMEM) times `nouter` clusters (folded through global partials) that share the key tiles.
+SmoothPlan smooth_tc_plan(long long rows, long long ktiles, bool remote) {
   const long long row_tiles = (rows + kBM - 1) / kBM;
-  int cl = 1;
-  while (cl * 2 <= kMaxCluster && cl * 2 <= ktiles) cl *= 2;
-  long long no = 1;
-  if (ktiles / cl > 8) {                                    // long serial key loops: add clusters while SMs are free
-    no = kNumSMs / (row_tiles * cl);
-    if (no < 1) no = 1;
-    if (no > ktiles / cl) no = ktiles / cl;
+  SmoothPlan pl{1, 1, 1};
+  const int force_mt = g_force_mt;
+  if ((remote || force_mt > 1) && row_tiles <= kMaxMT) {
+    // shards read over NVLink: one CTA serves every row tile from the key tile it staged, so a remote tile is fetched
+    // once per step; all SMs share the key tiles
+    pl.mt = (int)row_tiles;
+    while (pl.cluster * 2 <= kMaxCluster && pl.cluster * 2 <= ktiles) pl.cluster *= 2;
+    long long no = kNumSMs / pl.cluster;
+    if (no > ktiles / pl.cluster) no = ktiles / pl.cluster;
+    pl.nouter = (int)(no < 1 ? 1 : no);
+    return pl;
   }
-  *cluster = cl;
-  *nouter = (int)no;
+  if (row_tiles * ktiles < 2LL * kNumSMs || force_mt == 1) {
+    // latency-bound sizes: the widest cluster, more clusters only for long serial key loops while SMs are free
+    while (pl.cluster * 2 <= kMaxCluster && pl.cluster * 2 <= ktiles) pl.cluster *= 2;
+    long long no = 1;
+    if (ktiles / pl.cluster > 8) {
+      no = kNumSMs / (row_tiles * pl.cluster);
+      if (no < 1) no = 1;
+      if (no > ktiles / pl.cluster) no = ktiles / pl.cluster;
+    }
+    pl.nouter = (int)no;
+    return pl;
+  }
+  // throughput-bound sizes: minimise (waves of one CTA per SM) x (units a CTA runs), unit = one 128 x 128 S tile;
+  // a CTA's fixed cost (prologue, folds) is charged in units.  Row loops (mt > 1) cut the L2 traffic of the bank by mt.
+  double best = 1e300;
+  for (int mt = 1; mt <= kMaxMT; ++mt) {
+    const long long groups = (row_tiles + mt - 1) / mt;
+    for (int cl = 1; cl <= kMaxCluster; cl *= 2) {
+      if (cl > ktiles) break;
+      const long long no_max = ktiles / cl < 64 ? ktiles / cl : 64;
+      for (long long no = 1; no <= no_max; ++no) {
+        const long long ctas = groups * cl * no;
+        const long long waves = (ctas + kNumSMs - 1) / kNumSMs;
+        const long long T = (ktiles + cl * no - 1) / (cl * no);
+        // outer fold: `no` partials of 128 / cl rows read back by one CTA (x2 when it may be last for several row tiles)
+        const double fold = no > 1 ? 1.0 + 0.15 * (double)no / cl * (mt > 1 ? 2.0 : 1.0) : 0.0;
+        const double cost = (double)waves * ((double)mt * (double)T + 2.0 + (cl > 1 ? 0.5 : 0.0) + fold) - 0.01 * mt;
+        if (cost < best) { best = cost; pl = SmoothPlan{mt, cl, (int)no}; }
+      }
+    }
+  }
+  return pl;
+}
+
+template <int NPOLY>
+cudaError_t launch_smooth(const SmoothTcParams& p, const CUtensorMap& tm_f, const BankMaps& maps, dim3 grid, size_t smem, cudaStream_t stream) {
+  static size_t attr_smem = 0;
+  if (smem > attr_smem) {
+    cudaError_t e = cudaFuncSetAttribute(bank_smooth_tc_kernel<NPOLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_request(kMaxMT));
+    if (e != cudaSuccess) return e;
+    attr_smem = smem_request(kMaxMT);
+  }
+  return launch_pdl(PDL_SMOOTH, bank_smooth_tc_kernel<NPOLY>, grid, dim3(kTcThreads, 1, 1), smem, stream, dim3(1, (unsigned)p.cluster, 1), tm_f,
+                    maps, p);
 }
 
 }  // namespace
 
 size_t smooth_tc_workspace_floats(long long rows, long long bank_rows, int classes) {
   const long long row_tiles = (rows + kBM - 1) / kBM;
-  int cl, no;
-  smooth_tc_plan(rows, (bank_rows + kBN - 1) / kBN, &cl, &no);
-  return no > 1 ? (size_t)no * row_tiles * kBM * ((1 + classes + 3) & ~3) : 0;
+  size_t need = 0;
+  for (int remote = 0; remote < 2; ++remote) {             // the sizing call does not know where the bank lives
+    // shards whose rows are not a multiple of the key tile add up to one partial tile each
+    for (int extra = 0; extra <= (remote ? kMaxSeg : 0); extra += kMaxSeg) {
+      const SmoothPlan pl = smooth_tc_plan(rows, (bank_rows + kBN - 1) / kBN + extra, remote != 0);
+      const long long groups = (row_tiles + pl.mt - 1) / pl.mt;
+      const size_t n = pl.nouter > 1 ? (size_t)pl.nouter * groups * pl.mt * kBM * ((1 + classes + 3) & ~3) : 0;
+      if (n > need) need = n;
+    }
+  }
+  return need;
 }
 
 // bf16, dim 64, classes <= 31, bank rows a multiple of 8: the tensor-core path.
@@ -435,14 +533,18 @@ int bank_smooth_tc(const void* feats, const void* queue_feats, const void* queue
   }
   p.rows = rows; p.C = classes; p.W = (1 + classes + 3) & ~3;
   p.scale = (float)(1.4426950408889634 / (double)temperature);
+  p.s_min = -126.f / p.scale;
   p.rowsum = rowsum; p.numer = numer; p.rowsum_ld = rowsum_ld; p.numer_ld = numer_ld; p.dbg = debug_timing_buffer(PDL_SMOOTH);
-  smooth_tc_plan(rows, (long long)p.nseg * p.tps, &p.cluster, &p.nouter);
+  const SmoothPlan pl = smooth_tc_plan(rows, (long long)p.nseg * p.tps, direct);
+  p.mt = pl.mt; p.cluster = pl.cluster; p.nouter = pl.nouter;
   p.nsplit = p.cluster * p.nouter;
   const long long row_tiles = (rows + kBM - 1) / kBM;
-  p.rows_pad = row_tiles * kBM;
-  const size_t need = kWsHeaderBytes + sizeof(float) * (p.nouter > 1 ? (size_t)p.nouter * row_tiles * kBM * p.W : 0);
+  const long long groups = (row_tiles + p.mt - 1) / p.mt;
+  p.row_tiles = (int)row_tiles;
+  p.rows_pad = groups * p.mt * kBM;
+  const size_t need = kWsHeaderBytes + sizeof(float) * (p.nouter > 1 ? (size_t)p.nouter * p.rows_pad * p.W : 0);
   if (workspace_bytes < need) return fail(B200SSL_E_WORKSPACE, "%s: workspace %zu < %zu bytes", fn, workspace_bytes, need);
-  if ((size_t)row_tiles * 4 > kWsTicket2Bytes) return fail(B200SSL_E_SHAPE, "%s: too many row tiles", fn);
+  if ((size_t)groups * p.mt * kMaxCluster * 4 > kWsTicket2Bytes) return fail(B200SSL_E_SHAPE, "%s: too many row tiles", fn);
   p.tickets = reinterpret_cast<unsigned*>(static_cast<char*>(workspace) + kWsTicketBytes);
   p.part = reinterpret_cast<float*>(static_cast<char*>(workspace) + kWsHeaderBytes);
   CUtensorMap tm_f;
@@ -455,18 +557,39 @@ int bank_smooth_tc(const void* feats, const void* queue_feats, const void* queue
     if (int e = tc::make_tmap_bf16_2d(&maps.qf[s], qf, (uint64_t)seg_rows, 64, 128, kBN, 64)) return e;
     if (int e = tc::make_tmap_bf16_2d(&maps.qpt[s], qpt, kCP, (uint64_t)seg_rows, (uint64_t)seg_rows * 2, kCP, 64)) return e;
   }
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(bank_smooth_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemRequest);
-    if (e != cudaSuccess) return fail((int)e, "%s: cudaFuncSetAttribute: %s", fn, cudaGetErrorString(e));
-    attr_set = true;
-  }
-  static_assert(kSmemData + 1024 + 256 <= kSmemRequest, "shared memory budget");
-  static_assert(kBM * kRedLd * sizeof(float) <= kTileP, "reduction tile must fit in the P buffer");
-  cudaError_t e = launch_pdl(PDL_SMOOTH, bank_smooth_tc_kernel, dim3((unsigned)row_tiles, (unsigned)p.nsplit, 1), dim3(kTcThreads, 1, 1),
-                             kSmemRequest, stream, dim3(1, (unsigned)p.cluster, 1), tm_f, maps, p);
+  static_assert(smem_request(kMaxMT) <= 227 * 1024, "shared memory budget");
+  static_assert((size_t)kMaxMT * kRedTile <= kSmemStages, "the reduction tiles must fit in the drained pipeline buffers");
+  static_assert(2 * kBN + kMaxMT * kCP <= (int)kTmemCols, "TMEM budget");
+  // share of the exponentials computed on the FMA pipe (of 32 per thread and S tile); throughput-bound launches only --
+  // at latency-bound sizes the MUFU unit is idle anyway
+  const int poly_env = g_force_poly;
+  const bool big = row_tiles * ((long long)p.nseg * p.tps) >= 8LL * kNumSMs;
+  const int npoly = poly_env >= 0 ? poly_env : (big ? 12 : 0);
+  const dim3 grid((unsigned)groups, (unsigned)p.nsplit, 1);
+  const size_t smem = smem_request(p.mt);
+  cudaError_t e;
+  if (npoly >= 20) e = launch_smooth<20>(p, tm_f, maps, grid, smem, stream);
+  else if (npoly >= 16) e = launch_smooth<16>(p, tm_f, maps, grid, smem, stream);
+  else if (npoly >= 12) e = launch_smooth<12>(p, tm_f, maps, grid, smem, stream);
+  else if (npoly >= 8) e = launch_smooth<8>(p, tm_f, maps, grid, smem, stream);
+  else e = launch_smooth<0>(p, tm_f, maps, grid, smem, stream);
   if (e != cudaSuccess) return fail((int)e, "%s: cudaLaunchKernelEx: %s", fn, cudaGetErrorString(e));
   return check_launch(fn);
 }
 
 }  // namespace b200ssl
+
+extern "C" void b200ssl_debug_set_k3(int32_t row_tiles_per_cta, int32_t poly_of_32) {
+  b200ssl::g_force_mt = row_tiles_per_cta;
+  b200ssl::g_force_poly = poly_of_32;
+}
+
+// Launch geometry of the tensor-core K3 for a problem size (host only; CPU tests and tools).
+extern "C" int b200ssl_debug_smooth_plan(int64_t rows, int64_t bank_rows, int32_t remote_shards, int32_t* out_mt_cluster_nouter) {
+  if (!out_mt_cluster_nouter || rows <= 0 || bank_rows <= 0) return b200ssl::fail(B200SSL_E_ARG, "b200ssl_debug_smooth_plan: bad argument");
+  const b200ssl::SmoothPlan pl = b200ssl::smooth_tc_plan(rows, (bank_rows + b200ssl::kBN - 1) / b200ssl::kBN, remote_shards != 0);
+  out_mt_cluster_nouter[0] = pl.mt;
+  out_mt_cluster_nouter[1] = pl.cluster;
+  out_mt_cluster_nouter[2] = pl.nouter;
+  return 0;
+}

@@ -221,10 +221,21 @@ __global__ void __launch_bounds__(kRowThreads) fixmatch_head_kernel(const HeadPa
 }
 
 // ============================================================ f2 ============
+// Targets: F.cross_entropy's ignore_index (-100) drops a row (zero loss, zero gradient, not counted in the mean);
+// any other label outside [0, C) is a caller bug: the row is dropped too and the sticky counter `bad_labels`
+// (workspace slot kWsBadLabelSlot, read by b200ssl_bad_label_count) is raised instead of reading out of bounds.
+constexpr int kIgnoreIndex = -100;
+constexpr int kWsBadLabelSlot = 60;
+__device__ __forceinline__ int checked_label(long long y, int C, unsigned* bad) {
+  if (y >= 0 && y < C) return (int)y;
+  if (y != kIgnoreIndex) atomicAdd(bad, 1u);
+  return -1;
+}
+
 struct LabeledParams {
   const void* x; const long long* y; const float* cw; void* gx;
   long long rows; int C; int poly; float eps;
-  float* out; float* partials; unsigned* ticket;
+  float* out; float* partials; unsigned* ticket; unsigned* bad_labels;
 };
 
 template <typename T, int LPR, int EPL>
@@ -239,9 +250,12 @@ __global__ void __launch_bounds__(kRowThreads) labeled_ce_kernel(const LabeledPa
   const long long ntiles = (p.rows + ROWS - 1) / ROWS;
   // normaliser: rows (poly / unweighted) or sum of w[y] (F.cross_entropy weighted mean)
   __shared__ float s_norm;
-  if (!p.poly && p.cw) {
+  if (!p.poly) {
     float v[1] = {0.f};
-    for (long long i = threadIdx.x; i < p.rows; i += blockDim.x) v[0] += p.cw[p.y[i]];
+    for (long long i = threadIdx.x; i < p.rows; i += blockDim.x) {
+      const long long yi = p.y[i];
+      if (yi >= 0 && yi < C) v[0] += p.cw ? p.cw[yi] : 1.f;
+    }
     block_sum<1>(v);
     if (threadIdx.x == 0) s_norm = v[0];
   } else if (threadIdx.x == 0) {
@@ -263,14 +277,17 @@ __global__ void __launch_bounds__(kRowThreads) labeled_ce_kernel(const LabeledPa
     float mx, sum;
     row_load<LPR, EPL>(srow, C, gl, valid, x);
     row_softmax_stats<LPR, EPL>(x, e, mx, sum);
-    const int y = valid ? (int)p.y[row0 + r] : 0;
-    const float wy = (valid && p.cw) ? p.cw[y] : 1.f;
-    const float xy = row_pick<LPR, EPL>(x, gl, valid ? y : -1);
+    int y = -1;
+    if (valid && gl == 0) y = checked_label(p.y[row0 + r], C, p.bad_labels);
+    y = __shfl_sync(0xffffffffu, y, rw * LPR);                 // lane 0 of the row group validated (and counted) it
+    const bool live = valid && y >= 0;
+    const float wy = (live && p.cw) ? p.cw[y] : 1.f;
+    const float xy = row_pick<LPR, EPL>(x, gl, live ? y : -1);
     const float ce = -((xy - mx) - logf(sum));
     const float pt = __fdiv_rn(expf(xy - mx), sum);
     const float rowl = p.poly ? (wy * ce + p.eps * (1.f - pt)) : wy * ce;
-    if (valid && gl == 0) acc[0] += rowl;
-    const float coef = (p.poly ? (wy + p.eps * pt) : wy) * inv_norm;
+    if (live && gl == 0) acc[0] += rowl;
+    const float coef = live ? (p.poly ? (wy + p.eps * pt) : wy) * inv_norm : 0.f;
     if (valid) {
 #pragma unroll
       for (int k = 0; k < EPL; ++k) {
@@ -285,6 +302,92 @@ __global__ void __launch_bounds__(kRowThreads) labeled_ce_kernel(const LabeledPa
   block_sum<1>(acc);
   float total[1];
   if (grid_reduce_last<1>(acc, p.partials, p.ticket, total) && threadIdx.x == 0) p.out[0] = total[0] / s_norm;
+}
+
+
+// ---- f2, un-reduced: per-row losses (reduction='none' / 'sum', soft targets) ------------------------------------------
+// code/loss.py:118-124 + PolyLoss reduction='none' (:357-359): loss_rows[i] and the gradient of loss_rows[i] w.r.t. its
+// own logits row (unit upstream); autograd's per-row upstream gradient is applied by scale_rows_kernel.
+struct RowCeParams {
+  const void* x; const long long* y; const float* soft; const float* cw; void* gx; float* loss_rows;
+  long long rows; int C; int poly; float eps; unsigned* bad_labels;
+};
+
+template <typename T, int LPR, int EPL>
+__global__ void __launch_bounds__(kRowThreads) ce_rows_kernel(const RowCeParams p) {
+  using Cfg = RowCfg<LPR, EPL>;
+  constexpr int ROWS = Cfg::kRowsPerTile;
+  extern __shared__ float smem[];
+  const int C = p.C;
+  float* sx = smem;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int gl = lane % LPR, rw = lane / LPR;
+  const long long ntiles = (p.rows + ROWS - 1) / ROWS;
+  for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const long long row0 = tile * ROWS;
+    const int nrows = (int)min((long long)ROWS, p.rows - row0);
+    const int cnt = nrows * C;
+    tile_g2s(static_cast<const T*>(p.x) + row0 * C, sx, cnt);
+    __syncthreads();
+    const int r = warp * Cfg::kRowsPerWarp + rw;
+    const bool valid = r < nrows;
+    float* srow = sx + r * C;
+    float x[EPL], e[EPL];
+    float mx, sum;
+    row_load<LPR, EPL>(srow, C, gl, valid, x);
+    row_softmax_stats<LPR, EPL>(x, e, mx, sum);
+    const float logsum = logf(sum);
+    float rowl;
+    if (p.soft) {                                            // loss.py:120-124: sum_c -t_c log_softmax(x)_c
+      float t[EPL], d = 0.f, ts = 0.f;
+#pragma unroll
+      for (int k = 0; k < EPL; ++k) {
+        const int c = gl + k * LPR;
+        t[k] = (valid && c < C) ? p.soft[(row0 + r) * C + c] : 0.f;
+        if (valid && c < C) { d += -t[k] * ((x[k] - mx) - logsum); ts += t[k]; }
+      }
+      rowl = group_sum<LPR>(d);
+      const float tsum = group_sum<LPR>(ts);
+      if (valid) {
+#pragma unroll
+        for (int k = 0; k < EPL; ++k) {
+          const int c = gl + k * LPR;
+          if (c < C) srow[c] = __fdiv_rn(e[k], sum) * tsum - t[k];
+        }
+      }
+    } else {
+      int y = -1;
+      if (valid && gl == 0) y = checked_label(p.y[row0 + r], C, p.bad_labels);
+      y = __shfl_sync(0xffffffffu, y, rw * LPR);
+      const bool live = valid && y >= 0;
+      const float wy = (live && p.cw) ? p.cw[y] : 1.f;
+      const float xy = row_pick<LPR, EPL>(x, gl, live ? y : -1);
+      const float ce = -((xy - mx) - logsum);
+      const float pt = __fdiv_rn(expf(xy - mx), sum);
+      rowl = live ? (p.poly ? (wy * ce + p.eps * (1.f - pt)) : wy * ce) : 0.f;
+      const float coef = live ? (p.poly ? (wy + p.eps * pt) : wy) : 0.f;
+      if (valid) {
+#pragma unroll
+        for (int k = 0; k < EPL; ++k) {
+          const int c = gl + k * LPR;
+          if (c < C) srow[c] = coef * (__fdiv_rn(e[k], sum) - (c == y ? 1.f : 0.f));
+        }
+      }
+    }
+    if (valid && gl == 0) p.loss_rows[row0 + r] = rowl;
+    __syncthreads();
+    tile_s2g(sx, static_cast<T*>(p.gx) + row0 * C, cnt);
+    __syncthreads();
+  }
+}
+
+// out[i, :] = in[i, :] * row_scale[i]   (out-of-place: the stash survives a second backward)
+template <typename T>
+__global__ void scale_rows_kernel(const T* in, T* out, long long rows, int C, const float* row_scale) {
+  const long long n = rows * C;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += stride)
+    out[i] = from_f32<T>(to_f32<T>(in[i]) * row_scale[i / C]);
 }
 
 // ============================================================ K2 ============
@@ -923,7 +1026,7 @@ extern "C" int b200ssl_labeled_ce_fwd_bwd(const void* logits, const int64_t* tar
   LabeledParams p{logits, reinterpret_cast<const long long*>(targets), class_weights, grad, rows, classes,
                   poly ? 1 : 0, poly ? epsilon : 0.f, out_scalar,
                   reinterpret_cast<float*>(static_cast<char*>(workspace) + kWsHeaderBytes),
-                  reinterpret_cast<unsigned*>(workspace) + 1};
+                  reinterpret_cast<unsigned*>(workspace) + 1, reinterpret_cast<unsigned*>(workspace) + kWsBadLabelSlot};
   B200SSL_ROW_DISPATCH(dtype, classes, {
     RowLaunch l = row_launch<LPR, EPL>(rows, classes, 1);
     auto k = labeled_ce_kernel<T, LPR, EPL>;
@@ -931,6 +1034,48 @@ extern "C" int b200ssl_labeled_ce_fwd_bwd(const void* logits, const int64_t* tar
     k<<<l.grid, kRowThreads, l.smem, as_stream(stream)>>>(p);
   });
   return check_launch(fn);
+}
+
+extern "C" int b200ssl_ce_rows_fwd_bwd(const void* logits, const int64_t* targets, const float* soft_targets,
+                                       const float* class_weights, void* grad_unit, float* loss_rows, int64_t rows,
+                                       int32_t classes, int32_t dtype, int32_t poly, float epsilon, void* workspace,
+                                       size_t workspace_bytes, void* stream) {
+  const char* fn = "b200ssl_ce_rows_fwd_bwd";
+  if (int e = check_rows(fn, rows, classes, dtype)) return e;
+  if (!logits || !grad_unit || !loss_rows) return fail(B200SSL_E_NULL, "%s: NULL tensor", fn);
+  if ((targets == nullptr) == (soft_targets == nullptr)) return fail(B200SSL_E_ARG, "%s: exactly one of targets / soft_targets", fn);
+  if (int e = check_ws(fn, workspace, workspace_bytes, kWsHeaderBytes)) return e;
+  RowCeParams p{logits, reinterpret_cast<const long long*>(targets), soft_targets, class_weights, grad_unit, loss_rows, rows,
+                classes, poly ? 1 : 0, poly ? epsilon : 0.f, reinterpret_cast<unsigned*>(workspace) + kWsBadLabelSlot};
+  B200SSL_ROW_DISPATCH(dtype, classes, {
+    RowLaunch l = row_launch<LPR, EPL>(rows, classes, 1);
+    auto k = ce_rows_kernel<T, LPR, EPL>;
+    if (int e = set_smem(k, l.smem)) return e;
+    k<<<l.grid, kRowThreads, l.smem, as_stream(stream)>>>(p);
+  });
+  return check_launch(fn);
+}
+
+extern "C" int b200ssl_scale_rows(const void* grad_in, void* grad_out, int64_t rows, int32_t classes, int32_t dtype,
+                                  const float* row_scale, void* stream) {
+  const char* fn = "b200ssl_scale_rows";
+  if (int e = check_rows(fn, rows, classes, dtype)) return e;
+  if (!grad_in || !grad_out || !row_scale) return fail(B200SSL_E_NULL, "%s: NULL tensor", fn);
+  long long blocks = (rows * classes + 255) / 256;
+  if (blocks > 8 * kNumSMs) blocks = 8 * kNumSMs;
+  if (dtype == B200SSL_F32)
+    scale_rows_kernel<float><<<(int)blocks, 256, 0, as_stream(stream)>>>(static_cast<const float*>(grad_in), static_cast<float*>(grad_out), rows, classes, row_scale);
+  else
+    scale_rows_kernel<__nv_bfloat16><<<(int)blocks, 256, 0, as_stream(stream)>>>(static_cast<const __nv_bfloat16*>(grad_in), static_cast<__nv_bfloat16*>(grad_out), rows, classes, row_scale);
+  return check_launch(fn);
+}
+
+extern "C" int b200ssl_bad_label_count(void* workspace, uint32_t* count, int32_t reset) {
+  if (!workspace || !count) return fail(B200SSL_E_NULL, "b200ssl_bad_label_count: NULL pointer");
+  unsigned* slot = reinterpret_cast<unsigned*>(workspace) + kWsBadLabelSlot;
+  cudaError_t e = cudaMemcpy(count, slot, sizeof(uint32_t), cudaMemcpyDeviceToHost);
+  if (e == cudaSuccess && reset) e = cudaMemset(slot, 0, sizeof(uint32_t));
+  return e == cudaSuccess ? 0 : fail((int)e, "b200ssl_bad_label_count: %s", cudaGetErrorString(e));
 }
 
 extern "C" int b200ssl_comatch_da(const void* logits_u_w, int64_t rows, int32_t classes, int32_t dtype,

@@ -20,7 +20,7 @@ import torch.nn as nn
 
 from . import _native as N
 
-__all__ = ["consistency_loss", "consistency_loss_dual", "ce_loss", "PolyLoss", "fixmatch_head"]
+__all__ = ["consistency_loss", "consistency_loss_dual", "ce_loss", "PolyLoss", "fixmatch_head", "bad_label_count"]
 
 
 def _as_rows(t: torch.Tensor, what: str) -> torch.Tensor:
@@ -57,12 +57,17 @@ class _FixMatchHead(torch.autograd.Function):
             out.data_ptr(), N.ptr(idx), N.ptr(mask), ws, ws_bytes, N.stream_ptr(dev)), "fixmatch_head_fwd_bwd")
         ctx.save_for_backward(grad_s, grad_s2)
         ctx.has_s2 = s2 is not None
+        ctx.done = False
         ctx.set_materialize_grads(False)
         ctx.mark_non_differentiable(*(t for t in (idx, mask) if t is not None))
         return out[0], out[1], out[2], idx, mask
 
     @staticmethod
     def backward(ctx, g_loss, g_mask_mean, g_loss2, g_idx, g_mask):
+        if ctx.done:
+            raise RuntimeError("consistency_loss: backward through the fused head twice (its stashed gradient is scaled in "
+                               "place by the first backward; recompute the loss instead of retain_graph=True)")
+        ctx.done = True
         grad_s, grad_s2 = ctx.saved_tensors
         dev = grad_s.device
         lib = N.lib()
@@ -147,10 +152,15 @@ class _LabeledCE(torch.autograd.Function):
             x.data_ptr(), y.data_ptr(), N.ptr(cw), grad.data_ptr(), rows, classes, N.dtype_enum(x),
             1 if poly else 0, float(epsilon), out.data_ptr(), ws, ws_bytes, N.stream_ptr(dev)), "labeled_ce_fwd_bwd")
         ctx.save_for_backward(grad)
+        ctx.done = False
         return out[0]
 
     @staticmethod
     def backward(ctx, g):
+        if ctx.done:
+            raise RuntimeError("ce_loss: backward through the fused criterion twice (its stashed gradient is scaled in "
+                               "place by the first backward; recompute the loss instead of retain_graph=True)")
+        ctx.done = True
         (grad,) = ctx.saved_tensors
         g = g.detach().to(torch.float32).reshape(1).contiguous()
         N.check(N.lib().b200ssl_scale_inplace(grad.data_ptr(), grad.numel(), N.dtype_enum(grad), g.data_ptr(), 1.0,
@@ -158,19 +168,80 @@ class _LabeledCE(torch.autograd.Function):
         return grad, None, None, None, None
 
 
+class _RowCE(torch.autograd.Function):
+    """Un-reduced criterion (loss.py:118-124; PolyLoss ``reduction='none'``): per-row losses, with the per-row
+    gradient stashed by the same launch and chained out of place in backward (safe under ``retain_graph``)."""
+
+    @staticmethod
+    def forward(ctx, logits, targets, class_weights, poly, epsilon, soft):
+        dev = N.require_cuda(logits, targets, class_weights, what="ce_loss")
+        x = _as_rows(logits.detach(), "logits")
+        rows, classes = x.shape
+        y = t = cw = None
+        if soft:
+            if targets.shape != x.shape:
+                raise ValueError(f"soft targets {tuple(targets.shape)} must match logits {tuple(x.shape)}")
+            t = targets.detach().to(torch.float32).contiguous()
+        else:
+            y = targets.detach()
+            if y.dim() == 2 and y.shape[1] == 1:
+                y = y.squeeze(1)
+            if y.dim() != 1 or y.shape[0] != rows:
+                raise ValueError(f"targets {tuple(targets.shape)} do not match logits {tuple(x.shape)}")
+            y = y.to(torch.int64).contiguous()
+            if class_weights is not None:
+                cw = class_weights.detach().to(torch.float32).contiguous()
+                if cw.numel() != classes:
+                    raise ValueError("class_weights must have one entry per class")
+        grad = torch.empty_like(x)
+        loss_rows = torch.empty(rows, dtype=torch.float32, device=dev)
+        ws, ws_bytes = N.workspace(dev, rows, classes)
+        N.check(N.lib().b200ssl_ce_rows_fwd_bwd(x.data_ptr(), N.ptr(y), N.ptr(t), N.ptr(cw), grad.data_ptr(),
+                                                loss_rows.data_ptr(), rows, classes, N.dtype_enum(x), 1 if poly else 0,
+                                                float(epsilon), ws, ws_bytes, N.stream_ptr(dev)), "ce_rows_fwd_bwd")
+        ctx.save_for_backward(grad)
+        return loss_rows if x.dtype == torch.float32 else loss_rows.to(x.dtype)
+
+    @staticmethod
+    def backward(ctx, g_rows):
+        (grad,) = ctx.saved_tensors
+        g = g_rows.detach().to(torch.float32).contiguous()
+        out = torch.empty_like(grad)
+        N.check(N.lib().b200ssl_scale_rows(grad.data_ptr(), out.data_ptr(), grad.shape[0], grad.shape[1], N.dtype_enum(grad),
+                                           g.data_ptr(), N.stream_ptr(grad.device)), "scale_rows")
+        return out, None, None, None, None, None
+
+
+def bad_label_count(device=None, reset: bool = True) -> int:
+    """Labels outside ``[0, classes)`` (other than the ignore index -100) seen by the labeled kernels on ``device``
+    since the last reset.  Such rows are dropped instead of read out of bounds; this call synchronises, so use it as a
+    debugging check (``assert bad_label_count() == 0`` once per epoch), not per step."""
+    import ctypes
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    ws, _ = N.workspace(dev, 1, 2)
+    n = ctypes.c_uint32()
+    N.check(N.lib().b200ssl_bad_label_count(ws, ctypes.byref(n), 1 if reset else 0), "bad_label_count")
+    return int(n.value)
+
+
 def ce_loss(logits, targets, class_weights=None, use_hard_labels=True, reduction="none", type_loss="none",
             cls_num_list=None):
-    """Drop-in for ``code/loss.py:90-124`` on the branches the SSL trainers use:
-    ``reduction='mean'`` with ``type_loss`` ``'none'`` (``:118-119``; weighted mean of
-    ``F.cross_entropy``) or ``'poly'`` (``:103-114``; PolyLoss epsilon=2, plain mean).
-    Other combinations are not on the hot path and raise."""
+    """Drop-in for ``code/loss.py:90-124``: hard labels with ``type_loss`` ``'none'`` (``:118-119``,
+    ``F.cross_entropy`` with ``weight`` and ``reduction`` in ``'none' | 'mean' | 'sum'``) or ``'poly'`` (``:103-114``,
+    PolyLoss epsilon = 2 with the same reductions), and soft targets (``:120-124``, always un-reduced like the
+    reference).  ``reduction='mean'`` is one fused launch; the un-reduced forms return per-row losses from one launch.
+    The focal / LDAM variants (``:98-117``) are not used by the SSL trainers and raise."""
     if not use_hard_labels:
-        raise NotImplementedError("soft-target ce_loss (loss.py:120-124) is only reachable through "
-                                  "consistency_loss(use_hard_labels=False)")
-    if reduction != "mean" or type_loss not in ("none", "poly"):
-        raise NotImplementedError(f"ce_loss(reduction={reduction!r}, type_loss={type_loss!r}) is outside the fused "
-                                  "hot path (supported: reduction='mean', type_loss in {'none','poly'})")
-    return _LabeledCE.apply(logits, targets, class_weights, type_loss == "poly", 2.0)
+        assert logits.shape == targets.shape
+        return _RowCE.apply(logits, targets, None, False, 0.0, True)
+    if type_loss not in ("none", "poly"):
+        raise NotImplementedError(f"ce_loss(type_loss={type_loss!r}) is outside the SSL hot path (supported: 'none', 'poly')")
+    if reduction == "mean":
+        return _LabeledCE.apply(logits, targets, class_weights, type_loss == "poly", 2.0)
+    if reduction not in ("none", "sum"):
+        raise ValueError(f"reduction {reduction!r}")
+    rows = _RowCE.apply(logits, targets, class_weights, type_loss == "poly", 2.0, False)
+    return rows.sum() if reduction == "sum" else rows
 
 
 class PolyLoss(nn.Module):
@@ -179,10 +250,16 @@ class PolyLoss(nn.Module):
     def __init__(self, softmax: bool = True, ce_weight: Optional[torch.Tensor] = None, reduction: str = "mean",
                  epsilon: float = 1.0) -> None:
         super().__init__()
-        if not softmax or reduction != "mean":
-            raise NotImplementedError("fused PolyLoss supports softmax=True, reduction='mean'")
+        if not softmax:
+            raise NotImplementedError("fused PolyLoss supports softmax=True (logits in)")
+        if reduction not in ("mean", "sum", "none"):
+            raise ValueError(f'Unsupported reduction: {reduction}, available options are ["mean", "sum", "none"].')
         self.ce_weight = ce_weight
         self.epsilon = epsilon
+        self.reduction = reduction
 
     def forward(self, input: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
-        return _LabeledCE.apply(input, target, self.ce_weight, True, self.epsilon)
+        if self.reduction == "mean":
+            return _LabeledCE.apply(input, target, self.ce_weight, True, self.epsilon)
+        rows = _RowCE.apply(input, target, self.ce_weight, True, self.epsilon, False)
+        return rows.sum() if self.reduction == "sum" else rows

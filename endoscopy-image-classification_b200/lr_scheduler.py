@@ -17,9 +17,9 @@ class IterScheduler:
         self.optimizer, self.kind = optimizer, kind
         self.t_initial, self.warmup_t, self.warmup_lr_init = int(t_initial), int(warmup_t), float(warmup_lr_init)
         self.lr_min, self.lr_min_rate, self.decay_t, self.decay_rate = lr_min, lr_min_rate, max(int(decay_t), 1), decay_rate
-        self.base_values = [g["lr"] for g in optimizer.param_groups]
-        for g in optimizer.param_groups:
-            g.setdefault("initial_lr", g["lr"])
+        for g in optimizer.param_groups:           # like timm: the schedule is anchored on initial_lr, which survives a
+            g.setdefault("initial_lr", g["lr"])    # resume (optimizer.load_state_dict restores the decayed g["lr"])
+        self.base_values = [g["initial_lr"] for g in optimizer.param_groups]
         self.last_update = -1
         if self.warmup_t:
             self._set([self.warmup_lr_init] * len(self.base_values))

@@ -17,7 +17,7 @@ import torch
 
 from . import _native as N
 
-__all__ = ["PeerArena"]
+__all__ = ["PeerArena", "LocalArenaSet"]
 
 
 def _round_up(x: int, m: int) -> int:
@@ -27,10 +27,14 @@ def _round_up(x: int, m: int) -> int:
 class PeerArena:
     """``regions``: ``{exchange_id: bytes_per_rank}`` -- the largest block one rank contributes to that exchange."""
 
-    def __init__(self, pg, device, regions: Dict[int, int], named: Optional[Dict[str, int]] = None):
+    def __init__(self, pg, device, regions: Dict[int, int], named: Optional[Dict[str, int]] = None, *, _local=None):
         import torch.distributed as dist
         self.pg, self.device = pg, torch.device(device)
-        self.rank, self.world = dist.get_rank(pg), dist.get_world_size(pg)
+        self._local = _local                       # (LocalArenaSet, rank): all arenas live in this process (single-GPU validation)
+        if _local is not None:
+            self.rank, self.world = int(_local[1]), _local[0].world
+        else:
+            self.rank, self.world = dist.get_rank(pg), dist.get_world_size(pg)
         lib = N.lib()
         self.slot: Dict[int, int] = {}
         self.offset: Dict[int, int] = {}
@@ -46,25 +50,30 @@ class PeerArena:
             self.named_offset[name] = off
             off += _round_up(int(nbytes), 256)
         self.bytes = off
-        self._own = C.c_void_p()
-        handle = (C.c_ubyte * 64)()
-        with torch.cuda.device(self.device):
-            N.check(lib.b200ssl_peer_alloc(self.bytes, C.byref(self._own), handle), "peer_alloc")
-            handles = [None] * self.world
-            dist.all_gather_object(handles, bytes(handle), group=pg)
-            self._mapped = []
-            bases = []
-            for r, h in enumerate(handles):
-                if r == self.rank:
-                    bases.append(self._own.value)
-                    continue
-                p = C.c_void_p()
-                N.check(lib.b200ssl_peer_open((C.c_ubyte * 64).from_buffer_copy(h), C.byref(p)), f"peer_open(rank {r})")
-                self._mapped.append(p)
-                bases.append(p.value)
+        self._mapped = []
+        if _local is not None:
+            bases = _local[0]._allocate(self.bytes)
+            self._own = C.c_void_p(bases[self.rank])
+        else:
+            self._own = C.c_void_p()
+            handle = (C.c_ubyte * 64)()
+            with torch.cuda.device(self.device):
+                N.check(lib.b200ssl_peer_alloc(self.bytes, C.byref(self._own), handle), "peer_alloc")
+                handles = [None] * self.world
+                dist.all_gather_object(handles, bytes(handle), group=pg)
+                bases = []
+                for r, h in enumerate(handles):
+                    if r == self.rank:
+                        bases.append(self._own.value)
+                        continue
+                    p = C.c_void_p()
+                    N.check(lib.b200ssl_peer_open((C.c_ubyte * 64).from_buffer_copy(h), C.byref(p)), f"peer_open(rank {r})")
+                    self._mapped.append(p)
+                    bases.append(p.value)
         self.bases_host = (C.c_uint64 * self.world)(*bases)
         self.bases = torch.tensor(bases, dtype=torch.int64).to(self.device)
-        dist.barrier(group=pg)                  # nobody pushes before every rank has mapped every arena
+        if _local is None:
+            dist.barrier(group=pg)              # nobody pushes before every rank has mapped every arena
         torch.cuda.synchronize(self.device)
 
     def tensor(self, name: str, shape: Sequence[int], dtype: torch.dtype) -> torch.Tensor:
@@ -129,10 +138,13 @@ class PeerArena:
 
     def close(self) -> None:
         """Collective: unmap the peers' arenas, then free the own one."""
-        import torch.distributed as dist
         if self._own is None:
             return
         torch.cuda.synchronize(self.device)
+        if self._local is not None:             # the set owns the allocations
+            self._own = None
+            return
+        import torch.distributed as dist
         lib = N.lib()
         for p in self._mapped:
             lib.b200ssl_peer_close(p)
@@ -140,3 +152,39 @@ class PeerArena:
         dist.barrier(group=self.pg)             # every mapping is gone before any arena is freed
         lib.b200ssl_peer_free(self._own)
         self._own = None
+
+
+class LocalArenaSet:
+    """``world`` arenas of ONE process on ONE device: the multi-rank data path of the peer-memory bank (shard addressing, ring
+    positions, epoch flags) run rank after rank on a single GPU.  For validation only -- kernels of different ranks that wait
+    for each other must never be left to the mercy of one GPU's scheduler, so the caller launches the ranks phase by phase
+    (``comatch_head.lockstep_total_loss``): every flag a kernel looks at has been published by an earlier launch."""
+
+    def __init__(self, world: int, device):
+        if not 2 <= int(world) <= 8:
+            raise ValueError("2..8 emulated ranks")
+        self.world, self.device = int(world), torch.device(device)
+        self._bytes = None
+        self._ptrs = []
+
+    def _allocate(self, nbytes: int):
+        if self._bytes is None:
+            lib = N.lib()
+            with torch.cuda.device(self.device):
+                for _ in range(self.world):
+                    p, handle = C.c_void_p(), (C.c_ubyte * 64)()
+                    N.check(lib.b200ssl_peer_alloc(int(nbytes), C.byref(p), handle), "peer_alloc")
+                    self._ptrs.append(p)
+            self._bytes = int(nbytes)
+        elif int(nbytes) != self._bytes:
+            raise ValueError("every emulated rank must ask for the same arena layout")
+        return [p.value for p in self._ptrs]
+
+    def arena(self, rank: int, regions: Dict[int, int], named: Optional[Dict[str, int]] = None) -> "PeerArena":
+        return PeerArena(None, self.device, regions, named, _local=(self, int(rank)))
+
+    def close(self) -> None:
+        torch.cuda.synchronize(self.device)
+        for p in self._ptrs:
+            N.lib().b200ssl_peer_free(p)
+        self._ptrs, self._bytes = [], None

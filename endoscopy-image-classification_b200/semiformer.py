@@ -23,6 +23,11 @@ class SemiFormer(SemiSupervisedTrainer):
     def _steps_in_epoch(self, epoch):
         return len(self.train_labeled_dl) if self._supervised_phase(epoch) else self.config.TRAIN.EVAL_STEP
 
+    def _schedule_index(self, epoch, batch_idx, steps):
+        if self._supervised_phase(epoch):
+            return epoch * steps + batch_idx                                   # semiformer.py:93 (num_steps = len(labeled loader))
+        return super()._schedule_index(epoch, batch_idx, steps)                # semiformer.py:139
+
     def _eval_forward(self, model, images):
         out_conv, out_trans = model(images)
         return out_conv + out_trans

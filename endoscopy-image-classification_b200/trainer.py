@@ -155,13 +155,19 @@ class SemiSupervisedTrainer:
             else:
                 self.optimizer.zero_grad()
             losses.backward()
-            self._after_backward(epoch, epoch * steps + batch_idx, losses, summary_loss)
+            self._after_backward(epoch, self._schedule_index(epoch, batch_idx, steps), losses, summary_loss)
             if hasattr(bar, "set_postfix"):
                 bar.set_postfix(loss=summary_loss.avg)
         return summary_loss
 
     def _steps_in_epoch(self, epoch):
         return self.config.TRAIN.EVAL_STEP
+
+    def _schedule_index(self, epoch, batch_idx, steps):
+        """Argument of ``lr_scheduler.step_update``: the reference always counts ``TRAIN.EVAL_STEP`` updates per epoch
+        (``fixmatch.py:124``, ``comatch.py:228``, ``semiformer.py:139``) -- also in CoMatch, whose loop runs over the
+        unlabeled loader -- because the scheduler was built with ``n_iter_per_epoch = EVAL_STEP``."""
+        return epoch * self.config.TRAIN.EVAL_STEP + batch_idx
 
     def _train_step(self, epoch, batch_idx):  # pragma: no cover - abstract
         raise NotImplementedError
@@ -233,8 +239,16 @@ class SemiSupervisedTrainer:
     def load_checkpoint(self, checkpoint_dir, is_train=False):
         checkpoint = torch.load(checkpoint_dir, map_location="cpu", weights_only=False)
         self.model.load_state_dict(checkpoint["model_state_dict"])
-        for p in self.model.parameters():
-            p.requires_grad = bool(is_train)
+        if is_train:
+            # fixmatch.py:208-219: resuming re-applies TRAIN.IS_FREEZE (a frozen backbone stays frozen, so no stale
+            # gradients pile up on parameters the optimizer never zeroes)
+            for p in self.model.parameters():
+                p.requires_grad = True
+            if _cfg(self.config.TRAIN, "IS_FREEZE", False):
+                self._freeze_backbone()
+        else:
+            for p in self.model.parameters():
+                p.requires_grad = False
         if self.config.TRAIN.USE_EMA:
             self.ema_model.ema.load_state_dict(checkpoint["ema_state_dict"])     # in place: pointers stay valid
             for p in self.ema_model.ema.parameters():

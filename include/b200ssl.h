@@ -104,6 +104,24 @@ B200SSL_API int b200ssl_labeled_ce_fwd_bwd(const void* logits, const int64_t* ta
                                float epsilon, float* out_scalar, void* workspace, size_t workspace_bytes,
                                void* stream);
 
+/* Un-reduced labeled criterion (code/loss.py:118-124; PolyLoss reduction='none', :357-359): loss_rows[i] and, in
+ * grad_unit [rows, classes], the gradient of loss_rows[i] w.r.t. logits row i.  Exactly one of `targets` (int64 hard
+ * labels; class_weights / poly as in b200ssl_labeled_ce_fwd_bwd) and `soft_targets` (fp32 [rows, classes];
+ * loss.py:120-124: sum_c -t_c log_softmax(x)_c) is given.  Labels: -100 (F.cross_entropy's ignore_index) drops the
+ * row; any other label outside [0, classes) also drops it and raises the sticky counter read by
+ * b200ssl_bad_label_count (both labeled kernels) instead of reading out of bounds. */
+B200SSL_API int b200ssl_ce_rows_fwd_bwd(const void* logits, const int64_t* targets, const float* soft_targets,
+                            const float* class_weights, void* grad_unit, float* loss_rows, int64_t rows,
+                            int32_t classes, int32_t dtype, int32_t poly, float epsilon, void* workspace,
+                            size_t workspace_bytes, void* stream);
+
+/* grad_out[i, :] = grad_in[i, :] * row_scale[i]  (autograd's per-row upstream gradient; out of place). */
+B200SSL_API int b200ssl_scale_rows(const void* grad_in, void* grad_out, int64_t rows, int32_t classes, int32_t dtype,
+                       const float* row_scale, void* stream);
+
+/* Number of out-of-range labels the labeled kernels have seen on this workspace (synchronises; reset != 0 clears it). */
+B200SSL_API int b200ssl_bad_label_count(void* workspace, uint32_t* count, int32_t reset);
+
 /* ---------------------------------------------------------------- K2 ----
  * CoMatch distribution alignment statistics.  Replaces code/comatch.py:167-173:
  * softmax(logits_u_w).mean(0) is pushed on a device-resident history ring
@@ -389,6 +407,14 @@ B200SSL_API int b200ssl_peer_all_gather(const void* src0, size_t bytes0, const v
 B200SSL_API int b200ssl_peer_reduce_scatter_f32(const float* src, float* out, int64_t count_per_rank, void* const* arenas,
                                     size_t region_offset, size_t slot_bytes, int32_t exchange_id, int32_t rank,
                                     int32_t world, void* stream);
+
+/* Launch geometry of the tensor-core K3 (host only): out[0] = row tiles per CTA, out[1] = cluster size, out[2] = clusters
+ * per group of row tiles.  remote_shards != 0: the plan of a directly addressed rank-sharded bank. */
+/* Tuning aid: force the row tiles per CTA (0 = planner) and the number of exponentials out of 32 that the tensor-core K3
+ * computes with the FMA-pipe polynomial (-1 = default). */
+B200SSL_API void b200ssl_debug_set_k3(int32_t row_tiles_per_cta, int32_t poly_of_32);
+
+B200SSL_API int b200ssl_debug_smooth_plan(int64_t rows, int64_t bank_rows, int32_t remote_shards, int32_t* out_mt_cluster_nouter);
 
 #ifdef __cplusplus
 }

@@ -282,3 +282,66 @@ def test_peer_arena_layout_with_stubbed_allocation(native, monkeypatch):
         a.all_gather(0, [torch.zeros(3, 5)])                               # 60 bytes: not a multiple of 16
     with pytest.raises(ValueError):
         a.reduce_scatter(2, torch.zeros(8, 3, dtype=torch.float64))
+
+
+# ---- tensor-core K3: launch plan and the FMA-pipe exponential (host-side restatements) ---------------------------
+def test_k3_launch_plan_invariants(native):
+    """csrc/bank_tc.cu smooth_tc_plan: every plan splits the key tiles over at most one CTA per SM and wave, a directly
+    addressed sharded bank with <= 4 row tiles uses the row loop (each remote key tile crosses NVLink once), and the
+    workspace the sizing call reports covers the plan's outer partials."""
+    lib = native.lib()
+    out = (C.c_int32 * 3)()
+    for rows in (1, 100, 448, 512, 896, 1792, 3000, 3584, 7168, 14336):
+        for K in (8, 80, 2560, 4104, 8192, 16384, 20480, 32768, 65536):
+            for remote in (0, 1):
+                assert lib.b200ssl_debug_smooth_plan(rows, K, remote, out) == 0
+                mt, cl, no = list(out)
+                row_tiles, ktiles = (rows + 127) // 128, (K + 127) // 128
+                assert 1 <= mt <= 4 and cl in (1, 2, 4, 8) and no >= 1
+                assert cl * no <= ktiles, (rows, K, remote, mt, cl, no)          # every CTA owns at least one key tile
+                if remote and row_tiles <= 4:
+                    assert mt == row_tiles
+                    assert cl * no <= 148                                          # one group of row tiles: one wave
+                groups = (row_tiles + mt - 1) // mt
+                need = 256 + 65536 + (no * groups * mt * 128 * 24 * 4 if no > 1 else 0)
+                assert lib.b200ssl_workspace_bytes(rows, 23, K) >= need, (rows, K, remote)
+    # BASELINE cfg 4 on 8 ranks (448 queries per rank, 65536 rows): the whole chip shares the key tiles
+    lib.b200ssl_debug_smooth_plan(448, 65536, 1, out)
+    assert list(out) == [4, 8, 18]
+    # the sweep corner: no half-empty second wave (round 1 ran 224 CTAs on 148 SMs)
+    lib.b200ssl_debug_smooth_plan(3584, 65536, 0, out)
+    mt, cl, no = list(out)
+    assert ((28 + mt - 1) // mt) * cl * no <= 148
+
+
+def test_k3_polynomial_exp2_math():
+    """ex2_poly of csrc/bank_tc.cu restated in numpy fp32: round-to-nearest split through 1.5 * 2^23, degree-3 minimax
+    polynomial, exponent patched in with an integer shift-add.  Relative error <= 7.6e-5 (bf16 half-ulp: 2e-3) over the
+    whole logit range of unit-norm embeddings at temperature 0.2, and a finite tiny value below the clamp."""
+    def fma(a, b, c):
+        return (a.astype(np.float64) * b.astype(np.float64) + c.astype(np.float64)).astype(np.float32)
+
+    def ex2_poly(s, scale, s_min):
+        magic = np.float32(12582912.0)
+        s = np.maximum(s, s_min)
+        sc = np.full_like(s, scale)
+        t = fma(s, sc, np.full_like(s, magic))
+        f = fma(s, sc, -(t - magic).astype(np.float32))
+        c3, c2, c1, c0 = (np.float32(float.fromhex(h)) for h in ("0x1.c3f76p-5", "0x1.f0de1ap-3", "0x1.62f31ap-1", "0x1.fff692p-1"))
+        p = fma(np.full_like(s, c3), f, np.full_like(s, c2))
+        p = fma(p, f, np.full_like(s, c1))
+        p = fma(p, f, np.full_like(s, c0))
+        bits = (p.view(np.uint32).astype(np.uint64) + ((t.view(np.uint32).astype(np.uint64) << 23) & 0xFFFFFFFF)) & 0xFFFFFFFF
+        return bits.astype(np.uint32).view(np.float32)
+
+    src = (PKG / "csrc" / "bank_tc.cu").read_text()
+    for h in ("0x1.c3f76p-5f", "0x1.f0de1ap-3f", "0x1.62f31ap-1f", "0x1.fff692p-1f", "12582912.f"):
+        assert h in src, f"the kernel's constant {h} changed: update this restatement"
+    scale = np.float32(1.4426950408889634 / 0.2)
+    s_min = np.float32(-126.0 / scale)
+    s = np.linspace(-1.2, 1.2, 400001).astype(np.float32)
+    got = ex2_poly(s, scale, s_min).astype(np.float64)
+    ref = np.exp2(s.astype(np.float64) * float(scale))
+    assert np.abs(got / ref - 1).max() < 7.6e-5
+    low = ex2_poly(np.array([-30.0, -1e4], np.float32), scale, s_min)
+    assert np.all(np.isfinite(low)) and np.all(low >= 0) and np.all(low < 1e-37)

@@ -152,7 +152,71 @@ def test_labeled_ce_golden(pkg):
     r.backward()
     assert rel_err(l, r) < FP32_TOL and rel_err(xd.grad, xr.grad) < FP32_TOL
     with pytest.raises(NotImplementedError):
-        pkg["loss"].ce_loss(x, y, reduction="none")
+        pkg["loss"].ce_loss(x, y, reduction="mean", type_loss="focal")
+    # the fused criterion scales its stashed gradient in place: a second backward must raise, not double-scale
+    xd = x.clone().requires_grad_(True)
+    l = pkg["loss"].ce_loss(xd, y, reduction="mean")
+    l.backward(retain_graph=True)
+    with pytest.raises(RuntimeError):
+        l.backward()
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("rows,classes", [(16, 23), (1, 2), (513, 23), (64, 100)])
+def test_ce_loss_unreduced_sum_soft_and_ignore(pkg, rows, classes, dtype):
+    """loss.py:118-124 with the reference's default reduction='none', 'sum', PolyLoss reduction='none', soft targets
+    (use_hard_labels=False), F.cross_entropy's ignore_index and the out-of-range label guard -- against the oracle."""
+    loss = pkg["loss"]
+    tol = FP32_TOL if dtype == torch.float32 else BF16_TOL
+    g = torch.Generator().manual_seed(rows * 7 + classes)
+    x = (3 * torch.randn(rows, classes, generator=g)).to(dtype)
+    y = torch.randint(0, classes, (rows,), generator=g)
+    cw = torch.rand(classes, generator=g) + 0.5
+    up = torch.rand(rows, generator=g) + 0.5                       # per-row upstream gradient
+    for kw in (dict(), dict(class_weights=cw), dict(type_loss="poly"), dict(type_loss="poly", class_weights=cw)):
+        for red in ("none", "sum"):
+            xr = x.float().requires_grad_(True)
+            r = O.ce_loss(xr, y, reduction=red, **kw)
+            (r * up).sum().backward() if red == "none" else r.backward()
+            xd = x.cuda().requires_grad_(True)
+            kwd = {k: (v.cuda() if torch.is_tensor(v) else v) for k, v in kw.items()}
+            l = loss.ce_loss(xd, y.cuda(), reduction=red, **kwd)
+            assert l.shape == r.shape
+            (l.float() * up.cuda()).sum().backward(retain_graph=True) if red == "none" else l.backward(retain_graph=True)
+            assert rel_err(l.float(), r) < tol and rel_err(xd.grad.float(), xr.grad) < tol, (kw.keys(), red)
+            first = xd.grad.clone()                                # out-of-place chaining: a second backward is exact
+            xd.grad = None
+            (l.float() * up.cuda()).sum().backward() if red == "none" else l.backward()
+            assert torch.equal(first, xd.grad)
+    # soft targets (loss.py:120-124; always un-reduced, class weights unused)
+    t = torch.softmax(torch.randn(rows, classes, generator=g), 1)
+    xr = x.float().requires_grad_(True)
+    r = O.ce_loss(xr, t, use_hard_labels=False)
+    (r * up).sum().backward()
+    xd = x.cuda().requires_grad_(True)
+    l = loss.ce_loss(xd, t.cuda(), use_hard_labels=False)
+    (l.float() * up.cuda()).sum().backward()
+    assert rel_err(l.float(), r) < tol and rel_err(xd.grad.float(), xr.grad) < tol
+    # ignore_index rows and the out-of-range guard
+    if rows >= 4 and dtype == torch.float32:
+        yi = y.clone()
+        yi[1] = -100
+        for red in ("none", "mean"):
+            for w in (None, cw):
+                xr = x.float().requires_grad_(True)
+                r = torch.nn.functional.cross_entropy(xr, yi, weight=w, reduction=red)
+                r.sum().backward()
+                xd = x.cuda().requires_grad_(True)
+                l = loss.ce_loss(xd, yi.cuda(), class_weights=None if w is None else w.cuda(), reduction=red)
+                l.sum().backward()
+                assert rel_err(l, r) < tol and rel_err(xd.grad, xr.grad) < tol
+        assert loss.bad_label_count() == 0
+        yb = y.clone()
+        yb[0], yb[2] = classes, -7
+        l = loss.ce_loss(x.cuda(), yb.cuda(), reduction="none")
+        assert float(l[0]) == 0.0 and float(l[2]) == 0.0 and bool(torch.isfinite(l).all())
+        loss.ce_loss(x.cuda(), yb.cuda(), reduction="mean", type_loss="poly")
+        assert loss.bad_label_count() == 4 and loss.bad_label_count() == 0
 
 
 # =============================================================== K8 =========
