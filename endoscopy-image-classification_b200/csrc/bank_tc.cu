@@ -169,6 +169,10 @@ bank_smooth_tc_kernel(const __grid_constant__ CUtensorMap tm_f, const __grid_con
   const int cta = blockIdx.y * gridDim.x + blockIdx.x;
   const int tile0 = row_group * p.mt;                      // first row tile of this CTA
   const int M = min(p.mt, p.row_tiles - tile0);            // row tiles it serves (>= 1)
+  if (threadIdx.x == 0) {
+    B200SSL_STAMP(p.dbg, cta, 0);
+    B200SSL_STAMP_NS(p.dbg, cta, 10);
+  }
   pdl_launch_dependents();                                 // the next kernel may start its prologue
   const long long nktiles = (long long)p.nseg * p.tps;
   // Key tiles are dealt round-robin to the splits: tile u = split + t*nsplit of the enumeration that starts at the
@@ -399,7 +403,10 @@ bank_smooth_tc_kernel(const __grid_constant__ CUtensorMap tm_f, const __grid_con
     }
   }
   if (CL > 1) cluster.sync();                              // nobody leaves while its smem is still being read
-  if (threadIdx.x == 0) B200SSL_STAMP(p.dbg, cta, 7);      // cluster fold done
+  if (threadIdx.x == 0) {
+    B200SSL_STAMP(p.dbg, cta, 7);                          // cluster fold done
+    B200SSL_STAMP_NS(p.dbg, cta, 11);
+  }
   if (p.nouter == 1) return;
 
   // ---- then across clusters: the slice (row tile, cluster rank) = RB rows is folded, in cluster order, by whichever of
@@ -429,7 +436,10 @@ bank_smooth_tc_kernel(const __grid_constant__ CUtensorMap tm_f, const __grid_con
   }
   __syncthreads();
   if (threadIdx.x < M && s_last[threadIdx.x]) p.tickets[(tile0 + threadIdx.x) * kMaxCluster + crank] = 0u;
-  if (threadIdx.x == 0) B200SSL_STAMP(p.dbg, cta, 9);      // outer folds done
+  if (threadIdx.x == 0) {
+    B200SSL_STAMP(p.dbg, cta, 9);                          // outer folds done
+    B200SSL_STAMP_NS(p.dbg, cta, 12);
+  }
 }
 
 struct SmoothPlan { int mt, cluster, nouter; };
@@ -560,11 +570,10 @@ int bank_smooth_tc(const void* feats, const void* queue_feats, const void* queue
   static_assert(smem_request(kMaxMT) <= 227 * 1024, "shared memory budget");
   static_assert((size_t)kMaxMT * kRedTile <= kSmemStages, "the reduction tiles must fit in the drained pipeline buffers");
   static_assert(2 * kBN + kMaxMT * kCP <= (int)kTmemCols, "TMEM budget");
-  // share of the exponentials computed on the FMA pipe (of 32 per thread and S tile); throughput-bound launches only --
-  // at latency-bound sizes the MUFU unit is idle anyway
-  const int poly_env = g_force_poly;
-  const bool big = row_tiles * ((long long)p.nseg * p.tps) >= 8LL * kNumSMs;
-  const int npoly = poly_env >= 0 ? poly_env : (big ? 12 : 0);
+  // Share of the exponentials computed on the FMA pipe (of 32 per thread and S tile).  Measured on B200 (tools/k3_tune.py,
+  // profiles/r02_k3_tune.jsonl): every polynomial slot ADDS ~25 clocks per S tile at every size -- the epilogue is bound by
+  // its serial ld -> exp -> st -> fence chain per tile, not by the MUFU rate -- so the default is 0; the knob stays for A/B.
+  const int npoly = g_force_poly >= 0 ? g_force_poly : 0;
   const dim3 grid((unsigned)groups, (unsigned)p.nsplit, 1);
   const size_t smem = smem_request(p.mt);
   cudaError_t e;

@@ -31,6 +31,15 @@ unsigned long long* debug_timing_buffer(int kernel_tag);
   do {                                                                          \
     if ((dbg) != nullptr) (dbg)[(size_t)(cta) * 16 + (slot)] = clock64();       \
   } while (0)
+// wall-clock variant (%globaltimer, ns): comparable across SMs -- start skew and tail of a launch
+#define B200SSL_STAMP_NS(dbg, cta, slot)                                         \
+  do {                                                                          \
+    if ((dbg) != nullptr) {                                                     \
+      unsigned long long t_;                                                    \
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));                    \
+      (dbg)[(size_t)(cta) * 16 + (slot)] = t_;                                  \
+    }                                                                           \
+  } while (0)
 
 // Workspace layout (caller zero-fills it once): [0,256) ticket counters of the
 // row kernels, [256, 256+64K) per-row-tile tickets of the similarity kernels,

@@ -190,10 +190,10 @@ def test_ce_loss_unreduced_sum_soft_and_ignore(pkg, rows, classes, dtype):
             assert torch.equal(first, xd.grad)
     # soft targets (loss.py:120-124; always un-reduced, class weights unused)
     t = torch.softmax(torch.randn(rows, classes, generator=g), 1)
-    xr = x.float().requires_grad_(True)
+    xr = x.float().clone().requires_grad_(True)
     r = O.ce_loss(xr, t, use_hard_labels=False)
     (r * up).sum().backward()
-    xd = x.cuda().requires_grad_(True)
+    xd = x.clone().cuda().requires_grad_(True)
     l = loss.ce_loss(xd, t.cuda(), use_hard_labels=False)
     (l.float() * up.cuda()).sum().backward()
     assert rel_err(l.float(), r) < tol and rel_err(xd.grad.float(), xr.grad) < tol
@@ -203,10 +203,10 @@ def test_ce_loss_unreduced_sum_soft_and_ignore(pkg, rows, classes, dtype):
         yi[1] = -100
         for red in ("none", "mean"):
             for w in (None, cw):
-                xr = x.float().requires_grad_(True)
+                xr = x.float().clone().requires_grad_(True)
                 r = torch.nn.functional.cross_entropy(xr, yi, weight=w, reduction=red)
                 r.sum().backward()
-                xd = x.cuda().requires_grad_(True)
+                xd = x.clone().cuda().requires_grad_(True)
                 l = loss.ce_loss(xd, yi.cuda(), class_weights=None if w is None else w.cuda(), reduction=red)
                 l.sum().backward()
                 assert rel_err(l, r) < tol and rel_err(xd.grad, xr.grad) < tol
