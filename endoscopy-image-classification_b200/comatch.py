@@ -50,7 +50,10 @@ class CoMatch(SemiSupervisedTrainer):
                     setattr(self, attr, config.TRAIN[key])
         self.low_dim = config.MODEL.LOW_DIM
         pg, world = None, 1
-        if _cfg(config.TRAIN, "SHARD_BANK", False) and torch.distributed.is_available() and torch.distributed.is_initialized():
+        # one ring for the whole job, spread over the ranks, whenever the trainer runs data parallel (TRAIN.SHARD_BANK: False
+        # keeps an independent per-rank bank of the per-rank size instead)
+        if _cfg(config.TRAIN, "SHARD_BANK", True) and torch.distributed.is_available() and torch.distributed.is_initialized() \
+                and torch.distributed.get_world_size() > 1:
             pg = torch.distributed.group.WORLD
             world = torch.distributed.get_world_size(pg)
         # comatch.py:91 with the GLOBAL batch: one ring for the whole job, every rank contributes its block per step
@@ -84,7 +87,7 @@ class CoMatch(SemiSupervisedTrainer):
         imgs = torch.cat([inputs_x, inputs_u_w, inputs_u_s_0, inputs_u_s_1], dim=0).to(self.device, non_blocking=True)
         targets_x = targets_x.to(self.device, non_blocking=True)
         with self._autocast():
-            logits, _, features = self.model(imgs)
+            logits, _, features = self.net(imgs)
         logits_x = logits[:bt]
         logits_u_w, logits_u_s0, _ = torch.split(logits[bt:], btu)              # logits_u_s1 is unused (comatch.py:151)
         feats_x = features[:bt]
@@ -100,8 +103,10 @@ class CoMatch(SemiSupervisedTrainer):
 
     # the reference does not checkpoint the bank / DA history (comatch.py:285-306); we add them
     def _extra_state(self):
+        """Collective in a multi-rank job: the shards of the bank are gathered so that rank 0 stores the whole ring (the
+        checkpoint does not depend on the number of ranks that wrote it); the DA history is rank 0's."""
         return {"comatch_head": {k: (v.detach().cpu() if torch.is_tensor(v) else v)
-                                 for k, v in self.head.state_dict().items()}}
+                                 for k, v in self.head.state_dict(full=True).items()}}
 
     def _load_extra_state(self, checkpoint):
         if "comatch_head" in checkpoint and self.head is not None:

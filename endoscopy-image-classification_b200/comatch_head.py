@@ -250,15 +250,29 @@ class CoMatchHead:
             self.da_ring[i].copy_(e.to(self.device, torch.float32))
         self.da_state.copy_(torch.tensor([len(entries), len(entries) % self.da_window], dtype=torch.int32))
 
-    def state_dict(self) -> dict:
-        return {"queue_feats": self.queue_feats, "queue_probs": self.queue_probs, "queue_ptr": self.queue_ptr,
-                "da_ring": self.da_ring, "da_state": self.da_state}
+    def _holds_whole_ring(self) -> bool:
+        return self.geom.world_size == 1 or self.exchange == "replicated"
+
+    def state_dict(self, full: bool = False) -> dict:
+        """``full=True``: the whole ring (collective in a multi-rank job with a sharded bank: an all-gather of the
+        shards, rank-major = ring order); otherwise the rows this rank holds."""
+        qf, qp = self.queue_feats, self.queue_probs
+        if full and not self._holds_whole_ring():
+            if self._local is not None:
+                raise RuntimeError("emulated ranks: gather the shards of the heads yourself")
+            qf, qp = all_gather_rows(qf, self.pg), all_gather_rows(qp, self.pg)
+        return {"queue_feats": qf, "queue_probs": qp, "queue_ptr": self.queue_ptr, "da_ring": self.da_ring, "da_state": self.da_state}
 
     def load_state_dict(self, sd: dict) -> None:
+        """Accepts the rows this rank holds or the whole ring (a sharded bank then keeps its own slice)."""
         if sd["queue_feats"].dtype != self.dtype:          # otherwise copy in place: captured graphs
             self._alloc_bank(sd["queue_feats"].dtype)      # keep pointing at the same storage
-        self.queue_feats.copy_(sd["queue_feats"])
-        self.queue_probs.copy_(sd["queue_probs"])
+        qf, qp = sd["queue_feats"], sd["queue_probs"]
+        if qf.shape[0] == self.queue_size and not self._holds_whole_ring():
+            lo, hi = self.geom.shard_begin, self.geom.shard_begin + self.geom.shard_rows
+            qf, qp = qf[lo:hi], qp[lo:hi]
+        self.queue_feats.copy_(qf)
+        self.queue_probs.copy_(qp)
         if self.queue_probs_t is not None:
             self.queue_probs_t[: self.num_classes].copy_(self.queue_probs.t())
         self.queue_ptr = int(sd["queue_ptr"])

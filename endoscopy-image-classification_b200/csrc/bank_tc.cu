@@ -8,10 +8,13 @@
 //   QpT tile [32 x 128] ---->  numer[128 x 32] += P QpT^T (TMEM accumulator, K = 128 keys)
 //
 // Warp roles (576 threads): warp 0 = TMEM allocator + TMA producer, warp 1 = MMA
-// issuer (one thread), warps 2..17 = epilogue (4 threads per TMEM lane = query row,
-// 32 key columns each).  S (TMEM) and P (smem) are double-buffered so GEMM1 of key
-// tile t+1 and GEMM2 of tile t-1 overlap the exp of tile t; the bank is split over a
-// cluster of CTAs whose partials are folded through DSMEM in rank order (deterministic).
+// issuer (one thread), warps 2..17 = epilogue in TWO groups of 8 warps that take
+// alternate S tiles (group g owns S[g] in TMEM and P[g] in smem; 2 threads per query
+// row, 64 key columns each): while one group waits for its S tile, drains TMEM or
+// publishes P, the other keeps the MUFU unit busy -- one group alone left it idle for
+// half of every tile (ncu, round 2: 52 % XU, 23 % of the samples on the mbarriers).
+// The bank is split over a cluster of CTAs whose partials are folded through DSMEM in
+// rank order (deterministic).
 //
 // Bank layout for this path: queue_feats [K, 64] bf16 row-major (a row is exactly one
 // 128-byte swizzle row) and a transposed, class-padded copy of the probabilities
@@ -79,11 +82,13 @@ namespace cg = cooperative_groups;
 constexpr int kBM = 128;          // queries per row tile (UMMA M)
 constexpr int kBN = 128;          // keys per tile    (UMMA N of GEMM1 / K of GEMM2)
 constexpr int kCP = 32;           // classes + the "ones" column, padded (UMMA N of GEMM2)
-constexpr int kStages = 3;        // >= key tiles per CTA at the reference's sizes: every load is in flight at once (remote shards: NVLink latency)
+constexpr int kStages = 4;        // key tiles in flight: GEMM1 runs two units ahead of the exponentials, so three tiles are in use while the
+                                  // fourth is loading (and at the reference's sizes every load of a CTA is in flight at once)
 constexpr int kMaxMT = 4;         // row tiles one CTA can serve from ONE staged key tile ("row loop"): a remote key tile
                                   // then crosses NVLink once per step instead of once per row tile
-constexpr int kEpiWarps = 16;     // 4 per TMEM lane quarter: each thread owns 32 of the 128 key columns of its row.
+constexpr int kEpiWarps = 16;     // two groups of 8: 2 per TMEM lane quarter and group, each thread owns 64 of the 128 key columns of its row
 constexpr int kEpiThreads = kEpiWarps * 32;
+constexpr int kGroupThreads = kEpiThreads / 2;
 constexpr int kTcThreads = 64 + kEpiThreads;   // warp 0 TMA + TMEM alloc, warp 1 MMA, warps 2.. epilogue
 constexpr int kMaxCluster = 8;
 constexpr int kMaxSeg = 8;        // bank segments = shards of a rank-sharded bank (1 = the whole bank is local)
@@ -93,11 +98,11 @@ constexpr uint32_t kSubQp = kCP * 128;                  //  4 KB: [32][64] bf16
 constexpr uint32_t kTileQp = 2 * kSubQp;                //  8 KB
 constexpr uint32_t kSubP = kBM * 128;                   // 16 KB: [128][64] bf16
 constexpr uint32_t kTileP = 2 * kSubP;                  // 32 KB
-constexpr uint32_t kSmemStages = kStages * (kTileQf + kTileQp) + 2 * kTileP;   // 136 KB (P is double buffered)
+constexpr uint32_t kSmemStages = kStages * (kTileQf + kTileQp) + 2 * kTileP;   // 160 KB (P is double buffered)
 constexpr uint32_t kTmemCols = 512;                     // S[0] 0..127, S[1] 128..255, [numer | rowsum] of row tile m at 256 + 32 m
 constexpr int kRedLd = 36;                              // floats per row of a reduction tile (16-byte rows, 4-way bank spread)
 constexpr uint32_t kRedTile = kBM * kRedLd * 4;         // 18 KB per row tile, staged over the drained pipeline buffers
-constexpr size_t smem_request(int mt) { return 1024 + (size_t)mt * kTileA + kSmemStages + 512; }   // mt = 1: 153.5 KB > half an SM
+constexpr size_t smem_request(int mt) { return 1024 + (size_t)mt * kTileA + kSmemStages + 512; }   // mt = 1: 177.5 KB > half an SM; mt = 4: 225.5 KB
 
 struct BankMaps {                 // one pair of tensor maps per shard; remote shards are peer-mapped NVLink addresses
   CUtensorMap qf[kMaxSeg];
@@ -194,10 +199,10 @@ bank_smooth_tc_kernel(const __grid_constant__ CUtensorMap tm_f, const __grid_con
     }
     for (int s = 0; s < 2; ++s) {
       tc::mbar_init(&bars[BAR_S_FULL + s], 1);
-      tc::mbar_init(&bars[BAR_S_EMPTY + s], kEpiThreads);
+      tc::mbar_init(&bars[BAR_S_EMPTY + s], kGroupThreads);
     }
     for (int s = 0; s < 2; ++s) {
-      tc::mbar_init(&bars[BAR_P_FULL + s], kEpiThreads);
+      tc::mbar_init(&bars[BAR_P_FULL + s], kGroupThreads);
       tc::mbar_init(&bars[BAR_P_EMPTY + s], 1);
     }
     tc::mbar_init(&bars[BAR_ACC], 1);
@@ -255,10 +260,11 @@ bank_smooth_tc_kernel(const __grid_constant__ CUtensorMap tm_f, const __grid_con
       tc::mbar_wait(&bars[BAR_A], 0, abort_flag);
       B200SSL_STAMP(p.dbg, cta, 2);                         // query tiles landed (TMA)
       // unit j = (key tile t, row tile m), m fastest: S[j & 1] = F_m Qf_t^T   (K = 64 -> 4 x UMMA_K 16)
-      auto gemm1 = [&](int j, int t, int m) {
+      auto gemm1 = [&](int j) {
+        const int t = j / M, m = j - t * M;
         const int s = t % kStages, b = j & 1;
         if (m == 0) tc::mbar_wait(&bars[BAR_KV_FULL + s], (t / kStages) & 1, abort_flag);
-        if (j >= 2) tc::mbar_wait(&bars[BAR_S_EMPTY + b], ((j >> 1) - 1) & 1, abort_flag);
+        if (j >= 2) tc::mbar_wait(&bars[BAR_S_EMPTY + b], ((j >> 1) - 1) & 1, abort_flag);   // group b has S of unit j-2 in registers
         tc::tcgen05_fence_after();
         const uint64_t a_desc = tc::smem_desc_sw128(tc::smem_u32(sA + (size_t)m * kTileA));
         const uint64_t b_desc = tc::smem_desc_sw128(tc::smem_u32(sQf + s * kTileQf));
@@ -266,18 +272,13 @@ bank_smooth_tc_kernel(const __grid_constant__ CUtensorMap tm_f, const __grid_con
         for (int k = 0; k < 4; ++k) tc::mma_bf16_ss(tmem + b * kBN, a_desc + 2 * k, b_desc + 2 * k, idesc1, k > 0);
         tc::mma_commit(&bars[BAR_S_FULL + b]);
       };
-      gemm1(0, 0, 0);
-      int t = 0, m = 0;                                      // (t, m) of unit j
-      for (int j = 0; j < J; ++j) {
-        int tn = t, mn = m + 1;                              // (t, m) of unit j + 1
-        if (mn == M) { mn = 0; ++tn; }
-        if (j + 1 < J) gemm1(j + 1, tn, mn);
-        const int s = t % kStages;
-        const int pb = j & 1;                                // P is double buffered like S: exp of unit j+1 overlaps GEMM2 of j
+      auto gemm2 = [&](int j) {   // [numer | rowsum]_m += P [QpT | 1]^T   (K = 128 keys -> 2 sub-tiles x 4 x UMMA_K 16)
+        const int t = j / M, m = j - t * M;
+        const int s = t % kStages, pb = j & 1;
         tc::mbar_wait(&bars[BAR_P_FULL + pb], (j >> 1) & 1, abort_flag);
         tc::tcgen05_fence_after();
 #pragma unroll
-        for (int kb = 0; kb < 2; ++kb) {   // [numer | rowsum]_m += P [QpT | 1]^T   (K = 128 keys -> 2 sub-tiles x 4 x UMMA_K 16)
+        for (int kb = 0; kb < 2; ++kb) {
           const uint64_t pa = tc::smem_desc_sw128(tc::smem_u32(sP + pb * kTileP + kb * kSubP));
           const uint64_t qb = tc::smem_desc_sw128(tc::smem_u32(sQp + s * kTileQp + kb * kSubQp));
 #pragma unroll
@@ -285,47 +286,61 @@ bank_smooth_tc_kernel(const __grid_constant__ CUtensorMap tm_f, const __grid_con
         }
         if (m == M - 1) tc::mma_commit(&bars[BAR_KV_EMPTY + s]);   // the key tile has served every row tile
         tc::mma_commit(&bars[BAR_P_EMPTY + pb]);
-        t = tn; m = mn;
+      };
+      // Issue order follows the order in which the two epilogue groups (half a tile apart in steady state) raise their
+      // barriers: "S of unit j is in registers" comes early in unit j, "P of unit j-1 is in smem" half a tile later.
+      // GEMM1 of unit j+2 is therefore in flight long before its group finishes unit j.
+      gemm1(0);
+      if (J > 1) gemm1(1);
+      for (int j = 0; j < J; ++j) {
+        if (j + 2 < J) gemm1(j + 2);
+        if (j >= 1) gemm2(j - 1);
       }
+      gemm2(J - 1);
       tc::mma_commit(&bars[BAR_ACC]);
     }
   } else {
-    // ===== epilogue: four threads per TMEM lane (query row), 32 of the 128 key columns each =====
-    const int quarter = warp & 3, colq = (warp - 2) >> 2;   // TMEM lanes [32*quarter, +32) are visible to this warp
-    const int half = colq >> 1, c2 = colq & 1;              // P sub-tile (64 keys) and 32-column group inside it
+    // ===== epilogue: group g = units j = g, g+2, ...; two threads per TMEM lane (query row), 64 of the 128 key columns each =====
+    const int quarter = warp & 3;                           // TMEM lanes [32*quarter, +32) are visible to this warp
+    const int ew = warp - 2;                                // 0..15
+    const int grp = ew >> 3, colh = (ew >> 2) & 1;          // S / P buffer of the group; 64-column half = P sub-tile
+    const int colq = ew >> 2;                               // 0..3: row tile this warp stages at the end
     const int r_in = quarter * 32 + lane;
     const uint32_t lane_addr = tmem + ((uint32_t)(quarter * 32) << 16);
-    for (int j = 0; j < J; ++j) {
-      const int b = j & 1;
-      tc::mbar_wait(&bars[BAR_S_FULL + b], (j >> 1) & 1, abort_flag);
+    uint8_t* p_row = sP + grp * kTileP + colh * kSubP;
+    for (int j = grp; j < J; j += 2) {
+      const int n = j >> 1;                                 // n-th unit of this group
+      tc::mbar_wait(&bars[BAR_S_FULL + grp], n & 1, abort_flag);
       if (j == 0 && threadIdx.x == 64) B200SSL_STAMP(p.dbg, cta, 3);   // first S tile ready (TMA + GEMM1)
       tc::tcgen05_fence_after();
+      uint32_t r[64];
       {
-        uint32_t r[32];
-        tc::tmem_ld_32x32(lane_addr + b * kBN + colq * 32, r);
-        tc::tmem_ld_wait();
-        tc::tcgen05_fence_before();
-        tc::mbar_arrive(&bars[BAR_S_EMPTY + b]);            // S[b] is in registers: GEMM1 of unit j+2 may overwrite it
-        // keys beyond the bank need no mask: their QpT columns (incl. the ones column) are TMA zero fill
-        uint32_t w[16];
-#pragma unroll
-        for (int e = 0; e < 16; ++e) {
-          const float s0 = __uint_as_float(r[2 * e]), s1 = __uint_as_float(r[2 * e + 1]);               // comatch.py:180
-          const float e0 = poly_slot<NPOLY>(2 * e) ? ex2_poly(s0, p.scale, p.s_min) : ex2_approx(s0 * p.scale);
-          const float e1 = poly_slot<NPOLY>(2 * e + 1) ? ex2_poly(s1, p.scale, p.s_min) : ex2_approx(s1 * p.scale);
-          const __nv_bfloat162 h = __floats2bfloat162_rn(e0, e1);
-          w[e] = *reinterpret_cast<const uint32_t*>(&h);
-        }
-        // the P buffer of unit j-2 must have been consumed -- only now, after the exponentials
-        if (j >= 2) tc::mbar_wait(&bars[BAR_P_EMPTY + b], ((j >> 1) - 1) & 1, abort_flag);
-#pragma unroll
-        for (int q = 0; q < 4; ++q)
-          *reinterpret_cast<uint4*>(sP + b * kTileP + half * kSubP + tc::sw128_offset(r_in, c2 * 4 + q)) =
-              make_uint4(w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
+        uint32_t (&lo)[32] = *reinterpret_cast<uint32_t(*)[32]>(&r[0]);
+        uint32_t (&hi)[32] = *reinterpret_cast<uint32_t(*)[32]>(&r[32]);
+        tc::tmem_ld_32x32(lane_addr + grp * kBN + colh * 64, lo);
+        tc::tmem_ld_32x32(lane_addr + grp * kBN + colh * 64 + 32, hi);
       }
+      tc::tmem_ld_wait();
+      tc::tcgen05_fence_before();
+      tc::mbar_arrive(&bars[BAR_S_EMPTY + grp]);            // S[grp] is in registers: GEMM1 of unit j+2 may overwrite it
+      // keys beyond the bank need no mask: their QpT columns (incl. the ones column) are TMA zero fill
+      uint32_t w[32];
+#pragma unroll
+      for (int e = 0; e < 32; ++e) {
+        const float s0 = __uint_as_float(r[2 * e]), s1 = __uint_as_float(r[2 * e + 1]);                 // comatch.py:180
+        const float e0 = poly_slot<NPOLY>((2 * e) & 31) ? ex2_poly(s0, p.scale, p.s_min) : ex2_approx(s0 * p.scale);
+        const float e1 = poly_slot<NPOLY>((2 * e + 1) & 31) ? ex2_poly(s1, p.scale, p.s_min) : ex2_approx(s1 * p.scale);
+        const __nv_bfloat162 h = __floats2bfloat162_rn(e0, e1);
+        w[e] = *reinterpret_cast<const uint32_t*>(&h);
+      }
+      // the P buffer of unit j-2 must have been consumed -- only now, after the exponentials
+      if (n >= 1) tc::mbar_wait(&bars[BAR_P_EMPTY + grp], (n - 1) & 1, abort_flag);
+#pragma unroll
+      for (int q = 0; q < 8; ++q)
+        *reinterpret_cast<uint4*>(p_row + tc::sw128_offset(r_in, q)) = make_uint4(w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
       tc::fence_proxy_async_smem();               // generic-proxy writes of P -> visible to the tensor core
-      tc::mbar_arrive(&bars[BAR_P_FULL + b]);
-      if (j == J - 1 && threadIdx.x == 64) B200SSL_STAMP(p.dbg, cta, 4);   // last exp tile done
+      tc::mbar_arrive(&bars[BAR_P_FULL + grp]);
+      if (j == J - 1 && lane == 0 && quarter == 2 && colh == 0) B200SSL_STAMP(p.dbg, cta, 4);   // last exp tile done
     }
     tc::mbar_wait(&bars[BAR_ACC], 0, abort_flag);           // all MMAs retired: pipeline smem is free, accumulators final
     if (threadIdx.x == 64) B200SSL_STAMP(p.dbg, cta, 5);
@@ -444,58 +459,74 @@ bank_smooth_tc_kernel(const __grid_constant__ CUtensorMap tm_f, const __grid_con
 
 struct SmoothPlan { int mt, cluster, nouter; };
 
-// A/B aids (tools/k3_tune.py): B200SSL_K3_MT / B200SSL_K3_POLY in the environment, or b200ssl_debug_set_k3 at run time.
-int g_force_mt = getenv("B200SSL_K3_MT") ? atoi(getenv("B200SSL_K3_MT")) : 0;       // 1: no row loop, 2..4: row loop where it fits
+// A/B aids (tools/k3_tune.py): b200ssl_debug_set_k3 at run time (or B200SSL_K3_MT / B200SSL_K3_POLY in the environment).
+int g_force_mt = getenv("B200SSL_K3_MT") ? atoi(getenv("B200SSL_K3_MT")) : 0;          // > 0: row tiles per CTA
+int g_force_cluster = 0, g_force_nouter = 0;                                           // > 0: cluster size / clusters per row group
 int g_force_poly = getenv("B200SSL_K3_POLY") ? atoi(getenv("B200SSL_K3_POLY")) : -1;   // exponentials (of 32) on the FMA pipe
+
+// Clusters of `cl` CTAs (one CTA per SM: the kernel takes more than half an SM's shared memory) that the chip runs at once.
+// A cluster lives inside one GPC, so the SMs a GPC has beyond a multiple of `cl` stay idle: 148 / 74 / ~33 / ~16 on B200.
+// Asked from the driver once per size; the table is the fallback without a device (CPU tests of the plan).
+int max_active_clusters(int cl) {
+  static int cache[kMaxCluster + 1] = {0};
+  if (cache[cl]) return cache[cl];
+  int n = cl == 1 ? 148 : cl == 2 ? 74 : cl == 4 ? 33 : 16;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) == cudaSuccess && ndev > 0) {
+    cudaFuncSetAttribute(bank_smooth_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_request(kMaxMT));
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(1, (unsigned)(cl * kNumSMs), 1);
+    cfg.blockDim = dim3(kTcThreads, 1, 1);
+    cfg.dynamicSmemBytes = smem_request(1);
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 1; attr[0].val.clusterDim.y = (unsigned)cl; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    int q = 0;
+    if (cudaOccupancyMaxActiveClusters(&q, bank_smooth_tc_kernel<0>, &cfg) == cudaSuccess && q > 0) n = q;
+    else (void)cudaGetLastError();
+  } else {
+    (void)cudaGetLastError();
+  }
+  cache[cl] = n;
+  return n;
+}
+
+// Cost of a plan in microseconds (measured constants, profiles/r02_k3_*): a wave of CTAs pays its prologue (barrier init,
+// TMEM allocation, first TMA round trip) and mt * T S-tile units; the DSMEM fold of a cluster and the ticketed global fold
+// of `no` partials come on top.  Waves are counted in CLUSTERS the chip can hold at once.
+double plan_cost(long long row_tiles, long long ktiles, int mt, int cl, long long no) {
+  const long long groups = (row_tiles + mt - 1) / mt;
+  const long long waves = (groups * no + max_active_clusters(cl) - 1) / max_active_clusters(cl);
+  const long long T = (ktiles + cl * no - 1) / (cl * no);
+  return (double)waves * (1.8 + 0.62 * (double)mt * (double)T) + 1.5 + (cl > 1 ? 2.5 : 0.5) + (no > 1 ? 3.0 + 0.25 * (double)no / cl : 0.0) +
+         0.4 * (mt - 1);                                   // extra query tiles to stage and to fold
+}
 
 // How a launch is cut: `mt` row tiles per CTA, and per group of row tiles a cluster of `cluster` CTAs (power of two <= 8,
 // folded through DSMEM) times `nouter` clusters (folded through global partials) that share the key tiles.
 SmoothPlan smooth_tc_plan(long long rows, long long ktiles, bool remote) {
   const long long row_tiles = (rows + kBM - 1) / kBM;
-  SmoothPlan pl{1, 1, 1};
-  const int force_mt = g_force_mt;
-  if ((remote || force_mt > 1) && row_tiles <= kMaxMT) {
-    // shards read over NVLink: one CTA serves every row tile from the key tile it staged, so a remote tile is fetched
-    // once per step; all SMs share the key tiles
-    pl.mt = (int)row_tiles;
-    while (pl.cluster * 2 <= kMaxCluster && pl.cluster * 2 <= ktiles) pl.cluster *= 2;
-    long long no = kNumSMs / pl.cluster;
-    if (no > ktiles / pl.cluster) no = ktiles / pl.cluster;
-    pl.nouter = (int)(no < 1 ? 1 : no);
-    return pl;
-  }
-  if (row_tiles * ktiles < 2LL * kNumSMs || force_mt == 1) {
-    // latency-bound sizes: the widest cluster, more clusters only for long serial key loops while SMs are free
-    while (pl.cluster * 2 <= kMaxCluster && pl.cluster * 2 <= ktiles) pl.cluster *= 2;
-    long long no = 1;
-    if (ktiles / pl.cluster > 8) {
-      no = kNumSMs / (row_tiles * pl.cluster);
-      if (no < 1) no = 1;
-      if (no > ktiles / pl.cluster) no = ktiles / pl.cluster;
-    }
-    pl.nouter = (int)no;
-    return pl;
-  }
-  // throughput-bound sizes: minimise (waves of one CTA per SM) x (units a CTA runs), unit = one 128 x 128 S tile;
-  // a CTA's fixed cost (prologue, folds) is charged in units.  Row loops (mt > 1) cut the L2 traffic of the bank by mt.
-  double best = 1e300;
-  for (int mt = 1; mt <= kMaxMT; ++mt) {
-    const long long groups = (row_tiles + mt - 1) / mt;
+  SmoothPlan best{1, 1, 1};
+  double best_cost = 1e300;
+  // Shards read over NVLink: one CTA serves every row tile from the key tile it staged, so a remote tile crosses the link
+  // once per step (row loop), whenever the row tiles fit one CTA.
+  const int mt_lo = g_force_mt > 0 ? (g_force_mt < kMaxMT ? g_force_mt : kMaxMT) : (remote && row_tiles <= kMaxMT) ? (int)row_tiles : 1;
+  const int mt_hi = (g_force_mt > 0 || (remote && row_tiles <= kMaxMT)) ? mt_lo : kMaxMT;
+  for (int mt = mt_lo; mt <= mt_hi; ++mt) {
+    if (mt > row_tiles && mt > mt_lo) break;
     for (int cl = 1; cl <= kMaxCluster; cl *= 2) {
       if (cl > ktiles) break;
-      const long long no_max = ktiles / cl < 64 ? ktiles / cl : 64;
+      if (g_force_cluster > 0 && cl != g_force_cluster) continue;
+      const long long no_max = ktiles / cl < 148 ? ktiles / cl : 148;
       for (long long no = 1; no <= no_max; ++no) {
-        const long long ctas = groups * cl * no;
-        const long long waves = (ctas + kNumSMs - 1) / kNumSMs;
-        const long long T = (ktiles + cl * no - 1) / (cl * no);
-        // outer fold: `no` partials of 128 / cl rows read back by one CTA (x2 when it may be last for several row tiles)
-        const double fold = no > 1 ? 1.0 + 0.15 * (double)no / cl * (mt > 1 ? 2.0 : 1.0) : 0.0;
-        const double cost = (double)waves * ((double)mt * (double)T + 2.0 + (cl > 1 ? 0.5 : 0.0) + fold) - 0.01 * mt;
-        if (cost < best) { best = cost; pl = SmoothPlan{mt, cl, (int)no}; }
+        if (g_force_nouter > 0 && no != g_force_nouter) continue;
+        const double c = plan_cost(row_tiles, ktiles, mt, cl, no);
+        if (c < best_cost - 1e-9) { best_cost = c; best = SmoothPlan{mt, cl, (int)no}; }
       }
     }
   }
-  return pl;
+  return best;
 }
 
 template <int NPOLY>
@@ -588,9 +619,15 @@ int bank_smooth_tc(const void* feats, const void* queue_feats, const void* queue
 
 }  // namespace b200ssl
 
-extern "C" void b200ssl_debug_set_k3(int32_t row_tiles_per_cta, int32_t poly_of_32) {
+extern "C" void b200ssl_debug_set_k3(int32_t row_tiles_per_cta, int32_t cluster, int32_t clusters_per_row_group, int32_t poly_of_32) {
   b200ssl::g_force_mt = row_tiles_per_cta;
+  b200ssl::g_force_cluster = cluster;
+  b200ssl::g_force_nouter = clusters_per_row_group;
   b200ssl::g_force_poly = poly_of_32;
+}
+
+extern "C" int b200ssl_debug_max_active_clusters(int32_t cluster) {
+  return (cluster == 1 || cluster == 2 || cluster == 4 || cluster == 8) ? b200ssl::max_active_clusters(cluster) : 0;
 }
 
 // Launch geometry of the tensor-core K3 for a problem size (host only; CPU tests and tools).

@@ -25,7 +25,7 @@ class FixMatch(SemiSupervisedTrainer):
         targets_x = targets_x.to(self.device, non_blocking=True)
         inputs = torch.cat((inputs_x, inputs_u_w, inputs_u_s)).to(self.device, non_blocking=True)
         with self._autocast():
-            outputs = self.model(inputs)
+            outputs = self.net(inputs)
         outputs_x = outputs[:bs_lb]
         outputs_u_w, outputs_u_s = outputs[bs_lb:].chunk(2)                    # contiguous row blocks
         lx = ce_loss(outputs_x, targets_x, class_weights=self.class_weights, reduction="mean", type_loss="poly")

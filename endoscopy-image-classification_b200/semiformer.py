@@ -38,7 +38,7 @@ class SemiFormer(SemiSupervisedTrainer):
             images, targets = self._labeled.next()
             images, targets = images.to(self.device, non_blocking=True), targets.to(self.device, non_blocking=True)
             with self._autocast():
-                out_conv, out_trans = self.model(images)
+                out_conv, out_trans = self.net(images)
             return (ce_loss(out_conv, targets, class_weights=cw, reduction="mean")
                     + ce_loss(out_trans, targets, class_weights=cw, reduction="mean"))
         inputs_x, targets_x = self._labeled.next()
@@ -47,7 +47,7 @@ class SemiFormer(SemiSupervisedTrainer):
         targets_x = targets_x.to(self.device, non_blocking=True)
         inputs = torch.cat((inputs_x, inputs_u_w, inputs_u_s)).to(self.device, non_blocking=True)
         with self._autocast():
-            out_conv, out_trans = self.model(inputs)
+            out_conv, out_trans = self.net(inputs)
         outputs_u_w, outputs_u_s_conv = out_conv[bs_lb:].chunk(2)
         outputs_u_s_trans = out_trans[bs_lb:].chunk(2)[1]
         lx = (ce_loss(out_conv[:bs_lb], targets_x, class_weights=cw, reduction="mean")

@@ -67,6 +67,7 @@ class SemiSupervisedTrainer:
         self.epoch_start = 1
         self.best_valid_perf = None
         self._fused = None                 # fused_step.FusedOptimizerEMA when TRAIN.FUSED_OPT_EMA is set
+        self._ddp = None                   # DistributedDataParallel wrapper of self.model in a multi-rank job
 
     # ---- reference API ---------------------------------------------------------------
     def get_dataloader(self, train_dl, valid_dl, test_dl=None):
@@ -102,11 +103,58 @@ class SemiSupervisedTrainer:
         w = class_weight.compute_class_weight(class_weight="balanced", classes=np.unique(y).tolist(), y=y)
         return torch.tensor(w, dtype=torch.float).to(self.device)
 
+    # ---- data parallel (the reference is single process) -------------------------------------------
+    @staticmethod
+    def _dist():
+        import torch.distributed as dist
+        return dist if (dist.is_available() and dist.is_initialized()) else None
+
+    @property
+    def rank(self) -> int:
+        d = self._dist()
+        return d.get_rank() if d is not None else 0
+
+    @property
+    def world_size(self) -> int:
+        d = self._dist()
+        return d.get_world_size() if d is not None else 1
+
+    @property
+    def net(self):
+        """What the step calls: the DDP wrapper in a multi-rank job (its backward all-reduces the gradients), else the
+        module itself.  ``self.model`` always stays the bare module -- EMA, checkpoints and freezing see the reference's
+        parameter names."""
+        return self._ddp if self._ddp is not None else self.model
+
+    def _wrap_ddp(self):
+        """``TRAIN.DDP`` (default: on whenever torch.distributed is initialised with more than one rank): every rank
+        holds a replica, gradients are averaged by DistributedDataParallel during ``backward()``; the optimizer step
+        and ``ModelEMA.update`` then run identically on every rank (no further communication: SURVEY 8e)."""
+        self._ddp = None
+        want = _cfg(self.config.TRAIN, "DDP", None)          # None: whenever there is more than one rank; True: also a 1-rank group
+        if self._dist() is not None and (want or (want is None and self.world_size > 1)):
+            from torch.nn.parallel import DistributedDataParallel
+            if not any(p.requires_grad for p in self.model.parameters()):
+                return
+            dev = torch.device(self.device)
+            self._ddp = DistributedDataParallel(self.model, device_ids=[dev.index] if dev.type == "cuda" else None,
+                                                broadcast_buffers=_cfg(self.config.TRAIN, "DDP_BROADCAST_BUFFERS", True),
+                                                find_unused_parameters=_cfg(self.config.TRAIN, "DDP_FIND_UNUSED", False))
+
+    def distributed_loader(self, dataset, batch_size, shuffle=True, drop_last=True, **kw):
+        """A DataLoader whose sampler deals the dataset over the ranks (the reference's loaders are single-process
+        RandomSampler ones, ``dataset.py``); ``train_one`` calls ``sampler.set_epoch``."""
+        from torch.utils.data import DataLoader
+        from torch.utils.data.distributed import DistributedSampler
+        sampler = DistributedSampler(dataset, num_replicas=self.world_size, rank=self.rank, shuffle=shuffle, drop_last=drop_last)
+        return DataLoader(dataset, batch_size=batch_size, sampler=sampler, drop_last=drop_last, **kw)
+
     def get_config(self, config, optimizer=None, lr_scheduler=None):
         """``fixmatch.py:36-70`` / ``comatch.py:48-96`` / ``semiformer.py:37-62``.  ``optimizer`` /
         ``lr_scheduler`` may be injected; by default they are built like the reference does."""
         self.config = config
-        print(f"Training mode: {self.TRAINING_MODE}")
+        if self.rank == 0:
+            print(f"Training mode: {self.TRAINING_MODE}")
         if self.EMA_BEFORE_FREEZE:
             self._build_ema()
             self._apply_freeze()
@@ -117,6 +165,7 @@ class SemiSupervisedTrainer:
         self.lr_scheduler = lr_scheduler or build_scheduler(config=self.config, optimizer=self.optimizer,
                                                             n_iter_per_epoch=config.TRAIN.EVAL_STEP)
         self.class_weights = self._class_weights()
+        self._wrap_ddp()
         amp = _cfg(self.config.TRAIN, "AMP", False)
         # TRAIN.FUSED_OPT_EMA: optimizer.step() + ema.update() as one multi-tensor launch (fused_step.py)
         self._fused = None
@@ -147,7 +196,11 @@ class SemiSupervisedTrainer:
         self.model.train()
         summary_loss = AverageMeter()
         steps = self._steps_in_epoch(epoch)
-        bar = tqdm(range(steps), total=steps)
+        for dl in (getattr(self, "train_labeled_dl", None), getattr(self, "train_unlabeled_dl", None)):
+            sampler = getattr(dl, "sampler", None)
+            if hasattr(sampler, "set_epoch"):
+                sampler.set_epoch(epoch)                # DistributedSampler: a different shuffle every epoch
+        bar = tqdm(range(steps), total=steps, disable=self.rank != 0)
         for batch_idx in bar:
             losses = self._train_step(epoch, batch_idx)
             if self._fused is not None:
@@ -220,6 +273,14 @@ class SemiSupervisedTrainer:
         pass
 
     def save_checkpoint(self, foldname):
+        """Rank 0 writes the file (same dict keys as ``fixmatch.py:181-202``); the other ranks only take part in
+        gathering state that is spread over the ranks (a sharded CoMatch bank) and wait at the barrier."""
+        extra = self._extra_state()                     # collective when the bank is sharded
+        d = self._dist()
+        if self.rank != 0:
+            if d is not None:
+                d.barrier()
+            return None
         checkpoint = {}
         if self.config.TRAIN.USE_EMA:
             checkpoint["ema_state_dict"] = self.ema_model.ema.state_dict()
@@ -229,11 +290,13 @@ class SemiSupervisedTrainer:
         checkpoint["model_state_dict"] = self.model.state_dict()
         checkpoint["optimizer"] = self.optimizer.state_dict()
         checkpoint["scheduler"] = self.lr_scheduler.state_dict() if self.lr_scheduler is not None else None
-        checkpoint.update(self._extra_state())
+        checkpoint.update(extra)
         os.makedirs(foldname, exist_ok=True)
         path = os.path.join(foldname, f"{stamp}_epoch_{self.epoch}.pth")
         torch.save(checkpoint, path)
         print("Saved checkpoint")
+        if d is not None:
+            d.barrier()
         return path
 
     def load_checkpoint(self, checkpoint_dir, is_train=False):
@@ -264,9 +327,11 @@ class SemiSupervisedTrainer:
         for epoch in range(self.epoch_start, self.config.TRAIN.EPOCHS + 1):
             self.epoch = epoch
             best = f"{float(self.best_valid_perf):.3f}" if self.best_valid_perf else "inf"
-            print(f'Training epoch: {self.epoch} | Current LR: {self.optimizer.param_groups[0]["lr"]:.6f} | The best loss: {best}')
+            if self.rank == 0:
+                print(f'Training epoch: {self.epoch} | Current LR: {self.optimizer.param_groups[0]["lr"]:.6f} | The best loss: {best}')
             train_loss = self.train_one(self.epoch)
-            print(f"\tTrain Loss: {train_loss.avg:.3f}")
+            if self.rank == 0:
+                print(f"\tTrain Loss: {train_loss.avg:.3f}")
             if epoch % self.config.TRAIN.FREQ_EVAL == 0:
                 valid_loss, _ = self.evaluate_one()
                 if not self.best_valid_perf or self.best_valid_perf > valid_loss.avg:

@@ -410,9 +410,12 @@ B200SSL_API int b200ssl_peer_reduce_scatter_f32(const float* src, float* out, in
 
 /* Launch geometry of the tensor-core K3 (host only): out[0] = row tiles per CTA, out[1] = cluster size, out[2] = clusters
  * per group of row tiles.  remote_shards != 0: the plan of a directly addressed rank-sharded bank. */
-/* Tuning aid: force the row tiles per CTA (0 = planner) and the number of exponentials out of 32 that the tensor-core K3
- * computes with the FMA-pipe polynomial (-1 = default). */
-B200SSL_API void b200ssl_debug_set_k3(int32_t row_tiles_per_cta, int32_t poly_of_32);
+/* Tuning aid: force the row tiles per CTA, the cluster size and the clusters per group of row tiles (0 = planner) and the
+ * number of exponentials out of 32 that the tensor-core K3 computes with the FMA-pipe polynomial (-1 = default). */
+B200SSL_API void b200ssl_debug_set_k3(int32_t row_tiles_per_cta, int32_t cluster, int32_t clusters_per_row_group, int32_t poly_of_32);
+
+/* Clusters of `cluster` CTAs of the tensor-core K3 that the device runs at once (driver occupancy query; a table without a device). */
+B200SSL_API int b200ssl_debug_max_active_clusters(int32_t cluster);
 
 B200SSL_API int b200ssl_debug_smooth_plan(int64_t rows, int64_t bank_rows, int32_t remote_shards, int32_t* out_mt_cluster_nouter);
 

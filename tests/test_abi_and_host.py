@@ -301,17 +301,19 @@ def test_k3_launch_plan_invariants(native):
                 assert cl * no <= ktiles, (rows, K, remote, mt, cl, no)          # every CTA owns at least one key tile
                 if remote and row_tiles <= 4:
                     assert mt == row_tiles
-                    assert cl * no <= 148                                          # one group of row tiles: one wave
+                    assert no <= lib.b200ssl_debug_max_active_clusters(cl)         # one group of row tiles: one wave of clusters
                 groups = (row_tiles + mt - 1) // mt
                 need = 256 + 65536 + (no * groups * mt * 128 * 24 * 4 if no > 1 else 0)
                 assert lib.b200ssl_workspace_bytes(rows, 23, K) >= need, (rows, K, remote)
     # BASELINE cfg 4 on 8 ranks (448 queries per rank, 65536 rows): the whole chip shares the key tiles
+    # (a cluster lives inside one GPC: B200 holds 16 clusters of 8 one-CTA-per-SM blocks at once, not 148 / 8 = 18)
+    assert [lib.b200ssl_debug_max_active_clusters(c) for c in (1, 2, 4, 8)] == [148, 74, 33, 16]    # the no-device table
     lib.b200ssl_debug_smooth_plan(448, 65536, 1, out)
-    assert list(out) == [4, 8, 18]
+    assert list(out) == [4, 8, 16]
     # the sweep corner: no half-empty second wave (round 1 ran 224 CTAs on 148 SMs)
     lib.b200ssl_debug_smooth_plan(3584, 65536, 0, out)
     mt, cl, no = list(out)
-    assert ((28 + mt - 1) // mt) * cl * no <= 148
+    assert ((28 + mt - 1) // mt) * no <= lib.b200ssl_debug_max_active_clusters(cl)
 
 
 def test_k3_polynomial_exp2_math():

@@ -155,3 +155,60 @@ def test_trainer_with_fused_optimizer_ema_equals_the_eager_pair(opt_name):
         assert sa[k].keys() == sb[k].keys()
         for n in sa[k]:
             torch.testing.assert_close(sb[k][n].float().cpu(), sa[k][n].float().cpu(), rtol=1e-4, atol=1e-7)
+
+
+def test_ddp_single_rank_nccl(tmp_path):
+    """SURVEY 8 f3 on the GPU: the FixMatch trainer with its backbone inside DistributedDataParallel (a 1-rank NCCL group
+    on this box; the 2-rank wiring is covered on the CPU by tests/test_ddp_trainer_gloo.py) runs the fused criteria and the
+    multi-tensor EMA through DDP's backward hooks and ends with exactly the weights of the plain single-process trainer."""
+    import os
+    import socket
+
+    import torch.distributed as dist
+    import torch.nn as nn
+    from endoscopy_image_classification_b200 import utils
+    from endoscopy_image_classification_b200.fixmatch import FixMatch
+
+    class Net(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.body = nn.Sequential(nn.Conv2d(3, 8, 3), nn.BatchNorm2d(8), nn.ReLU(), nn.AdaptiveAvgPool2d(1), nn.Flatten())
+            self.fc = nn.Linear(8, C)
+
+        def forward(self, x):
+            return self.fc(self.body(x))
+
+    def run(ddp):
+        torch.manual_seed(0)
+        net = Net()
+        g = torch.Generator().manual_seed(1)
+        B, MU = 4, 2
+        lab = Loader([(torch.randn(B, 3, 8, 8, generator=g), torch.randint(0, C, (B,), generator=g)) for _ in range(3)])
+        unl = Loader([((torch.randn(B * MU, 3, 8, 8, generator=g), torch.randn(B * MU, 3, 8, 8, generator=g)), None) for _ in range(3)])
+        tr = FixMatch(net, opt_func="SGD", device="cuda")
+        tr.get_dataloader((lab, unl), None)
+        cfg = _config(utils, B=B, MU=MU, thr=0.05, steps=3, ema=True, save=str(tmp_path / "ck"), train_extra={"DDP": ddp})
+        cfg.TRAIN.BASE_LR = 0.1
+        tr.get_config(cfg, lr_scheduler=NoSched())
+        tr.train_one(epoch=0)
+        torch.cuda.synchronize()
+        return tr, [p.detach().clone() for p in net.parameters()], [v.clone() for v in tr.ema_model.ema.state_dict().values()]
+
+    _, w_plain, e_plain = run(False)
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("nccl", rank=0, world_size=1, device_id=torch.device("cuda", 0))
+    try:
+        tr, w_ddp, e_ddp = run(True)
+        from torch.nn.parallel import DistributedDataParallel
+        assert isinstance(tr.net, DistributedDataParallel) and tr.net.module is tr.model
+        for a, b in zip(w_plain, w_ddp):
+            assert torch.equal(a, b)
+        for a, b in zip(e_plain, e_ddp):
+            assert torch.equal(a, b)
+        tr.epoch = 1
+        assert tr.save_checkpoint(cfg_dir := str(tmp_path / "ck")) is not None and len(os.listdir(cfg_dir)) == 1
+    finally:
+        dist.destroy_process_group()

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """A handful of launches of the tensor-core K3 alone (for `ncu -k regex:bank_smooth`).
 
-    python tools/k3_only.py ROWS BANK [FORCE_MT [POLY]]
+    python tools/k3_only.py ROWS BANK [MT CLUSTER NOUTER [POLY]]     (0 = planner)
 """
 import sys
 from pathlib import Path
@@ -14,7 +14,7 @@ from endoscopy_image_classification_b200 import synthetic as S  # noqa: E402
 from endoscopy_image_classification_b200.comatch_head import CoMatchHead  # noqa: E402
 
 rows, K = int(sys.argv[1]), int(sys.argv[2])
-N.lib().b200ssl_debug_set_k3(int(sys.argv[3]) if len(sys.argv) > 3 else 0, int(sys.argv[4]) if len(sys.argv) > 4 else -1)
+N.lib().b200ssl_debug_set_k3(*(int(x) for x in (sys.argv[3:6] + ['0', '0', '0'])[:3]), int(sys.argv[6]) if len(sys.argv) > 6 else -1)
 dev = torch.device("cuda:0")
 g = torch.Generator().manual_seed(0)
 head = CoMatchHead(23, 64, K, 0.9, enqueue_mode="always", device=dev, dtype=torch.bfloat16)

@@ -2,7 +2,7 @@
 """In-kernel timeline of the tcgen05 smoothing kernel: clock64() / %globaltimer stamps per CTA (see B200SSL_STAMP in
 csrc/common.cuh).  Prints cycles between stages, min / median / max over CTAs, and the wall-clock span of the launch.
 
-    python tools/kernel_timeline.py ROWS BANK [FORCE_MT [POLY]]
+    python tools/kernel_timeline.py ROWS BANK [MT CLUSTER NOUTER [POLY]]     (0 = planner)
 """
 import sys
 from pathlib import Path
@@ -16,11 +16,11 @@ from endoscopy_image_classification_b200 import synthetic as S  # noqa: E402
 from endoscopy_image_classification_b200.comatch_head import CoMatchHead  # noqa: E402
 
 rows, K = (int(sys.argv[1]), int(sys.argv[2])) if len(sys.argv) > 2 else (448, 2560)
-mt = int(sys.argv[3]) if len(sys.argv) > 3 else 0
-poly = int(sys.argv[4]) if len(sys.argv) > 4 else -1
+force = [int(x) for x in (sys.argv[3:6] + ["0", "0", "0"])[:3]]
+poly = int(sys.argv[6]) if len(sys.argv) > 6 else -1
 dev = torch.device("cuda:0")
 g = torch.Generator().manual_seed(0)
-N.lib().b200ssl_debug_set_k3(mt, poly)
+N.lib().b200ssl_debug_set_k3(*force, poly)
 head = CoMatchHead(23, 64, K, 0.9, enqueue_mode="always", device=dev, dtype=torch.bfloat16)
 head.queue_feats.copy_(S.rownorm(torch.randn(K, 64, generator=g)).to(torch.bfloat16))
 fw = S.rownorm(torch.randn(rows, 64, generator=g)).to(torch.bfloat16).to(dev)
