@@ -58,6 +58,7 @@ SIGNATURES = {
     "b200ssl_ce_rows_fwd_bwd": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _f32, _vp, _sz, _vp]),
     "b200ssl_scale_rows": (_i32, [_vp, _vp, _i64, _i32, _i32, _vp, _vp]),
     "b200ssl_bad_label_count": (_i32, [_vp, _vp, _i32]),
+    "b200ssl_eval_head": (_i32, [_vp, _vp, _i64, _i32, _i32, _vp, _vp, _vp, _vp, _sz, _vp]),
     "b200ssl_comatch_da": (_i32, [_vp, _i64, _i32, _i32, _vp, _vp, _i32, _vp, _vp, _vp, _sz, _vp]),
     "b200ssl_bank_smooth_partial": (_i32, [_vp, _vp, _vp, _vp, _i64, _i64, _i32, _i32, _i32, _f32, _vp, _vp, _i32, _i32,
                                            _vp, _vp, _sz, _vp]),

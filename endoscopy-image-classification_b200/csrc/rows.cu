@@ -390,6 +390,64 @@ __global__ void scale_rows_kernel(const T* in, T* out, long long rows, int C, co
     out[i] = from_f32<T>(to_f32<T>(in[i]) * row_scale[i / C]);
 }
 
+// ============================================================ f4 ============
+// Evaluation head (code/fixmatch.py:148-168 per batch): mean cross-entropy of the batch (F.cross_entropy 'mean'),
+// softmax -> arg-max (first index on ties, over the probabilities like np.argmax of F.softmax) and the confusion
+// matrix [target, prediction] accumulated with integer atomics -- every metric of utils.calculate_metrics
+// (code/utils.py:38-55) is a function of that matrix, so an evaluation pass ends with ONE device-to-host copy.
+struct EvalParams {
+  const void* x; const long long* y; long long rows; int C;
+  unsigned long long* confusion; float* loss_out; long long* pred;
+  float* partials; unsigned* ticket; unsigned* bad_labels;
+};
+
+template <typename T, int LPR, int EPL>
+__global__ void __launch_bounds__(kRowThreads) eval_head_kernel(const EvalParams p) {
+  using Cfg = RowCfg<LPR, EPL>;
+  constexpr int ROWS = Cfg::kRowsPerTile;
+  extern __shared__ float smem[];
+  const int C = p.C;
+  float* sx = smem;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int gl = lane % LPR, rw = lane / LPR;
+  const long long ntiles = (p.rows + ROWS - 1) / ROWS;
+  float acc[2] = {0.f, 0.f};                                  // sum of CE, rows counted
+  for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const long long row0 = tile * ROWS;
+    const int nrows = (int)min((long long)ROWS, p.rows - row0);
+    tile_g2s(static_cast<const T*>(p.x) + row0 * C, sx, nrows * C);
+    __syncthreads();
+    const int r = warp * Cfg::kRowsPerWarp + rw;
+    const bool valid = r < nrows;
+    float x[EPL], e[EPL], pr[EPL];
+    float mx, sum;
+    row_load<LPR, EPL>(sx + r * C, C, gl, valid, x);
+    row_softmax_stats<LPR, EPL>(x, e, mx, sum);
+#pragma unroll
+    for (int k = 0; k < EPL; ++k) pr[k] = __fdiv_rn(e[k], sum);
+    float pmax; int idx;
+    row_argmax<LPR, EPL>(pr, C, gl, pmax, idx);               // fixmatch.py:160,166
+    int y = -1;
+    if (valid && gl == 0) y = checked_label(p.y[row0 + r], C, p.bad_labels);
+    y = __shfl_sync(0xffffffffu, y, rw * LPR);
+    const bool live = valid && y >= 0;
+    const float xy = row_pick<LPR, EPL>(x, gl, live ? y : -1);
+    const float ce = -((xy - mx) - logf(sum));                // fixmatch.py:156
+    if (valid && gl == 0) {
+      if (p.pred) p.pred[row0 + r] = idx;
+      if (live) {
+        acc[0] += ce;
+        acc[1] += 1.f;
+        atomicAdd(&p.confusion[(size_t)y * C + idx], 1ull);
+      }
+    }
+    __syncthreads();
+  }
+  block_sum<2>(acc);
+  float total[2];
+  if (grid_reduce_last<2>(acc, p.partials, p.ticket, total) && threadIdx.x == 0) p.loss_out[0] = total[0] / total[1];
+}
+
 // ============================================================ K2 ============
 struct DaParams {
   const void* w; long long rows; int C;
@@ -1067,6 +1125,25 @@ extern "C" int b200ssl_scale_rows(const void* grad_in, void* grad_out, int64_t r
     scale_rows_kernel<float><<<(int)blocks, 256, 0, as_stream(stream)>>>(static_cast<const float*>(grad_in), static_cast<float*>(grad_out), rows, classes, row_scale);
   else
     scale_rows_kernel<__nv_bfloat16><<<(int)blocks, 256, 0, as_stream(stream)>>>(static_cast<const __nv_bfloat16*>(grad_in), static_cast<__nv_bfloat16*>(grad_out), rows, classes, row_scale);
+  return check_launch(fn);
+}
+
+extern "C" int b200ssl_eval_head(const void* logits, const int64_t* targets, int64_t rows, int32_t classes, int32_t dtype,
+                                 uint64_t* confusion, float* loss_out, int64_t* pred, void* workspace, size_t workspace_bytes,
+                                 void* stream) {
+  const char* fn = "b200ssl_eval_head";
+  if (int e = check_rows(fn, rows, classes, dtype)) return e;
+  if (!logits || !targets || !confusion || !loss_out) return fail(B200SSL_E_NULL, "%s: NULL tensor", fn);
+  if (int e = check_ws(fn, workspace, workspace_bytes, kWsHeaderBytes + sizeof(float) * 2 * kMaxRowCtas)) return e;
+  EvalParams p{logits, reinterpret_cast<const long long*>(targets), rows, classes, reinterpret_cast<unsigned long long*>(confusion),
+               loss_out, reinterpret_cast<long long*>(pred), reinterpret_cast<float*>(static_cast<char*>(workspace) + kWsHeaderBytes),
+               reinterpret_cast<unsigned*>(workspace) + 5, reinterpret_cast<unsigned*>(workspace) + kWsBadLabelSlot};
+  B200SSL_ROW_DISPATCH(dtype, classes, {
+    RowLaunch l = row_launch<LPR, EPL>(rows, classes, 1);
+    auto k = eval_head_kernel<T, LPR, EPL>;
+    if (int e = set_smem(k, l.smem)) return e;
+    k<<<l.grid, kRowThreads, l.smem, as_stream(stream)>>>(p);
+  });
   return check_launch(fn);
 }
 

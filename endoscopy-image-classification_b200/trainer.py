@@ -229,41 +229,32 @@ class SemiSupervisedTrainer:
         return model(images)
 
     def evaluate_one(self, show_metric=False, show_report=False, show_cf_matrix=False):
-        """Validation on the EMA weights when ``USE_EMA`` (``fixmatch.py:135-178``).  Returns
-        ``(AverageMeter, metrics dict)``; metrics are micro/macro precision, recall, F1 like
-        ``utils.calculate_metrics`` (plots are out of scope)."""
+        """Validation on the EMA weights when ``USE_EMA`` (``fixmatch.py:135-178``).  Returns ``(AverageMeter, metrics
+        dict)`` with the keys of ``utils.calculate_metrics`` (micro / macro precision, recall, F1 and the ``sen/spec``
+        table).  Per batch ONE launch of the evaluation head (``evaluation.EvalAccumulator``: mean CE, softmax arg-max,
+        confusion matrix on the device); the pass synchronises once, for one device-to-host copy (the reference does
+        two round trips per batch and recounts the predictions on the host).  Plots are out of scope; ``show_cf_matrix``
+        prints the matrix."""
+        from .evaluation import EvalAccumulator
         eval_model = self.ema_model.ema if self.config.TRAIN.USE_EMA else self.model
         eval_model.eval()
-        summary_loss = AverageMeter()
-        preds, targs = [], []
+        acc = EvalAccumulator(self.config.MODEL.NUM_CLASSES, self.device, max_batches=max(len(self.valid_dl), 1),
+                              keep_predictions=bool(show_report))
         with torch.no_grad():
-            for images, targets in tqdm(self.valid_dl, total=len(self.valid_dl)):
+            for images, targets in tqdm(self.valid_dl, total=len(self.valid_dl), disable=self.rank != 0):
                 images = images.to(self.device, non_blocking=True)
                 targets = targets.to(self.device, non_blocking=True)
-                outputs = self._eval_forward(eval_model, images)
-                losses = ce_loss(outputs.float(), targets, reduction="mean")
-                summary_loss.update(losses.item(), self.config.DATA.BATCH_SIZE)
-                preds.append(outputs.argmax(dim=1).cpu())
-                targs.append(targets.cpu())
-        preds, targs = torch.cat(preds).numpy(), torch.cat(targs).numpy()
-        metric = self._metrics(preds, targs)
+                acc.update(self._eval_forward(eval_model, images), targets)
+        summary_loss, metric = acc.finalize(self.config.DATA.BATCH_SIZE)
         if show_metric:
             print("Metric:\n", metric)
         if show_report:
             from sklearn.metrics import classification_report
+            preds, targs = acc.predictions()
             print("Classification Report:\n", classification_report(targs, preds))
+        if show_cf_matrix:
+            print("Confusion matrix (rows: actual, columns: predicted):\n", acc.confusion)
         return summary_loss, metric
-
-    @staticmethod
-    def _metrics(pred, target):
-        from sklearn.metrics import f1_score, precision_score, recall_score
-        kw = dict(y_true=target, y_pred=pred, zero_division=0)
-        out = {}
-        for avg in ("micro", "macro"):
-            out[f"{avg}/precision"] = precision_score(average=avg, **kw)
-            out[f"{avg}/recall"] = recall_score(average=avg, **kw)
-            out[f"{avg}/f1"] = f1_score(average=avg, **kw)
-        return out
 
     # ---- checkpoints (same dict keys as fixmatch.py:181-236) -------------------------------
     def _extra_state(self):

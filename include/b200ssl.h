@@ -122,6 +122,18 @@ B200SSL_API int b200ssl_scale_rows(const void* grad_in, void* grad_out, int64_t 
 /* Number of out-of-range labels the labeled kernels have seen on this workspace (synchronises; reset != 0 clears it). */
 B200SSL_API int b200ssl_bad_label_count(void* workspace, uint32_t* count, int32_t reset);
 
+/* ------------------------------------------------------------ f4 (next) --
+ * Evaluation head: the per-batch tail of evaluate_one (code/fixmatch.py:154-168) in one launch.
+ *   loss_out[0]          = F.cross_entropy(logits, targets, reduction='mean') of this batch (fixmatch.py:156)
+ *   confusion[t*C + p]  += 1 for every row with target t and prediction p = argmax softmax(logits) (first index on
+ *                          ties; :160,166) -- uint64 [classes, classes], accumulated over the batches of a pass
+ *   pred[i]              = p (optional; classification_report)
+ * Every figure of utils.calculate_metrics (code/utils.py:38-55) is a function of the confusion matrix, so a pass ends
+ * with one device-to-host copy.  Labels as in b200ssl_ce_rows_fwd_bwd (-100 ignored, out of range counted and dropped). */
+B200SSL_API int b200ssl_eval_head(const void* logits, const int64_t* targets, int64_t rows, int32_t classes, int32_t dtype,
+                      uint64_t* confusion, float* loss_out, int64_t* pred, void* workspace, size_t workspace_bytes,
+                      void* stream);
+
 /* ---------------------------------------------------------------- K2 ----
  * CoMatch distribution alignment statistics.  Replaces code/comatch.py:167-173:
  * softmax(logits_u_w).mean(0) is pushed on a device-resident history ring

@@ -449,6 +449,42 @@ def pin_fixmatch_train_one(ref_fixmatch, ref_utils, out):
     np.savez_compressed(out / "fixmatch_train_one.npz", **arrs)
 
 
+def pin_evaluate_one(ref_fixmatch, ref_utils, out):
+    """The REAL ``FixMatch.evaluate_one`` (fixmatch.py:135-178) + ``utils.calculate_metrics`` (utils.py:38-55) on scripted
+    validation logits: summary loss, micro / macro precision / recall / F1 and the per-class sensitivity / specificity
+    table.  Pins ``oracle.evaluate_one`` and gives the evaluation head its golden vector."""
+    import contextlib
+    import io
+    N, BS = 500, 32                                   # a ragged last batch (20 rows)
+    g = torch.Generator().manual_seed(2024)
+    y = torch.randint(0, C, (N,), generator=g)
+    y[:C] = torch.arange(C)                           # every class present (the reference indexes recall[1] per class)
+    logits = 3.0 * torch.nn.functional.one_hot(y, C).float() + 2.0 * torch.randn(N, C, generator=g)
+    batches = [(torch.zeros(len(y[i:i + BS]), 1), y[i:i + BS]) for i in range(0, N, BS)]
+    model = ScriptedModel([{"logits": logits[i:i + BS]} for i in range(0, N, BS)], with_feats=False)
+    tr = ref_fixmatch.FixMatch(model, device="cpu")
+    tr.config = ref_utils.AttrDict(DATA=ref_utils.AttrDict(BATCH_SIZE=BS), MODEL=ref_utils.AttrDict(NUM_CLASSES=C),
+                                   TRAIN=ref_utils.AttrDict(USE_EMA=False))
+    tr.get_dataloader((None, None), _Loader(batches))
+    with contextlib.redirect_stderr(io.StringIO()):
+        meter, metric = tr.evaluate_one()
+    mine = O.evaluate_one([logits[i:i + BS] for i in range(0, N, BS)], [b[1] for b in batches], C, BS)
+    close(mine["loss_avg"], meter.avg, rtol=1e-6, what="evaluate_one loss")
+    keys = ["micro/precision", "micro/recall", "micro/f1", "macro/precision", "macro/recall", "macro/f1"]
+    for k in keys:
+        close(mine["metric"][k], metric[k], rtol=1e-12, what=k)
+    sen = metric["sen/spec"]
+    close(torch.tensor(mine["metric"]["sen/spec"]["sensitivity"].values), torch.tensor(sen["sensitivity"].values), rtol=1e-12, what="sensitivity")
+    close(torch.tensor(mine["metric"]["sen/spec"]["specificity"].values), torch.tensor(sen["specificity"].values), rtol=1e-12, what="specificity")
+    arrs = {"logits": logits.numpy(), "targets": y.numpy(), "loss_avg": np.float64(meter.avg), "loss_val": np.float64(meter.val),
+            "loss_sum": np.float64(meter.sum), "loss_count": np.float64(meter.count),
+            "metrics": np.array([metric[k] for k in keys], dtype=np.float64),
+            "sensitivity": sen["sensitivity"].values.astype(np.float64), "specificity": sen["specificity"].values.astype(np.float64),
+            "confusion": mine["confusion"].astype(np.int64),
+            "meta": np.array(json.dumps(dict(N=N, batch_size=BS, C=C, metric_keys=keys)))}
+    np.savez_compressed(out / "evaluate_one.npz", **arrs)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--out", default=str(REPO / "tests" / "golden"))
@@ -461,13 +497,14 @@ def main():
     pin_ema(ref_ema, out)
     pin_comatch(ref_comatch, ref_utils, ref_ema, out)
     pin_fixmatch_train_one(ref_fixmatch, ref_utils, out)
+    pin_evaluate_one(ref_fixmatch, ref_utils, out)
     manifest = {}
     for f in sorted(out.glob("*.npz")):
         with np.load(f, allow_pickle=False) as z:
             manifest[f.name] = sha({k: z[k] for k in z.files})
     (out / "MANIFEST.json").write_text(json.dumps(
         {"generator": "oracle/pin_against_reference.py", "torch": torch.__version__,
-         "reference": "taindp98/Endoscopy-Image-Classification @ /root/reference (code/loss.py, ema.py, comatch.py, fixmatch.py)",
+         "reference": "taindp98/Endoscopy-Image-Classification @ /root/reference (code/loss.py, ema.py, comatch.py, fixmatch.py, utils.py)",
          "sha256": manifest}, indent=1) + "\n")
     print("oracle pinned against the reference; fixtures:", ", ".join(manifest))
 

@@ -318,3 +318,47 @@ def comatch_head_sharded(state: CoMatchState, da_histories: List[List[torch.Tens
     for o in outs:
         bank_enqueue(state, o["feats_w"], o["probs_w"], "always")
     return outs
+
+
+# --------------------------------------------------------------------------
+# evaluation
+# --------------------------------------------------------------------------
+def calculate_metrics(pred: np.ndarray, target: np.ndarray, num_classes: int) -> Dict[str, object]:
+    """code/utils.py:38-55 verbatim in behaviour: per-class sensitivity / specificity from one-vs-rest
+    ``precision_recall_fscore_support`` and micro / macro precision, recall, F1 through scikit-learn."""
+    import pandas as pd
+    from sklearn.metrics import f1_score, precision_recall_fscore_support, precision_score, recall_score
+    res = []
+    for l in range(num_classes):
+        _, recall, _, _ = precision_recall_fscore_support(np.array(target) == l, np.array(pred) == l, pos_label=True, average=None)
+        res.append([l, recall[1], recall[0]])
+    df = pd.DataFrame(res, columns=["class", "sensitivity", "specificity"])
+    out = {"sen/spec": df}
+    for avg in ("micro", "macro"):
+        out[f"{avg}/precision"] = precision_score(y_true=target, y_pred=pred, average=avg)
+        out[f"{avg}/recall"] = recall_score(y_true=target, y_pred=pred, average=avg)
+        out[f"{avg}/f1"] = f1_score(y_true=target, y_pred=pred, average=avg)
+    return out
+
+
+def evaluate_one(logits_batches: Sequence[torch.Tensor], target_batches: Sequence[torch.Tensor], num_classes: int,
+                 batch_size: int) -> Dict[str, object]:
+    """code/fixmatch.py:135-178 for scripted model outputs: per batch ``ce_loss(outputs, targets, reduction='mean')`` into
+    an AverageMeter weighted by ``DATA.BATCH_SIZE`` (:158, the configured size, also for a ragged last batch), softmax ->
+    argmax over the whole set (:165-168), then ``calculate_metrics``.  Also returns the confusion matrix (rows = target,
+    columns = prediction) every metric above is a function of."""
+    s = cnt = 0.0
+    val = 0.0
+    preds, targs = [], []
+    for x, y in zip(logits_batches, target_batches):
+        val = float(F.cross_entropy(x.float(), y.long(), reduction="mean"))
+        s += val * batch_size
+        cnt += batch_size
+        preds.append(np.argmax(torch.softmax(x.float(), dim=1).numpy(), axis=1))
+        targs.append(y.numpy())
+    pred, targ = np.concatenate(preds), np.concatenate(targs)
+    conf = np.zeros((num_classes, num_classes), dtype=np.int64)
+    np.add.at(conf, (targ, pred), 1)
+    return {"loss_avg": s / cnt, "loss_val": val, "loss_sum": s, "loss_count": cnt, "pred": pred, "target": targ,
+            "confusion": conf, "metric": calculate_metrics(pred, targ, num_classes)}
+
