@@ -8,13 +8,15 @@
 //   QpT tile [32 x 128] ---->  numer[128 x 32] += P QpT^T (TMEM accumulator, K = 128 keys)
 //
 // Warp roles (576 threads): warp 0 = TMEM allocator + TMA producer, warp 1 = MMA
-// issuer (one thread), warps 2..17 = epilogue in TWO groups of 8 warps that take
-// alternate S tiles (group g owns S[g] in TMEM and P[g] in smem; 2 threads per query
-// row, 64 key columns each): while one group waits for its S tile, drains TMEM or
-// publishes P, the other keeps the MUFU unit busy -- one group alone left it idle for
-// half of every tile (ncu, round 2: 52 % XU, 23 % of the samples on the mbarriers).
-// The bank is split over a cluster of CTAs whose partials are folded through DSMEM in
-// rank order (deterministic).
+// issuer (one thread), warps 2..17 = epilogue (4 threads per TMEM lane = query row,
+// 32 key columns each).  S (TMEM) and P (smem) are double-buffered so GEMM1 of unit
+// j+1 and GEMM2 of unit j-1 overlap the exp of unit j, and the epilogue is software
+// pipelined: the tcgen05.ld of unit j+1 is issued before the exponentials of unit j, so
+// the S_FULL wait and the TMEM read latency hide behind the MUFU work (ncu, round 2:
+// one third of the epilogue's samples sat on the barriers / ld with the MUFU unit idle).
+// Two epilogue groups taking alternate tiles (64 columns per thread) were tried and were
+// 25 % slower (profiles/r02_k3_tune_pingpong.jsonl).  The bank is split over a cluster of
+// CTAs whose partials are folded through DSMEM in rank order (deterministic).
 //
 // Bank layout for this path: queue_feats [K, 64] bf16 row-major (a row is exactly one
 // 128-byte swizzle row) and a transposed, class-padded copy of the probabilities
@@ -82,13 +84,11 @@ namespace cg = cooperative_groups;
 constexpr int kBM = 128;          // queries per row tile (UMMA M)
 constexpr int kBN = 128;          // keys per tile    (UMMA N of GEMM1 / K of GEMM2)
 constexpr int kCP = 32;           // classes + the "ones" column, padded (UMMA N of GEMM2)
-constexpr int kStages = 4;        // key tiles in flight: GEMM1 runs two units ahead of the exponentials, so three tiles are in use while the
-                                  // fourth is loading (and at the reference's sizes every load of a CTA is in flight at once)
+constexpr int kStages = 4;        // key tiles in flight (at the reference's sizes every load of a CTA is in flight at once; remote shards: NVLink latency)
 constexpr int kMaxMT = 4;         // row tiles one CTA can serve from ONE staged key tile ("row loop"): a remote key tile
                                   // then crosses NVLink once per step instead of once per row tile
-constexpr int kEpiWarps = 16;     // two groups of 8: 2 per TMEM lane quarter and group, each thread owns 64 of the 128 key columns of its row
+constexpr int kEpiWarps = 16;     // 4 per TMEM lane quarter: each thread owns 32 of the 128 key columns of its row
 constexpr int kEpiThreads = kEpiWarps * 32;
-constexpr int kGroupThreads = kEpiThreads / 2;
 constexpr int kTcThreads = 64 + kEpiThreads;   // warp 0 TMA + TMEM alloc, warp 1 MMA, warps 2.. epilogue
 constexpr int kMaxCluster = 8;
 constexpr int kMaxSeg = 8;        // bank segments = shards of a rank-sharded bank (1 = the whole bank is local)
@@ -199,10 +199,10 @@ bank_smooth_tc_kernel(const __grid_constant__ CUtensorMap tm_f, const __grid_con
     }
     for (int s = 0; s < 2; ++s) {
       tc::mbar_init(&bars[BAR_S_FULL + s], 1);
-      tc::mbar_init(&bars[BAR_S_EMPTY + s], kGroupThreads);
+      tc::mbar_init(&bars[BAR_S_EMPTY + s], kEpiThreads);
     }
     for (int s = 0; s < 2; ++s) {
-      tc::mbar_init(&bars[BAR_P_FULL + s], kGroupThreads);
+      tc::mbar_init(&bars[BAR_P_FULL + s], kEpiThreads);
       tc::mbar_init(&bars[BAR_P_EMPTY + s], 1);
     }
     tc::mbar_init(&bars[BAR_ACC], 1);
@@ -264,7 +264,7 @@ bank_smooth_tc_kernel(const __grid_constant__ CUtensorMap tm_f, const __grid_con
         const int t = j / M, m = j - t * M;
         const int s = t % kStages, b = j & 1;
         if (m == 0) tc::mbar_wait(&bars[BAR_KV_FULL + s], (t / kStages) & 1, abort_flag);
-        if (j >= 2) tc::mbar_wait(&bars[BAR_S_EMPTY + b], ((j >> 1) - 1) & 1, abort_flag);   // group b has S of unit j-2 in registers
+        if (j >= 2) tc::mbar_wait(&bars[BAR_S_EMPTY + b], ((j >> 1) - 1) & 1, abort_flag);   // S of unit j-2 is in registers
         tc::tcgen05_fence_after();
         const uint64_t a_desc = tc::smem_desc_sw128(tc::smem_u32(sA + (size_t)m * kTileA));
         const uint64_t b_desc = tc::smem_desc_sw128(tc::smem_u32(sQf + s * kTileQf));
@@ -287,60 +287,63 @@ bank_smooth_tc_kernel(const __grid_constant__ CUtensorMap tm_f, const __grid_con
         if (m == M - 1) tc::mma_commit(&bars[BAR_KV_EMPTY + s]);   // the key tile has served every row tile
         tc::mma_commit(&bars[BAR_P_EMPTY + pb]);
       };
-      // Issue order follows the order in which the two epilogue groups (half a tile apart in steady state) raise their
-      // barriers: "S of unit j is in registers" comes early in unit j, "P of unit j-1 is in smem" half a tile later.
-      // GEMM1 of unit j+2 is therefore in flight long before its group finishes unit j.
       gemm1(0);
-      if (J > 1) gemm1(1);
       for (int j = 0; j < J; ++j) {
-        if (j + 2 < J) gemm1(j + 2);
-        if (j >= 1) gemm2(j - 1);
+        if (j + 1 < J) gemm1(j + 1);                       // S is double buffered: GEMM1 of unit j+1 overlaps the exp of unit j
+        gemm2(j);
       }
-      gemm2(J - 1);
       tc::mma_commit(&bars[BAR_ACC]);
     }
   } else {
-    // ===== epilogue: group g = units j = g, g+2, ...; two threads per TMEM lane (query row), 64 of the 128 key columns each =====
-    const int quarter = warp & 3;                           // TMEM lanes [32*quarter, +32) are visible to this warp
-    const int ew = warp - 2;                                // 0..15
-    const int grp = ew >> 3, colh = (ew >> 2) & 1;          // S / P buffer of the group; 64-column half = P sub-tile
-    const int colq = ew >> 2;                               // 0..3: row tile this warp stages at the end
+    // ===== epilogue: four threads per TMEM lane (query row), 32 of the 128 key columns each =====
+    const int quarter = warp & 3, colq = (warp - 2) >> 2;   // TMEM lanes [32*quarter, +32) are visible to this warp
+    const int half = colq >> 1, c2 = colq & 1;              // P sub-tile (64 keys) and 32-column group inside it
     const int r_in = quarter * 32 + lane;
     const uint32_t lane_addr = tmem + ((uint32_t)(quarter * 32) << 16);
-    uint8_t* p_row = sP + grp * kTileP + colh * kSubP;
-    for (int j = grp; j < J; j += 2) {
-      const int n = j >> 1;                                 // n-th unit of this group
-      tc::mbar_wait(&bars[BAR_S_FULL + grp], n & 1, abort_flag);
-      if (j == 0 && threadIdx.x == 64) B200SSL_STAMP(p.dbg, cta, 3);   // first S tile ready (TMA + GEMM1)
-      tc::tcgen05_fence_after();
-      uint32_t r[64];
-      {
-        uint32_t (&lo)[32] = *reinterpret_cast<uint32_t(*)[32]>(&r[0]);
-        uint32_t (&hi)[32] = *reinterpret_cast<uint32_t(*)[32]>(&r[32]);
-        tc::tmem_ld_32x32(lane_addr + grp * kBN + colh * 64, lo);
-        tc::tmem_ld_32x32(lane_addr + grp * kBN + colh * 64 + 32, hi);
+    uint32_t r[32], rn[32];                                 // S of the current / the next unit
+    tc::mbar_wait(&bars[BAR_S_FULL + 0], 0, abort_flag);
+    if (threadIdx.x == 64) B200SSL_STAMP(p.dbg, cta, 3);    // first S tile ready (TMA + GEMM1)
+    tc::tcgen05_fence_after();
+    tc::tmem_ld_32x32(lane_addr + colq * 32, r);
+    tc::tmem_ld_wait();
+    tc::tcgen05_fence_before();
+    tc::mbar_arrive(&bars[BAR_S_EMPTY + 0]);                // S[0] is in registers: GEMM1 of unit 2 may overwrite it
+    for (int j = 0; j < J; ++j) {
+      const int b = j & 1;
+      const bool more = j + 1 < J;
+      if (more) {
+        // software pipeline: the TMEM read of unit j+1 (ready long ago: its GEMM1 was issued a unit earlier) flies
+        // while this unit's exponentials keep the MUFU unit busy
+        tc::mbar_wait(&bars[BAR_S_FULL + (b ^ 1)], ((j + 1) >> 1) & 1, abort_flag);
+        tc::tcgen05_fence_after();
+        tc::tmem_ld_32x32(lane_addr + (b ^ 1) * kBN + colq * 32, rn);
       }
-      tc::tmem_ld_wait();
-      tc::tcgen05_fence_before();
-      tc::mbar_arrive(&bars[BAR_S_EMPTY + grp]);            // S[grp] is in registers: GEMM1 of unit j+2 may overwrite it
       // keys beyond the bank need no mask: their QpT columns (incl. the ones column) are TMA zero fill
-      uint32_t w[32];
+      uint32_t w[16];
 #pragma unroll
-      for (int e = 0; e < 32; ++e) {
-        const float s0 = __uint_as_float(r[2 * e]), s1 = __uint_as_float(r[2 * e + 1]);                 // comatch.py:180
-        const float e0 = poly_slot<NPOLY>((2 * e) & 31) ? ex2_poly(s0, p.scale, p.s_min) : ex2_approx(s0 * p.scale);
-        const float e1 = poly_slot<NPOLY>((2 * e + 1) & 31) ? ex2_poly(s1, p.scale, p.s_min) : ex2_approx(s1 * p.scale);
+      for (int e = 0; e < 16; ++e) {
+        const float s0 = __uint_as_float(r[2 * e]), s1 = __uint_as_float(r[2 * e + 1]);               // comatch.py:180
+        const float e0 = poly_slot<NPOLY>(2 * e) ? ex2_poly(s0, p.scale, p.s_min) : ex2_approx(s0 * p.scale);
+        const float e1 = poly_slot<NPOLY>(2 * e + 1) ? ex2_poly(s1, p.scale, p.s_min) : ex2_approx(s1 * p.scale);
         const __nv_bfloat162 h = __floats2bfloat162_rn(e0, e1);
         w[e] = *reinterpret_cast<const uint32_t*>(&h);
       }
       // the P buffer of unit j-2 must have been consumed -- only now, after the exponentials
-      if (n >= 1) tc::mbar_wait(&bars[BAR_P_EMPTY + grp], (n - 1) & 1, abort_flag);
+      if (j >= 2) tc::mbar_wait(&bars[BAR_P_EMPTY + b], ((j >> 1) - 1) & 1, abort_flag);
 #pragma unroll
-      for (int q = 0; q < 8; ++q)
-        *reinterpret_cast<uint4*>(p_row + tc::sw128_offset(r_in, q)) = make_uint4(w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
+      for (int q = 0; q < 4; ++q)
+        *reinterpret_cast<uint4*>(sP + b * kTileP + half * kSubP + tc::sw128_offset(r_in, c2 * 4 + q)) =
+            make_uint4(w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
+      if (more) {
+        tc::tmem_ld_wait(rn);
+        tc::tcgen05_fence_before();
+        tc::mbar_arrive(&bars[BAR_S_EMPTY + (b ^ 1)]);      // S of unit j+1 is in registers
+#pragma unroll
+        for (int i = 0; i < 32; ++i) r[i] = rn[i];
+      }
       tc::fence_proxy_async_smem();               // generic-proxy writes of P -> visible to the tensor core
-      tc::mbar_arrive(&bars[BAR_P_FULL + grp]);
-      if (j == J - 1 && lane == 0 && quarter == 2 && colh == 0) B200SSL_STAMP(p.dbg, cta, 4);   // last exp tile done
+      tc::mbar_arrive(&bars[BAR_P_FULL + b]);
+      if (j == J - 1 && threadIdx.x == 64) B200SSL_STAMP(p.dbg, cta, 4);   // last exp tile done
     }
     tc::mbar_wait(&bars[BAR_ACC], 0, abort_flag);           // all MMAs retired: pipeline smem is free, accumulators final
     if (threadIdx.x == 64) B200SSL_STAMP(p.dbg, cta, 5);
@@ -465,12 +468,12 @@ int g_force_cluster = 0, g_force_nouter = 0;                                    
 int g_force_poly = getenv("B200SSL_K3_POLY") ? atoi(getenv("B200SSL_K3_POLY")) : -1;   // exponentials (of 32) on the FMA pipe
 
 // Clusters of `cl` CTAs (one CTA per SM: the kernel takes more than half an SM's shared memory) that the chip runs at once.
-// A cluster lives inside one GPC, so the SMs a GPC has beyond a multiple of `cl` stay idle: 148 / 74 / ~33 / ~16 on B200.
+// A cluster lives inside one GPC, so the SMs a GPC has beyond a multiple of `cl` stay idle: 148 / 74 / 33 / 15 on B200.
 // Asked from the driver once per size; the table is the fallback without a device (CPU tests of the plan).
 int max_active_clusters(int cl) {
   static int cache[kMaxCluster + 1] = {0};
   if (cache[cl]) return cache[cl];
-  int n = cl == 1 ? 148 : cl == 2 ? 74 : cl == 4 ? 33 : 16;
+  int n = cl == 1 ? 148 : cl == 2 ? 74 : cl == 4 ? 33 : 15;     // measured on B200 (b200ssl_debug_max_active_clusters)
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) == cudaSuccess && ndev > 0) {
     cudaFuncSetAttribute(bank_smooth_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_request(kMaxMT));

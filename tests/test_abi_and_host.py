@@ -306,10 +306,11 @@ def test_k3_launch_plan_invariants(native):
                 need = 256 + 65536 + (no * groups * mt * 128 * 24 * 4 if no > 1 else 0)
                 assert lib.b200ssl_workspace_bytes(rows, 23, K) >= need, (rows, K, remote)
     # BASELINE cfg 4 on 8 ranks (448 queries per rank, 65536 rows): the whole chip shares the key tiles
-    # (a cluster lives inside one GPC: B200 holds 16 clusters of 8 one-CTA-per-SM blocks at once, not 148 / 8 = 18)
-    assert [lib.b200ssl_debug_max_active_clusters(c) for c in (1, 2, 4, 8)] == [148, 74, 33, 16]    # the no-device table
+    # (a cluster lives inside one GPC: B200 holds 15 clusters of 8 one-CTA-per-SM blocks at once, not 148 / 8 = 18)
+    assert [lib.b200ssl_debug_max_active_clusters(c) for c in (1, 2, 4, 8)] == [148, 74, 33, 15]    # the no-device table (= what a B200 reports)
     lib.b200ssl_debug_smooth_plan(448, 65536, 1, out)
-    assert list(out) == [4, 8, 16]
+    mt, cl, no = list(out)
+    assert mt == 4 and 100 <= cl * no <= 148 and no <= lib.b200ssl_debug_max_active_clusters(cl)
     # the sweep corner: no half-empty second wave (round 1 ran 224 CTAs on 148 SMs)
     lib.b200ssl_debug_smooth_plan(3584, 65536, 0, out)
     mt, cl, no = list(out)

@@ -175,10 +175,10 @@ def test_ce_loss_unreduced_sum_soft_and_ignore(pkg, rows, classes, dtype):
     up = torch.rand(rows, generator=g) + 0.5                       # per-row upstream gradient
     for kw in (dict(), dict(class_weights=cw), dict(type_loss="poly"), dict(type_loss="poly", class_weights=cw)):
         for red in ("none", "sum"):
-            xr = x.float().requires_grad_(True)
+            xr = x.float().clone().requires_grad_(True)
             r = O.ce_loss(xr, y, reduction=red, **kw)
             (r * up).sum().backward() if red == "none" else r.backward()
-            xd = x.cuda().requires_grad_(True)
+            xd = x.clone().cuda().requires_grad_(True)
             kwd = {k: (v.cuda() if torch.is_tensor(v) else v) for k, v in kw.items()}
             l = loss.ce_loss(xd, y.cuda(), reduction=red, **kwd)
             assert l.shape == r.shape
