@@ -75,6 +75,7 @@ SIGNATURES = {
                                     _vp, _i64, _vp, _f32, _vp, _sz, _vp]),
     "b200ssl_ema_multi_tensor": (_i32, [_vp, _i32, _i32, _i32, _f32, _f32, _i32, _vp]),
     "b200ssl_opt_ema_multi_tensor": (_i32, [_vp, _i32, _vp, _i32, _f32, _f32, _vp]),
+    "b200ssl_opt_ema_multi_tensor_dev": (_i32, [_vp, _i32, _vp, _i32, _f32, _f32, _vp]),
     "b200ssl_peer_control_bytes": (_sz, []),
     "b200ssl_peer_alloc": (_i32, [_sz, _vp, _vp]),
     "b200ssl_peer_open": (_i32, [_vp, _vp]),

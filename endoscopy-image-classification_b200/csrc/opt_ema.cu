@@ -51,11 +51,14 @@ __device__ __forceinline__ void update_elem(Elem& x, const GroupRow& h, float d,
     for (int r = 0; r < ema_repeat; ++r) x.e = __fadd_rn(__fmul_rn(d, x.e), __fmul_rn(o, x.p));   // ema.py:53-56
 }
 
+// dev_groups != NULL: the group rows are read from device memory (a CUDA graph replays the launch while the host refreshes
+// the step-dependent scalars with a 64-byte-per-group copy ahead of every replay); NULL: they travel as kernel parameters.
 __global__ void __launch_bounds__(kOptThreads, 4) opt_ema_kernel(const b200ssl_opt_block* __restrict__ blocks, int n_blocks,
-                                                                  const __grid_constant__ GroupTable groups, float d, float o) {
+                                                                  const __grid_constant__ GroupTable groups,
+                                                                  const GroupRow* __restrict__ dev_groups, float d, float o) {
   for (int b = blockIdx.x; b < n_blocks; b += gridDim.x) {
     const b200ssl_opt_block blk = blocks[b];
-    const GroupRow h = groups.g[blk.group & (kMaxGroups - 1)];
+    const GroupRow h = dev_groups ? dev_groups[blk.group & (kMaxGroups - 1)] : groups.g[blk.group & (kMaxGroups - 1)];
     float* p = static_cast<float*>(blk.param);
     const float* g = static_cast<const float*>(blk.grad);
     float* s1 = static_cast<float*>(blk.state1);
@@ -109,6 +112,22 @@ extern "C" int b200ssl_opt_ema_multi_tensor(const b200ssl_opt_block* blocks, int
     if (table.g[i].kind < B200SSL_OPT_SGD || table.g[i].kind > B200SSL_OPT_ADAMW) return fail(B200SSL_E_ARG, "%s: group %d: kind %d", fn, i, table.g[i].kind);
   const int max_grid = kNumSMs * 4;
   const int grid = n_blocks < max_grid ? n_blocks : max_grid;
-  opt_ema_kernel<<<grid, kOptThreads, 0, as_stream(stream)>>>(blocks, n_blocks, table, decay, one_minus_decay);
+  opt_ema_kernel<<<grid, kOptThreads, 0, as_stream(stream)>>>(blocks, n_blocks, table, nullptr, decay, one_minus_decay);
+  return check_launch(fn);
+}
+
+extern "C" int b200ssl_opt_ema_multi_tensor_dev(const b200ssl_opt_block* blocks, int32_t n_blocks, const b200ssl_opt_group* groups_dev,
+                                                int32_t n_groups, float decay, float one_minus_decay, void* stream) {
+  const char* fn = "b200ssl_opt_ema_multi_tensor_dev";
+  if (!blocks || !groups_dev) return fail(B200SSL_E_NULL, "%s: NULL table", fn);
+  if ((reinterpret_cast<uintptr_t>(blocks) | reinterpret_cast<uintptr_t>(groups_dev)) & 15u)
+    return fail(B200SSL_E_ALIGN, "%s: the tables must be 16-byte aligned", fn);
+  if (n_blocks <= 0 || n_groups <= 0 || n_groups > kMaxGroups)
+    return fail(B200SSL_E_SHAPE, "%s: n_blocks=%d n_groups=%d (1..%d parameter groups)", fn, n_blocks, n_groups, kMaxGroups);
+  GroupTable table{};
+  const int max_grid = kNumSMs * 4;
+  const int grid = n_blocks < max_grid ? n_blocks : max_grid;
+  opt_ema_kernel<<<grid, kOptThreads, 0, as_stream(stream)>>>(blocks, n_blocks, table, reinterpret_cast<const GroupRow*>(groups_dev), decay,
+                                                             one_minus_decay);
   return check_launch(fn);
 }

@@ -29,7 +29,7 @@ import torch
 from . import _native as N
 from .ema import ModelEMA, _EmaPlan
 
-__all__ = ["FusedOptimizerEMA"]
+__all__ = ["FusedOptimizerEMA", "CapturedFusedStep"]
 
 OPT_SGD, OPT_ADAM, OPT_ADAMW = 0, 1, 2
 BLOCK = np.dtype([("param", "<u8"), ("grad", "<u8"), ("s1", "<u8"), ("s2", "<u8"), ("ema", "<u8"), ("count", "<i4"),
@@ -61,6 +61,8 @@ def group_row(kind: int, g: dict, step: int) -> tuple:
                 int(step == 1), 0, 0.0, 0.0, 1.0, 0.0)
     b1, b2 = (float(b) for b in g["betas"])
     bc1, bc2 = 1.0 - b1 ** step, 1.0 - b2 ** step
+    if g.get("decoupled_weight_decay", False):       # torch.optim.Adam(decoupled_weight_decay=True) is AdamW
+        kind = OPT_ADAMW
     return (lr, b1, b2, float(g["eps"]), wd, lr / bc1, math.sqrt(bc2), 0.0, kind, 0, int(step == 1), 0, 1.0 - b1, 1.0 - b2,
             1.0 - lr * wd, 0.0)
 
@@ -172,6 +174,13 @@ class FusedOptimizerEMA:
         live = [[p for gi2, _, p in params if gi2 == gi] for gi in range(len(self.optimizer.param_groups))]
         steps = [] if self.kind == OPT_SGD else [self.optimizer.state[p]["step"] for p in plist]
         base = [int(self.optimizer.state[ps[0]]["step"]) if (ps and self.kind != OPT_SGD) else 0 for ps in live]
+        if self.kind != OPT_SGD:
+            # the bias corrections are per-group scalars: parameters of one group that have been stepped a different number
+            # of times (a head that received its first gradient later) cannot share them
+            for gi, ps in enumerate(live):
+                if any(int(self.optimizer.state[p]["step"]) != base[gi] for p in ps):
+                    raise NotImplementedError("Adam: parameters of one group must have been stepped equally often; put "
+                                              "late-starting parameters into their own param group")
         self._tables = dict(base=base, blocks=blocks, n_blocks=len(tbl), device=device, rest=rest_plan, params=plist, live=live, steps=steps,
                             grads=[(p, p.grad) for p in plist], ptrs=[(p, p.data_ptr()) for p in (plist[0], plist[-1])])
 
@@ -181,15 +190,15 @@ class FusedOptimizerEMA:
             return False
         if self.kind != OPT_SGD and any(self.optimizer.state[p].get("step") is not s for p, s in zip(t["params"][:1], t["steps"][:1])):
             return False                             # optimizer state was replaced (load_state_dict)
-        return all(p.grad is g for p, g in t["grads"]) and all(p.data_ptr() == a for p, a in t["ptrs"])
+        if not (all(p.grad is g for p, g in t["grads"]) and all(p.data_ptr() == a for p, a in t["ptrs"])):
+            return False
+        # a trainable parameter that received its first gradient since the tables were built must join them
+        return sum(1 for g in self.optimizer.param_groups for p in g["params"] if p.grad is not None) == len(t["params"])
 
     # ---- public API ---------------------------------------------------------------------------
-    @torch.no_grad()
-    def step(self) -> None:
-        if not self._valid():
-            self._build()
-        t = self._tables
-        # per-group scalars of this step (the step counters live in the optimizer's state like torch keeps them)
+    def _group_rows(self, t):
+        """Per-group scalars of the coming step (the step counters live in the optimizer's state like torch keeps them);
+        returns ``(rows, any_first)``."""
         rows = np.zeros(len(self.optimizer.param_groups), dtype=GROUP)
         any_first = False
         for gi, g in enumerate(self.optimizer.param_groups):
@@ -205,13 +214,10 @@ class FusedOptimizerEMA:
             elif live:
                 step = t["base"][gi] + self._pending + 1
             rows[gi] = group_row(self.kind, g, step)
-        d = self.ema.decay if self.ema is not None else 0.0
-        N.check(N.lib().b200ssl_opt_ema_multi_tensor(t["blocks"].data_ptr(), t["n_blocks"], rows.ctypes.data,
-                                                     len(rows), float(np.float32(d)), float(np.float32(1.0 - d)),
-                                                     N.stream_ptr(t["device"])), "opt_ema_multi_tensor")
-        if t["rest"] is not None and t["rest"].n_blocks > 0:
-            t["rest"].launch(self.ema.decay, 0)
-        # bookkeeping torch.optim would have done
+        return rows, any_first
+
+    def _after_step(self, t, any_first) -> None:
+        """Bookkeeping torch.optim would have done."""
         if self.kind == OPT_SGD:
             if any_first:
                 for p in t["params"]:
@@ -219,6 +225,41 @@ class FusedOptimizerEMA:
         else:
             self._pending += 1                       # written back to the per-parameter step tensors by _flush_steps()
         self._steps += 1
+
+    @property
+    def bytes_per_step(self) -> int:
+        """Algorithmic HBM bytes of one fused launch: p, g, state, e read once; p, state, e written once."""
+        if not self._valid():
+            self._build()
+        t, total = self._tables, 0
+        for p in t["params"]:
+            st = self.optimizer.state[p]
+            n_state = 0 if self.kind == OPT_SGD and st.get("momentum_buffer") is None else (1 if self.kind == OPT_SGD else 2)
+            total += p.numel() * 4 * (3 + 2 * n_state + 2)   # p r/w, g r, states r/w, ema r/w (parameters without an EMA copy are rare)
+        return total
+
+    @torch.no_grad()
+    def step(self) -> None:
+        if not self._valid():
+            self._build()
+        t = self._tables
+        rows, any_first = self._group_rows(t)
+        d = self.ema.decay if self.ema is not None else 0.0
+        N.check(N.lib().b200ssl_opt_ema_multi_tensor(t["blocks"].data_ptr(), t["n_blocks"], rows.ctypes.data,
+                                                     len(rows), float(np.float32(d)), float(np.float32(1.0 - d)),
+                                                     N.stream_ptr(t["device"])), "opt_ema_multi_tensor")
+        if t["rest"] is not None and t["rest"].n_blocks > 0:
+            t["rest"].launch(self.ema.decay, 0)
+        self._after_step(t, any_first)
+
+    @torch.no_grad()
+    def capture(self) -> "CapturedFusedStep":
+        """The fused step as a CUDA graph (the step of a captured training loop): the group rows live in device memory and
+        are refreshed by ``CapturedFusedStep.replay()`` with one 64-byte-per-group copy ahead of the graph launch, so the
+        learning-rate schedule and Adam's bias corrections keep changing while the launches are replayed."""
+        if not self._valid():
+            self._build()
+        return CapturedFusedStep(self)
 
     def zero_grad(self) -> None:
         """In-place zero of the gradients (their addresses are baked into the device table)."""
@@ -231,3 +272,52 @@ class FusedOptimizerEMA:
 
     def load_state_dict(self, sd) -> None:
         self.optimizer.load_state_dict(sd)      # the post hook drops the tables: state tensors were re-created
+
+
+class CapturedFusedStep:
+    """``optimizer.step(); ema.update(model)`` as one replayed graph node sequence.  ``replay()`` == ``FusedOptimizerEMA.step()``
+    bit for bit (same kernel, same scalars); the tables are those of the owner at capture time -- a gradient that moves
+    afterwards invalidates the graph (``replay`` raises)."""
+    RING = 64
+
+    def __init__(self, owner: FusedOptimizerEMA):
+        self.owner = owner
+        t = owner._tables
+        self.tables = t
+        dev = t["device"]
+        G = len(owner.optimizer.param_groups)
+        self._host = torch.zeros(self.RING, G * GROUP.itemsize, dtype=torch.uint8).pin_memory()
+        self._host_np = self._host.numpy()
+        self._dev = torch.zeros(G * GROUP.itemsize, dtype=torch.uint8, device=dev)
+        self._slot = 0
+        self._guard = [None] * self.RING           # event recorded after the copy out of a pinned slot
+        d = owner.ema.decay if owner.ema is not None else 0.0
+        rows, _ = owner._group_rows(t)
+        self._dev.copy_(torch.from_numpy(rows.view(np.uint8).copy()))
+        torch.cuda.synchronize(dev)
+        self.graph = torch.cuda.CUDAGraph()
+        # the capture only records the launches: parameters, optimizer state and EMA are NOT stepped by it
+        with torch.cuda.graph(self.graph):
+            N.check(N.lib().b200ssl_opt_ema_multi_tensor_dev(t["blocks"].data_ptr(), t["n_blocks"], self._dev.data_ptr(), G,
+                                                             float(np.float32(d)), float(np.float32(1.0 - d)),
+                                                             N.stream_ptr(dev)), "opt_ema_multi_tensor_dev")
+            if t["rest"] is not None and t["rest"].n_blocks > 0:
+                t["rest"].launch(owner.ema.decay, 0)
+
+    @torch.no_grad()
+    def replay(self) -> None:
+        o = self.owner
+        if o._tables is not self.tables or not o._valid():
+            raise RuntimeError("the captured fused step is stale (gradients or optimizer state were re-allocated): capture() again")
+        rows, any_first = o._group_rows(self.tables)
+        i = self._slot
+        if self._guard[i] is not None:
+            self._guard[i].synchronize()             # the copy that last read this pinned slot has run (64 replays ago)
+        self._host_np[i, :] = rows.view(np.uint8)
+        self._dev.copy_(self._host[i], non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        self._guard[i] = ev
+        self._slot = (i + 1) % self.RING
+        self.graph.replay()
+        o._after_step(self.tables, any_first)

@@ -374,6 +374,13 @@ typedef struct b200ssl_opt_group {
 B200SSL_API int b200ssl_opt_ema_multi_tensor(const b200ssl_opt_block* blocks, int32_t n_blocks, const b200ssl_opt_group* groups,
                                  int32_t n_groups, float decay, float one_minus_decay, void* stream);
 
+/* The same launch with the group rows in DEVICE memory (groups_dev: b200ssl_opt_group[n_groups], 16-byte aligned): the
+ * launch has no step-dependent parameter any more, so a CUDA graph can replay it; the host refreshes the rows (learning rate,
+ * bias corrections) with one small copy ahead of every replay (fused_step.FusedOptimizerEMA.capture). */
+B200SSL_API int b200ssl_opt_ema_multi_tensor_dev(const b200ssl_opt_block* blocks, int32_t n_blocks,
+                                     const b200ssl_opt_group* groups_dev, int32_t n_groups, float decay,
+                                     float one_minus_decay, void* stream);
+
 /* ------------------------------------------------------------ SURVEY 8e ----
  * Row exchanges of the rank-sharded memory bank over NVLink peer memory.  The
  * reference has no distributed code (one bank per process, code/comatch.py:90-96);

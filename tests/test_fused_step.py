@@ -179,6 +179,57 @@ def test_fused_optimizer_ema_matches_torch_optim_then_ema(kind, use_ema):
     opt_n.step()
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind", ["sgd", "adam", "adamw"])
+def test_captured_fused_step_replays_bit_exact(kind):
+    """SURVEY 8 f1 inside a CUDA graph: ``FusedOptimizerEMA.capture()`` keeps the group scalars in device memory, so the
+    replayed launch follows the LR schedule and Adam's bias corrections; 6 replays == 6 eager fused steps, bit for bit
+    (weights, optimizer state, EMA, step counters)."""
+    from endoscopy_image_classification_b200.ema import ModelEMA
+    from endoscopy_image_classification_b200.fused_step import FusedOptimizerEMA
+    from endoscopy_image_classification_b200.optimizer import set_weight_decay
+    dev = torch.device("cuda:0")
+    torch.manual_seed(2)
+    a = _Net().to(dev)
+    b = copy.deepcopy(a)
+    gen = torch.Generator(device=dev).manual_seed(9)
+    for pa, pb in zip(a.parameters(), b.parameters()):
+        pa.grad = torch.randn(pa.shape, device=dev, generator=gen)
+        pb.grad = pa.grad.clone()
+    opt_a, opt_b = _make_opt(kind, set_weight_decay(a), lr=2e-3), _make_opt(kind, set_weight_decay(b), lr=2e-3)
+    ema_a, ema_b = ModelEMA(a, 0.99, device=dev), ModelEMA(b, 0.99, device=dev)
+    eager, graphed = FusedOptimizerEMA(opt_a, ema_a, a), FusedOptimizerEMA(opt_b, ema_b, b)
+    eager.step()                                   # first step eagerly on both sides (SGD: the momentum buffer is born here)
+    graphed.step()
+    cap = graphed.capture()
+    before = [p.detach().clone() for p in b.parameters()]
+    for p, q in zip(b.parameters(), before):       # capturing records, it does not step
+        assert torch.equal(p, q)
+    for step in range(6):
+        for o in (opt_a, opt_b):
+            for grp in o.param_groups:
+                grp["lr"] = 2e-3 * (1.0 - 0.1 * step)
+        for pa, pb in zip(a.parameters(), b.parameters()):
+            pa.grad.copy_(torch.randn(pa.shape, device=dev, generator=gen))
+            pb.grad.copy_(pa.grad)
+        eager.step()
+        cap.replay()
+    torch.cuda.synchronize()
+    for (n, x), (_, y) in zip(a.state_dict().items(), b.state_dict().items()):
+        assert torch.equal(x, y), n
+    for (n, x), (_, y) in zip(ema_a.ema.state_dict().items(), ema_b.ema.state_dict().items()):
+        assert torch.equal(x, y), n
+    sa, sb = opt_a.state_dict()["state"], opt_b.state_dict()["state"]
+    for k in sa:
+        for name in sa[k]:
+            assert torch.equal(torch.as_tensor(sa[k][name]).cpu(), torch.as_tensor(sb[k][name]).cpu()), (k, name)
+    for p in b.parameters():                       # a gradient that moves invalidates the captured tables
+        p.grad = p.grad.clone()
+        break
+    with pytest.raises(RuntimeError):
+        cap.replay()
+
+
 class _StubLib:
     """Records the C-ABI calls of the fused step so its host logic can run on CPU tensors (no GPU here)."""
 
