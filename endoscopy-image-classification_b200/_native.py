@@ -59,6 +59,7 @@ SIGNATURES = {
     "b200ssl_scale_rows": (_i32, [_vp, _vp, _i64, _i32, _i32, _vp, _vp]),
     "b200ssl_bad_label_count": (_i32, [_vp, _vp, _i32]),
     "b200ssl_eval_head": (_i32, [_vp, _vp, _i64, _i32, _i32, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "b200ssl_normalize_views": (_i32, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp, C.POINTER(C.c_float), C.POINTER(C.c_float), _i32, _vp]),
     "b200ssl_comatch_da": (_i32, [_vp, _i64, _i32, _i32, _vp, _vp, _i32, _vp, _vp, _vp, _sz, _vp]),
     "b200ssl_bank_smooth_partial": (_i32, [_vp, _vp, _vp, _vp, _i64, _i64, _i32, _i32, _i32, _f32, _vp, _vp, _i32, _i32,
                                            _vp, _vp, _sz, _vp]),

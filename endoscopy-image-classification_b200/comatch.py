@@ -84,7 +84,7 @@ class CoMatch(SemiSupervisedTrainer):
         (inputs_u_w, inputs_u_s_0, inputs_u_s_1), _ = self._unlabeled.next()
         inputs_x, targets_x = self._labeled.next()
         bt, btu = inputs_x.size(0), inputs_u_w.size(0)
-        imgs = torch.cat([inputs_x, inputs_u_w, inputs_u_s_0, inputs_u_s_1], dim=0).to(self.device, non_blocking=True)
+        imgs = self.to_device_views(inputs_x, inputs_u_w, inputs_u_s_0, inputs_u_s_1)
         targets_x = targets_x.to(self.device, non_blocking=True)
         with self._autocast():
             logits, _, features = self.net(imgs)

@@ -84,7 +84,8 @@ namespace cg = cooperative_groups;
 constexpr int kBM = 128;          // queries per row tile (UMMA M)
 constexpr int kBN = 128;          // keys per tile    (UMMA N of GEMM1 / K of GEMM2)
 constexpr int kCP = 32;           // classes + the "ones" column, padded (UMMA N of GEMM2)
-constexpr int kStages = 4;        // key tiles in flight (at the reference's sizes every load of a CTA is in flight at once; remote shards: NVLink latency)
+constexpr int kMaxStages = 5;      // key tiles in flight: 5 while they fit (mt <= 2), else 4.  GEMM1 runs two units ahead of the exponentials, so
+                                  // three tiles can be in use while the next ones load (remote shards: NVLink latency)
 constexpr int kMaxMT = 4;         // row tiles one CTA can serve from ONE staged key tile ("row loop"): a remote key tile
                                   // then crosses NVLink once per step instead of once per row tile
 constexpr int kEpiWarps = 16;     // 4 per TMEM lane quarter: each thread owns 32 of the 128 key columns of its row
@@ -98,11 +99,12 @@ constexpr uint32_t kSubQp = kCP * 128;                  //  4 KB: [32][64] bf16
 constexpr uint32_t kTileQp = 2 * kSubQp;                //  8 KB
 constexpr uint32_t kSubP = kBM * 128;                   // 16 KB: [128][64] bf16
 constexpr uint32_t kTileP = 2 * kSubP;                  // 32 KB
-constexpr uint32_t kSmemStages = kStages * (kTileQf + kTileQp) + 2 * kTileP;   // 160 KB (P is double buffered)
+constexpr int stages_for(int mt) { return mt <= 2 ? kMaxStages : 4; }
+constexpr uint32_t smem_stages(int mt) { return stages_for(mt) * (kTileQf + kTileQp) + 2 * kTileP; }   // 184 / 160 KB (P is double buffered)
 constexpr uint32_t kTmemCols = 512;                     // S[0] 0..127, S[1] 128..255, [numer | rowsum] of row tile m at 256 + 32 m
 constexpr int kRedLd = 36;                              // floats per row of a reduction tile (16-byte rows, 4-way bank spread)
 constexpr uint32_t kRedTile = kBM * kRedLd * 4;         // 18 KB per row tile, staged over the drained pipeline buffers
-constexpr size_t smem_request(int mt) { return 1024 + (size_t)mt * kTileA + kSmemStages + 512; }   // mt = 1: 177.5 KB > half an SM; mt = 4: 225.5 KB
+constexpr size_t smem_request(int mt) { return 1024 + (size_t)mt * kTileA + smem_stages(mt) + 512; }   // mt = 1: 201.5 KB, 2: 217.5 KB, 4: 225.5 KB
 
 struct BankMaps {                 // one pair of tensor maps per shard; remote shards are peer-mapped NVLink addresses
   CUtensorMap qf[kMaxSeg];
@@ -125,7 +127,7 @@ struct SmoothTcParams {
   unsigned long long* dbg;
 };
 
-enum { BAR_A = 0, BAR_KV_FULL = 1, BAR_KV_EMPTY = BAR_KV_FULL + kStages, BAR_S_FULL = BAR_KV_EMPTY + kStages,
+enum { BAR_A = 0, BAR_KV_FULL = 1, BAR_KV_EMPTY = BAR_KV_FULL + kMaxStages, BAR_S_FULL = BAR_KV_EMPTY + kMaxStages,
        BAR_S_EMPTY = BAR_S_FULL + 2, BAR_P_FULL = BAR_S_EMPTY + 2, BAR_P_EMPTY = BAR_P_FULL + 2,
        BAR_ACC = BAR_P_EMPTY + 2, BAR_COUNT };
 
@@ -161,6 +163,7 @@ bank_smooth_tc_kernel(const __grid_constant__ CUtensorMap tm_f, const __grid_con
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* sA = smem;                                       // [mt][128][64] bf16 query tiles
+  const int kStages = stages_for(p.mt);
   uint8_t* sQf = sA + (size_t)p.mt * kTileA;
   uint8_t* sQp = sQf + kStages * kTileQf;
   uint8_t* sP = sQp + kStages * kTileQp;
@@ -287,9 +290,12 @@ bank_smooth_tc_kernel(const __grid_constant__ CUtensorMap tm_f, const __grid_con
         if (m == M - 1) tc::mma_commit(&bars[BAR_KV_EMPTY + s]);   // the key tile has served every row tile
         tc::mma_commit(&bars[BAR_P_EMPTY + pb]);
       };
+      // The epilogue reads S of unit j+1 out of TMEM at the START of unit j (software pipeline), so GEMM1 runs two units
+      // ahead: S of unit j+2 goes into the buffer unit j has just been read from.
       gemm1(0);
+      if (J > 1) gemm1(1);
       for (int j = 0; j < J; ++j) {
-        if (j + 1 < J) gemm1(j + 1);                       // S is double buffered: GEMM1 of unit j+1 overlaps the exp of unit j
+        if (j + 2 < J) gemm1(j + 2);
         gemm2(j);
       }
       tc::mma_commit(&bars[BAR_ACC]);
@@ -601,8 +607,8 @@ int bank_smooth_tc(const void* feats, const void* queue_feats, const void* queue
     if (int e = tc::make_tmap_bf16_2d(&maps.qf[s], qf, (uint64_t)seg_rows, 64, 128, kBN, 64)) return e;
     if (int e = tc::make_tmap_bf16_2d(&maps.qpt[s], qpt, kCP, (uint64_t)seg_rows, (uint64_t)seg_rows * 2, kCP, 64)) return e;
   }
-  static_assert(smem_request(kMaxMT) <= 227 * 1024, "shared memory budget");
-  static_assert((size_t)kMaxMT * kRedTile <= kSmemStages, "the reduction tiles must fit in the drained pipeline buffers");
+  static_assert(smem_request(kMaxMT) <= 227 * 1024 && smem_request(2) <= 227 * 1024 && smem_request(1) <= 227 * 1024, "shared memory budget");
+  static_assert((size_t)kMaxMT * kRedTile <= smem_stages(kMaxMT), "the reduction tiles must fit in the drained pipeline buffers");
   static_assert(2 * kBN + kMaxMT * kCP <= (int)kTmemCols, "TMEM budget");
   // Share of the exponentials computed on the FMA pipe (of 32 per thread and S tile).  Measured on B200 (tools/k3_tune.py,
   // profiles/r02_k3_tune.jsonl): every polynomial slot ADDS ~25 clocks per S tile at every size -- the epilogue is bound by

@@ -45,7 +45,7 @@ class SemiFormer(SemiSupervisedTrainer):
         (inputs_u_w, inputs_u_s), _ = self._unlabeled.next()
         bs_lb = inputs_x.shape[0]
         targets_x = targets_x.to(self.device, non_blocking=True)
-        inputs = torch.cat((inputs_x, inputs_u_w, inputs_u_s)).to(self.device, non_blocking=True)
+        inputs = self.to_device_views(inputs_x, inputs_u_w, inputs_u_s)
         with self._autocast():
             out_conv, out_trans = self.net(inputs)
         outputs_u_w, outputs_u_s_conv = out_conv[bs_lb:].chunk(2)

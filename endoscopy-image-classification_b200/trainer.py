@@ -176,6 +176,16 @@ class SemiSupervisedTrainer:
         self._labeled = BatchSource(self.train_labeled_dl) if hasattr(self, "train_labeled_dl") else None
         self._unlabeled = BatchSource(self.train_unlabeled_dl) if hasattr(self, "train_unlabeled_dl") else None
 
+    def to_device_views(self, *batches):
+        """Concatenate image batches on the device.  fp32 NCHW tensors (the reference's loaders, ``dataset.py:51-53``) are
+        simply moved; uint8 ``[N, H, W, 3]`` batches -- loaders that stop before ``ToTensor`` -- are moved at one byte per
+        sample and finished there by ``views.normalize_views`` (``ToTensor`` + ``Normalize`` in one launch, bit-exact)."""
+        if all(b.dtype == torch.uint8 and b.dim() == 4 and b.shape[-1] == 3 for b in batches):
+            from .views import normalize_views
+            x = torch.cat([b.to(self.device, non_blocking=True) for b in batches], dim=0)
+            return normalize_views(x)
+        return torch.cat(batches, dim=0).to(self.device, non_blocking=True)
+
     def _after_backward(self, epoch, step_index, losses, summary_loss):
         """optimizer step, per-iteration LR schedule, EMA, bookkeeping (``fixmatch.py:120-131``)."""
         if self._fused is not None:

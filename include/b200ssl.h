@@ -429,6 +429,19 @@ B200SSL_API int b200ssl_peer_reduce_scatter_f32(const float* src, float* out, in
 
 /* Launch geometry of the tensor-core K3 (host only): out[0] = row tiles per CTA, out[1] = cluster size, out[2] = clusters
  * per group of row tiles.  remote_shards != 0: the plan of a directly addressed rank-sharded bank. */
+/* ------------------------------------------------------- f4 (next), data side --
+ * The pixel-exact tail of the reference's view transforms (code/dataset.py:24-109) on uint8 HWC images:
+ * RandomHorizontalFlip -> RandomCrop(out_size, padding, padding_mode='reflect') -> ToTensor -> Normalize(mean, std), i.e.
+ *   out[n, c, y, x] = ((u8 / 255) - mean[c]) / std[c]      (fp32, every operation rounded like ToTensor / Normalize do)
+ * of the source pixel that the flip and the crop window select.  images_hwc: [n, height, width, 3] uint8 (device);
+ * out_nchw: [n, 3, out_size, out_size] fp32 or bf16 (out_dtype), 16-byte aligned; flip: int32 [n] or NULL; crop_xy:
+ * int32 [n, 2] = (left, top) of the window inside the reflect-padded image, or NULL for the centred window; mean3 /
+ * std3: HOST arrays of 3 floats.  The random decisions stay with the caller (views.draw_view_params draws them in the
+ * order the reference's Compose does). */
+B200SSL_API int b200ssl_normalize_views(const uint8_t* images_hwc, void* out_nchw, int32_t n, int32_t height, int32_t width,
+                            int32_t out_size, int32_t padding, const int32_t* flip, const int32_t* crop_xy,
+                            const float* mean3, const float* std3, int32_t out_dtype, void* stream);
+
 /* Tuning aid: force the row tiles per CTA, the cluster size and the clusters per group of row tiles (0 = planner) and the
  * number of exponentials out of 32 that the tensor-core K3 computes with the FMA-pipe polynomial (-1 = default). */
 B200SSL_API void b200ssl_debug_set_k3(int32_t row_tiles_per_cta, int32_t cluster, int32_t clusters_per_row_group, int32_t poly_of_32);
