@@ -10,13 +10,15 @@
 // Warp roles (576 threads): warp 0 = TMEM allocator + TMA producer, warp 1 = MMA
 // issuer (one thread), warps 2..17 = epilogue (4 threads per TMEM lane = query row,
 // 32 key columns each).  S (TMEM) and P (smem) are double-buffered so GEMM1 of unit
-// j+1 and GEMM2 of unit j-1 overlap the exp of unit j, and the epilogue is software
-// pipelined: the tcgen05.ld of unit j+1 is issued before the exponentials of unit j, so
-// the S_FULL wait and the TMEM read latency hide behind the MUFU work (ncu, round 2:
-// one third of the epilogue's samples sat on the barriers / ld with the MUFU unit idle).
-// Two epilogue groups taking alternate tiles (64 columns per thread) were tried and were
-// 25 % slower (profiles/r02_k3_tune_pingpong.jsonl).  The bank is split over a cluster of
-// CTAs whose partials are folded through DSMEM in rank order (deterministic).
+// j+1 and GEMM2 of unit j-1 overlap the exp of unit j; the bank is split over a
+// cluster of CTAs whose partials are folded through DSMEM in rank order (deterministic).
+// Measured dead ends of round 2 (profiles/r02_k3_experiments.md): an FMA-pipe polynomial
+// for part of the exponentials, two epilogue groups on alternate tiles, and a software-
+// pipelined tcgen05.ld all ran SLOWER than this plain ld -> exp -> st chain: TMEM reads,
+// MUFU and shared-memory stores share the SM's MIO path, so overlapping them buys nothing.
+// What does help is making fewer MUFU ops: P = exp2(.) is formed as packed fp16 pairs
+// (ex2.approx.f16x2: two exponentials per MUFU op, 11 mantissa bits -- more than the bf16
+// P it replaces) whenever 1/tau is small enough for fp16's range.
 //
 // Bank layout for this path: queue_feats [K, 64] bf16 row-major (a row is exactly one
 // 128-byte swizzle row) and a transposed, class-padded copy of the probabilities
@@ -153,9 +155,11 @@ __device__ __forceinline__ float ex2_poly(float s, float scale, float s_min) {
   return __uint_as_float(__float_as_uint(p) + (__float_as_uint(t) << 23));    // (magic << 23) == 0 (mod 2^32)
 }
 
-// NPOLY of the 32 exponentials a thread makes per S tile go through ex2_poly, spread evenly between the MUFU ones.
+// NPOLY of the 32 exponentials a thread makes per S tile go through ex2_poly, spread evenly between the MUFU ones;
+// NPOLY == kF16x2 selects the packed-fp16 exponentials instead.
+constexpr int kF16x2 = -1;
 template <int NPOLY>
-__device__ __forceinline__ constexpr bool poly_slot(int i) { return ((i + 1) * NPOLY) / 32 != (i * NPOLY) / 32; }
+__device__ __forceinline__ constexpr bool poly_slot(int i) { return NPOLY > 0 && ((i + 1) * NPOLY) / 32 != (i * NPOLY) / 32; }
 
 template <int NPOLY>
 __global__ void __launch_bounds__(kTcThreads, 1)
@@ -259,7 +263,8 @@ bank_smooth_tc_kernel(const __grid_constant__ CUtensorMap tm_f, const __grid_con
     // ================= MMA issuer (one thread) =================
     if (lane == 0) {
       constexpr uint32_t idesc1 = tc::idesc_bf16_f32(kBM, kBN);
-      constexpr uint32_t idesc2 = tc::idesc_bf16_f32(kBM, kCP);
+      // GEMM2: A = P (bf16, or fp16 when the exponentials are made as f16x2 pairs), B = QpT (bf16)
+      constexpr uint32_t idesc2 = NPOLY == kF16x2 ? (tc::idesc_bf16_f32(kBM, kCP) & ~(7u << 7)) : tc::idesc_bf16_f32(kBM, kCP);
       tc::mbar_wait(&bars[BAR_A], 0, abort_flag);
       B200SSL_STAMP(p.dbg, cta, 2);                         // query tiles landed (TMA)
       // unit j = (key tile t, row tile m), m fastest: S[j & 1] = F_m Qf_t^T   (K = 64 -> 4 x UMMA_K 16)
@@ -290,12 +295,9 @@ bank_smooth_tc_kernel(const __grid_constant__ CUtensorMap tm_f, const __grid_con
         if (m == M - 1) tc::mma_commit(&bars[BAR_KV_EMPTY + s]);   // the key tile has served every row tile
         tc::mma_commit(&bars[BAR_P_EMPTY + pb]);
       };
-      // The epilogue reads S of unit j+1 out of TMEM at the START of unit j (software pipeline), so GEMM1 runs two units
-      // ahead: S of unit j+2 goes into the buffer unit j has just been read from.
       gemm1(0);
-      if (J > 1) gemm1(1);
       for (int j = 0; j < J; ++j) {
-        if (j + 2 < J) gemm1(j + 2);
+        if (j + 1 < J) gemm1(j + 1);                       // S is double buffered: GEMM1 of unit j+1 overlaps the exp of unit j
         gemm2(j);
       }
       tc::mma_commit(&bars[BAR_ACC]);
@@ -306,46 +308,43 @@ bank_smooth_tc_kernel(const __grid_constant__ CUtensorMap tm_f, const __grid_con
     const int half = colq >> 1, c2 = colq & 1;              // P sub-tile (64 keys) and 32-column group inside it
     const int r_in = quarter * 32 + lane;
     const uint32_t lane_addr = tmem + ((uint32_t)(quarter * 32) << 16);
-    uint32_t r[32], rn[32];                                 // S of the current / the next unit
-    tc::mbar_wait(&bars[BAR_S_FULL + 0], 0, abort_flag);
-    if (threadIdx.x == 64) B200SSL_STAMP(p.dbg, cta, 3);    // first S tile ready (TMA + GEMM1)
-    tc::tcgen05_fence_after();
-    tc::tmem_ld_32x32(lane_addr + colq * 32, r);
-    tc::tmem_ld_wait();
-    tc::tcgen05_fence_before();
-    tc::mbar_arrive(&bars[BAR_S_EMPTY + 0]);                // S[0] is in registers: GEMM1 of unit 2 may overwrite it
+    uint32_t scale2 = 0;                                    // (scale, scale) as packed fp16
+    if (NPOLY == kF16x2) asm("cvt.rn.f16x2.f32 %0, %1, %1;" : "=r"(scale2) : "f"(p.scale));
     for (int j = 0; j < J; ++j) {
       const int b = j & 1;
-      const bool more = j + 1 < J;
-      if (more) {
-        // software pipeline: the TMEM read of unit j+1 (ready long ago: its GEMM1 was issued a unit earlier) flies
-        // while this unit's exponentials keep the MUFU unit busy
-        tc::mbar_wait(&bars[BAR_S_FULL + (b ^ 1)], ((j + 1) >> 1) & 1, abort_flag);
-        tc::tcgen05_fence_after();
-        tc::tmem_ld_32x32(lane_addr + (b ^ 1) * kBN + colq * 32, rn);
-      }
-      // keys beyond the bank need no mask: their QpT columns (incl. the ones column) are TMA zero fill
-      uint32_t w[16];
-#pragma unroll
-      for (int e = 0; e < 16; ++e) {
-        const float s0 = __uint_as_float(r[2 * e]), s1 = __uint_as_float(r[2 * e + 1]);               // comatch.py:180
-        const float e0 = poly_slot<NPOLY>(2 * e) ? ex2_poly(s0, p.scale, p.s_min) : ex2_approx(s0 * p.scale);
-        const float e1 = poly_slot<NPOLY>(2 * e + 1) ? ex2_poly(s1, p.scale, p.s_min) : ex2_approx(s1 * p.scale);
-        const __nv_bfloat162 h = __floats2bfloat162_rn(e0, e1);
-        w[e] = *reinterpret_cast<const uint32_t*>(&h);
-      }
-      // the P buffer of unit j-2 must have been consumed -- only now, after the exponentials
-      if (j >= 2) tc::mbar_wait(&bars[BAR_P_EMPTY + b], ((j >> 1) - 1) & 1, abort_flag);
-#pragma unroll
-      for (int q = 0; q < 4; ++q)
-        *reinterpret_cast<uint4*>(sP + b * kTileP + half * kSubP + tc::sw128_offset(r_in, c2 * 4 + q)) =
-            make_uint4(w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
-      if (more) {
-        tc::tmem_ld_wait(rn);
+      tc::mbar_wait(&bars[BAR_S_FULL + b], (j >> 1) & 1, abort_flag);
+      if (j == 0 && threadIdx.x == 64) B200SSL_STAMP(p.dbg, cta, 3);   // first S tile ready (TMA + GEMM1)
+      tc::tcgen05_fence_after();
+      {
+        uint32_t r[32];
+        tc::tmem_ld_32x32(lane_addr + b * kBN + colq * 32, r);
+        tc::tmem_ld_wait();
         tc::tcgen05_fence_before();
-        tc::mbar_arrive(&bars[BAR_S_EMPTY + (b ^ 1)]);      // S of unit j+1 is in registers
+        tc::mbar_arrive(&bars[BAR_S_EMPTY + b]);            // S[b] is in registers: GEMM1 of unit j+2 may overwrite it
+        // keys beyond the bank need no mask: their QpT columns (incl. the ones column) are TMA zero fill
+        uint32_t w[16];
 #pragma unroll
-        for (int i = 0; i < 32; ++i) r[i] = rn[i];
+        for (int e = 0; e < 16; ++e) {
+          const float s0 = __uint_as_float(r[2 * e]), s1 = __uint_as_float(r[2 * e + 1]);               // comatch.py:180
+          if (NPOLY == kF16x2) {
+            // two exponentials per MUFU op: S pair -> fp16 pair, scaled, exp2'd as a pair; P stays fp16
+            uint32_t h, x;
+            asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(h) : "f"(s1), "f"(s0));
+            asm("mul.rn.f16x2 %0, %1, %2;" : "=r"(x) : "r"(h), "r"(scale2));
+            asm("ex2.approx.f16x2 %0, %1;" : "=r"(w[e]) : "r"(x));
+          } else {
+            const float e0 = poly_slot<NPOLY>(2 * e) ? ex2_poly(s0, p.scale, p.s_min) : ex2_approx(s0 * p.scale);
+            const float e1 = poly_slot<NPOLY>(2 * e + 1) ? ex2_poly(s1, p.scale, p.s_min) : ex2_approx(s1 * p.scale);
+            const __nv_bfloat162 hh = __floats2bfloat162_rn(e0, e1);
+            w[e] = *reinterpret_cast<const uint32_t*>(&hh);
+          }
+        }
+        // the P buffer of unit j-2 must have been consumed -- only now, after the exponentials
+        if (j >= 2) tc::mbar_wait(&bars[BAR_P_EMPTY + b], ((j >> 1) - 1) & 1, abort_flag);
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          *reinterpret_cast<uint4*>(sP + b * kTileP + half * kSubP + tc::sw128_offset(r_in, c2 * 4 + q)) =
+              make_uint4(w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
       }
       tc::fence_proxy_async_smem();               // generic-proxy writes of P -> visible to the tensor core
       tc::mbar_arrive(&bars[BAR_P_FULL + b]);
@@ -610,14 +609,16 @@ int bank_smooth_tc(const void* feats, const void* queue_feats, const void* queue
   static_assert(smem_request(kMaxMT) <= 227 * 1024 && smem_request(2) <= 227 * 1024 && smem_request(1) <= 227 * 1024, "shared memory budget");
   static_assert((size_t)kMaxMT * kRedTile <= smem_stages(kMaxMT), "the reduction tiles must fit in the drained pipeline buffers");
   static_assert(2 * kBN + kMaxMT * kCP <= (int)kTmemCols, "TMEM budget");
-  // Share of the exponentials computed on the FMA pipe (of 32 per thread and S tile).  Measured on B200 (tools/k3_tune.py,
-  // profiles/r02_k3_tune.jsonl): every polynomial slot ADDS ~25 clocks per S tile at every size -- the epilogue is bound by
-  // its serial ld -> exp -> st -> fence chain per tile, not by the MUFU rate -- so the default is 0; the knob stays for A/B.
-  const int npoly = g_force_poly >= 0 ? g_force_poly : 0;
+  // How the exponentials are made.  Default: packed fp16 pairs (two per MUFU op) while exp(|s|/tau) <= exp(1.05/tau) fits
+  // fp16 (tau >= 0.1; the reference's temperature is 0.2, comatch.py:35), else one fp32 MUFU op each.  The FMA-pipe
+  // polynomial (b200ssl_debug_set_k3(.., poly 8..20)) stays as an A/B aid: every polynomial slot ADDS ~25 clocks per S tile.
+  const bool f16_ok = temperature >= 0.1f;
+  const int npoly = g_force_poly >= 0 ? g_force_poly : (g_force_poly == -2 || !f16_ok ? 0 : kF16x2);
   const dim3 grid((unsigned)groups, (unsigned)p.nsplit, 1);
   const size_t smem = smem_request(p.mt);
   cudaError_t e;
-  if (npoly >= 20) e = launch_smooth<20>(p, tm_f, maps, grid, smem, stream);
+  if (npoly == kF16x2) e = launch_smooth<kF16x2>(p, tm_f, maps, grid, smem, stream);
+  else if (npoly >= 20) e = launch_smooth<20>(p, tm_f, maps, grid, smem, stream);
   else if (npoly >= 16) e = launch_smooth<16>(p, tm_f, maps, grid, smem, stream);
   else if (npoly >= 12) e = launch_smooth<12>(p, tm_f, maps, grid, smem, stream);
   else if (npoly >= 8) e = launch_smooth<8>(p, tm_f, maps, grid, smem, stream);

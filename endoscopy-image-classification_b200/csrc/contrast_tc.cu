@@ -594,11 +594,16 @@ contrast_tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_f0, const __grid_c
   if (threadIdx.x == 0) B200SSL_STAMP(p.dbg, ctaid, 6);     // fold done
 }
 
-int ct_cluster(long long rows) {
+// Cluster size of a launch with `tiles * slices` clusters: the widest cluster (shortest per-CTA tile loop) whose clusters
+// are all resident at once.  A cluster lives inside one GPC, so a B200 runs only 15 clusters of 8 one-CTA-per-SM blocks at a
+// time (33 of 4, 74 of 2 -- b200ssl_debug_max_active_clusters); a launch that needs several waves of clusters pays the
+// prologue and the folds once per wave (28 strips x 8 at rows 3584 were two forward and four backward waves in round 1).
+int ct_cluster(long long rows, int slices) {
   const long long tiles = (rows + kT - 1) / kT;
-  int cl = 1;
-  while (cl * 2 <= kMaxCl && cl * 2 <= tiles) cl *= 2;
-  return cl;
+  static const int cap[4][2] = {{8, 15}, {4, 33}, {2, 74}, {1, 148}};
+  for (const auto& c : cap)
+    if (c[0] <= tiles && tiles * slices <= c[1]) return c[0];
+  return 1;
 }
 
 }  // namespace
@@ -637,7 +642,7 @@ int contrast_fwd_tc(const void* f0, const void* f1, const void* probs_hl, long l
   p.rows = rows; p.C = classes; p.scale = (float)(1.4426950408889634 / (double)temperature);
   p.inv_tau = 1.0f / temperature; p.th = contrast_th; p.stats = stats; p.out = out_scalar;
   p.loss_u = loss_u; p.lambda_u = lambda_u; p.lambda_c = lambda_c; p.total_out = total_out;
-  p.cluster = ct_cluster(rows); p.dbg = debug_timing_buffer(PDL_CONTRAST_FWD);
+  p.cluster = ct_cluster(rows, 1); p.dbg = debug_timing_buffer(PDL_CONTRAST_FWD);
   const size_t need = kWsHeaderBytes + sizeof(float) * contrast_tc_workspace_floats(rows);
   if (workspace_bytes < need) return fail(B200SSL_E_WORKSPACE, "%s: workspace %zu < %zu bytes", fn, workspace_bytes, need);
   p.grid_ticket = reinterpret_cast<unsigned*>(workspace) + 4;
@@ -662,7 +667,7 @@ int contrast_bwd_tc(const void* f0, const void* f1, const void* probs_hl, const 
   p.rows = rows; p.C = classes; p.scale = (float)(1.4426950408889634 / (double)temperature);
   p.inv_tau = 1.0f / temperature; p.th = contrast_th; p.stats = const_cast<float*>(stats);
   p.upstream = upstream; p.factor = factor; p.g0 = g0; p.g1 = g1;
-  p.cluster = ct_cluster(rows); p.dbg = debug_timing_buffer(PDL_CONTRAST_BWD);
+  p.cluster = ct_cluster(rows, scale_grad ? 3 : 2); p.dbg = debug_timing_buffer(PDL_CONTRAST_BWD);
   p.sgrad = static_cast<__nv_bfloat16*>(scale_grad); p.snumel = scale_numel; p.sup = scale_up; p.sfactor = scale_factor;
   CUtensorMap m[3];
   if (int e = ct_maps(m, f0, f1, probs_hl, rows)) return e;
