@@ -16,9 +16,8 @@
 // for part of the exponentials, two epilogue groups on alternate tiles, and a software-
 // pipelined tcgen05.ld all ran SLOWER than this plain ld -> exp -> st chain: TMEM reads,
 // MUFU and shared-memory stores share the SM's MIO path, so overlapping them buys nothing.
-// What does help is making fewer MUFU ops: P = exp2(.) is formed as packed fp16 pairs
-// (ex2.approx.f16x2: two exponentials per MUFU op, 11 mantissa bits -- more than the bf16
-// P it replaces) whenever 1/tau is small enough for fp16's range.
+// Packed fp16 exponentials (ex2.approx.f16x2) do not help either: they compile to two MUFU.EX2.F16 per pair, and
+// tcgen05.mma kind::f16 takes no fp16 A next to a bf16 B (illegal instruction), so P would drag the bank copy to fp16.
 //
 // Bank layout for this path: queue_feats [K, 64] bf16 row-major (a row is exactly one
 // 128-byte swizzle row) and a transposed, class-padded copy of the probabilities
@@ -155,9 +154,7 @@ __device__ __forceinline__ float ex2_poly(float s, float scale, float s_min) {
   return __uint_as_float(__float_as_uint(p) + (__float_as_uint(t) << 23));    // (magic << 23) == 0 (mod 2^32)
 }
 
-// NPOLY of the 32 exponentials a thread makes per S tile go through ex2_poly, spread evenly between the MUFU ones;
-// NPOLY == kF16x2 selects the packed-fp16 exponentials instead.
-constexpr int kF16x2 = -1;
+// NPOLY of the 32 exponentials a thread makes per S tile go through ex2_poly, spread evenly between the MUFU ones.
 template <int NPOLY>
 __device__ __forceinline__ constexpr bool poly_slot(int i) { return NPOLY > 0 && ((i + 1) * NPOLY) / 32 != (i * NPOLY) / 32; }
 
@@ -263,8 +260,7 @@ bank_smooth_tc_kernel(const __grid_constant__ CUtensorMap tm_f, const __grid_con
     // ================= MMA issuer (one thread) =================
     if (lane == 0) {
       constexpr uint32_t idesc1 = tc::idesc_bf16_f32(kBM, kBN);
-      // GEMM2: A = P (bf16, or fp16 when the exponentials are made as f16x2 pairs), B = QpT (bf16)
-      constexpr uint32_t idesc2 = NPOLY == kF16x2 ? (tc::idesc_bf16_f32(kBM, kCP) & ~(7u << 7)) : tc::idesc_bf16_f32(kBM, kCP);
+      constexpr uint32_t idesc2 = tc::idesc_bf16_f32(kBM, kCP);
       tc::mbar_wait(&bars[BAR_A], 0, abort_flag);
       B200SSL_STAMP(p.dbg, cta, 2);                         // query tiles landed (TMA)
       // unit j = (key tile t, row tile m), m fastest: S[j & 1] = F_m Qf_t^T   (K = 64 -> 4 x UMMA_K 16)
@@ -308,8 +304,6 @@ bank_smooth_tc_kernel(const __grid_constant__ CUtensorMap tm_f, const __grid_con
     const int half = colq >> 1, c2 = colq & 1;              // P sub-tile (64 keys) and 32-column group inside it
     const int r_in = quarter * 32 + lane;
     const uint32_t lane_addr = tmem + ((uint32_t)(quarter * 32) << 16);
-    uint32_t scale2 = 0;                                    // (scale, scale) as packed fp16
-    if (NPOLY == kF16x2) asm("cvt.rn.f16x2.f32 %0, %1, %1;" : "=r"(scale2) : "f"(p.scale));
     for (int j = 0; j < J; ++j) {
       const int b = j & 1;
       tc::mbar_wait(&bars[BAR_S_FULL + b], (j >> 1) & 1, abort_flag);
@@ -326,18 +320,10 @@ bank_smooth_tc_kernel(const __grid_constant__ CUtensorMap tm_f, const __grid_con
 #pragma unroll
         for (int e = 0; e < 16; ++e) {
           const float s0 = __uint_as_float(r[2 * e]), s1 = __uint_as_float(r[2 * e + 1]);               // comatch.py:180
-          if (NPOLY == kF16x2) {
-            // two exponentials per MUFU op: S pair -> fp16 pair, scaled, exp2'd as a pair; P stays fp16
-            uint32_t h, x;
-            asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(h) : "f"(s1), "f"(s0));
-            asm("mul.rn.f16x2 %0, %1, %2;" : "=r"(x) : "r"(h), "r"(scale2));
-            asm("ex2.approx.f16x2 %0, %1;" : "=r"(w[e]) : "r"(x));
-          } else {
-            const float e0 = poly_slot<NPOLY>(2 * e) ? ex2_poly(s0, p.scale, p.s_min) : ex2_approx(s0 * p.scale);
-            const float e1 = poly_slot<NPOLY>(2 * e + 1) ? ex2_poly(s1, p.scale, p.s_min) : ex2_approx(s1 * p.scale);
-            const __nv_bfloat162 hh = __floats2bfloat162_rn(e0, e1);
-            w[e] = *reinterpret_cast<const uint32_t*>(&hh);
-          }
+          const float e0 = poly_slot<NPOLY>(2 * e) ? ex2_poly(s0, p.scale, p.s_min) : ex2_approx(s0 * p.scale);
+          const float e1 = poly_slot<NPOLY>(2 * e + 1) ? ex2_poly(s1, p.scale, p.s_min) : ex2_approx(s1 * p.scale);
+          const __nv_bfloat162 hh = __floats2bfloat162_rn(e0, e1);
+          w[e] = *reinterpret_cast<const uint32_t*>(&hh);
         }
         // the P buffer of unit j-2 must have been consumed -- only now, after the exponentials
         if (j >= 2) tc::mbar_wait(&bars[BAR_P_EMPTY + b], ((j >> 1) - 1) & 1, abort_flag);
@@ -609,16 +595,14 @@ int bank_smooth_tc(const void* feats, const void* queue_feats, const void* queue
   static_assert(smem_request(kMaxMT) <= 227 * 1024 && smem_request(2) <= 227 * 1024 && smem_request(1) <= 227 * 1024, "shared memory budget");
   static_assert((size_t)kMaxMT * kRedTile <= smem_stages(kMaxMT), "the reduction tiles must fit in the drained pipeline buffers");
   static_assert(2 * kBN + kMaxMT * kCP <= (int)kTmemCols, "TMEM budget");
-  // How the exponentials are made.  Default: packed fp16 pairs (two per MUFU op) while exp(|s|/tau) <= exp(1.05/tau) fits
-  // fp16 (tau >= 0.1; the reference's temperature is 0.2, comatch.py:35), else one fp32 MUFU op each.  The FMA-pipe
-  // polynomial (b200ssl_debug_set_k3(.., poly 8..20)) stays as an A/B aid: every polynomial slot ADDS ~25 clocks per S tile.
-  const bool f16_ok = temperature >= 0.1f;
-  const int npoly = g_force_poly >= 0 ? g_force_poly : (g_force_poly == -2 || !f16_ok ? 0 : kF16x2);
+  // Share of the exponentials computed on the FMA pipe (of 32 per thread and S tile).  Measured on B200 (tools/k3_tune.py,
+  // profiles/r02_k3_experiments.md): every polynomial slot ADDS ~25 clocks per S tile at every size -- the epilogue is bound by
+  // its serial ld -> exp -> st -> fence chain per tile, not by the MUFU rate -- so the default is 0; the knob stays for A/B.
+  const int npoly = g_force_poly >= 0 ? g_force_poly : 0;
   const dim3 grid((unsigned)groups, (unsigned)p.nsplit, 1);
   const size_t smem = smem_request(p.mt);
   cudaError_t e;
-  if (npoly == kF16x2) e = launch_smooth<kF16x2>(p, tm_f, maps, grid, smem, stream);
-  else if (npoly >= 20) e = launch_smooth<20>(p, tm_f, maps, grid, smem, stream);
+  if (npoly >= 20) e = launch_smooth<20>(p, tm_f, maps, grid, smem, stream);
   else if (npoly >= 16) e = launch_smooth<16>(p, tm_f, maps, grid, smem, stream);
   else if (npoly >= 12) e = launch_smooth<12>(p, tm_f, maps, grid, smem, stream);
   else if (npoly >= 8) e = launch_smooth<8>(p, tm_f, maps, grid, smem, stream);

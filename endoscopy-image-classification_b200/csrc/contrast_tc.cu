@@ -505,28 +505,37 @@ contrast_tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_f0, const __grid_c
         tc::tmem_ld_32x32(lane_addr + kT + col0, qv);
         tc::tmem_ld_wait();
         uint32_t packed[16], packed_lo[16];
-        float dz_even = 0.f;
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          float q = __uint_as_float(qv[j]);
-          bool ok = true;
-          if (!interior) {
-            const int gj = j0 + col0 + j;
-            ok = (gi < rows_i) && (gj < rows_i);
-            q = (gi == gj) ? 1.f : q;
-          }
-          // dZ = P (G - r),  G = -(qm / qsum) / (P + 1e-7) / rows   (branch-free: qm = 0 off the graph)
+        // dZ = P (G - r),  G = -(qm / qsum) / (P + 1e-7) / rows   (branch-free: qm = 0 off the graph).  Interior tiles (all
+        // but the diagonal and the ragged edge) skip every per-element bound / diagonal test: two instantiations of the
+        // loop instead of a uniform branch and three selects per element (ncu, round 1: 35 instructions per element).
+        auto dz_of = [&](float s, float q) {
           const float qm = (q >= p.th) ? q : 0.f;
-          const float P = ex2a(__uint_as_float(sv[j]) * p.scale) * inv_rs;
-          float dz = P * (qm * qscale * rcpa(P + 1e-7f) - r_i);
-          dz = ok ? dz : 0.f;
-          if (j & 1) {
-            const __nv_bfloat162 h = __floats2bfloat162_rn(dz_even, dz);
-            const __nv_bfloat162 l = __floats2bfloat162_rn(dz_even - __low2float(h), dz - __high2float(h));
-            packed[j >> 1] = *reinterpret_cast<const uint32_t*>(&h);
-            packed_lo[j >> 1] = *reinterpret_cast<const uint32_t*>(&l);
-          } else {
-            dz_even = dz;
+          const float P = ex2a(s * p.scale) * inv_rs;
+          return P * (qm * qscale * rcpa(P + 1e-7f) - r_i);
+        };
+        auto pack_pair = [&](int k, float d0, float d1) {
+          const __nv_bfloat162 h = __floats2bfloat162_rn(d0, d1);
+          const __nv_bfloat162 l = __floats2bfloat162_rn(d0 - __low2float(h), d1 - __high2float(h));
+          packed[k] = *reinterpret_cast<const uint32_t*>(&h);
+          packed_lo[k] = *reinterpret_cast<const uint32_t*>(&l);
+        };
+        if (interior) {
+#pragma unroll
+          for (int k = 0; k < 16; ++k)
+            pack_pair(k, dz_of(__uint_as_float(sv[2 * k]), __uint_as_float(qv[2 * k])),
+                      dz_of(__uint_as_float(sv[2 * k + 1]), __uint_as_float(qv[2 * k + 1])));
+        } else {
+#pragma unroll
+          for (int k = 0; k < 16; ++k) {
+            float d[2];
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+              const int j = 2 * k + u, gj = j0 + col0 + j;
+              const bool ok = (gi < rows_i) && (gj < rows_i);
+              const float q = (gi == gj) ? 1.f : __uint_as_float(qv[j]);       // fill_diagonal_(1)
+              d[u] = ok ? dz_of(__uint_as_float(sv[j]), q) : 0.f;
+            }
+            pack_pair(k, d[0], d[1]);
           }
         }
 #pragma unroll
