@@ -56,6 +56,7 @@ struct ContrastTcParams {
   const float* loss_u; float lambda_u, lambda_c; float* total_out;
   const float* upstream; float factor; void* g0; void* g1;
   unsigned long long* dbg;
+  int dense_b;            // forward pass B: dense math instead of the compaction list (A/B knob)
   // optional piggy-backed task of the backward launch: sgrad[i] *= (*sup) * sfactor  (the stashed focal-CE gradient)
   __nv_bfloat16* sgrad; long long snumel; const float* sup; float sfactor;
 };
@@ -213,6 +214,25 @@ contrast_tc_fwd_kernel(const __grid_constant__ CUtensorMap tm_f0, const __grid_c
             a0 += ok ? ex2a(__uint_as_float(sv[j]) * p.scale) : 0.f;
             a1 += (ok && q >= p.th) ? q : 0.f;
           }
+        }
+      } else if (p.dense_b) {
+        // pass B without the compaction: every element pays the exp / log / rcp (3 MUFU ops) but there is no serial
+        // list-building chain and no divergent loop over the positives
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          float q = __uint_as_float(qv[j]);
+          bool pos;
+          if (interior) {
+            pos = q >= p.th;
+          } else {
+            const int gj = j0 + col0 + j;
+            q = (gi_i == gj) ? 1.f : q;
+            pos = (gi_i < rows_i) && (gj < rows_i) && (q >= p.th);
+          }
+          const float P = ex2a(__uint_as_float(sv[j]) * p.scale) * inv_rs;              // :201
+          const float qn = pos ? q * inv_qs : 0.f;                                      // :209
+          a0 -= lg2a(P + 1e-7f) * 0.6931471805599453f * qn;                             // :212
+          a1 += qn * P * rcpa(P + 1e-7f);
         }
       } else {
         int cnt = 0;
@@ -607,6 +627,8 @@ contrast_tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_f0, const __grid_c
 // are all resident at once.  A cluster lives inside one GPC, so a B200 runs only 15 clusters of 8 one-CTA-per-SM blocks at a
 // time (33 of 4, 74 of 2 -- b200ssl_debug_max_active_clusters); a launch that needs several waves of clusters pays the
 // prologue and the folds once per wave (28 strips x 8 at rows 3584 were two forward and four backward waves in round 1).
+int g_contrast_dense_b = getenv("B200SSL_K6_DENSE_B") ? atoi(getenv("B200SSL_K6_DENSE_B")) : 0;
+
 int ct_cluster(long long rows, int slices) {
   const long long tiles = (rows + kT - 1) / kT;
   static const int cap[4][2] = {{8, 15}, {4, 33}, {2, 74}, {1, 148}};
@@ -652,6 +674,7 @@ int contrast_fwd_tc(const void* f0, const void* f1, const void* probs_hl, long l
   p.inv_tau = 1.0f / temperature; p.th = contrast_th; p.stats = stats; p.out = out_scalar;
   p.loss_u = loss_u; p.lambda_u = lambda_u; p.lambda_c = lambda_c; p.total_out = total_out;
   p.cluster = ct_cluster(rows, 1); p.dbg = debug_timing_buffer(PDL_CONTRAST_FWD);
+  p.dense_b = g_contrast_dense_b;
   const size_t need = kWsHeaderBytes + sizeof(float) * contrast_tc_workspace_floats(rows);
   if (workspace_bytes < need) return fail(B200SSL_E_WORKSPACE, "%s: workspace %zu < %zu bytes", fn, workspace_bytes, need);
   p.grid_ticket = reinterpret_cast<unsigned*>(workspace) + 4;
