@@ -100,12 +100,14 @@ constexpr uint32_t kSubQp = kCP * 128;                  //  4 KB: [32][64] bf16
 constexpr uint32_t kTileQp = 2 * kSubQp;                //  8 KB
 constexpr uint32_t kSubP = kBM * 128;                   // 16 KB: [128][64] bf16
 constexpr uint32_t kTileP = 2 * kSubP;                  // 32 KB
-constexpr int stages_for(int mt) { return mt <= 2 ? kMaxStages : 4; }
-constexpr uint32_t smem_stages(int mt) { return stages_for(mt) * (kTileQf + kTileQp) + 2 * kTileP; }   // 184 / 160 KB (P is double buffered)
+constexpr int stages_for(int mt) { return mt <= 2 ? kMaxStages : 4; }   // the most that fit next to mt query tiles
+constexpr uint32_t smem_stages_n(int stages) { return stages * (kTileQf + kTileQp) + 2 * kTileP; }   // P is double buffered
+constexpr uint32_t smem_stages(int mt) { return smem_stages_n(stages_for(mt)); }                      // 184 / 160 KB
 constexpr uint32_t kTmemCols = 512;                     // S[0] 0..127, S[1] 128..255, [numer | rowsum] of row tile m at 256 + 32 m
 constexpr int kRedLd = 36;                              // floats per row of a reduction tile (16-byte rows, 4-way bank spread)
 constexpr uint32_t kRedTile = kBM * kRedLd * 4;         // 18 KB per row tile, staged over the drained pipeline buffers
 constexpr size_t smem_request(int mt) { return 1024 + (size_t)mt * kTileA + smem_stages(mt) + 512; }   // mt = 1: 201.5 KB, 2: 217.5 KB, 4: 225.5 KB
+constexpr size_t smem_request_n(int mt, int stages) { return 1024 + (size_t)mt * kTileA + smem_stages_n(stages) + 512; }
 
 struct BankMaps {                 // one pair of tensor maps per shard; remote shards are peer-mapped NVLink addresses
   CUtensorMap qf[kMaxSeg];
@@ -116,6 +118,7 @@ struct SmoothTcParams {
   long long rows, rows_pad;
   int row_tiles;                  // ceil(rows / 128)
   int mt;                         // row tiles per CTA
+  int stages;                     // key tiles in flight (3..5)
   int nseg, tps;                  // key tiles are enumerated shard by shard: tile kt -> (kt / tps, kt % tps)
   uint8_t* const* arenas;         // non-NULL: directly addressed sharded bank (peer.cuh flags / epochs)
   int rank, world, seg_first;     // seg_first: segment the tile enumeration starts at (the own shard)
@@ -164,7 +167,7 @@ bank_smooth_tc_kernel(const __grid_constant__ CUtensorMap tm_f, const __grid_con
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* sA = smem;                                       // [mt][128][64] bf16 query tiles
-  const int kStages = stages_for(p.mt);
+  const int kStages = p.stages;
   uint8_t* sQf = sA + (size_t)p.mt * kTileA;
   uint8_t* sQp = sQf + kStages * kTileQf;
   uint8_t* sP = sQp + kStages * kTileQp;
@@ -432,8 +435,8 @@ bank_smooth_tc_kernel(const __grid_constant__ CUtensorMap tm_f, const __grid_con
     __threadfence();
     const long long r0 = (long long)(tile0 + m) * kBM + crank * RB;
     const int mrows = (int)max(0LL, min((long long)RB, p.rows - r0));
-    fold_splits_vec4(reinterpret_cast<const float4*>(p.part + (size_t)r0 * W), (size_t)p.rows_pad * W / 4, p.nouter,
-                     mrows * W / 4, [&](int i, float4 v) {
+    fold_splits_wide(reinterpret_cast<const float4*>(p.part + (size_t)r0 * W), (size_t)p.rows_pad * W / 4, p.nouter,
+                     mrows * W / 4, reinterpret_cast<float4*>(sRed), [&](int i, float4 v) {
                        const float vv[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
                        for (int j = 0; j < 4; ++j) {
@@ -456,6 +459,7 @@ struct SmoothPlan { int mt, cluster, nouter; };
 // A/B aids (tools/k3_tune.py): b200ssl_debug_set_k3 at run time (or B200SSL_K3_MT / B200SSL_K3_POLY in the environment).
 int g_force_mt = getenv("B200SSL_K3_MT") ? atoi(getenv("B200SSL_K3_MT")) : 0;          // > 0: row tiles per CTA
 int g_force_cluster = 0, g_force_nouter = 0;                                           // > 0: cluster size / clusters per row group
+int g_force_stages = getenv("B200SSL_K3_STAGES") ? atoi(getenv("B200SSL_K3_STAGES")) : 0;   // 3..5 key-tile stages
 int g_force_poly = getenv("B200SSL_K3_POLY") ? atoi(getenv("B200SSL_K3_POLY")) : -1;   // exponentials (of 32) on the FMA pipe
 
 // Clusters of `cl` CTAs (one CTA per SM: the kernel takes more than half an SM's shared memory) that the chip runs at once.
@@ -493,8 +497,13 @@ double plan_cost(long long row_tiles, long long ktiles, int mt, int cl, long lon
   const long long groups = (row_tiles + mt - 1) / mt;
   const long long waves = (groups * no + max_active_clusters(cl) - 1) / max_active_clusters(cl);
   const long long T = (ktiles + cl * no - 1) / (cl * no);
-  return (double)waves * (1.8 + 0.62 * (double)mt * (double)T) + 1.5 + (cl > 1 ? 2.5 : 0.5) + (no > 1 ? 3.0 + 0.25 * (double)no / cl : 0.0) +
-         0.4 * (mt - 1);                                   // extra query tiles to stage and to fold
+  // outer fold: the last CTA of a (row tile, cluster rank) slice adds `no` partials of 128 / cl rows, 8 loads in flight per
+  // thread group (576 / (6 * 128 / cl) groups), one slice after the other for the mt row tiles it may be last for
+  const int count4 = 6 * kBM / cl;
+  const long long groups_t = kTcThreads / count4 > 1 ? kTcThreads / count4 : 1;
+  const long long rounds = ((no + groups_t - 1) / groups_t + 7) / 8;
+  const double fold = no > 1 ? 3.0 + 0.9 * (double)rounds * mt * (count4 > kTcThreads ? 2.0 : 1.0) : 0.0;
+  return (double)waves * (1.8 + 0.62 * (double)mt * (double)T) + 1.5 + (cl > 1 ? 2.5 : 0.5) + fold + 0.4 * (mt - 1);   // + extra query tiles to stage
 }
 
 // How a launch is cut: `mt` row tiles per CTA, and per group of row tiles a cluster of `cluster` CTAs (power of two <= 8,
@@ -600,7 +609,9 @@ int bank_smooth_tc(const void* feats, const void* queue_feats, const void* queue
   // its serial ld -> exp -> st -> fence chain per tile, not by the MUFU rate -- so the default is 0; the knob stays for A/B.
   const int npoly = g_force_poly >= 0 ? g_force_poly : 0;
   const dim3 grid((unsigned)groups, (unsigned)p.nsplit, 1);
-  const size_t smem = smem_request(p.mt);
+  p.stages = stages_for(p.mt);
+  if (g_force_stages >= 3 && g_force_stages < p.stages) p.stages = g_force_stages;
+  const size_t smem = smem_request_n(p.mt, p.stages);
   cudaError_t e;
   if (npoly >= 20) e = launch_smooth<20>(p, tm_f, maps, grid, smem, stream);
   else if (npoly >= 16) e = launch_smooth<16>(p, tm_f, maps, grid, smem, stream);

@@ -241,6 +241,50 @@ __device__ __forceinline__ void fold_splits_vec4(const float4* __restrict__ part
   }
 }
 
+// The same fold with the splits dealt to thread groups: `count4` float4 items, P = blockDim / count4 groups, group g adds the
+// splits [g * per, (g + 1) * per) in order (8 loads in flight), the partial sums meet in `scratch` ([P][count4] float4 of
+// shared memory) and are added in group order.  A long fold (tens of splits of a short vector) costs ceil(nsplit / (8 P))
+// L2 round trips instead of ceil(nsplit / 8).  Fixed order for a fixed launch geometry: deterministic.  All threads of
+// the CTA must call it.
+template <typename F>
+__device__ __forceinline__ void fold_splits_wide(const float4* __restrict__ part, size_t stride4, int nsplit, int count4, float4* scratch,
+                                                 F f) {
+  const int nt = blockDim.x;
+  if (count4 <= 0) return;
+  int P = nt / count4;
+  if (P > (nsplit + 7) / 8) P = (nsplit + 7) / 8;
+  if (P <= 1) {                                              // short fold or long vector: the plain strided loop
+    fold_splits_vec4(part, stride4, nsplit, count4, f);
+    return;
+  }
+  const int per = (nsplit + P - 1) / P;
+  const int item = threadIdx.x % count4, grp = threadIdx.x / count4;
+  if (grp < P) {
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int s_end = min(nsplit, (grp + 1) * per);
+    for (int s0 = grp * per; s0 < s_end; s0 += 8) {
+      float4 v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+        if (s0 + u < s_end) v[u] = __ldcg(part + (size_t)(s0 + u) * stride4 + item);
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+        if (s0 + u < s_end) { acc.x += v[u].x; acc.y += v[u].y; acc.z += v[u].z; acc.w += v[u].w; }
+    }
+    scratch[grp * count4 + item] = acc;
+  }
+  __syncthreads();
+  if (threadIdx.x < count4) {
+    float4 t = scratch[threadIdx.x];
+    for (int g = 1; g < P; ++g) {
+      const float4 v = scratch[g * count4 + threadIdx.x];
+      t.x += v.x; t.y += v.y; t.z += v.z; t.w += v.w;
+    }
+    f(threadIdx.x, t);
+  }
+  __syncthreads();
+}
+
 // Deterministic grid-wide sum of NV floats per CTA: every CTA stores its
 // partials, takes a ticket; the last CTA to arrive adds all partials in a
 // fixed order and returns true with the totals in `total` (valid in thread 0).

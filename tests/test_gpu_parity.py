@@ -402,8 +402,10 @@ def test_comatch_head_always_mode_vs_oracle(pkg, B, MU, D, qbatches, dtype, fuse
         assert torch.equal(head.queue_feats.float().cpu(), state.queue_feats)
         assert rel_err(head.queue_probs.float(), state.queue_probs) < tol
         assert rel_err(probs, ref["probs"]) < tol
-        assert_labels_match(lbs, ref["lbs"], top2_gap(ref["probs"]), "lbs", tol=1e-6 if dtype == torch.float32 else 2e-2)
-        assert_mask_match(mask, ref["mask"], ref["scores"], thr, tol=1e-6 if dtype == torch.float32 else 2e-2)
+        # bf16 storage: the inputs are rounded identically on both sides; what differs is K3's bf16 P (measured 3e-3 on the
+        # smoothing sums, times 1 - alpha = 0.1) -- a label / mask may flip only where the reference grazes within 4e-3
+        assert_labels_match(lbs, ref["lbs"], top2_gap(ref["probs"]), "lbs", tol=1e-6 if dtype == torch.float32 else 4e-3)
+        assert_mask_match(mask, ref["mask"], ref["scores"], thr, tol=1e-6 if dtype == torch.float32 else 4e-3)
         assert rel_err(loss_c, ref["loss_contrast"]) < tol
         assert rel_err(din["feats_u_s0"].grad.float(), ref["grad_feats_s0"]) < tol
         assert rel_err(din["feats_u_s1"].grad.float(), ref["grad_feats_s1"]) < tol
