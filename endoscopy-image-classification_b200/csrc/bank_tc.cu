@@ -248,15 +248,15 @@ bank_smooth_tc_kernel(const __grid_constant__ CUtensorMap tm_f, const __grid_con
       __syncwarp();
     }
     if (lane == 0) {
-      for (int t = 0; t < T; ++t) {
-        const int s = t % kStages;
-        if (t >= kStages) tc::mbar_wait(&bars[BAR_KV_EMPTY + s], ((t / kStages) - 1) & 1, abort_flag);
+      for (int t = 0, s = 0, lap = 0; t < T; ++t) {
+        if (t >= kStages) tc::mbar_wait(&bars[BAR_KV_EMPTY + s], (lap - 1) & 1, abort_flag);
         int seg;
         const int key0 = tile_of(t, &seg);
         tc::mbar_arrive_expect_tx(&bars[BAR_KV_FULL + s], kTileQf + kTileQp);
         tc::tma_load_2d(sQf + s * kTileQf, &maps.qf[seg], 0, key0, &bars[BAR_KV_FULL + s]);
         tc::tma_load_2d(sQp + s * kTileQp, &maps.qpt[seg], key0, 0, &bars[BAR_KV_FULL + s]);
         tc::tma_load_2d(sQp + s * kTileQp + kSubQp, &maps.qpt[seg], key0 + 64, 0, &bars[BAR_KV_FULL + s]);
+        if (++s == kStages) { s = 0; ++lap; }
       }
     }
   } else if (warp == 1) {
@@ -266,11 +266,12 @@ bank_smooth_tc_kernel(const __grid_constant__ CUtensorMap tm_f, const __grid_con
       constexpr uint32_t idesc2 = tc::idesc_bf16_f32(kBM, kCP);
       tc::mbar_wait(&bars[BAR_A], 0, abort_flag);
       B200SSL_STAMP(p.dbg, cta, 2);                         // query tiles landed (TMA)
-      // unit j = (key tile t, row tile m), m fastest: S[j & 1] = F_m Qf_t^T   (K = 64 -> 4 x UMMA_K 16)
-      auto gemm1 = [&](int j) {
-        const int t = j / M, m = j - t * M;
-        const int s = t % kStages, b = j & 1;
-        if (m == 0) tc::mbar_wait(&bars[BAR_KV_FULL + s], (t / kStages) & 1, abort_flag);
+      // unit j = (key tile t, row tile m), m fastest: S[j & 1] = F_m Qf_t^T   (K = 64 -> 4 x UMMA_K 16).
+      // This thread sits on the critical path of every unit (P_FULL -> GEMM2 -> P_EMPTY, S_EMPTY -> GEMM1 -> S_FULL): (t, m)
+      // and the stage index are carried as counters -- a runtime division per GEMM cost 17 % at rows 3584 x K 65536.
+      auto gemm1 = [&](int j, int m, int s, int lap) {
+        const int b = j & 1;
+        if (m == 0) tc::mbar_wait(&bars[BAR_KV_FULL + s], lap, abort_flag);
         if (j >= 2) tc::mbar_wait(&bars[BAR_S_EMPTY + b], ((j >> 1) - 1) & 1, abort_flag);   // S of unit j-2 is in registers
         tc::tcgen05_fence_after();
         const uint64_t a_desc = tc::smem_desc_sw128(tc::smem_u32(sA + (size_t)m * kTileA));
@@ -279,9 +280,8 @@ bank_smooth_tc_kernel(const __grid_constant__ CUtensorMap tm_f, const __grid_con
         for (int k = 0; k < 4; ++k) tc::mma_bf16_ss(tmem + b * kBN, a_desc + 2 * k, b_desc + 2 * k, idesc1, k > 0);
         tc::mma_commit(&bars[BAR_S_FULL + b]);
       };
-      auto gemm2 = [&](int j) {   // [numer | rowsum]_m += P [QpT | 1]^T   (K = 128 keys -> 2 sub-tiles x 4 x UMMA_K 16)
-        const int t = j / M, m = j - t * M;
-        const int s = t % kStages, pb = j & 1;
+      auto gemm2 = [&](int j, int t, int m, int s) {   // [numer | rowsum]_m += P [QpT | 1]^T   (K = 128 keys -> 2 sub-tiles x 4 x UMMA_K 16)
+        const int pb = j & 1;
         tc::mbar_wait(&bars[BAR_P_FULL + pb], (j >> 1) & 1, abort_flag);
         tc::tcgen05_fence_after();
 #pragma unroll
@@ -294,10 +294,18 @@ bank_smooth_tc_kernel(const __grid_constant__ CUtensorMap tm_f, const __grid_con
         if (m == M - 1) tc::mma_commit(&bars[BAR_KV_EMPTY + s]);   // the key tile has served every row tile
         tc::mma_commit(&bars[BAR_P_EMPTY + pb]);
       };
-      gemm1(0);
+      int m1 = 0, s1 = 0, ph1 = 0;                           // (row tile, stage, stage-ring lap) of the next GEMM1
+      auto next1 = [&]() { if (++m1 == M) { m1 = 0; if (++s1 == kStages) { s1 = 0; ph1 ^= 1; } } };
+      int t2 = 0, m2 = 0, s2 = 0;                            // ... of the next GEMM2
+      gemm1(0, m1, s1, ph1);
+      next1();
       for (int j = 0; j < J; ++j) {
-        if (j + 1 < J) gemm1(j + 1);                       // S is double buffered: GEMM1 of unit j+1 overlaps the exp of unit j
-        gemm2(j);
+        if (j + 1 < J) {                                     // S is double buffered: GEMM1 of unit j+1 overlaps the exp of unit j
+          gemm1(j + 1, m1, s1, ph1);
+          next1();
+        }
+        gemm2(j, t2, m2, s2);
+        if (++m2 == M) { m2 = 0; ++t2; if (++s2 == kStages) s2 = 0; }
       }
       tc::mma_commit(&bars[BAR_ACC]);
     }
@@ -421,35 +429,82 @@ bank_smooth_tc_kernel(const __grid_constant__ CUtensorMap tm_f, const __grid_con
   }
   if (p.nouter == 1) return;
 
-  // ---- then across clusters: the slice (row tile, cluster rank) = RB rows is folded, in cluster order, by whichever of
-  // the `nouter` CTAs that wrote it arrives last -- the outer folds of a launch run on M * CL CTAs in parallel ----
-  __shared__ int s_last[kMaxMT];
+  // ---- then across clusters: the slice "rows [crank*RB, +RB) of every row tile of this group" is folded, in cluster order,
+  // by whichever of the `nouter` CTAs that wrote it arrives last -- the outer folds of a launch run on CL CTAs per row group
+  // in parallel, each ONE pass over all its row tiles (items = M * RB * W / 4 float4, dealt to thread groups that each add a
+  // contiguous range of the partials with 8 loads in flight; the group sums meet in shared memory in group order) ----
+  __shared__ int s_last;
   __threadfence();
   __syncthreads();
-  if (threadIdx.x < M)
-    s_last[threadIdx.x] = atomicAdd(&p.tickets[(tile0 + threadIdx.x) * kMaxCluster + crank], 1u) == (unsigned)p.nouter - 1;
+  if (threadIdx.x == 0) s_last = atomicAdd(&p.tickets[row_group * kMaxCluster + crank], 1u) == (unsigned)p.nouter - 1;
   __syncthreads();
-  if (threadIdx.x == 0) B200SSL_STAMP(p.dbg, cta, 8);      // tickets taken
-  for (int m = 0; m < M; ++m) {
-    if (!s_last[m]) continue;
-    __threadfence();
-    const long long r0 = (long long)(tile0 + m) * kBM + crank * RB;
-    const int mrows = (int)max(0LL, min((long long)RB, p.rows - r0));
-    fold_splits_wide(reinterpret_cast<const float4*>(p.part + (size_t)r0 * W), (size_t)p.rows_pad * W / 4, p.nouter,
-                     mrows * W / 4, reinterpret_cast<float4*>(sRed), [&](int i, float4 v) {
-                       const float vv[4] = {v.x, v.y, v.z, v.w};
+  if (threadIdx.x == 0) B200SSL_STAMP(p.dbg, cta, 8);      // ticket taken
+  if (!s_last) return;
+  __threadfence();
+  {
+    const int per_tile = RB * W4, items = M * per_tile;
+    float4* scratch = reinterpret_cast<float4*>(sRed);     // the cluster is past its last DSMEM read
+    const int nt = blockDim.x;
+    int P = items <= nt ? nt / items : 1;                  // thread groups (items > nt: one group strides over the items)
+    if (P > (p.nouter + 7) / 8) P = (p.nouter + 7) / 8;
+    const int per = (p.nouter + P - 1) / P;
+    const size_t stride = (size_t)p.rows_pad * W;          // floats between two partials
+    auto src_of = [&](int item, long long* grow) -> const float* {
+      const int m = item / per_tile, rem = item - m * per_tile;
+      const int rr = rem / W4, q4 = rem - rr * W4;
+      *grow = (long long)(tile0 + m) * kBM + crank * RB + rr;
+      return p.part + (size_t)(*grow) * W + 4 * q4;
+    };
+    auto emit = [&](int item, long long grow, const float4& v) {
+      if (grow >= p.rows) return;
+      const int q4 = item % W4;
+      const float vv[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-                       for (int j = 0; j < 4; ++j) {
-                         const int e = 4 * i + j, row = e / W, col = e - row * W;
-                         if (col < C) p.numer[(r0 + row) * p.numer_ld + col] = vv[j];
-                         else if (col == C) p.rowsum[(r0 + row) * p.rowsum_ld] = vv[j];
-                       }
-                     });
+      for (int j = 0; j < 4; ++j) {
+        const int col = 4 * q4 + j;
+        if (col < C) p.numer[grow * p.numer_ld + col] = vv[j];
+        else if (col == C) p.rowsum[grow * p.rowsum_ld] = vv[j];
+      }
+    };
+    auto range_sum = [&](const float* src, int s_begin, int s_end) {
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int s0 = s_begin; s0 < s_end; s0 += 8) {
+        float4 v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+          if (s0 + u < s_end) v[u] = __ldcg(reinterpret_cast<const float4*>(src + (size_t)(s0 + u) * stride));
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+          if (s0 + u < s_end) { acc.x += v[u].x; acc.y += v[u].y; acc.z += v[u].z; acc.w += v[u].w; }
+      }
+      return acc;
+    };
+    if (P <= 1) {
+      for (int item = threadIdx.x; item < items; item += nt) {
+        long long grow;
+        const float* src = src_of(item, &grow);
+        emit(item, grow, range_sum(src, 0, p.nouter));
+      }
+    } else {
+      const int item = threadIdx.x % items, grp = threadIdx.x / items;
+      long long grow;
+      const float* src = src_of(item, &grow);
+      if (grp < P) scratch[grp * items + item] = range_sum(src, grp * per, min(p.nouter, (grp + 1) * per));
+      __syncthreads();
+      if ((int)threadIdx.x < items) {
+        float4 t = scratch[threadIdx.x];
+        for (int g = 1; g < P; ++g) {
+          const float4 v = scratch[g * items + threadIdx.x];
+          t.x += v.x; t.y += v.y; t.z += v.z; t.w += v.w;
+        }
+        emit(item, grow, t);
+      }
+    }
   }
   __syncthreads();
-  if (threadIdx.x < M && s_last[threadIdx.x]) p.tickets[(tile0 + threadIdx.x) * kMaxCluster + crank] = 0u;
   if (threadIdx.x == 0) {
-    B200SSL_STAMP(p.dbg, cta, 9);                          // outer folds done
+    p.tickets[row_group * kMaxCluster + crank] = 0u;
+    B200SSL_STAMP(p.dbg, cta, 9);                          // outer fold done
     B200SSL_STAMP_NS(p.dbg, cta, 12);
   }
 }
@@ -497,12 +552,12 @@ double plan_cost(long long row_tiles, long long ktiles, int mt, int cl, long lon
   const long long groups = (row_tiles + mt - 1) / mt;
   const long long waves = (groups * no + max_active_clusters(cl) - 1) / max_active_clusters(cl);
   const long long T = (ktiles + cl * no - 1) / (cl * no);
-  // outer fold: the last CTA of a (row tile, cluster rank) slice adds `no` partials of 128 / cl rows, 8 loads in flight per
-  // thread group (576 / (6 * 128 / cl) groups), one slice after the other for the mt row tiles it may be last for
-  const int count4 = 6 * kBM / cl;
-  const long long groups_t = kTcThreads / count4 > 1 ? kTcThreads / count4 : 1;
+  // outer fold: the last CTA of a (row group, cluster rank) slice adds `no` partials of mt * 128 / cl rows in one pass, 8 loads
+  // in flight per thread group (576 / items groups)
+  const int items = mt * 6 * kBM / cl;
+  const long long groups_t = kTcThreads / items > 1 ? kTcThreads / items : 1;
   const long long rounds = ((no + groups_t - 1) / groups_t + 7) / 8;
-  const double fold = no > 1 ? 3.0 + 0.9 * (double)rounds * mt * (count4 > kTcThreads ? 2.0 : 1.0) : 0.0;
+  const double fold = no > 1 ? 3.0 + 0.9 * (double)rounds * (items > kTcThreads ? (double)((items + kTcThreads - 1) / kTcThreads) : 1.0) : 0.0;
   return (double)waves * (1.8 + 0.62 * (double)mt * (double)T) + 1.5 + (cl > 1 ? 2.5 : 0.5) + fold + 0.4 * (mt - 1);   // + extra query tiles to stage
 }
 
@@ -588,7 +643,7 @@ int bank_smooth_tc(const void* feats, const void* queue_feats, const void* queue
   p.rows_pad = groups * p.mt * kBM;
   const size_t need = kWsHeaderBytes + sizeof(float) * (p.nouter > 1 ? (size_t)p.nouter * p.rows_pad * p.W : 0);
   if (workspace_bytes < need) return fail(B200SSL_E_WORKSPACE, "%s: workspace %zu < %zu bytes", fn, workspace_bytes, need);
-  if ((size_t)groups * p.mt * kMaxCluster * 4 > kWsTicket2Bytes) return fail(B200SSL_E_SHAPE, "%s: too many row tiles", fn);
+  if ((size_t)groups * kMaxCluster * 4 > kWsTicket2Bytes) return fail(B200SSL_E_SHAPE, "%s: too many row tiles", fn);
   p.tickets = reinterpret_cast<unsigned*>(static_cast<char*>(workspace) + kWsTicketBytes);
   p.part = reinterpret_cast<float*>(static_cast<char*>(workspace) + kWsHeaderBytes);
   CUtensorMap tm_f;

@@ -26,7 +26,7 @@ if world > 1:
     dist.init_process_group("nccl", device_id=dev)
     pg = dist.group.WORLD
 exchange = sys.argv[1] if len(sys.argv) > 1 else "auto"
-B, MU, C, D, K = 64, 7, 23, 64, 2560 * world
+B, MU, C, D, K = 64, 7, 23, 64, int(os.environ.get("K_GLOBAL", 2560 * world))      # K_GLOBAL=65536: BASELINE cfg 4
 keys = ["logits_u_w", "logits_u_s0", "feats_u_w", "feats_u_s0", "feats_u_s1", "feats_x", "targets_x"]
 g = torch.Generator().manual_seed(1 + rank)
 protos = S.rownorm(torch.randn(C, D, generator=torch.Generator().manual_seed(99)))
@@ -49,12 +49,12 @@ torch.cuda.synchronize()
 if world > 1:
     dist.barrier()
 REGION = 4096 * 16
-buf = torch.zeros(4 * REGION, dtype=torch.int64, device=dev)
+buf = torch.zeros(6 * REGION, dtype=torch.int64, device=dev)
 N.lib().b200ssl_debug_set_timing_buffer(buf.data_ptr())
 step()
 torch.cuda.synchronize()
 N.lib().b200ssl_debug_set_timing_buffer(None)
-t = buf.cpu().numpy().reshape(4, -1, 16)
+t = buf.cpu().numpy().reshape(6, -1, 16)
 if rank == 0:
     # clock64() is per SM: only differences inside one CTA are meaningful
     print(f"exchange={head.exchange} world={world}; us since the CTA's first stamp (min / median / max over CTAs), 1.965 GHz")
@@ -63,9 +63,14 @@ if rank == 0:
         r = r[(r != 0).any(axis=1)]
         if not len(r):
             continue
-        first = np.where(r != 0, r, np.iinfo(np.int64).max).min(axis=1)
+        clk = r[:, :10]                                        # slots 0..9: clock64; 10..12 (smooth): %globaltimer ns
+        first = np.where(clk != 0, clk, np.iinfo(np.int64).max).min(axis=1)
         print(f"  {name} ({len(r)} CTAs)")
-        for slot in range(16):
+        if tag == 0 and (r[:, 10] != 0).any():
+            end = np.maximum(r[:, 11], r[:, 12])
+            print(f"    wall clock: CTA starts spread {(r[:, 10].max() - r[:, 10].min()) / 1e3:.2f} us, first start -> last CTA done "
+                  f"{(end.max() - r[:, 10].min()) / 1e3:.2f} us")
+        for slot in range(10):
             ok = r[:, slot] != 0
             if ok.any():
                 d = (r[ok, slot] - first[ok]) / 1965.0
