@@ -298,7 +298,7 @@ def block_stats(ms_blocks, steps):
 class Case:
     """One workload on this rank: head (+ bank), model / EMA state, synthetic batches, the step, its CUDA graph."""
 
-    def __init__(self, ctx, wl, exchange="auto", dtype_name=None, seed=1234):
+    def __init__(self, ctx, wl, exchange="auto", dtype_name=None, seed=1234, ema_overlap=True):
         from endoscopy_image_classification_b200 import synthetic as S
         from endoscopy_image_classification_b200.comatch_head import CoMatchHead
         from endoscopy_image_classification_b200.ema import ModelEMA
@@ -323,7 +323,10 @@ class Case:
         host, self.keys = make_batches(wl, g, 4, dtype)
         self.host = [{k: v.pin_memory() for k, v in b.items()} for b in host]
         self.resident = [{k: v.to(dev) for k, v in b.items()} for b in self.host]
-        self.ema = ModelEMA(self.model, decay=wl["decay"], device=dev)
+        # ema_overlap: the EMA launch is a parallel branch of the step (side stream forked at the start of the step, joined at
+        # its end) -- in the trainer EMA(t) runs next to the head of step t+1 and is joined ahead of optimizer.step(t+1)
+        self.ema_overlap = bool(ema_overlap)
+        self.ema = ModelEMA(self.model, decay=wl["decay"], device=dev, overlap=self.ema_overlap)
         S.perturb_(self.model, torch.Generator(device=dev).manual_seed(5))        # m != e, like after an optimizer step
         self.grad_keys = {"comatch": ("logits_u_s0", "feats_u_s0", "feats_u_s1"), "fixmatch": ("logits_u_s",),
                           "semiformer": ("logits_u_s", "logits_u_s_trans")}[wl["kind"]]
@@ -337,6 +340,8 @@ class Case:
         head, ema, model, keys = self.head, self.ema, self.model, self.keys
 
         def step(batch):
+            if self.ema_overlap:
+                ema.update(model)                                                 # side stream; joined below
             for k in self.grad_keys:
                 batch[k].grad = None
                 batch[k].requires_grad_(True)
@@ -351,7 +356,10 @@ class Case:
                 lu, _ = consistency_loss(batch["logits_u_w"], batch["logits_u_s"], T=1.0, p_cutoff=wl["thr"])
                 total = wl["lambda_u"] * lu                                        # fixmatch.py:118
             total.backward(gradient=one)                                          # cached ones scalar: no fill kernel per step
-            ema.update(model)
+            if self.ema_overlap:
+                ema.join()
+            else:
+                ema.update(model)
             return total
 
         self.step = step
@@ -363,7 +371,8 @@ class Case:
         head = self.head
         self.graphed = self._GraphedStep(lambda b: self.step(b), self.resident[0], self.ctx.dev, warmup=3,
                                          on_replay=(lambda: head.note_graph_replay(n_rows)) if head is not None else None,
-                                         after_capture=(lambda: head.sync_ptr_from_device()) if head is not None else None)
+                                         after_capture=(lambda: head.sync_ptr_from_device()) if head is not None else None,
+                                         high_priority=self.ema_overlap)
         return self.graphed
 
     def release(self):
@@ -483,7 +492,9 @@ def measure_case(ctx, case, args, blocks, with_e2e=True, with_eager=True):
 def ema_roofline(ctx, case, args):
     """The dominant kernel alone: back-to-back EMA launches (300 MB each > L2) between two CUDA events."""
     n_ema = max(50, min(args.steps, 500))
+    overlap, case.ema.overlap = case.ema.overlap, False          # on the timed (current) stream
     ms = timed_blocks(ctx, lambda i: case.ema.update(case.model), n_ema, 5, 3)
+    case.ema.overlap = overlap
     return statistics.median(ms) / n_ema, n_ema
 
 
@@ -541,7 +552,7 @@ def run_b200(args, wl, rank, world, local_rank):
         parity = multirank_parity(ctx, wl, args.exchange)
 
     # ---------------- the headline workload -------------------------------------------------
-    case = Case(ctx, wl, exchange=args.exchange)
+    case = Case(ctx, wl, exchange=args.exchange, ema_overlap=args.ema_overlap)
     m = measure_case(ctx, case, args, blocks)
     ema_ms, n_ema = ema_roofline(ctx, case, args)
     ema_ms = ctx.max_over_ranks([ema_ms])[0]
@@ -558,7 +569,7 @@ def run_b200(args, wl, rank, world, local_rank):
         wl4 = WORKLOADS["cfg4"]
         ex4 = "auto" if world == 1 else "direct"
         par4 = multirank_parity(ctx, wl4, ex4) if (world > 1 and not args.no_parity) else None
-        c4 = Case(ctx, wl4, exchange=ex4)
+        c4 = Case(ctx, wl4, exchange=ex4, ema_overlap=args.ema_overlap)
         m4 = measure_case(ctx, c4, args, blocks, with_e2e=True, with_eager=False)
         K4, R = wl4["K"], world
         line_extra["cfg4"] = {
@@ -576,7 +587,7 @@ def run_b200(args, wl, rank, world, local_rank):
         del c4
         if world == 1:
             # the reference's own precision: fp32 logits / embeddings / bank (exact-fp32 similarity kernels)
-            c32 = Case(ctx, wl, dtype_name="f32")
+            c32 = Case(ctx, wl, dtype_name="f32", ema_overlap=args.ema_overlap)
             m32 = measure_case(ctx, c32, args, blocks, with_e2e=False, with_eager=False)
             line_extra["fp32"] = {"workload": wl["desc"].replace("bf16", "fp32 storage"), "dtype": "f32",
                                   "value": c32.Bu / (m32["ms_per_step"] * 1e-3), "unit": UNIT, "ms_per_step": m32["ms_per_step"],
@@ -614,7 +625,12 @@ def run_b200(args, wl, rank, world, local_rank):
                            "ema_state": {"entries": plan.n_entries, "unique_storages": plan.n_unique,
                                          "unique_elems": plan.unique_elems, "blocks": plan.n_blocks},
                            "execution": "whole step (head fwd+bwd + EMA) captured once in a CUDA graph and replayed; "
-                                        "eager_ms_per_step is the same API without the graph",
+                                        "eager_ms_per_step is the same API without the graph"
+                                        + ("; the EMA launch is a parallel branch of the step graph (ModelEMA(overlap=True): side stream "
+                                           "forked at the start of the step and joined at its end, the head's stream at high priority) -- "
+                                           "EMA(t) only has to finish before optimizer.step(t+1), so in the trainer it runs next to the "
+                                           "following step's head" if args.ema_overlap else "; EMA after the backward, in series"),
+                           "ema_overlap": bool(args.ema_overlap),
                            "timing": {"method": f"{m['blocks']['blocks']} blocks of [barrier+sync, {args.warmup} untimed replays, event, "
                                                 f"{args.steps} timed replays, event]; per block MAX over ranks; the line reports the MEDIAN block",
                                       **m["blocks"], "e2e": m["e2e_blocks"]},
@@ -650,6 +666,8 @@ def main():
     ap.add_argument("--blocks", type=int, default=0, help="timed blocks (0 = 25 for short runs, 9 for long ones)")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
+    ap.add_argument("--ema-overlap", type=int, default=1, choices=[0, 1],
+                    help="1: the EMA launch runs as a parallel branch of the step (default); 0: after the backward, in series")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the cfg4 / fp32 / fused-optimizer blocks")
     ap.add_argument("--no-parity", action="store_true", help="skip the multi-rank parity check before timing")

@@ -161,7 +161,7 @@ __device__ __forceinline__ float ex2_poly(float s, float scale, float s_min) {
 template <int NPOLY>
 __device__ __forceinline__ constexpr bool poly_slot(int i) { return NPOLY > 0 && ((i + 1) * NPOLY) / 32 != (i * NPOLY) / 32; }
 
-template <int NPOLY>
+template <int NPOLY, int EPI>
 __global__ void __launch_bounds__(kTcThreads, 1)
 bank_smooth_tc_kernel(const __grid_constant__ CUtensorMap tm_f, const __grid_constant__ BankMaps maps, const SmoothTcParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -315,38 +315,63 @@ bank_smooth_tc_kernel(const __grid_constant__ CUtensorMap tm_f, const __grid_con
     const int half = colq >> 1, c2 = colq & 1;              // P sub-tile (64 keys) and 32-column group inside it
     const int r_in = quarter * 32 + lane;
     const uint32_t lane_addr = tmem + ((uint32_t)(quarter * 32) << 16);
+    // shared-window addresses of this thread's four 16-byte P chunks (loop invariant; st.shared, not generic stores)
+    const uint32_t p_base = tc::smem_u32(sP) + half * kSubP;
+    uint32_t p_off[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) p_off[q] = p_base + tc::sw128_offset(r_in, c2 * 4 + q);
+    uint32_t r[32];
+    if (EPI == 1) {                                         // S of unit 0
+      tc::mbar_wait(&bars[BAR_S_FULL], 0, abort_flag);
+      if (threadIdx.x == 64) B200SSL_STAMP(p.dbg, cta, 3);
+      tc::tcgen05_fence_after();
+      tc::tmem_ld_32x32(lane_addr + colq * 32, r);
+      tc::tmem_ld_wait(r);
+      tc::tcgen05_fence_before();
+      tc::mbar_arrive(&bars[BAR_S_EMPTY]);
+    }
     for (int j = 0; j < J; ++j) {
       const int b = j & 1;
-      tc::mbar_wait(&bars[BAR_S_FULL + b], (j >> 1) & 1, abort_flag);
-      if (j == 0 && threadIdx.x == 64) B200SSL_STAMP(p.dbg, cta, 3);   // first S tile ready (TMA + GEMM1)
-      tc::tcgen05_fence_after();
-      {
-        uint32_t r[32];
+      if (EPI == 0) {
+        tc::mbar_wait(&bars[BAR_S_FULL + b], (j >> 1) & 1, abort_flag);
+        if (j == 0 && threadIdx.x == 64) B200SSL_STAMP(p.dbg, cta, 3);   // first S tile ready (TMA + GEMM1)
+        tc::tcgen05_fence_after();
         tc::tmem_ld_32x32(lane_addr + b * kBN + colq * 32, r);
-        tc::tmem_ld_wait();
+        tc::tmem_ld_wait(r);
         tc::tcgen05_fence_before();
         tc::mbar_arrive(&bars[BAR_S_EMPTY + b]);            // S[b] is in registers: GEMM1 of unit j+2 may overwrite it
-        // keys beyond the bank need no mask: their QpT columns (incl. the ones column) are TMA zero fill
-        uint32_t w[16];
-#pragma unroll
-        for (int e = 0; e < 16; ++e) {
-          const float s0 = __uint_as_float(r[2 * e]), s1 = __uint_as_float(r[2 * e + 1]);               // comatch.py:180
-          const float e0 = poly_slot<NPOLY>(2 * e) ? ex2_poly(s0, p.scale, p.s_min) : ex2_approx(s0 * p.scale);
-          const float e1 = poly_slot<NPOLY>(2 * e + 1) ? ex2_poly(s1, p.scale, p.s_min) : ex2_approx(s1 * p.scale);
-          const __nv_bfloat162 hh = __floats2bfloat162_rn(e0, e1);
-          w[e] = *reinterpret_cast<const uint32_t*>(&hh);
-        }
-        // the P buffer of unit j-2 must have been consumed -- only now, after the exponentials
-        if (j >= 2) tc::mbar_wait(&bars[BAR_P_EMPTY + b], ((j >> 1) - 1) & 1, abort_flag);
-#pragma unroll
-        for (int q = 0; q < 4; ++q)
-          *reinterpret_cast<uint4*>(sP + b * kTileP + half * kSubP + tc::sw128_offset(r_in, c2 * 4 + q)) =
-              make_uint4(w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
       }
+      // keys beyond the bank need no mask: their QpT columns (incl. the ones column) are TMA zero fill
+      uint32_t w[16];
+#pragma unroll
+      for (int e = 0; e < 16; ++e) {
+        const float s0 = __uint_as_float(r[2 * e]), s1 = __uint_as_float(r[2 * e + 1]);               // comatch.py:180
+        const float e0 = poly_slot<NPOLY>(2 * e) ? ex2_poly(s0, p.scale, p.s_min) : ex2_approx(s0 * p.scale);
+        const float e1 = poly_slot<NPOLY>(2 * e + 1) ? ex2_poly(s1, p.scale, p.s_min) : ex2_approx(s1 * p.scale);
+        const __nv_bfloat162 hh = __floats2bfloat162_rn(e0, e1);
+        w[e] = *reinterpret_cast<const uint32_t*>(&hh);
+      }
+      const bool more = j + 1 < J;
+      if (EPI == 1 && more) {
+        // the TMEM read of the NEXT unit is issued here, so that its latency hides behind the stores, the proxy fence and
+        // the barrier traffic of this unit (GEMM1 of unit j+1 was issued a whole unit ago)
+        tc::mbar_wait(&bars[BAR_S_FULL + (b ^ 1)], ((j + 1) >> 1) & 1, abort_flag);
+        tc::tcgen05_fence_after();
+        tc::tmem_ld_32x32(lane_addr + (b ^ 1) * kBN + colq * 32, r);
+      }
+      // the P buffer of unit j-2 must have been consumed -- only now, after the exponentials
+      if (j >= 2) tc::mbar_wait(&bars[BAR_P_EMPTY + b], ((j >> 1) - 1) & 1, abort_flag);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) tc::st_shared_v4(p_off[q] + b * kTileP, w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
       tc::fence_proxy_async_smem();               // generic-proxy writes of P -> visible to the tensor core
       tc::mbar_arrive(&bars[BAR_P_FULL + b]);
-      if (j == J - 1 && threadIdx.x == 64) B200SSL_STAMP(p.dbg, cta, 4);   // last exp tile done
+      if (EPI == 1 && more) {
+        tc::tmem_ld_wait(r);
+        tc::tcgen05_fence_before();
+        tc::mbar_arrive(&bars[BAR_S_EMPTY + (b ^ 1)]);      // S of unit j+1 is in registers: GEMM1 of unit j+3 may overwrite it
+      }
     }
+    if (threadIdx.x == 64) B200SSL_STAMP(p.dbg, cta, 4);   // last exp tile done
     tc::mbar_wait(&bars[BAR_ACC], 0, abort_flag);           // all MMAs retired: pipeline smem is free, accumulators final
     if (threadIdx.x == 64) B200SSL_STAMP(p.dbg, cta, 5);
     tc::tcgen05_fence_after();
@@ -515,6 +540,7 @@ struct SmoothPlan { int mt, cluster, nouter; };
 int g_force_mt = getenv("B200SSL_K3_MT") ? atoi(getenv("B200SSL_K3_MT")) : 0;          // > 0: row tiles per CTA
 int g_force_cluster = 0, g_force_nouter = 0;                                           // > 0: cluster size / clusters per row group
 int g_force_stages = getenv("B200SSL_K3_STAGES") ? atoi(getenv("B200SSL_K3_STAGES")) : 0;   // 3..5 key-tile stages
+int g_force_epi = getenv("B200SSL_K3_EPI") ? atoi(getenv("B200SSL_K3_EPI")) : 0;        // epilogue variant (A/B), see the kernel
 int g_force_poly = getenv("B200SSL_K3_POLY") ? atoi(getenv("B200SSL_K3_POLY")) : -1;   // exponentials (of 32) on the FMA pipe
 
 // Clusters of `cl` CTAs (one CTA per SM: the kernel takes more than half an SM's shared memory) that the chip runs at once.
@@ -526,7 +552,7 @@ int max_active_clusters(int cl) {
   int n = cl == 1 ? 148 : cl == 2 ? 74 : cl == 4 ? 33 : 15;     // measured on B200 (b200ssl_debug_max_active_clusters)
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) == cudaSuccess && ndev > 0) {
-    cudaFuncSetAttribute(bank_smooth_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_request(kMaxMT));
+    cudaFuncSetAttribute(bank_smooth_tc_kernel<0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_request(kMaxMT));
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(1, (unsigned)(cl * kNumSMs), 1);
     cfg.blockDim = dim3(kTcThreads, 1, 1);
@@ -536,7 +562,7 @@ int max_active_clusters(int cl) {
     attr[0].val.clusterDim.x = 1; attr[0].val.clusterDim.y = (unsigned)cl; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
     int q = 0;
-    if (cudaOccupancyMaxActiveClusters(&q, bank_smooth_tc_kernel<0>, &cfg) == cudaSuccess && q > 0) n = q;
+    if (cudaOccupancyMaxActiveClusters(&q, bank_smooth_tc_kernel<0, 1>, &cfg) == cudaSuccess && q > 0) n = q;
     else (void)cudaGetLastError();
   } else {
     (void)cudaGetLastError();
@@ -587,15 +613,15 @@ SmoothPlan smooth_tc_plan(long long rows, long long ktiles, bool remote) {
   return best;
 }
 
-template <int NPOLY>
+template <int NPOLY, int EPI>
 cudaError_t launch_smooth(const SmoothTcParams& p, const CUtensorMap& tm_f, const BankMaps& maps, dim3 grid, size_t smem, cudaStream_t stream) {
   static size_t attr_smem = 0;
   if (smem > attr_smem) {
-    cudaError_t e = cudaFuncSetAttribute(bank_smooth_tc_kernel<NPOLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_request(kMaxMT));
+    cudaError_t e = cudaFuncSetAttribute(bank_smooth_tc_kernel<NPOLY, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_request(kMaxMT));
     if (e != cudaSuccess) return e;
     attr_smem = smem_request(kMaxMT);
   }
-  return launch_pdl(PDL_SMOOTH, bank_smooth_tc_kernel<NPOLY>, grid, dim3(kTcThreads, 1, 1), smem, stream, dim3(1, (unsigned)p.cluster, 1), tm_f,
+  return launch_pdl(PDL_SMOOTH, bank_smooth_tc_kernel<NPOLY, EPI>, grid, dim3(kTcThreads, 1, 1), smem, stream, dim3(1, (unsigned)p.cluster, 1), tm_f,
                     maps, p);
 }
 
@@ -668,11 +694,12 @@ int bank_smooth_tc(const void* feats, const void* queue_feats, const void* queue
   if (g_force_stages >= 3 && g_force_stages < p.stages) p.stages = g_force_stages;
   const size_t smem = smem_request_n(p.mt, p.stages);
   cudaError_t e;
-  if (npoly >= 20) e = launch_smooth<20>(p, tm_f, maps, grid, smem, stream);
-  else if (npoly >= 16) e = launch_smooth<16>(p, tm_f, maps, grid, smem, stream);
-  else if (npoly >= 12) e = launch_smooth<12>(p, tm_f, maps, grid, smem, stream);
-  else if (npoly >= 8) e = launch_smooth<8>(p, tm_f, maps, grid, smem, stream);
-  else e = launch_smooth<0>(p, tm_f, maps, grid, smem, stream);
+  if (g_force_epi == 0) e = launch_smooth<0, 0>(p, tm_f, maps, grid, smem, stream);      // A/B: the TMEM read inside the unit it belongs to
+  else if (npoly >= 16) e = launch_smooth<16, 1>(p, tm_f, maps, grid, smem, stream);
+  else if (npoly >= 12) e = launch_smooth<12, 1>(p, tm_f, maps, grid, smem, stream);
+  else if (npoly >= 8) e = launch_smooth<8, 1>(p, tm_f, maps, grid, smem, stream);
+  else if (npoly >= 4) e = launch_smooth<4, 1>(p, tm_f, maps, grid, smem, stream);
+  else e = launch_smooth<0, 1>(p, tm_f, maps, grid, smem, stream);
   if (e != cudaSuccess) return fail((int)e, "%s: cudaLaunchKernelEx: %s", fn, cudaGetErrorString(e));
   return check_launch(fn);
 }
@@ -683,7 +710,8 @@ extern "C" void b200ssl_debug_set_k3(int32_t row_tiles_per_cta, int32_t cluster,
   b200ssl::g_force_mt = row_tiles_per_cta;
   b200ssl::g_force_cluster = cluster;
   b200ssl::g_force_nouter = clusters_per_row_group;
-  b200ssl::g_force_poly = poly_of_32;
+  b200ssl::g_force_epi = poly_of_32 == -2 ? 0 : 1;          // -2: the un-pipelined epilogue (A/B), no polynomial
+  b200ssl::g_force_poly = poly_of_32 == -2 ? 0 : poly_of_32;
 }
 
 extern "C" int b200ssl_debug_max_active_clusters(int32_t cluster) {

@@ -12,6 +12,8 @@
 // the update is __fmul_rn, __fmul_rn, __fadd_rn -- never an FMA.  `repeat`
 // re-applies the update in registers for storages that appear more than once
 // in state_dict() (custom_model.py:194-200).
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace b200ssl {
@@ -144,7 +146,10 @@ extern "C" int b200ssl_ema_multi_tensor(const b200ssl_ema_block* blocks, int32_t
   if (reinterpret_cast<uintptr_t>(blocks) & 15u) return fail(B200SSL_E_ALIGN, "%s: block table must be 16-byte aligned", fn);
   if (n_blocks <= 0) return fail(B200SSL_E_SHAPE, "%s: n_blocks must be > 0", fn);
   if (mode != 0 && mode != 1) return fail(B200SSL_E_ARG, "%s: mode %d (0 update, 1 set)", fn, mode);
-  const int max_grid = kNumSMs * 4;  // 4 resident CTAs of 256 threads per SM
+  // 4 resident CTAs of 256 threads per SM by default.  B200SSL_EMA_GRID (A/B aid) caps or lifts the grid: with the update on
+  // a side stream next to the head kernels (ModelEMA(overlap=True)), a non-persistent grid lets the head's CTAs in as SMs drain.
+  static const int env_grid = getenv("B200SSL_EMA_GRID") ? atoi(getenv("B200SSL_EMA_GRID")) : 0;
+  const int max_grid = env_grid > 0 ? env_grid : kNumSMs * 4;
   const int grid = n_blocks < max_grid ? n_blocks : max_grid;
   cudaStream_t st = as_stream(stream);
   cudaError_t e = cudaSuccess;

@@ -131,7 +131,11 @@ class ModelEMA(object):
     parameters by hand (``load_state_dict`` copies in place and needs nothing).
     """
 
-    def __init__(self, model, decay=0.9999, device=None, revalidate_every: int = 1024):
+    def __init__(self, model, decay=0.9999, device=None, revalidate_every: int = 1024, overlap: bool = False):
+        """``overlap=True``: ``update`` is launched on a side stream forked from the current one, so the 300 MB weight
+        stream runs next to whatever the caller queues afterwards (the next step's forward / SSL head); ``join()`` makes the
+        current stream wait for it and has to be called before the model's weights are written again (the trainer does so
+        ahead of ``optimizer.step()``), before the EMA weights are read, and before the end of a CUDA-graph capture."""
         super(ModelEMA, self).__init__()
         self.ema = deepcopy(model)
         self.ema.eval()
@@ -142,6 +146,9 @@ class ModelEMA(object):
         self._plan: Optional[_EmaPlan] = None
         self._calls = 0
         self._revalidate_every = int(revalidate_every)
+        self.overlap = bool(overlap)
+        self._side: Optional[torch.cuda.Stream] = None
+        self._pending = False
 
     def refresh(self) -> None:
         self._plan = None
@@ -166,10 +173,28 @@ class ModelEMA(object):
 
     def update(self, model):
         """``ema.py:58-59``: e <- decay*e + (1-decay)*m for every state entry."""
-        self._get_plan(model).launch(self.decay, 0)
+        plan = self._get_plan(model)
+        if not self.overlap:
+            plan.launch(self.decay, 0)
+            return
+        dev = plan.device
+        if self._side is None:
+            self._side = torch.cuda.Stream(dev)                 # default (low) priority: the head's stream may be created above it
+        cur = torch.cuda.current_stream(dev)
+        self._side.wait_stream(cur)                               # after everything queued so far (the optimizer step)
+        with torch.cuda.stream(self._side):
+            plan.launch(self.decay, 0)
+        self._pending = True
+
+    def join(self):
+        """Make the current stream wait for an overlapped ``update`` (no-op otherwise)."""
+        if self._pending and self._side is not None:
+            torch.cuda.current_stream(self._side.device).wait_stream(self._side)
+            self._pending = False
 
     def set(self, model):
         """``ema.py:61-62``: e <- m."""
+        self.join()
         self._get_plan(model).launch(self.decay, 1)
 
     # introspection used by bench.py / tests

@@ -27,12 +27,15 @@ __all__ = ["GraphedStep"]
 class GraphedStep:
     def __init__(self, step_fn: Callable[[Dict[str, torch.Tensor]], torch.Tensor], example: Dict[str, torch.Tensor],
                  device, warmup: int = 3, on_replay: Optional[Callable[[], None]] = None,
-                 after_capture: Optional[Callable[[], None]] = None, capture_host_io: bool = True):
+                 after_capture: Optional[Callable[[], None]] = None, capture_host_io: bool = True,
+                 high_priority: bool = False):
         """``step_fn(static_inputs) -> scalar loss tensor`` must do all its work on the current
         stream.  ``example`` gives shapes/dtypes (and the initial contents) of the inputs.
         ``on_replay`` runs after every replay (host mirrors of device state, e.g.
         ``CoMatchHead.note_graph_replay``); ``after_capture`` runs once after the captures, whose
-        host code ran without device work (e.g. ``CoMatchHead.sync_ptr_from_device``)."""
+        host code ran without device work (e.g. ``CoMatchHead.sync_ptr_from_device``).  ``high_priority``: capture on a
+        high-priority stream, so the kernel nodes of ``step_fn``'s own stream outrank work it forks onto default-priority
+        side streams (an overlapped ``ModelEMA.update``: the head's few CTAs are placed as soon as an SM has room)."""
         self.device = torch.device(device)
         self.on_replay = None
         # All inputs live in ONE device buffer (256-byte aligned slices) mirrored by ONE pinned host buffer, so the
@@ -64,7 +67,8 @@ class GraphedStep:
         torch.cuda.current_stream(self.device).wait_stream(side)
         torch.cuda.synchronize(self.device)
         self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
+        cap = {"stream": torch.cuda.Stream(self.device, priority=-1)} if high_priority else {}
+        with torch.cuda.graph(self.graph, **cap):
             self.result = step_fn(self.static).detach().reshape(1).float()
         # gradients the captured backward writes (static buffers of THIS graph)
         self.grads = {k: v.grad for k, v in self.static.items() if v.grad is not None}
@@ -72,7 +76,7 @@ class GraphedStep:
         self.graph_host = None
         if capture_host_io:
             self.graph_host = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(self.graph_host, pool=self.graph.pool()):
+            with torch.cuda.graph(self.graph_host, pool=self.graph.pool(), **cap):
                 with torch.no_grad():
                     self._packed_dev.copy_(self._packed_host, non_blocking=True)      # one H2D node for all inputs
                 res = step_fn(self.static).detach().reshape(1).float()

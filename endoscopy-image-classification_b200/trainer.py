@@ -92,7 +92,10 @@ class SemiSupervisedTrainer:
 
     def _build_ema(self):
         if self.config.TRAIN.USE_EMA:
-            self.ema_model = ModelEMA(model=self.model, decay=self.config.TRAIN.EMA_DECAY, device=self.device)
+            # TRAIN.EMA_OVERLAP: the update runs on a side stream next to the following step's forward / head and is joined
+            # ahead of the next optimizer step (EMA(t) only has to be finished before the weights change again)
+            self.ema_model = ModelEMA(model=self.model, decay=self.config.TRAIN.EMA_DECAY, device=self.device,
+                                      overlap=bool(_cfg(self.config.TRAIN, "EMA_OVERLAP", False)))
 
     def _class_weights(self):
         if not _cfg(self.config.TRAIN, "CLS_WEIGHT", False):
@@ -194,6 +197,8 @@ class SemiSupervisedTrainer:
                 self.lr_scheduler.step_update(step_index)
             self._fused.zero_grad()
         else:
+            if self.config.TRAIN.USE_EMA:
+                self.ema_model.join()                  # an overlapped EMA(t-1) still reads the weights this step rewrites
             self.optimizer.step()
             if self.lr_scheduler is not None:
                 self.lr_scheduler.step_update(step_index)
@@ -246,6 +251,8 @@ class SemiSupervisedTrainer:
         two round trips per batch and recounts the predictions on the host).  Plots are out of scope; ``show_cf_matrix``
         prints the matrix."""
         from .evaluation import EvalAccumulator
+        if self.config.TRAIN.USE_EMA:
+            self.ema_model.join()
         eval_model = self.ema_model.ema if self.config.TRAIN.USE_EMA else self.model
         eval_model.eval()
         acc = EvalAccumulator(self.config.MODEL.NUM_CLASSES, self.device, max_batches=max(len(self.valid_dl), 1),
@@ -284,6 +291,7 @@ class SemiSupervisedTrainer:
             return None
         checkpoint = {}
         if self.config.TRAIN.USE_EMA:
+            self.ema_model.join()
             checkpoint["ema_state_dict"] = self.ema_model.ema.state_dict()
         stamp = date.today().strftime("%m_%d_%Y") + "_" + datetime.now().strftime("%H_%M_%S")
         checkpoint["epoch"] = self.epoch
@@ -314,6 +322,7 @@ class SemiSupervisedTrainer:
             for p in self.model.parameters():
                 p.requires_grad = False
         if self.config.TRAIN.USE_EMA:
+            self.ema_model.join()
             self.ema_model.ema.load_state_dict(checkpoint["ema_state_dict"])     # in place: pointers stay valid
             for p in self.ema_model.ema.parameters():
                 p.requires_grad = bool(is_train)

@@ -498,9 +498,12 @@ def test_enqueue_kernel_matches_segment_plan(pkg):
         assert torch.equal(touched, (qf.cpu() != 0).any(1))
 
 
-def test_graphed_step_matches_eager(pkg):
+@pytest.mark.parametrize("overlap", [False, True])
+def test_graphed_step_matches_eager(pkg, overlap):
     """CUDA-graph replay of head fwd+bwd (+EMA) == the eager calls: same losses, grads, bank,
-    device write pointer and DA history after several steps."""
+    device write pointer and DA history after several steps.  ``overlap``: the EMA update as a parallel branch of the
+    step graph (``ModelEMA(overlap=True)``: side stream forked at the start of the step, joined at its end, the head
+    captured on a high-priority stream) against the serial eager step."""
     from endoscopy_image_classification_b200.graphs import GraphedStep
     g = torch.Generator().manual_seed(21)
     B, MU, D, thr = 8, 7, 64, 0.9
@@ -510,18 +513,23 @@ def test_graphed_step_matches_eager(pkg):
     keys = list(batches[0].keys())
     net = torch.nn.Linear(32, 32).cuda()
 
-    def make():
+    def make(ov=False):
         head = pkg["head"].CoMatchHead(C, D, 3 * n, thr, enqueue_mode="always")
-        ema = pkg["ema"].ModelEMA(net, decay=0.9, device="cuda")
+        ema = pkg["ema"].ModelEMA(net, decay=0.9, device="cuda", overlap=ov)
         return head, ema
 
     def run(head, ema, batch):
+        if ema.overlap:
+            ema.update(net)
         for k in ("logits_u_s0", "feats_u_s0", "feats_u_s1"):
             batch[k].grad = None
             batch[k].requires_grad_(True)
         total, lu, lc, mm = head.total_loss(**batch, lambda_u=2.0, lambda_c=2.0)
         total.backward()
-        ema.update(net)
+        if ema.overlap:
+            ema.join()
+        else:
+            ema.update(net)
         return total
 
     head_e, ema_e = make()
@@ -531,10 +539,11 @@ def test_graphed_step_matches_eager(pkg):
         t = run(head_e, ema_e, db)
         eager.append((float(t), db["feats_u_s0"].grad.clone(), db["logits_u_s0"].grad.clone()))
 
-    head_g, ema_g = make()
+    head_g, ema_g = make(overlap)
     # capture runs 3 warm-up steps + captures on batch 0; rewind the state afterwards
     gs = GraphedStep(lambda sb: run(head_g, ema_g, sb), {k: v.cuda() for k, v in batches[0].items()}, "cuda", warmup=3,
-                     on_replay=lambda: head_g.note_graph_replay(n), after_capture=lambda: head_g.sync_ptr_from_device())
+                     on_replay=lambda: head_g.note_graph_replay(n), after_capture=lambda: head_g.sync_ptr_from_device(),
+                     high_priority=overlap)
     fresh, ema_f = make()
     head_g.load_state_dict(fresh.state_dict())
     head_g.queue_ptr = 0
