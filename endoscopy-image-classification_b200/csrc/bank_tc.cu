@@ -85,7 +85,7 @@ namespace cg = cooperative_groups;
 constexpr int kBM = 128;          // queries per row tile (UMMA M)
 constexpr int kBN = 128;          // keys per tile    (UMMA N of GEMM1 / K of GEMM2)
 constexpr int kCP = 32;           // classes + the "ones" column, padded (UMMA N of GEMM2)
-constexpr int kMaxStages = 5;      // key tiles in flight: 5 while they fit (mt <= 2), else 4.  GEMM1 runs two units ahead of the exponentials, so
+constexpr int kMaxStages = 6;      // key tiles in flight: 6 with P in tensor memory; with P in shared memory 5 while they fit (mt <= 2), else 4
                                   // three tiles can be in use while the next ones load (remote shards: NVLink latency)
 constexpr int kMaxMT = 4;         // row tiles one CTA can serve from ONE staged key tile ("row loop"): a remote key tile
                                   // then crosses NVLink once per step instead of once per row tile
@@ -100,14 +100,16 @@ constexpr uint32_t kSubQp = kCP * 128;                  //  4 KB: [32][64] bf16
 constexpr uint32_t kTileQp = 2 * kSubQp;                //  8 KB
 constexpr uint32_t kSubP = kBM * 128;                   // 16 KB: [128][64] bf16
 constexpr uint32_t kTileP = 2 * kSubP;                  // 32 KB
-constexpr int stages_for(int mt) { return mt <= 2 ? kMaxStages : 4; }   // the most that fit next to mt query tiles
-constexpr uint32_t smem_stages_n(int stages) { return stages * (kTileQf + kTileQp) + 2 * kTileP; }   // P is double buffered
-constexpr uint32_t smem_stages(int mt) { return smem_stages_n(stages_for(mt)); }                      // 184 / 160 KB
-constexpr uint32_t kTmemCols = 512;                     // S[0] 0..127, S[1] 128..255, [numer | rowsum] of row tile m at 256 + 32 m
+constexpr int stages_for(int mt, bool ptmem = true) { return ptmem ? kMaxStages : mt <= 2 ? 5 : 4; }   // the most that fit next to mt query tiles
+constexpr uint32_t smem_stages_n(int stages, bool ptmem = true) { return stages * (kTileQf + kTileQp) + (ptmem ? 0 : 2 * kTileP); }   // P double buffered
+constexpr uint32_t smem_stages(int mt, bool ptmem = true) { return smem_stages_n(stages_for(mt, ptmem), ptmem); }   // 144 KB (P in TMEM) / 184 / 160 KB
+constexpr uint32_t kTmemCols = 512;                     // S[0] 0..127, S[1] 128..255, [numer | rowsum] of row tile m at 256 + 32 m,
+constexpr uint32_t kTmemP = 384;                        // bf16 P[0] 384..447, P[1] 448..511 (A operand of GEMM2 in tensor memory)
 constexpr int kRedLd = 36;                              // floats per row of a reduction tile (16-byte rows, 4-way bank spread)
 constexpr uint32_t kRedTile = kBM * kRedLd * 4;         // 18 KB per row tile, staged over the drained pipeline buffers
-constexpr size_t smem_request(int mt) { return 1024 + (size_t)mt * kTileA + smem_stages(mt) + 512; }   // mt = 1: 201.5 KB, 2: 217.5 KB, 4: 225.5 KB
-constexpr size_t smem_request_n(int mt, int stages) { return 1024 + (size_t)mt * kTileA + smem_stages_n(stages) + 512; }
+constexpr size_t smem_request_n(int mt, int stages, bool ptmem = true) { return 1024 + (size_t)mt * kTileA + smem_stages_n(stages, ptmem) + 512; }
+constexpr size_t smem_request(int mt, bool ptmem = true) { return smem_request_n(mt, stages_for(mt, ptmem), ptmem); }   // P in TMEM: 161.5 .. 209.5 KB
+constexpr size_t kSmemMax = smem_request(kMaxMT, false) > smem_request(kMaxMT, true) ? smem_request(kMaxMT, false) : smem_request(kMaxMT, true);
 
 struct BankMaps {                 // one pair of tensor maps per shard; remote shards are peer-mapped NVLink addresses
   CUtensorMap qf[kMaxSeg];
@@ -161,7 +163,9 @@ __device__ __forceinline__ float ex2_poly(float s, float scale, float s_min) {
 template <int NPOLY>
 __device__ __forceinline__ constexpr bool poly_slot(int i) { return NPOLY > 0 && ((i + 1) * NPOLY) / 32 != (i * NPOLY) / 32; }
 
-template <int NPOLY, int EPI>
+// PTMEM: P = bf16(exp) goes back into tensor memory and is the A operand of the second GEMM (tcgen05.mma with A in TMEM);
+// false = the round-2 A/B form, P through swizzled shared memory (st.shared + fence.proxy.async, SS-form MMA).
+template <int NPOLY, bool PTMEM>
 __global__ void __launch_bounds__(kTcThreads, 1)
 bank_smooth_tc_kernel(const __grid_constant__ CUtensorMap tm_f, const __grid_constant__ BankMaps maps, const SmoothTcParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -172,11 +176,11 @@ bank_smooth_tc_kernel(const __grid_constant__ CUtensorMap tm_f, const __grid_con
   uint8_t* sQp = sQf + kStages * kTileQf;
   uint8_t* sP = sQp + kStages * kTileQp;
   float* sRed = reinterpret_cast<float*>(sQf);             // [mt][128][kRedLd] after the pipeline has drained
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * kTileP);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + (PTMEM ? 0 : 2 * kTileP));
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + BAR_COUNT);
   volatile int* abort_flag = reinterpret_cast<volatile int*>(tmem_slot + 1);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;   // warp-uniform for the compiler
   const int row_group = blockIdx.x, split = blockIdx.y;
   const int cta = blockIdx.y * gridDim.x + blockIdx.x;
   const int tile0 = row_group * p.mt;                      // first row tile of this CTA
@@ -206,10 +210,10 @@ bank_smooth_tc_kernel(const __grid_constant__ CUtensorMap tm_f, const __grid_con
     }
     for (int s = 0; s < 2; ++s) {
       tc::mbar_init(&bars[BAR_S_FULL + s], 1);
-      tc::mbar_init(&bars[BAR_S_EMPTY + s], kEpiThreads);
+      tc::mbar_init(&bars[BAR_S_EMPTY + s], kEpiWarps);        // one arrival per epilogue warp
     }
     for (int s = 0; s < 2; ++s) {
-      tc::mbar_init(&bars[BAR_P_FULL + s], kEpiThreads);
+      tc::mbar_init(&bars[BAR_P_FULL + s], kEpiWarps);
       tc::mbar_init(&bars[BAR_P_EMPTY + s], 1);
     }
     tc::mbar_init(&bars[BAR_ACC], 1);
@@ -260,39 +264,56 @@ bank_smooth_tc_kernel(const __grid_constant__ CUtensorMap tm_f, const __grid_con
       }
     }
   } else if (warp == 1) {
-    // ================= MMA issuer (one thread) =================
-    if (lane == 0) {
+    // ================= MMA issuer: the whole warp runs the loop (warp-uniform control flow), one elected lane issues =========
+    // The issue path of this warp bounds the kernel: a unit is 12 small MMAs (64 / 16 clocks of tensor work each) plus
+    // three commits, so every instruction between two tcgen05.mma counts (profiles/r02_k3_experiments.md).
+    {
+      const bool leader = tc::elect_one();
+      const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem, 0);
       constexpr uint32_t idesc1 = tc::idesc_bf16_f32(kBM, kBN);
       constexpr uint32_t idesc2 = tc::idesc_bf16_f32(kBM, kCP);
+      const uint32_t a_u32 = tc::smem_u32(sA), qf_u32 = tc::smem_u32(sQf), qp_u32 = tc::smem_u32(sQp), p_u32 = tc::smem_u32(sP);
       tc::mbar_wait(&bars[BAR_A], 0, abort_flag);
-      B200SSL_STAMP(p.dbg, cta, 2);                         // query tiles landed (TMA)
+      if (threadIdx.x == 32) B200SSL_STAMP(p.dbg, cta, 2);  // query tiles landed (TMA)
       // unit j = (key tile t, row tile m), m fastest: S[j & 1] = F_m Qf_t^T   (K = 64 -> 4 x UMMA_K 16).
-      // This thread sits on the critical path of every unit (P_FULL -> GEMM2 -> P_EMPTY, S_EMPTY -> GEMM1 -> S_FULL): (t, m)
-      // and the stage index are carried as counters -- a runtime division per GEMM cost 17 % at rows 3584 x K 65536.
+      // (t, m) and the stage index are carried as counters -- a runtime division per GEMM cost 17 % at rows 3584 x K 65536.
       auto gemm1 = [&](int j, int m, int s, int lap) {
         const int b = j & 1;
         if (m == 0) tc::mbar_wait(&bars[BAR_KV_FULL + s], lap, abort_flag);
         if (j >= 2) tc::mbar_wait(&bars[BAR_S_EMPTY + b], ((j >> 1) - 1) & 1, abort_flag);   // S of unit j-2 is in registers
         tc::tcgen05_fence_after();
-        const uint64_t a_desc = tc::smem_desc_sw128(tc::smem_u32(sA + (size_t)m * kTileA));
-        const uint64_t b_desc = tc::smem_desc_sw128(tc::smem_u32(sQf + s * kTileQf));
+        const uint64_t a_desc = tc::smem_desc_sw128(a_u32 + (uint32_t)m * kTileA);
+        const uint64_t b_desc = tc::smem_desc_sw128(qf_u32 + (uint32_t)s * kTileQf);
+        if (leader) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) tc::mma_bf16_ss(tmem + b * kBN, a_desc + 2 * k, b_desc + 2 * k, idesc1, k > 0);
-        tc::mma_commit(&bars[BAR_S_FULL + b]);
+          for (int k = 0; k < 4; ++k) tc::mma_bf16_ss(tmem_u + b * kBN, a_desc + 2 * k, b_desc + 2 * k, idesc1, k > 0);
+          tc::mma_commit(&bars[BAR_S_FULL + b]);
+        }
+        __syncwarp();
       };
       auto gemm2 = [&](int j, int t, int m, int s) {   // [numer | rowsum]_m += P [QpT | 1]^T   (K = 128 keys -> 2 sub-tiles x 4 x UMMA_K 16)
         const int pb = j & 1;
         tc::mbar_wait(&bars[BAR_P_FULL + pb], (j >> 1) & 1, abort_flag);
         tc::tcgen05_fence_after();
+        const uint64_t pa0 = tc::smem_desc_sw128(p_u32 + (uint32_t)pb * kTileP);
+        const uint64_t qb0 = tc::smem_desc_sw128(qp_u32 + (uint32_t)s * kTileQp);
+        if (leader) {
 #pragma unroll
-        for (int kb = 0; kb < 2; ++kb) {
-          const uint64_t pa = tc::smem_desc_sw128(tc::smem_u32(sP + pb * kTileP + kb * kSubP));
-          const uint64_t qb = tc::smem_desc_sw128(tc::smem_u32(sQp + s * kTileQp + kb * kSubQp));
+          for (int kb = 0; kb < 2; ++kb) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k) tc::mma_bf16_ss(tmem + 2 * kBN + m * kCP, pa + 2 * k, qb + 2 * k, idesc2, (t | kb | k) != 0);
+            for (int k = 0; k < 4; ++k) {
+              if (PTMEM)
+                tc::mma_bf16_ts(tmem_u + 2 * kBN + m * kCP, tmem_u + kTmemP + pb * (kBN / 2) + (kb * 4 + k) * 8,
+                                qb0 + (uint64_t)(kb * (kSubQp >> 4) + 2 * k), idesc2, (t | kb | k) != 0);
+              else
+                tc::mma_bf16_ss(tmem_u + 2 * kBN + m * kCP, pa0 + (uint64_t)(kb * (kSubP >> 4) + 2 * k), qb0 + (uint64_t)(kb * (kSubQp >> 4) + 2 * k),
+                                idesc2, (t | kb | k) != 0);
+            }
+          }
+          if (m == M - 1) tc::mma_commit(&bars[BAR_KV_EMPTY + s]);   // the key tile has served every row tile
+          tc::mma_commit(&bars[BAR_P_EMPTY + pb]);
         }
-        if (m == M - 1) tc::mma_commit(&bars[BAR_KV_EMPTY + s]);   // the key tile has served every row tile
-        tc::mma_commit(&bars[BAR_P_EMPTY + pb]);
+        __syncwarp();
       };
       int m1 = 0, s1 = 0, ph1 = 0;                           // (row tile, stage, stage-ring lap) of the next GEMM1
       auto next1 = [&]() { if (++m1 == M) { m1 = 0; if (++s1 == kStages) { s1 = 0; ph1 ^= 1; } } };
@@ -307,7 +328,8 @@ bank_smooth_tc_kernel(const __grid_constant__ CUtensorMap tm_f, const __grid_con
         gemm2(j, t2, m2, s2);
         if (++m2 == M) { m2 = 0; ++t2; if (++s2 == kStages) s2 = 0; }
       }
-      tc::mma_commit(&bars[BAR_ACC]);
+      if (leader) tc::mma_commit(&bars[BAR_ACC]);
+      __syncwarp();
     }
   } else {
     // ===== epilogue: four threads per TMEM lane (query row), 32 of the 128 key columns each =====
@@ -320,56 +342,57 @@ bank_smooth_tc_kernel(const __grid_constant__ CUtensorMap tm_f, const __grid_con
     uint32_t p_off[4];
 #pragma unroll
     for (int q = 0; q < 4; ++q) p_off[q] = p_base + tc::sw128_offset(r_in, c2 * 4 + q);
-    uint32_t r[32];
-    if (EPI == 1) {                                         // S of unit 0
+    if (threadIdx.x == 64) {                                // first S tile ready (TMA + GEMM1): stamped outside the unit loop
       tc::mbar_wait(&bars[BAR_S_FULL], 0, abort_flag);
-      if (threadIdx.x == 64) B200SSL_STAMP(p.dbg, cta, 3);
-      tc::tcgen05_fence_after();
-      tc::tmem_ld_32x32(lane_addr + colq * 32, r);
-      tc::tmem_ld_wait(r);
-      tc::tcgen05_fence_before();
-      tc::mbar_arrive(&bars[BAR_S_EMPTY]);
+      B200SSL_STAMP(p.dbg, cta, 3);
     }
+    __syncwarp();
+    uint32_t r[32];
+    auto exp_pack = [&](int e) {                                                                    // comatch.py:180
+      const float s0 = __uint_as_float(r[2 * e]), s1 = __uint_as_float(r[2 * e + 1]);
+      float e0, e1;
+      if (poly_slot<NPOLY>(2 * e) || poly_slot<NPOLY>(2 * e + 1)) {
+        e0 = poly_slot<NPOLY>(2 * e) ? ex2_poly(s0, p.scale, p.s_min) : ex2_approx(s0 * p.scale);
+        e1 = poly_slot<NPOLY>(2 * e + 1) ? ex2_poly(s1, p.scale, p.s_min) : ex2_approx(s1 * p.scale);
+      } else {
+        float x0, x1;                                       // one packed multiply for the pair (bit-identical to two FMULs)
+        tc::mul_f32x2(x0, x1, s0, s1, p.scale);
+        e0 = ex2_approx(x0);
+        e1 = ex2_approx(x1);
+      }
+      const __nv_bfloat162 hh = __floats2bfloat162_rn(e0, e1);
+      return *reinterpret_cast<const uint32_t*>(&hh);
+    };
     for (int j = 0; j < J; ++j) {
       const int b = j & 1;
-      if (EPI == 0) {
-        tc::mbar_wait(&bars[BAR_S_FULL + b], (j >> 1) & 1, abort_flag);
-        if (j == 0 && threadIdx.x == 64) B200SSL_STAMP(p.dbg, cta, 3);   // first S tile ready (TMA + GEMM1)
-        tc::tcgen05_fence_after();
-        tc::tmem_ld_32x32(lane_addr + b * kBN + colq * 32, r);
-        tc::tmem_ld_wait(r);
-        tc::tcgen05_fence_before();
-        tc::mbar_arrive(&bars[BAR_S_EMPTY + b]);            // S[b] is in registers: GEMM1 of unit j+2 may overwrite it
-      }
-      // keys beyond the bank need no mask: their QpT columns (incl. the ones column) are TMA zero fill
+      tc::mbar_wait(&bars[BAR_S_FULL + b], (j >> 1) & 1, abort_flag);
+      tc::tcgen05_fence_after();
+      // keys beyond the bank need no mask: their QpT columns (incl. the ones column) are TMA zero fill.
+      // The S read is split in two 16-column loads: the second is in flight during the exponentials of the first.
       uint32_t w[16];
+      tc::tmem_ld_32x16<0>(lane_addr + b * kBN + colq * 32, r);
+      tc::tmem_ld_wait(r);
+      tc::tmem_ld_32x16<16>(lane_addr + b * kBN + colq * 32 + 16, r);
 #pragma unroll
-      for (int e = 0; e < 16; ++e) {
-        const float s0 = __uint_as_float(r[2 * e]), s1 = __uint_as_float(r[2 * e + 1]);               // comatch.py:180
-        const float e0 = poly_slot<NPOLY>(2 * e) ? ex2_poly(s0, p.scale, p.s_min) : ex2_approx(s0 * p.scale);
-        const float e1 = poly_slot<NPOLY>(2 * e + 1) ? ex2_poly(s1, p.scale, p.s_min) : ex2_approx(s1 * p.scale);
-        const __nv_bfloat162 hh = __floats2bfloat162_rn(e0, e1);
-        w[e] = *reinterpret_cast<const uint32_t*>(&hh);
-      }
-      const bool more = j + 1 < J;
-      if (EPI == 1 && more) {
-        // the TMEM read of the NEXT unit is issued here, so that its latency hides behind the stores, the proxy fence and
-        // the barrier traffic of this unit (GEMM1 of unit j+1 was issued a whole unit ago)
-        tc::mbar_wait(&bars[BAR_S_FULL + (b ^ 1)], ((j + 1) >> 1) & 1, abort_flag);
-        tc::tcgen05_fence_after();
-        tc::tmem_ld_32x32(lane_addr + (b ^ 1) * kBN + colq * 32, r);
-      }
+      for (int e = 0; e < 8; ++e) w[e] = exp_pack(e);
+      tc::tmem_ld_wait(r);
+      tc::tcgen05_fence_before();
+      tc::mbar_arrive_warp(&bars[BAR_S_EMPTY + b], lane);   // S[b] is in registers: GEMM1 of unit j+2 may overwrite it
+#pragma unroll
+      for (int e = 8; e < 16; ++e) w[e] = exp_pack(e);
       // the P buffer of unit j-2 must have been consumed -- only now, after the exponentials
       if (j >= 2) tc::mbar_wait(&bars[BAR_P_EMPTY + b], ((j >> 1) - 1) & 1, abort_flag);
-#pragma unroll
-      for (int q = 0; q < 4; ++q) tc::st_shared_v4(p_off[q] + b * kTileP, w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
-      tc::fence_proxy_async_smem();               // generic-proxy writes of P -> visible to the tensor core
-      tc::mbar_arrive(&bars[BAR_P_FULL + b]);
-      if (EPI == 1 && more) {
-        tc::tmem_ld_wait(r);
+      if (PTMEM) {
+        tc::tcgen05_fence_after();
+        tc::tmem_st_32x16(lane_addr + kTmemP + b * (kBN / 2) + colq * 16, w);
+        tc::tmem_st_wait();
         tc::tcgen05_fence_before();
-        tc::mbar_arrive(&bars[BAR_S_EMPTY + (b ^ 1)]);      // S of unit j+1 is in registers: GEMM1 of unit j+3 may overwrite it
+      } else {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) tc::st_shared_v4(p_off[q] + b * kTileP, w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
+        tc::fence_proxy_async_smem();               // generic-proxy writes of P -> visible to the tensor core
       }
+      tc::mbar_arrive_warp(&bars[BAR_P_FULL + b], lane);
     }
     if (threadIdx.x == 64) B200SSL_STAMP(p.dbg, cta, 4);   // last exp tile done
     tc::mbar_wait(&bars[BAR_ACC], 0, abort_flag);           // all MMAs retired: pipeline smem is free, accumulators final
@@ -540,7 +563,7 @@ struct SmoothPlan { int mt, cluster, nouter; };
 int g_force_mt = getenv("B200SSL_K3_MT") ? atoi(getenv("B200SSL_K3_MT")) : 0;          // > 0: row tiles per CTA
 int g_force_cluster = 0, g_force_nouter = 0;                                           // > 0: cluster size / clusters per row group
 int g_force_stages = getenv("B200SSL_K3_STAGES") ? atoi(getenv("B200SSL_K3_STAGES")) : 0;   // 3..5 key-tile stages
-int g_force_epi = getenv("B200SSL_K3_EPI") ? atoi(getenv("B200SSL_K3_EPI")) : 0;        // epilogue variant (A/B), see the kernel
+int g_p_tmem = getenv("B200SSL_K3_P_SMEM") ? 0 : 1;                                    // 0: P through shared memory (A/B)
 int g_force_poly = getenv("B200SSL_K3_POLY") ? atoi(getenv("B200SSL_K3_POLY")) : -1;   // exponentials (of 32) on the FMA pipe
 
 // Clusters of `cl` CTAs (one CTA per SM: the kernel takes more than half an SM's shared memory) that the chip runs at once.
@@ -552,7 +575,7 @@ int max_active_clusters(int cl) {
   int n = cl == 1 ? 148 : cl == 2 ? 74 : cl == 4 ? 33 : 15;     // measured on B200 (b200ssl_debug_max_active_clusters)
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) == cudaSuccess && ndev > 0) {
-    cudaFuncSetAttribute(bank_smooth_tc_kernel<0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_request(kMaxMT));
+    cudaFuncSetAttribute(bank_smooth_tc_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax);
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(1, (unsigned)(cl * kNumSMs), 1);
     cfg.blockDim = dim3(kTcThreads, 1, 1);
@@ -562,7 +585,7 @@ int max_active_clusters(int cl) {
     attr[0].val.clusterDim.x = 1; attr[0].val.clusterDim.y = (unsigned)cl; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
     int q = 0;
-    if (cudaOccupancyMaxActiveClusters(&q, bank_smooth_tc_kernel<0, 1>, &cfg) == cudaSuccess && q > 0) n = q;
+    if (cudaOccupancyMaxActiveClusters(&q, bank_smooth_tc_kernel<0, true>, &cfg) == cudaSuccess && q > 0) n = q;
     else (void)cudaGetLastError();
   } else {
     (void)cudaGetLastError();
@@ -613,15 +636,15 @@ SmoothPlan smooth_tc_plan(long long rows, long long ktiles, bool remote) {
   return best;
 }
 
-template <int NPOLY, int EPI>
+template <int NPOLY, bool PTMEM>
 cudaError_t launch_smooth(const SmoothTcParams& p, const CUtensorMap& tm_f, const BankMaps& maps, dim3 grid, size_t smem, cudaStream_t stream) {
   static size_t attr_smem = 0;
   if (smem > attr_smem) {
-    cudaError_t e = cudaFuncSetAttribute(bank_smooth_tc_kernel<NPOLY, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_request(kMaxMT));
+    cudaError_t e = cudaFuncSetAttribute(bank_smooth_tc_kernel<NPOLY, PTMEM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax);
     if (e != cudaSuccess) return e;
-    attr_smem = smem_request(kMaxMT);
+    attr_smem = kSmemMax;
   }
-  return launch_pdl(PDL_SMOOTH, bank_smooth_tc_kernel<NPOLY, EPI>, grid, dim3(kTcThreads, 1, 1), smem, stream, dim3(1, (unsigned)p.cluster, 1), tm_f,
+  return launch_pdl(PDL_SMOOTH, bank_smooth_tc_kernel<NPOLY, PTMEM>, grid, dim3(kTcThreads, 1, 1), smem, stream, dim3(1, (unsigned)p.cluster, 1), tm_f,
                     maps, p);
 }
 
@@ -682,24 +705,23 @@ int bank_smooth_tc(const void* feats, const void* queue_feats, const void* queue
     if (int e = tc::make_tmap_bf16_2d(&maps.qf[s], qf, (uint64_t)seg_rows, 64, 128, kBN, 64)) return e;
     if (int e = tc::make_tmap_bf16_2d(&maps.qpt[s], qpt, kCP, (uint64_t)seg_rows, (uint64_t)seg_rows * 2, kCP, 64)) return e;
   }
-  static_assert(smem_request(kMaxMT) <= 227 * 1024 && smem_request(2) <= 227 * 1024 && smem_request(1) <= 227 * 1024, "shared memory budget");
-  static_assert((size_t)kMaxMT * kRedTile <= smem_stages(kMaxMT), "the reduction tiles must fit in the drained pipeline buffers");
+  static_assert(kSmemMax <= 227 * 1024 && smem_request(2, false) <= 227 * 1024 && smem_request(1, false) <= 227 * 1024, "shared memory budget");
+  static_assert((size_t)kMaxMT * kRedTile <= smem_stages(kMaxMT, true) && (size_t)kMaxMT * kRedTile <= smem_stages(kMaxMT, false),
+                "the reduction tiles must fit in the drained pipeline buffers");
   static_assert(2 * kBN + kMaxMT * kCP <= (int)kTmemCols, "TMEM budget");
   // Share of the exponentials computed on the FMA pipe (of 32 per thread and S tile).  Measured on B200 (tools/k3_tune.py,
   // profiles/r02_k3_experiments.md): every polynomial slot ADDS ~25 clocks per S tile at every size -- the epilogue is bound by
   // its serial ld -> exp -> st -> fence chain per tile, not by the MUFU rate -- so the default is 0; the knob stays for A/B.
   const int npoly = g_force_poly >= 0 ? g_force_poly : 0;
   const dim3 grid((unsigned)groups, (unsigned)p.nsplit, 1);
-  p.stages = stages_for(p.mt);
+  p.stages = stages_for(p.mt, g_p_tmem != 0);
   if (g_force_stages >= 3 && g_force_stages < p.stages) p.stages = g_force_stages;
-  const size_t smem = smem_request_n(p.mt, p.stages);
+  const size_t smem = smem_request_n(p.mt, p.stages, g_p_tmem != 0);
   cudaError_t e;
-  if (g_force_epi == 0) e = launch_smooth<0, 0>(p, tm_f, maps, grid, smem, stream);      // A/B: the TMEM read inside the unit it belongs to
-  else if (npoly >= 16) e = launch_smooth<16, 1>(p, tm_f, maps, grid, smem, stream);
-  else if (npoly >= 12) e = launch_smooth<12, 1>(p, tm_f, maps, grid, smem, stream);
-  else if (npoly >= 8) e = launch_smooth<8, 1>(p, tm_f, maps, grid, smem, stream);
-  else if (npoly >= 4) e = launch_smooth<4, 1>(p, tm_f, maps, grid, smem, stream);
-  else e = launch_smooth<0, 1>(p, tm_f, maps, grid, smem, stream);
+  if (!g_p_tmem) e = npoly >= 8 ? launch_smooth<8, false>(p, tm_f, maps, grid, smem, stream) : launch_smooth<0, false>(p, tm_f, maps, grid, smem, stream);
+  else e = npoly >= 16 ? launch_smooth<16, true>(p, tm_f, maps, grid, smem, stream)
+           : npoly >= 8 ? launch_smooth<8, true>(p, tm_f, maps, grid, smem, stream)
+                        : launch_smooth<0, true>(p, tm_f, maps, grid, smem, stream);
   if (e != cudaSuccess) return fail((int)e, "%s: cudaLaunchKernelEx: %s", fn, cudaGetErrorString(e));
   return check_launch(fn);
 }
@@ -710,8 +732,9 @@ extern "C" void b200ssl_debug_set_k3(int32_t row_tiles_per_cta, int32_t cluster,
   b200ssl::g_force_mt = row_tiles_per_cta;
   b200ssl::g_force_cluster = cluster;
   b200ssl::g_force_nouter = clusters_per_row_group;
-  b200ssl::g_force_epi = poly_of_32 == -2 ? 0 : 1;          // -2: the un-pipelined epilogue (A/B), no polynomial
-  b200ssl::g_force_poly = poly_of_32 == -2 ? 0 : poly_of_32;
+  // poly_of_32 < 0: defaults; otherwise exponentials (of 32) on the FMA pipe, + 100: P through shared memory (A/B)
+  b200ssl::g_p_tmem = poly_of_32 < 0 ? 1 : (poly_of_32 / 100 == 0);
+  b200ssl::g_force_poly = poly_of_32 < 0 ? -1 : poly_of_32 % 100;
 }
 
 extern "C" int b200ssl_debug_max_active_clusters(int32_t cluster) {

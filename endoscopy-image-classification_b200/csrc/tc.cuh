@@ -44,6 +44,25 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, volati
   }
 }
 
+// one arrival per warp: every lane has done its part (and its own fences) before the warp-level sync
+__device__ __forceinline__ void mbar_arrive_warp(uint64_t* bar, int lane) {
+  __syncwarp();
+  if (lane == 0) mbar_arrive(bar);
+}
+
+// One lane of a converged warp (elect.sync).  The MMA warps run their loops with ALL lanes in warp-uniform control flow and
+// issue under this predicate: descriptor arithmetic then stays in uniform registers (a loop inside `if (lane == 0)` makes
+// the compiler rebuild every tcgen05.mma operand with an ELECT / R2UR sequence, ~17 dependent instructions per MMA).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // ---- proxies / fences ----------------------------------------------------------
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -51,6 +70,15 @@ __device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fe
 
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+
+// {x0, x1} = {a0 * c, a1 * c} with one packed FMUL2 (sm_100 f32x2 arithmetic; each lane rounds like a scalar FMUL)
+__device__ __forceinline__ void mul_f32x2(float& x0, float& x1, float a0, float a1, float c) {
+  asm("{\n\t.reg .b64 a, b, d;\n\t"
+      "mov.b64 a, {%2, %3};\n\tmov.b64 b, {%4, %4};\n\t"
+      "mul.rn.f32x2 d, a, b;\n\t"
+      "mov.b64 {%0, %1}, d;\n\t}"
+      : "=f"(x0), "=f"(x1) : "f"(a0), "f"(a1), "f"(c));
 }
 
 // ---- TMA -------------------------------------------------------------------------
@@ -87,6 +115,28 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32])
       : "r"(taddr)
       : "memory");
 }
+// 32 lanes x 16 columns into r[O .. O+16)
+template <int O>
+__device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[O + 0]), "=r"(r[O + 1]), "=r"(r[O + 2]), "=r"(r[O + 3]), "=r"(r[O + 4]), "=r"(r[O + 5]), "=r"(r[O + 6]),
+        "=r"(r[O + 7]), "=r"(r[O + 8]), "=r"(r[O + 9]), "=r"(r[O + 10]), "=r"(r[O + 11]), "=r"(r[O + 12]), "=r"(r[O + 13]),
+        "=r"(r[O + 14]), "=r"(r[O + 15])
+      : "r"(taddr)
+      : "memory");
+}
+// registers -> 32 lanes x 16 columns (thread i of the warp writes lane lane_base + i)
+__device__ __forceinline__ void tmem_st_32x16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+        "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 // The same wait for a load that was issued EARLIER than the statement before it (software pipelining): the registers are
 // in/out operands, so no use of them can be scheduled above the wait by the compiler.
@@ -129,6 +179,16 @@ __device__ __forceinline__ void mma_bf16_ss(uint32_t d_tmem, uint64_t a_desc, ui
       "setp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
       ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"((uint32_t)accumulate)
+      : "memory");
+}
+// D[tmem] (+)= A[tmem] * B[smem]^T : the A operand read from tensor memory (lane = row of A, one 32-bit column = two
+// consecutive bf16 of K, low half first).  Half the shared-memory traffic of the SS form and no proxy fence for A.
+__device__ __forceinline__ void mma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, bool accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"((uint32_t)accumulate)
       : "memory");
 }
 // mbarrier arrive once all tcgen05 ops issued so far by this thread have completed.
