@@ -53,6 +53,8 @@ extern "C" size_t b200ssl_workspace_bytes(int64_t rows, int32_t classes, int64_t
     if (sm > need) need = sm;
     const size_t tc = sizeof(float) * smooth_tc_workspace_floats(rows, bank_rows, classes);
     if (tc > need) need = tc;
+    const size_t tc32 = smooth_tc_f32_workspace_bytes(rows, bank_rows, classes);     // fold partials + bf16 hi / mid operand copies
+    if (classes <= 31 && tc32 > need) need = tc32;
   }
   return kWsHeaderBytes + ((need + 255) & ~(size_t)255);
 }

@@ -9,6 +9,8 @@
 // (comatch.py:180-181).
 #include <math.h>
 
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "tiles.cuh"
 
@@ -195,10 +197,16 @@ int smooth_nsplit(long long rows, long long bank_rows, int* tiles_per_split) {
 using namespace b200ssl;
 
 namespace b200ssl {
+static int g_f32_simt = getenv("B200SSL_K3_F32_SIMT") != nullptr;
 int bank_smooth_tc(const void* feats, const void* queue_feats, const void* queue_probs_t, long long rows,
                    long long bank_rows, int classes, float temperature, float* rowsum, float* numer, int rowsum_ld,
                    int numer_ld, const b200ssl_bank_shards* shards, void* workspace, size_t workspace_bytes, cudaStream_t stream);
+int bank_smooth_tc_f32(const float* feats, const float* queue_feats, const float* queue_probs, long long rows, long long bank_rows,
+                       int classes, float temperature, float* rowsum, float* numer, int rowsum_ld, int numer_ld, void* workspace,
+                       size_t workspace_bytes, cudaStream_t stream);
 }
+
+extern "C" void b200ssl_debug_set_k3_f32_simt(int32_t on) { b200ssl::g_f32_simt = on != 0; }
 
 extern "C" int b200ssl_bank_smooth_partial(const void* feats_u_w, const void* queue_feats, const void* queue_probs,
                                            const void* queue_probs_t, int64_t rows, int64_t bank_rows, int32_t dim, int32_t classes,
@@ -236,6 +244,13 @@ extern "C" int b200ssl_bank_smooth_partial(const void* feats_u_w, const void* qu
     return bank_smooth_tc(feats_u_w, queue_feats, queue_probs_t, rows, bank_rows, classes, temperature, rowsum, numer,
                           rowsum_ld > 0 ? rowsum_ld : 1, numer_ld > 0 ? numer_ld : classes, nullptr, workspace, workspace_bytes,
                           as_stream(stream));
+  // fp32 storage with 64-wide embeddings: the same tensor-core kernel on bf16 hi + mid operands (1e-6 on the smoothed
+  // probabilities, the reference's fp32 torch.mm is 3e-7); B200SSL_K3_F32_SIMT=1 keeps the exact-fp32 FFMA tiles (A/B)
+  if (dtype == B200SSL_F32 && dim == 64 && classes <= 31 && !g_f32_simt && !(reinterpret_cast<uintptr_t>(feats_u_w) & 15u) &&
+      !(reinterpret_cast<uintptr_t>(queue_feats) & 15u))
+    return bank_smooth_tc_f32(static_cast<const float*>(feats_u_w), static_cast<const float*>(queue_feats),
+                              static_cast<const float*>(queue_probs), rows, bank_rows, classes, temperature, rowsum, numer,
+                              rowsum_ld > 0 ? rowsum_ld : 1, numer_ld > 0 ? numer_ld : classes, workspace, workspace_bytes, as_stream(stream));
   SmoothParams p{};
   p.f = feats_u_w; p.qf = queue_feats; p.qp = queue_probs;
   p.rows = rows; p.bank_rows = bank_rows; p.D = dim; p.C = classes; p.tau = temperature;

@@ -165,16 +165,22 @@ __device__ __forceinline__ constexpr bool poly_slot(int i) { return NPOLY > 0 &&
 
 // PTMEM: P = bf16(exp) goes back into tensor memory and is the A operand of the second GEMM (tcgen05.mma with A in TMEM);
 // false = the round-2 A/B form, P through swizzled shared memory (st.shared + fence.proxy.async, SS-form MMA).
-template <int NPOLY, bool PTMEM>
+// NT: bf16 terms per operand.  1 = bf16 storage.  2 = fp32 storage split on the fly into bf16 hi + mid (csrc/bank_tc.cu:
+// split_operands_kernel): S = F_mid Q_hi^T + F_hi Q_mid^T + F_hi Q_hi^T, and likewise [numer | rowsum] from P = P_hi + P_mid
+// (both in tensor memory, single buffered) against Qp_hi / Qp_mid -- 2^-17 per operand, 1e-6 on the smoothed probabilities
+// (the reference's fp32 torch.mm: 3e-7), at 36 instead of 12 MMAs per unit.
+template <int NPOLY, bool PTMEM, int NT = 1>
 __global__ void __launch_bounds__(kTcThreads, 1)
 bank_smooth_tc_kernel(const __grid_constant__ CUtensorMap tm_f, const __grid_constant__ BankMaps maps, const SmoothTcParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* sA = smem;                                       // [mt][128][64] bf16 query tiles
   const int kStages = p.stages;
-  uint8_t* sQf = sA + (size_t)p.mt * kTileA;
-  uint8_t* sQp = sQf + kStages * kTileQf;
-  uint8_t* sP = sQp + kStages * kTileQp;
+  static_assert(NT == 1 || (NT == 2 && PTMEM && NPOLY == 0), "split operands: P in tensor memory, MUFU exponentials");
+  constexpr uint32_t tA = NT * kTileA, tQf = NT * kTileQf, tQp = NT * kTileQp;    // all terms of one tile, term-major
+  uint8_t* sQf = sA + (size_t)p.mt * tA;
+  uint8_t* sQp = sQf + kStages * tQf;
+  uint8_t* sP = sQp + kStages * tQp;
   float* sRed = reinterpret_cast<float*>(sQf);             // [mt][128][kRedLd] after the pipeline has drained
   uint64_t* bars = reinterpret_cast<uint64_t*>(sP + (PTMEM ? 0 : 2 * kTileP));
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + BAR_COUNT);
@@ -238,8 +244,10 @@ bank_smooth_tc_kernel(const __grid_constant__ CUtensorMap tm_f, const __grid_con
   if (warp == 0) {
     // ================= TMA producer =================
     if (lane == 0) {
-      tc::mbar_arrive_expect_tx(&bars[BAR_A], (uint32_t)M * kTileA);
-      for (int m = 0; m < M; ++m) tc::tma_load_2d(sA + (size_t)m * kTileA, &tm_f, 0, (tile0 + m) * kBM, &bars[BAR_A]);
+      tc::mbar_arrive_expect_tx(&bars[BAR_A], (uint32_t)M * tA);
+      for (int m = 0; m < M; ++m)
+#pragma unroll
+        for (int tt = 0; tt < NT; ++tt) tc::tma_load_2d(sA + (size_t)m * tA + tt * kTileA, &tm_f, 64 * tt, (tile0 + m) * kBM, &bars[BAR_A]);
     }
     if (p.arenas) {
       // multi-rank bank: every rank's enqueue of the previous step must have landed (its flag was published a
@@ -256,10 +264,13 @@ bank_smooth_tc_kernel(const __grid_constant__ CUtensorMap tm_f, const __grid_con
         if (t >= kStages) tc::mbar_wait(&bars[BAR_KV_EMPTY + s], (lap - 1) & 1, abort_flag);
         int seg;
         const int key0 = tile_of(t, &seg);
-        tc::mbar_arrive_expect_tx(&bars[BAR_KV_FULL + s], kTileQf + kTileQp);
-        tc::tma_load_2d(sQf + s * kTileQf, &maps.qf[seg], 0, key0, &bars[BAR_KV_FULL + s]);
-        tc::tma_load_2d(sQp + s * kTileQp, &maps.qpt[seg], key0, 0, &bars[BAR_KV_FULL + s]);
-        tc::tma_load_2d(sQp + s * kTileQp + kSubQp, &maps.qpt[seg], key0 + 64, 0, &bars[BAR_KV_FULL + s]);
+        tc::mbar_arrive_expect_tx(&bars[BAR_KV_FULL + s], tQf + tQp);
+#pragma unroll
+        for (int tt = 0; tt < NT; ++tt) {                   // term tt: columns [64 tt, +64) of a key row, rows [32 tt, +32) of QpT
+          tc::tma_load_2d(sQf + s * tQf + tt * kTileQf, &maps.qf[seg], 64 * tt, key0, &bars[BAR_KV_FULL + s]);
+          tc::tma_load_2d(sQp + s * tQp + tt * kTileQp, &maps.qpt[seg], key0, 32 * tt, &bars[BAR_KV_FULL + s]);
+          tc::tma_load_2d(sQp + s * tQp + tt * kTileQp + kSubQp, &maps.qpt[seg], key0 + 64, 32 * tt, &bars[BAR_KV_FULL + s]);
+        }
         if (++s == kStages) { s = 0; ++lap; }
       }
     }
@@ -272,6 +283,7 @@ bank_smooth_tc_kernel(const __grid_constant__ CUtensorMap tm_f, const __grid_con
       const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem, 0);
       constexpr uint32_t idesc1 = tc::idesc_bf16_f32(kBM, kBN);
       constexpr uint32_t idesc2 = tc::idesc_bf16_f32(kBM, kCP);
+      constexpr int kPairs = NT == 2 ? 3 : 1;
       const uint32_t a_u32 = tc::smem_u32(sA), qf_u32 = tc::smem_u32(sQf), qp_u32 = tc::smem_u32(sQp), p_u32 = tc::smem_u32(sP);
       tc::mbar_wait(&bars[BAR_A], 0, abort_flag);
       if (threadIdx.x == 32) B200SSL_STAMP(p.dbg, cta, 2);  // query tiles landed (TMA)
@@ -282,32 +294,41 @@ bank_smooth_tc_kernel(const __grid_constant__ CUtensorMap tm_f, const __grid_con
         if (m == 0) tc::mbar_wait(&bars[BAR_KV_FULL + s], lap, abort_flag);
         if (j >= 2) tc::mbar_wait(&bars[BAR_S_EMPTY + b], ((j >> 1) - 1) & 1, abort_flag);   // S of unit j-2 is in registers
         tc::tcgen05_fence_after();
-        const uint64_t a_desc = tc::smem_desc_sw128(a_u32 + (uint32_t)m * kTileA);
-        const uint64_t b_desc = tc::smem_desc_sw128(qf_u32 + (uint32_t)s * kTileQf);
+        const uint64_t a_desc = tc::smem_desc_sw128(a_u32 + (uint32_t)m * tA);
+        const uint64_t b_desc = tc::smem_desc_sw128(qf_u32 + (uint32_t)s * tQf);
         if (leader) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k) tc::mma_bf16_ss(tmem_u + b * kBN, a_desc + 2 * k, b_desc + 2 * k, idesc1, k > 0);
+          for (int pr = 0; pr < kPairs; ++pr) {             // (term of F, term of Q): (mid, hi), (hi, mid), (hi, hi) -- small products first
+            const uint64_t ta = (NT == 2 && pr == 0) ? (kTileA >> 4) : 0, tb = (NT == 2 && pr == 1) ? (kTileQf >> 4) : 0;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) tc::mma_bf16_ss(tmem_u + b * kBN, a_desc + ta + 2 * k, b_desc + tb + 2 * k, idesc1, (pr | k) != 0);
+          }
           tc::mma_commit(&bars[BAR_S_FULL + b]);
         }
         __syncwarp();
       };
       auto gemm2 = [&](int j, int t, int m, int s) {   // [numer | rowsum]_m += P [QpT | 1]^T   (K = 128 keys -> 2 sub-tiles x 4 x UMMA_K 16)
-        const int pb = j & 1;
-        tc::mbar_wait(&bars[BAR_P_FULL + pb], (j >> 1) & 1, abort_flag);
+        const int pb = NT == 2 ? 0 : (j & 1);               // split operands: one P buffer holding [P_hi | P_mid]
+        tc::mbar_wait(&bars[BAR_P_FULL + pb], (NT == 2 ? j : (j >> 1)) & 1, abort_flag);
         tc::tcgen05_fence_after();
         const uint64_t pa0 = tc::smem_desc_sw128(p_u32 + (uint32_t)pb * kTileP);
-        const uint64_t qb0 = tc::smem_desc_sw128(qp_u32 + (uint32_t)s * kTileQp);
+        const uint64_t qb0 = tc::smem_desc_sw128(qp_u32 + (uint32_t)s * tQp);
         if (leader) {
 #pragma unroll
-          for (int kb = 0; kb < 2; ++kb) {
+          for (int pr = 0; pr < kPairs; ++pr) {             // (term of P, term of Qp): (mid, hi), (hi, mid), (hi, hi)
+            const int ta = (NT == 2 && pr == 0) ? 1 : 0;
+            const uint64_t tb = (NT == 2 && pr == 1) ? (kTileQp >> 4) : 0;
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              if (PTMEM)
-                tc::mma_bf16_ts(tmem_u + 2 * kBN + m * kCP, tmem_u + kTmemP + pb * (kBN / 2) + (kb * 4 + k) * 8,
-                                qb0 + (uint64_t)(kb * (kSubQp >> 4) + 2 * k), idesc2, (t | kb | k) != 0);
-              else
-                tc::mma_bf16_ss(tmem_u + 2 * kBN + m * kCP, pa0 + (uint64_t)(kb * (kSubP >> 4) + 2 * k), qb0 + (uint64_t)(kb * (kSubQp >> 4) + 2 * k),
-                                idesc2, (t | kb | k) != 0);
+            for (int kb = 0; kb < 2; ++kb) {
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                if (PTMEM)
+                  tc::mma_bf16_ts(tmem_u + 2 * kBN + m * kCP, tmem_u + kTmemP + (NT == 2 ? ta : pb) * (kBN / 2) + (kb * 4 + k) * 8,
+                                  qb0 + tb + (uint64_t)(kb * (kSubQp >> 4) + 2 * k), idesc2, ((NT == 2 ? 0 : t) | pr | kb | k) != 0);
+                else
+                  tc::mma_bf16_ss(tmem_u + 2 * kBN + m * kCP, pa0 + (uint64_t)(kb * (kSubP >> 4) + 2 * k), qb0 + (uint64_t)(kb * (kSubQp >> 4) + 2 * k),
+                                  idesc2, (t | kb | k) != 0);
+              }
             }
           }
           if (m == M - 1) tc::mma_commit(&bars[BAR_KV_EMPTY + s]);   // the key tile has served every row tile
@@ -348,6 +369,11 @@ bank_smooth_tc_kernel(const __grid_constant__ CUtensorMap tm_f, const __grid_con
     }
     __syncwarp();
     uint32_t r[32];
+    uint32_t w[16], wm[16];                                 // packed bf16 pairs of P (hi; split operands: + mid)
+    // Split operands (1e-5 parity bar): the tensor core adds into its fp32 accumulator with truncation, a bias that grows with
+    // the length of the chain (measured 8e-5 after 100 units).  There every unit starts a fresh accumulator (24 MMAs) and the
+    // unit tiles are summed here in registers, round-to-nearest: 8 of the 32 [numer | rowsum] columns of the row per thread.
+    float acc8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     auto exp_pack = [&](int e) {                                                                    // comatch.py:180
       const float s0 = __uint_as_float(r[2 * e]), s1 = __uint_as_float(r[2 * e + 1]);
       float e0, e1;
@@ -361,7 +387,11 @@ bank_smooth_tc_kernel(const __grid_constant__ CUtensorMap tm_f, const __grid_con
         e1 = ex2_approx(x1);
       }
       const __nv_bfloat162 hh = __floats2bfloat162_rn(e0, e1);
-      return *reinterpret_cast<const uint32_t*>(&hh);
+      w[e] = *reinterpret_cast<const uint32_t*>(&hh);
+      if (NT == 2) {                                        // what bf16 dropped, as a second bf16: P = P_hi + P_mid to 2^-17
+        const __nv_bfloat162 mm = __floats2bfloat162_rn(e0 - __low2float(hh), e1 - __high2float(hh));
+        wm[e] = *reinterpret_cast<const uint32_t*>(&mm);
+      }
     };
     for (int j = 0; j < J; ++j) {
       const int b = j & 1;
@@ -369,22 +399,30 @@ bank_smooth_tc_kernel(const __grid_constant__ CUtensorMap tm_f, const __grid_con
       tc::tcgen05_fence_after();
       // keys beyond the bank need no mask: their QpT columns (incl. the ones column) are TMA zero fill.
       // The S read is split in two 16-column loads: the second is in flight during the exponentials of the first.
-      uint32_t w[16];
       tc::tmem_ld_32x16<0>(lane_addr + b * kBN + colq * 32, r);
       tc::tmem_ld_wait(r);
       tc::tmem_ld_32x16<16>(lane_addr + b * kBN + colq * 32 + 16, r);
 #pragma unroll
-      for (int e = 0; e < 8; ++e) w[e] = exp_pack(e);
+      for (int e = 0; e < 8; ++e) exp_pack(e);
       tc::tmem_ld_wait(r);
       tc::tcgen05_fence_before();
       tc::mbar_arrive_warp(&bars[BAR_S_EMPTY + b], lane);   // S[b] is in registers: GEMM1 of unit j+2 may overwrite it
 #pragma unroll
-      for (int e = 8; e < 16; ++e) w[e] = exp_pack(e);
-      // the P buffer of unit j-2 must have been consumed -- only now, after the exponentials
-      if (j >= 2) tc::mbar_wait(&bars[BAR_P_EMPTY + b], ((j >> 1) - 1) & 1, abort_flag);
+      for (int e = 8; e < 16; ++e) exp_pack(e);
+      // the P buffer this unit writes must have been consumed (unit j-2; split operands: j-1) -- only now, after the exponentials
+      const int pb = NT == 2 ? 0 : b;
+      if (NT == 2 ? j >= 1 : j >= 2) tc::mbar_wait(&bars[BAR_P_EMPTY + pb], (NT == 2 ? j - 1 : (j >> 1) - 1) & 1, abort_flag);
+      if (NT == 2 && j >= 1) {                              // GEMM2 of unit j-1 has retired: bank its [numer | rowsum] tile (see acc8)
+        uint32_t t8[8];
+        tc::tcgen05_fence_after();
+        tc::tmem_ld_32x8(lane_addr + 2 * kBN + colq * 8, t8);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc8[i] += __uint_as_float(t8[i]);
+      }
       if (PTMEM) {
         tc::tcgen05_fence_after();
-        tc::tmem_st_32x16(lane_addr + kTmemP + b * (kBN / 2) + colq * 16, w);
+        tc::tmem_st_32x16(lane_addr + kTmemP + (NT == 2 ? 0 : b) * (kBN / 2) + colq * 16, w);
+        if (NT == 2) tc::tmem_st_32x16(lane_addr + kTmemP + (kBN / 2) + colq * 16, wm);
         tc::tmem_st_wait();
         tc::tcgen05_fence_before();
       } else {
@@ -392,13 +430,21 @@ bank_smooth_tc_kernel(const __grid_constant__ CUtensorMap tm_f, const __grid_con
         for (int q = 0; q < 4; ++q) tc::st_shared_v4(p_off[q] + b * kTileP, w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
         tc::fence_proxy_async_smem();               // generic-proxy writes of P -> visible to the tensor core
       }
-      tc::mbar_arrive_warp(&bars[BAR_P_FULL + b], lane);
+      tc::mbar_arrive_warp(&bars[BAR_P_FULL + pb], lane);
     }
     if (threadIdx.x == 64) B200SSL_STAMP(p.dbg, cta, 4);   // last exp tile done
     tc::mbar_wait(&bars[BAR_ACC], 0, abort_flag);           // all MMAs retired: pipeline smem is free, accumulators final
     if (threadIdx.x == 64) B200SSL_STAMP(p.dbg, cta, 5);
     tc::tcgen05_fence_after();
-    if (colq < M) {                                         // warp group colq stages row tile colq: [numer | rowsum] -> fp32 tile
+    if (NT == 2) {                                          // last unit's tile, then this thread's 8 columns of the (single) row tile
+      uint32_t t8[8];
+      tc::tmem_ld_32x8(lane_addr + 2 * kBN + colq * 8, t8);
+      float4* dst = reinterpret_cast<float4*>(sRed + (size_t)r_in * kRedLd + colq * 8);
+      dst[0] = make_float4(acc8[0] + __uint_as_float(t8[0]), acc8[1] + __uint_as_float(t8[1]), acc8[2] + __uint_as_float(t8[2]),
+                           acc8[3] + __uint_as_float(t8[3]));
+      dst[1] = make_float4(acc8[4] + __uint_as_float(t8[4]), acc8[5] + __uint_as_float(t8[5]), acc8[6] + __uint_as_float(t8[6]),
+                           acc8[7] + __uint_as_float(t8[7]));
+    } else if (colq < M) {                                  // warp group colq stages row tile colq: [numer | rowsum] -> fp32 tile
       uint32_t r[32];
       tc::tmem_ld_32x32(lane_addr + 2 * kBN + colq * kCP, r);
       tc::tmem_ld_wait();
@@ -557,6 +603,50 @@ bank_smooth_tc_kernel(const __grid_constant__ CUtensorMap tm_f, const __grid_con
   }
 }
 
+// ---- fp32 storage -> bf16 hi + mid operands (one launch per K3 call; 2^-17 relative per element) -------------------------
+// x = hi + mid + O(2^-17 |x|): hi = bf16(x), mid = bf16(x - hi).  Rows of the queries and of the bank become [hi(64) | mid(64)]
+// (term tt of a row = TMA columns [64 tt, +64)); the probabilities become the transposed, class-padded [2][32][Kp] with the
+// ones row (-> row sums) in term 0.
+struct SplitParams {
+  const float* f; long long rows; __nv_bfloat16* f2;        // queries [rows, 64] -> [rows, 128]
+  const float* qf; long long K; __nv_bfloat16* qf2;         // bank    [K, 64]    -> [K, 128]
+  const float* qp; int C; long long Kp; __nv_bfloat16* qpt2; // probs   [K, C]     -> [2][32][Kp]
+};
+
+__device__ __forceinline__ void split8(const float* src, __nv_bfloat16* hi, __nv_bfloat16* mid) {
+  const float4 a = __ldg(reinterpret_cast<const float4*>(src)), b = __ldg(reinterpret_cast<const float4*>(src) + 1);
+  const float x[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+  float h[8], m[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    h[i] = __bfloat162float(__float2bfloat16_rn(x[i]));
+    m[i] = x[i] - h[i];
+  }
+  *reinterpret_cast<uint4*>(hi) = pack16(h, __nv_bfloat16());
+  *reinterpret_cast<uint4*>(mid) = pack16(m, __nv_bfloat16());
+}
+
+__global__ void __launch_bounds__(256) split_operands_kernel(const SplitParams p) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const long long nthreads = (long long)gridDim.x * blockDim.x, tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long nvec = (p.rows + p.K) * 8;                // 8 floats per item
+  for (long long v = tid; v < nvec; v += nthreads) {
+    const long long row = v >> 3;
+    const int c8 = (int)(v & 7) * 8;
+    if (row < p.rows) split8(p.f + row * 64 + c8, p.f2 + row * 128 + c8, p.f2 + row * 128 + 64 + c8);
+    else split8(p.qf + (row - p.rows) * 64 + c8, p.qf2 + (row - p.rows) * 128 + c8, p.qf2 + (row - p.rows) * 128 + 64 + c8);
+  }
+  for (long long k = tid; k < p.Kp; k += nthreads) {        // coalesced over k for every class row
+    for (int c = 0; c < kCP; ++c) {
+      const float x = k < p.K ? (c < p.C ? __ldg(p.qp + k * p.C + c) : c == p.C ? 1.f : 0.f) : 0.f;
+      const __nv_bfloat16 h = __float2bfloat16_rn(x);
+      p.qpt2[(size_t)c * p.Kp + k] = h;
+      p.qpt2[(size_t)(kCP + c) * p.Kp + k] = __float2bfloat16_rn(x - __bfloat162float(h));
+    }
+  }
+}
+
 struct SmoothPlan { int mt, cluster, nouter; };
 
 // A/B aids (tools/k3_tune.py): b200ssl_debug_set_k3 at run time (or B200SSL_K3_MT / B200SSL_K3_POLY in the environment).
@@ -597,7 +687,7 @@ int max_active_clusters(int cl) {
 // Cost of a plan in microseconds (measured constants, profiles/r02_k3_*): a wave of CTAs pays its prologue (barrier init,
 // TMEM allocation, first TMA round trip) and mt * T S-tile units; the DSMEM fold of a cluster and the ticketed global fold
 // of `no` partials come on top.  Waves are counted in CLUSTERS the chip can hold at once.
-double plan_cost(long long row_tiles, long long ktiles, int mt, int cl, long long no) {
+double plan_cost(long long row_tiles, long long ktiles, int mt, int cl, long long no, double unit_scale = 1.0) {
   const long long groups = (row_tiles + mt - 1) / mt;
   const long long waves = (groups * no + max_active_clusters(cl) - 1) / max_active_clusters(cl);
   const long long T = (ktiles + cl * no - 1) / (cl * no);
@@ -607,17 +697,31 @@ double plan_cost(long long row_tiles, long long ktiles, int mt, int cl, long lon
   const long long groups_t = kTcThreads / items > 1 ? kTcThreads / items : 1;
   const long long rounds = ((no + groups_t - 1) / groups_t + 7) / 8;
   const double fold = no > 1 ? 3.0 + 0.9 * (double)rounds * (items > kTcThreads ? (double)((items + kTcThreads - 1) / kTcThreads) : 1.0) : 0.0;
-  return (double)waves * (1.8 + 0.62 * (double)mt * (double)T) + 1.5 + (cl > 1 ? 2.5 : 0.5) + fold + 0.4 * (mt - 1);   // + extra query tiles to stage
+  return (double)waves * (1.8 + 0.62 * unit_scale * (double)mt * (double)T) + 1.5 + (cl > 1 ? 2.5 : 0.5) + fold + 0.4 * (mt - 1);   // + extra query tiles to stage
 }
 
 // How a launch is cut: `mt` row tiles per CTA, and per group of row tiles a cluster of `cluster` CTAs (power of two <= 8,
 // folded through DSMEM) times `nouter` clusters (folded through global partials) that share the key tiles.
-SmoothPlan smooth_tc_plan(long long rows, long long ktiles, bool remote) {
+// `nt` = 2 (fp32 storage as bf16 hi + mid): a unit is 36 instead of 12 MMAs, ~1.6 x the time of a bf16 unit.
+SmoothPlan smooth_tc_plan(long long rows, long long ktiles, bool remote, int nt = 1) {
   const long long row_tiles = (rows + kBM - 1) / kBM;
   SmoothPlan best{1, 1, 1};
   double best_cost = 1e300;
   // Shards read over NVLink: one CTA serves every row tile from the key tile it staged, so a remote tile crosses the link
   // once per step (row loop), whenever the row tiles fit one CTA.
+  if (nt == 2) {                                            // split operands: the unit tiles are summed in registers, one row tile per CTA
+    SmoothPlan b1{1, 1, 1};
+    double bc = 1e300;
+    for (int cl = 1; cl <= kMaxCluster; cl *= 2) {
+      if (cl > ktiles) break;
+      const long long no_max = ktiles / cl < 148 ? ktiles / cl : 148;
+      for (long long no = 1; no <= no_max; ++no) {
+        const double c = plan_cost(row_tiles, ktiles, 1, cl, no, 1.6);
+        if (c < bc - 1e-9) { bc = c; b1 = SmoothPlan{1, cl, (int)no}; }
+      }
+    }
+    return b1;
+  }
   const int mt_lo = g_force_mt > 0 ? (g_force_mt < kMaxMT ? g_force_mt : kMaxMT) : (remote && row_tiles <= kMaxMT) ? (int)row_tiles : 1;
   const int mt_hi = (g_force_mt > 0 || (remote && row_tiles <= kMaxMT)) ? mt_lo : kMaxMT;
   for (int mt = mt_lo; mt <= mt_hi; ++mt) {
@@ -628,7 +732,7 @@ SmoothPlan smooth_tc_plan(long long rows, long long ktiles, bool remote) {
       const long long no_max = ktiles / cl < 148 ? ktiles / cl : 148;
       for (long long no = 1; no <= no_max; ++no) {
         if (g_force_nouter > 0 && no != g_force_nouter) continue;
-        const double c = plan_cost(row_tiles, ktiles, mt, cl, no);
+        const double c = plan_cost(row_tiles, ktiles, mt, cl, no, nt == 2 ? 1.6 : 1.0);
         if (c < best_cost - 1e-9) { best_cost = c; best = SmoothPlan{mt, cl, (int)no}; }
       }
     }
@@ -636,15 +740,15 @@ SmoothPlan smooth_tc_plan(long long rows, long long ktiles, bool remote) {
   return best;
 }
 
-template <int NPOLY, bool PTMEM>
+template <int NPOLY, bool PTMEM, int NT = 1>
 cudaError_t launch_smooth(const SmoothTcParams& p, const CUtensorMap& tm_f, const BankMaps& maps, dim3 grid, size_t smem, cudaStream_t stream) {
   static size_t attr_smem = 0;
   if (smem > attr_smem) {
-    cudaError_t e = cudaFuncSetAttribute(bank_smooth_tc_kernel<NPOLY, PTMEM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax);
+    cudaError_t e = cudaFuncSetAttribute(bank_smooth_tc_kernel<NPOLY, PTMEM, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax);
     if (e != cudaSuccess) return e;
     attr_smem = kSmemMax;
   }
-  return launch_pdl(PDL_SMOOTH, bank_smooth_tc_kernel<NPOLY, PTMEM>, grid, dim3(kTcThreads, 1, 1), smem, stream, dim3(1, (unsigned)p.cluster, 1), tm_f,
+  return launch_pdl(PDL_SMOOTH, bank_smooth_tc_kernel<NPOLY, PTMEM, NT>, grid, dim3(kTcThreads, 1, 1), smem, stream, dim3(1, (unsigned)p.cluster, 1), tm_f,
                     maps, p);
 }
 
@@ -665,8 +769,17 @@ size_t smooth_tc_workspace_floats(long long rows, long long bank_rows, int class
   return need;
 }
 
-// bf16, dim 64, classes <= 31, bank rows a multiple of 8: the tensor-core path.
-int bank_smooth_tc(const void* feats, const void* queue_feats, const void* queue_probs_t, long long rows,
+namespace {
+// smem of the split-operand form: 32 KB per query tile, 48 KB per key-tile stage; 3 stages while they fit (mt <= 2), else 2
+constexpr int stages_for_split(int mt) { return mt <= 2 ? 3 : 2; }
+constexpr size_t smem_request_split(int mt) { return 1024 + (size_t)mt * 2 * kTileA + (size_t)stages_for_split(mt) * 2 * (kTileQf + kTileQp) + 512; }
+static_assert(smem_request_split(kMaxMT) <= kSmemMax && smem_request_split(2) <= kSmemMax, "shared memory budget (split operands)");
+static_assert((size_t)kMaxMT * kRedTile <= (size_t)stages_for_split(kMaxMT) * 2 * (kTileQf + kTileQp), "reduction tiles over the drained key stages (split operands)");
+}  // namespace
+
+// dim 64, classes <= 31: the tensor-core path.  nt = 1: bf16 operands (bank rows a multiple of 8).  nt = 2: operands split into
+// bf16 hi + mid -- `feats` / `queue_feats` are [*, 128] bf16, `queue_probs_t` is [2][32][qpt_ld] bf16 (bank_smooth_tc_f32).
+static int bank_smooth_tc_impl(int nt, long long qpt_ld, const void* feats, const void* queue_feats, const void* queue_probs_t, long long rows,
                    long long bank_rows, int classes, float temperature, float* rowsum, float* numer, int rowsum_ld,
                    int numer_ld, const b200ssl_bank_shards* sh, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
   const char* fn = "b200ssl_bank_smooth_partial[tcgen05]";
@@ -683,7 +796,7 @@ int bank_smooth_tc(const void* feats, const void* queue_feats, const void* queue
   p.scale = (float)(1.4426950408889634 / (double)temperature);
   p.s_min = -126.f / p.scale;
   p.rowsum = rowsum; p.numer = numer; p.rowsum_ld = rowsum_ld; p.numer_ld = numer_ld; p.dbg = debug_timing_buffer(PDL_SMOOTH);
-  const SmoothPlan pl = smooth_tc_plan(rows, (long long)p.nseg * p.tps, direct);
+  const SmoothPlan pl = smooth_tc_plan(rows, (long long)p.nseg * p.tps, direct, nt);
   p.mt = pl.mt; p.cluster = pl.cluster; p.nouter = pl.nouter;
   p.nsplit = p.cluster * p.nouter;
   const long long row_tiles = (rows + kBM - 1) / kBM;
@@ -697,13 +810,13 @@ int bank_smooth_tc(const void* feats, const void* queue_feats, const void* queue
   p.part = reinterpret_cast<float*>(static_cast<char*>(workspace) + kWsHeaderBytes);
   CUtensorMap tm_f;
   BankMaps maps;
-  if (int e = tc::make_tmap_bf16_2d(&tm_f, feats, (uint64_t)rows, 64, 128, kBM, 64)) return e;
+  if (int e = tc::make_tmap_bf16_2d(&tm_f, feats, (uint64_t)rows, 64 * nt, 128 * nt, kBM, 64)) return e;
   for (int s = 0; s < kMaxSeg; ++s) {
     const int src = direct ? (s < p.nseg ? s : 0) : (sh ? sh->rank : 0);   // unused entries repeat a valid one (never dereferenced)
     const void* qf = sh ? reinterpret_cast<const void*>(sh->arenas_host[src] + sh->feats_offset) : queue_feats;
     const void* qpt = sh ? reinterpret_cast<const void*>(sh->arenas_host[src] + sh->probs_t_offset) : queue_probs_t;
-    if (int e = tc::make_tmap_bf16_2d(&maps.qf[s], qf, (uint64_t)seg_rows, 64, 128, kBN, 64)) return e;
-    if (int e = tc::make_tmap_bf16_2d(&maps.qpt[s], qpt, kCP, (uint64_t)seg_rows, (uint64_t)seg_rows * 2, kCP, 64)) return e;
+    if (int e = tc::make_tmap_bf16_2d(&maps.qf[s], qf, (uint64_t)seg_rows, 64 * nt, 128 * nt, kBN, 64)) return e;
+    if (int e = tc::make_tmap_bf16_2d(&maps.qpt[s], qpt, kCP * nt, (uint64_t)seg_rows, (uint64_t)(nt == 2 ? qpt_ld : seg_rows) * 2, kCP, 64)) return e;
   }
   static_assert(kSmemMax <= 227 * 1024 && smem_request(2, false) <= 227 * 1024 && smem_request(1, false) <= 227 * 1024, "shared memory budget");
   static_assert((size_t)kMaxMT * kRedTile <= smem_stages(kMaxMT, true) && (size_t)kMaxMT * kRedTile <= smem_stages(kMaxMT, false),
@@ -714,16 +827,70 @@ int bank_smooth_tc(const void* feats, const void* queue_feats, const void* queue
   // its serial ld -> exp -> st -> fence chain per tile, not by the MUFU rate -- so the default is 0; the knob stays for A/B.
   const int npoly = g_force_poly >= 0 ? g_force_poly : 0;
   const dim3 grid((unsigned)groups, (unsigned)p.nsplit, 1);
+  cudaError_t e;
+  if (nt == 2) {
+    p.stages = stages_for_split(p.mt);
+    e = launch_smooth<0, true, 2>(p, tm_f, maps, grid, smem_request_split(p.mt), stream);
+    if (e != cudaSuccess) return fail((int)e, "%s: cudaLaunchKernelEx: %s", fn, cudaGetErrorString(e));
+    return check_launch(fn);
+  }
   p.stages = stages_for(p.mt, g_p_tmem != 0);
   if (g_force_stages >= 3 && g_force_stages < p.stages) p.stages = g_force_stages;
   const size_t smem = smem_request_n(p.mt, p.stages, g_p_tmem != 0);
-  cudaError_t e;
   if (!g_p_tmem) e = npoly >= 8 ? launch_smooth<8, false>(p, tm_f, maps, grid, smem, stream) : launch_smooth<0, false>(p, tm_f, maps, grid, smem, stream);
   else e = npoly >= 16 ? launch_smooth<16, true>(p, tm_f, maps, grid, smem, stream)
            : npoly >= 8 ? launch_smooth<8, true>(p, tm_f, maps, grid, smem, stream)
                         : launch_smooth<0, true>(p, tm_f, maps, grid, smem, stream);
   if (e != cudaSuccess) return fail((int)e, "%s: cudaLaunchKernelEx: %s", fn, cudaGetErrorString(e));
   return check_launch(fn);
+}
+
+int bank_smooth_tc(const void* feats, const void* queue_feats, const void* queue_probs_t, long long rows,
+                   long long bank_rows, int classes, float temperature, float* rowsum, float* numer, int rowsum_ld,
+                   int numer_ld, const b200ssl_bank_shards* sh, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+  return bank_smooth_tc_impl(1, 0, feats, queue_feats, queue_probs_t, rows, bank_rows, classes, temperature, rowsum, numer, rowsum_ld, numer_ld,
+                             sh, workspace, workspace_bytes, stream);
+}
+
+// Room behind the fold partials for the bf16 hi + mid copies of the queries, the bank and the transposed probabilities.
+static size_t split_region(long long rows, long long bank_rows, size_t* off_f2, size_t* off_qf2, size_t* off_qpt2, long long* kp) {
+  const long long Kp = (bank_rows + 7) & ~7LL;              // 16-byte row pitch of the transposed probabilities
+  auto up = [](size_t x) { return (x + 1023) & ~(size_t)1023; };
+  const size_t f2 = up((size_t)rows * 256), qf2 = up((size_t)bank_rows * 256), qpt2 = up((size_t)2 * kCP * Kp * 2);
+  if (off_f2) { *off_f2 = 0; *off_qf2 = f2; *off_qpt2 = f2 + qf2; *kp = Kp; }
+  return f2 + qf2 + qpt2;
+}
+
+size_t smooth_tc_f32_workspace_bytes(long long rows, long long bank_rows, int classes) {
+  size_t part = 0;
+  const SmoothPlan pl = smooth_tc_plan(rows, (bank_rows + kBN - 1) / kBN, false, 2);
+  const long long row_tiles = (rows + kBM - 1) / kBM, groups = (row_tiles + pl.mt - 1) / pl.mt;
+  if (pl.nouter > 1) part = sizeof(float) * (size_t)pl.nouter * groups * pl.mt * kBM * ((1 + classes + 3) & ~3);
+  return ((part + 1023) & ~(size_t)1023) + 2048 + split_region(rows, bank_rows, nullptr, nullptr, nullptr, nullptr);   // + alignment slack of the tail carve
+}
+
+// fp32 storage (the reference's own precision, code/comatch.py:180-181 is a true-fp32 torch.mm): one pre-pass splits the queries,
+// the bank and the probabilities into bf16 hi + mid inside the workspace, then the tensor-core kernel runs on the split operands.
+// dim 64, classes <= 31, any number of bank rows.
+int bank_smooth_tc_f32(const float* feats, const float* queue_feats, const float* queue_probs, long long rows, long long bank_rows,
+                       int classes, float temperature, float* rowsum, float* numer, int rowsum_ld, int numer_ld, void* workspace,
+                       size_t workspace_bytes, cudaStream_t stream) {
+  const char* fn = "b200ssl_bank_smooth_partial[tcgen05, fp32 storage]";
+  const size_t need = kWsHeaderBytes + smooth_tc_f32_workspace_bytes(rows, bank_rows, classes);
+  if (workspace_bytes < need) return fail(B200SSL_E_WORKSPACE, "%s: workspace %zu < %zu bytes", fn, workspace_bytes, need);
+  size_t o_f2, o_qf2, o_qpt2;
+  long long Kp;
+  const size_t split_bytes = split_region(rows, bank_rows, &o_f2, &o_qf2, &o_qpt2, &Kp);
+  char* base = static_cast<char*>(workspace) + ((workspace_bytes - split_bytes) & ~(size_t)1023);    // the tail of the workspace
+  SplitParams sp{feats, rows, reinterpret_cast<__nv_bfloat16*>(base + o_f2), queue_feats, bank_rows,
+                 reinterpret_cast<__nv_bfloat16*>(base + o_qf2), queue_probs, classes, Kp, reinterpret_cast<__nv_bfloat16*>(base + o_qpt2)};
+  const long long items = (rows + bank_rows) * 8;
+  long long blocks = (items + 255) / 256;
+  if (blocks > 8 * kNumSMs) blocks = 8 * kNumSMs;
+  cudaError_t e = launch_pdl(PDL_SMOOTH, split_operands_kernel, dim3((unsigned)blocks), dim3(256), 0, stream, dim3(1, 1, 1), sp);
+  if (e != cudaSuccess) return fail((int)e, "%s: split launch: %s", fn, cudaGetErrorString(e));
+  return bank_smooth_tc_impl(2, Kp, sp.f2, sp.qf2, sp.qpt2, rows, bank_rows, classes, temperature, rowsum, numer, rowsum_ld, numer_ld, nullptr,
+                             workspace, (size_t)(base - static_cast<char*>(workspace)), stream);
 }
 
 }  // namespace b200ssl

@@ -52,6 +52,7 @@ int smooth_nsplit(long long rows, long long bank_rows, int* tiles_per_split);
 int contrast_nsplit(long long rows, int modes, int* tiles_per_split);
 size_t contrast_workspace_floats(long long rows, int dim);
 size_t smooth_tc_workspace_floats(long long rows, long long bank_rows, int classes);
+size_t smooth_tc_f32_workspace_bytes(long long rows, long long bank_rows, int classes);   // fold partials + split operand copies (fp32 storage)
 size_t contrast_tc_workspace_floats(long long rows);
 
 // ---- programmatic dependent launch (PDL) -------------------------------------

@@ -445,6 +445,34 @@ def test_bank_smooth_partial_vs_oracle(pkg, rows, K, D):
     assert rel_err(numer, A @ qp.double()) < FP32_TOL
 
 
+@pytest.mark.parametrize("simt", [0, 1])
+@pytest.mark.parametrize("rows,K", [(448, 2560), (300, 20003), (1000, 65536)])
+def test_bank_smooth_fp32_storage_both_paths(pkg, rows, K, simt):
+    """fp32 storage (the reference's precision, comatch.py:180-181): the tensor-core kernel on bf16 hi + mid operands
+    (csrc/bank_tc.cu, default) and the exact-fp32 FFMA tiles (csrc/bank.cu) both meet the 1e-5 bar against fp64 math --
+    ragged K (not a multiple of the key tile or of 8), a long bank (the per-unit accumulator flush), clustered embeddings."""
+    from endoscopy_image_classification_b200 import _native as N
+    g = torch.Generator().manual_seed(rows + K)
+    protos = torch.nn.functional.normalize(torch.randn(C, 64, generator=g), dim=1)
+    lab = torch.randint(0, C, (K,), generator=g)
+    qf = torch.nn.functional.normalize(protos[lab] + 0.35 * torch.randn(K, 64, generator=g), dim=1)
+    f = torch.nn.functional.normalize(protos[torch.randint(0, C, (rows,), generator=g)] + 0.35 * torch.randn(rows, 64, generator=g), dim=1)
+    qp = torch.softmax(3.0 * torch.randn(K, C, generator=g) + 4.0 * torch.nn.functional.one_hot(lab, C), 1)
+    head = pkg["head"].CoMatchHead(C, 64, K, 0.9, enqueue_mode="always")
+    head.queue_feats.copy_(qf)
+    head.queue_probs.copy_(qp)
+    N.lib().b200ssl_debug_set_k3_f32_simt(simt)
+    try:
+        rowsum, numer = head._k_smooth(f.cuda())
+        torch.cuda.synchronize()
+    finally:
+        N.lib().b200ssl_debug_set_k3_f32_simt(0)
+    A = torch.exp(f.double() @ qf.double().t() / 0.2)
+    assert rel_err(rowsum, A.sum(1)) < FP32_TOL
+    assert rel_err(numer, A @ qp.double()) < FP32_TOL
+    assert rel_err(numer.double().cpu() / rowsum.double().cpu().unsqueeze(1), (A @ qp.double()) / A.sum(1, keepdim=True)) < FP32_TOL
+
+
 @pytest.mark.parametrize("rows,D", [(448, 64), (1, 8), (63, 16), (65, 64), (1000, 128), (3584, 64)])
 def test_contrast_fwd_bwd_vs_oracle(pkg, rows, D):
     g = torch.Generator().manual_seed(rows * 7 + D)
