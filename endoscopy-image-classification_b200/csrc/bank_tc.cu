@@ -395,10 +395,11 @@ bank_smooth_tc_kernel(const __grid_constant__ CUtensorMap tm_f, const __grid_con
     };
     for (int j = 0; j < J; ++j) {
       const int b = j & 1;
-      tc::mbar_wait(&bars[BAR_S_FULL + b], (j >> 1) & 1, abort_flag);
-      tc::tcgen05_fence_after();
       // keys beyond the bank need no mask: their QpT columns (incl. the ones column) are TMA zero fill.
       // The S read is split in two 16-column loads: the second is in flight during the exponentials of the first.
+      // (issuing the first half of unit j+1 ahead of the P store of unit j was measured 15 % SLOWER, twice: r02_k3_experiments.md)
+      tc::mbar_wait(&bars[BAR_S_FULL + b], (j >> 1) & 1, abort_flag);
+      tc::tcgen05_fence_after();
       tc::tmem_ld_32x16<0>(lane_addr + b * kBN + colq * 32, r);
       tc::tmem_ld_wait(r);
       tc::tmem_ld_32x16<16>(lane_addr + b * kBN + colq * 32 + 16, r);
@@ -900,7 +901,7 @@ extern "C" void b200ssl_debug_set_k3(int32_t row_tiles_per_cta, int32_t cluster,
   b200ssl::g_force_cluster = cluster;
   b200ssl::g_force_nouter = clusters_per_row_group;
   // poly_of_32 < 0: defaults; otherwise exponentials (of 32) on the FMA pipe, + 100: P through shared memory (A/B)
-  b200ssl::g_p_tmem = poly_of_32 < 0 ? 1 : (poly_of_32 / 100 == 0);
+  b200ssl::g_p_tmem = poly_of_32 < 0 ? 1 : (poly_of_32 / 100 != 1);
   b200ssl::g_force_poly = poly_of_32 < 0 ? -1 : poly_of_32 % 100;
 }
 

@@ -7,16 +7,17 @@
 // into TMEM (S: columns 0..127, Q: 128..255).  Q uses the bf16 hi/lo split of the fp32
 // pseudo-label probabilities (probs_hl [rows, 64] = [hi(32) | lo(32)], written by the
 // finalize kernel) so the 0.8 graph threshold sees ~fp32 accuracy although the operands
-// are bf16.  256 epilogue threads (two per TMEM lane, 64 columns each) read S/Q with
-// tcgen05.ld and do the exp / threshold / log math.
+// are bf16.  512 epilogue threads (four per TMEM lane, 32 columns each) read S/Q with
+// tcgen05.ld and do the exp / threshold / log math; the MMA warp runs in warp-uniform control
+// flow and issues from one elected lane (tc::elect_one: operands stay in uniform registers).
 //
 // One thread-block CLUSTER owns one 128-row strip; its CTAs split the streamed dimension
 // and exchange their per-row partials through distributed shared memory, in rank order
 // (deterministic, no global round trips, no atomics):
 //   forward (one launch):  pass A  rowsum_i = sum_j exp(S/tau), qsum_i = sum_j Qm
 //                          -- cluster exchange --
-//                          pass B  loss_i, r_i   (exp/log only where Qm != 0; with one tile
-//                                  per CTA the S/Q tile is simply re-read from TMEM)
+//                          pass B  loss_i, r_i   (dense: exp / log / rcp for every element; with one
+//                                  tile per CTA the S/Q tile is simply re-read from TMEM)
 //   backward (one launch): dZ = P o (G - r) -> bf16 hi + lo -> swizzled smem -> third MMA group
 //                          blockIdx.z = 0: dF0_i += dZ F1_j      (A = dZ K-major,  B = F1 tile MN-major)
 //                          blockIdx.z = 1: dF1_j += dZ^T F0_i    (A = dZ MN-major, B = F0 tile MN-major)
@@ -33,18 +34,21 @@ namespace {
 namespace cg = cooperative_groups;
 
 constexpr int kT = 128;                       // tile edge (UMMA M and N)
-constexpr int kCtThreads = 320;               // warp 0 TMA/alloc, warp 1 MMA, warps 2..9 epilogue
+constexpr int kCtEpiWarps = 16;               // 4 per TMEM lane quarter: each thread owns 32 of the 128 columns of its row
+constexpr int kCtThreads = 64 + 32 * kCtEpiWarps;   // warp 0 TMA/alloc, warp 1 MMA, warps 2..17 epilogue
 constexpr int kMaxCl = 8;
 constexpr uint32_t kTileF = kT * 128;         // 16 KB: [128][64] bf16
 constexpr uint32_t kStageBytes = 2 * kTileF;  // F tile + probs hi/lo tile
 constexpr uint32_t kSubZ = kT * 128;          // 16 KB: dZ columns [64*kb, +64)
 constexpr uint32_t kSmemCt = 2 * kTileF + 2 * kStageBytes + 4 * kSubZ;   // 160 KB (dZ is kept as a bf16 hi + lo pair)
-constexpr size_t kSmemCtRequest = kSmemCt + 1024 + 512 + 2 * kMaxCl * 4 * kT * sizeof(float);   // + two [8][4][128] exchange areas
-constexpr uint32_t kTmemColsCt = 512;         // S 0..127, Q 128..255, dF accumulator 256..319
+constexpr int kStatRows = 8;                  // per source rank: [value 0/1][column group 0..3][128 rows]
+constexpr size_t kSmemCtRequest = kSmemCt + 1024 + 512 + 2 * kMaxCl * kStatRows * kT * sizeof(float);   // + two [8][8][128] exchange areas (225.5 KB)
+static_assert(kSmemCtRequest <= 227 * 1024, "shared memory budget");
+constexpr uint32_t kTmemColsCt = 512;         // S 0..127, Q 128..255; forward: second S/Q buffer 256..511; backward: dF accumulator 256..319
 constexpr int kAccLd = 68;                    // floats per row of the staged accumulator (16-byte rows, bank spread)
 
-enum { CB_OWN = 0, CB_KV_FULL = 1, CB_KV_EMPTY = 3, CB_SQ_FULL = 5, CB_SQ_EMPTY = 6, CB_Z_FULL = 7, CB_Z_EMPTY = 8,
-       CB_ACC = 9, CB_COUNT = 10 };
+enum { CB_OWN = 0, CB_KV_FULL = 1, CB_KV_EMPTY = 3, CB_SQ_FULL = 5, CB_SQ_EMPTY = 7, CB_Z_FULL = 9, CB_Z_EMPTY = 10,
+       CB_ACC = 11, CB_COUNT = 12 };     // SQ_FULL / SQ_EMPTY: two S/Q buffers in the forward, one (index 0) in the backward
 
 struct ContrastTcParams {
   long long rows;
@@ -56,7 +60,6 @@ struct ContrastTcParams {
   const float* loss_u; float lambda_u, lambda_c; float* total_out;
   const float* upstream; float factor; void* g0; void* g1;
   unsigned long long* dbg;
-  int dense_b;            // forward pass B: dense math instead of the compaction list (A/B knob)
   // optional piggy-backed task of the backward launch: sgrad[i] *= (*sup) * sfactor  (the stashed focal-CE gradient)
   __nv_bfloat16* sgrad; long long snumel; const float* sup; float sfactor;
 };
@@ -64,6 +67,13 @@ struct ContrastTcParams {
 __device__ __forceinline__ float ex2a(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float lg2a(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float rcpa(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+// 1 / x for x > 0 on the FMA pipe (the epilogues are bound by the MUFU unit): exponent-flip seed (12 % off) and two Newton
+// steps -> 2.4e-4 relative, inside the bf16 kernels' 1e-2 budget by 40 x
+__device__ __forceinline__ float rcp_fma(float x) {
+  float y = __uint_as_float(0x7EF311C7u - __float_as_uint(x));
+  y = y * fmaf(-x, y, 2.0f);
+  return y * fmaf(-x, y, 2.0f);
+}
 
 // kind::f16 instruction descriptor with explicit operand majors (0 = K-major, 1 = MN-major)
 __host__ __device__ constexpr uint32_t idesc_bf16(int M, int N, int a_mn, int b_mn) {
@@ -86,7 +96,7 @@ struct Smem {
   uint64_t* bars;
   uint32_t* tmem_slot;
   volatile int* abort_flag;
-  float* stat;            // [2 passes][8 source ranks][4][128]: per-row partials (value 0/1 x half 0/1) pushed by the cluster
+  float* stat;            // [2 passes][8 source ranks][8][128]: per-row partials (value 0/1 x column group 0..3) pushed by the cluster
 };
 
 __device__ __forceinline__ Smem carve(uint8_t* smem_raw) {
@@ -111,9 +121,11 @@ __device__ __forceinline__ uint32_t setup(const Smem& sm, int warp, int lane, co
       tc::mbar_init(&sm.bars[CB_KV_FULL + s], 1);
       tc::mbar_init(&sm.bars[CB_KV_EMPTY + s], 1);
     }
-    tc::mbar_init(&sm.bars[CB_SQ_FULL], 1);
-    tc::mbar_init(&sm.bars[CB_SQ_EMPTY], 256);
-    tc::mbar_init(&sm.bars[CB_Z_FULL], 256);
+    for (int s = 0; s < 2; ++s) {
+      tc::mbar_init(&sm.bars[CB_SQ_FULL + s], 1);
+      tc::mbar_init(&sm.bars[CB_SQ_EMPTY + s], kCtEpiWarps);  // one arrival per epilogue warp
+    }
+    tc::mbar_init(&sm.bars[CB_Z_FULL], kCtEpiWarps);
     tc::mbar_init(&sm.bars[CB_Z_EMPTY], 1);
     tc::mbar_init(&sm.bars[CB_ACC], 1);
     *sm.abort_flag = 0;
@@ -133,11 +145,15 @@ __device__ __forceinline__ uint32_t setup(const Smem& sm, int warp, int lane, co
 }
 
 // S = A_F B_F^T (4 MMAs) and Q = hi.hi + hi.lo + lo.hi (6 MMAs) into TMEM columns [0,128) and [128,256)
-__device__ __forceinline__ void issue_sq(uint32_t tmem, const uint8_t* aFp, const uint8_t* bFp, const uint8_t* aPp,
-                                         const uint8_t* bPp) {
+struct SqDesc { uint64_t aF, bF, aP, bP; };
+// built by every lane of the MMA warp (warp-uniform values), consumed by the elected issuer
+__device__ __forceinline__ SqDesc sq_desc(const uint8_t* aFp, const uint8_t* bFp, const uint8_t* aPp, const uint8_t* bPp) {
+  return SqDesc{tc::smem_desc_sw128(tc::smem_u32(aFp)), tc::smem_desc_sw128(tc::smem_u32(bFp)),
+                tc::smem_desc_sw128(tc::smem_u32(aPp)), tc::smem_desc_sw128(tc::smem_u32(bPp))};
+}
+__device__ __forceinline__ void issue_sq(uint32_t tmem, const SqDesc& d) {
   constexpr uint32_t idesc_sq = idesc_bf16(kT, kT, 0, 0);
-  const uint64_t aF = tc::smem_desc_sw128(tc::smem_u32(aFp)), bF = tc::smem_desc_sw128(tc::smem_u32(bFp));
-  const uint64_t aP = tc::smem_desc_sw128(tc::smem_u32(aPp)), bP = tc::smem_desc_sw128(tc::smem_u32(bPp));
+  const uint64_t aF = d.aF, bF = d.bF, aP = d.aP, bP = d.bP;
 #pragma unroll
   for (int k = 0; k < 4; ++k) tc::mma_bf16_ss(tmem, aF + 2 * k, bF + 2 * k, idesc_sq, k > 0);
   // hi = columns 0..31 (byte 0), lo = columns 32..63 (byte 64 -> +4 descriptor units)
@@ -156,7 +172,7 @@ contrast_tc_fwd_kernel(const __grid_constant__ CUtensorMap tm_f0, const __grid_c
                        const __grid_constant__ CUtensorMap tm_ph, const ContrastTcParams p) {
   extern __shared__ uint8_t smem_raw[];
   const Smem sm = carve(smem_raw);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;   // warp-uniform for the compiler
   const int own_tile = blockIdx.x, CL = p.cluster;
   cg::cluster_group cluster = cg::this_cluster();
   const int crank = CL > 1 ? (int)cluster.block_rank() : 0;
@@ -169,96 +185,70 @@ contrast_tc_fwd_kernel(const __grid_constant__ CUtensorMap tm_f0, const __grid_c
   const uint32_t tmem = setup(sm, warp, lane, &tm_f0, &tm_f1, &tm_ph);
   if (threadIdx.x == 0) B200SSL_STAMP(p.dbg, ctaid, 0);
   if (threadIdx.x == 0) B200SSL_STAMP(p.dbg, ctaid, 1);
-  float* statA = sm.stat;                                   // [src rank][4][128]
-  float* statB = sm.stat + kMaxCl * 4 * kT;
+  float* statA = sm.stat;                                   // [src rank][8][128]
+  float* statB = sm.stat + kMaxCl * kStatRows * kT;
 
-  // per-thread epilogue state (valid in warps 2..9)
-  const int quarter = warp & 3, half = (warp - 2) >> 2;
+  // per-thread epilogue state (valid in warps 2..17)
+  const int quarter = warp & 3, colq = (warp - 2) >> 2;
   const int r_in = quarter * 32 + lane;
   const uint32_t lane_addr = tmem + ((uint32_t)(quarter * 32) << 16);
   const long long gi = (long long)own_tile * kT + r_in;
   float inv_rs = 1.f, inv_qs = 1.f;
 
-  // Positives of the pseudo-label graph are ~1/classes dense: pass B first compacts (s, qm) of the positive
-  // columns into a shared-memory list (static register indices on the read side, conflict-free [slot][thread]
-  // layout), then runs the exp / log / rcp math only over that list.
-  float2* plist = reinterpret_cast<float2*>(sm.z);           // [32 (+1 scratch)][256] float2 <= 66 KB (the dZ buffers are idle in fwd)
-  const int et = threadIdx.x - 64;                          // epilogue thread index 0..255
   const int rows_i = (int)p.rows, gi_i = (int)gi;
-  auto epilogue_tile = [&](int pass, long long j0ll, float& a0, float& a1) {
+  auto epilogue_tile = [&](int pass, int buf, long long j0ll, float& a0, float& a1) {
     const int j0 = (int)j0ll;
+    const uint32_t sq_addr = lane_addr + buf * (2 * kT);
     // interior tile: every (row, column) is inside the matrix and off the diagonal -> no per-element checks
     const bool interior = (own_tile * kT + kT <= rows_i) && (j0 + kT <= rows_i) && (j0 != own_tile * kT);
 #pragma unroll 1
-    for (int c2 = 0; c2 < 2; ++c2) {
-      const int col0 = half * 64 + c2 * 32;
-      uint32_t sv[32], qv[32];
-      tc::tmem_ld_32x32(lane_addr + col0, sv);
-      tc::tmem_ld_32x32(lane_addr + kT + col0, qv);
-      tc::tmem_ld_wait();
-      if (pass == 0) {
-        if (interior) {
+    for (int h = 0; h < 2; ++h) {                           // 2 x 16 columns: S and Q of a half fit the register budget (96 at 576 threads)
+    const int col0 = colq * 32 + h * 16;
+    uint32_t sv[32], qv[32];                                // (entries 0..15 used)
+    tc::tmem_ld_32x16<0>(sq_addr + col0, sv);
+    tc::tmem_ld_32x16<0>(sq_addr + kT + col0, qv);
+    tc::tmem_ld_wait(sv);
+    tc::tmem_ld_wait(qv);
+    if (pass == 0) {
+      if (interior) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const float q = __uint_as_float(qv[j]);
-            a0 += ex2a(__uint_as_float(sv[j]) * p.scale);                         // comatch.py:200
-            a1 += (q >= p.th) ? q : 0.f;                                          // :206-208
-          }
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const int gj = j0 + col0 + j;
-            const bool ok = (gi_i < rows_i) && (gj < rows_i);
-            float q = __uint_as_float(qv[j]);
-            q = (gi_i == gj) ? 1.f : q;                                           // fill_diagonal_(1)  :205
-            a0 += ok ? ex2a(__uint_as_float(sv[j]) * p.scale) : 0.f;
-            a1 += (ok && q >= p.th) ? q : 0.f;
-          }
-        }
-      } else if (p.dense_b) {
-        // pass B without the compaction: every element pays the exp / log / rcp (3 MUFU ops) but there is no serial
-        // list-building chain and no divergent loop over the positives
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          float q = __uint_as_float(qv[j]);
-          bool pos;
-          if (interior) {
-            pos = q >= p.th;
-          } else {
-            const int gj = j0 + col0 + j;
-            q = (gi_i == gj) ? 1.f : q;
-            pos = (gi_i < rows_i) && (gj < rows_i) && (q >= p.th);
-          }
-          const float P = ex2a(__uint_as_float(sv[j]) * p.scale) * inv_rs;              // :201
-          const float qn = pos ? q * inv_qs : 0.f;                                      // :209
-          a0 -= lg2a(P + 1e-7f) * 0.6931471805599453f * qn;                             // :212
-          a1 += qn * P * rcpa(P + 1e-7f);
+        for (int j = 0; j < 16; ++j) {
+          const float q = __uint_as_float(qv[j]);
+          a0 += ex2a(__uint_as_float(sv[j]) * p.scale);                           // comatch.py:200
+          a1 += (q >= p.th) ? q : 0.f;                                            // :206-208
         }
       } else {
-        int cnt = 0;
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
+        for (int j = 0; j < 16; ++j) {
           const int gj = j0 + col0 + j;
+          const bool ok = (gi_i < rows_i) && (gj < rows_i);
           float q = __uint_as_float(qv[j]);
-          bool pos;
-          if (interior) {
-            pos = q >= p.th;
-          } else {
-            q = (gi_i == gj) ? 1.f : q;
-            pos = (gi_i < rows_i) && (gj < rows_i) && (q >= p.th);
-          }
-          plist[cnt * 256 + et] = make_float2(__uint_as_float(sv[j]), q);   // branch-free: the slot is simply
-          cnt += pos ? 1 : 0;                                               // re-used when this column is no positive
-        }
-        if (threadIdx.x == 64) B200SSL_STAMP(p.dbg, ctaid, 10 + c2);           // positives of this chunk compacted
-        for (int k = 0; k < cnt; ++k) {
-          const float2 sq = plist[k * 256 + et];
-          const float P = ex2a(sq.x * p.scale) * inv_rs;                          // :201
-          const float qn = sq.y * inv_qs;                                         // :209
-          a0 -= lg2a(P + 1e-7f) * 0.6931471805599453f * qn;                       // :212
-          a1 += qn * P * rcpa(P + 1e-7f);
+          q = (gi_i == gj) ? 1.f : q;                                             // fill_diagonal_(1)  :205
+          a0 += ok ? ex2a(__uint_as_float(sv[j]) * p.scale) : 0.f;
+          a1 += (ok && q >= p.th) ? q : 0.f;
         }
       }
+    } else {
+      // pass B, dense: every element pays exp / log (2 MUFU ops; the reciprocal runs on the FMA pipe); the positives of the pseudo-label graph are only
+      // ~1/classes of them, but compacting them first (a shared-memory list per thread, round 2) cost 2.5 x more than
+      // the arithmetic it saved
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        float q = __uint_as_float(qv[j]);
+        bool pos;
+        if (interior) {
+          pos = q >= p.th;
+        } else {
+          const int gj = j0 + col0 + j;
+          q = (gi_i == gj) ? 1.f : q;
+          pos = (gi_i < rows_i) && (gj < rows_i) && (q >= p.th);
+        }
+        const float P = ex2a(__uint_as_float(sv[j]) * p.scale) * inv_rs;                // :201
+        const float qn = pos ? q * inv_qs : 0.f;                                        // :209
+        a0 -= lg2a(P + 1e-7f) * 0.6931471805599453f * qn;                               // :212
+        a1 += qn * P * rcp_fma(P + 1e-7f);
+      }
+    }
     }
   };
 
@@ -283,54 +273,59 @@ contrast_tc_fwd_kernel(const __grid_constant__ CUtensorMap tm_f0, const __grid_c
         }
       }
     } else if (warp == 1) {
-      if (lane == 0) {
-        if (phase == 0) tc::mbar_wait(&sm.bars[CB_OWN], 0, sm.abort_flag);
-        for (int u = u_begin; u < u_end; ++u) {
-          const int s = u & 1;
-          tc::mbar_wait(&sm.bars[CB_KV_FULL + s], (u >> 1) & 1, sm.abort_flag);
-          if (u >= 1) tc::mbar_wait(&sm.bars[CB_SQ_EMPTY], (u - 1) & 1, sm.abort_flag);
-          tc::tcgen05_fence_after();
-          const uint8_t* stF = sm.stage + s * kStageBytes;
-          issue_sq(tmem, sm.ownF, stF, sm.ownP, stF + kTileF);
-          tc::mma_commit(&sm.bars[CB_SQ_FULL]);
+      // the whole warp runs the loop (warp-uniform control flow), one elected lane issues the MMAs
+      const bool leader = tc::elect_one();
+      const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem, 0);
+      if (phase == 0) tc::mbar_wait(&sm.bars[CB_OWN], 0, sm.abort_flag);
+      for (int u = u_begin; u < u_end; ++u) {
+        const int s = u & 1;                                // key-tile stage and S/Q buffer of this visit
+        tc::mbar_wait(&sm.bars[CB_KV_FULL + s], (u >> 1) & 1, sm.abort_flag);
+        if (u >= 2) tc::mbar_wait(&sm.bars[CB_SQ_EMPTY + s], ((u >> 1) - 1) & 1, sm.abort_flag);   // S/Q of visit u-2 consumed
+        tc::tcgen05_fence_after();
+        const uint8_t* stF = sm.stage + s * kStageBytes;
+        const SqDesc d = sq_desc(sm.ownF, stF, sm.ownP, stF + kTileF);
+        if (leader) {
+          issue_sq(tmem_u + s * (2 * kT), d);              // the MMAs of visit u+1 run under the epilogue of visit u
+          tc::mma_commit(&sm.bars[CB_SQ_FULL + s]);
           tc::mma_commit(&sm.bars[CB_KV_EMPTY + s]);
         }
+        __syncwarp();
       }
     } else {
       if (phase == 1) {                                     // full row statistics from every CTA of the cluster
         float rs = 0.f, qs = 0.f;
         for (int r = 0; r < CL; ++r) {                      // pushed by every rank before the cluster sync: local reads
-          const float* st = statA + r * 4 * kT;
-          rs += st[0 * kT + r_in] + st[1 * kT + r_in];
-          qs += st[2 * kT + r_in] + st[3 * kT + r_in];
+          const float* st = statA + r * kStatRows * kT;
+          rs += (st[0 * kT + r_in] + st[1 * kT + r_in]) + (st[2 * kT + r_in] + st[3 * kT + r_in]);
+          qs += (st[4 * kT + r_in] + st[5 * kT + r_in]) + (st[6 * kT + r_in] + st[7 * kT + r_in]);
         }
         inv_rs = 1.0f / rs;
         inv_qs = 1.0f / qs;
-        if (half == 0 && crank == 0 && gi < p.rows) { p.stats[gi] = rs; p.stats[p.rows + gi] = qs; }
+        if (colq == 0 && crank == 0 && gi < p.rows) { p.stats[gi] = rs; p.stats[p.rows + gi] = qs; }
         a0 = a1 = 0.f;
         if (threadIdx.x == 64) B200SSL_STAMP(p.dbg, ctaid, 9);                // row statistics assembled
         if (T == 1) {                                       // the only S/Q tile of this CTA is still in TMEM
           tc::tcgen05_fence_after();
-          epilogue_tile(1, t0 * kT, a0, a1);
+          epilogue_tile(1, 0, t0 * kT, a0, a1);
         }
       }
       for (int u = u_begin; u < u_end; ++u) {
-        tc::mbar_wait(&sm.bars[CB_SQ_FULL], u & 1, sm.abort_flag);
+        tc::mbar_wait(&sm.bars[CB_SQ_FULL + (u & 1)], (u >> 1) & 1, sm.abort_flag);
         if (u == 0 && threadIdx.x == 64) B200SSL_STAMP(p.dbg, ctaid, 2);     // first S/Q tile ready (TMA + 10 MMAs)
         tc::tcgen05_fence_after();
-        epilogue_tile(phase, (t0 + (u % T)) * kT, a0, a1);
+        epilogue_tile(phase, u & 1, (t0 + (u % T)) * kT, a0, a1);
         tc::tcgen05_fence_before();
-        if (!(T == 1)) tc::mbar_arrive(&sm.bars[CB_SQ_EMPTY]);
+        if (!(T == 1)) tc::mbar_arrive_warp(&sm.bars[CB_SQ_EMPTY + (u & 1)], lane);
       }
       // push the per-row partials: pass A to every CTA of the cluster (all need the full row statistics),
       // pass B only to the CTA that folds this row
       const int RBx = kT / CL;
       for (int r = 0; r < CL; ++r) {
         if (phase == 1 && r != r_in / RBx) continue;
-        float* st = (phase == 0 ? statA : statB) + crank * 4 * kT;
+        float* st = (phase == 0 ? statA : statB) + crank * kStatRows * kT;
         if (CL > 1) st = cluster.map_shared_rank(st, r);
-        st[(0 + half) * kT + r_in] = a0;
-        st[(2 + half) * kT + r_in] = a1;
+        st[(0 + colq) * kT + r_in] = a0;
+        st[(4 + colq) * kT + r_in] = a1;
       }
       if (threadIdx.x == 64) B200SSL_STAMP(p.dbg, ctaid, 3 + 2 * phase);     // pass A (3) / pass B (5) done
     }
@@ -344,9 +339,9 @@ contrast_tc_fwd_kernel(const __grid_constant__ CUtensorMap tm_f0, const __grid_c
     const int row = crank * RB + threadIdx.x;
     float li = 0.f, rr = 0.f;
     for (int r = 0; r < CL; ++r) {                          // rank order, local reads
-      const float* st = statB + r * 4 * kT;
-      li += st[0 * kT + row] + st[1 * kT + row];
-      rr += st[2 * kT + row] + st[3 * kT + row];
+      const float* st = statB + r * kStatRows * kT;
+      li += (st[0 * kT + row] + st[1 * kT + row]) + (st[2 * kT + row] + st[3 * kT + row]);
+      rr += (st[4 * kT + row] + st[5 * kT + row]) + (st[6 * kT + row] + st[7 * kT + row]);
     }
     const long long g = (long long)own_tile * kT + row;
     if (g < p.rows) {
@@ -419,7 +414,7 @@ contrast_tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_f0, const __grid_c
   }
   extern __shared__ uint8_t smem_raw[];
   const Smem sm = carve(smem_raw);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;   // warp-uniform for the compiler
   const bool colmode = blockIdx.z == 1;                     // own tile = j rows of F1
   const int own_tile = blockIdx.x, CL = p.cluster;
   cg::cluster_group cluster = cg::this_cluster();
@@ -449,50 +444,66 @@ contrast_tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_f0, const __grid_c
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc_row = idesc_bf16(kT, 64, 0, 1);    // dF0: A = dZ (K-major),  B = F1 tile (MN-major)
-      constexpr uint32_t idesc_col = idesc_bf16(kT, 64, 1, 1);    // dF1: A = dZ (MN-major), B = F0 tile (MN-major)
-      tc::mbar_wait(&sm.bars[CB_OWN], 0, sm.abort_flag);
-      for (int t = 0; t < T; ++t) {
-        const int s = t & 1;
-        const uint8_t* stF = sm.stage + s * kStageBytes;
-        const uint8_t* stP = stF + kTileF;
-        tc::mbar_wait(&sm.bars[CB_KV_FULL + s], (t >> 1) & 1, sm.abort_flag);
-        if (t >= 1) tc::mbar_wait(&sm.bars[CB_SQ_EMPTY], (t - 1) & 1, sm.abort_flag);
-        tc::tcgen05_fence_after();
-        // rows of S/Q are always the i side (F0), columns the j side (F1)
-        if (!colmode) issue_sq(tmem, sm.ownF, stF, sm.ownP, stP); else issue_sq(tmem, stF, sm.ownF, stP, sm.ownP);
+    // the whole warp runs the loop (warp-uniform control flow), one elected lane issues: 10 + 16 MMAs per tile
+    const bool leader = tc::elect_one();
+    const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem, 0);
+    constexpr uint32_t idesc_row = idesc_bf16(kT, 64, 0, 1);    // dF0: A = dZ (K-major),  B = F1 tile (MN-major)
+    constexpr uint32_t idesc_col = idesc_bf16(kT, 64, 1, 1);    // dF1: A = dZ (MN-major), B = F0 tile (MN-major)
+    tc::mbar_wait(&sm.bars[CB_OWN], 0, sm.abort_flag);
+    const uint32_t zaddr = tc::smem_u32(sm.z);
+    // rows of S/Q are always the i side (F0), columns the j side (F1).  S/Q of tile t+1 is issued as soon as the epilogue
+    // holds tile t in registers (SQ_EMPTY), i.e. under the dZ arithmetic of tile t; the gradient MMAs of tile t follow.
+    auto sq = [&](int t) {
+      const int s = t & 1;
+      const uint8_t* stF = sm.stage + s * kStageBytes;
+      tc::mbar_wait(&sm.bars[CB_KV_FULL + s], (t >> 1) & 1, sm.abort_flag);
+      if (t >= 1) tc::mbar_wait(&sm.bars[CB_SQ_EMPTY], (t - 1) & 1, sm.abort_flag);
+      tc::tcgen05_fence_after();
+      const SqDesc d = !colmode ? sq_desc(sm.ownF, stF, sm.ownP, stF + kTileF) : sq_desc(stF, sm.ownF, stF + kTileF, sm.ownP);
+      if (leader) {
+        issue_sq(tmem_u, d);
         tc::mma_commit(&sm.bars[CB_SQ_FULL]);
-        tc::mbar_wait(&sm.bars[CB_Z_FULL], t & 1, sm.abort_flag);
-        tc::tcgen05_fence_after();
-        const uint32_t zaddr = tc::smem_u32(sm.z);
-        const uint64_t bB = smem_desc_sw128_mn(tc::smem_u32(stF), 0);
+      }
+      __syncwarp();
+    };
+    sq(0);
+    for (int t = 0; t < T; ++t) {
+      const int s = t & 1;
+      const uint8_t* stF = sm.stage + s * kStageBytes;
+      if (t + 1 < T) sq(t + 1);
+      tc::mbar_wait(&sm.bars[CB_Z_FULL], t & 1, sm.abort_flag);
+      tc::tcgen05_fence_after();
+      const uint64_t bB = smem_desc_sw128_mn(tc::smem_u32(stF), 0);
+      const uint64_t aZk = tc::smem_desc_sw128(zaddr);            // dZ K-major: sub-tile q at + q * kSubZ
+      const uint64_t aZm = smem_desc_sw128_mn(zaddr, kSubZ);      // dZ MN-major: hi pair at 0, lo pair at + 2 * kSubZ
+      if (leader) {
         if (!colmode) {
           // dF0[i, d] += sum_j dZ[i, j] F1[j, d]      (dZ = hi + lo: two bf16 terms ~ 16 mantissa bits)
 #pragma unroll
           for (int part = 0; part < 2; ++part)
 #pragma unroll
-            for (int k = 0; k < 8; ++k) {
-              const uint64_t aZ = tc::smem_desc_sw128(zaddr + (2 * part + (k >> 2)) * kSubZ) + 2 * (k & 3);
-              tc::mma_bf16_ss(tmem + 2 * kT, aZ, bB + 128 * k, idesc_row, (t | k | part) != 0);
-            }
+            for (int k = 0; k < 8; ++k)
+              tc::mma_bf16_ss(tmem_u + 2 * kT, aZk + (uint64_t)((2 * part + (k >> 2)) * (kSubZ >> 4) + 2 * (k & 3)), bB + 128 * k, idesc_row,
+                              (t | k | part) != 0);
         } else {
           // dF1[j, d] += sum_i dZ[i, j] F0[i, d]
 #pragma unroll
-          for (int part = 0; part < 2; ++part) {
-            const uint64_t aZ = smem_desc_sw128_mn(zaddr + 2 * part * kSubZ, kSubZ);
+          for (int part = 0; part < 2; ++part)
 #pragma unroll
-            for (int k = 0; k < 8; ++k) tc::mma_bf16_ss(tmem + 2 * kT, aZ + 128 * k, bB + 128 * k, idesc_col, (t | k | part) != 0);
-          }
+            for (int k = 0; k < 8; ++k)
+              tc::mma_bf16_ss(tmem_u + 2 * kT, aZm + (uint64_t)(2 * part * (kSubZ >> 4) + 128 * k), bB + 128 * k, idesc_col, (t | k | part) != 0);
         }
         tc::mma_commit(&sm.bars[CB_KV_EMPTY + s]);
         tc::mma_commit(&sm.bars[CB_Z_EMPTY]);
       }
-      tc::mma_commit(&sm.bars[CB_ACC]);
+      __syncwarp();
     }
+    if (leader) tc::mma_commit(&sm.bars[CB_ACC]);
+    __syncwarp();
   } else {
-    // ===== epilogue: 2 threads per TMEM lane (row i), 64 columns (j) each =====
-    const int quarter = warp & 3, half = (warp - 2) >> 2;
+    // ===== epilogue: 4 threads per TMEM lane (row i), 32 columns (j) each =====
+    const int quarter = warp & 3, colq = (warp - 2) >> 2;
+    const int half = colq >> 1, c2 = colq & 1;              // dZ sub-tile (64 columns) and 32-column group inside it
     const int r_in = quarter * 32 + lane;
     const uint32_t lane_addr = tmem + ((uint32_t)(quarter * 32) << 16);
     const float inv_rows = 1.0f / (float)p.rows;
@@ -508,6 +519,7 @@ contrast_tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_f0, const __grid_c
       }
     };
     if (!colmode) load_stats();
+    const uint32_t z_u32 = tc::smem_u32(sm.z);
     for (int t = 0; t < T; ++t) {
       const int o0 = (int)((t0 + t) * kT);
       const int i0 = colmode ? o0 : own_tile * kT, j0 = colmode ? own_tile * kT : o0;
@@ -515,15 +527,15 @@ contrast_tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_f0, const __grid_c
       const bool interior = (i0 + kT <= rows_i) && (j0 + kT <= rows_i) && (i0 != j0);
       tc::mbar_wait(&sm.bars[CB_SQ_FULL], t & 1, sm.abort_flag);
       if (t == 0 && threadIdx.x == 64) B200SSL_STAMP(p.dbg, ctaid, 2);       // first S/Q tile ready
-      if (t >= 1) tc::mbar_wait(&sm.bars[CB_Z_EMPTY], (t - 1) & 1, sm.abort_flag);
       tc::tcgen05_fence_after();
-#pragma unroll 1
-      for (int c2 = 0; c2 < 2; ++c2) {
-        const int col0 = half * 64 + c2 * 32;
+      {
+        const int col0 = colq * 32;
         uint32_t sv[32], qv[32];
         tc::tmem_ld_32x32(lane_addr + col0, sv);
         tc::tmem_ld_32x32(lane_addr + kT + col0, qv);
         tc::tmem_ld_wait();
+        tc::tcgen05_fence_before();
+        tc::mbar_arrive_warp(&sm.bars[CB_SQ_EMPTY], lane);  // S/Q are in registers: the MMA warp may issue the next tile's
         uint32_t packed[16], packed_lo[16];
         // dZ = P (G - r),  G = -(qm / qsum) / (P + 1e-7) / rows   (branch-free: qm = 0 off the graph).  Interior tiles (all
         // but the diagonal and the ragged edge) skip every per-element bound / diagonal test: two instantiations of the
@@ -531,7 +543,7 @@ contrast_tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_f0, const __grid_c
         auto dz_of = [&](float s, float q) {
           const float qm = (q >= p.th) ? q : 0.f;
           const float P = ex2a(s * p.scale) * inv_rs;
-          return P * (qm * qscale * rcpa(P + 1e-7f) - r_i);
+          return P * (qm * qscale * rcp_fma(P + 1e-7f) - r_i);
         };
         auto pack_pair = [&](int k, float d0, float d1) {
           const __nv_bfloat162 h = __floats2bfloat162_rn(d0, d1);
@@ -558,36 +570,36 @@ contrast_tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_f0, const __grid_c
             pack_pair(k, d[0], d[1]);
           }
         }
+        // the dZ buffer must have been consumed by the gradient MMAs of the previous tile -- only now, after the arithmetic
+        if (t >= 1) tc::mbar_wait(&sm.bars[CB_Z_EMPTY], (t - 1) & 1, sm.abort_flag);
 #pragma unroll
         for (int q4 = 0; q4 < 4; ++q4) {
           const int chunk = c2 * 4 + q4;                     // 16-byte chunk inside the 64-column sub-tile `half`
           const uint4 v = make_uint4(packed[4 * q4], packed[4 * q4 + 1], packed[4 * q4 + 2], packed[4 * q4 + 3]);
           const uint4 vl = make_uint4(packed_lo[4 * q4], packed_lo[4 * q4 + 1], packed_lo[4 * q4 + 2], packed_lo[4 * q4 + 3]);
-          *reinterpret_cast<uint4*>(sm.z + half * kSubZ + tc::sw128_offset(r_in, chunk)) = v;
-          *reinterpret_cast<uint4*>(sm.z + (2 + half) * kSubZ + tc::sw128_offset(r_in, chunk)) = vl;
+          tc::st_shared_v4(z_u32 + half * kSubZ + tc::sw128_offset(r_in, chunk), v.x, v.y, v.z, v.w);
+          tc::st_shared_v4(z_u32 + (2 + half) * kSubZ + tc::sw128_offset(r_in, chunk), vl.x, vl.y, vl.z, vl.w);
         }
       }
-      tc::tcgen05_fence_before();
-      tc::mbar_arrive(&sm.bars[CB_SQ_EMPTY]);
       tc::fence_proxy_async_smem();
-      tc::mbar_arrive(&sm.bars[CB_Z_FULL]);
+      tc::mbar_arrive_warp(&sm.bars[CB_Z_FULL], lane);
       if (t == T - 1 && threadIdx.x == 64) B200SSL_STAMP(p.dbg, ctaid, 3);   // last dZ tile written
     }
     tc::mbar_wait(&sm.bars[CB_ACC], 0, sm.abort_flag);       // all MMAs retired: dZ smem is free, accumulator final
     if (threadIdx.x == 64) B200SSL_STAMP(p.dbg, ctaid, 4);   // gradient accumulator complete
     tc::tcgen05_fence_after();
-    {   // accumulator -> the CTA that folds this row: thread (row, half) pushes 32 fp32 columns into the owner's
-        // gather buffer [source rank][local row][kAccLd] through distributed shared memory
+    {   // accumulator -> the CTA that folds this row: thread (row, colq) pushes 16 fp32 columns into the owner's
+        // gather buffer [source rank][local row][64] through distributed shared memory
       uint32_t av[32];
-      tc::tmem_ld_32x32(lane_addr + 2 * kT + half * 32, av);
-      tc::tmem_ld_wait();
+      tc::tmem_ld_32x16<0>(lane_addr + 2 * kT + colq * 16, av);
+      tc::tmem_ld_wait(av);
       // (the gather buffer must not alias the pipeline buffers: a peer may push while this CTA still runs MMAs)
       const int RBx = kT / CL, owner = r_in / RBx, lrow = r_in - owner * RBx;
       float* base = sGather + ((size_t)crank * RBx + lrow) * 64;
       float4* dst = reinterpret_cast<float4*>(CL > 1 ? cluster.map_shared_rank(base, owner) : base);
 #pragma unroll
-      for (int q4 = 0; q4 < 8; ++q4)                        // 16-byte chunk index XOR (row & 7): bank spread at the destination
-        dst[(half * 8 + q4) ^ (lrow & 7)] = make_float4(__uint_as_float(av[4 * q4]), __uint_as_float(av[4 * q4 + 1]),
+      for (int q4 = 0; q4 < 4; ++q4)                        // 16-byte chunk index XOR (row & 7): bank spread at the destination
+        dst[(colq * 4 + q4) ^ (lrow & 7)] = make_float4(__uint_as_float(av[4 * q4]), __uint_as_float(av[4 * q4 + 1]),
                                                         __uint_as_float(av[4 * q4 + 2]), __uint_as_float(av[4 * q4 + 3]));
     }
     tc::tcgen05_fence_before();
@@ -627,8 +639,6 @@ contrast_tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_f0, const __grid_c
 // are all resident at once.  A cluster lives inside one GPC, so a B200 runs only 15 clusters of 8 one-CTA-per-SM blocks at a
 // time (33 of 4, 74 of 2 -- b200ssl_debug_max_active_clusters); a launch that needs several waves of clusters pays the
 // prologue and the folds once per wave (28 strips x 8 at rows 3584 were two forward and four backward waves in round 1).
-int g_contrast_dense_b = getenv("B200SSL_K6_DENSE_B") ? atoi(getenv("B200SSL_K6_DENSE_B")) : 0;
-
 int ct_cluster(long long rows, int slices) {
   const long long tiles = (rows + kT - 1) / kT;
   static const int cap[4][2] = {{8, 15}, {4, 33}, {2, 74}, {1, 148}};
@@ -674,7 +684,6 @@ int contrast_fwd_tc(const void* f0, const void* f1, const void* probs_hl, long l
   p.inv_tau = 1.0f / temperature; p.th = contrast_th; p.stats = stats; p.out = out_scalar;
   p.loss_u = loss_u; p.lambda_u = lambda_u; p.lambda_c = lambda_c; p.total_out = total_out;
   p.cluster = ct_cluster(rows, 1); p.dbg = debug_timing_buffer(PDL_CONTRAST_FWD);
-  p.dense_b = g_contrast_dense_b;
   const size_t need = kWsHeaderBytes + sizeof(float) * contrast_tc_workspace_floats(rows);
   if (workspace_bytes < need) return fail(B200SSL_E_WORKSPACE, "%s: workspace %zu < %zu bytes", fn, workspace_bytes, need);
   p.grid_ticket = reinterpret_cast<unsigned*>(workspace) + 4;
