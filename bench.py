@@ -326,7 +326,8 @@ class Case:
         # ema_overlap: the EMA launch is a parallel branch of the step (side stream forked at the start of the step, joined at
         # its end) -- in the trainer EMA(t) runs next to the head of step t+1 and is joined ahead of optimizer.step(t+1)
         self.ema_overlap = bool(ema_overlap)
-        self.ema = ModelEMA(self.model, decay=wl["decay"], device=dev, overlap=self.ema_overlap)
+        self.ema = ModelEMA(self.model, decay=wl["decay"], device=dev, overlap=self.ema_overlap,
+                            overlap_ctas=int(os.environ.get("B200SSL_EMA_CTAS", "0")) or None)
         S.perturb_(self.model, torch.Generator(device=dev).manual_seed(5))        # m != e, like after an optimizer step
         self.grad_keys = {"comatch": ("logits_u_s0", "feats_u_s0", "feats_u_s1"), "fixmatch": ("logits_u_s",),
                           "semiformer": ("logits_u_s", "logits_u_s_trans")}[wl["kind"]]

@@ -137,19 +137,16 @@ __global__ void __launch_bounds__(kEmaThreads, 4) ema_multi_tensor_kernel(const 
 
 using namespace b200ssl;
 
-extern "C" int b200ssl_ema_multi_tensor(const b200ssl_ema_block* blocks, int32_t n_blocks, int32_t float_dtype,
-                                        int32_t do_ints, float decay, float one_minus_decay, int32_t mode,
-                                        void* stream) {
-  const char* fn = "b200ssl_ema_multi_tensor";
+static int ema_launch(const char* fn, const b200ssl_ema_block* blocks, int32_t n_blocks, int32_t float_dtype, int32_t do_ints,
+                      float decay, float one_minus_decay, int32_t mode, int32_t max_ctas, void* stream) {
   static_assert(sizeof(b200ssl_ema_block) == 32, "block table row must be 32 bytes");
   if (!blocks) return fail(B200SSL_E_NULL, "%s: NULL block table", fn);
   if (reinterpret_cast<uintptr_t>(blocks) & 15u) return fail(B200SSL_E_ALIGN, "%s: block table must be 16-byte aligned", fn);
   if (n_blocks <= 0) return fail(B200SSL_E_SHAPE, "%s: n_blocks must be > 0", fn);
   if (mode != 0 && mode != 1) return fail(B200SSL_E_ARG, "%s: mode %d (0 update, 1 set)", fn, mode);
-  // 4 resident CTAs of 256 threads per SM by default.  B200SSL_EMA_GRID (A/B aid) caps or lifts the grid: with the update on
-  // a side stream next to the head kernels (ModelEMA(overlap=True)), a non-persistent grid lets the head's CTAs in as SMs drain.
-  static const int env_grid = getenv("B200SSL_EMA_GRID") ? atoi(getenv("B200SSL_EMA_GRID")) : 0;
-  const int max_grid = env_grid > 0 ? env_grid : kNumSMs * 4;
+  if (max_ctas < 0) return fail(B200SSL_E_ARG, "%s: max_ctas %d < 0", fn, max_ctas);
+  // 4 resident CTAs of 256 threads per SM; max_ctas caps the grid (see b200ssl_ema_multi_tensor_ctas)
+  const int max_grid = (max_ctas > 0 && max_ctas < kNumSMs * 4) ? max_ctas : kNumSMs * 4;
   const int grid = n_blocks < max_grid ? n_blocks : max_grid;
   cudaStream_t st = as_stream(stream);
   cudaError_t e = cudaSuccess;
@@ -171,4 +168,16 @@ extern "C" int b200ssl_ema_multi_tensor(const b200ssl_ema_block* blocks, int32_t
   }
   if (e != cudaSuccess) return fail((int)e, "%s: cudaLaunchKernelEx: %s", fn, cudaGetErrorString(e));
   return check_launch(fn);
+}
+
+extern "C" int b200ssl_ema_multi_tensor(const b200ssl_ema_block* blocks, int32_t n_blocks, int32_t float_dtype,
+                                        int32_t do_ints, float decay, float one_minus_decay, int32_t mode,
+                                        void* stream) {
+  return ema_launch("b200ssl_ema_multi_tensor", blocks, n_blocks, float_dtype, do_ints, decay, one_minus_decay, mode, 0, stream);
+}
+
+extern "C" int b200ssl_ema_multi_tensor_ctas(const b200ssl_ema_block* blocks, int32_t n_blocks, int32_t float_dtype,
+                                             int32_t do_ints, float decay, float one_minus_decay, int32_t mode,
+                                             int32_t max_ctas, void* stream) {
+  return ema_launch("b200ssl_ema_multi_tensor_ctas", blocks, n_blocks, float_dtype, do_ints, decay, one_minus_decay, mode, max_ctas, stream);
 }

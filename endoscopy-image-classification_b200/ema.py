@@ -111,14 +111,19 @@ class _EmaPlan:
             return False
         return all(t.data_ptr() == p for t, p in self._sentinels)
 
-    def launch(self, decay: float, mode: int) -> None:
+    def launch(self, decay: float, mode: int, max_ctas: int = 0) -> None:
+        """``max_ctas`` > 0: cap the grid (``b200ssl_ema_multi_tensor_ctas``)."""
         d32 = float(np.float32(decay))
         o32 = float(np.float32(1.0 - decay))
         lib, st = N.lib(), N.stream_ptr(self.device)
         for i, fd in enumerate(self.float_dtypes):
-            N.check(lib.b200ssl_ema_multi_tensor(self.table.data_ptr(), self.n_blocks, fd,
-                                                 1 if (i == 0 and self.has_ints) else 0, d32, o32, mode, st),
-                    "ema_multi_tensor")
+            ints = 1 if (i == 0 and self.has_ints) else 0
+            if max_ctas > 0:
+                N.check(lib.b200ssl_ema_multi_tensor_ctas(self.table.data_ptr(), self.n_blocks, fd, ints, d32, o32, mode, int(max_ctas), st),
+                        "ema_multi_tensor_ctas")
+            else:
+                N.check(lib.b200ssl_ema_multi_tensor(self.table.data_ptr(), self.n_blocks, fd, ints, d32, o32, mode, st),
+                        "ema_multi_tensor")
 
 
 class ModelEMA(object):
@@ -131,11 +136,18 @@ class ModelEMA(object):
     parameters by hand (``load_state_dict`` copies in place and needs nothing).
     """
 
-    def __init__(self, model, decay=0.9999, device=None, revalidate_every: int = 1024, overlap: bool = False):
+    OVERLAP_CTAS = 4 * (148 - 48)      # grid of an overlapped update: 4 CTAs per SM on all but 48 SMs (see __init__; 336..464 measured, bench cfg 2)
+
+    def __init__(self, model, decay=0.9999, device=None, revalidate_every: int = 1024, overlap: bool = False,
+                 overlap_ctas: Optional[int] = None):
         """``overlap=True``: ``update`` is launched on a side stream forked from the current one, so the 300 MB weight
         stream runs next to whatever the caller queues afterwards (the next step's forward / SSL head); ``join()`` makes the
         current stream wait for it and has to be called before the model's weights are written again (the trainer does so
-        ahead of ``optimizer.step()``), before the EMA weights are read, and before the end of a CUDA-graph capture."""
+        ahead of ``optimizer.step()``), before the EMA weights are read, and before the end of a CUDA-graph capture.
+        The grid of an overlapped update is capped at ``overlap_ctas`` (default ``OVERLAP_CTAS``): its CTAs are persistent and
+        four of them fill an SM, so the SMs that the kernel launched just ahead of it holds (the head's first kernel, on a
+        higher-priority stream) are never handed to the update and stay free for the rest of the head, whose tensor-core
+        kernels need whole SMs."""
         super(ModelEMA, self).__init__()
         self.ema = deepcopy(model)
         self.ema.eval()
@@ -147,6 +159,7 @@ class ModelEMA(object):
         self._calls = 0
         self._revalidate_every = int(revalidate_every)
         self.overlap = bool(overlap)
+        self.overlap_ctas = int(self.OVERLAP_CTAS if overlap_ctas is None else overlap_ctas)
         self._side: Optional[torch.cuda.Stream] = None
         self._pending = False
 
@@ -183,7 +196,7 @@ class ModelEMA(object):
         cur = torch.cuda.current_stream(dev)
         self._side.wait_stream(cur)                               # after everything queued so far (the optimizer step)
         with torch.cuda.stream(self._side):
-            plan.launch(self.decay, 0)
+            plan.launch(self.decay, 0, max_ctas=self.overlap_ctas)
         self._pending = True
 
     def join(self):

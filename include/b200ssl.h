@@ -334,6 +334,14 @@ B200SSL_API int b200ssl_ema_multi_tensor(const b200ssl_ema_block* blocks, int32_
                              int32_t do_ints, float decay, float one_minus_decay,
                              int32_t mode /*0 update, 1 set*/, void* stream);
 
+/* The same update with at most `max_ctas` CTAs (0 = 4 per SM on every SM, as above).  For an update that runs on a side
+ * stream next to other kernels (ema.ModelEMA(overlap=True)): its CTAs are persistent and four of them fill an SM's register
+ * file, so a grid of 4 x (SMs - n) leaves n SMs -- the ones a kernel launched ahead of it already holds -- free for the whole
+ * update; the SSL head's tensor-core kernels need whole SMs (160-225 KB of shared memory, 55 K registers). */
+B200SSL_API int b200ssl_ema_multi_tensor_ctas(const b200ssl_ema_block* blocks, int32_t n_blocks, int32_t float_dtype,
+                                  int32_t do_ints, float decay, float one_minus_decay,
+                                  int32_t mode /*0 update, 1 set*/, int32_t max_ctas, void* stream);
+
 /* ------------------------------------------------------------ SURVEY 8(f1) ----
  * Optimizer step + EMA in one multi-tensor pass over the trainable fp32 parameters.
  * Replaces `self.optimizer.step()` (code/fixmatch.py:123; the SGD-nesterov / Adam /
