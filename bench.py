@@ -628,9 +628,11 @@ def run_b200(args, wl, rank, world, local_rank):
                            "execution": "whole step (head fwd+bwd + EMA) captured once in a CUDA graph and replayed; "
                                         "eager_ms_per_step is the same API without the graph"
                                         + ("; the EMA launch is a parallel branch of the step graph (ModelEMA(overlap=True): side stream "
-                                           "forked at the start of the step and joined at its end, the head's stream at high priority) -- "
-                                           "EMA(t) only has to finish before optimizer.step(t+1), so in the trainer it runs next to the "
-                                           "following step's head" if args.ema_overlap else "; EMA after the backward, in series"),
+                                           "forked at the start of the step and joined at its end, the head's stream at high priority, the "
+                                           "update's grid capped at 400 persistent CTAs so that the SMs the head's first kernel holds stay "
+                                           "free for the rest of the head) -- EMA(t) only has to finish before optimizer.step(t+1), so in "
+                                           "the trainer it runs next to the following step's head" if args.ema_overlap
+                                           else "; EMA after the backward, in series"),
                            "ema_overlap": bool(args.ema_overlap),
                            "timing": {"method": f"{m['blocks']['blocks']} blocks of [barrier+sync, {args.warmup} untimed replays, event, "
                                                 f"{args.steps} timed replays, event]; per block MAX over ranks; the line reports the MEDIAN block",
