@@ -604,6 +604,14 @@ def run_b200(args, wl, rank, world, local_rank):
     if rank == 0:
         peak, peak_src = peaks()
         achieved = plan.bytes_per_update / (ema_ms * 1e-3) / 1e9
+        traffic, traffic_src = None, None
+        tfile = REPO / "profiles" / "ema_traffic.json"
+        if tfile.exists() and wl["kind"] == "comatch":          # the capture is of the ModelwEmb-ResNet-50 update
+            try:
+                tj = json.loads(tfile.read_text())
+                traffic, traffic_src = float(tj["traffic_bytes_per_launch"]), tj["source"]
+            except Exception:
+                pass
         Bu = wl["B"] * wl["MU"]
         cpu = cpu_baseline_sample(wl) if world == 1 and not args.no_cpu_baseline else None
         ms, e2e_ms = m["ms_per_step"], m["e2e_ms_per_step"]
@@ -642,8 +650,9 @@ def run_b200(args, wl, rank, world, local_rank):
                                  "come straight from the backbone in training, i.e. L2-resident there too"},
                 "roofline": {"kernel": "ema_multi_tensor_kernel", "bound": "hbm", "achieved": achieved, "peak": peak,
                              "unit": "GB/s", "frac": achieved / peak,
-                             # not measured by this run (dram__bytes of the same kernel: profiles/, ncu --set full)
-                             "traffic": None, "peak_source": peak_src,
+                             # DRAM bytes of one launch of the same kernel on the same state, from the committed ncu --set full
+                             # capture (profiles/ema_traffic.json, written by tools/ncu_extract.py); null when absent
+                             "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                              "algorithmic_bytes_per_launch": plan.bytes_per_update, "avg_launch_ms": ema_ms,
                              "timed": f"{n_ema} back-to-back launches between two CUDA events on the launching stream (median of 3)"},
                 "e2e": {"value": world * Bu / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": m["h2d_bytes_per_step"],

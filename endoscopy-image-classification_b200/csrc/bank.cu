@@ -197,7 +197,7 @@ int smooth_nsplit(long long rows, long long bank_rows, int* tiles_per_split) {
 using namespace b200ssl;
 
 namespace b200ssl {
-static int g_f32_simt = getenv("B200SSL_K3_F32_SIMT") != nullptr;
+int g_f32_simt = getenv("B200SSL_K3_F32_SIMT") != nullptr;   // also read by contrast.cu
 int bank_smooth_tc(const void* feats, const void* queue_feats, const void* queue_probs_t, long long rows,
                    long long bank_rows, int classes, float temperature, float* rowsum, float* numer, int rowsum_ld,
                    int numer_ld, const b200ssl_bank_shards* shards, void* workspace, size_t workspace_bytes, cudaStream_t stream);

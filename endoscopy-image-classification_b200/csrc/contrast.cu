@@ -356,6 +356,19 @@ int contrast_bwd_tc(const void* f0, const void* f1, const void* probs_hl, const 
                     float temperature, float contrast_th, const float* upstream, float factor, void* g0, void* g1,
                     void* scale_grad, long long scale_numel, const float* scale_up, float scale_factor,
                     void* workspace, size_t workspace_bytes, cudaStream_t stream);
+int contrast_fwd_tc_f32(const float* f0, const float* f1, const float* probs, long long rows, int classes, float temperature,
+                        float contrast_th, float* stats, float* out_scalar, const float* loss_u, float lambda_u, float lambda_c,
+                        float* total_out, void* workspace, size_t workspace_bytes, cudaStream_t stream);
+int contrast_bwd_tc_f32(const float* f0, const float* f1, const float* probs, const float* stats, long long rows, int classes,
+                        float temperature, float contrast_th, const float* upstream, float factor, float* g0, float* g1,
+                        float* scale_grad, long long scale_numel, const float* scale_up, float scale_factor,
+                        void* workspace, size_t workspace_bytes, cudaStream_t stream);
+extern int g_f32_simt;     // bank.cu: fp32 storage on the exact-fp32 FFMA tiles (A/B) instead of the split-operand tensor-core kernels
+}
+// fp32 storage, 64-wide embeddings: the tensor-core kernels on bf16 hi + mid operands (contrast_tc.cu)
+static bool use_tc_f32(const void* f0, const void* f1, int dim, int classes, int dtype, const void* g0 = nullptr, const void* g1 = nullptr) {
+  auto al = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15u) == 0; };
+  return dtype == B200SSL_F32 && dim == 64 && classes <= 32 && !g_f32_simt && al(f0) && al(f1) && al(g0) && al(g1);
 }
 // bf16 embeddings with 128-byte rows + the hi/lo probability split: tcgen05 path (contrast_tc.cu)
 static bool use_tc(const void* f0, const void* f1, const void* probs_hl, int dim, int classes, int dtype, const void* g0 = nullptr,
@@ -392,6 +405,10 @@ extern "C" int b200ssl_contrast_fwd(const void* feats_s0, const void* feats_s1, 
   if (use_tc(feats_s0, feats_s1, probs_hl, dim, classes, dtype))
     return contrast_fwd_tc(feats_s0, feats_s1, probs_hl, rows, classes, temperature, contrast_th, stats, out_scalar, loss_u,
                            lambda_u, lambda_c, total_out, workspace, workspace_bytes, as_stream(stream));
+  if (use_tc_f32(feats_s0, feats_s1, dim, classes, dtype))
+    return contrast_fwd_tc_f32(static_cast<const float*>(feats_s0), static_cast<const float*>(feats_s1), probs, rows, classes, temperature,
+                               contrast_th, stats, out_scalar, loss_u, lambda_u, lambda_c, total_out, workspace, workspace_bytes,
+                               as_stream(stream));
   ContrastParams p{};
   p.f0 = feats_s0; p.f1 = feats_s1; p.probs = probs; p.rows = rows; p.D = dim; p.C = classes;
   p.tau = temperature; p.th = contrast_th; p.stats = stats; p.out = out_scalar;
@@ -437,6 +454,11 @@ extern "C" int b200ssl_contrast_bwd(const void* feats_s0, const void* feats_s1, 
                            grad_f0, grad_f1, piggy ? scale_grad : nullptr, scale_numel, scale_upstream, scale_factor, workspace,
                            workspace_bytes, as_stream(stream));
   }
+  if (use_tc_f32(feats_s0, feats_s1, dim, classes, dtype, grad_f0, grad_f1))
+    return contrast_bwd_tc_f32(static_cast<const float*>(feats_s0), static_cast<const float*>(feats_s1), probs, stats, rows, classes,
+                               temperature, contrast_th, upstream, factor, static_cast<float*>(grad_f0), static_cast<float*>(grad_f1),
+                               static_cast<float*>(scale_grad), scale_numel, scale_upstream, scale_factor, workspace, workspace_bytes,
+                               as_stream(stream));
   if (scale_grad)      // exact-fp32 path: the scaling is its own (tiny) launch
     if (int e = b200ssl_scale_inplace(scale_grad, scale_numel, dtype, scale_upstream, scale_factor, stream)) return e;
   ContrastParams p{};

@@ -38,12 +38,28 @@ constexpr int kCtEpiWarps = 16;               // 4 per TMEM lane quarter: each t
 constexpr int kCtThreads = 64 + 32 * kCtEpiWarps;   // warp 0 TMA/alloc, warp 1 MMA, warps 2..17 epilogue
 constexpr int kMaxCl = 8;
 constexpr uint32_t kTileF = kT * 128;         // 16 KB: [128][64] bf16
-constexpr uint32_t kStageBytes = 2 * kTileF;  // F tile + probs hi/lo tile
 constexpr uint32_t kSubZ = kT * 128;          // 16 KB: dZ columns [64*kb, +64)
-constexpr uint32_t kSmemCt = 2 * kTileF + 2 * kStageBytes + 4 * kSubZ;   // 160 KB (dZ is kept as a bf16 hi + lo pair)
 constexpr int kStatRows = 8;                  // per source rank: [value 0/1][column group 0..3][128 rows]
-constexpr size_t kSmemCtRequest = kSmemCt + 1024 + 512 + 2 * kMaxCl * kStatRows * kT * sizeof(float);   // + two [8][8][128] exchange areas (225.5 KB)
-static_assert(kSmemCtRequest <= 227 * 1024, "shared memory budget");
+// NT = bf16 terms per embedding: 1 = bf16 storage; 2 = fp32 storage split into bf16 hi + mid by split_contrast_kernel (S from
+// three cross terms, gradient GEMMs from dZ_hi F_hi + dZ_hi F_mid + dZ_lo F_hi; precise reciprocals; pairs within 2e-5 of the
+// graph threshold recomputed in fp32 from the probabilities: 1e-5 parity with the reference's fp32 arithmetic).
+// Shared memory: own tile (NT F terms + probs hi/lo), key-tile stages of the same shape (two; the backward with NT = 2 has
+// room for one and runs its tiles in series), the backward's dZ hi + lo pair (64 KB), barriers, then the exchange area
+// (forward: two [8][8][128] fp32 stat areas; backward: the [128][64] fp32 gather buffer).
+// Gradient GEMMs of the fp32-storage backward: sums with heavy cancellation (sum_j dZ_ij = 0), two bf16 terms per operand
+// leave 1.5e-5 -- so there dZ and the streamed embeddings carry THREE terms (hi, mid, lo; six cross products, 2e-8).
+template <int NT, bool BWD> constexpr int stage_terms() { return (NT == 2 && BWD) ? 3 : NT; }
+template <int NT, bool BWD> constexpr int z_terms() { return !BWD ? 0 : NT == 2 ? 3 : 2; }
+template <int NT> constexpr uint32_t own_bytes() { return (NT + 1) * kTileF; }
+template <int NT, bool BWD> constexpr uint32_t stage_bytes() { return (stage_terms<NT, BWD>() + 1) * kTileF; }
+template <int NT, bool BWD> constexpr int n_stages() { return (NT == 2 && BWD) ? 1 : 2; }
+template <int NT, bool BWD> constexpr size_t smem_ct_request() {
+  return 1024 + (size_t)own_bytes<NT>() + (size_t)stage_bytes<NT, BWD>() * n_stages<NT, BWD>() + (size_t)z_terms<NT, BWD>() * 2 * kSubZ + 512 +
+         (!BWD ? (size_t)2 * kMaxCl * kStatRows * kT * sizeof(float)     // forward: two stat areas
+               : NT == 2 ? 0 : (size_t)kT * 64 * sizeof(float));         // backward: gather buffer (fp32 storage: it reuses the dZ buffers)
+}
+static_assert(smem_ct_request<1, false>() <= 227 * 1024 && smem_ct_request<2, false>() <= 227 * 1024 &&
+              smem_ct_request<1, true>() <= 227 * 1024 && smem_ct_request<2, true>() <= 227 * 1024, "shared memory budget");
 constexpr uint32_t kTmemColsCt = 512;         // S 0..127, Q 128..255; forward: second S/Q buffer 256..511; backward: dF accumulator 256..319
 constexpr int kAccLd = 68;                    // floats per row of the staged accumulator (16-byte rows, bank spread)
 
@@ -59,9 +75,10 @@ struct ContrastTcParams {
   float* out; unsigned* grid_ticket; float* grid_part;
   const float* loss_u; float lambda_u, lambda_c; float* total_out;
   const float* upstream; float factor; void* g0; void* g1;
+  const float* probs;     // NT = 2: fp32 pseudo-label probabilities [rows, C] (exact Q for pairs at the graph threshold)
   unsigned long long* dbg;
   // optional piggy-backed task of the backward launch: sgrad[i] *= (*sup) * sfactor  (the stashed focal-CE gradient)
-  __nv_bfloat16* sgrad; long long snumel; const float* sup; float sfactor;
+  void* sgrad; long long snumel; const float* sup; float sfactor;     // sgrad: bf16 (NT = 1) or fp32 (NT = 2)
 };
 
 __device__ __forceinline__ float ex2a(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
@@ -91,6 +108,24 @@ __device__ __forceinline__ uint64_t smem_desc_sw128_mn(uint32_t smem_addr, uint3
   return d;
 }
 
+// reciprocal of a positive number: FMA-pipe Newton (2.4e-4) for bf16 storage, MUFU seed + one Newton step (~1e-7) for fp32
+template <int NT> __device__ __forceinline__ float rcp_pos(float x) {
+  if (NT == 1) return rcp_fma(x);
+  const float y = rcpa(x);
+  return y * fmaf(-x, y, 2.0f);
+}
+// q_ij = p_i . p_j in fp32 (fp32 storage only): the tensor-core Q (bf16 hi / lo probabilities) is good to ~1e-5 -- enough to
+// rule a pair out of the pseudo-label graph, not for the 1e-5 parity of what the positives contribute (q enters the loss and
+// dZ linearly).  Every pair at or above the threshold (~1 / classes of them) takes its q from here, as rarely on the other
+// side of the threshold as any other fp32 summation order of the reference's product.
+__device__ __forceinline__ float exact_q(const float* probs, int C, long long i, long long j) {
+  const float* a = probs + i * C;
+  const float* b = probs + j * C;
+  float acc = 0.f;
+  for (int c = 0; c < C; ++c) acc = fmaf(__ldg(a + c), __ldg(b + c), acc);
+  return acc;
+}
+
 struct Smem {
   uint8_t *ownF, *ownP, *stage, *z;
   uint64_t* bars;
@@ -99,17 +134,18 @@ struct Smem {
   float* stat;            // [2 passes][8 source ranks][8][128]: per-row partials (value 0/1 x column group 0..3) pushed by the cluster
 };
 
+template <int NT, bool BWD>
 __device__ __forceinline__ Smem carve(uint8_t* smem_raw) {
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   Smem s;
-  s.ownF = smem;
-  s.ownP = s.ownF + kTileF;
-  s.stage = s.ownP + kTileF;
-  s.z = s.stage + 2 * kStageBytes;
-  s.bars = reinterpret_cast<uint64_t*>(s.z + 4 * kSubZ);
+  s.ownF = smem;                                            // NT term tiles
+  s.ownP = s.ownF + NT * kTileF;
+  s.stage = s.ownP + kTileF;                                // per stage: NT term tiles of F, then the probs hi/lo tile
+  s.z = s.stage + n_stages<NT, BWD>() * stage_bytes<NT, BWD>();
+  s.bars = reinterpret_cast<uint64_t*>(s.z + z_terms<NT, BWD>() * 2 * kSubZ);
   s.tmem_slot = reinterpret_cast<uint32_t*>(s.bars + CB_COUNT);
   s.abort_flag = reinterpret_cast<volatile int*>(s.tmem_slot + 1);
-  s.stat = reinterpret_cast<float*>(s.bars + CB_COUNT + 2);
+  s.stat = (BWD && NT == 2) ? reinterpret_cast<float*>(s.z) : reinterpret_cast<float*>(s.bars + CB_COUNT + 2);
   return s;
 }
 
@@ -151,11 +187,17 @@ __device__ __forceinline__ SqDesc sq_desc(const uint8_t* aFp, const uint8_t* bFp
   return SqDesc{tc::smem_desc_sw128(tc::smem_u32(aFp)), tc::smem_desc_sw128(tc::smem_u32(bFp)),
                 tc::smem_desc_sw128(tc::smem_u32(aPp)), tc::smem_desc_sw128(tc::smem_u32(bPp))};
 }
+template <int NT>
 __device__ __forceinline__ void issue_sq(uint32_t tmem, const SqDesc& d) {
   constexpr uint32_t idesc_sq = idesc_bf16(kT, kT, 0, 0);
   const uint64_t aF = d.aF, bF = d.bF, aP = d.aP, bP = d.bP;
 #pragma unroll
-  for (int k = 0; k < 4; ++k) tc::mma_bf16_ss(tmem, aF + 2 * k, bF + 2 * k, idesc_sq, k > 0);
+  for (int pr = 0; pr < (NT == 2 ? 4 : 1); ++pr) {          // split embeddings: (mid, mid), (mid, hi), (hi, mid), (hi, hi) -- small products first
+    // all four cross terms: the logits sit in an exponent (x 1 / tau), the 2^-18 of mid x mid is worth its four MMAs here
+    const uint64_t ta = (NT == 2 && pr <= 1) ? (kTileF >> 4) : 0, tb = (NT == 2 && (pr == 0 || pr == 2)) ? (kTileF >> 4) : 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) tc::mma_bf16_ss(tmem, aF + ta + 2 * k, bF + tb + 2 * k, idesc_sq, (pr | k) != 0);
+  }
   // hi = columns 0..31 (byte 0), lo = columns 32..63 (byte 64 -> +4 descriptor units)
 #pragma unroll
   for (int k = 0; k < 2; ++k) tc::mma_bf16_ss(tmem + kT, aP + 2 * k, bP + 2 * k, idesc_sq, k > 0);
@@ -167,11 +209,13 @@ __device__ __forceinline__ void issue_sq(uint32_t tmem, const SqDesc& d) {
 
 // ============================================================== forward ==============================
 // grid = (row tiles, CL), cluster (1, CL, 1): cluster rank c streams the j tiles [c*nt/CL, (c+1)*nt/CL).
+template <int NT>
 __global__ void __launch_bounds__(kCtThreads, 1)
 contrast_tc_fwd_kernel(const __grid_constant__ CUtensorMap tm_f0, const __grid_constant__ CUtensorMap tm_f1,
                        const __grid_constant__ CUtensorMap tm_ph, const ContrastTcParams p) {
   extern __shared__ uint8_t smem_raw[];
-  const Smem sm = carve(smem_raw);
+  const Smem sm = carve<NT, false>(smem_raw);
+  constexpr uint32_t kStageBytes = stage_bytes<NT, false>();
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;   // warp-uniform for the compiler
   const int own_tile = blockIdx.x, CL = p.cluster;
   cg::cluster_group cluster = cg::this_cluster();
@@ -213,7 +257,8 @@ contrast_tc_fwd_kernel(const __grid_constant__ CUtensorMap tm_f0, const __grid_c
       if (interior) {
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
-          const float q = __uint_as_float(qv[j]);
+          float q = __uint_as_float(qv[j]);
+          if (NT == 2 && q > p.th - 2e-5f) q = exact_q(p.probs, p.C, gi, j0 + col0 + j);
           a0 += ex2a(__uint_as_float(sv[j]) * p.scale);                           // comatch.py:200
           a1 += (q >= p.th) ? q : 0.f;                                            // :206-208
         }
@@ -223,6 +268,7 @@ contrast_tc_fwd_kernel(const __grid_constant__ CUtensorMap tm_f0, const __grid_c
           const int gj = j0 + col0 + j;
           const bool ok = (gi_i < rows_i) && (gj < rows_i);
           float q = __uint_as_float(qv[j]);
+          if (NT == 2 && ok && q > p.th - 2e-5f) q = exact_q(p.probs, p.C, gi, gj);
           q = (gi_i == gj) ? 1.f : q;                                             // fill_diagonal_(1)  :205
           a0 += ok ? ex2a(__uint_as_float(sv[j]) * p.scale) : 0.f;
           a1 += (ok && q >= p.th) ? q : 0.f;
@@ -237,16 +283,19 @@ contrast_tc_fwd_kernel(const __grid_constant__ CUtensorMap tm_f0, const __grid_c
         float q = __uint_as_float(qv[j]);
         bool pos;
         if (interior) {
+          if (NT == 2 && q > p.th - 2e-5f) q = exact_q(p.probs, p.C, gi, j0 + col0 + j);
           pos = q >= p.th;
         } else {
           const int gj = j0 + col0 + j;
+          const bool ok = (gi_i < rows_i) && (gj < rows_i);
+          if (NT == 2 && ok && q > p.th - 2e-5f) q = exact_q(p.probs, p.C, gi, gj);
           q = (gi_i == gj) ? 1.f : q;
-          pos = (gi_i < rows_i) && (gj < rows_i) && (q >= p.th);
+          pos = ok && (q >= p.th);
         }
         const float P = ex2a(__uint_as_float(sv[j]) * p.scale) * inv_rs;                // :201
         const float qn = pos ? q * inv_qs : 0.f;                                        // :209
         a0 -= lg2a(P + 1e-7f) * 0.6931471805599453f * qn;                               // :212
-        a1 += qn * P * rcp_fma(P + 1e-7f);
+        a1 += qn * P * rcp_pos<NT>(P + 1e-7f);
       }
     }
     }
@@ -259,8 +308,9 @@ contrast_tc_fwd_kernel(const __grid_constant__ CUtensorMap tm_f0, const __grid_c
     if (warp == 0) {
       if (lane == 0) {
         if (phase == 0) {
-          tc::mbar_arrive_expect_tx(&sm.bars[CB_OWN], 2 * kTileF);
-          tc::tma_load_2d(sm.ownF, &tm_f0, 0, own_tile * kT, &sm.bars[CB_OWN]);
+          tc::mbar_arrive_expect_tx(&sm.bars[CB_OWN], own_bytes<NT>());
+#pragma unroll
+          for (int tt = 0; tt < NT; ++tt) tc::tma_load_2d(sm.ownF + tt * kTileF, &tm_f0, 64 * tt, own_tile * kT, &sm.bars[CB_OWN]);
           tc::tma_load_2d(sm.ownP, &tm_ph, 0, own_tile * kT, &sm.bars[CB_OWN]);
         }
         for (int u = u_begin; u < u_end; ++u) {
@@ -268,8 +318,10 @@ contrast_tc_fwd_kernel(const __grid_constant__ CUtensorMap tm_f0, const __grid_c
           if (u >= 2) tc::mbar_wait(&sm.bars[CB_KV_EMPTY + s], ((u >> 1) - 1) & 1, sm.abort_flag);
           const int o0 = (int)((t0 + (u % T)) * kT);
           tc::mbar_arrive_expect_tx(&sm.bars[CB_KV_FULL + s], kStageBytes);
-          tc::tma_load_2d(sm.stage + s * kStageBytes, &tm_f1, 0, o0, &sm.bars[CB_KV_FULL + s]);
-          tc::tma_load_2d(sm.stage + s * kStageBytes + kTileF, &tm_ph, 0, o0, &sm.bars[CB_KV_FULL + s]);
+#pragma unroll
+          for (int tt = 0; tt < NT; ++tt)
+            tc::tma_load_2d(sm.stage + s * kStageBytes + tt * kTileF, &tm_f1, 64 * tt, o0, &sm.bars[CB_KV_FULL + s]);
+          tc::tma_load_2d(sm.stage + s * kStageBytes + NT * kTileF, &tm_ph, 0, o0, &sm.bars[CB_KV_FULL + s]);
         }
       }
     } else if (warp == 1) {
@@ -283,9 +335,9 @@ contrast_tc_fwd_kernel(const __grid_constant__ CUtensorMap tm_f0, const __grid_c
         if (u >= 2) tc::mbar_wait(&sm.bars[CB_SQ_EMPTY + s], ((u >> 1) - 1) & 1, sm.abort_flag);   // S/Q of visit u-2 consumed
         tc::tcgen05_fence_after();
         const uint8_t* stF = sm.stage + s * kStageBytes;
-        const SqDesc d = sq_desc(sm.ownF, stF, sm.ownP, stF + kTileF);
+        const SqDesc d = sq_desc(sm.ownF, stF, sm.ownP, stF + NT * kTileF);
         if (leader) {
-          issue_sq(tmem_u + s * (2 * kT), d);              // the MMAs of visit u+1 run under the epilogue of visit u
+          issue_sq<NT>(tmem_u + s * (2 * kT), d);          // the MMAs of visit u+1 run under the epilogue of visit u
           tc::mma_commit(&sm.bars[CB_SQ_FULL + s]);
           tc::mma_commit(&sm.bars[CB_KV_EMPTY + s]);
         }
@@ -393,6 +445,7 @@ contrast_tc_fwd_kernel(const __grid_constant__ CUtensorMap tm_f0, const __grid_c
 
 // ============================================================== backward =============================
 // grid = (tiles, CL, 2), cluster (1, CL, 1): z = 0 -> dF0 of row tile x, z = 1 -> dF1 of column tile x.
+template <int NT>
 __global__ void __launch_bounds__(kCtThreads, 1)
 contrast_tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_f0, const __grid_constant__ CUtensorMap tm_f1,
                        const __grid_constant__ CUtensorMap tm_ph, const ContrastTcParams p) {
@@ -400,20 +453,30 @@ contrast_tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_f0, const __grid_c
   if (blockIdx.z == 2) {                                    // whole clusters of this z-slice only scale the stashed gradient
     pdl_wait();
     const float sc = (p.sup ? *p.sup : 1.f) * p.sfactor;
-    const long long nvec = p.snumel / 8, stride = (long long)gridDim.x * gridDim.y * blockDim.x;
-    for (long long v = (long long)(blockIdx.y * gridDim.x + blockIdx.x) * blockDim.x + threadIdx.x; v < nvec; v += stride) {
+    const long long stride = (long long)gridDim.x * gridDim.y * blockDim.x;
+    const long long first = (long long)(blockIdx.y * gridDim.x + blockIdx.x) * blockDim.x + threadIdx.x;
+    if (NT == 2) {                                          // fp32 storage
+      float* g = static_cast<float*>(p.sgrad);
+      for (long long i = first; i < p.snumel; i += stride) g[i] *= sc;
+      return;
+    }
+    __nv_bfloat16* g = static_cast<__nv_bfloat16*>(p.sgrad);
+    const long long nvec = p.snumel / 8;
+    for (long long v = first; v < nvec; v += stride) {
       float f[8];
-      unpack16(*reinterpret_cast<const uint4*>(p.sgrad + v * 8), f, __nv_bfloat16());
+      unpack16(*reinterpret_cast<const uint4*>(g + v * 8), f, __nv_bfloat16());
 #pragma unroll
       for (int e = 0; e < 8; ++e) f[e] *= sc;
-      *reinterpret_cast<uint4*>(p.sgrad + v * 8) = pack16(f, __nv_bfloat16());
+      *reinterpret_cast<uint4*>(g + v * 8) = pack16(f, __nv_bfloat16());
     }
-    for (long long i = nvec * 8 + (long long)(blockIdx.y * gridDim.x + blockIdx.x) * blockDim.x + threadIdx.x; i < p.snumel; i += stride)
-      p.sgrad[i] = __float2bfloat16_rn(__bfloat162float(p.sgrad[i]) * sc);
+    for (long long i = nvec * 8 + first; i < p.snumel; i += stride) g[i] = __float2bfloat16_rn(__bfloat162float(g[i]) * sc);
     return;
   }
   extern __shared__ uint8_t smem_raw[];
-  const Smem sm = carve(smem_raw);
+  const Smem sm = carve<NT, true>(smem_raw);
+  constexpr uint32_t kStageBytes = stage_bytes<NT, true>();
+  constexpr int kStages = n_stages<NT, true>();             // 1: tiles in series (S/Q of tile t+1 cannot be issued under tile t)
+  constexpr int kSTerms = stage_terms<NT, true>();          // bf16 terms of the streamed embeddings (3 with fp32 storage)
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;   // warp-uniform for the compiler
   const bool colmode = blockIdx.z == 1;                     // own tile = j rows of F1
   const int own_tile = blockIdx.x, CL = p.cluster;
@@ -427,20 +490,24 @@ contrast_tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_f0, const __grid_c
   if (threadIdx.x == 0) B200SSL_STAMP(p.dbg, ctaid, 0);
   if (threadIdx.x == 0) B200SSL_STAMP(p.dbg, ctaid, 1);
   float* sGather = sm.stat;                                 // [source rank][RB rows][64] fp32 = 32 KB, written by the peers
+  float fin[16];                                            // epilogue threads: their 16 columns of the finished gradient tile
   const float up = (p.upstream ? *p.upstream : 1.f) * p.factor * p.inv_tau;   // fetched early: off the critical tail
 
   if (warp == 0) {
     if (lane == 0) {
-      tc::mbar_arrive_expect_tx(&sm.bars[CB_OWN], 2 * kTileF);
-      tc::tma_load_2d(sm.ownF, colmode ? &tm_f1 : &tm_f0, 0, own_tile * kT, &sm.bars[CB_OWN]);
+      tc::mbar_arrive_expect_tx(&sm.bars[CB_OWN], own_bytes<NT>());
+#pragma unroll
+      for (int tt = 0; tt < NT; ++tt) tc::tma_load_2d(sm.ownF + tt * kTileF, colmode ? &tm_f1 : &tm_f0, 64 * tt, own_tile * kT, &sm.bars[CB_OWN]);
       tc::tma_load_2d(sm.ownP, &tm_ph, 0, own_tile * kT, &sm.bars[CB_OWN]);
       for (int t = 0; t < T; ++t) {
-        const int s = t & 1;
-        if (t >= 2) tc::mbar_wait(&sm.bars[CB_KV_EMPTY + s], ((t >> 1) - 1) & 1, sm.abort_flag);
+        const int s = t % kStages;
+        if (t >= kStages) tc::mbar_wait(&sm.bars[CB_KV_EMPTY + s], (t / kStages - 1) & 1, sm.abort_flag);
         const int o0 = (int)((t0 + t) * kT);
         tc::mbar_arrive_expect_tx(&sm.bars[CB_KV_FULL + s], kStageBytes);
-        tc::tma_load_2d(sm.stage + s * kStageBytes, colmode ? &tm_f0 : &tm_f1, 0, o0, &sm.bars[CB_KV_FULL + s]);
-        tc::tma_load_2d(sm.stage + s * kStageBytes + kTileF, &tm_ph, 0, o0, &sm.bars[CB_KV_FULL + s]);
+#pragma unroll
+        for (int tt = 0; tt < kSTerms; ++tt)
+          tc::tma_load_2d(sm.stage + s * kStageBytes + tt * kTileF, colmode ? &tm_f0 : &tm_f1, 64 * tt, o0, &sm.bars[CB_KV_FULL + s]);
+        tc::tma_load_2d(sm.stage + s * kStageBytes + kSTerms * kTileF, &tm_ph, 0, o0, &sm.bars[CB_KV_FULL + s]);
       }
     }
   } else if (warp == 1) {
@@ -454,49 +521,56 @@ contrast_tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_f0, const __grid_c
     // rows of S/Q are always the i side (F0), columns the j side (F1).  S/Q of tile t+1 is issued as soon as the epilogue
     // holds tile t in registers (SQ_EMPTY), i.e. under the dZ arithmetic of tile t; the gradient MMAs of tile t follow.
     auto sq = [&](int t) {
-      const int s = t & 1;
+      const int s = t % kStages;
       const uint8_t* stF = sm.stage + s * kStageBytes;
-      tc::mbar_wait(&sm.bars[CB_KV_FULL + s], (t >> 1) & 1, sm.abort_flag);
+      tc::mbar_wait(&sm.bars[CB_KV_FULL + s], (t / kStages) & 1, sm.abort_flag);
       if (t >= 1) tc::mbar_wait(&sm.bars[CB_SQ_EMPTY], (t - 1) & 1, sm.abort_flag);
       tc::tcgen05_fence_after();
-      const SqDesc d = !colmode ? sq_desc(sm.ownF, stF, sm.ownP, stF + kTileF) : sq_desc(stF, sm.ownF, stF + kTileF, sm.ownP);
+      const SqDesc d = !colmode ? sq_desc(sm.ownF, stF, sm.ownP, stF + kSTerms * kTileF) : sq_desc(stF, sm.ownF, stF + kSTerms * kTileF, sm.ownP);
       if (leader) {
-        issue_sq(tmem_u, d);
+        issue_sq<NT>(tmem_u, d);
         tc::mma_commit(&sm.bars[CB_SQ_FULL]);
       }
       __syncwarp();
     };
     sq(0);
     for (int t = 0; t < T; ++t) {
-      const int s = t & 1;
+      const int s = t % kStages;
       const uint8_t* stF = sm.stage + s * kStageBytes;
-      if (t + 1 < T) sq(t + 1);
+      if (kStages == 2 && t + 1 < T) sq(t + 1);
       tc::mbar_wait(&sm.bars[CB_Z_FULL], t & 1, sm.abort_flag);
       tc::tcgen05_fence_after();
       const uint64_t bB = smem_desc_sw128_mn(tc::smem_u32(stF), 0);
       const uint64_t aZk = tc::smem_desc_sw128(zaddr);            // dZ K-major: sub-tile q at + q * kSubZ
       const uint64_t aZm = smem_desc_sw128_mn(zaddr, kSubZ);      // dZ MN-major: hi pair at 0, lo pair at + 2 * kSubZ
       if (leader) {
-        if (!colmode) {
-          // dF0[i, d] += sum_j dZ[i, j] F1[j, d]      (dZ = hi + lo: two bf16 terms ~ 16 mantissa bits)
+        // (dZ term, F term).  bf16 storage: (hi, hi), (lo, hi) -- dZ = hi + lo, two bf16 terms ~ 16 mantissa bits.
+        // fp32 storage: (mid, mid), (hi, lo), (lo, hi), (hi, mid), (mid, hi), (hi, hi) -- three terms each, small products first
+        constexpr int kPairs = NT == 2 ? 6 : 2;
+        constexpr int zt[6] = {1, 0, 2, 0, 1, 0}, ft[6] = {1, 2, 0, 1, 0, 0};
 #pragma unroll
-          for (int part = 0; part < 2; ++part)
-#pragma unroll
-            for (int k = 0; k < 8; ++k)
-              tc::mma_bf16_ss(tmem_u + 2 * kT, aZk + (uint64_t)((2 * part + (k >> 2)) * (kSubZ >> 4) + 2 * (k & 3)), bB + 128 * k, idesc_row,
-                              (t | k | part) != 0);
-        } else {
-          // dF1[j, d] += sum_i dZ[i, j] F0[i, d]
-#pragma unroll
-          for (int part = 0; part < 2; ++part)
+        for (int pr = 0; pr < kPairs; ++pr) {
+          const int part = NT == 2 ? zt[pr] : pr;
+          const uint64_t bT = bB + (NT == 2 ? (uint64_t)ft[pr] * (kTileF >> 4) : 0);
+          if (!colmode) {
+            // dF0[i, d] += sum_j dZ[i, j] F1[j, d]
 #pragma unroll
             for (int k = 0; k < 8; ++k)
-              tc::mma_bf16_ss(tmem_u + 2 * kT, aZm + (uint64_t)(2 * part * (kSubZ >> 4) + 128 * k), bB + 128 * k, idesc_col, (t | k | part) != 0);
+              tc::mma_bf16_ss(tmem_u + 2 * kT, aZk + (uint64_t)((2 * part + (k >> 2)) * (kSubZ >> 4) + 2 * (k & 3)), bT + 128 * k, idesc_row,
+                              ((NT == 2 ? 0 : t) | k | pr) != 0);
+          } else {
+            // dF1[j, d] += sum_i dZ[i, j] F0[i, d]
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+              tc::mma_bf16_ss(tmem_u + 2 * kT, aZm + (uint64_t)(2 * part * (kSubZ >> 4) + 128 * k), bT + 128 * k, idesc_col,
+                              ((NT == 2 ? 0 : t) | k | pr) != 0);
+          }
         }
         tc::mma_commit(&sm.bars[CB_KV_EMPTY + s]);
         tc::mma_commit(&sm.bars[CB_Z_EMPTY]);
       }
       __syncwarp();
+      if (kStages == 1 && t + 1 < T) sq(t + 1);             // one stage: the next tile's S/Q only after this tile's gradient MMAs
     }
     if (leader) tc::mma_commit(&sm.bars[CB_ACC]);
     __syncwarp();
@@ -520,6 +594,12 @@ contrast_tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_f0, const __grid_c
     };
     if (!colmode) load_stats();
     const uint32_t z_u32 = tc::smem_u32(sm.z);
+    // fp32 storage (1e-5 parity bar): the tensor core truncates when it adds into its fp32 accumulator, a bias that grows with
+    // the length of the chain.  There every tile starts a fresh accumulator (24 MMAs) and the tile results are summed here
+    // in registers, round-to-nearest: 16 of the 64 gradient columns of the row per thread.
+    float acc16[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) acc16[i] = 0.f;
     for (int t = 0; t < T; ++t) {
       const int o0 = (int)((t0 + t) * kT);
       const int i0 = colmode ? o0 : own_tile * kT, j0 = colmode ? own_tile * kT : o0;
@@ -536,6 +616,58 @@ contrast_tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_f0, const __grid_c
         tc::tmem_ld_wait();
         tc::tcgen05_fence_before();
         tc::mbar_arrive_warp(&sm.bars[CB_SQ_EMPTY], lane);  // S/Q are in registers: the MMA warp may issue the next tile's
+        if constexpr (NT == 2) {
+          // fp32 storage: dZ as THREE bf16 terms, formed and stored 8 columns at a time (register budget).  The tiles run in
+          // series here, so the dZ buffers are free by now: the gradient MMAs of tile t-1 retired before S/Q of tile t were issued
+          if (t >= 1) {
+            tc::mbar_wait(&sm.bars[CB_Z_EMPTY], (t - 1) & 1, sm.abort_flag);
+            uint32_t av[32];                                // bank the gradient tile of t-1 (see acc16)
+            tc::tcgen05_fence_after();
+            tc::tmem_ld_32x16<0>(lane_addr + 2 * kT + colq * 16, av);
+            tc::tmem_ld_wait(av);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) acc16[i] += __uint_as_float(av[i]);
+            tc::tcgen05_fence_before();
+          }
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {                    // pairs of the graph: q from the fp32 probabilities
+            const float q = __uint_as_float(qv[j]);
+            if (q > p.th - 2e-5f && gi < rows_i && j0 + col0 + j < rows_i) qv[j] = __float_as_uint(exact_q(p.probs, p.C, gi, j0 + col0 + j));
+          }
+#pragma unroll
+          for (int q4 = 0; q4 < 4; ++q4) {
+            uint32_t ph[4], pm[4], pl[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              float d[2];
+#pragma unroll
+              for (int u = 0; u < 2; ++u) {
+                const int j = 8 * q4 + 2 * k + u, gj = j0 + col0 + j;
+                const float s = __uint_as_float(sv[j]);
+                float q = __uint_as_float(qv[j]);
+                bool ok = true;
+                if (!interior) {
+                  ok = (gi < rows_i) && (gj < rows_i);
+                  q = (gi == gj) ? 1.f : q;                                       // fill_diagonal_(1)
+                }
+                const float qm = (q >= p.th) ? q : 0.f;
+                const float P = ex2a(s * p.scale) * inv_rs;
+                d[u] = ok ? P * (qm * qscale * rcp_pos<2>(P + 1e-7f) - r_i) : 0.f;
+              }
+              const __nv_bfloat162 h = __floats2bfloat162_rn(d[0], d[1]);
+              const float r0 = d[0] - __low2float(h), r1 = d[1] - __high2float(h);
+              const __nv_bfloat162 m = __floats2bfloat162_rn(r0, r1);
+              const __nv_bfloat162 l = __floats2bfloat162_rn(r0 - __low2float(m), r1 - __high2float(m));
+              ph[k] = *reinterpret_cast<const uint32_t*>(&h);
+              pm[k] = *reinterpret_cast<const uint32_t*>(&m);
+              pl[k] = *reinterpret_cast<const uint32_t*>(&l);
+            }
+            const uint32_t off = half * kSubZ + tc::sw128_offset(r_in, c2 * 4 + q4);
+            tc::st_shared_v4(z_u32 + off, ph[0], ph[1], ph[2], ph[3]);
+            tc::st_shared_v4(z_u32 + 2 * kSubZ + off, pm[0], pm[1], pm[2], pm[3]);
+            tc::st_shared_v4(z_u32 + 4 * kSubZ + off, pl[0], pl[1], pl[2], pl[3]);
+          }
+        } else {
         uint32_t packed[16], packed_lo[16];
         // dZ = P (G - r),  G = -(qm / qsum) / (P + 1e-7) / rows   (branch-free: qm = 0 off the graph).  Interior tiles (all
         // but the diagonal and the ragged edge) skip every per-element bound / diagonal test: two instantiations of the
@@ -543,8 +675,9 @@ contrast_tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_f0, const __grid_c
         auto dz_of = [&](float s, float q) {
           const float qm = (q >= p.th) ? q : 0.f;
           const float P = ex2a(s * p.scale) * inv_rs;
-          return P * (qm * qscale * rcp_fma(P + 1e-7f) - r_i);
+          return P * (qm * qscale * rcp_pos<NT>(P + 1e-7f) - r_i);
         };
+
         auto pack_pair = [&](int k, float d0, float d1) {
           const __nv_bfloat162 h = __floats2bfloat162_rn(d0, d1);
           const __nv_bfloat162 l = __floats2bfloat162_rn(d0 - __low2float(h), d1 - __high2float(h));
@@ -580,6 +713,7 @@ contrast_tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_f0, const __grid_c
           tc::st_shared_v4(z_u32 + half * kSubZ + tc::sw128_offset(r_in, chunk), v.x, v.y, v.z, v.w);
           tc::st_shared_v4(z_u32 + (2 + half) * kSubZ + tc::sw128_offset(r_in, chunk), vl.x, vl.y, vl.z, vl.w);
         }
+        }
       }
       tc::fence_proxy_async_smem();
       tc::mbar_arrive_warp(&sm.bars[CB_Z_FULL], lane);
@@ -588,21 +722,28 @@ contrast_tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_f0, const __grid_c
     tc::mbar_wait(&sm.bars[CB_ACC], 0, sm.abort_flag);       // all MMAs retired: dZ smem is free, accumulator final
     if (threadIdx.x == 64) B200SSL_STAMP(p.dbg, ctaid, 4);   // gradient accumulator complete
     tc::tcgen05_fence_after();
-    {   // accumulator -> the CTA that folds this row: thread (row, colq) pushes 16 fp32 columns into the owner's
-        // gather buffer [source rank][local row][64] through distributed shared memory
+    {   // accumulator (+ the tiles banked in registers) -> fin[]: this thread's 16 fp32 columns of its row
       uint32_t av[32];
       tc::tmem_ld_32x16<0>(lane_addr + 2 * kT + colq * 16, av);
       tc::tmem_ld_wait(av);
-      // (the gather buffer must not alias the pipeline buffers: a peer may push while this CTA still runs MMAs)
-      const int RBx = kT / CL, owner = r_in / RBx, lrow = r_in - owner * RBx;
-      float* base = sGather + ((size_t)crank * RBx + lrow) * 64;
-      float4* dst = reinterpret_cast<float4*>(CL > 1 ? cluster.map_shared_rank(base, owner) : base);
 #pragma unroll
-      for (int q4 = 0; q4 < 4; ++q4)                        // 16-byte chunk index XOR (row & 7): bank spread at the destination
-        dst[(colq * 4 + q4) ^ (lrow & 7)] = make_float4(__uint_as_float(av[4 * q4]), __uint_as_float(av[4 * q4 + 1]),
-                                                        __uint_as_float(av[4 * q4 + 2]), __uint_as_float(av[4 * q4 + 3]));
+      for (int i = 0; i < 16; ++i) fin[i] = __uint_as_float(av[i]) + acc16[i];
     }
     tc::tcgen05_fence_before();
+  }
+  // fp32 storage: the gather buffer reuses the dZ buffers, which a CTA's gradient MMAs read until its last tile -- so nobody
+  // pushes before EVERY CTA of the cluster has retired its MMAs.  (bf16 storage has a gather buffer of its own: no extra sync.)
+  if (NT == 2) { if (CL > 1) cluster.sync(); else __syncthreads(); }
+  if (warp >= 2) {
+    // -> the CTA that folds this row: thread (row, colq) pushes its 16 fp32 columns into the owner's gather buffer
+    // [source rank][local row][64] through distributed shared memory
+    const int quarter = warp & 3, colq = (warp - 2) >> 2, r_in = quarter * 32 + lane;
+    const int RBx = kT / CL, owner = r_in / RBx, lrow = r_in - owner * RBx;
+    float* base = sGather + ((size_t)crank * RBx + lrow) * 64;
+    float4* dst = reinterpret_cast<float4*>(CL > 1 ? cluster.map_shared_rank(base, owner) : base);
+#pragma unroll
+    for (int q4 = 0; q4 < 4; ++q4)                          // 16-byte chunk index XOR (row & 7): bank spread at the destination
+      dst[(colq * 4 + q4) ^ (lrow & 7)] = make_float4(fin[4 * q4], fin[4 * q4 + 1], fin[4 * q4 + 2], fin[4 * q4 + 3]);
   }
   if (CL > 1) cluster.sync(); else __syncthreads();          // every slice has landed; afterwards only local reads
   if (threadIdx.x == 0) B200SSL_STAMP(p.dbg, ctaid, 5);
@@ -612,6 +753,23 @@ contrast_tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_f0, const __grid_c
   }
   // ---- fold: this CTA owns rows [crank*RB, (crank+1)*RB) and adds the CL pushed slices in rank order ----
   const int RB = kT / CL;
+  if (NT == 2) {                                            // fp32 gradients: 16 x (4 fp32 = 16 B) per row
+    float* out = static_cast<float*>(colmode ? p.g1 : p.g0);
+    for (int idx = threadIdx.x; idx < RB * 16; idx += blockDim.x) {
+      const int rr = idx >> 4, c4 = idx & 15;
+      float4 f = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int r = 0; r < kMaxCl; ++r)
+        if (r < CL) {
+          const float4 v = reinterpret_cast<const float4*>(sGather + ((size_t)r * RB + rr) * 64)[c4 ^ (rr & 7)];
+          f.x += v.x; f.y += v.y; f.z += v.z; f.w += v.w;
+        }
+      const long long grow = (long long)own_tile * kT + crank * RB + rr;
+      if (grow < p.rows) *reinterpret_cast<float4*>(out + grow * 64 + 4 * c4) = make_float4(f.x * up, f.y * up, f.z * up, f.w * up);
+    }
+    if (threadIdx.x == 0) B200SSL_STAMP(p.dbg, ctaid, 6);
+    return;
+  }
   __nv_bfloat16* out = static_cast<__nv_bfloat16*>(colmode ? p.g1 : p.g0);
   for (int idx = threadIdx.x; idx < RB * 8; idx += blockDim.x) {     // 8 x (8 bf16 = 16 B) per row
     const int rr = idx >> 3, c8 = idx & 7;
@@ -647,79 +805,179 @@ int ct_cluster(long long rows, int slices) {
   return 1;
 }
 
+// ---- fp32 storage -> bf16 operands (one launch ahead of the forward and of the backward kernel) ----------------------
+// embeddings [rows, 64] fp32 -> [rows, 192] bf16 = [hi(64) | mid(64) | lo(64)];  probabilities [rows, C] fp32 -> [rows, 64] bf16 =
+// [hi(32) | lo(32)], classes >= C zero (what the row kernels emit as probs_hl for bf16 steps)
+struct SplitCtParams {
+  const float* f0; const float* f1; const float* probs; long long rows; int C;
+  __nv_bfloat16* f0s; __nv_bfloat16* f1s; __nv_bfloat16* hl;
+};
+
+__global__ void __launch_bounds__(256) split_contrast_kernel(const SplitCtParams p) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const long long nthreads = (long long)gridDim.x * blockDim.x, tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  for (long long v = tid; v < p.rows * 16; v += nthreads) {           // 8 floats per item, both embedding matrices
+    const long long row = v >> 4;
+    const int which = (int)(v >> 3) & 1, c8 = (int)(v & 7) * 8;
+    const float* src = (which ? p.f1 : p.f0) + row * 64 + c8;
+    __nv_bfloat16* dst = (which ? p.f1s : p.f0s) + row * 192 + c8;
+    const float4 a = __ldg(reinterpret_cast<const float4*>(src)), b = __ldg(reinterpret_cast<const float4*>(src) + 1);
+    const float x[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    float h[8], m[8], l[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      h[i] = __bfloat162float(__float2bfloat16_rn(x[i]));
+      m[i] = __bfloat162float(__float2bfloat16_rn(x[i] - h[i]));
+      l[i] = (x[i] - h[i]) - m[i];
+    }
+    *reinterpret_cast<uint4*>(dst) = pack16(h, __nv_bfloat16());
+    *reinterpret_cast<uint4*>(dst + 64) = pack16(m, __nv_bfloat16());
+    *reinterpret_cast<uint4*>(dst + 128) = pack16(l, __nv_bfloat16());
+  }
+  for (long long v = tid; v < p.rows * 32; v += nthreads) {
+    const long long row = v >> 5;
+    const int c = (int)(v & 31);
+    const float x = c < p.C ? __ldg(p.probs + row * p.C + c) : 0.f;
+    const __nv_bfloat16 h = __float2bfloat16_rn(x);
+    p.hl[row * 64 + c] = h;
+    p.hl[row * 64 + 32 + c] = __float2bfloat16_rn(x - __bfloat162float(h));
+  }
+}
+
+static size_t ct_split_bytes(long long rows) { return (size_t)rows * (384 + 384 + 128) + 3 * 1024; }
+
+// carves the split copies out of the tail of the workspace and launches the pre-pass
+static int ct_split(const char* fn, const float* f0, const float* f1, const float* probs, long long rows, int classes, void* workspace,
+                    size_t workspace_bytes, cudaStream_t stream, SplitCtParams* out) {
+  const size_t need = kWsHeaderBytes + sizeof(float) * (size_t)((rows + kT - 1) / kT) * kMaxCl + ct_split_bytes(rows);
+  if (workspace_bytes < need) return fail(B200SSL_E_WORKSPACE, "%s: workspace %zu < %zu bytes", fn, workspace_bytes, need);
+  auto up = [](size_t x) { return (x + 1023) & ~(size_t)1023; };
+  char* base = static_cast<char*>(workspace) + ((workspace_bytes - ct_split_bytes(rows)) & ~(size_t)1023);
+  SplitCtParams sp{f0, f1, probs, rows, classes, reinterpret_cast<__nv_bfloat16*>(base),
+                   reinterpret_cast<__nv_bfloat16*>(base + up((size_t)rows * 384)),
+                   reinterpret_cast<__nv_bfloat16*>(base + 2 * up((size_t)rows * 384))};
+  long long blocks = (rows * 32 + 255) / 256;
+  if (blocks > 4 * kNumSMs) blocks = 4 * kNumSMs;
+  cudaError_t e = launch_pdl(PDL_CONTRAST_FWD, split_contrast_kernel, dim3((unsigned)blocks), dim3(256), 0, stream, dim3(1, 1, 1), sp);
+  if (e != cudaSuccess) return fail((int)e, "%s: split launch: %s", fn, cudaGetErrorString(e));
+  *out = sp;
+  return 0;
+}
+
 }  // namespace
 
 size_t contrast_tc_workspace_floats(long long rows) {
   const long long tiles = (rows + kT - 1) / kT;
-  return (size_t)tiles * kMaxCl;                             // per-CTA loss partials
+  return (size_t)tiles * kMaxCl + (ct_split_bytes(rows) + 3) / 4;    // per-CTA loss partials + the split copies of fp32 storage
 }
 
-template <typename K>
+template <int NT, bool BWD, typename K>
 static int ct_attr(const char* fn, K kernel) {
-  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemCtRequest);
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_ct_request<NT, BWD>());
   if (e != cudaSuccess) return fail((int)e, "%s: cudaFuncSetAttribute: %s", fn, cudaGetErrorString(e));
   return 0;
 }
 
-static int ct_maps(CUtensorMap* m, const void* f0, const void* f1, const void* ph, long long rows) {
-  if (int e = tc::make_tmap_bf16_2d(&m[0], f0, (uint64_t)rows, 64, 128, kT, 64)) return e;
-  if (int e = tc::make_tmap_bf16_2d(&m[1], f1, (uint64_t)rows, 64, 128, kT, 64)) return e;
+static int ct_maps(CUtensorMap* m, const void* f0, const void* f1, const void* ph, long long rows, int nt) {
+  const int terms = nt == 2 ? 3 : 1;                       // fp32 storage: [hi | mid | lo] per row (the forward reads hi, mid only)
+  if (int e = tc::make_tmap_bf16_2d(&m[0], f0, (uint64_t)rows, 64 * terms, 128 * terms, kT, 64)) return e;
+  if (int e = tc::make_tmap_bf16_2d(&m[1], f1, (uint64_t)rows, 64 * terms, 128 * terms, kT, 64)) return e;
   return tc::make_tmap_bf16_2d(&m[2], ph, (uint64_t)rows, 64, 128, kT, 64);
 }
 
-template <typename K>
+template <int NT, bool BWD, typename K>
 static int ct_launch(const char* fn, int tag, K kernel, dim3 grid, int cluster, cudaStream_t stream, const CUtensorMap* m,
                      const ContrastTcParams& p) {
-  cudaError_t e = launch_pdl(tag, kernel, grid, dim3(kCtThreads, 1, 1), kSmemCtRequest, stream, dim3(1, (unsigned)cluster, 1), m[0], m[1], m[2], p);
+  cudaError_t e = launch_pdl(tag, kernel, grid, dim3(kCtThreads, 1, 1), smem_ct_request<NT, BWD>(), stream, dim3(1, (unsigned)cluster, 1), m[0],
+                             m[1], m[2], p);
   if (e != cudaSuccess) return fail((int)e, "%s: cudaLaunchKernelEx: %s", fn, cudaGetErrorString(e));
   return check_launch(fn);
+}
+
+// nt = 1: f0 / f1 bf16 [rows, 64];  nt = 2: fp32 storage, f0 / f1 / probs_hl are the split copies made by ct_split
+static int contrast_fwd_tc_impl(int nt, const void* f0, const void* f1, const void* probs_hl, const float* probs, long long rows, int classes,
+                                float temperature, float contrast_th, float* stats, float* out_scalar, const float* loss_u, float lambda_u,
+                                float lambda_c, float* total_out, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+  const char* fn = "b200ssl_contrast_fwd[tcgen05]";
+  ContrastTcParams p{};
+  p.rows = rows; p.C = classes; p.scale = (float)(1.4426950408889634 / (double)temperature);
+  p.inv_tau = 1.0f / temperature; p.th = contrast_th; p.stats = stats; p.out = out_scalar; p.probs = probs;
+  p.loss_u = loss_u; p.lambda_u = lambda_u; p.lambda_c = lambda_c; p.total_out = total_out;
+  p.cluster = ct_cluster(rows, 1); p.dbg = debug_timing_buffer(PDL_CONTRAST_FWD);
+  const size_t need = kWsHeaderBytes + sizeof(float) * (size_t)((rows + kT - 1) / kT) * kMaxCl;
+  if (workspace_bytes < need) return fail(B200SSL_E_WORKSPACE, "%s: workspace %zu < %zu bytes", fn, workspace_bytes, need);
+  p.grid_ticket = reinterpret_cast<unsigned*>(workspace) + 4;
+  p.grid_part = reinterpret_cast<float*>(static_cast<char*>(workspace) + kWsHeaderBytes);
+  CUtensorMap m[3];
+  if (int e = ct_maps(m, f0, f1, probs_hl, rows, nt)) return e;
+  const dim3 grid((unsigned)((rows + kT - 1) / kT), (unsigned)p.cluster, 1);
+  static bool attr[2] = {false, false};
+  if (nt == 2) {
+    if (!attr[1]) { if (int e = ct_attr<2, false>(fn, contrast_tc_fwd_kernel<2>)) return e; attr[1] = true; }
+    return ct_launch<2, false>(fn, PDL_CONTRAST_FWD, contrast_tc_fwd_kernel<2>, grid, p.cluster, stream, m, p);
+  }
+  if (!attr[0]) { if (int e = ct_attr<1, false>(fn, contrast_tc_fwd_kernel<1>)) return e; attr[0] = true; }
+  return ct_launch<1, false>(fn, PDL_CONTRAST_FWD, contrast_tc_fwd_kernel<1>, grid, p.cluster, stream, m, p);
 }
 
 int contrast_fwd_tc(const void* f0, const void* f1, const void* probs_hl, long long rows, int classes, float temperature,
                     float contrast_th, float* stats, float* out_scalar, const float* loss_u, float lambda_u, float lambda_c,
                     float* total_out, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
-  const char* fn = "b200ssl_contrast_fwd[tcgen05]";
+  return contrast_fwd_tc_impl(1, f0, f1, probs_hl, nullptr, rows, classes, temperature, contrast_th, stats, out_scalar, loss_u, lambda_u,
+                              lambda_c, total_out, workspace, workspace_bytes, stream);
+}
+
+// fp32 storage (dim 64, classes <= 32): split pre-pass into the workspace, then the tensor-core kernel on the split operands
+int contrast_fwd_tc_f32(const float* f0, const float* f1, const float* probs, long long rows, int classes, float temperature,
+                        float contrast_th, float* stats, float* out_scalar, const float* loss_u, float lambda_u, float lambda_c,
+                        float* total_out, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+  SplitCtParams sp;
+  if (int e = ct_split("b200ssl_contrast_fwd[tcgen05, fp32 storage]", f0, f1, probs, rows, classes, workspace, workspace_bytes, stream, &sp)) return e;
+  return contrast_fwd_tc_impl(2, sp.f0s, sp.f1s, sp.hl, probs, rows, classes, temperature, contrast_th, stats, out_scalar, loss_u, lambda_u,
+                              lambda_c, total_out, workspace, (size_t)(reinterpret_cast<char*>(sp.f0s) - static_cast<char*>(workspace)), stream);
+}
+
+static int contrast_bwd_tc_impl(int nt, const void* f0, const void* f1, const void* probs_hl, const float* probs, const float* stats,
+                                long long rows, int classes, float temperature, float contrast_th, const float* upstream, float factor,
+                                void* g0, void* g1, void* scale_grad, long long scale_numel, const float* scale_up, float scale_factor,
+                                cudaStream_t stream) {
+  const char* fn = "b200ssl_contrast_bwd[tcgen05]";
   ContrastTcParams p{};
   p.rows = rows; p.C = classes; p.scale = (float)(1.4426950408889634 / (double)temperature);
-  p.inv_tau = 1.0f / temperature; p.th = contrast_th; p.stats = stats; p.out = out_scalar;
-  p.loss_u = loss_u; p.lambda_u = lambda_u; p.lambda_c = lambda_c; p.total_out = total_out;
-  p.cluster = ct_cluster(rows, 1); p.dbg = debug_timing_buffer(PDL_CONTRAST_FWD);
-  const size_t need = kWsHeaderBytes + sizeof(float) * contrast_tc_workspace_floats(rows);
-  if (workspace_bytes < need) return fail(B200SSL_E_WORKSPACE, "%s: workspace %zu < %zu bytes", fn, workspace_bytes, need);
-  p.grid_ticket = reinterpret_cast<unsigned*>(workspace) + 4;
-  p.grid_part = reinterpret_cast<float*>(static_cast<char*>(workspace) + kWsHeaderBytes);
+  p.inv_tau = 1.0f / temperature; p.th = contrast_th; p.stats = const_cast<float*>(stats); p.probs = probs;
+  p.upstream = upstream; p.factor = factor; p.g0 = g0; p.g1 = g1;
+  p.cluster = ct_cluster(rows, scale_grad ? 3 : 2); p.dbg = debug_timing_buffer(PDL_CONTRAST_BWD);
+  p.sgrad = scale_grad; p.snumel = scale_numel; p.sup = scale_up; p.sfactor = scale_factor;
   CUtensorMap m[3];
-  if (int e = ct_maps(m, f0, f1, probs_hl, rows)) return e;
-  static bool attr = false;
-  if (!attr) {
-    if (int e = ct_attr(fn, contrast_tc_fwd_kernel)) return e;
-    attr = true;
+  if (int e = ct_maps(m, f0, f1, probs_hl, rows, nt)) return e;
+  const dim3 grid((unsigned)((rows + kT - 1) / kT), (unsigned)p.cluster, scale_grad ? 3 : 2);
+  static bool attr[2] = {false, false};
+  if (nt == 2) {
+    if (!attr[1]) { if (int e = ct_attr<2, true>(fn, contrast_tc_bwd_kernel<2>)) return e; attr[1] = true; }
+    return ct_launch<2, true>(fn, PDL_CONTRAST_BWD, contrast_tc_bwd_kernel<2>, grid, p.cluster, stream, m, p);
   }
-  return ct_launch(fn, PDL_CONTRAST_FWD, contrast_tc_fwd_kernel, dim3((unsigned)((rows + kT - 1) / kT), (unsigned)p.cluster, 1), p.cluster, stream, m, p);
+  if (!attr[0]) { if (int e = ct_attr<1, true>(fn, contrast_tc_bwd_kernel<1>)) return e; attr[0] = true; }
+  return ct_launch<1, true>(fn, PDL_CONTRAST_BWD, contrast_tc_bwd_kernel<1>, grid, p.cluster, stream, m, p);
 }
 
 int contrast_bwd_tc(const void* f0, const void* f1, const void* probs_hl, const float* stats, long long rows, int classes,
                     float temperature, float contrast_th, const float* upstream, float factor, void* g0, void* g1,
                     void* scale_grad, long long scale_numel, const float* scale_up, float scale_factor,
                     void* workspace, size_t workspace_bytes, cudaStream_t stream) {
-  const char* fn = "b200ssl_contrast_bwd[tcgen05]";
   (void)workspace; (void)workspace_bytes;
-  ContrastTcParams p{};
-  p.rows = rows; p.C = classes; p.scale = (float)(1.4426950408889634 / (double)temperature);
-  p.inv_tau = 1.0f / temperature; p.th = contrast_th; p.stats = const_cast<float*>(stats);
-  p.upstream = upstream; p.factor = factor; p.g0 = g0; p.g1 = g1;
-  p.cluster = ct_cluster(rows, scale_grad ? 3 : 2); p.dbg = debug_timing_buffer(PDL_CONTRAST_BWD);
-  p.sgrad = static_cast<__nv_bfloat16*>(scale_grad); p.snumel = scale_numel; p.sup = scale_up; p.sfactor = scale_factor;
-  CUtensorMap m[3];
-  if (int e = ct_maps(m, f0, f1, probs_hl, rows)) return e;
-  static bool attr = false;
-  if (!attr) {
-    if (int e = ct_attr(fn, contrast_tc_bwd_kernel)) return e;
-    attr = true;
-  }
-  static_assert(kT * 64 * sizeof(float) <= 2 * kMaxCl * 4 * kT * sizeof(float), "gather buffer must fit in the exchange area");
-  return ct_launch(fn, PDL_CONTRAST_BWD, contrast_tc_bwd_kernel, dim3((unsigned)((rows + kT - 1) / kT), (unsigned)p.cluster, scale_grad ? 3 : 2), p.cluster,
-                   stream, m, p);
+  return contrast_bwd_tc_impl(1, f0, f1, probs_hl, nullptr, stats, rows, classes, temperature, contrast_th, upstream, factor, g0, g1,
+                              scale_grad, scale_numel, scale_up, scale_factor, stream);
+}
+
+int contrast_bwd_tc_f32(const float* f0, const float* f1, const float* probs, const float* stats, long long rows, int classes,
+                        float temperature, float contrast_th, const float* upstream, float factor, float* g0, float* g1,
+                        float* scale_grad, long long scale_numel, const float* scale_up, float scale_factor,
+                        void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+  SplitCtParams sp;
+  if (int e = ct_split("b200ssl_contrast_bwd[tcgen05, fp32 storage]", f0, f1, probs, rows, classes, workspace, workspace_bytes, stream, &sp)) return e;
+  return contrast_bwd_tc_impl(2, sp.f0s, sp.f1s, sp.hl, probs, stats, rows, classes, temperature, contrast_th, upstream, factor, g0, g1,
+                              scale_grad, scale_numel, scale_up, scale_factor, stream);
 }
 
 }  // namespace b200ssl

@@ -454,8 +454,9 @@ B200SSL_API int b200ssl_normalize_views(const uint8_t* images_hwc, void* out_nch
  * number of exponentials out of 32 that the tensor-core K3 computes with the FMA-pipe polynomial (-1 = default). */
 B200SSL_API void b200ssl_debug_set_k3(int32_t row_tiles_per_cta, int32_t cluster, int32_t clusters_per_row_group, int32_t poly_of_32);
 
-/* A/B aid: 1 = K3 with fp32 storage runs the exact-fp32 FFMA tiles (csrc/bank.cu) instead of the tensor-core kernel on bf16
- * hi + mid operands (csrc/bank_tc.cu); 0 = default.  B200SSL_K3_F32_SIMT=1 in the environment sets it at load time. */
+/* A/B aid: 1 = K3 and K6 with fp32 storage run the exact-fp32 FFMA tiles (csrc/bank.cu, csrc/contrast.cu) instead of the
+ * tensor-core kernels on bf16 hi + mid operands (csrc/bank_tc.cu, csrc/contrast_tc.cu); 0 = default.  B200SSL_K3_F32_SIMT=1 in
+ * the environment sets it at load time. */
 B200SSL_API void b200ssl_debug_set_k3_f32_simt(int32_t on);
 
 /* Clusters of `cluster` CTAs of the tensor-core K3 that the device runs at once (driver occupancy query; a table without a device). */

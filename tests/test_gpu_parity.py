@@ -473,8 +473,22 @@ def test_bank_smooth_fp32_storage_both_paths(pkg, rows, K, simt):
     assert rel_err(numer.double().cpu() / rowsum.double().cpu().unsqueeze(1), (A @ qp.double()) / A.sum(1, keepdim=True)) < FP32_TOL
 
 
+@pytest.mark.parametrize("simt", [0, 1])
 @pytest.mark.parametrize("rows,D", [(448, 64), (1, 8), (63, 16), (65, 64), (1000, 128), (3584, 64)])
-def test_contrast_fwd_bwd_vs_oracle(pkg, rows, D):
+def test_contrast_fwd_bwd_vs_oracle(pkg, rows, D, simt):
+    """fp32 storage against the fp64 oracle at 1e-5.  64-wide embeddings run the tensor-core kernels on bf16 hi + mid operands
+    (``simt=0``, default) or the exact-fp32 FFMA tiles (``simt=1``); other widths always the FFMA tiles."""
+    from endoscopy_image_classification_b200 import _native as N
+    if simt and D != 64:
+        pytest.skip("only 64-wide embeddings have two paths")
+    N.lib().b200ssl_debug_set_k3_f32_simt(simt)
+    try:
+        _contrast_fwd_bwd_vs_oracle(pkg, rows, D)
+    finally:
+        N.lib().b200ssl_debug_set_k3_f32_simt(0)
+
+
+def _contrast_fwd_bwd_vs_oracle(pkg, rows, D):
     g = torch.Generator().manual_seed(rows * 7 + D)
     nf = lambda: torch.nn.functional.normalize(torch.randn(rows, D, generator=g), dim=1)
     y = torch.randint(0, C, (rows,), generator=g)
@@ -488,6 +502,7 @@ def test_contrast_fwd_bwd_vs_oracle(pkg, rows, D):
     stats, _ = head._k_contrast_fwd(d0, d1, dp, scal)
     up = torch.tensor(1.5, device="cuda")
     g0, g1 = head._k_contrast_bwd(d0, d1, dp, stats, up)
+    torch.cuda.synchronize()
     assert abs(float(scal[2]) - float(ref)) < FP32_TOL * max(abs(float(ref)), 1e-2)   # rows=1: loss ~ -1e-7
     assert rel_err(g0, 1.5 * f0.grad) < FP32_TOL and rel_err(g1, 1.5 * f1.grad) < FP32_TOL
 

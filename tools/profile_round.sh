@@ -38,9 +38,9 @@ ncu --set full --clock-control none --import-source on -k regex:contrast_tc_bwd 
     python tools/contrast_only.py 3584 > $O/${R}_ncu_contrast_bwd_big.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:comatch_rows_fused -s 2 -c 1 -f -o $O/${R}_ncu_rows_fused \
     python tools/microbench.py --reps 2 > $O/${R}_ncu_rows_fused.log 2>&1
-# ---- compute-sanitizer over the launches whose correctness rests on intra-kernel synchronisation --------------------
-compute-sanitizer --tool racecheck --racecheck-report all python tools/sanitize_target.py > $O/${R}_sanitizer_racecheck.log 2>&1
-compute-sanitizer --tool synccheck python tools/sanitize_target.py > $O/${R}_sanitizer_synccheck.log 2>&1
-compute-sanitizer --tool memcheck python tools/sanitize_target.py > $O/${R}_sanitizer_memcheck.log 2>&1
-tail -3 $O/${R}_sanitizer_*.log
+# ---- compute-sanitizer (racecheck / synccheck of tools/sanitize_target.py) is closed on this pool ("runs under it have left
+# GPUs needing a reset"): the attempt of round 2 is kept as profiles/r02_sanitizer_closed.log.  The intra-kernel protocols are
+# covered by the randomised interleaving model (tests/test_peer_protocol_model.py), bounded waits with sticky abort / timeout
+# counters in every kernel, and bit-exact replay-vs-eager tests.
+python tools/microbench.py --dtype f32 > $O/${R}_microbench_cfg2_f32.txt 2>&1
 ls -la $O | grep ${R}_ | tail -40
