@@ -157,6 +157,40 @@ def test_trainer_with_fused_optimizer_ema_equals_the_eager_pair(opt_name):
             torch.testing.assert_close(sb[k][n].float().cpu(), sa[k][n].float().cpu(), rtol=1e-4, atol=1e-7)
 
 
+def test_trainer_with_overlapped_ema_equals_the_serial_one():
+    """TRAIN.EMA_OVERLAP: the EMA update on a side stream (capped grid), joined ahead of the next optimizer step and before the
+    EMA weights are read -- FixMatch.train_one ends with the same weights and EMA weights as the in-stream update, and
+    evaluate_one / save paths see the finished update."""
+    import copy
+
+    from endoscopy_image_classification_b200 import utils
+    from endoscopy_image_classification_b200.fixmatch import FixMatch
+    from endoscopy_image_classification_b200.optimizer import build_optimizer
+    g = torch.Generator().manual_seed(13)
+    B, MU, steps = 4, 2, 5
+    Bu = B * MU
+    lab = [(torch.randn(B, 3, 4, 4, generator=g), torch.randint(0, C, (B,), generator=g)) for _ in range(steps)]
+    unl = [((torch.randn(Bu, 3, 4, 4, generator=g), torch.randn(Bu, 3, 4, 4, generator=g)), None) for _ in range(steps)]
+    base = torch.nn.Sequential(torch.nn.Flatten(), torch.nn.Linear(48, 37), torch.nn.ReLU(), torch.nn.Linear(37, C))
+    result = {}
+    for overlap in (False, True):
+        torch.manual_seed(0)
+        model = copy.deepcopy(base)
+        tr = FixMatch(model, device="cuda")
+        tr.get_dataloader((Loader(lab), Loader(unl)), None)
+        cfg = _config(utils, B=B, MU=MU, thr=0.0, ema=True, steps=steps, train_extra={"EMA_OVERLAP": overlap})
+        tr.get_config(cfg, optimizer=build_optimizer(model.cuda(), "sgd", lr=1e-2), lr_scheduler=NoSched())
+        assert tr.ema_model.overlap == overlap
+        tr.train_one(epoch=0)
+        tr.ema_model.join()
+        torch.cuda.synchronize()
+        result[overlap] = (copy.deepcopy(tr.model.state_dict()), copy.deepcopy(tr.ema_model.ema.state_dict()))
+    for a, b in zip(result[False], result[True]):
+        for k in a:
+            torch.testing.assert_close(b[k], a[k], rtol=1e-5, atol=1e-6)
+    assert any(float((result[True][1][k] - base.state_dict()[k].cuda()).abs().max()) > 1e-5 for k in result[True][1])
+
+
 def test_ddp_single_rank_nccl(tmp_path):
     """SURVEY 8 f3 on the GPU: the FixMatch trainer with its backbone inside DistributedDataParallel (a 1-rank NCCL group
     on this box; the 2-rank wiring is covered on the CPU by tests/test_ddp_trainer_gloo.py) runs the fused criteria and the
