@@ -680,6 +680,7 @@ def main():
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
     ap.add_argument("--ema-overlap", type=int, default=1, choices=[0, 1],
                     help="1: the EMA launch runs as a parallel branch of the step (default); 0: after the backward, in series")
+    ap.add_argument("--bank-rows", type=int, default=0, help="override the workload's bank rows per rank (tuning aid)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the cfg4 / fp32 / fused-optimizer blocks")
     ap.add_argument("--no-parity", action="store_true", help="skip the multi-rank parity check before timing")
@@ -693,6 +694,8 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
     wl = WORKLOADS[args.workload]
+    if args.bank_rows:                         # tuning aid: e.g. cfg 2's N = 8 ring (20480 rows) on one GPU
+        wl = dict(wl, K=args.bank_rows, desc=wl["desc"] + f" [bank rows overridden: {args.bank_rows}]")
     if args.impl == "reference":
         run_reference(args, wl, rank, world)
         return

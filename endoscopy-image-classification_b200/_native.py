@@ -51,6 +51,7 @@ SIGNATURES = {
     "b200ssl_debug_smooth_plan": (_i32, [_i64, _i64, _i32, _vp]),
     "b200ssl_debug_set_k3": (None, [_i32, _i32, _i32, _i32]),
     "b200ssl_debug_set_k3_f32_simt": (None, [_i32]),
+    "b200ssl_set_head_sm_budget": (_i32, [_i32]),
     "b200ssl_debug_max_active_clusters": (_i32, [_i32]),
     "b200ssl_fixmatch_head_fwd_bwd": (_i32, [_vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _f32, _f32, _i32,
                                              _vp, _vp, _vp, _vp, _sz, _vp]),

@@ -10,6 +10,7 @@ namespace {
 thread_local char g_err[512] = "";
 unsigned long long* g_timing = nullptr;
 }
+int g_head_sm_budget = 0;
 unsigned long long* debug_timing_buffer(int kernel_tag) { return g_timing ? g_timing + (size_t)kernel_tag * kDebugRegion : nullptr; }
 
 int fail(int code, const char* fmt, ...) {
@@ -34,6 +35,12 @@ extern "C" int b200ssl_version(void) { return B200SSL_VERSION; }
 extern "C" void b200ssl_debug_set_timing_buffer(void* device_u64) { g_timing = static_cast<unsigned long long*>(device_u64); }
 
 extern "C" const char* b200ssl_last_error_string(void) { return g_err; }
+
+extern "C" int b200ssl_set_head_sm_budget(int32_t sms) {
+  const int prev = g_head_sm_budget;
+  g_head_sm_budget = sms > 0 && sms < kNumSMs ? sms : 0;
+  return prev;
+}
 
 extern "C" size_t b200ssl_workspace_bytes(int64_t rows, int32_t classes, int64_t bank_rows) {
   if (rows < 1) rows = 1;

@@ -725,8 +725,13 @@ SmoothPlan smooth_tc_plan(long long rows, long long ktiles, bool remote, int nt 
   }
   const int mt_lo = g_force_mt > 0 ? (g_force_mt < kMaxMT ? g_force_mt : kMaxMT) : (remote && row_tiles <= kMaxMT) ? (int)row_tiles : 1;
   const int mt_hi = (g_force_mt > 0 || (remote && row_tiles <= kMaxMT)) ? mt_lo : kMaxMT;
+  // with an SM budget (g_head_sm_budget): also the best plan of at most that many CTAs; it wins while it costs <= 1.5 x the best
+  SmoothPlan best_b{1, 1, 1};
+  double best_b_cost = 1e300;
+  const bool forced = g_force_mt > 0 || g_force_cluster > 0 || g_force_nouter > 0;
   for (int mt = mt_lo; mt <= mt_hi; ++mt) {
     if (mt > row_tiles && mt > mt_lo) break;
+    const long long groups = (row_tiles + mt - 1) / mt;
     for (int cl = 1; cl <= kMaxCluster; cl *= 2) {
       if (cl > ktiles) break;
       if (g_force_cluster > 0 && cl != g_force_cluster) continue;
@@ -735,9 +740,11 @@ SmoothPlan smooth_tc_plan(long long rows, long long ktiles, bool remote, int nt 
         if (g_force_nouter > 0 && no != g_force_nouter) continue;
         const double c = plan_cost(row_tiles, ktiles, mt, cl, no, nt == 2 ? 1.6 : 1.0);
         if (c < best_cost - 1e-9) { best_cost = c; best = SmoothPlan{mt, cl, (int)no}; }
+        if (g_head_sm_budget > 0 && groups * cl * no <= g_head_sm_budget && c < best_b_cost - 1e-9) { best_b_cost = c; best_b = SmoothPlan{mt, cl, (int)no}; }
       }
     }
   }
+  if (!forced && g_head_sm_budget > 0 && best_b_cost <= 1.5 * best_cost) return best_b;
   return best;
 }
 

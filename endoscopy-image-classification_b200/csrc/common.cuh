@@ -51,6 +51,10 @@ constexpr int kMaxRowCtas = 4 * kNumSMs;
 int smooth_nsplit(long long rows, long long bank_rows, int* tiles_per_split);
 int contrast_nsplit(long long rows, int modes, int* tiles_per_split);
 size_t contrast_workspace_floats(long long rows, int dim);
+// SMs the head's kernels should confine themselves to (0 = no limit): set by ModelEMA(overlap=True), whose capped update leaves
+// that many SMs free for the whole update -- a head kernel that takes more would hand its surplus SMs to the update's pending
+// CTAs when it retires, and the kernels after it would find no whole SM (b200ssl_set_head_sm_budget)
+extern int g_head_sm_budget;
 size_t smooth_tc_workspace_floats(long long rows, long long bank_rows, int classes);
 size_t smooth_tc_f32_workspace_bytes(long long rows, long long bank_rows, int classes);   // fold partials + split operand copies (fp32 storage)
 size_t contrast_tc_workspace_floats(long long rows);

@@ -800,6 +800,10 @@ contrast_tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_f0, const __grid_c
 int ct_cluster(long long rows, int slices) {
   const long long tiles = (rows + kT - 1) / kT;
   static const int cap[4][2] = {{8, 15}, {4, 33}, {2, 74}, {1, 148}};
+  // with an SM budget of the head (g_head_sm_budget): the widest cluster whose launch stays inside it, if any
+  if (g_head_sm_budget > 0)
+    for (const auto& c : cap)
+      if (c[0] <= tiles && tiles * slices <= c[1] && tiles * slices * c[0] <= g_head_sm_budget) return c[0];
   for (const auto& c : cap)
     if (c[0] <= tiles && tiles * slices <= c[1]) return c[0];
   return 1;

@@ -160,6 +160,9 @@ class ModelEMA(object):
         self._revalidate_every = int(revalidate_every)
         self.overlap = bool(overlap)
         self.overlap_ctas = int(self.OVERLAP_CTAS if overlap_ctas is None else overlap_ctas)
+        if self.overlap:
+            # the head's launch planners keep to the SMs the capped update leaves free (process-wide setting)
+            N.lib().b200ssl_set_head_sm_budget(max(148 - self.overlap_ctas // 4, 8))
         self._side: Optional[torch.cuda.Stream] = None
         self._pending = False
 

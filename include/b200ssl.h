@@ -454,6 +454,13 @@ B200SSL_API int b200ssl_normalize_views(const uint8_t* images_hwc, void* out_nch
  * number of exponentials out of 32 that the tensor-core K3 computes with the FMA-pipe polynomial (-1 = default). */
 B200SSL_API void b200ssl_debug_set_k3(int32_t row_tiles_per_cta, int32_t cluster, int32_t clusters_per_row_group, int32_t poly_of_32);
 
+/* SM budget of the SSL head (process-wide; 0 = none, the default; returns the previous value).  With a budget the launch
+ * planners of K3 and K6 pick the best geometry of at most `sms` CTAs, as long as it costs no more than 1.5 x the unconstrained
+ * one.  Set by ema.ModelEMA(overlap=True) to the SMs its capped update (b200ssl_ema_multi_tensor_ctas) leaves free: a head
+ * kernel that took more SMs would hand the surplus to the update's pending CTAs when it retires, and the tensor-core kernels
+ * after it -- which need whole SMs -- would wait for the update to finish. */
+B200SSL_API int b200ssl_set_head_sm_budget(int32_t sms);
+
 /* A/B aid: 1 = K3 and K6 with fp32 storage run the exact-fp32 FFMA tiles (csrc/bank.cu, csrc/contrast.cu) instead of the
  * tensor-core kernels on bf16 hi + mid operands (csrc/bank_tc.cu, csrc/contrast_tc.cu); 0 = default.  B200SSL_K3_F32_SIMT=1 in
  * the environment sets it at load time. */

@@ -63,3 +63,14 @@ def assert_mask_match(mask, mask_ref, score_ref, thr, what="mask", tol=1e-6):
 def top2_gap(probs):
     t = probs.double().topk(2, dim=1).values
     return (t[:, 0] - t[:, 1]).cpu()
+
+
+@pytest.fixture(autouse=True)
+def _reset_process_wide_knobs():
+    """ModelEMA(overlap=True) sets a process-wide SM budget for the head's launch planners: tests must not leak it."""
+    yield
+    try:
+        from endoscopy_image_classification_b200 import _native as N
+        N.lib().b200ssl_set_head_sm_budget(0)
+    except Exception:
+        pass
