@@ -744,7 +744,9 @@ SmoothPlan smooth_tc_plan(long long rows, long long ktiles, bool remote, int nt 
       }
     }
   }
-  if (!forced && g_head_sm_budget > 0 && best_b_cost <= 1.5 * best_cost) return best_b;
+  // (not for shards read over NVLink: there the launch lives off the number of tile streams in flight -- measured at N = 8,
+  // K = 65536: 100 us/step with the unconstrained plan, 128 with 48 CTAs)
+  if (!forced && !remote && g_head_sm_budget > 0 && best_b_cost <= 1.5 * best_cost) return best_b;
   return best;
 }
 
