@@ -292,7 +292,8 @@ def timed_blocks(ctx, run_once, steps, warmup, blocks):
 
 def block_stats(ms_blocks, steps):
     per = sorted(x / steps for x in ms_blocks)
-    return {"blocks": len(per), "median_ms_per_step": statistics.median(per), "min_ms_per_step": per[0], "max_ms_per_step": per[-1]}
+    return {"blocks": len(per), "median_ms_per_step": statistics.median(per), "min_ms_per_step": per[0], "max_ms_per_step": per[-1],
+            "blocks_slower_than_1p25_median": sum(1 for x in per if x > 1.25 * statistics.median(per))}
 
 
 class Case:
