@@ -137,6 +137,16 @@ __global__ void __launch_bounds__(kEmaThreads, 4) ema_multi_tensor_kernel(const 
 
 using namespace b200ssl;
 
+// one thread that returns after `ns` nanoseconds: put ahead of an overlapped update on its side stream, it lets the kernel
+// queued at the same time on the other stream place its CTAs first (see b200ssl_stream_delay)
+__global__ void delay_kernel(unsigned long long ns) {
+  unsigned long long t0, t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+  do {
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  } while (t - t0 < ns);
+}
+
 static int ema_launch(const char* fn, const b200ssl_ema_block* blocks, int32_t n_blocks, int32_t float_dtype, int32_t do_ints,
                       float decay, float one_minus_decay, int32_t mode, int32_t max_ctas, void* stream) {
   static_assert(sizeof(b200ssl_ema_block) == 32, "block table row must be 32 bytes");
@@ -180,4 +190,11 @@ extern "C" int b200ssl_ema_multi_tensor_ctas(const b200ssl_ema_block* blocks, in
                                              int32_t do_ints, float decay, float one_minus_decay, int32_t mode,
                                              int32_t max_ctas, void* stream) {
   return ema_launch("b200ssl_ema_multi_tensor_ctas", blocks, n_blocks, float_dtype, do_ints, decay, one_minus_decay, mode, max_ctas, stream);
+}
+
+extern "C" int b200ssl_stream_delay(int64_t nanoseconds, void* stream) {
+  if (nanoseconds < 0 || nanoseconds > 1000000) return fail(B200SSL_E_ARG, "b200ssl_stream_delay: %lld ns outside [0, 1e6]", (long long)nanoseconds);
+  if (nanoseconds == 0) return 0;
+  delay_kernel<<<1, 1, 0, as_stream(stream)>>>((unsigned long long)nanoseconds);
+  return check_launch("b200ssl_stream_delay");
 }

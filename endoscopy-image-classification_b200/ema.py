@@ -16,6 +16,7 @@ with bit-identical results:
 from __future__ import annotations
 
 import ctypes as C
+import os
 from copy import deepcopy
 from typing import List, Optional
 
@@ -136,6 +137,7 @@ class ModelEMA(object):
     parameters by hand (``load_state_dict`` copies in place and needs nothing).
     """
 
+    OVERLAP_DELAY_NS = 500             # head start (ns) given to the kernel queued next to an overlapped update (0: 2-3 slow blocks of 25; >= 2500: the whole PDL-chained head is resident first and the update starves, 90 us)
     OVERLAP_CTAS = 4 * (148 - 48)      # grid of an overlapped update: 4 CTAs per SM on all but 48 SMs (see __init__; 336..464 measured, bench cfg 2)
 
     def __init__(self, model, decay=0.9999, device=None, revalidate_every: int = 1024, overlap: bool = False,
@@ -160,6 +162,7 @@ class ModelEMA(object):
         self._revalidate_every = int(revalidate_every)
         self.overlap = bool(overlap)
         self.overlap_ctas = int(self.OVERLAP_CTAS if overlap_ctas is None else overlap_ctas)
+        self.overlap_delay_ns = int(os.environ.get("B200SSL_EMA_DELAY_NS", self.OVERLAP_DELAY_NS))
         if self.overlap:
             # the head's launch planners keep to the SMs the capped update leaves free (process-wide setting)
             N.lib().b200ssl_set_head_sm_budget(max(148 - self.overlap_ctas // 4, 8))
@@ -199,6 +202,8 @@ class ModelEMA(object):
         cur = torch.cuda.current_stream(dev)
         self._side.wait_stream(cur)                               # after everything queued so far (the optimizer step)
         with torch.cuda.stream(self._side):
+            if self.overlap_delay_ns > 0:                         # the kernel queued next on the caller's stream places its CTAs first
+                N.check(N.lib().b200ssl_stream_delay(self.overlap_delay_ns, N.stream_ptr(dev)), "stream_delay")
             plan.launch(self.decay, 0, max_ctas=self.overlap_ctas)
         self._pending = True
 

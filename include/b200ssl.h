@@ -342,6 +342,11 @@ B200SSL_API int b200ssl_ema_multi_tensor_ctas(const b200ssl_ema_block* blocks, i
                                   int32_t do_ints, float decay, float one_minus_decay,
                                   int32_t mode /*0 update, 1 set*/, int32_t max_ctas, void* stream);
 
+/* A one-thread kernel that holds `stream` for `nanoseconds` (<= 1 ms).  ema.ModelEMA(overlap=True) queues it ahead of the
+ * capped update on the side stream: the head's first kernel, queued at the same moment on the other stream, then places
+ * its CTAs first -- the order that keeps whole SMs free for the rest of the head. */
+B200SSL_API int b200ssl_stream_delay(int64_t nanoseconds, void* stream);
+
 /* ------------------------------------------------------------ SURVEY 8(f1) ----
  * Optimizer step + EMA in one multi-tensor pass over the trainable fp32 parameters.
  * Replaces `self.optimizer.step()` (code/fixmatch.py:123; the SGD-nesterov / Adam /
