@@ -338,6 +338,8 @@ class Case:
         self.launches_per_step = {"comatch": 5, "fixmatch": 3, "semiformer": 4}[wl["kind"]]
         if world > 1 and self.head is not None:
             self.launches_per_step += {"replicated": 1, "direct": 1, "peer": 4, "collective": 1}[self.head.exchange]
+        if self.ema_overlap and self.ema.overlap_mode == "capped" and self.ema.overlap_delay_ns > 0:
+            self.launches_per_step += 1              # the one-thread head-start kernel ahead of the overlapped update
         one = torch.ones((), dtype=torch.float32, device=dev)
         head, ema, model, keys = self.head, self.ema, self.model, self.keys
 

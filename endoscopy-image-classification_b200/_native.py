@@ -79,6 +79,8 @@ SIGNATURES = {
     "b200ssl_ema_multi_tensor": (_i32, [_vp, _i32, _i32, _i32, _f32, _f32, _i32, _vp]),
     "b200ssl_ema_multi_tensor_ctas": (_i32, [_vp, _i32, _i32, _i32, _f32, _f32, _i32, _i32, _vp]),
     "b200ssl_stream_delay": (_i32, [_i64, _vp]),
+    "b200ssl_probe_sm_set": (_i32, [_i32, _i32, _vp, _vp, _vp]),
+    "b200ssl_ema_multi_tensor_masked": (_i32, [_vp, _i32, _i32, _i32, _f32, _f32, _i32, _vp, _vp, _vp]),
     "b200ssl_opt_ema_multi_tensor": (_i32, [_vp, _i32, _vp, _i32, _f32, _f32, _vp]),
     "b200ssl_opt_ema_multi_tensor_dev": (_i32, [_vp, _i32, _vp, _i32, _f32, _f32, _vp]),
     "b200ssl_peer_control_bytes": (_sz, []),

@@ -132,6 +132,71 @@ __global__ void __launch_bounds__(kEmaThreads, 4) ema_multi_tensor_kernel(const 
   }
 }
 
+// ---- the update next to other kernels: a fixed set of SMs left alone ------------------------------------------------------
+// `mask` (one bit per SM id) marks SMs that the update must not use: a CTA that finds itself on one exits at once, the
+// others fetch 4096-element chunks from a device-side counter until the table is done.  Which SMs are free for the kernels
+// next to the update no longer depends on who was placed first.  probe_sm_set_kernel finds a set that clusters fit in.
+__device__ __forceinline__ unsigned smid() {
+  unsigned v;
+  asm volatile("mov.u32 %0, %%smid;" : "=r"(v));
+  return v;
+}
+
+template <typename T, int DT>
+__global__ void __launch_bounds__(kEmaThreads, 4) ema_masked_kernel(const b200ssl_ema_block* __restrict__ blocks, int n_blocks, float d,
+                                                                    float o, int mode, int do_ints, const unsigned* __restrict__ mask,
+                                                                    unsigned* sched) {
+  __shared__ int s_next[2];
+  pdl_launch_dependents();
+  pdl_wait();                                               // the weights may still be written by the previous kernel
+  const unsigned sm = smid();
+  const bool reserved = (__ldg(&mask[sm >> 5]) >> (sm & 31)) & 1u;
+  if (!reserved) {
+    if (threadIdx.x == 0) s_next[0] = (int)atomicAdd(&sched[0], 1u);
+    __syncthreads();
+    for (int it = 0;; ++it) {
+      const int b = s_next[it & 1];
+      if (b >= n_blocks) break;
+      if (threadIdx.x == 0) s_next[(it + 1) & 1] = (int)atomicAdd(&sched[0], 1u);    // next chunk, fetched under this one
+      const uint4 lo = ldg128(&blocks[b]);
+      const uint4 hi = ldg128(reinterpret_cast<const char*>(&blocks[b]) + 16);
+      void* e = reinterpret_cast<void*>(((unsigned long long)lo.y << 32) | lo.x);
+      const void* m = reinterpret_cast<const void*>(((unsigned long long)lo.w << 32) | lo.z);
+      const int count = (int)hi.x, dtype = (int)hi.y, repeat = (int)hi.z;
+      if (dtype == DT) {
+        ema_block_float<T>((T*)e, (const T*)m, count, d, o, repeat, mode);
+      } else if (do_ints) {
+        if (dtype == B200SSL_I64) ema_block_int<long long>((long long*)e, (const long long*)m, count, d, o, repeat, mode);
+        else if (dtype == B200SSL_I32) ema_block_int<int>((int*)e, (const int*)m, count, d, o, repeat, mode);
+        else if (dtype == B200SSL_U8) ema_block_int<unsigned char>((unsigned char*)e, (const unsigned char*)m, count, d, o, repeat, mode);
+      }
+      __syncthreads();
+    }
+  }
+  // the last CTA of the grid re-arms the scheduler for the next launch (stream order; CUDA-graph replay safe)
+  if (threadIdx.x == 0) {
+    __threadfence();
+    if (atomicAdd(&sched[1], 1u) == gridDim.x - 1) {
+      sched[0] = 0u;
+      sched[1] = 0u;
+      __threadfence();
+    }
+  }
+}
+
+// `gridDim.x` CTAs in clusters of `cluster` CTAs, one CTA per SM (shared-memory request), all resident at once: each marks
+// its SM in `mask`.  The marked set is one in which that many clusters fit side by side.
+__global__ void probe_sm_set_kernel(unsigned* mask, unsigned* counter) {
+  const unsigned sm = smid();
+  if (threadIdx.x == 0) {
+    atomicOr(&mask[sm >> 5], 1u << (sm & 31));
+    __threadfence();
+    atomicAdd(counter, 1u);
+    for (unsigned it = 0; *reinterpret_cast<volatile unsigned*>(counter) < gridDim.x && it < (1u << 22); ++it) {}   // bounded: never hangs
+  }
+  __syncthreads();
+}
+
 }  // namespace
 }  // namespace b200ssl
 
@@ -197,4 +262,49 @@ extern "C" int b200ssl_stream_delay(int64_t nanoseconds, void* stream) {
   if (nanoseconds == 0) return 0;
   delay_kernel<<<1, 1, 0, as_stream(stream)>>>((unsigned long long)nanoseconds);
   return check_launch("b200ssl_stream_delay");
+}
+
+extern "C" int b200ssl_probe_sm_set(int32_t n_clusters, int32_t cluster, uint32_t* mask8, uint32_t* counter, void* stream) {
+  const char* fn = "b200ssl_probe_sm_set";
+  if (!mask8 || !counter) return fail(B200SSL_E_NULL, "%s: NULL buffer", fn);
+  if (n_clusters < 1 || cluster < 1 || cluster > 8 || (cluster & (cluster - 1)) || n_clusters * cluster > kNumSMs / 2)
+    return fail(B200SSL_E_ARG, "%s: %d clusters of %d (cluster a power of two <= 8, at most half the SMs)", fn, n_clusters, cluster);
+  const size_t smem = 160 * 1024;                          // more than half an SM: one CTA per SM
+  cudaError_t e = cudaFuncSetAttribute(probe_sm_set_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e == cudaSuccess)
+    e = launch_pdl(PDL_EMA, probe_sm_set_kernel, dim3((unsigned)(n_clusters * cluster)), dim3(32), smem, as_stream(stream),
+                   dim3((unsigned)cluster, 1, 1), mask8, counter);
+  if (e != cudaSuccess) return fail((int)e, "%s: %s", fn, cudaGetErrorString(e));
+  return check_launch(fn);
+}
+
+extern "C" int b200ssl_ema_multi_tensor_masked(const b200ssl_ema_block* blocks, int32_t n_blocks, int32_t float_dtype, int32_t do_ints,
+                                               float decay, float one_minus_decay, int32_t mode, const uint32_t* sm_mask8,
+                                               uint32_t* sched2, void* stream) {
+  const char* fn = "b200ssl_ema_multi_tensor_masked";
+  if (!blocks || !sm_mask8 || !sched2) return fail(B200SSL_E_NULL, "%s: NULL argument", fn);
+  if (reinterpret_cast<uintptr_t>(blocks) & 15u) return fail(B200SSL_E_ALIGN, "%s: block table must be 16-byte aligned", fn);
+  if (n_blocks <= 0) return fail(B200SSL_E_SHAPE, "%s: n_blocks must be > 0", fn);
+  if (mode != 0 && mode != 1) return fail(B200SSL_E_ARG, "%s: mode %d (0 update, 1 set)", fn, mode);
+  const int grid = kNumSMs * 4;                            // four CTAs per SM everywhere; the ones on masked SMs leave at once
+  cudaStream_t st = as_stream(stream);
+  cudaError_t e;
+  switch (float_dtype) {
+    case B200SSL_F32:
+      e = launch_pdl(PDL_EMA, ema_masked_kernel<float, B200SSL_F32>, dim3(grid), dim3(kEmaThreads), 0, st, dim3(1, 1, 1), blocks, n_blocks, decay,
+                     one_minus_decay, mode, do_ints, sm_mask8, sched2);
+      break;
+    case B200SSL_BF16:
+      e = launch_pdl(PDL_EMA, ema_masked_kernel<__nv_bfloat16, B200SSL_BF16>, dim3(grid), dim3(kEmaThreads), 0, st, dim3(1, 1, 1), blocks,
+                     n_blocks, decay, one_minus_decay, mode, do_ints, sm_mask8, sched2);
+      break;
+    case B200SSL_F16:
+      e = launch_pdl(PDL_EMA, ema_masked_kernel<__half, B200SSL_F16>, dim3(grid), dim3(kEmaThreads), 0, st, dim3(1, 1, 1), blocks, n_blocks,
+                     decay, one_minus_decay, mode, do_ints, sm_mask8, sched2);
+      break;
+    default:
+      return fail(B200SSL_E_DTYPE, "%s: float_dtype %d (want F32, BF16 or F16)", fn, float_dtype);
+  }
+  if (e != cudaSuccess) return fail((int)e, "%s: cudaLaunchKernelEx: %s", fn, cudaGetErrorString(e));
+  return check_launch(fn);
 }

@@ -112,14 +112,18 @@ class _EmaPlan:
             return False
         return all(t.data_ptr() == p for t, p in self._sentinels)
 
-    def launch(self, decay: float, mode: int, max_ctas: int = 0) -> None:
-        """``max_ctas`` > 0: cap the grid (``b200ssl_ema_multi_tensor_ctas``)."""
+    def launch(self, decay: float, mode: int, max_ctas: int = 0, masked=None) -> None:
+        """``max_ctas`` > 0: cap the grid (``b200ssl_ema_multi_tensor_ctas``); ``masked = (sm_mask, sched)``: leave the marked
+        SMs alone (``b200ssl_ema_multi_tensor_masked``)."""
         d32 = float(np.float32(decay))
         o32 = float(np.float32(1.0 - decay))
         lib, st = N.lib(), N.stream_ptr(self.device)
         for i, fd in enumerate(self.float_dtypes):
             ints = 1 if (i == 0 and self.has_ints) else 0
-            if max_ctas > 0:
+            if masked is not None:
+                N.check(lib.b200ssl_ema_multi_tensor_masked(self.table.data_ptr(), self.n_blocks, fd, ints, d32, o32, mode,
+                                                            masked[0].data_ptr(), masked[1].data_ptr(), st), "ema_multi_tensor_masked")
+            elif max_ctas > 0:
                 N.check(lib.b200ssl_ema_multi_tensor_ctas(self.table.data_ptr(), self.n_blocks, fd, ints, d32, o32, mode, int(max_ctas), st),
                         "ema_multi_tensor_ctas")
             else:
@@ -137,6 +141,8 @@ class ModelEMA(object):
     parameters by hand (``load_state_dict`` copies in place and needs nothing).
     """
 
+    OVERLAP_MODE = "capped"            # 'masked': the update leaves a probed set of SMs alone (b200ssl_ema_multi_tensor_masked)
+    OVERLAP_FREE_CLUSTERS = 6          # ... of this many clusters of 8 SMs
     OVERLAP_DELAY_NS = 500             # head start (ns) given to the kernel queued next to an overlapped update (0: 2-3 slow blocks of 25; >= 2500: the whole PDL-chained head is resident first and the update starves, 90 us)
     OVERLAP_CTAS = 4 * (148 - 48)      # grid of an overlapped update: 4 CTAs per SM on all but 48 SMs (see __init__; 336..464 measured, bench cfg 2)
 
@@ -163,6 +169,8 @@ class ModelEMA(object):
         self.overlap = bool(overlap)
         self.overlap_ctas = int(self.OVERLAP_CTAS if overlap_ctas is None else overlap_ctas)
         self.overlap_delay_ns = int(os.environ.get("B200SSL_EMA_DELAY_NS", self.OVERLAP_DELAY_NS))
+        self.overlap_mode = os.environ.get("B200SSL_EMA_OVERLAP_MODE", self.OVERLAP_MODE)      # 'masked' | 'capped'
+        self._masked = None
         if self.overlap:
             # the head's launch planners keep to the SMs the capped update leaves free (process-wide setting)
             N.lib().b200ssl_set_head_sm_budget(max(148 - self.overlap_ctas // 4, 8))
@@ -201,11 +209,30 @@ class ModelEMA(object):
             self._side = torch.cuda.Stream(dev)                 # default (low) priority: the head's stream may be created above it
         cur = torch.cuda.current_stream(dev)
         self._side.wait_stream(cur)                               # after everything queued so far (the optimizer step)
+        if self.overlap_mode == "masked" and self._masked is None and not torch.cuda.is_current_stream_capturing():
+            self._probe_sm_set(dev)
         with torch.cuda.stream(self._side):
-            if self.overlap_delay_ns > 0:                         # the kernel queued next on the caller's stream places its CTAs first
-                N.check(N.lib().b200ssl_stream_delay(self.overlap_delay_ns, N.stream_ptr(dev)), "stream_delay")
-            plan.launch(self.decay, 0, max_ctas=self.overlap_ctas)
+            if self._masked is not None:                          # a fixed set of SMs left alone: placement order does not matter
+                plan.launch(self.decay, 0, masked=self._masked)
+            else:
+                if self.overlap_delay_ns > 0:                     # the kernel queued next on the caller's stream places its CTAs first
+                    N.check(N.lib().b200ssl_stream_delay(self.overlap_delay_ns, N.stream_ptr(dev)), "stream_delay")
+                plan.launch(self.decay, 0, max_ctas=self.overlap_ctas)
         self._pending = True
+
+    def _probe_sm_set(self, dev) -> None:
+        """Find ``OVERLAP_FREE_CLUSTERS`` x 8 SMs in which that many clusters of 8 one-CTA-per-SM blocks fit side by side (the
+        head's tensor-core kernels run as such clusters) and keep them free of the update from now on."""
+        mask = torch.zeros(8, dtype=torch.int32, device=dev)
+        scratch = torch.zeros(1, dtype=torch.int32, device=dev)
+        N.check(N.lib().b200ssl_probe_sm_set(self.OVERLAP_FREE_CLUSTERS, 8, mask.data_ptr(), scratch.data_ptr(), N.stream_ptr(dev)),
+                "probe_sm_set")
+        bits = sum(bin(int(w) & 0xFFFFFFFF).count("1") for w in mask.tolist())       # synchronises (once)
+        if bits == 8 * self.OVERLAP_FREE_CLUSTERS:
+            self._masked = (mask, torch.zeros(2, dtype=torch.int32, device=dev))
+            N.lib().b200ssl_set_head_sm_budget(bits)
+        else:                                                     # e.g. a busy device: keep the capped-grid form
+            self.overlap_mode = "capped"
 
     def join(self):
         """Make the current stream wait for an overlapped ``update`` (no-op otherwise)."""

@@ -342,6 +342,17 @@ B200SSL_API int b200ssl_ema_multi_tensor_ctas(const b200ssl_ema_block* blocks, i
                                   int32_t do_ints, float decay, float one_minus_decay,
                                   int32_t mode /*0 update, 1 set*/, int32_t max_ctas, void* stream);
 
+/* The update with a set of SMs left alone: `sm_mask8` (8 x uint32, bit i = SM id i) marks SMs whose CTAs exit at once; the
+ * other CTAs fetch the table's chunks from the device-side scheduler `sched2` (2 x uint32, zero before the first launch,
+ * re-armed by every launch).  For an update that runs next to kernels which need whole SMs (ema.ModelEMA(overlap=True)): the
+ * marked SMs are free for them whatever the order in which the launches were placed.  b200ssl_probe_sm_set finds a set in
+ * which `n_clusters` thread-block clusters of `cluster` one-CTA-per-SM blocks fit side by side (it ORs their SM ids into
+ * `mask8`; `counter` is one zeroed uint32 of scratch). */
+B200SSL_API int b200ssl_probe_sm_set(int32_t n_clusters, int32_t cluster, uint32_t* mask8, uint32_t* counter, void* stream);
+B200SSL_API int b200ssl_ema_multi_tensor_masked(const b200ssl_ema_block* blocks, int32_t n_blocks, int32_t float_dtype,
+                                    int32_t do_ints, float decay, float one_minus_decay, int32_t mode /*0 update, 1 set*/,
+                                    const uint32_t* sm_mask8, uint32_t* sched2, void* stream);
+
 /* A one-thread kernel that holds `stream` for `nanoseconds` (<= 1 ms).  ema.ModelEMA(overlap=True) queues it ahead of the
  * capped update on the side stream: the head's first kernel, queued at the same moment on the other stream, then places
  * its CTAs first -- the order that keeps whole SMs free for the rest of the head. */
