@@ -171,6 +171,7 @@ class ModelEMA(object):
         self.overlap_delay_ns = int(os.environ.get("B200SSL_EMA_DELAY_NS", self.OVERLAP_DELAY_NS))
         self.overlap_mode = os.environ.get("B200SSL_EMA_OVERLAP_MODE", self.OVERLAP_MODE)      # 'masked' | 'capped'
         self._masked = None
+        self.free_clusters = int(os.environ.get("B200SSL_EMA_FREE_CLUSTERS", self.OVERLAP_FREE_CLUSTERS))
         if self.overlap:
             # the head's launch planners keep to the SMs the capped update leaves free (process-wide setting)
             N.lib().b200ssl_set_head_sm_budget(max(148 - self.overlap_ctas // 4, 8))
@@ -225,10 +226,10 @@ class ModelEMA(object):
         head's tensor-core kernels run as such clusters) and keep them free of the update from now on."""
         mask = torch.zeros(8, dtype=torch.int32, device=dev)
         scratch = torch.zeros(1, dtype=torch.int32, device=dev)
-        N.check(N.lib().b200ssl_probe_sm_set(self.OVERLAP_FREE_CLUSTERS, 8, mask.data_ptr(), scratch.data_ptr(), N.stream_ptr(dev)),
+        N.check(N.lib().b200ssl_probe_sm_set(self.free_clusters, 8, mask.data_ptr(), scratch.data_ptr(), N.stream_ptr(dev)),
                 "probe_sm_set")
         bits = sum(bin(int(w) & 0xFFFFFFFF).count("1") for w in mask.tolist())       # synchronises (once)
-        if bits == 8 * self.OVERLAP_FREE_CLUSTERS:
+        if bits == 8 * self.free_clusters:
             self._masked = (mask, torch.zeros(2, dtype=torch.int32, device=dev))
             N.lib().b200ssl_set_head_sm_budget(bits)
         else:                                                     # e.g. a busy device: keep the capped-grid form

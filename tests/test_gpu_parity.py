@@ -285,6 +285,49 @@ def test_ema_torchvision_bit_exact(pkg, arch, dtype):
     assert ema.plan.unique_elems == sum(v.numel() for v in ref_e.values())
 
 
+@pytest.mark.parametrize("mode", ["capped", "masked"])
+def test_ema_overlapped_forms_bit_exact(pkg, mode):
+    """ModelEMA(overlap=True): the update on a side stream -- with a capped grid behind a short head start, or with a probed
+    set of SMs left alone and chunks fetched from a device-side scheduler -- gives the bits of the in-stream update, launch
+    after launch (the scheduler re-arms itself) and replayed from a CUDA graph."""
+    import torchvision
+    torch.manual_seed(0)
+    model = torchvision.models.resnet18(num_classes=C).cuda()
+    ref = pkg["ema"].ModelEMA(model, decay=0.999, device="cuda")
+    ema = pkg["ema"].ModelEMA(model, decay=0.999, device="cuda", overlap=True)
+    ema.overlap_mode = mode
+    g = torch.Generator(device="cuda").manual_seed(1)
+
+    def perturb():
+        with torch.no_grad():
+            for v in model.state_dict().values():
+                if v.is_floating_point():
+                    v.add_(1e-3 * torch.randn(v.shape, generator=g, device="cuda"))
+                else:
+                    v.add_(3)
+
+    def same():
+        torch.cuda.synchronize()
+        return all(torch.equal(a, b) for a, b in zip(ema.ema.state_dict().values(), ref.ema.state_dict().values()))
+
+    for _ in range(3):
+        perturb()
+        ref.update(model)
+        ema.update(model)
+        ema.join()
+    assert (ema._masked is not None) == (mode == "masked")
+    assert same()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):                           # (the capture does not execute)
+        ema.update(model)
+        ema.join()
+    for _ in range(3):
+        perturb()
+        ref.update(model)
+        graph.replay()
+    assert same()
+
+
 def test_ema_rejects_cpu_and_detects_realloc(pkg):
     import torch.nn as nn
     m = nn.Linear(8, 8)
