@@ -516,14 +516,12 @@ def test_bank_smooth_fp32_storage_both_paths(pkg, rows, K, simt):
     assert rel_err(numer.double().cpu() / rowsum.double().cpu().unsqueeze(1), (A @ qp.double()) / A.sum(1, keepdim=True)) < FP32_TOL
 
 
-@pytest.mark.parametrize("simt", [0, 1])
-@pytest.mark.parametrize("rows,D", [(448, 64), (1, 8), (63, 16), (65, 64), (1000, 128), (3584, 64)])
+@pytest.mark.parametrize("rows,D,simt", [(448, 64, 0), (448, 64, 1), (1, 8, 0), (63, 16, 0), (65, 64, 0), (65, 64, 1), (1000, 128, 0),
+                                         (3584, 64, 0), (3584, 64, 1)])
 def test_contrast_fwd_bwd_vs_oracle(pkg, rows, D, simt):
     """fp32 storage against the fp64 oracle at 1e-5.  64-wide embeddings run the tensor-core kernels on bf16 hi + mid operands
     (``simt=0``, default) or the exact-fp32 FFMA tiles (``simt=1``); other widths always the FFMA tiles."""
     from endoscopy_image_classification_b200 import _native as N
-    if simt and D != 64:
-        pytest.skip("only 64-wide embeddings have two paths")
     N.lib().b200ssl_debug_set_k3_f32_simt(simt)
     try:
         _contrast_fwd_bwd_vs_oracle(pkg, rows, D)
