@@ -1,28 +1,30 @@
-// K3 on the 5th-generation tensor cores: memory-smoothing partial sums against the
-// bf16 bank (code/comatch.py:180-181), FlashAttention-shaped, never materialising
-// A[rows, K]:
+// K3 on the 5th-generation tensor cores: memory-smoothing partial sums against the bank
+// (code/comatch.py:180-181), FlashAttention-shaped, never materialising A[rows, K]:
 //
-//   TMA (128B swizzle)        tcgen05.mma kind::f16           tcgen05.ld + MUFU
+//   TMA (128B swizzle)        tcgen05.mma kind::f16           tcgen05.ld + FMUL2 + MUFU
 //   F tile [128 x 64]   -+->  S[128 x 128] = F Qf^T (TMEM) -> E = exp2(S * log2e/tau)
-//   Qf tile [128 x 64]  -+                                     rowsum += E ; P = bf16(E) -> smem (swizzled)
-//   QpT tile [32 x 128] ---->  numer[128 x 32] += P QpT^T (TMEM accumulator, K = 128 keys)
+//   Qf tile [128 x 64]  -+                                     P = bf16(E) -> back into TMEM (tcgen05.st)
+//   QpT tile [32 x 128] ---->  [numer | rowsum][128 x 32] += P [QpT | 1]^T   (A = P read from TMEM, K = 128 keys)
 //
-// Warp roles (576 threads): warp 0 = TMEM allocator + TMA producer, warp 1 = MMA
-// issuer (one thread), warps 2..17 = epilogue (4 threads per TMEM lane = query row,
-// 32 key columns each).  S (TMEM) and P (smem) are double-buffered so GEMM1 of unit
-// j+1 and GEMM2 of unit j-1 overlap the exp of unit j; the bank is split over a
-// cluster of CTAs whose partials are folded through DSMEM in rank order (deterministic).
-// Measured dead ends of round 2 (profiles/r02_k3_experiments.md): an FMA-pipe polynomial
-// for part of the exponentials, two epilogue groups on alternate tiles, and a software-
-// pipelined tcgen05.ld all ran SLOWER than this plain ld -> exp -> st chain: TMEM reads,
-// MUFU and shared-memory stores share the SM's MIO path, so overlapping them buys nothing.
-// Packed fp16 exponentials (ex2.approx.f16x2) do not help either: they compile to two MUFU.EX2.F16 per pair, and
-// tcgen05.mma kind::f16 takes no fp16 A next to a bf16 B (illegal instruction), so P would drag the bank copy to fp16.
+// Warp roles (576 threads): warp 0 = TMEM allocator + TMA producer, warp 1 = MMA issuer, warps 2..17 = epilogue (4 threads
+// per TMEM lane = query row, 32 key columns each).  S and P are double-buffered in tensor memory so GEMM1 of unit j+1 and
+// GEMM2 of unit j-1 overlap the exponentials of unit j; the bank is split over a cluster of CTAs whose partials are folded
+// through DSMEM in rank order (deterministic).
 //
-// Bank layout for this path: queue_feats [K, 64] bf16 row-major (a row is exactly one
-// 128-byte swizzle row) and a transposed, class-padded copy of the probabilities
-// queue_probs_t [32, K] bf16 (K-major B operand of the second GEMM), both written by
-// b200ssl_bank_enqueue.
+// What bounds it (profiles/r02_k3_experiments.md, tools/micro/): a unit is 12 SMALL MMAs (628 clocks of tensor pipe, 43-88 each)
+// and 16384 exponentials (1096 clocks of MUFU).  The MMA warp therefore runs its loop in warp-uniform control flow and issues
+// from one elected lane -- inside `if (lane == 0)` the compiler rebuilds every tcgen05.mma operand with an ELECT / R2UR sequence,
+// ~17 dependent instructions per MMA, and THAT bounded the round-1 kernel, not the exponentials.  Keeping P in tensor memory
+// halves the shared-memory traffic of a unit and removes the st.shared + fence.proxy.async of every epilogue thread.  Measured
+// dead ends: an FMA-pipe polynomial for part of the exponentials (pays nothing until the kernel is MUFU-bound; 8 of 32 slots are
+// a wash now), two epilogue groups on alternate tiles, issuing the TMEM read of the next unit early (twice).
+//
+// fp32 storage (NT = 2): the same kernel on bf16 hi + mid operands made by split_operands_kernel (three cross-term MMA groups
+// per GEMM, P_hi / P_mid in TMEM, unit accumulators summed in registers) -- 1e-6 of fp64, see the kernel.
+//
+// Bank layout for this path: queue_feats [K, 64] bf16 row-major (a row is exactly one 128-byte swizzle row) and a transposed,
+// class-padded copy of the probabilities queue_probs_t [32, K] bf16 (K-major B operand of the second GEMM, row C = ones ->
+// row sums), both written by b200ssl_bank_enqueue.
 #include <math.h>
 
 #include <cooperative_groups.h>
@@ -833,8 +835,8 @@ static int bank_smooth_tc_impl(int nt, long long qpt_ld, const void* feats, cons
                 "the reduction tiles must fit in the drained pipeline buffers");
   static_assert(2 * kBN + kMaxMT * kCP <= (int)kTmemCols, "TMEM budget");
   // Share of the exponentials computed on the FMA pipe (of 32 per thread and S tile).  Measured on B200 (tools/k3_tune.py,
-  // profiles/r02_k3_experiments.md): every polynomial slot ADDS ~25 clocks per S tile at every size -- the epilogue is bound by
-  // its serial ld -> exp -> st -> fence chain per tile, not by the MUFU rate -- so the default is 0; the knob stays for A/B.
+  // profiles/r02_k3_experiments.md): while the MMA issue path bounded the kernel every polynomial slot ADDED ~25 clocks per
+  // S tile; now 8 of 32 are a wash (81.5 vs 82.1 us at rows 3584 x K 65536) and 16 lose -- the default stays 0, the knob for A/B.
   const int npoly = g_force_poly >= 0 ? g_force_poly : 0;
   const dim3 grid((unsigned)groups, (unsigned)p.nsplit, 1);
   cudaError_t e;

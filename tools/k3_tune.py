@@ -1,6 +1,7 @@
 #!/usr/bin/env python
 """A/B of the tensor-core K3 (csrc/bank_tc.cu) on one GPU: launch plans (row tiles per CTA x cluster size x clusters per
-row group; 0 = the planner's choice) and the share of the exponentials on the FMA-pipe polynomial, per problem size.
+row group; 0 = the planner's choice) and the share of the exponentials on the FMA-pipe polynomial (--poly N of 32; + 100 keeps
+the P tile in shared memory, the round-1 form), per problem size.
 Times graphs of back-to-back launches with CUDA events and checks every variant against fp64 math on the same bf16
 operands.  One JSON line per (size, variant); the first line reports the cluster residency the driver grants.
 
