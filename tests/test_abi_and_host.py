@@ -86,6 +86,21 @@ def test_argument_validation_without_gpu(native):
     assert lib.b200ssl_ema_multi_tensor(p256, 4, 3, 1, 0.999, 0.001, 0, None) == E_DTYPE
     assert lib.b200ssl_ema_multi_tensor(p256, 4, 0, 1, 0.999, 0.001, 7, None) == E_ARG
     assert lib.b200ssl_scale_inplace(None, 4, 0, p, 1.0, None) == E_NULL
+    # the forms of the update that run next to other kernels (ema.ModelEMA(overlap=True))
+    ctas, masked = lib.b200ssl_ema_multi_tensor_ctas, lib.b200ssl_ema_multi_tensor_masked
+    assert ctas(None, 4, 0, 1, 0.999, 0.001, 0, 400, None) == E_NULL
+    assert ctas(p256, 4, 0, 1, 0.999, 0.001, 0, -1, None) == E_ARG                    # negative grid cap
+    assert ctas(p256 + 8, 4, 0, 1, 0.999, 0.001, 0, 400, None) == E_ALIGN
+    assert masked(p256, 4, 0, 1, 0.999, 0.001, 0, None, p, None) == E_NULL            # no SM mask
+    assert masked(p256, 4, 0, 1, 0.999, 0.001, 0, p, None, None) == E_NULL            # no scheduler words
+    assert masked(p256, 0, 0, 1, 0.999, 0.001, 0, p, p, None) == E_SHAPE
+    assert masked(p256, 4, 9, 1, 0.999, 0.001, 0, p, p, None) == E_DTYPE
+    assert lib.b200ssl_probe_sm_set(6, 8, None, p, None) == E_NULL
+    assert lib.b200ssl_probe_sm_set(6, 3, p, p, None) == E_ARG                        # cluster not a power of two
+    assert lib.b200ssl_probe_sm_set(12, 8, p, p, None) == E_ARG                       # more than half the SMs
+    assert lib.b200ssl_stream_delay(-5, None) == E_ARG
+    assert lib.b200ssl_stream_delay(10**9, None) == E_ARG
+    assert lib.b200ssl_stream_delay(0, None) == 0                                     # nothing to launch
     # multi-rank bank / peer memory entry points
     out = C.c_void_p()
     assert lib.b200ssl_peer_alloc(16, C.byref(out), p) == E_ARG                      # smaller than the control page
@@ -315,6 +330,31 @@ def test_k3_launch_plan_invariants(native):
     lib.b200ssl_debug_smooth_plan(3584, 65536, 0, out)
     mt, cl, no = list(out)
     assert ((28 + mt - 1) // mt) * no <= lib.b200ssl_debug_max_active_clusters(cl)
+
+
+def test_head_sm_budget_shapes_the_k3_plan(native):
+    """b200ssl_set_head_sm_budget (set by ModelEMA(overlap=True)): the K3 planner keeps to that many CTAs while the
+    constrained plan costs at most 1.5 x the free one; big problems and shards read over NVLink ignore it."""
+    lib = native.lib()
+    out = (C.c_int32 * 3)()
+
+    def ctas(rows, K, remote=0):
+        assert lib.b200ssl_debug_smooth_plan(rows, K, remote, out) == 0
+        mt, cl, no = list(out)
+        return ((rows + 127) // 128 + mt - 1) // mt * cl * no
+
+    assert lib.b200ssl_set_head_sm_budget(0) == 0
+    free_n8, free_big, free_remote = ctas(448, 20480), ctas(3584, 65536), ctas(448, 65536, 1)
+    assert free_n8 > 48                                          # cfg 2's ring at N = 8: the free plan spreads over the chip
+    try:
+        assert lib.b200ssl_set_head_sm_budget(48) == 0            # returns the previous value
+        assert ctas(448, 2560) <= 48 and ctas(448, 20480) <= 48   # the head stays inside the SMs the capped update leaves free
+        assert ctas(3584, 65536) == free_big                      # 28 row tiles x 512 key tiles: a 48-CTA plan would cost > 1.5 x
+        assert ctas(448, 65536, 1) == free_remote                 # shards over NVLink live off the tile streams in flight
+        assert lib.b200ssl_set_head_sm_budget(1000) == 48         # out of range = no budget
+        assert ctas(448, 20480) == free_n8
+    finally:
+        lib.b200ssl_set_head_sm_budget(0)
 
 
 def test_k3_polynomial_exp2_math():
