@@ -343,8 +343,16 @@ class Case:
         one = torch.ones((), dtype=torch.float32, device=dev)
         head, ema, model, keys = self.head, self.ema, self.model, self.keys
 
-        def step(batch):
-            if self.ema_overlap:
+        # masked form of the overlapped update: its placement is independent of the head's, so it is forked ahead of the inputs
+        # (end-to-end graph: under the H2D copy); capped form: forked together with the head's first kernel
+        prefork = self.ema_overlap and self.ema.overlap_mode == "masked"
+
+        def pre():
+            if prefork:
+                ema.update(model)
+
+        def main_part(batch):
+            if self.ema_overlap and not prefork:
                 ema.update(model)                                                 # side stream; joined below
             for k in self.grad_keys:
                 batch[k].grad = None
@@ -366,14 +374,18 @@ class Case:
                 ema.update(model)
             return total
 
-        self.step = step
+        def step(batch):                                                          # the eager step
+            pre()
+            return main_part(batch)
+
+        self.step, self.pre, self.main_part = step, pre, main_part
         self._GraphedStep = GraphedStep
         self.graphed = None
 
     def capture(self):
         n_rows = self.wl["B"] + self.Bu
         head = self.head
-        self.graphed = self._GraphedStep(lambda b: self.step(b), self.resident[0], self.ctx.dev, warmup=3,
+        self.graphed = self._GraphedStep(lambda b: self.main_part(b), self.resident[0], self.ctx.dev, warmup=3, pre_fn=self.pre,
                                          on_replay=(lambda: head.note_graph_replay(n_rows)) if head is not None else None,
                                          after_capture=(lambda: head.sync_ptr_from_device()) if head is not None else None,
                                          high_priority=self.ema_overlap)

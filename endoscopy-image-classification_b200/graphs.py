@@ -17,6 +17,7 @@ Two graphs are captured over the same static tensors:
 """
 from __future__ import annotations
 
+import ctypes
 from typing import Callable, Dict, Optional
 
 import torch
@@ -28,14 +29,17 @@ class GraphedStep:
     def __init__(self, step_fn: Callable[[Dict[str, torch.Tensor]], torch.Tensor], example: Dict[str, torch.Tensor],
                  device, warmup: int = 3, on_replay: Optional[Callable[[], None]] = None,
                  after_capture: Optional[Callable[[], None]] = None, capture_host_io: bool = True,
-                 high_priority: bool = False):
+                 high_priority: bool = False, pre_fn: Optional[Callable[[], None]] = None):
         """``step_fn(static_inputs) -> scalar loss tensor`` must do all its work on the current
         stream.  ``example`` gives shapes/dtypes (and the initial contents) of the inputs.
         ``on_replay`` runs after every replay (host mirrors of device state, e.g.
         ``CoMatchHead.note_graph_replay``); ``after_capture`` runs once after the captures, whose
         host code ran without device work (e.g. ``CoMatchHead.sync_ptr_from_device``).  ``high_priority``: capture on a
         high-priority stream, so the kernel nodes of ``step_fn``'s own stream outrank work it forks onto default-priority
-        side streams (an overlapped ``ModelEMA.update``: the head's few CTAs are placed as soon as an SM has room)."""
+        side streams (an overlapped ``ModelEMA.update``: the head's few CTAs are placed as soon as an SM has room).
+        ``pre_fn``: work that does not depend on the inputs (forking that update); it is queued AHEAD of the H2D copy of the
+        end-to-end graph, so the copy runs under it.  Only for work whose placement does not have to follow the head's first
+        kernel (``ModelEMA.overlap_mode == 'masked'``)."""
         self.device = torch.device(device)
         self.on_replay = None
         # All inputs live in ONE device buffer (256-byte aligned slices) mirrored by ONE pinned host buffer, so the
@@ -55,6 +59,7 @@ class GraphedStep:
         self.staging = {k: carve(self._packed_host, k, v) for k, v in example.items()}
         for k, v in example.items():
             self.static[k].copy_(v.detach())
+        self._stage_plan = [(k, b.data_ptr(), b.numel() * b.element_size(), b.dtype, b.shape) for k, b in self.staging.items()]
         self.result_host = torch.zeros(1, dtype=torch.float32).pin_memory()
         self.h2d_bytes = int(self._packed_dev.numel())       # what the H2D node moves per step (tensors + alignment padding)
         self._calls = 0
@@ -62,6 +67,8 @@ class GraphedStep:
         side.wait_stream(torch.cuda.current_stream(self.device))
         with torch.cuda.stream(side):
             for _ in range(max(1, warmup)):
+                if pre_fn is not None:
+                    pre_fn()
                 step_fn(self.static)
                 self._note()
         torch.cuda.current_stream(self.device).wait_stream(side)
@@ -69,6 +76,8 @@ class GraphedStep:
         self.graph = torch.cuda.CUDAGraph()
         cap = {"stream": torch.cuda.Stream(self.device, priority=-1)} if high_priority else {}
         with torch.cuda.graph(self.graph, **cap):
+            if pre_fn is not None:
+                pre_fn()
             self.result = step_fn(self.static).detach().reshape(1).float()
         # gradients the captured backward writes (static buffers of THIS graph)
         self.grads = {k: v.grad for k, v in self.static.items() if v.grad is not None}
@@ -77,6 +86,8 @@ class GraphedStep:
         if capture_host_io:
             self.graph_host = torch.cuda.CUDAGraph()
             with torch.cuda.graph(self.graph_host, pool=self.graph.pool(), **cap):
+                if pre_fn is not None:
+                    pre_fn()
                 with torch.no_grad():
                     self._packed_dev.copy_(self._packed_host, non_blocking=True)      # one H2D node for all inputs
                 res = step_fn(self.static).detach().reshape(1).float()
@@ -105,8 +116,14 @@ class GraphedStep:
         if self.graph_host is None:
             raise RuntimeError("captured without host I/O")
         if host_batch is not None:
-            for k, buf in self.staging.items():
-                buf.copy_(host_batch[k])
+            # ordinary host tensors -> the pinned staging buffer: a plain memmove per tensor (a torch ``copy_`` of a few KB
+            # is ~2 us of dispatch; seven of them were an eighth of the end-to-end step)
+            for k, dst, nbytes, dtype, shape in self._stage_plan:
+                src = host_batch[k]
+                if src.dtype == dtype and src.shape == shape and src.device.type == "cpu" and src.is_contiguous():
+                    ctypes.memmove(dst, src.data_ptr(), nbytes)
+                else:
+                    self.staging[k].copy_(src)
         self.graph_host.replay()
         self._note()
         torch.cuda.current_stream(self.device).synchronize()
