@@ -84,10 +84,12 @@ struct ContrastTcParams {
 __device__ __forceinline__ float ex2a(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float lg2a(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float rcpa(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
-// 1 / x for x > 0 on the FMA pipe (the epilogues are bound by the MUFU unit): exponent-flip seed (12 % off) and two Newton
-// steps -> 2.4e-4 relative, inside the bf16 kernels' 1e-2 budget by 40 x
+// 1 / x for x > 0 on the FMA pipe (the epilogues are bound by the MUFU unit): exponent-flip seed (12 % off) and three Newton
+// steps -> 6e-8 relative.  (Two steps, 2.4e-4, are inside the bf16 budget too -- but the forward now closes r_i = sum qn P / (P + eps)
+// in exact arithmetic while the backward evaluates P / (P + eps) per pair, and the two have to cancel in dZ = P (G - r).)
 __device__ __forceinline__ float rcp_fma(float x) {
   float y = __uint_as_float(0x7EF311C7u - __float_as_uint(x));
+  y = y * fmaf(-x, y, 2.0f);
   y = y * fmaf(-x, y, 2.0f);
   return y * fmaf(-x, y, 2.0f);
 }
@@ -240,6 +242,20 @@ contrast_tc_fwd_kernel(const __grid_constant__ CUtensorMap tm_f0, const __grid_c
   float inv_rs = 1.f, inv_qs = 1.f;
 
   const int rows_i = (int)p.rows, gi_i = (int)gi;
+  // pass 0 accumulators of a thread: mo[0] = sum E, mo[1] = sum qm, mo[2] = sum qm*y (y = log2 of E), mo[3..6] = sum qm * E^-k
+  // (k = 1..4), mo[7] = min of E over the pairs of the graph -- everything pass B needs, if the Taylor series below holds
+  float mo[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 3.0e38f};
+  auto moments = [&](float y, float E, float qm) {
+    const float ei = rcp_pos<NT>(E), ei2 = ei * ei;
+    mo[1] += qm;
+    mo[2] = fmaf(qm, y, mo[2]);
+    const float qe = qm * ei;
+    mo[3] += qe;
+    mo[4] = fmaf(qe, ei, mo[4]);
+    mo[5] = fmaf(qe, ei2, mo[5]);
+    mo[6] = fmaf(qe * ei, ei2, mo[6]);
+    mo[7] = qm > 0.f ? fminf(mo[7], E) : mo[7];
+  };
   auto epilogue_tile = [&](int pass, int buf, long long j0ll, float& a0, float& a1) {
     const int j0 = (int)j0ll;
     const uint32_t sq_addr = lane_addr + buf * (2 * kT);
@@ -259,8 +275,9 @@ contrast_tc_fwd_kernel(const __grid_constant__ CUtensorMap tm_f0, const __grid_c
         for (int j = 0; j < 16; ++j) {
           float q = __uint_as_float(qv[j]);
           if (NT == 2 && q > p.th - 2e-5f) q = exact_q(p.probs, p.C, gi, j0 + col0 + j);
-          a0 += ex2a(__uint_as_float(sv[j]) * p.scale);                           // comatch.py:200
-          a1 += (q >= p.th) ? q : 0.f;                                            // :206-208
+          const float y = __uint_as_float(sv[j]) * p.scale, E = ex2a(y);
+          mo[0] += E;                                                             // comatch.py:200
+          moments(y, E, (q >= p.th) ? q : 0.f);                                   // :206-208
         }
       } else {
 #pragma unroll
@@ -270,8 +287,9 @@ contrast_tc_fwd_kernel(const __grid_constant__ CUtensorMap tm_f0, const __grid_c
           float q = __uint_as_float(qv[j]);
           if (NT == 2 && ok && q > p.th - 2e-5f) q = exact_q(p.probs, p.C, gi, gj);
           q = (gi_i == gj) ? 1.f : q;                                             // fill_diagonal_(1)  :205
-          a0 += ok ? ex2a(__uint_as_float(sv[j]) * p.scale) : 0.f;
-          a1 += (ok && q >= p.th) ? q : 0.f;
+          const float y = __uint_as_float(sv[j]) * p.scale, E = ex2a(y);
+          mo[0] += ok ? E : 0.f;
+          moments(y, E, (ok && q >= p.th) ? q : 0.f);
         }
       }
     } else {
@@ -302,8 +320,12 @@ contrast_tc_fwd_kernel(const __grid_constant__ CUtensorMap tm_f0, const __grid_c
   };
 
   float a0 = 0.f, a1 = 0.f;
+  float* scratch = statB;                                   // [8 values][4 column groups][128 rows]: idle until a pass B pushes
+  __shared__ float rowres[8 * kT];                          // [8][128]: cluster-wide row results after exchange A
+  bool need_b = false;
 #pragma unroll 1
   for (int phase = 0; phase < 2; ++phase) {
+    if (phase == 1 && !need_b) break;                       // the closed form below covered pass B
     const int u_begin = phase == 0 ? 0 : T, u_end = phase == 0 ? T : U;     // phase 1 is empty when T == 1
     if (warp == 0) {
       if (lane == 0) {
@@ -344,18 +366,10 @@ contrast_tc_fwd_kernel(const __grid_constant__ CUtensorMap tm_f0, const __grid_c
         __syncwarp();
       }
     } else {
-      if (phase == 1) {                                     // full row statistics from every CTA of the cluster
-        float rs = 0.f, qs = 0.f;
-        for (int r = 0; r < CL; ++r) {                      // pushed by every rank before the cluster sync: local reads
-          const float* st = statA + r * kStatRows * kT;
-          rs += (st[0 * kT + r_in] + st[1 * kT + r_in]) + (st[2 * kT + r_in] + st[3 * kT + r_in]);
-          qs += (st[4 * kT + r_in] + st[5 * kT + r_in]) + (st[6 * kT + r_in] + st[7 * kT + r_in]);
-        }
-        inv_rs = 1.0f / rs;
-        inv_qs = 1.0f / qs;
-        if (colq == 0 && crank == 0 && gi < p.rows) { p.stats[gi] = rs; p.stats[p.rows + gi] = qs; }
+      if (phase == 1) {                                     // exact pass B: full row statistics from exchange A
+        inv_rs = 1.0f / rowres[0 * kT + r_in];
+        inv_qs = 1.0f / rowres[1 * kT + r_in];
         a0 = a1 = 0.f;
-        if (threadIdx.x == 64) B200SSL_STAMP(p.dbg, ctaid, 9);                // row statistics assembled
         if (T == 1) {                                       // the only S/Q tile of this CTA is still in TMEM
           tc::tcgen05_fence_after();
           epilogue_tile(1, 0, t0 * kT, a0, a1);
@@ -369,20 +383,67 @@ contrast_tc_fwd_kernel(const __grid_constant__ CUtensorMap tm_f0, const __grid_c
         tc::tcgen05_fence_before();
         if (!(T == 1)) tc::mbar_arrive_warp(&sm.bars[CB_SQ_EMPTY + (u & 1)], lane);
       }
-      // push the per-row partials: pass A to every CTA of the cluster (all need the full row statistics),
-      // pass B only to the CTA that folds this row
       const int RBx = kT / CL;
-      for (int r = 0; r < CL; ++r) {
-        if (phase == 1 && r != r_in / RBx) continue;
-        float* st = (phase == 0 ? statA : statB) + crank * kStatRows * kT;
-        if (CL > 1) st = cluster.map_shared_rank(st, r);
-        st[(0 + colq) * kT + r_in] = a0;
-        st[(4 + colq) * kT + r_in] = a1;
+      if (phase == 0) {
+        // the four column groups of a row meet in shared memory (fixed order), then ONE thread per row pushes the eight
+        // row partials of this CTA to every CTA of the cluster (all of them need the full row statistics)
+#pragma unroll
+        for (int v = 0; v < 8; ++v) scratch[(v * 4 + colq) * kT + r_in] = mo[v];
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * kCtEpiWarps) : "memory");
+        if (colq == 0) {
+          float sum[8];
+#pragma unroll
+          for (int v = 0; v < 7; ++v)
+            sum[v] = (scratch[(v * 4 + 0) * kT + r_in] + scratch[(v * 4 + 1) * kT + r_in]) +
+                     (scratch[(v * 4 + 2) * kT + r_in] + scratch[(v * 4 + 3) * kT + r_in]);
+          sum[7] = fminf(fminf(scratch[(28 + 0) * kT + r_in], scratch[(28 + 1) * kT + r_in]),
+                         fminf(scratch[(28 + 2) * kT + r_in], scratch[(28 + 3) * kT + r_in]));
+          for (int r = 0; r < CL; ++r) {
+            float* st = statA + crank * kStatRows * kT;
+            if (CL > 1) st = cluster.map_shared_rank(st, r);
+#pragma unroll
+            for (int v = 0; v < 8; ++v) st[v * kT + r_in] = sum[v];
+          }
+        }
+      } else {
+        // exact pass B: partials only to the CTA that folds this row
+        for (int r = 0; r < CL; ++r) {
+          if (r != r_in / RBx) continue;
+          float* st = statB + crank * kStatRows * kT;
+          if (CL > 1) st = cluster.map_shared_rank(st, r);
+          st[(0 + colq) * kT + r_in] = a0;
+          st[(4 + colq) * kT + r_in] = a1;
+        }
       }
       if (threadIdx.x == 64) B200SSL_STAMP(p.dbg, ctaid, 3 + 2 * phase);     // pass A (3) / pass B (5) done
     }
     if (CL > 1) cluster.sync(); else __syncthreads();       // partials of this pass visible cluster-wide
     if (threadIdx.x == 0) B200SSL_STAMP(p.dbg, ctaid, 4 + 2 * phase);       // after exchange A (4) / B (6)
+    if (phase == 0) {
+      // Row results from every CTA's partials (rank order; every CTA of the cluster computes the same numbers) and the
+      // decision whether the closed form holds: with z = eps * rs / E,
+      //   log(P + eps) = ln2 * y - log(rs) + log1p(z),   P / (P + eps) = 1 / (1 + z),
+      // and sum_j qm z^k = (eps rs)^k sum_j qm E^-k, so a degree-4 Taylor series of both needs only the moments of pass A.
+      // It holds while the largest z of a row (its smallest E among the pairs of the graph) stays below kZLim; otherwise
+      // (never seen with unit-norm embeddings below ~1e5 rows) the whole cluster runs the exact second pass.
+      constexpr float kZLim = NT == 2 ? 0.03f : 0.25f;      // z^5 / 5: 5e-9 / 2e-4 absolute on a log of magnitude >= 1
+      int bad = 0;
+      if (warp >= 2 && colq == 0) {
+        float v8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 3.0e38f};
+        for (int r = 0; r < CL; ++r) {
+          const float* st = statA + r * kStatRows * kT;
+#pragma unroll
+          for (int v = 0; v < 7; ++v) v8[v] += st[v * kT + r_in];
+          v8[7] = fminf(v8[7], st[7 * kT + r_in]);
+        }
+#pragma unroll
+        for (int v = 0; v < 8; ++v) rowres[v * kT + r_in] = v8[v];
+        if (crank == 0 && gi < p.rows) { p.stats[gi] = v8[0]; p.stats[p.rows + gi] = v8[1]; }
+        bad = (gi < p.rows) && (1e-7f * v8[0] > kZLim * v8[7]);
+      }
+      need_b = __syncthreads_or(bad) != 0;                  // (also orders rowres for every reader below)
+      if (threadIdx.x == 64) B200SSL_STAMP(p.dbg, ctaid, 9);                  // row statistics assembled
+    }
   }
   // ---- loss_i and r_i: cluster rank c folds rows [c*RB, (c+1)*RB) in rank order ----
   const int RB = kT / CL;
@@ -390,10 +451,21 @@ contrast_tc_fwd_kernel(const __grid_constant__ CUtensorMap tm_f0, const __grid_c
   if (threadIdx.x < RB) {
     const int row = crank * RB + threadIdx.x;
     float li = 0.f, rr = 0.f;
-    for (int r = 0; r < CL; ++r) {                          // rank order, local reads
-      const float* st = statB + r * kStatRows * kT;
-      li += (st[0 * kT + row] + st[1 * kT + row]) + (st[2 * kT + row] + st[3 * kT + row]);
-      rr += (st[4 * kT + row] + st[5 * kT + row]) + (st[6 * kT + row] + st[7 * kT + row]);
+    if (need_b) {
+      for (int r = 0; r < CL; ++r) {                        // rank order, local reads
+        const float* st = statB + r * kStatRows * kT;
+        li += (st[0 * kT + row] + st[1 * kT + row]) + (st[2 * kT + row] + st[3 * kT + row]);
+        rr += (st[4 * kT + row] + st[5 * kT + row]) + (st[6 * kT + row] + st[7 * kT + row]);
+      }
+    } else {
+      const float rs = rowres[0 * kT + row], qs = rowres[1 * kT + row], m1 = rowres[2 * kT + row];
+      const float c = 1e-7f * rs, c2 = c * c;
+      const float s1 = c * rowres[3 * kT + row], s2 = c2 * rowres[4 * kT + row], s3 = c2 * c * rowres[5 * kT + row],
+                  s4 = c2 * c2 * rowres[6 * kT + row];
+      const float inv_q = 1.0f / qs;
+      // loss_i = -sum_j qn log(P + eps)   (:209-212);   r_i = sum_j qn P / (P + eps)
+      li = -inv_q * (0.6931471805599453f * m1 - logf(rs) * qs + (s1 - 0.5f * s2 + s3 * (1.0f / 3.0f) - 0.25f * s4));
+      rr = inv_q * (qs - s1 + s2 - s3 + s4);
     }
     const long long g = (long long)own_tile * kT + row;
     if (g < p.rows) {

@@ -709,6 +709,11 @@ def test_contrast_tcgen05_bf16(pkg, rows):
     assert abs(float(scal[2]) - float(ref)) < 2e-3 * max(abs(float(ref)), 1e-2)
     A = torch.exp(f0b.double() @ f1b.double().t() / 0.2)
     assert rel_err(stats[0], A.sum(1)) < 1e-3
+    if rows == 1:
+        # one sample: P = 1, dZ = P (G - r) is identically zero in exact arithmetic.  The forward closes r in the moments of its
+        # first pass, the backward evaluates G per pair: they cancel to rounding, not to the bit
+        assert float(f0.grad.abs().max()) == 0.0 and float(g0.float().abs().max()) < 1e-6 and float(g1.float().abs().max()) < 1e-6
+        return
     assert rel_err(g0.float(), 3.0 * f0.grad) < BF16_TOL and rel_err(g1.float(), 3.0 * f1.grad) < BF16_TOL
 
 
