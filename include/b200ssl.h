@@ -188,14 +188,20 @@ typedef struct b200ssl_bank_shards {
  *   numer[i,c]  = sum_k exp(<f_i, q_k> / temperature) * queue_probs[k,c]
  * feats / queue_* share `dtype`; rowsum/numer are fp32.  No running max (the
  * reference has none; |<f,q>|/tau <= 5 for unit-norm embeddings).
- * Two code paths, chosen by storage type (not a backend switch):
+ * Code paths, chosen by storage type and shape (not a backend switch):
  *   - bf16 bank, dim == 64, classes <= 31, bank_rows % 8 == 0 and queue_probs_t
  *     given (bf16 [32, bank_rows]: rows 0..classes-1 = transposed copy of queue_probs
  *     maintained by b200ssl_bank_enqueue, row `classes` = all ones so that the second
  *     MMA also produces the row sums, remaining rows zero): tcgen05.mma with TMEM
- *     accumulators, operands staged by TMA, split partials folded through thread-block
+ *     accumulators, operands staged by TMA, the exponentials kept in tensor memory as
+ *     the A operand of the second MMA, split partials folded through thread-block
  *     cluster distributed shared memory (csrc/bank_tc.cu);
+ *   - fp32 bank, dim == 64, classes <= 31 (any bank_rows; queue_probs_t unused): a pre-pass
+ *     splits feats, queue_feats and queue_probs into bf16 hi + mid operands inside the
+ *     workspace and the same tensor-core kernel runs three cross-term MMA groups per GEMM
+ *     -- 1e-6 of fp64 on numer / rowsum (the reference's fp32 product: 3e-7);
  *   - otherwise exact-fp32 FFMA tiles (the reference's matrix product is true fp32).
+ * b200ssl_workspace_bytes(rows, classes, bank_rows) covers the operand copies of the second form.
  * rowsum_ld / numer_ld are the row strides of the two outputs in floats (0 = dense: 1 and
  * `classes`); a packed [rows, W] buffer (numer at column 0, rowsum at column `classes`,
  * both strides W) lets the sharded bank reduce-scatter both with one collective.
