@@ -290,10 +290,14 @@ B200SSL_API int b200ssl_bank_enqueue(void* queue_feats, void* queue_probs, void*
  * fwd writes loss to out_scalar[0]; when total_out != NULL it also writes
  * total_out[0] = lambda_u * loss_u[0] + lambda_c * loss (comatch.py:222 without
  * loss_x; loss_u is the device scalar produced by b200ssl_comatch_finalize).
- * Two code paths by storage type: bf16 embeddings with dim == 64, classes <= 32 and
+ * Code paths by storage type and shape: bf16 embeddings with dim == 64, classes <= 32 and
  * probs_hl given run on tcgen05/TMEM/TMA (csrc/contrast_tc.cu, S = F0 F1^T and the
  * hi/lo-split Q = probs probs^T as MMAs, dZ staged through swizzled shared memory for the
- * two gradient GEMMs); everything else uses exact-fp32 FFMA tiles (csrc/contrast.cu).
+ * two gradient GEMMs; the forward is ONE pass over the S/Q tiles: its second pass is closed
+ * in per-row moments); fp32 embeddings with dim == 64, classes <= 32 run the
+ * same kernels on bf16 hi / mid / lo operands split into the workspace by a pre-pass (probs_hl
+ * unused; pairs of the pseudo-label graph take Q from the fp32 probabilities; 1e-5 parity);
+ * everything else uses exact-fp32 FFMA tiles (csrc/contrast.cu).
  * fwd also stores the row statistics (rowsum, qsum, r) into
  * stats f32[3*rows]; bwd consumes them and writes grad_f0 / grad_f1 scaled by
  * (*upstream) * factor (upstream: device scalar from autograd, NULL => 1; factor:
