@@ -21,6 +21,10 @@ python tools/k3_f32.py > $O/${R}_k3_fp32_storage_tc.jsonl 2>&1
 B200SSL_K3_F32_SIMT=1 python tools/k3_f32.py --sizes 448x2560,448x65536,3584x32768 > $O/${R}_k3_fp32_storage_ffma.jsonl 2>&1
 python tools/opt_bench.py > $O/${R}_opt_bench.json 2>&1
 python tools/sweep.py --cpu-budget 1.0 > $O/${R}_sweep_cfg5.jsonl 2> $O/${R}_sweep_cfg5.err
+for b in tmem_bench mma_bench; do          # the two micro-benchmarks are plain nvcc programs (binaries are not tracked)
+  [ -x tools/micro/$b ] || nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -Iendoscopy-image-classification_b200/csrc -Iinclude \
+      -o tools/micro/$b tools/micro/$b.cu
+done
 tools/micro/tmem_bench > $O/${R}_micro_tmem_mufu_sts.jsonl 2>&1
 tools/micro/mma_bench > $O/${R}_micro_mma_issue.jsonl 2>&1
 # ---- ncu: launch list of the bench command, then one full capture per hot kernel -------------------------------------
